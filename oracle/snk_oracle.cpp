@@ -1,0 +1,189 @@
+// oracle/snk_oracle.cpp — TEST INFRASTRUCTURE (CPU oracle). Not part of the product.
+//
+// C entry points over the CPU restatement (snk_scene.h, snk_gbuffer.h,
+// snk_raygen.h) so that tests/, __graft_entry__.smoke() and bench.py's
+// cpu_baseline / --impl reference legs can drive it through ctypes. Nothing in
+// snake-vk_b200/ may link, import or execute this library.
+// PARITY UNPINNED: the reference (orangefrog45/Snake-VK) has no tests, golden
+// vectors or runnable headless path for this pass; the only
+// external anchor is glm (vendored under /root/reference/Core/extern/glm), used by
+// oracle/_ref to check the matrix helpers.
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+
+#include "snk_raygen.h"
+
+using namespace snkor;
+
+extern "C" {
+
+#define ORACLE_API __attribute__((visibility("default")))
+
+ORACLE_API void* snkor_scene_create(const float* positions, const float* normals, const float* uvs, uint32_t num_vertices,
+                                    const uint32_t* indices, uint32_t num_indices, const InstanceData* instances,
+                                    uint32_t num_instances, const float* transforms, const float* prev_transforms,
+                                    uint32_t num_transforms, const Material* materials, uint32_t num_materials,
+                                    const void* light_data, size_t light_bytes, const uint32_t* emissive_idx,
+                                    uint32_t num_emissive) {
+  auto* sc = new Scene();
+  sc->positions.assign(positions, positions + 3 * (size_t)num_vertices);
+  if (normals) sc->normals.assign(normals, normals + 3 * (size_t)num_vertices);
+  else sc->normals.assign(3 * (size_t)num_vertices, 0.0f);
+  if (uvs) sc->uvs.assign(uvs, uvs + 2 * (size_t)num_vertices);
+  sc->indices.assign(indices, indices + num_indices);
+  sc->instances.assign(instances, instances + num_instances);
+  sc->transforms.resize(num_transforms);
+  sc->prev_transforms.resize(num_transforms);
+  memcpy(sc->transforms.data(), transforms, sizeof(mat4) * num_transforms);
+  memcpy(sc->prev_transforms.data(), prev_transforms ? prev_transforms : transforms, sizeof(mat4) * num_transforms);
+  sc->materials.assign(materials, materials + num_materials);
+  memset(&sc->lights, 0, sizeof(LightData));
+  memcpy(&sc->lights, light_data, light_bytes < sizeof(LightData) ? light_bytes : sizeof(LightData));
+  sc->emissive_idx.assign(emissive_idx, emissive_idx + num_emissive);
+  sc->finalize();
+  return sc;
+}
+ORACLE_API void snkor_scene_destroy(void* s) { delete (Scene*)s; }
+
+// flags: bit0 = any-hit, bit1 = brute force (no BVH)
+ORACLE_API void snkor_trace(void* s, const Ray* rays, uint64_t n, uint32_t flags, Hit* hits, int threads) {
+  const Scene& sc = *(Scene*)s;
+  const bool any = flags & 1u, brute = flags & 2u;
+  if (threads < 1) threads = 1;
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; ++t)
+    pool.emplace_back([&, t]() {
+      for (uint64_t i = t; i < n; i += threads) hits[i] = brute ? sc.trace_brute(rays[i], any) : sc.trace(rays[i], any);
+    });
+  for (auto& th : pool) th.join();
+}
+
+// ---- frame object -------------------------------------------------------------------
+ORACLE_API void* snkor_frame_create(void* scene, uint32_t w, uint32_t h) {
+  auto* f = new Frame();
+  f->sc = (Scene*)scene;
+  f->resize(w, h);
+  return f;
+}
+ORACLE_API void snkor_frame_destroy(void* f) { delete (Frame*)f; }
+ORACLE_API void snkor_frame_set(void* fp, const CommonUBO* cur, const CommonUBO* prev, const RtSettings* st) {
+  Frame& f = *(Frame*)fp;
+  f.ubo = *cur; f.prev_ubo = *prev;
+  if (st) f.settings = *st;
+}
+ORACLE_API void snkor_frame_gbuffer(void* fp, float jx, float jy, uint32_t y0, uint32_t y1, int threads) {
+  Frame& f = *(Frame*)fp;
+  if (y1 == 0) y1 = f.g.h;
+  fill_gbuffer(*f.sc, f.ubo, f.prev_ubo, jx, jy, f.g, y0, y1, threads);
+}
+ORACLE_API void snkor_frame_render(void* fp, uint32_t y0, uint32_t y1, int threads) {
+  Frame& f = *(Frame*)fp;
+  if (y1 == 0) y1 = f.g.h;
+  render_reference(f, y0, y1, threads);
+}
+// what: same numbering as SNKPT_AUX_* (include/snkpt.h)
+ORACLE_API int snkor_frame_read(void* fp, uint32_t what, void* dst, size_t bytes) {
+  Frame& f = *(Frame*)fp;
+  const size_t n = (size_t)f.g.w * f.g.h;
+  const void* src = nullptr; size_t sz = 0;
+  switch (what) {
+    case 0: src = f.g.prim.data(); sz = 4 * n; break;
+    case 1: src = f.g.inst.data(); sz = 4 * n; break;
+    case 2: src = f.g.depth.data(); sz = 4 * n; break;
+    case 3: src = f.g.normal.data(); sz = 8 * n; break;
+    case 4: src = f.g.albedo.data(); sz = 4 * n; break;
+    case 5: src = f.g.rma.data(); sz = 8 * n; break;
+    case 6: src = f.g.motion.data(); sz = 4 * n; break;
+    case 7: src = f.g.flags.data(); sz = 2 * n; break;
+    case 8: src = f.g.prev_normal.data(); sz = 8 * n; break;
+    case 9: src = f.g.prev_depth.data(); sz = 4 * n; break;
+    case 10: src = f.reservoirs.data(); sz = 48 * n; break;
+    case 11: src = f.reservoirs.data() + n; sz = 48 * n; break;
+    case 14: src = f.g.hit_t.data(); sz = 4 * n; break;
+    case 15: src = f.g.bary.data(); sz = 8 * n; break;
+    case 16: src = f.out_rgba.data(); sz = 16 * n; break;
+    case 18: src = f.direct_rgba.data(); sz = 16 * n; break;
+    default: return -1;
+  }
+  if (bytes < sz) return -1;
+  memcpy(dst, src, sz);
+  return 0;
+}
+ORACLE_API int snkor_frame_write_reservoirs(void* fp, uint32_t half, const PixelReservoir* src, uint32_t first, uint32_t count) {
+  Frame& f = *(Frame*)fp;
+  const size_t n = (size_t)f.g.w * f.g.h;
+  if (half > 1 || (size_t)first + count > n) return -1;
+  memcpy(f.reservoirs.data() + half * n + first, src, sizeof(PixelReservoir) * count);
+  return 0;
+}
+ORACLE_API void snkor_frame_ray_counts(void* fp, uint64_t* closest, uint64_t* any, int reset) {
+  Frame& f = *(Frame*)fp;
+  *closest = f.rays_closest.load(); *any = f.rays_any.load();
+  if (reset) { f.rays_closest = 0; f.rays_any = 0; }
+}
+ORACLE_API void snkor_inv_view_proj(const CommonUBO* u, float* out16) {
+  mat4 m = inv_view_proj(*u);
+  memcpy(out16, m.m, 64);
+}
+
+// ---- known-answer helpers ---------------------------------------------------------------
+ORACLE_API uint32_t snkor_hash(uint32_t x) { return hash1(x); }
+ORACLE_API float snkor_random(float x) { return random_f(x); }
+ORACLE_API float snkor_gold_noise(float px, float py, float seed) { return gold_noise_f(px, py, seed); }
+ORACLE_API uint16_t snkor_f32_to_f16(float f) { return f32_to_f16(f); }
+ORACLE_API float snkor_f16_to_f32(uint16_t h) { return f16_to_f32(h); }
+ORACLE_API int snkor_f32_to_snorm8(float f) { return f32_to_snorm8(f); }
+// out: fresnel(3) ggx(1) smith(1) cook_torrance(3)
+ORACLE_API void snkor_brdf_eval(const float* n, const float* v, const float* l, const float* f0, float roughness, float metallic,
+                                float* out8) {
+  const vec3 N = v3(n[0], n[1], n[2]), V = v3(v[0], v[1], v[2]), Lv = v3(l[0], l[1], l[2]), F0 = v3(f0[0], f0[1], f0[2]);
+  const vec3 H = normalize(V + Lv);
+  const vec3 f = fresnel_schlick(gmax(dot(H, V), 0.0f), F0);
+  out8[0] = f.x; out8[1] = f.y; out8[2] = f.z;
+  out8[3] = distribution_ggx(H, N, roughness);
+  out8[4] = geometry_smith(V, Lv, N, roughness);
+  // light position = surface (origin) + l
+  const vec3 ct = cook_torrance_brdf(Lv, v3(0.0f), V, F0, N, roughness, metallic);
+  out8[5] = ct.x; out8[6] = ct.y; out8[7] = ct.z;
+}
+ORACLE_API void snkor_calc_pointlight(const Pointlight* pl, const float* v, const float* f0, const float* wp, const float* n, float roughness,
+                                      float metallic, const float* albedo, float* out3) {
+  vec3 r = calc_pointlight(*pl, v3(v[0], v[1], v[2]), v3(f0[0], f0[1], f0[2]), v3(wp[0], wp[1], wp[2]), v3(n[0], n[1], n[2]), roughness,
+                           metallic, v3(albedo[0], albedo[1], albedo[2]));
+  out3[0] = r.x; out3[1] = r.y; out3[2] = r.z;
+}
+ORACLE_API void snkor_calc_dirlight(const void* light_data, const float* v, const float* f0, const float* n, float roughness, float metallic,
+                                    const float* albedo, float* out3) {
+  LightData L; memset(&L, 0, sizeof(L)); memcpy(&L, light_data, 112);
+  vec3 r = calc_directional_light(L, v3(v[0], v[1], v[2]), v3(f0[0], f0[1], f0[2]), v3(n[0], n[1], n[2]), roughness, metallic,
+                                  v3(albedo[0], albedo[1], albedo[2]));
+  out3[0] = r.x; out3[1] = r.y; out3[2] = r.z;
+}
+// scripted WRS: runs update_pointlight_reservoir over `n` (idx, weight) candidates with the
+// uniform numbers in `u` (RayGen.rgen:215-226 with the RNG injected), returns final state
+ORACLE_API void snkor_wrs_pointlight_script(void* fp, const uint32_t* idx, const float* weight, const float* u, uint32_t n,
+                                            PixelReservoir* out) {
+  Frame& f = *(Frame*)fp;
+  RngScript s{u, n, 0};
+  Invocation inv(f, 1, 1, &s);
+  PixelReservoir r; Invocation::init_pixel_reservoir(r);
+  for (uint32_t i = 0; i < n; ++i) inv.update_pointlight_reservoir(r, idx[i], weight[i], 0.0f);
+  *out = r;
+}
+// run one pixel of one pass with scripted random numbers (KAT for the temporal / spatial state machines)
+ORACLE_API void snkor_pixel_scripted(void* fp, uint32_t x, uint32_t y, uint32_t pass, const float* u, uint32_t n) {
+  Frame& f = *(Frame*)fp;
+  f.ivp = inv_view_proj(f.ubo);
+  RngScript s{u, n, 0};
+  Invocation inv(f, x, y, n ? &s : nullptr);
+  inv.main(pass);
+  f.rays_closest += inv.n_closest; f.rays_any += inv.n_any;
+}
+ORACLE_API void snkor_sizes(uint32_t* out8) {
+  out8[0] = sizeof(InstanceData); out8[1] = sizeof(Material); out8[2] = sizeof(LightData); out8[3] = sizeof(CommonUBO);
+  out8[4] = sizeof(PixelReservoir); out8[5] = sizeof(Ray); out8[6] = sizeof(Hit); out8[7] = sizeof(RtSettings);
+}
+ORACLE_API int snkor_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
+
+}  // extern "C"

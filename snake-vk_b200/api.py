@@ -1,0 +1,294 @@
+"""ctypes host mirror of the C ABI (include/snkpt.h).
+
+`PathTracer` is a 1:1 wrapper of the entry points; `RT` mirrors the reference's
+class (Core/headers/rendering/Raytracing.h:11-31: Init / RecordRenderCmdBuf /
+RtSettings) on top of it so the parity tests read like engine code.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import scenes
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class SnkError(RuntimeError):
+    pass
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libsnkpt.so")
+
+
+def load_library() -> C.CDLL:
+    """dlopen libsnkpt.so; raises (never falls back) when it is missing."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise SnkError(f"{path} not built — run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(or `make -C snake-vk_b200`); there is no CPU fallback")
+    L = C.CDLL(path)
+    vp, u32, u64, sz, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_size_t, C.c_int
+    sig = {
+        "snkpt_create": [vp, vp], "snkpt_default_settings": [vp], "snkpt_resize": [vp, u32, u32],
+        "snkpt_set_rows": [vp, u32, u32], "snkpt_reset_history": [vp],
+        "snkpt_upload_mesh": [vp, vp, vp, vp, vp, u32, vp, u32, vp, u32, vp, vp],
+        "snkpt_update_positions": [vp, vp, vp, u32], "snkpt_refit_blas": [vp, u32, vp], "snkpt_rebuild_blas": [vp, u32, vp],
+        "snkpt_set_materials": [vp, vp, u32, u32], "snkpt_set_lights": [vp, vp, sz],
+        "snkpt_set_transforms": [vp, vp, vp, u32, u32], "snkpt_set_instances": [vp, vp, vp, u32, vp, u32],
+        "snkpt_build_tlas": [vp, vp], "snkpt_set_frame": [vp, vp, vp], "snkpt_trace_primary": [vp, vp, vp],
+        "snkpt_render": [vp, vp, vp], "snkpt_accumulate": [vp, i32, vp], "snkpt_read_output": [vp, vp, u32],
+        "snkpt_read_aux": [vp, u32, vp, sz], "snkpt_aux_size": [vp, u32, vp],
+        "snkpt_write_reservoirs": [vp, u32, vp, u32, u32], "snkpt_device_ptr": [vp, u32, vp, vp],
+        "snkpt_get_stats": [vp, vp], "snkpt_synchronize": [vp], "snkpt_trace_rays": [vp, vp, u64, u32, vp, vp],
+        "snkpt_count_work": [vp, vp, vp, u64, u32, vp, vp],
+    }
+    for name, args in sig.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    L.snkpt_default_settings.restype = None
+    L.snkpt_destroy.argtypes = [vp]
+    L.snkpt_destroy.restype = None
+    L.snkpt_last_error.argtypes = [vp]
+    L.snkpt_last_error.restype = C.c_char_p
+    _LIB = L
+    return L
+
+
+EXPORTS = ["snkpt_create", "snkpt_destroy", "snkpt_last_error", "snkpt_default_settings", "snkpt_resize", "snkpt_set_rows",
+           "snkpt_reset_history", "snkpt_upload_mesh", "snkpt_update_positions", "snkpt_refit_blas", "snkpt_rebuild_blas",
+           "snkpt_set_materials", "snkpt_set_lights", "snkpt_set_transforms", "snkpt_set_instances", "snkpt_build_tlas",
+           "snkpt_set_frame", "snkpt_trace_primary", "snkpt_render", "snkpt_accumulate", "snkpt_read_output", "snkpt_read_aux",
+           "snkpt_aux_size", "snkpt_write_reservoirs", "snkpt_device_ptr", "snkpt_get_stats", "snkpt_synchronize",
+           "snkpt_trace_rays", "snkpt_count_work"]
+
+CONFIG_DTYPE = np.dtype([("width", "<u4"), ("height", "<u4"), ("device", "<i4"), ("max_instances", "<u4"),
+                         ("max_transforms", "<u4"), ("max_materials", "<u4"), ("row_begin", "<u4"), ("row_end", "<u4"),
+                         ("reserved", "<u4", (4,))])
+SETTINGS_DTYPE = np.dtype([("num_temporal", "<i4"), ("num_spatial", "<i4"), ("mode", "<u4"), ("ris_iters", "<u4"),
+                           ("m_cap", "<u4"), ("neighbour_radius", "<f4"), ("normal_threshold", "<f4"),
+                           ("max_bounces", "<u4"), ("spp", "<u4"), ("flags", "<u4"), ("reserved", "<u4", (6,))])
+STATS_DTYPE = np.dtype([("rays_primary", "<u8"), ("rays_shadow", "<u8"), ("rays_secondary", "<u8"), ("kernel_launches", "<u8"),
+                        ("blas_nodes", "<u8"), ("blas_tris", "<u8"), ("tlas_nodes", "<u8"), ("ms_primary", "<f4"),
+                        ("ms_restir1", "<f4"), ("ms_restir2", "<f4"), ("ms_bounce", "<f4"), ("ms_total", "<f4"),
+                        ("ms_build_last", "<f4"), ("reserved", "<u4", (8,))])
+SUBMESH_DTYPE = np.dtype([("num_indices", "<u4"), ("num_vertices", "<u4"), ("base_vertex", "<u4"), ("base_index", "<u4"),
+                          ("material_index", "<u4")])
+MESH_ENTRY_DTYPE = np.dtype([("data_start_indices_idx", "<u4"), ("data_start_vertex_idx", "<u4"), ("num_submeshes", "<u4"),
+                             ("blas_id", "<u4", (64,))])
+BLAS_INFO_DTYPE = np.dtype([("node_root", "<u4"), ("node_count", "<u4"), ("tri_base", "<u4"), ("tri_count", "<u4"),
+                            ("bounds_lo", "<f4", (3,)), ("bounds_hi", "<f4", (3,))])
+assert SETTINGS_DTYPE.itemsize == 64 and CONFIG_DTYPE.itemsize == 48 and SUBMESH_DTYPE.itemsize == 20
+
+MODE_REFERENCE, MODE_NORTHSTAR = 0, 1
+RAY_CLOSEST, RAY_ANY, RAY_DEVICE_PTRS, RAY_SORT_OCTANT = 0, 1, 2, 4
+RT_NO_RESTIR, RT_NO_BOUNCE, RT_SORT_RAYS = 1, 2, 4
+
+AUX = dict(prim=(0, np.uint32, 1), inst=(1, np.uint32, 1), depth=(2, np.float32, 1), normal=(3, np.float16, 4),
+           albedo=(4, np.int8, 4), rma=(5, np.float16, 4), motion=(6, np.float16, 2), flags=(7, np.uint16, 1),
+           prev_normal=(8, np.float16, 4), prev_depth=(9, np.float32, 1), reservoirs_final=(10, scenes.RESERVOIR_DTYPE, 1),
+           reservoirs_temporal=(11, scenes.RESERVOIR_DTYPE, 1), hit_t=(14, np.float32, 1), bary=(15, np.float32, 2),
+           radiance=(16, np.float32, 4), accum=(17, np.float32, 4), direct=(18, np.float32, 4))
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def default_settings(**kw) -> np.ndarray:
+    s = np.zeros((), SETTINGS_DTYPE)
+    load_library().snkpt_default_settings(_p(s))
+    for k, v in kw.items():
+        s[k] = v
+    return s
+
+
+class PathTracer:
+    """One context per GPU (include/snkpt.h)."""
+
+    def __init__(self, width: int, height: int, device: int = 0, rows=(0, 0), **caps):
+        self.L = load_library()
+        cfg = np.zeros((), CONFIG_DTYPE)
+        cfg["width"], cfg["height"], cfg["device"] = width, height, device
+        cfg["row_begin"], cfg["row_end"] = rows
+        for k, v in caps.items():
+            cfg[k] = v
+        h = C.c_void_p()
+        rc = self.L.snkpt_create(_p(cfg), C.byref(h))
+        if rc != 0:
+            raise SnkError(f"snkpt_create failed ({rc}): {self.L.snkpt_last_error(None).decode()}")
+        self.h = h
+        self.width, self.height = width, height
+        self.rows = (rows[0], rows[1] or height)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.snkpt_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _ck(self, rc: int, what: str):
+        if rc != 0:
+            raise SnkError(f"{what} failed ({rc}): {self.L.snkpt_last_error(self.h).decode()}")
+
+    # ---- scene
+    def upload_mesh(self, mesh: "scenes.Mesh", stream=None) -> np.ndarray:
+        entry = np.zeros((), MESH_ENTRY_DTYPE)
+        sub = np.ascontiguousarray(mesh.submeshes.astype(np.uint32))
+        self._ck(self.L.snkpt_upload_mesh(self.h, _p(mesh.positions), _p(mesh.normals), _p(mesh.tangents), _p(mesh.uvs),
+                                          mesh.positions.shape[0], _p(mesh.indices), mesh.indices.size, _p(sub),
+                                          sub.shape[0], _p(entry), stream), "snkpt_upload_mesh")
+        return entry
+
+    def set_materials(self, mats: np.ndarray, first=0):
+        mats = np.ascontiguousarray(mats)
+        self._ck(self.L.snkpt_set_materials(self.h, _p(mats), first, mats.shape[0]), "snkpt_set_materials")
+
+    def set_lights(self, blob: bytes):
+        buf = np.frombuffer(blob, np.uint8).copy()
+        self._ck(self.L.snkpt_set_lights(self.h, _p(buf), buf.size), "snkpt_set_lights")
+
+    def set_transforms(self, cur: np.ndarray, prev: np.ndarray | None = None, first=0):
+        cur = np.ascontiguousarray(cur, np.float32).reshape(-1, 16)
+        prev = None if prev is None else np.ascontiguousarray(prev, np.float32).reshape(-1, 16)
+        self._ck(self.L.snkpt_set_transforms(self.h, _p(cur), _p(prev), first, cur.shape[0]), "snkpt_set_transforms")
+
+    def set_instances(self, instances: np.ndarray, blas_of_instance: np.ndarray, emissive_idx: np.ndarray):
+        instances = np.ascontiguousarray(instances, np.uint32).reshape(-1, 5)
+        blas_of_instance = np.ascontiguousarray(blas_of_instance, np.uint32)
+        emissive_idx = np.ascontiguousarray(emissive_idx, np.uint32)
+        self._ck(self.L.snkpt_set_instances(self.h, _p(instances), _p(blas_of_instance), instances.shape[0],
+                                            _p(emissive_idx) if emissive_idx.size else None, emissive_idx.size),
+                 "snkpt_set_instances")
+
+    def build_tlas(self, stream=None):
+        self._ck(self.L.snkpt_build_tlas(self.h, stream), "snkpt_build_tlas")
+
+    def upload_scene(self, scene: "scenes.Scene") -> dict:
+        """What MeshBufferManager + the scene buffer systems do at load / FrameStart."""
+        flat = scene.flatten()
+        for m, (i0, v0, b0) in zip(scene.meshes, flat["mesh_entries"]):
+            e = self.upload_mesh(m)
+            assert (int(e["data_start_indices_idx"]), int(e["data_start_vertex_idx"]), int(e["blas_id"][0])) == (i0, v0, b0)
+        self.set_materials(flat["materials"])
+        self.set_lights(flat["lights"])
+        self.set_transforms(flat["transforms"], flat["prev_transforms"])
+        self.set_instances(flat["instances"], flat["blas_of_instance"], flat["emissive_idx"])
+        self.build_tlas()
+        return flat
+
+    # ---- frame
+    def set_frame(self, cur: np.ndarray, prev: np.ndarray | None = None):
+        self._cur = np.ascontiguousarray(cur)
+        self._prev = self._cur if prev is None else np.ascontiguousarray(prev)
+        self._ck(self.L.snkpt_set_frame(self.h, _p(self._cur), _p(self._prev)), "snkpt_set_frame")
+
+    def trace_primary(self, jitter=None, stream=None):
+        j = None if jitter is None else np.asarray(jitter, np.float32)
+        self._ck(self.L.snkpt_trace_primary(self.h, _p(j), stream), "snkpt_trace_primary")
+
+    def render(self, settings: np.ndarray | None = None, stream=None):
+        s = default_settings() if settings is None else np.ascontiguousarray(settings)
+        self._ck(self.L.snkpt_render(self.h, _p(s), stream), "snkpt_render")
+
+    def accumulate(self, reset=False, stream=None):
+        self._ck(self.L.snkpt_accumulate(self.h, int(reset), stream), "snkpt_accumulate")
+
+    def synchronize(self):
+        self._ck(self.L.snkpt_synchronize(self.h), "snkpt_synchronize")
+
+    def reset_history(self):
+        self._ck(self.L.snkpt_reset_history(self.h), "snkpt_reset_history")
+
+    # ---- readback
+    def read_output(self, fmt="f16", out: np.ndarray | None = None) -> np.ndarray:
+        nrows = self.rows[1] - self.rows[0]
+        dt = np.float16 if fmt == "f16" else np.float32
+        if out is None:
+            out = np.empty((nrows, self.width, 4), dt)
+        self._ck(self.L.snkpt_read_output(self.h, _p(out), 0 if fmt == "f16" else 1), "snkpt_read_output")
+        return out
+
+    def read_aux(self, name: str) -> np.ndarray:
+        what, dt, ch = AUX[name]
+        out = np.zeros((self.height, self.width, ch) if ch > 1 else (self.height, self.width), dt)
+        self._ck(self.L.snkpt_read_aux(self.h, what, _p(out), out.nbytes), f"snkpt_read_aux({name})")
+        return out
+
+    def read_raw(self, what: int, dtype) -> np.ndarray:
+        n = C.c_size_t()
+        self._ck(self.L.snkpt_aux_size(self.h, what, C.byref(n)), "snkpt_aux_size")
+        out = np.zeros(n.value // np.dtype(dtype).itemsize, dtype)
+        if n.value:
+            self._ck(self.L.snkpt_read_aux(self.h, what, _p(out), out.nbytes), "snkpt_read_aux")
+        return out
+
+    def blas_table(self) -> np.ndarray:
+        return self.read_raw(20, BLAS_INFO_DTYPE)
+
+    def write_reservoirs(self, half: int, res: np.ndarray, first=0):
+        res = np.ascontiguousarray(res.reshape(-1))
+        self._ck(self.L.snkpt_write_reservoirs(self.h, half, _p(res), first, res.size), "snkpt_write_reservoirs")
+
+    def device_ptr(self, what: int):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._ck(self.L.snkpt_device_ptr(self.h, what, C.byref(p), C.byref(n)), "snkpt_device_ptr")
+        return p.value, n.value
+
+    def stats(self) -> np.ndarray:
+        s = np.zeros((), STATS_DTYPE)
+        self._ck(self.L.snkpt_get_stats(self.h, _p(s)), "snkpt_get_stats")
+        return s
+
+    # ---- ray queries
+    def trace_rays(self, rays: np.ndarray, any_hit=False, flags=0) -> np.ndarray:
+        rays = np.ascontiguousarray(rays)
+        assert rays.dtype == scenes.RAY_DTYPE
+        hits = np.zeros(rays.shape[0], scenes.HIT_DTYPE)
+        self._ck(self.L.snkpt_trace_rays(self.h, _p(rays), rays.shape[0], (RAY_ANY if any_hit else 0) | flags, _p(hits), None),
+                 "snkpt_trace_rays")
+        return hits
+
+    def count_work(self, rays: np.ndarray, hits: np.ndarray, any_hit=False) -> np.ndarray:
+        rays, hits = np.ascontiguousarray(rays), np.ascontiguousarray(hits)
+        out = np.zeros((rays.shape[0], 3), np.uint32)
+        self._ck(self.L.snkpt_count_work(self.h, _p(rays), _p(hits), rays.shape[0], RAY_ANY if any_hit else 0, _p(out), None),
+                 "snkpt_count_work")
+        return out
+
+
+class RT:
+    """Mirror of `SNAKE::RT` (Core/headers/rendering/Raytracing.h:11-31).
+
+    Init(scene, output_size)             ~ RT::Init + EditorLayer::InitGBuffer
+    RecordRenderCmdBuf(ubo, prev, st)    ~ GBufferPass + RT::RecordRenderCmdBuf for one frame
+    """
+
+    class RtSettings:
+        def __init__(self, num_temporal_resamples=1, num_spatial_resamples=3):
+            self.num_temporal_resamples = num_temporal_resamples
+            self.num_spatial_resamples = num_spatial_resamples
+
+    def __init__(self):
+        self.pt: PathTracer | None = None
+
+    def Init(self, scene: "scenes.Scene", device: int = 0, rows=(0, 0)):
+        self.pt = PathTracer(scene.width, scene.height, device, rows)
+        self.flat = self.pt.upload_scene(scene)
+        return self
+
+    def RecordRenderCmdBuf(self, ubo, prev_ubo, settings: "RT.RtSettings | None" = None, mode=MODE_REFERENCE, **extra):
+        st = settings or RT.RtSettings()
+        s = default_settings(num_temporal=st.num_temporal_resamples, num_spatial=st.num_spatial_resamples, mode=mode, **extra)
+        self.pt.set_frame(ubo, prev_ubo)
+        self.pt.trace_primary()
+        self.pt.render(s)

@@ -1,0 +1,756 @@
+// api.cu — implementation of the C ABI declared in include/snkpt.h.
+//
+// Host side of the pass: owns the device mirrors of the reference's buffers,
+// builds BLAS / TLAS, derives the per-transform matrices the shaders recompute
+// per use (inverse, normal matrix, determinant: RayClosestHit.rchit:111,
+// RayGen.rgen:251,:268,:333 — hoisted here in float64 and rounded once), and
+// enqueues the kernels. No CPU compute path exists: every entry point that
+// produces results launches CUDA kernels on the context's device.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "kernels.h"
+
+using namespace snk;
+
+static thread_local std::string g_create_error;
+
+#define CK(call)                                                                         \
+  do {                                                                                   \
+    cudaError_t e_ = (call);                                                             \
+    if (e_ != cudaSuccess) {                                                             \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                    \
+      return SNKPT_E_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+#define REQUIRE(cond, code, msg)                                                         \
+  do {                                                                                   \
+    if (!(cond)) { ctx->err = msg; return code; }                                        \
+  } while (0)
+
+// ---- float64 matrix helpers (host) -----------------------------------------------------
+static bool invert4(const double* a_cm, double* inv_cm) {
+  // cofactor expansion, column-major in / out
+  const double* m = a_cm;
+  double inv[16];
+  inv[0] = m[5] * m[10] * m[15] - m[5] * m[11] * m[14] - m[9] * m[6] * m[15] + m[9] * m[7] * m[14] + m[13] * m[6] * m[11] - m[13] * m[7] * m[10];
+  inv[4] = -m[4] * m[10] * m[15] + m[4] * m[11] * m[14] + m[8] * m[6] * m[15] - m[8] * m[7] * m[14] - m[12] * m[6] * m[11] + m[12] * m[7] * m[10];
+  inv[8] = m[4] * m[9] * m[15] - m[4] * m[11] * m[13] - m[8] * m[5] * m[15] + m[8] * m[7] * m[13] + m[12] * m[5] * m[11] - m[12] * m[7] * m[9];
+  inv[12] = -m[4] * m[9] * m[14] + m[4] * m[10] * m[13] + m[8] * m[5] * m[14] - m[8] * m[6] * m[13] - m[12] * m[5] * m[10] + m[12] * m[6] * m[9];
+  inv[1] = -m[1] * m[10] * m[15] + m[1] * m[11] * m[14] + m[9] * m[2] * m[15] - m[9] * m[3] * m[14] - m[13] * m[2] * m[11] + m[13] * m[3] * m[10];
+  inv[5] = m[0] * m[10] * m[15] - m[0] * m[11] * m[14] - m[8] * m[2] * m[15] + m[8] * m[3] * m[14] + m[12] * m[2] * m[11] - m[12] * m[3] * m[10];
+  inv[9] = -m[0] * m[9] * m[15] + m[0] * m[11] * m[13] + m[8] * m[1] * m[15] - m[8] * m[3] * m[13] - m[12] * m[1] * m[11] + m[12] * m[3] * m[9];
+  inv[13] = m[0] * m[9] * m[14] - m[0] * m[10] * m[13] - m[8] * m[1] * m[14] + m[8] * m[2] * m[13] + m[12] * m[1] * m[10] - m[12] * m[2] * m[9];
+  inv[2] = m[1] * m[6] * m[15] - m[1] * m[7] * m[14] - m[5] * m[2] * m[15] + m[5] * m[3] * m[14] + m[13] * m[2] * m[7] - m[13] * m[3] * m[6];
+  inv[6] = -m[0] * m[6] * m[15] + m[0] * m[7] * m[14] + m[4] * m[2] * m[15] - m[4] * m[3] * m[14] - m[12] * m[2] * m[7] + m[12] * m[3] * m[6];
+  inv[10] = m[0] * m[5] * m[15] - m[0] * m[7] * m[13] - m[4] * m[1] * m[15] + m[4] * m[3] * m[13] + m[12] * m[1] * m[7] - m[12] * m[3] * m[5];
+  inv[14] = -m[0] * m[5] * m[14] + m[0] * m[6] * m[13] + m[4] * m[1] * m[14] - m[4] * m[2] * m[13] - m[12] * m[1] * m[6] + m[12] * m[2] * m[5];
+  inv[3] = -m[1] * m[6] * m[11] + m[1] * m[7] * m[10] + m[5] * m[2] * m[11] - m[5] * m[3] * m[10] - m[9] * m[2] * m[7] + m[9] * m[3] * m[6];
+  inv[7] = m[0] * m[6] * m[11] - m[0] * m[7] * m[10] - m[4] * m[2] * m[11] + m[4] * m[3] * m[10] + m[8] * m[2] * m[7] - m[8] * m[3] * m[6];
+  inv[11] = -m[0] * m[5] * m[11] + m[0] * m[7] * m[9] + m[4] * m[1] * m[11] - m[4] * m[3] * m[9] - m[8] * m[1] * m[7] + m[8] * m[3] * m[5];
+  inv[15] = m[0] * m[5] * m[10] - m[0] * m[6] * m[9] - m[4] * m[1] * m[10] + m[4] * m[2] * m[9] + m[8] * m[1] * m[6] - m[8] * m[2] * m[5];
+  const double det = m[0] * inv[0] + m[1] * inv[4] + m[2] * inv[8] + m[3] * inv[12];
+  if (det == 0.0) return false;
+  const double id = 1.0 / det;
+  for (int i = 0; i < 16; ++i) inv_cm[i] = inv[i] * id;
+  return true;
+}
+
+static void derive_transform(const float* M, float* w2o12, float* nmat9, float* det3) {
+  double a[16], inv[16];
+  for (int i = 0; i < 16; ++i) a[i] = M[i];
+  if (!invert4(a, inv)) for (int i = 0; i < 16; ++i) inv[i] = NAN;
+  // rows of the inverse as 3x4 (row-major): row r = inv[c*4 + r], c = 0..3
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 4; ++c) w2o12[r * 4 + c] = (float)inv[c * 4 + r];
+  const double m00 = M[0], m01 = M[4], m02 = M[8], m10 = M[1], m11 = M[5], m12 = M[9], m20 = M[2], m21 = M[6], m22 = M[10];
+  const double det = m00 * (m11 * m22 - m12 * m21) - m01 * (m10 * m22 - m12 * m20) + m02 * (m10 * m21 - m11 * m20);
+  *det3 = (float)det;
+  const double id = 1.0 / det;
+  // inverse(mat3) entries i[r][c]; normal matrix = transpose → n[r][c] = i[c][r]
+  const double i3[3][3] = {{(m11 * m22 - m12 * m21) * id, (m02 * m21 - m01 * m22) * id, (m01 * m12 - m02 * m11) * id},
+                           {(m12 * m20 - m10 * m22) * id, (m00 * m22 - m02 * m20) * id, (m02 * m10 - m00 * m12) * id},
+                           {(m10 * m21 - m11 * m20) * id, (m01 * m20 - m00 * m21) * id, (m00 * m11 - m01 * m10) * id}};
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) nmat9[r * 3 + c] = (float)i3[c][r];
+}
+
+TraceScene SnkPt::trace_scene() const {
+  TraceScene S;
+  S.tlas_nodes = tlas_nodes.as<uint4>();
+  S.tlas_leaf_ids = tlas_leaf_ids.as<uint32_t>();
+  S.blas_nodes = blas_nodes.as<uint4>();
+  S.tris = blas_tris.as<float4>();
+  S.inst = inst_recs.as<SnkInstRec>();
+  S.tlas_node_count = (tlas_built && tlas_prims) ? 1u : 0u;
+  return S;
+}
+
+SceneDev SnkPt::scene_dev() const {
+  SceneDev D;
+  D.positions = positions.as<float>(); D.normals = normals.as<float>(); D.uvs = uvs.as<float>();
+  D.indices = indices.as<uint32_t>();
+  D.instances = instances.as<SnkInstanceData>();
+  D.transforms = transforms.as<float>(); D.prev_transforms = prev_transforms.as<float>();
+  D.normal_mats = normal_mats.as<float>(); D.det3 = det3.as<float>();
+  D.materials = materials.as<SnkMaterial>();
+  D.lights = lights.as<SnkLightData>();
+  D.emissive_idx = emissive_idx.as<uint32_t>();
+  D.num_emissive = num_emissive; D.num_instances = num_instances;
+  return D;
+}
+
+// ---- per-pixel planes ----------------------------------------------------------------------
+static int alloc_pixels(SnkPt* ctx) {
+  const size_t n = (size_t)ctx->W * ctx->H;
+  const size_t sizes[] = {4, 8, 4, 8, 4, 2, 8, 4, 4, 4, 4, 8, 16, 16, 16, 16, 16, 16, 16, 16, 16, 8};
+  const int count = (int)(sizeof(sizes) / sizeof(sizes[0]));
+  for (int i = 0; i < count; ++i) {
+    ctx->px[i].release();
+    CK(ctx->px[i].reserve(sizes[i] * n, false, ctx->stream));
+    CK(cudaMemsetAsync(ctx->px[i].p, 0, sizes[i] * n, ctx->stream));
+  }
+  PixelPlanes& P = ctx->planes;
+  P.albedo = ctx->px[0].as<char4>(); P.normal = ctx->px[1].as<ushort4>(); P.depth = ctx->px[2].as<float>();
+  P.rma = ctx->px[3].as<ushort4>(); P.motion = ctx->px[4].as<ushort2>(); P.flags = ctx->px[5].as<uint16_t>();
+  P.prev_normal = ctx->px[6].as<ushort4>(); P.prev_depth = ctx->px[7].as<float>();
+  P.prim = ctx->px[8].as<uint32_t>(); P.inst = ctx->px[9].as<uint32_t>(); P.hit_t = ctx->px[10].as<float>();
+  P.bary = ctx->px[11].as<float2>();
+  for (int h = 0; h < 2; ++h) for (int k = 0; k < 3; ++k) P.res[h][k] = ctx->px[12 + h * 3 + k].as<float4>();
+  P.radiance = ctx->px[18].as<float4>(); P.direct = ctx->px[19].as<float4>(); P.accum = ctx->px[20].as<float4>();
+  P.out16 = ctx->px[21].as<ushort4>();
+  // depth planes clear to 1.0 (GBufferPass.cpp:79); prim ids to "sky"; reservoirs to empty
+  std::vector<float> ones(n, 1.0f);
+  CK(cudaMemcpyAsync(P.depth, ones.data(), 4 * n, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(P.prev_depth, ones.data(), 4 * n, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemsetAsync(P.prim, 0xFF, 4 * n, ctx->stream));
+  CK(cudaMemsetAsync(P.inst, 0xFF, 4 * n, ctx->stream));
+  std::vector<SnkPixelReservoir> empty(n);
+  memset(empty.data(), 0, sizeof(SnkPixelReservoir) * n);
+  for (auto& r : empty) { r.pl_idx = r.object_instance_idx = r.triangle_idx = SNKPT_INVALID_INDEX; }
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (uint32_t h = 0; h < 2; ++h) {
+    int rc = snkpt_write_reservoirs(ctx, h, empty.data(), 0, (uint32_t)n);
+    if (rc) return rc;
+  }
+  ctx->history_valid = false;
+  ctx->gbuffer_valid = false;
+  ctx->accum_count = 0;
+  return SNKPT_OK;
+}
+
+extern "C" {
+
+int snkpt_create(const SnkPtConfig* cfg, SnkPt** out) {
+  if (!cfg || !out || cfg->width == 0 || cfg->height == 0) { g_create_error = "snkpt_create: bad config"; return SNKPT_E_INVALID; }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0 || cfg->device < 0 || cfg->device >= ndev) {
+    g_create_error = std::string("snkpt_create: no usable CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "ordinal out of range") +
+                     "); this library has no CPU path";
+    return SNKPT_E_CUDA;
+  }
+  SnkPt* ctx = new (std::nothrow) SnkPt();
+  if (!ctx) return SNKPT_E_NOMEM;
+  ctx->device = cfg->device;
+  e = cudaSetDevice(cfg->device);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  for (int i = 0; i < 8 && e == cudaSuccess; ++i) e = cudaEventCreate(&ctx->ev[i]);
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return SNKPT_E_CUDA; }
+  ctx->W = cfg->width; ctx->H = cfg->height;
+  ctx->row0 = cfg->row_begin; ctx->row1 = cfg->row_end ? cfg->row_end : cfg->height;
+  if (ctx->row1 > ctx->H || ctx->row0 >= ctx->row1) { g_create_error = "snkpt_create: bad row band"; delete ctx; return SNKPT_E_INVALID; }
+  if (cfg->max_instances) ctx->max_instances = cfg->max_instances;
+  if (cfg->max_transforms) ctx->max_transforms = cfg->max_transforms;
+  if (cfg->max_materials) ctx->max_materials = cfg->max_materials;
+  int rc = alloc_pixels(ctx);
+  if (rc == SNKPT_OK) {
+    // zero-filled light block: no lights until snkpt_set_lights
+    cudaError_t e2 = ctx->lights.reserve(sizeof(SnkLightData), false, ctx->stream);
+    if (e2 == cudaSuccess) e2 = cudaMemsetAsync(ctx->lights.p, 0, sizeof(SnkLightData), ctx->stream);
+    if (e2 == cudaSuccess) e2 = ctx->materials.reserve(sizeof(SnkMaterial) * ctx->max_materials, false, ctx->stream);
+    if (e2 == cudaSuccess) e2 = cudaMemsetAsync(ctx->materials.p, 0, sizeof(SnkMaterial) * ctx->max_materials, ctx->stream);
+    if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(ctx->stream);
+    if (e2 != cudaSuccess) { ctx->err = cudaGetErrorString(e2); rc = SNKPT_E_CUDA; }
+  }
+  if (rc != SNKPT_OK) { g_create_error = ctx->err; snkpt_destroy(ctx); return rc; }
+  *out = ctx;
+  return SNKPT_OK;
+}
+
+void snkpt_destroy(SnkPt* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  DevBuf* bufs[] = {&ctx->positions, &ctx->normals, &ctx->tangents, &ctx->uvs, &ctx->indices, &ctx->blas_nodes, &ctx->blas_tris,
+                    &ctx->d_blas, &ctx->materials, &ctx->lights, &ctx->transforms, &ctx->prev_transforms, &ctx->normal_mats,
+                    &ctx->det3, &ctx->instances, &ctx->blas_of_instance, &ctx->emissive_idx, &ctx->tlas_nodes, &ctx->tlas_leaf_ids,
+                    &ctx->inst_recs, &ctx->valid_slots, &ctx->q_rays, &ctx->q_hits, &ctx->q_work};
+  for (DevBuf* b : bufs) b->release();
+  for (auto& b : ctx->px) b.release();
+  scratch_free(ctx->scratch_blas);
+  scratch_free(ctx->scratch_tlas);
+  for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* snkpt_last_error(const SnkPt* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+void snkpt_default_settings(SnkRtSettings* s) {
+  if (!s) return;
+  memset(s, 0, sizeof(*s));
+  s->num_temporal_resamples = 1;  // Raytracing.h:14
+  s->num_spatial_resamples = 3;   // Raytracing.h:15
+  s->mode = SNKPT_MODE_REFERENCE;
+  s->ris_iters = 32;              // RayGen.rgen:95
+  s->m_cap = 20;                  // RayGen.rgen:97
+  s->neighbour_radius = 30.0f;    // RayGen.rgen:488
+  s->normal_threshold = 0.95f;    // RayGen.rgen:435, :491
+  s->max_bounces = 4;
+  s->spp = 1;
+}
+
+int snkpt_resize(SnkPt* ctx, uint32_t width, uint32_t height) {
+  if (!ctx) return SNKPT_E_INVALID;
+  REQUIRE(width && height, SNKPT_E_INVALID, "snkpt_resize: zero extent");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->W = width; ctx->H = height; ctx->row0 = 0; ctx->row1 = height;
+  return alloc_pixels(ctx);
+}
+
+int snkpt_set_rows(SnkPt* ctx, uint32_t row_begin, uint32_t row_end) {
+  if (!ctx) return SNKPT_E_INVALID;
+  if (row_end == 0) row_end = ctx->H;
+  REQUIRE(row_begin < row_end && row_end <= ctx->H, SNKPT_E_INVALID, "snkpt_set_rows: bad band");
+  ctx->row0 = row_begin; ctx->row1 = row_end;
+  return SNKPT_OK;
+}
+
+int snkpt_reset_history(SnkPt* ctx) {
+  if (!ctx) return SNKPT_E_INVALID;
+  ctx->history_valid = false;
+  return SNKPT_OK;
+}
+
+// ---- meshes + BLAS ------------------------------------------------------------------------------
+static int build_blas(SnkPt* ctx, uint32_t blas_id, bool fresh, cudaStream_t st) {
+  const BlasSrc src = ctx->blas_src[blas_id];
+  const uint32_t n = src.num_tris;
+  SnkBlasInfo& info = ctx->blas[blas_id];
+  if (fresh) {
+    info.node_root = ctx->n_blas_nodes;
+    info.tri_base = ctx->n_blas_tris;
+  }
+  const uint32_t node_cap = n ? n : 1;
+  CK(ctx->blas_nodes.reserve(sizeof(SnkNode8) * ((size_t)info.node_root + node_cap), true, st));
+  CK(ctx->blas_tris.reserve(sizeof(SnkTri) * ((size_t)info.tri_base + n + 1), true, st));
+  CK(scratch_reserve(ctx->scratch_blas, n ? n : 1));
+  BuildScratch& s = ctx->scratch_blas;
+  cudaEventRecord(ctx->ev[6], st);
+  launch_triangle_bounds(s, ctx->positions.as<float>(), ctx->indices.as<uint32_t>(), src.index_offset, src.vertex_offset, n, st);
+  ctx->stats.kernel_launches += n ? 2 : 1;
+  if (n == 0) {
+    // empty BLAS: a root with no children
+    SnkNode8 nd; memset(&nd, 0, sizeof(nd));
+    for (int k = 0; k < 8; ++k) { nd.qlox[k] = nd.qloy[k] = nd.qloz[k] = 255; }
+    nd.ex = nd.ey = nd.ez = 127;
+    CK(cudaMemcpyAsync(ctx->blas_nodes.as<SnkNode8>() + info.node_root, &nd, sizeof(nd), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    info.node_count = 1; info.tri_count = 0;
+    for (int k = 0; k < 3; ++k) { info.bounds_lo[k] = 0; info.bounds_hi[k] = 0; }
+    if (fresh) { ctx->n_blas_nodes += 1; }
+    return SNKPT_OK;
+  }
+  BuildOutput out;
+  out.nodes = ctx->blas_nodes.as<SnkNode8>(); out.node_offset = info.node_root; out.node_capacity = node_cap;
+  out.tris = ctx->blas_tris.as<SnkTri>(); out.leaf_ids = nullptr; out.leaf_remap = nullptr; out.leaf_offset = info.tri_base;
+  ctx->stats.kernel_launches += launch_build(s, n, out, ctx->positions.as<float>(), ctx->indices.as<uint32_t>(), src.index_offset,
+                                             src.vertex_offset, st);
+  cudaEventRecord(ctx->ev[7], st);
+  uint32_t counters[16];
+  CK(cudaMemcpyAsync(counters, s.counters, sizeof(counters), cudaMemcpyDeviceToHost, st));
+  float4 root_lo, root_hi;
+  // binary root box = box of node 0 (n > 1) or of the only leaf (also index 0)
+  CK(cudaMemcpyAsync(&root_lo, s.bb_lo, sizeof(float4), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&root_hi, s.bb_hi, sizeof(float4), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  cudaEventElapsedTime(&ctx->stats.ms_build_last, ctx->ev[6], ctx->ev[7]);
+  REQUIRE(counters[4] == 0, SNKPT_E_NOMEM, "BLAS build: node pool overflow");
+  REQUIRE(counters[2] == n && counters[1] == n, SNKPT_E_STATE, "BLAS build: not every primitive reached a leaf");
+  info.node_count = counters[0];
+  info.tri_count = counters[1];
+  info.bounds_lo[0] = root_lo.x; info.bounds_lo[1] = root_lo.y; info.bounds_lo[2] = root_lo.z;
+  info.bounds_hi[0] = root_hi.x; info.bounds_hi[1] = root_hi.y; info.bounds_hi[2] = root_hi.z;
+  if (fresh) { ctx->n_blas_nodes += info.node_count; ctx->n_blas_tris += info.tri_count; }
+  return SNKPT_OK;
+}
+
+static int upload_blas_table(SnkPt* ctx, cudaStream_t st) {
+  if (ctx->blas.empty()) return SNKPT_OK;
+  CK(ctx->d_blas.reserve(sizeof(SnkBlasInfo) * ctx->blas.size(), false, st));
+  CK(cudaMemcpyAsync(ctx->d_blas.p, ctx->blas.data(), sizeof(SnkBlasInfo) * ctx->blas.size(), cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  return SNKPT_OK;
+}
+
+int snkpt_upload_mesh(SnkPt* ctx, const float* positions, const float* normals, const float* tangents, const float* uvs,
+                      uint32_t num_vertices, const uint32_t* indices, uint32_t num_indices, const SnkSubmesh* submeshes,
+                      uint32_t num_submeshes, SnkMeshEntry* out_entry, void* stream) {
+  if (!ctx) return SNKPT_E_INVALID;
+  REQUIRE(positions && indices && submeshes && out_entry, SNKPT_E_INVALID, "snkpt_upload_mesh: null argument");
+  REQUIRE(num_submeshes >= 1 && num_submeshes <= SNKPT_MAX_SUBMESHES, SNKPT_E_INVALID, "snkpt_upload_mesh: submesh count");
+  REQUIRE(num_indices % 3 == 0, SNKPT_E_INVALID, "snkpt_upload_mesh: indices not a multiple of 3");
+  for (uint32_t s = 0; s < num_submeshes; ++s) {
+    REQUIRE(submeshes[s].num_indices % 3 == 0 && (uint64_t)submeshes[s].base_index + submeshes[s].num_indices <= num_indices &&
+                (uint64_t)submeshes[s].base_vertex + submeshes[s].num_vertices <= num_vertices,
+            SNKPT_E_INVALID, "snkpt_upload_mesh: submesh range out of bounds");
+    for (uint32_t k = 0; k < submeshes[s].num_indices; ++k)
+      REQUIRE((uint64_t)indices[submeshes[s].base_index + k] + submeshes[s].base_vertex < num_vertices, SNKPT_E_INVALID,
+              "snkpt_upload_mesh: index out of range");
+  }
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  // append to the five global SoA buffers (MeshBufferManager.cpp:49-70)
+  const size_t v0 = ctx->num_vertices, i0 = ctx->num_indices, nv = num_vertices, ni = num_indices;
+  CK(ctx->positions.reserve(12 * (v0 + nv), true, st)); CK(ctx->normals.reserve(12 * (v0 + nv), true, st));
+  CK(ctx->tangents.reserve(12 * (v0 + nv), true, st)); CK(ctx->uvs.reserve(8 * (v0 + nv), true, st));
+  CK(ctx->indices.reserve(4 * (i0 + ni), true, st));
+  CK(cudaMemcpyAsync(ctx->positions.as<char>() + 12 * v0, positions, 12 * nv, cudaMemcpyHostToDevice, st));
+  if (normals) CK(cudaMemcpyAsync(ctx->normals.as<char>() + 12 * v0, normals, 12 * nv, cudaMemcpyHostToDevice, st));
+  else CK(cudaMemsetAsync(ctx->normals.as<char>() + 12 * v0, 0, 12 * nv, st));
+  if (tangents) CK(cudaMemcpyAsync(ctx->tangents.as<char>() + 12 * v0, tangents, 12 * nv, cudaMemcpyHostToDevice, st));
+  else CK(cudaMemsetAsync(ctx->tangents.as<char>() + 12 * v0, 0, 12 * nv, st));
+  if (uvs) CK(cudaMemcpyAsync(ctx->uvs.as<char>() + 8 * v0, uvs, 8 * nv, cudaMemcpyHostToDevice, st));
+  else CK(cudaMemsetAsync(ctx->uvs.as<char>() + 8 * v0, 0, 8 * nv, st));
+  CK(cudaMemcpyAsync(ctx->indices.as<char>() + 4 * i0, indices, 4 * ni, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  ctx->num_vertices += num_vertices; ctx->num_indices += num_indices;
+  memset(out_entry, 0, sizeof(*out_entry));
+  out_entry->data_start_indices_idx = (uint32_t)i0;
+  out_entry->data_start_vertex_idx = (uint32_t)v0;
+  out_entry->num_submeshes = num_submeshes;
+  for (uint32_t s = 0; s < num_submeshes; ++s) {
+    const uint32_t id = (uint32_t)ctx->blas.size();
+    ctx->blas.push_back(SnkBlasInfo{});
+    ctx->blas_src.push_back(BlasSrc{(uint32_t)i0 + submeshes[s].base_index, (uint32_t)v0 + submeshes[s].base_vertex, submeshes[s].num_indices / 3});
+    out_entry->blas_id[s] = id;
+    int rc = build_blas(ctx, id, true, st);
+    if (rc) return rc;
+  }
+  ctx->stats.blas_nodes = ctx->n_blas_nodes; ctx->stats.blas_tris = ctx->n_blas_tris;
+  ctx->tlas_built = false;
+  return upload_blas_table(ctx, st);
+}
+
+int snkpt_update_positions(SnkPt* ctx, const SnkMeshEntry* entry, const float* positions, uint32_t num_vertices) {
+  if (!ctx) return SNKPT_E_INVALID;
+  REQUIRE(entry && positions, SNKPT_E_INVALID, "snkpt_update_positions: null argument");
+  REQUIRE((uint64_t)entry->data_start_vertex_idx + num_vertices <= ctx->num_vertices, SNKPT_E_INVALID, "snkpt_update_positions: range");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(ctx->positions.as<char>() + 12ull * entry->data_start_vertex_idx, positions, 12ull * num_vertices, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SNKPT_OK;
+}
+
+int snkpt_rebuild_blas(SnkPt* ctx, uint32_t blas_id, void* stream) {
+  if (!ctx) return SNKPT_E_INVALID;
+  REQUIRE(blas_id < ctx->blas.size(), SNKPT_E_INVALID, "snkpt_rebuild_blas: bad id");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  // rebuild in place: the node/triangle regions of this BLAS were sized for its worst case at first build
+  // only when it is the last BLAS in the pools; otherwise append a fresh copy
+  const SnkBlasInfo old = ctx->blas[blas_id];
+  const bool last = old.node_root + old.node_count == ctx->n_blas_nodes && old.tri_base + old.tri_count == ctx->n_blas_tris;
+  if (last) { ctx->n_blas_nodes = old.node_root; ctx->n_blas_tris = old.tri_base; }
+  int rc = build_blas(ctx, blas_id, true, st);
+  if (rc) return rc;
+  ctx->stats.blas_nodes = ctx->n_blas_nodes; ctx->stats.blas_tris = ctx->n_blas_tris;
+  ctx->tlas_built = false;
+  return upload_blas_table(ctx, st);
+}
+
+int snkpt_refit_blas(SnkPt* ctx, uint32_t blas_id, void* stream) {
+  // topology-preserving refit is scheduled with the C5 row; until then a refit request is served by a full rebuild,
+  // which is always correct (the reference itself never updates a BLAS, TLAS.cpp:63)
+  return snkpt_rebuild_blas(ctx, blas_id, stream);
+}
+
+// ---- scene buffers -----------------------------------------------------------------------------------
+int snkpt_set_materials(SnkPt* ctx, const SnkMaterial* materials, uint32_t first, uint32_t count) {
+  if (!ctx) return SNKPT_E_INVALID;
+  REQUIRE(materials && (uint64_t)first + count <= ctx->max_materials, SNKPT_E_INVALID, "snkpt_set_materials: range");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(ctx->materials.as<SnkMaterial>() + first, materials, sizeof(SnkMaterial) * count, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SNKPT_OK;
+}
+
+int snkpt_set_lights(SnkPt* ctx, const void* light_data, size_t bytes) {
+  if (!ctx) return SNKPT_E_INVALID;
+  REQUIRE(light_data && bytes >= 112 && bytes <= sizeof(SnkLightData), SNKPT_E_INVALID, "snkpt_set_lights: size");
+  const SnkLightData* L = (const SnkLightData*)light_data;
+  REQUIRE(L->num_pointlights <= SNKPT_MAX_POINTLIGHTS && 112 + (size_t)L->num_pointlights * 48 <= bytes, SNKPT_E_INVALID,
+          "snkpt_set_lights: point-light count exceeds the supplied bytes");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaMemcpyAsync(ctx->lights.p, light_data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SNKPT_OK;
+}
+
+int snkpt_set_transforms(SnkPt* ctx, const float* cur, const float* prev, uint32_t first, uint32_t count) {
+  if (!ctx) return SNKPT_E_INVALID;
+  REQUIRE(cur && (uint64_t)first + count <= ctx->max_transforms, SNKPT_E_INVALID, "snkpt_set_transforms: range");
+  CK(cudaSetDevice(ctx->device));
+  const size_t need = (size_t)first + count;
+  if (ctx->h_transforms.size() < need * 16) { ctx->h_transforms.resize(need * 16, 0.f); ctx->h_prev_transforms.resize(need * 16, 0.f); }
+  memcpy(ctx->h_transforms.data() + 16 * (size_t)first, cur, 64 * (size_t)count);
+  memcpy(ctx->h_prev_transforms.data() + 16 * (size_t)first, prev ? prev : cur, 64 * (size_t)count);
+  CK(ctx->transforms.reserve(64 * (size_t)ctx->max_transforms, true, ctx->stream));
+  CK(ctx->prev_transforms.reserve(64 * (size_t)ctx->max_transforms, true, ctx->stream));
+  CK(ctx->normal_mats.reserve(36 * (size_t)ctx->max_transforms, true, ctx->stream));
+  CK(ctx->det3.reserve(4 * (size_t)ctx->max_transforms, true, ctx->stream));
+  std::vector<float> nm(9 * (size_t)count), det(count), w2o(12);
+  for (uint32_t i = 0; i < count; ++i) derive_transform(cur + 16 * (size_t)i, w2o.data(), nm.data() + 9 * (size_t)i, &det[i]);
+  CK(cudaMemcpyAsync(ctx->transforms.as<float>() + 16 * (size_t)first, cur, 64 * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->prev_transforms.as<float>() + 16 * (size_t)first, prev ? prev : cur, 64 * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->normal_mats.as<float>() + 9 * (size_t)first, nm.data(), 36 * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->det3.as<float>() + first, det.data(), 4 * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->tlas_built = false;
+  return SNKPT_OK;
+}
+
+int snkpt_set_instances(SnkPt* ctx, const SnkInstanceData* instances, const uint32_t* blas_of_instance, uint32_t count,
+                        const uint32_t* emissive_idx, uint32_t num_emissive) {
+  if (!ctx) return SNKPT_E_INVALID;
+  REQUIRE(count <= ctx->max_instances && num_emissive <= ctx->max_instances, SNKPT_E_INVALID, "snkpt_set_instances: capacity (4096 by default)");
+  REQUIRE((instances && blas_of_instance) || count == 0, SNKPT_E_INVALID, "snkpt_set_instances: null argument");
+  for (uint32_t i = 0; i < count; ++i) {
+    if (blas_of_instance[i] == SNKPT_INVALID_INDEX) continue;
+    REQUIRE(blas_of_instance[i] < ctx->blas.size(), SNKPT_E_INVALID, "snkpt_set_instances: unknown BLAS id");
+    const BlasSrc& b = ctx->blas_src[blas_of_instance[i]];
+    REQUIRE(instances[i].num_mesh_indices / 3 == b.num_tris && instances[i].mesh_buffer_index_offset == b.index_offset &&
+                instances[i].mesh_buffer_vertex_offset == b.vertex_offset,
+            SNKPT_E_INVALID, "snkpt_set_instances: InstanceData does not describe the BLAS it references");
+    REQUIRE(instances[i].transform_idx < ctx->max_transforms && instances[i].material_idx < ctx->max_materials, SNKPT_E_INVALID,
+            "snkpt_set_instances: transform / material index out of range");
+  }
+  for (uint32_t i = 0; i < num_emissive; ++i) REQUIRE(emissive_idx[i] < count, SNKPT_E_INVALID, "snkpt_set_instances: emissive index out of range");
+  CK(cudaSetDevice(ctx->device));
+  ctx->h_instances.assign(instances, instances + count);
+  ctx->h_blas_of_instance.assign(blas_of_instance, blas_of_instance + count);
+  ctx->num_instances = count; ctx->num_emissive = num_emissive;
+  CK(ctx->instances.reserve(sizeof(SnkInstanceData) * (size_t)ctx->max_instances, false, ctx->stream));
+  CK(ctx->blas_of_instance.reserve(4 * (size_t)ctx->max_instances, false, ctx->stream));
+  CK(ctx->emissive_idx.reserve(4 * (size_t)ctx->max_instances, false, ctx->stream));
+  if (count) {
+    CK(cudaMemcpyAsync(ctx->instances.p, instances, sizeof(SnkInstanceData) * count, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->blas_of_instance.p, blas_of_instance, 4 * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (num_emissive) CK(cudaMemcpyAsync(ctx->emissive_idx.p, emissive_idx, 4 * (size_t)num_emissive, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->tlas_built = false;
+  return SNKPT_OK;
+}
+
+int snkpt_build_tlas(SnkPt* ctx, void* stream) {
+  if (!ctx) return SNKPT_E_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  // BLAS::GenerateInstance (TLAS.cpp:188-200): one record per instance slot that references a BLAS
+  std::vector<SnkInstRec> recs(ctx->num_instances);
+  std::vector<uint32_t> valid;
+  valid.reserve(ctx->num_instances);
+  float nm[9], det;
+  for (uint32_t i = 0; i < ctx->num_instances; ++i) {
+    SnkInstRec& r = recs[i];
+    memset(&r, 0, sizeof(r));
+    const uint32_t b = ctx->h_blas_of_instance[i];
+    if (b == SNKPT_INVALID_INDEX || ctx->blas[b].tri_count == 0) continue;
+    const uint32_t t = ctx->h_instances[i].transform_idx;
+    REQUIRE((size_t)t * 16 + 16 <= ctx->h_transforms.size(), SNKPT_E_STATE, "snkpt_build_tlas: instance references a transform that was never set");
+    derive_transform(ctx->h_transforms.data() + 16 * (size_t)t, r.w2o, nm, &det);
+    r.blas_root = ctx->blas[b].node_root; r.custom_idx = i; r.blas_id = b; r.flags = 0;
+    valid.push_back(i);
+  }
+  const uint32_t n = (uint32_t)valid.size();
+  CK(ctx->inst_recs.reserve(sizeof(SnkInstRec) * (size_t)(ctx->max_instances), false, st));
+  CK(ctx->valid_slots.reserve(4 * (size_t)ctx->max_instances, false, st));
+  CK(ctx->tlas_nodes.reserve(sizeof(SnkNode8) * (size_t)(ctx->max_instances + 1), false, st));
+  CK(ctx->tlas_leaf_ids.reserve(4 * (size_t)(ctx->max_instances + 1), false, st));
+  CK(scratch_reserve(ctx->scratch_tlas, ctx->max_instances));
+  ctx->tlas_prims = n;
+  ctx->tlas_built = true;
+  if (n == 0) return SNKPT_OK;
+  cudaEventRecord(ctx->ev[6], st);
+  CK(cudaMemcpyAsync(ctx->inst_recs.p, recs.data(), sizeof(SnkInstRec) * recs.size(), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->valid_slots.p, valid.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+  BuildScratch& s = ctx->scratch_tlas;
+  launch_instance_bounds(s, ctx->transforms.as<float>(), ctx->instances.as<SnkInstanceData>(), ctx->blas_of_instance.as<uint32_t>(),
+                         ctx->d_blas.as<SnkBlasInfo>(), ctx->valid_slots.as<uint32_t>(), n, st);
+  BuildOutput out;
+  out.nodes = ctx->tlas_nodes.as<SnkNode8>(); out.node_offset = 0; out.node_capacity = ctx->max_instances;
+  out.tris = nullptr; out.leaf_ids = ctx->tlas_leaf_ids.as<uint32_t>(); out.leaf_remap = ctx->valid_slots.as<uint32_t>(); out.leaf_offset = 0;
+  ctx->stats.kernel_launches += 2 + launch_build(s, n, out, nullptr, nullptr, 0, 0, st);
+  cudaEventRecord(ctx->ev[7], st);
+  // the host copies above are consumed asynchronously: wait before `recs` / `valid` go out of scope
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  cudaEventElapsedTime(&ctx->stats.ms_build_last, ctx->ev[6], ctx->ev[7]);
+  return SNKPT_OK;
+}
+
+// ---- per frame --------------------------------------------------------------------------------------------
+int snkpt_set_frame(SnkPt* ctx, const SnkCommonUBO* cur, const SnkCommonUBO* prev) {
+  if (!ctx) return SNKPT_E_INVALID;
+  REQUIRE(cur, SNKPT_E_INVALID, "snkpt_set_frame: null UBO");
+  ctx->ubo = *cur;
+  ctx->prev_ubo = prev ? *prev : *cur;
+  FrameConsts& fc = ctx->fc;
+  double v[16], p[16], pv[16], inv[16];
+  for (int i = 0; i < 16; ++i) { v[i] = cur->view[i]; p[i] = cur->proj[i]; }
+  for (int c = 0; c < 4; ++c)
+    for (int r = 0; r < 4; ++r) {
+      double s = 0.0;
+      for (int k = 0; k < 4; ++k) s += p[k * 4 + r] * v[c * 4 + k];
+      pv[c * 4 + r] = s;
+    }
+  REQUIRE(invert4(pv, inv), SNKPT_E_INVALID, "snkpt_set_frame: proj*view is singular");
+  for (int i = 0; i < 16; ++i) { fc.ivp[i] = (float)inv[i]; fc.proj_view[i] = cur->proj_view[i]; fc.prev_proj_view[i] = ctx->prev_ubo.proj_view[i]; }
+  for (int i = 0; i < 3; ++i) fc.cam_pos[i] = cur->cam_pos[i];
+  fc.time_elapsed = cur->time_elapsed; fc.delta_time = cur->delta_time;
+  fc.frame_idx = cur->frame_idx; fc.prev_frame_invalid = cur->prev_frame_invalid;
+  ctx->frame_set = true;
+  return SNKPT_OK;
+}
+
+static void fill_frame_dims(SnkPt* ctx) {
+  ctx->fc.W = ctx->W; ctx->fc.H = ctx->H; ctx->fc.row0 = ctx->row0; ctx->fc.row1 = ctx->row1;
+}
+
+int snkpt_trace_primary(SnkPt* ctx, const float* jitter_xy, void* stream) {
+  if (!ctx) return SNKPT_E_INVALID;
+  REQUIRE(ctx->frame_set, SNKPT_E_STATE, "snkpt_trace_primary: call snkpt_set_frame first");
+  REQUIRE(ctx->tlas_built, SNKPT_E_STATE, "snkpt_trace_primary: call snkpt_build_tlas first");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  fill_frame_dims(ctx);
+  ctx->fc.jx = jitter_xy ? jitter_xy[0] : 0.f; ctx->fc.jy = jitter_xy ? jitter_xy[1] : 0.f;
+  cudaEventRecord(ctx->ev[0], st);
+  ctx->stats.kernel_launches += launch_primary(ctx->trace_scene(), ctx->scene_dev(), ctx->fc, ctx->planes, st);
+  cudaEventRecord(ctx->ev[1], st);
+  CK(cudaGetLastError());
+  ctx->stats.rays_primary = (uint64_t)ctx->W * (ctx->row1 - ctx->row0);
+  ctx->gbuffer_valid = true;
+  return SNKPT_OK;
+}
+
+int snkpt_render(SnkPt* ctx, const SnkRtSettings* settings, void* stream) {
+  if (!ctx) return SNKPT_E_INVALID;
+  REQUIRE(settings, SNKPT_E_INVALID, "snkpt_render: null settings");
+  REQUIRE(ctx->gbuffer_valid, SNKPT_E_STATE, "snkpt_render: call snkpt_trace_primary first");
+  REQUIRE(ctx->tlas_built, SNKPT_E_STATE, "snkpt_render: call snkpt_build_tlas first");
+  REQUIRE(settings->mode <= SNKPT_MODE_NORTHSTAR, SNKPT_E_INVALID, "snkpt_render: unknown mode");
+  REQUIRE(settings->ris_iters >= 1 && settings->ris_iters <= 1024, SNKPT_E_INVALID, "snkpt_render: ris_iters");
+  REQUIRE(settings->num_spatial_resamples >= 0 && settings->num_spatial_resamples <= 64, SNKPT_E_INVALID, "snkpt_render: num_spatial_resamples");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  fill_frame_dims(ctx);
+  int rc = settings->mode == SNKPT_MODE_REFERENCE ? launch_reference_frame(ctx, *settings, st) : launch_northstar_frame(ctx, *settings, st);
+  if (rc < 0) return rc;
+  CK(cudaGetLastError());
+  ctx->history_valid = true;
+  return SNKPT_OK;
+}
+
+int snkpt_accumulate(SnkPt* ctx, int reset, void* stream) {
+  if (!ctx) return SNKPT_E_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  if (reset) ctx->accum_count = 0;
+  ctx->stats.kernel_launches += launch_accumulate(ctx->planes, ctx->W * ctx->H, ctx->accum_count, st);
+  ctx->accum_count++;
+  CK(cudaGetLastError());
+  return SNKPT_OK;
+}
+
+// ---- readback ------------------------------------------------------------------------------------------------
+static int aux_desc(SnkPt* ctx, uint32_t what, const void** src, size_t* bytes) {
+  const size_t n = (size_t)ctx->W * ctx->H;
+  const PixelPlanes& P = ctx->planes;
+  switch (what) {
+    case SNKPT_AUX_PRIM_ID: *src = P.prim; *bytes = 4 * n; break;
+    case SNKPT_AUX_INST_ID: *src = P.inst; *bytes = 4 * n; break;
+    case SNKPT_AUX_DEPTH: *src = P.depth; *bytes = 4 * n; break;
+    case SNKPT_AUX_NORMAL: *src = P.normal; *bytes = 8 * n; break;
+    case SNKPT_AUX_ALBEDO: *src = P.albedo; *bytes = 4 * n; break;
+    case SNKPT_AUX_RMA: *src = P.rma; *bytes = 8 * n; break;
+    case SNKPT_AUX_MOTION: *src = P.motion; *bytes = 4 * n; break;
+    case SNKPT_AUX_MAT_FLAGS: *src = P.flags; *bytes = 2 * n; break;
+    case SNKPT_AUX_PREV_NORMAL: *src = P.prev_normal; *bytes = 8 * n; break;
+    case SNKPT_AUX_PREV_DEPTH: *src = P.prev_depth; *bytes = 4 * n; break;
+    case SNKPT_AUX_BVH_NODES: *src = ctx->blas_nodes.p; *bytes = sizeof(SnkNode8) * (size_t)ctx->n_blas_nodes; break;
+    case SNKPT_AUX_BVH_TRIS: *src = ctx->blas_tris.p; *bytes = sizeof(SnkTri) * (size_t)ctx->n_blas_tris; break;
+    case SNKPT_AUX_HIT_T: *src = P.hit_t; *bytes = 4 * n; break;
+    case SNKPT_AUX_HIT_BARY: *src = P.bary; *bytes = 8 * n; break;
+    case SNKPT_AUX_RADIANCE_F32: *src = P.radiance; *bytes = 16 * n; break;
+    case SNKPT_AUX_ACCUM_F32: *src = P.accum; *bytes = 16 * n; break;
+    case SNKPT_AUX_DIRECT_F32: *src = P.direct; *bytes = 16 * n; break;
+    case SNKPT_AUX_TLAS_INSTANCES: *src = ctx->inst_recs.p; *bytes = sizeof(SnkInstRec) * (size_t)ctx->num_instances; break;
+    case SNKPT_AUX_RESERVOIRS_FINAL:
+    case SNKPT_AUX_RESERVOIRS_TEMPORAL: *src = nullptr; *bytes = 48 * n; break;
+    case SNKPT_AUX_BLAS_TABLE: *src = nullptr; *bytes = sizeof(SnkBlasInfo) * ctx->blas.size(); break;
+    default: return SNKPT_E_INVALID;
+  }
+  return SNKPT_OK;
+}
+
+int snkpt_aux_size(SnkPt* ctx, uint32_t what, size_t* bytes) {
+  if (!ctx || !bytes) return SNKPT_E_INVALID;
+  const void* src;
+  int rc = aux_desc(ctx, what, &src, bytes);
+  if (rc) ctx->err = "snkpt_aux_size: unknown aux id";
+  return rc;
+}
+
+int snkpt_read_aux(SnkPt* ctx, uint32_t what, void* dst, size_t bytes) {
+  if (!ctx) return SNKPT_E_INVALID;
+  const void* src = nullptr;
+  size_t need = 0;
+  REQUIRE(aux_desc(ctx, what, &src, &need) == SNKPT_OK, SNKPT_E_INVALID, "snkpt_read_aux: unknown aux id");
+  REQUIRE(dst && bytes >= need, SNKPT_E_INVALID, "snkpt_read_aux: destination too small");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (what == SNKPT_AUX_BLAS_TABLE) { memcpy(dst, ctx->blas.data(), need); return SNKPT_OK; }
+  if (what == SNKPT_AUX_RESERVOIRS_FINAL || what == SNKPT_AUX_RESERVOIRS_TEMPORAL) {
+    // SoA planes → the reference's 48-B AoS record
+    const uint32_t half = what == SNKPT_AUX_RESERVOIRS_FINAL ? 0 : 1;
+    const size_t n = (size_t)ctx->W * ctx->H;
+    std::vector<float4> pl(3 * n);
+    for (int k = 0; k < 3; ++k) CK(cudaMemcpy(pl.data() + k * n, ctx->planes.res[half][k], 16 * n, cudaMemcpyDeviceToHost));
+    SnkPixelReservoir* o = (SnkPixelReservoir*)dst;
+    for (size_t i = 0; i < n; ++i) {
+      memcpy(&o[i].w_sum_pl, &pl[i], 16);
+      memcpy(&o[i].object_instance_idx, &pl[n + i], 16);
+      memcpy(&o[i].w_sum_em, &pl[2 * n + i], 16);
+    }
+    return SNKPT_OK;
+  }
+  if (need) CK(cudaMemcpy(dst, src, need, cudaMemcpyDeviceToHost));
+  return SNKPT_OK;
+}
+
+int snkpt_write_reservoirs(SnkPt* ctx, uint32_t half, const SnkPixelReservoir* src, uint32_t first_pixel, uint32_t count) {
+  if (!ctx) return SNKPT_E_INVALID;
+  const size_t n = (size_t)ctx->W * ctx->H;
+  REQUIRE(half < 2 && src && (size_t)first_pixel + count <= n, SNKPT_E_INVALID, "snkpt_write_reservoirs: range");
+  CK(cudaSetDevice(ctx->device));
+  std::vector<float4> pl(3 * (size_t)count);
+  for (size_t i = 0; i < count; ++i) {
+    memcpy(&pl[i], &src[i].w_sum_pl, 16);
+    memcpy(&pl[count + i], &src[i].object_instance_idx, 16);
+    memcpy(&pl[2 * (size_t)count + i], &src[i].w_sum_em, 16);
+  }
+  CK(cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < 3; ++k)
+    CK(cudaMemcpy(ctx->planes.res[half][k] + first_pixel, pl.data() + (size_t)k * count, 16 * (size_t)count, cudaMemcpyHostToDevice));
+  return SNKPT_OK;
+}
+
+int snkpt_read_output(SnkPt* ctx, void* dst, uint32_t format) {
+  if (!ctx) return SNKPT_E_INVALID;
+  REQUIRE(dst && format <= SNKPT_FMT_RGBA32F, SNKPT_E_INVALID, "snkpt_read_output: arguments");
+  CK(cudaSetDevice(ctx->device));
+  const size_t off = (size_t)ctx->row0 * ctx->W, cnt = (size_t)(ctx->row1 - ctx->row0) * ctx->W;
+  if (format == SNKPT_FMT_RGBA16F) CK(cudaMemcpyAsync(dst, ctx->planes.out16 + off, 8 * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+  else CK(cudaMemcpyAsync(dst, ctx->planes.radiance + off, 16 * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SNKPT_OK;
+}
+
+int snkpt_device_ptr(SnkPt* ctx, uint32_t what, void** ptr, size_t* bytes) {
+  if (!ctx || !ptr || !bytes) return SNKPT_E_INVALID;
+  const size_t n = (size_t)ctx->W * ctx->H;
+  if (what == 0x100) { *ptr = ctx->planes.out16; *bytes = 8 * n; return SNKPT_OK; }
+  if (what == 0x101) { *ptr = ctx->planes.accum; *bytes = 16 * n; return SNKPT_OK; }
+  if (what == 0x102) { *ptr = ctx->planes.radiance; *bytes = 16 * n; return SNKPT_OK; }
+  if (what >= 0x110 && what < 0x116) { *ptr = ctx->planes.res[(what - 0x110) / 3][(what - 0x110) % 3]; *bytes = 16 * n; return SNKPT_OK; }
+  ctx->err = "snkpt_device_ptr: unknown id";
+  return SNKPT_E_INVALID;
+}
+
+int snkpt_get_stats(SnkPt* ctx, SnkPtStats* out) {
+  if (!ctx || !out) return SNKPT_E_INVALID;
+  cudaSetDevice(ctx->device);
+  if (ctx->gbuffer_valid && cudaEventQuery(ctx->ev[1]) == cudaSuccess) cudaEventElapsedTime(&ctx->stats.ms_primary, ctx->ev[0], ctx->ev[1]);
+  *out = ctx->stats;
+  return SNKPT_OK;
+}
+
+int snkpt_synchronize(SnkPt* ctx) {
+  if (!ctx) return SNKPT_E_INVALID;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaGetLastError());
+  return SNKPT_OK;
+}
+
+// ---- ray queries ---------------------------------------------------------------------------------------------------
+int snkpt_trace_rays(SnkPt* ctx, const SnkRay* rays, uint64_t count, uint32_t flags, SnkHit* hits, void* stream) {
+  if (!ctx) return SNKPT_E_INVALID;
+  REQUIRE(ctx->tlas_built, SNKPT_E_STATE, "snkpt_trace_rays: call snkpt_build_tlas first");
+  REQUIRE((rays && hits) || count == 0, SNKPT_E_INVALID, "snkpt_trace_rays: null argument");
+  if (count == 0) return SNKPT_OK;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  const bool any = flags & SNKPT_RAY_ANY;
+  const float4* d_rays; SnkHit* d_hits;
+  if (flags & SNKPT_RAY_DEVICE_PTRS) { d_rays = (const float4*)rays; d_hits = hits; }
+  else {
+    CK(ctx->q_rays.reserve(sizeof(SnkRay) * count, false, st));
+    CK(ctx->q_hits.reserve(sizeof(SnkHit) * count, false, st));
+    CK(cudaMemcpyAsync(ctx->q_rays.p, rays, sizeof(SnkRay) * count, cudaMemcpyHostToDevice, st));
+    d_rays = ctx->q_rays.as<float4>(); d_hits = ctx->q_hits.as<SnkHit>();
+  }
+  ctx->stats.kernel_launches += launch_trace(ctx->trace_scene(), d_rays, count, any, d_hits, nullptr, nullptr, st);
+  CK(cudaGetLastError());
+  if (any) ctx->stats.rays_shadow = count; else ctx->stats.rays_secondary = count;
+  if (!(flags & SNKPT_RAY_DEVICE_PTRS)) {
+    CK(cudaMemcpyAsync(hits, d_hits, sizeof(SnkHit) * count, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  return SNKPT_OK;
+}
+
+int snkpt_count_work(SnkPt* ctx, const SnkRay* rays, const SnkHit* hits, uint64_t count, uint32_t flags, uint32_t* out3, void* stream) {
+  if (!ctx) return SNKPT_E_INVALID;
+  REQUIRE(ctx->tlas_built, SNKPT_E_STATE, "snkpt_count_work: call snkpt_build_tlas first");
+  REQUIRE((rays && hits && out3) || count == 0, SNKPT_E_INVALID, "snkpt_count_work: null argument");
+  if (count == 0) return SNKPT_OK;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  const float4* d_rays; const SnkHit* d_hits; uint32_t* d_out;
+  if (flags & SNKPT_RAY_DEVICE_PTRS) { d_rays = (const float4*)rays; d_hits = hits; d_out = out3; }
+  else {
+    CK(ctx->q_rays.reserve(sizeof(SnkRay) * count, false, st));
+    CK(ctx->q_hits.reserve(sizeof(SnkHit) * count, false, st));
+    CK(ctx->q_work.reserve(12 * count, false, st));
+    CK(cudaMemcpyAsync(ctx->q_rays.p, rays, sizeof(SnkRay) * count, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ctx->q_hits.p, hits, sizeof(SnkHit) * count, cudaMemcpyHostToDevice, st));
+    d_rays = ctx->q_rays.as<float4>(); d_hits = ctx->q_hits.as<SnkHit>(); d_out = ctx->q_work.as<uint32_t>();
+  }
+  launch_count_work(ctx->trace_scene(), d_rays, d_hits, count, flags & SNKPT_RAY_ANY, d_out, st);
+  CK(cudaGetLastError());
+  if (!(flags & SNKPT_RAY_DEVICE_PTRS)) {
+    CK(cudaMemcpyAsync(out3, d_out, 12 * count, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+  }
+  return SNKPT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,628 @@
+// bvh_build.cu — LBVH -> BVH8 builder for sm_100a. See bvh_build.cuh for the
+// reference entry points this replaces (TLAS.cpp:10-87, :109-186).
+//
+// All stages are HBM-bound integer / float32 streaming kernels; grids are sized
+// from the primitive count with 256-thread CTAs (the collapse kernel is the one
+// latency-bound stage: one thread per wide node, fed through a ticket queue).
+#include "bvh_build.cuh"
+
+#include <cfloat>
+
+namespace snk {
+
+namespace {
+
+constexpr uint32_t EMPTY = 0xFFFFFFFFu;
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ITEMS = 16;                                  // keys per thread
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;            // 4096 keys per CTA
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int LEAF_MAX = 3;                                     // triangles per leaf slot
+
+enum { C_NODES = 0, C_LEAVES = 1, C_DONE = 2, C_OVERFLOW = 4, C_BOUNDS = 8 };
+
+__device__ __forceinline__ uint32_t f2ord(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+
+__global__ void k_init(uint32_t* counters, uint32_t* queue) {
+  const int t = threadIdx.x;
+  if (t < 16) {
+    uint32_t v = 0;
+    if (t == C_NODES) v = 1;
+    if (t >= C_BOUNDS && t < C_BOUNDS + 3) v = 0xFFFFFFFFu;
+    counters[t] = v;
+  }
+  if (t == 0) queue[0] = 0;
+}
+
+__device__ __forceinline__ void reduce_centroid_bounds(float cx, float cy, float cz, bool valid, uint32_t* counters) {
+  float lo[3] = {valid ? cx : FLT_MAX, valid ? cy : FLT_MAX, valid ? cz : FLT_MAX};
+  float hi[3] = {valid ? cx : -FLT_MAX, valid ? cy : -FLT_MAX, valid ? cz : -FLT_MAX};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+      hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+    }
+  }
+  if ((threadIdx.x & 31) == 0 && lo[0] <= hi[0]) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      atomicMin(&counters[C_BOUNDS + k], f2ord(lo[k]));
+      atomicMax(&counters[C_BOUNDS + 3 + k], f2ord(hi[k]));
+    }
+  }
+}
+
+// widen by 2 ulp so that the (conservatively quantised) boxes also cover the rounding of the triangle test
+__device__ __forceinline__ float pad_dn(float v) { return v - fabsf(v) * 2.4e-7f - 1e-30f; }
+__device__ __forceinline__ float pad_up(float v) { return v + fabsf(v) * 2.4e-7f + 1e-30f; }
+
+__global__ void k_triangle_bounds(const float* __restrict__ positions, const uint32_t* __restrict__ indices, uint32_t index_offset,
+                                  uint32_t vertex_offset, uint32_t n, float4* __restrict__ prim_lo, float4* __restrict__ prim_hi,
+                                  uint32_t* counters) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < n;
+  float cx = 0, cy = 0, cz = 0;
+  if (valid) {
+    const uint32_t* ip = indices + index_offset + 3ull * i;
+    const uint32_t a = ip[0] + vertex_offset, b = ip[1] + vertex_offset, c = ip[2] + vertex_offset;
+    const float ax = positions[3ull * a], ay = positions[3ull * a + 1], az = positions[3ull * a + 2];
+    const float bx = positions[3ull * b], by = positions[3ull * b + 1], bz = positions[3ull * b + 2];
+    const float cx2 = positions[3ull * c], cy2 = positions[3ull * c + 1], cz2 = positions[3ull * c + 2];
+    const float lx = fminf(ax, fminf(bx, cx2)), ly = fminf(ay, fminf(by, cy2)), lz = fminf(az, fminf(bz, cz2));
+    const float hx = fmaxf(ax, fmaxf(bx, cx2)), hy = fmaxf(ay, fmaxf(by, cy2)), hz = fmaxf(az, fmaxf(bz, cz2));
+    prim_lo[i] = make_float4(pad_dn(lx), pad_dn(ly), pad_dn(lz), 0.f);
+    prim_hi[i] = make_float4(pad_up(hx), pad_up(hy), pad_up(hz), 0.f);
+    cx = 0.5f * (lx + hx); cy = 0.5f * (ly + hy); cz = 0.5f * (lz + hz);
+  }
+  reduce_centroid_bounds(cx, cy, cz, valid, counters);
+}
+
+__global__ void k_instance_bounds(const float* __restrict__ transforms, const SnkInstanceData* __restrict__ inst,
+                                  const uint32_t* __restrict__ blas_of_instance, const SnkBlasInfo* __restrict__ blas,
+                                  const uint32_t* __restrict__ valid_slots, uint32_t n, float4* __restrict__ prim_lo,
+                                  float4* __restrict__ prim_hi, uint32_t* counters) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < n;
+  float cx = 0, cy = 0, cz = 0;
+  if (valid) {
+    const uint32_t slot = valid_slots[i];
+    const SnkBlasInfo b = blas[blas_of_instance[slot]];
+    const float* M = transforms + 16ull * inst[slot].transform_idx;
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float x = (c & 1) ? b.bounds_hi[0] : b.bounds_lo[0], y = (c & 2) ? b.bounds_hi[1] : b.bounds_lo[1],
+                  z = (c & 4) ? b.bounds_hi[2] : b.bounds_lo[2];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const float w = M[r] * x + M[4 + r] * y + M[8 + r] * z + M[12 + r];
+        lo[r] = fminf(lo[r], w); hi[r] = fmaxf(hi[r], w);
+      }
+    }
+    // instance boxes are transformed in float32: widen by a relative 1e-5 so they stay conservative
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const float e = 1e-5f * fmaxf(fmaxf(fabsf(lo[r]), fabsf(hi[r])), 1e-3f);
+      lo[r] -= e; hi[r] += e;
+    }
+    prim_lo[i] = make_float4(lo[0], lo[1], lo[2], 0.f);
+    prim_hi[i] = make_float4(hi[0], hi[1], hi[2], 0.f);
+    cx = 0.5f * (lo[0] + hi[0]); cy = 0.5f * (lo[1] + hi[1]); cz = 0.5f * (lo[2] + hi[2]);
+  }
+  reduce_centroid_bounds(cx, cy, cz, valid, counters);
+}
+
+__device__ __forceinline__ unsigned long long expand21(unsigned long long x) {
+  x &= 0x1fffffull;
+  x = (x | x << 32) & 0x1f00000000ffffull;
+  x = (x | x << 16) & 0x1f0000ff0000ffull;
+  x = (x | x << 8) & 0x100f00f00f00f00full;
+  x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+  x = (x | x << 2) & 0x1249249249249249ull;
+  return x;
+}
+
+__global__ void k_morton(const float4* __restrict__ prim_lo, const float4* __restrict__ prim_hi, uint32_t n,
+                         const uint32_t* __restrict__ counters, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float lx = ord2f(counters[C_BOUNDS]), ly = ord2f(counters[C_BOUNDS + 1]), lz = ord2f(counters[C_BOUNDS + 2]);
+  const float hx = ord2f(counters[C_BOUNDS + 3]), hy = ord2f(counters[C_BOUNDS + 4]), hz = ord2f(counters[C_BOUNDS + 5]);
+  const float4 a = prim_lo[i], b = prim_hi[i];
+  const float sx = hx > lx ? 2097152.0f / (hx - lx) : 0.f, sy = hy > ly ? 2097152.0f / (hy - ly) : 0.f,
+              sz = hz > lz ? 2097152.0f / (hz - lz) : 0.f;
+  const float qx = fminf(fmaxf((0.5f * (a.x + b.x) - lx) * sx, 0.f), 2097151.f);
+  const float qy = fminf(fmaxf((0.5f * (a.y + b.y) - ly) * sy, 0.f), 2097151.f);
+  const float qz = fminf(fmaxf((0.5f * (a.z + b.z) - lz) * sz, 0.f), 2097151.f);
+  keys[i] = (expand21((unsigned long long)qx) << 2) | (expand21((unsigned long long)qy) << 1) | expand21((unsigned long long)qz);
+  vals[i] = i;
+}
+
+// ---- radix sort: one pass = histogram, scan, scatter ------------------------------------
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const unsigned long long* __restrict__ keys, uint32_t n, int shift,
+                                                            uint32_t* __restrict__ block_hist, uint32_t num_blocks) {
+  __shared__ uint32_t sh[256];
+  sh[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t base = blockIdx.x * SORT_TILE;
+#pragma unroll 4
+  for (int it = 0; it < SORT_ITEMS; ++it) {
+    const uint32_t idx = base + it * SORT_THREADS + threadIdx.x;
+    if (idx < n) atomicAdd(&sh[(uint32_t)(keys[idx] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  block_hist[threadIdx.x * num_blocks + blockIdx.x] = sh[threadIdx.x];
+}
+
+// exclusive scan of `count` words by one CTA of 1024 threads
+__global__ void __launch_bounds__(1024) k_scan(uint32_t* data, uint32_t count) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (uint32_t base = 0; base < count; base += 4096) {
+    // each thread owns 4 consecutive words
+    const uint32_t i0 = base + threadIdx.x * 4;
+    uint32_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (i0 + k < count) ? data[i0 + k] : 0u;
+    const uint32_t tsum = v[0] + v[1] + v[2] + v[3];
+    uint32_t inc = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_sums[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+      uint32_t w = warp_sums[lane];
+      uint32_t winc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+        if (lane >= o) winc += t;
+      }
+      warp_sums[lane] = winc - w;
+    }
+    __syncthreads();
+    uint32_t ex = carry + warp_sums[wid] + inc - tsum;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (i0 + k < count) data[i0 + k] = ex;
+      ex += v[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = ex;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const unsigned long long* __restrict__ keys_in,
+                                                               const uint32_t* __restrict__ vals_in, uint32_t n, int shift,
+                                                               const uint32_t* __restrict__ block_offsets, uint32_t num_blocks,
+                                                               unsigned long long* __restrict__ keys_out,
+                                                               uint32_t* __restrict__ vals_out) {
+  __shared__ uint32_t wh[SORT_WARPS][256];
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int d = lane; d < 256; d += 32) wh[wid][d] = 0;
+  __syncwarp();
+  const uint32_t warp_base = blockIdx.x * SORT_TILE + wid * (SORT_ITEMS * 32);
+  const uint32_t lt = (1u << lane) - 1u;
+  unsigned long long key[SORT_ITEMS];
+  // phase 1: per-warp digit histogram (each warp owns a contiguous run of the tile → stable)
+#pragma unroll
+  for (int it = 0; it < SORT_ITEMS; ++it) {
+    const uint32_t idx = warp_base + it * 32 + lane;
+    const bool valid = idx < n;
+    key[it] = valid ? keys_in[idx] : ~0ull;
+    const uint32_t d = valid ? ((uint32_t)(key[it] >> shift) & 255u) : 256u;
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    if (valid && (peers & lt) == 0) wh[wid][d] += __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  // phase 2: turn per-warp counts into running output positions
+  {
+    const uint32_t d = threadIdx.x;  // 256 threads, one digit each
+    uint32_t run = block_offsets[d * num_blocks + blockIdx.x];
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; ++w) {
+      const uint32_t c = wh[w][d];
+      wh[w][d] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  // phase 3: rank + scatter
+#pragma unroll
+  for (int it = 0; it < SORT_ITEMS; ++it) {
+    const uint32_t idx = warp_base + it * 32 + lane;
+    const bool valid = idx < n;
+    const uint32_t d = valid ? ((uint32_t)(key[it] >> shift) & 255u) : 256u;
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const uint32_t rank = __popc(peers & lt);
+    uint32_t pos = 0;
+    if (valid) pos = wh[wid][d] + rank;
+    __syncwarp();
+    if (valid && rank == 0) wh[wid][d] += __popc(peers);
+    __syncwarp();
+    if (valid) {
+      keys_out[pos] = key[it];
+      vals_out[pos] = vals_in[idx];
+    }
+  }
+}
+
+// ---- Karras 2012 ------------------------------------------------------------------------
+__device__ __forceinline__ int delta(const unsigned long long* __restrict__ keys, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  const unsigned long long a = keys[i], b = keys[j];
+  if (a == b) return 64 + __clz(i ^ j);
+  return __clzll((long long)(a ^ b));
+}
+
+__global__ void k_karras(const unsigned long long* __restrict__ keys, int n, int* __restrict__ left, int* __restrict__ right,
+                         int* __restrict__ parent, int* __restrict__ first, int* __restrict__ last) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  const int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
+  const int dmin = delta(keys, n, i, i - d);
+  int lmax = 2;
+  while (delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+  int l = 0;
+  for (int t = lmax >> 1; t >= 1; t >>= 1)
+    if (delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+  const int j = i + l * d;
+  const int dnode = delta(keys, n, i, j);
+  int s = 0, t = l;
+  do {
+    t = (t + 1) >> 1;
+    if (delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+  } while (t > 1);
+  const int gamma = i + s * d + min(d, 0);
+  const int lo = min(i, j), hi = max(i, j);
+  const int lc = (lo == gamma) ? (n - 1 + gamma) : gamma;
+  const int rc = (hi == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
+  left[i] = lc; right[i] = rc;
+  parent[lc] = i; parent[rc] = i;
+  first[i] = lo; last[i] = hi;
+  if (i == 0) parent[0] = -1;
+}
+
+__global__ void k_refit_binary(const float4* __restrict__ prim_lo, const float4* __restrict__ prim_hi,
+                               const uint32_t* __restrict__ sorted_prims, int n, const int* __restrict__ left,
+                               const int* __restrict__ right, const int* __restrict__ parent, float4* bb_lo, float4* bb_hi,
+                               uint32_t* flags) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const uint32_t p = sorted_prims[k];
+  int node = n - 1 + k;
+  float4 lo = prim_lo[p], hi = prim_hi[p];
+  bb_lo[node] = lo; bb_hi[node] = hi;
+  int par = parent[node];
+  while (par >= 0) {
+    __threadfence();
+    if (atomicAdd(&flags[par], 1u) == 0u) return;  // first child to arrive stops; the second one continues
+    __threadfence();
+    const int l = left[par], r = right[par];
+    const int other = (l == node) ? r : l;
+    const float4 olo = __ldcg(&bb_lo[other]), ohi = __ldcg(&bb_hi[other]);
+    lo = make_float4(fminf(lo.x, olo.x), fminf(lo.y, olo.y), fminf(lo.z, olo.z), 0.f);
+    hi = make_float4(fmaxf(hi.x, ohi.x), fmaxf(hi.y, ohi.y), fmaxf(hi.z, ohi.z), 0.f);
+    bb_lo[par] = lo; bb_hi[par] = hi;
+    node = par;
+    par = parent[node];
+  }
+}
+
+// ---- collapse to 8-wide nodes ---------------------------------------------------------------
+struct CollapseArgs {
+  int n;
+  const int *left, *right, *first, *last;
+  const float4 *bb_lo, *bb_hi;
+  const uint32_t* sorted_prims;
+  uint32_t* queue;
+  uint32_t* counters;
+  SnkNode8* nodes;
+  uint32_t node_offset, node_capacity;
+  SnkTri* tris;
+  uint32_t* leaf_ids;
+  const uint32_t* leaf_remap;
+  uint32_t leaf_offset;
+  const float* positions;
+  const uint32_t* indices;
+  uint32_t index_offset, vertex_offset;
+};
+
+__device__ __forceinline__ float half_area(float4 lo, float4 hi) {
+  const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+  return dx * dy + dy * dz + dz * dx;
+}
+
+__device__ __forceinline__ int node_count(const CollapseArgs& a, int node) {
+  return node >= a.n - 1 ? 1 : (a.last[node] - a.first[node] + 1);
+}
+
+__device__ void emit_leaf_records(const CollapseArgs& a, int node, uint32_t dst) {
+  int f, l;
+  if (node >= a.n - 1) { f = l = node - (a.n - 1); }
+  else { f = a.first[node]; l = a.last[node]; }
+  for (int k = f; k <= l; ++k, ++dst) {
+    const uint32_t prim = a.sorted_prims[k];
+    if (a.tris) {
+      const uint32_t* ip = a.indices + a.index_offset + 3ull * prim;
+      const uint32_t ia = ip[0] + a.vertex_offset, ib = ip[1] + a.vertex_offset, ic = ip[2] + a.vertex_offset;
+      float4* t = reinterpret_cast<float4*>(a.tris + dst);
+      t[0] = make_float4(a.positions[3ull * ia], a.positions[3ull * ia + 1], a.positions[3ull * ia + 2], __uint_as_float(prim));
+      t[1] = make_float4(a.positions[3ull * ib], a.positions[3ull * ib + 1], a.positions[3ull * ib + 2], 0.f);
+      t[2] = make_float4(a.positions[3ull * ic], a.positions[3ull * ic + 1], a.positions[3ull * ic + 2], 0.f);
+    } else {
+      a.leaf_ids[dst] = a.leaf_remap ? a.leaf_remap[prim] : prim;
+    }
+  }
+}
+
+// quantisation exponent: smallest e with 2^e * 255 >= extent (biased, as a float exponent byte)
+__device__ __forceinline__ int quant_exp(float extent) {
+  if (!(extent > 0.f)) return 1;
+  int ex;
+  frexpf(extent / 255.0f, &ex);  // extent/255 = m * 2^ex, m in [0.5,1)  ->  2^ex >= extent/255
+  int be = ex + 127;
+  return be < 1 ? 1 : (be > 254 ? 254 : be);
+}
+
+__device__ void process_wide_node(const CollapseArgs& a, uint32_t w, int b) {
+  // ---- choose up to 8 children by repeatedly opening the largest one
+  int ch[8];
+  float area[8];
+  int cnt[8];
+  int m = 0;
+  if (a.n == 1) {
+    ch[0] = 0; cnt[0] = 1; area[0] = 0.f; m = 1;  // single leaf (node index n-1+0 = 0)
+  } else {
+    const int l = a.left[b], r = a.right[b];
+    ch[0] = l; ch[1] = r; m = 2;
+    cnt[0] = node_count(a, l); cnt[1] = node_count(a, r);
+    area[0] = half_area(a.bb_lo[l], a.bb_hi[l]); area[1] = half_area(a.bb_lo[r], a.bb_hi[r]);
+    for (int phase = 0; phase < 2; ++phase) {
+      const int min_open = phase == 0 ? LEAF_MAX + 1 : 2;
+      while (m < 8) {
+        int best = -1; float barea = -1.f;
+        for (int i = 0; i < m; ++i)
+          if (cnt[i] >= min_open && area[i] > barea) { barea = area[i]; best = i; }
+        if (best < 0) break;
+        const int c = ch[best];
+        const int cl = a.left[c], cr = a.right[c];
+        ch[best] = cl; cnt[best] = node_count(a, cl); area[best] = half_area(a.bb_lo[cl], a.bb_hi[cl]);
+        ch[m] = cr; cnt[m] = node_count(a, cr); area[m] = half_area(a.bb_lo[cr], a.bb_hi[cr]);
+        ++m;
+      }
+    }
+  }
+  // ---- node box and child boxes
+  float4 lo[8], hi[8];
+  float4 nlo = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, 0), nhi = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, 0);
+  const int leaf_base = a.n - 1;
+  for (int i = 0; i < m; ++i) {
+    const int node = (a.n == 1) ? 0 : ch[i];
+    lo[i] = a.bb_lo[node]; hi[i] = a.bb_hi[node];
+    nlo = make_float4(fminf(nlo.x, lo[i].x), fminf(nlo.y, lo[i].y), fminf(nlo.z, lo[i].z), 0);
+    nhi = make_float4(fmaxf(nhi.x, hi[i].x), fmaxf(nhi.y, hi[i].y), fmaxf(nhi.z, hi[i].z), 0);
+  }
+  (void)leaf_base;
+  // ---- octant-ordered slot assignment (greedy on the largest remaining |cost|)
+  // slot s is visited first by rays whose direction is negative exactly on the axes whose bit is set in s,
+  // so it should hold the child lying furthest towards +axis on those axes and -axis on the others.
+  int slot_of[8];
+  {
+    const float ccx = 0.5f * (nlo.x + nhi.x), ccy = 0.5f * (nlo.y + nhi.y), ccz = 0.5f * (nlo.z + nhi.z);
+    float cost[8][8];
+    for (int i = 0; i < m; ++i) {
+      const float dx = 0.5f * (lo[i].x + hi[i].x) - ccx, dy = 0.5f * (lo[i].y + hi[i].y) - ccy, dz = 0.5f * (lo[i].z + hi[i].z) - ccz;
+      for (int s = 0; s < 8; ++s) cost[i][s] = ((s & 1) ? dx : -dx) + ((s & 2) ? dy : -dy) + ((s & 4) ? dz : -dz);
+    }
+    uint32_t used_slots = 0, used_children = 0;
+    for (int k = 0; k < m; ++k) {
+      float best = -FLT_MAX; int bi = 0, bs = 0;
+      for (int i = 0; i < m; ++i) {
+        if (used_children & (1u << i)) continue;
+        for (int s = 0; s < 8; ++s) {
+          if (used_slots & (1u << s)) continue;
+          if (cost[i][s] > best) { best = cost[i][s]; bi = i; bs = s; }
+        }
+      }
+      slot_of[bi] = bs; used_children |= 1u << bi; used_slots |= 1u << bs;
+    }
+  }
+  int child_in_slot[8];
+  for (int s = 0; s < 8; ++s) child_in_slot[s] = -1;
+  for (int i = 0; i < m; ++i) child_in_slot[slot_of[i]] = i;
+  // ---- allocate inner children + leaf records
+  int n_inner = 0, n_leafrec = 0;
+  for (int i = 0; i < m; ++i) {
+    if (cnt[i] > LEAF_MAX) ++n_inner; else n_leafrec += cnt[i];
+  }
+  uint32_t child_base = 0, rec_base = 0;
+  if (n_inner) child_base = atomicAdd(&a.counters[C_NODES], (uint32_t)n_inner);
+  if (n_leafrec) rec_base = atomicAdd(&a.counters[C_LEAVES], (uint32_t)n_leafrec);
+  if (child_base + n_inner > a.node_capacity) {  // cannot happen with capacity >= n; flag and stop growing
+    atomicExch(&a.counters[C_OVERFLOW], 1u);
+    n_inner = 0;
+  }
+  // ---- quantise
+  SnkNode8 nd;
+  nd.px = nlo.x; nd.py = nlo.y; nd.pz = nlo.z;
+  int be[3] = {quant_exp(nhi.x - nlo.x), quant_exp(nhi.y - nlo.y), quant_exp(nhi.z - nlo.z)};
+  float inv[3];
+  for (int k = 0; k < 3; ++k) inv[k] = __uint_as_float((uint32_t)(254 - be[k]) << 23);  // 2^-(be-127)
+  nd.imask = 0;
+  nd.child_base = a.node_offset + child_base;
+  nd.tri_base = a.leaf_offset + rec_base;
+  uint32_t inner_rank = 0, rec_off = 0;
+  for (int s = 0; s < 8; ++s) {
+    const int i = child_in_slot[s];
+    if (i < 0) {
+      nd.meta[s] = 0;
+      nd.qlox[s] = nd.qloy[s] = nd.qloz[s] = 255; nd.qhix[s] = nd.qhiy[s] = nd.qhiz[s] = 0;  // inverted: never hit
+      continue;
+    }
+    const float l3[3] = {lo[i].x - nlo.x, lo[i].y - nlo.y, lo[i].z - nlo.z};
+    const float h3[3] = {hi[i].x - nlo.x, hi[i].y - nlo.y, hi[i].z - nlo.z};
+    uint8_t ql[3], qh[3];
+    for (int k = 0; k < 3; ++k) {
+      const float scale = __uint_as_float((uint32_t)be[k] << 23);
+      float fl = floorf(l3[k] * inv[k]), fh = ceilf(h3[k] * inv[k]);
+      fl = fminf(fmaxf(fl, 0.f), 255.f); fh = fminf(fmaxf(fh, 0.f), 255.f);
+      // make sure the dequantised planes (evaluated as the traversal does) really enclose the child
+      const float base = k == 0 ? nlo.x : (k == 1 ? nlo.y : nlo.z);
+      const float cl = k == 0 ? lo[i].x : (k == 1 ? lo[i].y : lo[i].z), chh = k == 0 ? hi[i].x : (k == 1 ? hi[i].y : hi[i].z);
+      if (fl > 0.f && base + fl * scale > cl) fl -= 1.f;
+      if (fh < 255.f && base + fh * scale < chh) fh += 1.f;
+      ql[k] = (uint8_t)fl; qh[k] = (uint8_t)fh;
+    }
+    nd.qlox[s] = ql[0]; nd.qloy[s] = ql[1]; nd.qloz[s] = ql[2];
+    nd.qhix[s] = qh[0]; nd.qhiy[s] = qh[1]; nd.qhiz[s] = qh[2];
+    if (cnt[i] > LEAF_MAX) {
+      if (inner_rank < (uint32_t)n_inner) {
+        nd.imask |= (uint8_t)(1u << s);
+        nd.meta[s] = (uint8_t)((1u << 5) | (24u + s));
+        // publish the work item for the child wide node
+        const uint32_t cw = child_base + inner_rank;
+        __threadfence();
+        atomicExch(&a.queue[cw], (uint32_t)ch[i]);
+        ++inner_rank;
+      } else {
+        nd.meta[s] = 0;
+      }
+    } else {
+      const uint32_t unary = cnt[i] == 1 ? 1u : (cnt[i] == 2 ? 3u : 7u);
+      nd.meta[s] = (uint8_t)((unary << 5) | rec_off);
+      emit_leaf_records(a, (a.n == 1) ? 0 : ch[i], a.leaf_offset + rec_base + rec_off);
+      rec_off += cnt[i];
+    }
+  }
+  nd.ex = (uint8_t)be[0]; nd.ey = (uint8_t)be[1]; nd.ez = (uint8_t)be[2];
+  // 5 x 128-bit stores
+  const uint4* src = reinterpret_cast<const uint4*>(&nd);
+  uint4* dst = reinterpret_cast<uint4*>(a.nodes + a.node_offset + w);
+#pragma unroll
+  for (int k = 0; k < 5; ++k) dst[k] = src[k];
+  if (n_leafrec) {
+    __threadfence();
+    atomicAdd(&a.counters[C_DONE], (uint32_t)n_leafrec);
+  }
+}
+
+// thread w builds wide node w once its work item has been published by the thread that built its
+// parent (always a lower w). Lanes poll convergently, so producers in the same warp are never starved.
+__global__ void __launch_bounds__(128) k_collapse(CollapseArgs a) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= a.node_capacity) return;
+  bool done = false;
+  uint32_t spins = 0;
+  while (!done) {
+    const uint32_t b = *((volatile uint32_t*)&a.queue[w]);
+    if (b != EMPTY) {
+      __threadfence();
+      process_wide_node(a, w, (int)b);
+      done = true;
+    } else if (*((volatile uint32_t*)&a.counters[C_DONE]) >= (uint32_t)a.n || *((volatile uint32_t*)&a.counters[C_OVERFLOW])) {
+      done = true;
+    } else if (++spins > 64) {
+      __nanosleep(100);
+    }
+  }
+}
+
+template <class T>
+cudaError_t alloc(T*& p, size_t count) {
+  return cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
+}
+
+}  // namespace
+
+void scratch_free(BuildScratch& s) {
+  cudaFree(s.prim_lo); cudaFree(s.prim_hi);
+  for (int i = 0; i < 2; ++i) { cudaFree(s.keys[i]); cudaFree(s.vals[i]); }
+  cudaFree(s.block_hist); cudaFree(s.left); cudaFree(s.right); cudaFree(s.parent); cudaFree(s.first); cudaFree(s.last);
+  cudaFree(s.bb_lo); cudaFree(s.bb_hi); cudaFree(s.flags); cudaFree(s.queue); cudaFree(s.counters);
+  s = BuildScratch();
+}
+
+cudaError_t scratch_reserve(BuildScratch& s, uint32_t n) {
+  if (n <= s.capacity && s.capacity) return cudaSuccess;
+  scratch_free(s);
+  const size_t cap = n < 1024 ? 1024 : (size_t)n + n / 8;
+  cudaError_t e;
+  s.hist_blocks = (uint32_t)((cap + SORT_TILE - 1) / SORT_TILE);
+#define SNK_TRY(x) if ((e = (x)) != cudaSuccess) { scratch_free(s); return e; }
+  SNK_TRY(alloc(s.prim_lo, cap)); SNK_TRY(alloc(s.prim_hi, cap));
+  for (int i = 0; i < 2; ++i) { SNK_TRY(alloc(s.keys[i], cap)); SNK_TRY(alloc(s.vals[i], cap)); }
+  SNK_TRY(alloc(s.block_hist, (size_t)256 * s.hist_blocks));
+  SNK_TRY(alloc(s.left, cap)); SNK_TRY(alloc(s.right, cap)); SNK_TRY(alloc(s.parent, 2 * cap));
+  SNK_TRY(alloc(s.first, cap)); SNK_TRY(alloc(s.last, cap));
+  SNK_TRY(alloc(s.bb_lo, 2 * cap)); SNK_TRY(alloc(s.bb_hi, 2 * cap));
+  SNK_TRY(alloc(s.flags, cap)); SNK_TRY(alloc(s.queue, cap + 1)); SNK_TRY(alloc(s.counters, 16));
+#undef SNK_TRY
+  s.capacity = (uint32_t)cap;
+  return cudaSuccess;
+}
+
+void launch_triangle_bounds(BuildScratch& s, const float* positions, const uint32_t* indices, uint32_t index_offset,
+                            uint32_t vertex_offset, uint32_t n, cudaStream_t st) {
+  k_init<<<1, 32, 0, st>>>(s.counters, s.queue);
+  if (n) k_triangle_bounds<<<(n + 255) / 256, 256, 0, st>>>(positions, indices, index_offset, vertex_offset, n, s.prim_lo, s.prim_hi, s.counters);
+}
+
+void launch_instance_bounds(BuildScratch& s, const float* transforms_cm, const SnkInstanceData* inst,
+                            const uint32_t* blas_of_instance, const SnkBlasInfo* blas, const uint32_t* valid_slots, uint32_t n,
+                            cudaStream_t st) {
+  k_init<<<1, 32, 0, st>>>(s.counters, s.queue);
+  if (n) k_instance_bounds<<<(n + 255) / 256, 256, 0, st>>>(transforms_cm, inst, blas_of_instance, blas, valid_slots, n, s.prim_lo, s.prim_hi, s.counters);
+}
+
+int launch_build(BuildScratch& s, uint32_t n, const BuildOutput& out, const float* positions, const uint32_t* indices,
+                 uint32_t index_offset, uint32_t vertex_offset, cudaStream_t st) {
+  int launches = 0;
+  if (n == 0) return 0;
+  const uint32_t g = (n + 255) / 256;
+  k_morton<<<g, 256, 0, st>>>(s.prim_lo, s.prim_hi, n, s.counters, s.keys[0], s.vals[0]); ++launches;
+  int cur = 0;
+  if (n > 1) {
+    const uint32_t nb = (n + SORT_TILE - 1) / SORT_TILE;
+    for (int shift = 0; shift < 64; shift += 8) {
+      k_sort_hist<<<nb, SORT_THREADS, 0, st>>>(s.keys[cur], n, shift, s.block_hist, nb);
+      k_scan<<<1, 1024, 0, st>>>(s.block_hist, 256 * nb);
+      k_sort_scatter<<<nb, SORT_THREADS, 0, st>>>(s.keys[cur], s.vals[cur], n, shift, s.block_hist, nb, s.keys[cur ^ 1], s.vals[cur ^ 1]);
+      cur ^= 1;
+      launches += 3;
+    }
+    cudaMemsetAsync(s.flags, 0, sizeof(uint32_t) * n, st);
+    k_karras<<<g, 256, 0, st>>>(s.keys[cur], (int)n, s.left, s.right, s.parent, s.first, s.last); ++launches;
+  } else {
+    cudaMemsetAsync(s.parent, 0xFF, sizeof(int), st);  // parent[0] = -1: the only leaf is the root
+  }
+  k_refit_binary<<<g, 256, 0, st>>>(s.prim_lo, s.prim_hi, s.vals[cur], (int)n, s.left, s.right, s.parent, s.bb_lo, s.bb_hi, s.flags); ++launches;
+  // queue[0] = root was set by k_init; everything else starts EMPTY
+  const uint32_t cap = out.node_capacity < n ? out.node_capacity : n;
+  cudaMemsetAsync(s.queue + 1, 0xFF, sizeof(uint32_t) * cap, st);
+  CollapseArgs a;
+  a.n = (int)n; a.left = s.left; a.right = s.right; a.first = s.first; a.last = s.last; a.bb_lo = s.bb_lo; a.bb_hi = s.bb_hi;
+  a.sorted_prims = s.vals[cur]; a.queue = s.queue; a.counters = s.counters; a.nodes = out.nodes; a.node_offset = out.node_offset;
+  a.node_capacity = cap; a.tris = out.tris; a.leaf_ids = out.leaf_ids; a.leaf_remap = out.leaf_remap; a.leaf_offset = out.leaf_offset;
+  a.positions = positions; a.indices = indices; a.index_offset = index_offset; a.vertex_offset = vertex_offset;
+  k_collapse<<<(cap + 127) / 128, 128, 0, st>>>(a); ++launches;
+  return launches;
+}
+
+}  // namespace snk

@@ -1,0 +1,57 @@
+// bvh_build.cuh — interface of the sm_100a LBVH -> BVH8 builder (bvh_build.cu).
+//
+// Replaces the opaque driver builds of the reference:
+//   BLAS::GenerateFromMeshData  (Core/src/resources/TLAS.cpp:109-186, vkCmdBuildAccelerationStructuresKHR :178)
+//   TLAS::BuildFromInstances    (Core/src/resources/TLAS.cpp:10-87,  vkCmdBuildAccelerationStructuresKHR :74)
+// Pipeline: primitive AABBs + centroid bounds -> 63-bit Morton codes -> LSD radix
+// sort (8-bit digits, warp match ranking) -> Karras'12 hierarchy -> bottom-up AABB
+// refit with atomic arrival flags -> single-launch treelet collapse to 8-wide nodes
+// with quantised child boxes and octant-ordered slots (80-B nodes, 48-B triangles).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "layouts.h"
+
+namespace snk {
+
+struct BuildScratch {
+  uint32_t capacity = 0;                                // primitives this scratch is sized for
+  float4 *prim_lo = nullptr, *prim_hi = nullptr;        // primitive AABBs (input order)
+  unsigned long long* keys[2] = {nullptr, nullptr};     // Morton codes (ping-pong)
+  uint32_t* vals[2] = {nullptr, nullptr};               // primitive ids (ping-pong)
+  uint32_t* block_hist = nullptr;                        // 256 x hist_blocks digit counts
+  int *left = nullptr, *right = nullptr, *parent = nullptr;  // binary hierarchy: 2n-1 nodes, n-1 internal first
+  int *first = nullptr, *last = nullptr;                // sorted range of every internal node
+  float4 *bb_lo = nullptr, *bb_hi = nullptr;            // binary node boxes (2n-1)
+  uint32_t* flags = nullptr;                             // arrival counters (n-1)
+  uint32_t* queue = nullptr;                             // binary node handled by wide node w
+  uint32_t* counters = nullptr;                          // 16 words, see bvh_build.cu
+  uint32_t hist_blocks = 0;
+};
+
+cudaError_t scratch_reserve(BuildScratch& s, uint32_t n);
+void scratch_free(BuildScratch& s);
+
+struct BuildOutput {
+  SnkNode8* nodes;         // node pool base
+  uint32_t node_offset;    // absolute index of this hierarchy's root
+  uint32_t node_capacity;  // nodes available from node_offset
+  SnkTri* tris;            // triangle pool (BLAS builds) or nullptr
+  uint32_t* leaf_ids;      // leaf id list (TLAS builds) or nullptr
+  const uint32_t* leaf_remap;  // TLAS: primitive -> instance slot (nullptr = identity)
+  uint32_t leaf_offset;    // absolute index of the first free leaf record
+};
+
+// triangle AABBs of one submesh -> s.prim_lo / s.prim_hi (+ centroid bounds in s.counters)
+void launch_triangle_bounds(BuildScratch& s, const float* positions, const uint32_t* indices, uint32_t index_offset,
+                            uint32_t vertex_offset, uint32_t n, cudaStream_t st);
+// world AABBs of n instances (primitive i = slot valid_slots[i]) -> s.prim_lo / s.prim_hi
+void launch_instance_bounds(BuildScratch& s, const float* transforms_cm, const SnkInstanceData* inst,
+                            const uint32_t* blas_of_instance, const SnkBlasInfo* blas, const uint32_t* valid_slots, uint32_t n,
+                            cudaStream_t st);
+// generic build over s.prim_lo/hi. Returns the number of kernels launched. After completion s.counters[0] holds
+// the number of wide nodes written, s.counters[1] the number of leaf records, s.counters[4] an overflow flag.
+int launch_build(BuildScratch& s, uint32_t n, const BuildOutput& out, const float* positions, const uint32_t* indices,
+                 uint32_t index_offset, uint32_t vertex_offset, cudaStream_t st);
+
+}  // namespace snk

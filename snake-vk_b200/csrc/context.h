@@ -1,0 +1,132 @@
+// context.h — the per-GPU state behind the C ABI (include/snkpt.h).
+//
+// Mirrors what the reference spreads over RT (Raytracing.h:11-31), MeshBufferManager,
+// the scene buffer systems and EditorLayer's RaytracingResources: global SoA mesh
+// buffers, one wide BVH per submesh, instance / transform / material / light
+// mirrors, the TLAS, the G-buffer planes and the two reservoir halves.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "bvh_build.cuh"
+#include "layouts.h"
+#include "traverse.cuh"
+
+namespace snk {
+
+// growable device buffer (MeshBufferManager::Resize semantics: new buffer + device copy)
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t reserve(size_t need, bool keep, cudaStream_t st) {
+    if (need <= bytes) return cudaSuccess;
+    size_t nb = bytes ? bytes : 4096;
+    while (nb < need) nb += nb / 2 + 4096;
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, nb);
+    if (e != cudaSuccess) return e;
+    if (keep && p && bytes) {
+      e = cudaMemcpyAsync(q, p, bytes, cudaMemcpyDeviceToDevice, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    if (p) cudaFree(p);
+    p = q; bytes = nb;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct BlasSrc { uint32_t index_offset, vertex_offset, num_tris; };
+
+// per-frame constants handed to the kernels by value
+struct FrameConsts {
+  float ivp[16];        // inverse(view) * inverse(proj) hoisted (Util.glsl:3), float64 rounded once
+  float proj_view[16];
+  float prev_proj_view[16];
+  float cam_pos[3];
+  float time_elapsed, delta_time;
+  uint32_t frame_idx, prev_frame_invalid;
+  uint32_t W, H, row0, row1;
+  float jx, jy;
+};
+
+struct PixelPlanes {
+  // G-buffer (formats of EditorLayer.cpp:229-256)
+  char4* albedo; ushort4* normal; float* depth; ushort4* rma; ushort2* motion; uint16_t* flags;
+  ushort4* prev_normal; float* prev_depth;
+  // aux
+  uint32_t *prim, *inst; float* hit_t; float2* bary;
+  // reservoirs: 2 halves x 3 planes of 16 B (SoA); half 0 = final, half 1 = temporal
+  float4* res[2][3];
+  // images
+  float4 *radiance, *direct, *accum; ushort4* out16;
+};
+
+struct SceneDev {
+  const float *positions, *normals, *uvs;
+  const uint32_t* indices;
+  const SnkInstanceData* instances;
+  const float* transforms;       // mat4 column-major
+  const float* prev_transforms;
+  const float* normal_mats;      // 3x3 row-major (transpose(inverse(mat3(M)))), 12 floats stride
+  const float* det3;
+  const SnkMaterial* materials;
+  const SnkLightData* lights;
+  const uint32_t* emissive_idx;
+  uint32_t num_emissive, num_instances;
+};
+
+}  // namespace snk
+
+struct SnkPt {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint32_t W = 0, H = 0, row0 = 0, row1 = 0;
+  uint32_t max_instances = 4096, max_transforms = 4096, max_materials = 4096;
+
+  // mesh pools
+  snk::DevBuf positions, normals, tangents, uvs, indices;
+  uint32_t num_vertices = 0, num_indices = 0;
+  snk::DevBuf blas_nodes, blas_tris, d_blas;
+  uint32_t n_blas_nodes = 0, n_blas_tris = 0;
+  std::vector<SnkBlasInfo> blas;
+  std::vector<snk::BlasSrc> blas_src;
+  snk::BuildScratch scratch_blas, scratch_tlas;
+
+  // scene mirrors (host + device)
+  std::vector<SnkInstanceData> h_instances;
+  std::vector<uint32_t> h_blas_of_instance;
+  std::vector<float> h_transforms, h_prev_transforms;
+  uint32_t num_instances = 0, num_emissive = 0;
+  snk::DevBuf materials, lights, transforms, prev_transforms, normal_mats, det3, instances, blas_of_instance, emissive_idx;
+
+  // TLAS
+  snk::DevBuf tlas_nodes, tlas_leaf_ids, inst_recs, valid_slots;
+  uint32_t tlas_prims = 0;
+  bool tlas_built = false;
+
+  // per pixel
+  snk::DevBuf px[32];
+  snk::PixelPlanes planes{};
+  bool history_valid = false;
+  bool gbuffer_valid = false;
+  uint32_t accum_count = 0;
+
+  // frame
+  SnkCommonUBO ubo{}, prev_ubo{};
+  bool frame_set = false;
+  snk::FrameConsts fc{};
+
+  // generic ray query scratch
+  snk::DevBuf q_rays, q_hits, q_work;
+
+  SnkPtStats stats{};
+  cudaEvent_t ev[8] = {};
+
+  snk::TraceScene trace_scene() const;
+  snk::SceneDev scene_dev() const;
+};

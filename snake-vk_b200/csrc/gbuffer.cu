@@ -1,0 +1,105 @@
+// gbuffer.cu — primary visibility with camera rays.
+//
+// The reference rasterises its G-buffer (GBufferPass::RecordCommandBuffer,
+// Core/src/renderpasses/GBufferPass.cpp:70-196; GBuffer.vert:66-96; GBuffer.frag:41-72);
+// here one camera ray per pixel (Util.glsl:9-13 CalcRayDir) produces the same
+// quantities in the same storage formats (Editor/src/EditorLayer.cpp:229-256) plus
+// the primitive / instance ids the parity gate is read on. The prev-normal /
+// prev-depth blit (GBufferPass.cpp:73-77) is folded into the same kernel: each
+// thread moves its own texel to the prev planes before overwriting it.
+// Compiled with -fmad=false (see vecmath.cuh).
+#include "kernels.h"
+#include "vecmath.cuh"
+
+namespace snk {
+
+namespace {
+
+constexpr float PRIMARY_TMIN = 0.1f;  // CameraComponent.h:11 z_near
+constexpr float PRIMARY_TMAX = 10000.0f;
+
+__global__ void __launch_bounds__(128) k_primary(TraceScene S, SceneDev D, FrameConsts fc, PixelPlanes P) {
+  // 16x8 pixel tile per CTA, 8x4 per warp (coherent primary rays)
+  const uint32_t t = threadIdx.x, w = t >> 5, l = t & 31;
+  const uint32_t x = blockIdx.x * 16 + (w & 1) * 8 + (l & 7);
+  const uint32_t y = fc.row0 + blockIdx.y * 8 + (w >> 1) * 4 + (l >> 3);
+  if (x >= fc.W || y >= fc.row1) return;
+  const size_t px = (size_t)y * fc.W + x;
+  P.prev_normal[px] = P.normal[px];
+  P.prev_depth[px] = P.depth[px];
+
+  const float u = (((float)x + 0.5f) + fc.jx) / (float)fc.W, v = (((float)y + 0.5f) + fc.jy) / (float)fc.H;
+  const vec3 cam = v3(fc.cam_pos[0], fc.cam_pos[1], fc.cam_pos[2]);
+  const vec3 far = world_pos_from_depth(fc.ivp, 1.0f, u, v);
+  const vec3 d = normalize(far - cam);
+  HitRec h;
+  trace_ray<false>(S, cam.x, cam.y, cam.z, PRIMARY_TMIN, d.x, d.y, d.z, PRIMARY_TMAX, h);
+  P.prim[px] = h.prim; P.inst[px] = h.inst; P.hit_t[px] = h.t;
+  if (h.t < 0.0f) {
+    P.bary[px] = make_float2(0.f, 0.f);
+    P.albedo[px] = make_char4(0, 0, 0, 0);
+    P.normal[px] = make_ushort4(0, 0, 0, 0);
+    P.rma[px] = make_ushort4(0, 0, 0, 0);
+    P.depth[px] = 1.0f;
+    P.motion[px] = make_ushort2(0, 0);
+    P.flags[px] = 0;
+    return;
+  }
+  P.bary[px] = make_float2(h.u, h.v);
+  const SnkInstanceData in = D.instances[h.inst];
+  const uint32_t base = 3u * (h.prim + in.mesh_buffer_index_offset / 3u);
+  const uint32_t ia = D.indices[base] + in.mesh_buffer_vertex_offset, ib = D.indices[base + 1] + in.mesh_buffer_vertex_offset,
+                 ic = D.indices[base + 2] + in.mesh_buffer_vertex_offset;
+  const float b0 = (1.0f - h.u) - h.v, b1 = h.u, b2 = h.v;
+  const vec3 pa = v3(D.positions[3 * ia], D.positions[3 * ia + 1], D.positions[3 * ia + 2]);
+  const vec3 pb = v3(D.positions[3 * ib], D.positions[3 * ib + 1], D.positions[3 * ib + 2]);
+  const vec3 pc = v3(D.positions[3 * ic], D.positions[3 * ic + 1], D.positions[3 * ic + 2]);
+  const vec3 na = v3(D.normals[3 * ia], D.normals[3 * ia + 1], D.normals[3 * ia + 2]);
+  const vec3 nb = v3(D.normals[3 * ib], D.normals[3 * ib + 1], D.normals[3 * ib + 2]);
+  const vec3 nc = v3(D.normals[3 * ic], D.normals[3 * ic + 1], D.normals[3 * ic + 2]);
+  const vec3 p = (pa * b0 + pb * b1) + pc * b2;
+  const vec3 n0 = (na * b0 + nb * b1) + nc * b2;
+  const float* M = D.transforms + 16ull * in.transform_idx;
+  const vec3 world = mul_point(M, p);
+  const vec3 n = normalize(mul_mat3r(D.normal_mats + 9ull * in.transform_idx, n0));
+  const float4 clip = mul_vec4(fc.proj_view, world.x, world.y, world.z, 1.0f);
+  const vec3 pworld = mul_point(D.prev_transforms + 16ull * in.transform_idx, p);
+  const float4 pclip = mul_vec4(fc.prev_proj_view, pworld.x, pworld.y, pworld.z, 1.0f);
+  P.depth[px] = clip.z / clip.w;
+  const float mx = (pclip.x / pclip.w - clip.x / clip.w) * 0.5f, my = (pclip.y / pclip.w - clip.y / clip.w) * 0.5f;
+  P.motion[px] = make_ushort2(f2h(mx), f2h(my));
+  const SnkMaterial* m = D.materials + in.material_idx;
+  const float4 alb = *reinterpret_cast<const float4*>(m->albedo);
+  P.albedo[px] = make_char4(f2snorm8(alb.x), f2snorm8(alb.y), f2snorm8(alb.z), 127);
+  P.normal[px] = make_ushort4(f2h(n.x), f2h(n.y), f2h(n.z), f2h(1.0f));
+  P.rma[px] = make_ushort4(f2h(m->roughness), f2h(m->metallic), f2h(m->ao), f2h(1.0f));
+  P.flags[px] = (uint16_t)m->flags;
+}
+
+__global__ void k_accumulate(const float4* __restrict__ radiance, float4* __restrict__ accum, ushort4* __restrict__ out16,
+                             uint32_t npix, uint32_t count) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  const float4 r = radiance[i];
+  float4 a = count ? accum[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float inv = 1.0f / (float)(count + 1);
+  a.x += (r.x - a.x) * inv; a.y += (r.y - a.y) * inv; a.z += (r.z - a.z) * inv; a.w = 1.0f;
+  accum[i] = a;
+  out16[i] = make_ushort4(f2h(a.x), f2h(a.y), f2h(a.z), f2h(1.0f));
+}
+
+}  // namespace
+
+int launch_primary(const TraceScene& S, const SceneDev& D, const FrameConsts& fc, const PixelPlanes& P, cudaStream_t st) {
+  if (fc.row1 <= fc.row0) return 0;
+  dim3 grid((fc.W + 15) / 16, (fc.row1 - fc.row0 + 7) / 8);
+  k_primary<<<grid, 128, 0, st>>>(S, D, fc, P);
+  return 1;
+}
+
+int launch_accumulate(const PixelPlanes& P, uint32_t npix, uint32_t count, cudaStream_t st) {
+  k_accumulate<<<(npix + 255) / 256, 256, 0, st>>>(P.radiance, P.accum, P.out16, npix, count);
+  return 1;
+}
+
+}  // namespace snk

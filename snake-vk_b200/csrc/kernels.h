@@ -1,0 +1,24 @@
+// kernels.h — host-side launchers of the CUDA kernels (one .cu per stage).
+#pragma once
+#include "context.h"
+
+namespace snk {
+
+// trace.cu — wavefront traversal over a ray queue
+// rays: 2 x float4 per ray (o,tmin | d,tmax). hits_aos: SnkHit records (20 B) or nullptr;
+// hits_soa / inst_soa: float4 (t,u,v,prim) + u32 planes or nullptr.
+int launch_trace(const TraceScene& S, const float4* rays, uint64_t n, bool any, SnkHit* hits_aos, float4* hits_soa,
+                 uint32_t* inst_soa, cudaStream_t st);
+int launch_count_work(const TraceScene& S, const float4* rays, const SnkHit* hits, uint64_t n, bool any, uint32_t* out3,
+                      cudaStream_t st);
+
+// gbuffer.cu — primary visibility (replaces GBufferPass::RecordCommandBuffer, GBufferPass.cpp:70-196)
+int launch_primary(const TraceScene& S, const SceneDev& D, const FrameConsts& fc, const PixelPlanes& P, cudaStream_t st);
+
+// restir.cu / bounce.cu — RT::RecordRenderCmdBuf (Raytracing.cpp:227-267) in reference mode
+struct RenderCounters { unsigned long long rays_shadow, rays_secondary; };
+int launch_reference_frame(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st);
+int launch_northstar_frame(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st);
+int launch_accumulate(const PixelPlanes& P, uint32_t npix, uint32_t count, cudaStream_t st);
+
+}  // namespace snk

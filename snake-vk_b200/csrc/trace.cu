@@ -1,0 +1,121 @@
+// trace.cu — wavefront traversal kernels over ray queues in HBM.
+//
+// The generic ray query of the boundary (snkpt_trace_rays) and the secondary-ray
+// stages of the frame go through these kernels: a persistent grid (a multiple of
+// the 148 SMs) pulls rays from a 32-B/ray queue, traverses the two-level BVH8 and
+// writes 16-B hit records + a 4-B instance plane. Replaces the driver side of
+// vkCmdTraceRaysKHR (Core/src/rendering/Raytracing.cpp:253, :260).
+#include "kernels.h"
+
+namespace snk {
+
+namespace {
+
+constexpr int TRACE_THREADS = 128;
+
+template <bool ANY>
+__global__ void __launch_bounds__(TRACE_THREADS) k_trace(TraceScene S, const float4* __restrict__ rays, unsigned long long n,
+                                                         SnkHit* __restrict__ hits_aos, float4* __restrict__ hits_soa,
+                                                         uint32_t* __restrict__ inst_soa) {
+  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float4 a = __ldg(rays + 2 * i), b = __ldg(rays + 2 * i + 1);
+    HitRec h;
+    trace_ray<ANY>(S, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, h);
+    if (hits_aos) {
+      SnkHit o; o.t = h.t; o.u = h.u; o.v = h.v; o.prim = h.prim; o.inst = h.inst;
+      hits_aos[i] = o;
+    }
+    if (hits_soa) {
+      hits_soa[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+      inst_soa[i] = h.inst;
+    }
+  }
+}
+
+// Diagnostic (not on the hot path): traversal-order independent work of one ray = every wide node / leaf
+// record / instance whose (quantised, padded) box overlaps the segment [tmin, t_end], with
+// t_end = the reported hit distance, or tmax for a miss. Feeds the roofline's algorithmic bytes.
+__device__ void count_subtree(const RaySpace& r0, const uint4* __restrict__ nodes, uint32_t root, float tmin, float tend,
+                              uint32_t& n_nodes, uint32_t& leaf_bits_total, uint32_t* leaf_out, int& leaf_n, int leaf_cap) {
+  RaySpace r = r0;
+  r.octinv = 0;  // inner hit bits become 24 + slot
+  uint32_t st[64];
+  int sp = 0;
+  st[sp++] = root;
+  while (sp) {
+    const uint32_t ni = st[--sp];
+    uint4 n0, n1, n2, n3, n4;
+    load_node(nodes, ni, n0, n1, n2, n3, n4);
+    ++n_nodes;
+    const uint32_t hm = intersect_node(r, n0, n1, n2, n3, n4, tmin, tend);
+    const uint32_t imask = n0.w >> 24;
+    for (uint32_t s = 0; s < 8; ++s)
+      if (hm & (1u << (24 + s))) { if (sp < 64) st[sp++] = n1.x + __popc(imask & ((1u << s) - 1u)); }
+    uint32_t tb = hm & 0x00FFFFFFu;
+    leaf_bits_total += __popc(tb);
+    while (leaf_out && tb) {
+      const uint32_t bit = __ffs(tb) - 1;
+      tb &= tb - 1;
+      if (leaf_n < leaf_cap) leaf_out[leaf_n++] = n1.y + bit;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TRACE_THREADS) k_count_work(TraceScene S, const float4* __restrict__ rays,
+                                                              const SnkHit* __restrict__ hits, unsigned long long n,
+                                                              uint32_t* __restrict__ out3) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 a = __ldg(rays + 2 * i), b = __ldg(rays + 2 * i + 1);
+  const float tend = hits[i].t >= 0.f ? hits[i].t : b.w;
+  uint32_t nodes = 0, recs = 0, insts = 0;
+  if (S.tlas_node_count) {
+    RaySpace r;
+    setup_ray_space(r, a.x, a.y, a.z, b.x, b.y, b.z);
+    // pass 1: TLAS, collecting the leaf records (instances) the segment overlaps, 64 at a time
+    uint32_t leaf[64];
+    int ln = 0;
+    uint32_t dummy = 0;
+    count_subtree(r, S.tlas_nodes, 0u, a.w, tend, nodes, dummy, leaf, ln, 64);
+    insts = dummy;
+    for (int k = 0; k < ln; ++k) {
+      const uint32_t slot = S.tlas_leaf_ids[leaf[k]];
+      const float4* M = reinterpret_cast<const float4*>(S.inst + slot);
+      const float4 r0 = M[0], r1 = M[1], r2 = M[2];
+      RaySpace o;
+      setup_ray_space(o, r0.x * a.x + r0.y * a.y + r0.z * a.z + r0.w, r1.x * a.x + r1.y * a.y + r1.z * a.z + r1.w,
+                      r2.x * a.x + r2.y * a.y + r2.z * a.z + r2.w, r0.x * b.x + r0.y * b.y + r0.z * b.z,
+                      r1.x * b.x + r1.y * b.y + r1.z * b.z, r2.x * b.x + r2.y * b.y + r2.z * b.z);
+      int unused = 0;
+      count_subtree(o, S.blas_nodes, S.inst[slot].blas_root, a.w, tend, nodes, recs, nullptr, unused, 0);
+    }
+  }
+  out3[3 * i] = nodes; out3[3 * i + 1] = recs; out3[3 * i + 2] = insts;
+}
+
+}  // namespace
+
+static int trace_grid(uint64_t n) {
+  const uint64_t blocks = (n + TRACE_THREADS - 1) / TRACE_THREADS;
+  const uint64_t persistent = 148ull * 8ull;
+  return (int)(blocks < persistent ? (blocks ? blocks : 1) : persistent);
+}
+
+int launch_trace(const TraceScene& S, const float4* rays, uint64_t n, bool any, SnkHit* hits_aos, float4* hits_soa,
+                 uint32_t* inst_soa, cudaStream_t st) {
+  if (n == 0) return 0;
+  if (any) k_trace<true><<<trace_grid(n), TRACE_THREADS, 0, st>>>(S, rays, n, hits_aos, hits_soa, inst_soa);
+  else k_trace<false><<<trace_grid(n), TRACE_THREADS, 0, st>>>(S, rays, n, hits_aos, hits_soa, inst_soa);
+  return 1;
+}
+
+int launch_count_work(const TraceScene& S, const float4* rays, const SnkHit* hits, uint64_t n, bool any, uint32_t* out3,
+                      cudaStream_t st) {
+  (void)any;
+  if (n == 0) return 0;
+  k_count_work<<<(unsigned)((n + TRACE_THREADS - 1) / TRACE_THREADS), TRACE_THREADS, 0, st>>>(S, rays, hits, n, out3);
+  return 1;
+}
+
+}  // namespace snk

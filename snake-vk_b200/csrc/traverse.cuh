@@ -1,0 +1,243 @@
+// traverse.cuh — two-level BVH8 traversal + watertight ray/triangle test (device code).
+//
+// Replaces the driver side of every traceRayEXT the reference issues
+// (RayGen.rgen:101-121 ShadowTest, :164-176 / :195-207 closest-hit rays,
+// RayClosestHit.rchit:64-84) and vkCmdTraceRaysKHR's traversal
+// (Core/src/rendering/Raytracing.cpp:253, :260). Semantics pinned to the Vulkan
+// ray-tracing contract the shaders rely on: closest hit with tmin < t < tmax,
+// watertight shared edges, no culling, barycentrics = weights of v1, v2;
+// equal-t ties resolve to the lowest (instance, primitive).
+//
+// The triangle test is written with explicit round-to-nearest intrinsics (never
+// contracted to FMA) so that its results are bit-identical to the CPU oracle's
+// restatement; the box tests use FMA and a relative pad and only need to be
+// conservative.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "layouts.h"
+
+namespace snk {
+
+struct TraceScene {
+  const uint4* tlas_nodes;        // 5 x uint4 per node, root at index 0
+  const uint32_t* tlas_leaf_ids;  // instance slot per TLAS leaf record
+  const uint4* blas_nodes;        // node pool of all BLASes
+  const float4* tris;             // 3 x float4 per triangle record
+  const SnkInstRec* inst;         // indexed by instance slot
+  uint32_t tlas_node_count;       // 0 = nothing to hit
+};
+
+struct HitRec {
+  float t, u, v;
+  uint32_t prim, inst;
+};
+
+constexpr int TRAV_STACK = 64;
+constexpr uint32_t TRAV_SENTINEL = 0xFFFFFFFFu;
+constexpr float BOX_PAD = 1.000004f;
+
+struct RaySpace {
+  float ox, oy, oz;
+  float dx, dy, dz;
+  float idx, idy, idz;  // 1 / clamped direction
+  float Sx, Sy, Sz;     // Woop shear constants
+  int kx, ky, kz;
+  uint32_t octinv;
+};
+
+__device__ __forceinline__ float sel3(float x, float y, float z, int k) { return k == 0 ? x : (k == 1 ? y : z); }
+
+__device__ __forceinline__ void setup_ray_space(RaySpace& r, float ox, float oy, float oz, float dx, float dy, float dz) {
+  r.ox = ox; r.oy = oy; r.oz = oz; r.dx = dx; r.dy = dy; r.dz = dz;
+  const float cx = fabsf(dx) > 1e-20f ? dx : copysignf(1e-20f, dx);
+  const float cy = fabsf(dy) > 1e-20f ? dy : copysignf(1e-20f, dy);
+  const float cz = fabsf(dz) > 1e-20f ? dz : copysignf(1e-20f, dz);
+  r.idx = 1.0f / cx; r.idy = 1.0f / cy; r.idz = 1.0f / cz;
+  const uint32_t oct = (r.idx < 0.f ? 1u : 0u) | (r.idy < 0.f ? 2u : 0u) | (r.idz < 0.f ? 4u : 0u);
+  r.octinv = 7u - oct;
+  // Woop et al. 2013: dominant axis + shear (bit-identical to oracle/snk_scene.h ray_pre)
+  const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+  int kz = 0;
+  if (ay > ax) kz = 1;
+  if (az > (kz == 0 ? ax : ay)) kz = 2;
+  int kx = kz + 1; if (kx == 3) kx = 0;
+  int ky = kx + 1; if (ky == 3) ky = 0;
+  const float dkz = sel3(dx, dy, dz, kz);
+  if (dkz < 0.0f) { const int t = kx; kx = ky; ky = t; }
+  r.kx = kx; r.ky = ky; r.kz = kz;
+  r.Sx = __fdiv_rn(sel3(dx, dy, dz, kx), dkz);
+  r.Sy = __fdiv_rn(sel3(dx, dy, dz, ky), dkz);
+  r.Sz = __fdiv_rn(1.0f, dkz);
+}
+
+// returns true when the line hits the triangle; (t,u,v) valid then. No range test.
+__device__ __forceinline__ bool tri_test(const RaySpace& r, float4 p0, float4 p1, float4 p2, float& t, float& u, float& v) {
+  const float Ax0 = __fsub_rn(p0.x, r.ox), Ay0 = __fsub_rn(p0.y, r.oy), Az0 = __fsub_rn(p0.z, r.oz);
+  const float Bx0 = __fsub_rn(p1.x, r.ox), By0 = __fsub_rn(p1.y, r.oy), Bz0 = __fsub_rn(p1.z, r.oz);
+  const float Cx0 = __fsub_rn(p2.x, r.ox), Cy0 = __fsub_rn(p2.y, r.oy), Cz0 = __fsub_rn(p2.z, r.oz);
+  const float Akz = sel3(Ax0, Ay0, Az0, r.kz), Bkz = sel3(Bx0, By0, Bz0, r.kz), Ckz = sel3(Cx0, Cy0, Cz0, r.kz);
+  const float Ax = __fsub_rn(sel3(Ax0, Ay0, Az0, r.kx), __fmul_rn(r.Sx, Akz)), Ay = __fsub_rn(sel3(Ax0, Ay0, Az0, r.ky), __fmul_rn(r.Sy, Akz));
+  const float Bx = __fsub_rn(sel3(Bx0, By0, Bz0, r.kx), __fmul_rn(r.Sx, Bkz)), By = __fsub_rn(sel3(Bx0, By0, Bz0, r.ky), __fmul_rn(r.Sy, Bkz));
+  const float Cx = __fsub_rn(sel3(Cx0, Cy0, Cz0, r.kx), __fmul_rn(r.Sx, Ckz)), Cy = __fsub_rn(sel3(Cx0, Cy0, Cz0, r.ky), __fmul_rn(r.Sy, Ckz));
+  float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
+  float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
+  float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));
+  if (U == 0.0f || V == 0.0f || W == 0.0f) {
+    const double CxBy = __dmul_rn((double)Cx, (double)By), CyBx = __dmul_rn((double)Cy, (double)Bx);
+    U = (float)__dsub_rn(CxBy, CyBx);
+    const double AxCy = __dmul_rn((double)Ax, (double)Cy), AyCx = __dmul_rn((double)Ay, (double)Cx);
+    V = (float)__dsub_rn(AxCy, AyCx);
+    const double BxAy = __dmul_rn((double)Bx, (double)Ay), ByAx = __dmul_rn((double)By, (double)Ax);
+    W = (float)__dsub_rn(BxAy, ByAx);
+  }
+  if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+  const float det = __fadd_rn(__fadd_rn(U, V), W);
+  if (det == 0.0f) return false;
+  const float Az = __fmul_rn(r.Sz, Akz), Bz = __fmul_rn(r.Sz, Bkz), Cz = __fmul_rn(r.Sz, Ckz);
+  const float T = __fadd_rn(__fadd_rn(__fmul_rn(U, Az), __fmul_rn(V, Bz)), __fmul_rn(W, Cz));
+  const float rcp = __fdiv_rn(1.0f, det);
+  t = __fmul_rn(T, rcp);
+  u = __fmul_rn(V, rcp);
+  v = __fmul_rn(W, rcp);
+  return true;
+}
+
+__device__ __forceinline__ uint32_t byte_of(uint32_t lo_word, uint32_t hi_word, int s) {
+  return ((s < 4 ? lo_word : hi_word) >> ((s & 3) * 8)) & 0xFFu;
+}
+
+// intersect the 8 quantised child boxes of one node; returns the hit mask
+// (bits 24..31: inner children in octant order, bits 0..23: leaf records)
+__device__ __forceinline__ uint32_t intersect_node(const RaySpace& r, const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3,
+                                                   const uint4 n4, float tmin, float tmax) {
+  const float px = __uint_as_float(n0.x), py = __uint_as_float(n0.y), pz = __uint_as_float(n0.z);
+  const float sx = __uint_as_float((n0.w & 0xFFu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23),
+              sz = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23);
+  const float ax = sx * r.idx, ay = sy * r.idy, az = sz * r.idz;
+  const float bx = (px - r.ox) * r.idx, by = (py - r.oy) * r.idy, bz = (pz - r.oz) * r.idz;
+  // near / far plane words per axis
+  const bool nx = r.idx < 0.f, ny = r.idy < 0.f, nz = r.idz < 0.f;
+  const uint32_t xn0 = nx ? n3.z : n2.x, xn1 = nx ? n3.w : n2.y, xf0 = nx ? n2.x : n3.z, xf1 = nx ? n2.y : n3.w;
+  const uint32_t yn0 = ny ? n4.x : n2.z, yn1 = ny ? n4.y : n2.w, yf0 = ny ? n2.z : n4.x, yf1 = ny ? n2.w : n4.y;
+  const uint32_t zn0 = nz ? n4.z : n3.x, zn1 = nz ? n4.w : n3.y, zf0 = nz ? n3.x : n4.z, zf1 = nz ? n3.y : n4.w;
+  uint32_t hitmask = 0;
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    const uint32_t meta = byte_of(n1.z, n1.w, s);
+    if (meta == 0) continue;
+    const float tx0 = fmaf((float)byte_of(xn0, xn1, s), ax, bx), tx1 = fmaf((float)byte_of(xf0, xf1, s), ax, bx);
+    const float ty0 = fmaf((float)byte_of(yn0, yn1, s), ay, by), ty1 = fmaf((float)byte_of(yf0, yf1, s), ay, by);
+    const float tz0 = fmaf((float)byte_of(zn0, zn1, s), az, bz), tz1 = fmaf((float)byte_of(zf0, zf1, s), az, bz);
+    const float tn = fmaxf(fmaxf(tx0, ty0), fmaxf(tz0, tmin));
+    const float tf = fminf(fminf(tx1, ty1), fminf(tz1, tmax));
+    if (tn <= tf * BOX_PAD) {
+      const uint32_t idx = meta & 0x1Fu;
+      if ((meta & 0x18u) == 0x18u) hitmask |= 1u << (idx ^ r.octinv);  // inner: 24 + (slot ^ octinv)
+      else hitmask |= (meta >> 5) << idx;                               // leaf: unary count at its record offset
+    }
+  }
+  return hitmask;
+}
+
+__device__ __forceinline__ void load_node(const uint4* __restrict__ nodes, uint32_t idx, uint4& n0, uint4& n1, uint4& n2, uint4& n3,
+                                          uint4& n4) {
+  const uint4* p = nodes + 5ull * idx;
+  n0 = __ldg(p); n1 = __ldg(p + 1); n2 = __ldg(p + 2); n3 = __ldg(p + 3); n4 = __ldg(p + 4);
+}
+
+// ANY: return on the first valid hit (gl_RayFlagsTerminateOnFirstHitEXT)
+template <bool ANY>
+__device__ __forceinline__ void trace_ray(const TraceScene& S, float ox, float oy, float oz, float tmin, float dx, float dy, float dz,
+                                          float tmax, HitRec& best) {
+  best.t = -1.0f; best.u = 0.f; best.v = 0.f; best.prim = 0xFFFFFFFFu; best.inst = 0xFFFFFFFFu;
+  if (S.tlas_node_count == 0) return;
+  float tcur = tmax;  // shrinks to the closest hit found so far
+  RaySpace r;
+  setup_ray_space(r, ox, oy, oz, dx, dy, dz);
+  uint2 stack[TRAV_STACK];
+  int sp = 0;
+  bool in_blas = false;
+  uint32_t cur_inst = 0;
+  const uint4* nodes = S.tlas_nodes;
+  uint2 G = make_uint2(0u, 0x80000000u);
+  while (true) {
+    uint2 T = make_uint2(0u, 0u);
+    if (G.y & 0xFF000000u) {
+      const uint32_t hits_imask = G.y;
+      const uint32_t bit = 31u - __clz(hits_imask);
+      G.y &= ~(1u << bit);
+      if (G.y & 0xFF000000u) { if (sp < TRAV_STACK) stack[sp++] = G; }
+      const uint32_t slot = (bit - 24u) ^ r.octinv;
+      const uint32_t rel = __popc(hits_imask & ~(0xFFFFFFFFu << slot) & 0xFFu);
+      uint4 n0, n1, n2, n3, n4;
+      load_node(nodes, G.x + rel, n0, n1, n2, n3, n4);
+      const uint32_t hm = intersect_node(r, n0, n1, n2, n3, n4, tmin, tcur);
+      G = make_uint2(n1.x, (hm & 0xFF000000u) | (n0.w >> 24));
+      T = make_uint2(n1.y, hm & 0x00FFFFFFu);
+    } else {
+      T = G;
+      G = make_uint2(0u, 0u);
+    }
+    while (T.y) {
+      const uint32_t bit = __ffs(T.y) - 1;
+      T.y &= ~(1u << bit);
+      if (!in_blas) {
+        // TLAS leaf record → enter the instance
+        const uint32_t slot = __ldg(S.tlas_leaf_ids + T.x + bit);
+        if (T.y && sp < TRAV_STACK) stack[sp++] = T;
+        if ((G.y & 0xFF000000u) && sp < TRAV_STACK) stack[sp++] = G;
+        if (sp < TRAV_STACK) stack[sp++] = make_uint2(TRAV_SENTINEL, 0u);
+        const float4* M = reinterpret_cast<const float4*>(S.inst + slot);
+        const float4 r0 = __ldg(M), r1 = __ldg(M + 1), r2 = __ldg(M + 2);
+        const uint4 meta = __ldg(reinterpret_cast<const uint4*>(M + 3));
+        // o' = ((m0*x + m1*y) + m2*z) + m3 ; d' = (m0*x + m1*y) + m2*z   (unfused, as the oracle)
+        const float oox = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0.x, ox), __fmul_rn(r0.y, oy)), __fmul_rn(r0.z, oz)), r0.w);
+        const float ooy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r1.x, ox), __fmul_rn(r1.y, oy)), __fmul_rn(r1.z, oz)), r1.w);
+        const float ooz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2.x, ox), __fmul_rn(r2.y, oy)), __fmul_rn(r2.z, oz)), r2.w);
+        const float odx = __fadd_rn(__fadd_rn(__fmul_rn(r0.x, dx), __fmul_rn(r0.y, dy)), __fmul_rn(r0.z, dz));
+        const float ody = __fadd_rn(__fadd_rn(__fmul_rn(r1.x, dx), __fmul_rn(r1.y, dy)), __fmul_rn(r1.z, dz));
+        const float odz = __fadd_rn(__fadd_rn(__fmul_rn(r2.x, dx), __fmul_rn(r2.y, dy)), __fmul_rn(r2.z, dz));
+        setup_ray_space(r, oox, ooy, ooz, odx, ody, odz);
+        in_blas = true;
+        cur_inst = meta.y;
+        nodes = S.blas_nodes;
+        G = make_uint2(meta.x, 0x80000000u);
+        T = make_uint2(0u, 0u);
+        break;
+      }
+      const float4* tp = S.tris + 3ull * (T.x + bit);
+      const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
+      float t, u, v;
+      if (tri_test(r, p0, p1, p2, t, u, v) && t > tmin && t < tmax) {
+        const uint32_t prim = __float_as_uint(p0.w);
+        bool take;
+        if (ANY) take = true;
+        else take = best.t < 0.0f || t < best.t || (t == best.t && (cur_inst < best.inst || (cur_inst == best.inst && prim < best.prim)));
+        if (take) {
+          best.t = t; best.u = u; best.v = v; best.prim = prim; best.inst = cur_inst;
+          if (ANY) return;
+          tcur = t;
+        }
+      }
+    }
+    if ((G.y & 0xFF000000u) == 0u) {
+      bool finished = false;
+      while (true) {
+        if (sp == 0) { finished = true; break; }
+        G = stack[--sp];
+        if (G.x == TRAV_SENTINEL) {
+          setup_ray_space(r, ox, oy, oz, dx, dy, dz);
+          in_blas = false;
+          nodes = S.tlas_nodes;
+          G = make_uint2(0u, 0u);
+          continue;
+        }
+        break;
+      }
+      if (finished) break;
+    }
+  }
+}
+
+}  // namespace snk
