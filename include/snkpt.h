@@ -234,7 +234,8 @@ typedef struct SnkPtStats {
   uint64_t blas_nodes, blas_tris, tlas_nodes;
   float ms_primary, ms_restir1, ms_restir2, ms_bounce, ms_total; /* CUDA events of last frame */
   float ms_build_last;       /* last BLAS / TLAS build                            */
-  uint32_t reserved[8];
+  uint32_t stack_overflows;  /* traversal-stack overflows since create (must be 0) */
+  uint32_t reserved[7];
 } SnkPtStats;
 
 typedef struct SnkBlasInfo {

@@ -79,7 +79,7 @@ SETTINGS_DTYPE = np.dtype([("num_temporal", "<i4"), ("num_spatial", "<i4"), ("mo
 STATS_DTYPE = np.dtype([("rays_primary", "<u8"), ("rays_shadow", "<u8"), ("rays_secondary", "<u8"), ("kernel_launches", "<u8"),
                         ("blas_nodes", "<u8"), ("blas_tris", "<u8"), ("tlas_nodes", "<u8"), ("ms_primary", "<f4"),
                         ("ms_restir1", "<f4"), ("ms_restir2", "<f4"), ("ms_bounce", "<f4"), ("ms_total", "<f4"),
-                        ("ms_build_last", "<f4"), ("reserved", "<u4", (8,))])
+                        ("ms_build_last", "<f4"), ("stack_overflows", "<u4"), ("reserved", "<u4", (7,))])
 SUBMESH_DTYPE = np.dtype([("num_indices", "<u4"), ("num_vertices", "<u4"), ("base_vertex", "<u4"), ("base_index", "<u4"),
                           ("material_index", "<u4")])
 MESH_ENTRY_DTYPE = np.dtype([("data_start_indices_idx", "<u4"), ("data_start_vertex_idx", "<u4"), ("num_submeshes", "<u4"),

@@ -84,6 +84,7 @@ TraceScene SnkPt::trace_scene() const {
   S.blas_nodes = blas_nodes.as<uint4>();
   S.tris = blas_tris.as<float4>();
   S.inst = inst_recs.as<SnkInstRec>();
+  S.overflow = dev_counters.as<uint32_t>();
   S.tlas_node_count = (tlas_built && tlas_prims) ? 1u : 0u;
   return S;
 }
@@ -172,6 +173,8 @@ int snkpt_create(const SnkPtConfig* cfg, SnkPt** out) {
     if (e2 == cudaSuccess) e2 = cudaMemsetAsync(ctx->lights.p, 0, sizeof(SnkLightData), ctx->stream);
     if (e2 == cudaSuccess) e2 = ctx->materials.reserve(sizeof(SnkMaterial) * ctx->max_materials, false, ctx->stream);
     if (e2 == cudaSuccess) e2 = cudaMemsetAsync(ctx->materials.p, 0, sizeof(SnkMaterial) * ctx->max_materials, ctx->stream);
+    if (e2 == cudaSuccess) e2 = ctx->dev_counters.reserve(256, false, ctx->stream);
+    if (e2 == cudaSuccess) e2 = cudaMemsetAsync(ctx->dev_counters.p, 0, 256, ctx->stream);
     if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(ctx->stream);
     if (e2 != cudaSuccess) { ctx->err = cudaGetErrorString(e2); rc = SNKPT_E_CUDA; }
   }
@@ -187,7 +190,7 @@ void snkpt_destroy(SnkPt* ctx) {
   DevBuf* bufs[] = {&ctx->positions, &ctx->normals, &ctx->tangents, &ctx->uvs, &ctx->indices, &ctx->blas_nodes, &ctx->blas_tris,
                     &ctx->d_blas, &ctx->materials, &ctx->lights, &ctx->transforms, &ctx->prev_transforms, &ctx->normal_mats,
                     &ctx->det3, &ctx->instances, &ctx->blas_of_instance, &ctx->emissive_idx, &ctx->tlas_nodes, &ctx->tlas_leaf_ids,
-                    &ctx->inst_recs, &ctx->valid_slots, &ctx->q_rays, &ctx->q_hits, &ctx->q_work};
+                    &ctx->inst_recs, &ctx->valid_slots, &ctx->q_rays, &ctx->q_hits, &ctx->q_work, &ctx->dev_counters};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : ctx->px) b.release();
   scratch_free(ctx->scratch_blas);
@@ -688,6 +691,9 @@ int snkpt_get_stats(SnkPt* ctx, SnkPtStats* out) {
   if (!ctx || !out) return SNKPT_E_INVALID;
   cudaSetDevice(ctx->device);
   if (ctx->gbuffer_valid && cudaEventQuery(ctx->ev[1]) == cudaSuccess) cudaEventElapsedTime(&ctx->stats.ms_primary, ctx->ev[0], ctx->ev[1]);
+  uint32_t c[4] = {0, 0, 0, 0};
+  if (cudaStreamSynchronize(ctx->stream) == cudaSuccess && cudaMemcpy(c, ctx->dev_counters.p, sizeof(c), cudaMemcpyDeviceToHost) == cudaSuccess)
+    ctx->stats.stack_overflows = c[0];
   *out = ctx->stats;
   return SNKPT_OK;
 }

@@ -123,6 +123,7 @@ struct SnkPt {
 
   // generic ray query scratch
   snk::DevBuf q_rays, q_hits, q_work;
+  snk::DevBuf dev_counters;  // [0] traversal stack overflows, [1] shadow rays, [2..3] secondary rays (u64)
 
   SnkPtStats stats{};
   cudaEvent_t ev[8] = {};

@@ -20,6 +20,7 @@ constexpr float PRIMARY_TMAX = 10000.0f;
 
 __global__ void __launch_bounds__(128) k_primary(TraceScene S, SceneDev D, FrameConsts fc, PixelPlanes P) {
   // 16x8 pixel tile per CTA, 8x4 per warp (coherent primary rays)
+  SNK_DECLARE_TRAV_STACK(128);
   const uint32_t t = threadIdx.x, w = t >> 5, l = t & 31;
   const uint32_t x = blockIdx.x * 16 + (w & 1) * 8 + (l & 7);
   const uint32_t y = fc.row0 + blockIdx.y * 8 + (w >> 1) * 4 + (l >> 3);
@@ -33,7 +34,7 @@ __global__ void __launch_bounds__(128) k_primary(TraceScene S, SceneDev D, Frame
   const vec3 far = world_pos_from_depth(fc.ivp, 1.0f, u, v);
   const vec3 d = normalize(far - cam);
   HitRec h;
-  trace_ray<false>(S, cam.x, cam.y, cam.z, PRIMARY_TMIN, d.x, d.y, d.z, PRIMARY_TMAX, h);
+  trace_ray<false, 128>(S, cam.x, cam.y, cam.z, PRIMARY_TMIN, d.x, d.y, d.z, PRIMARY_TMAX, snk_trav_stack + t, h);
   P.prim[px] = h.prim; P.inst[px] = h.inst; P.hit_t[px] = h.t;
   if (h.t < 0.0f) {
     P.bary[px] = make_float2(0.f, 0.f);

@@ -17,11 +17,13 @@ template <bool ANY>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace(TraceScene S, const float4* __restrict__ rays, unsigned long long n,
                                                          SnkHit* __restrict__ hits_aos, float4* __restrict__ hits_soa,
                                                          uint32_t* __restrict__ inst_soa) {
+  SNK_DECLARE_TRAV_STACK(TRACE_THREADS);
+  uint2* stk = snk_trav_stack + threadIdx.x;
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
   for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float4 a = __ldg(rays + 2 * i), b = __ldg(rays + 2 * i + 1);
     HitRec h;
-    trace_ray<ANY>(S, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, h);
+    trace_ray<ANY, TRACE_THREADS>(S, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, stk, h);
     if (hits_aos) {
       SnkHit o; o.t = h.t; o.u = h.u; o.v = h.v; o.prim = h.prim; o.inst = h.inst;
       hits_aos[i] = o;

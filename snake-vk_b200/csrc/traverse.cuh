@@ -25,6 +25,7 @@ struct TraceScene {
   const uint4* blas_nodes;        // node pool of all BLASes
   const float4* tris;             // 3 x float4 per triangle record
   const SnkInstRec* inst;         // indexed by instance slot
+  uint32_t* overflow;             // device counter: traversal stack overflows (must stay 0)
   uint32_t tlas_node_count;       // 0 = nothing to hit
 };
 
@@ -33,8 +34,14 @@ struct HitRec {
   uint32_t prim, inst;
 };
 
-constexpr int TRAV_STACK = 64;
+// Traversal stack: TRAV_STACK 8-byte entries per thread, kept in SHARED memory and interleaved by thread
+// (entry e of thread t lives at stk[e * STRIDE], STRIDE = CTA size) so a warp's pushes / pops are
+// conflict-free 64-bit accesses. Deliberately not a local-memory array: ptxas keeps the local-frame base
+// in a uniform register across the divergent traversal loop, and lanes that leave the loop early were
+// observed (compute-sanitizer, k_primary on C2) to overwrite that register while others still traverse.
+constexpr int TRAV_STACK = 32;
 constexpr uint32_t TRAV_SENTINEL = 0xFFFFFFFFu;
+#define SNK_DECLARE_TRAV_STACK(threads) __shared__ uint2 snk_trav_stack[snk::TRAV_STACK * (threads)]
 constexpr float BOX_PAD = 1.000004f;
 
 struct RaySpace {
@@ -147,15 +154,20 @@ __device__ __forceinline__ void load_node(const uint4* __restrict__ nodes, uint3
 }
 
 // ANY: return on the first valid hit (gl_RayFlagsTerminateOnFirstHitEXT)
-template <bool ANY>
+#define SNK_PUSH(val)                                              \
+  do {                                                             \
+    if (sp < TRAV_STACK) stk[(sp++) * STRIDE] = (val);             \
+    else atomicAdd(S.overflow, 1u);                                \
+  } while (0)
+
+template <bool ANY, int STRIDE>
 __device__ __forceinline__ void trace_ray(const TraceScene& S, float ox, float oy, float oz, float tmin, float dx, float dy, float dz,
-                                          float tmax, HitRec& best) {
+                                          float tmax, uint2* __restrict__ stk, HitRec& best) {
   best.t = -1.0f; best.u = 0.f; best.v = 0.f; best.prim = 0xFFFFFFFFu; best.inst = 0xFFFFFFFFu;
   if (S.tlas_node_count == 0) return;
   float tcur = tmax;  // shrinks to the closest hit found so far
   RaySpace r;
   setup_ray_space(r, ox, oy, oz, dx, dy, dz);
-  uint2 stack[TRAV_STACK];
   int sp = 0;
   bool in_blas = false;
   uint32_t cur_inst = 0;
@@ -167,7 +179,7 @@ __device__ __forceinline__ void trace_ray(const TraceScene& S, float ox, float o
       const uint32_t hits_imask = G.y;
       const uint32_t bit = 31u - __clz(hits_imask);
       G.y &= ~(1u << bit);
-      if (G.y & 0xFF000000u) { if (sp < TRAV_STACK) stack[sp++] = G; }
+      if (G.y & 0xFF000000u) SNK_PUSH(G);
       const uint32_t slot = (bit - 24u) ^ r.octinv;
       const uint32_t rel = __popc(hits_imask & ~(0xFFFFFFFFu << slot) & 0xFFu);
       uint4 n0, n1, n2, n3, n4;
@@ -185,9 +197,9 @@ __device__ __forceinline__ void trace_ray(const TraceScene& S, float ox, float o
       if (!in_blas) {
         // TLAS leaf record → enter the instance
         const uint32_t slot = __ldg(S.tlas_leaf_ids + T.x + bit);
-        if (T.y && sp < TRAV_STACK) stack[sp++] = T;
-        if ((G.y & 0xFF000000u) && sp < TRAV_STACK) stack[sp++] = G;
-        if (sp < TRAV_STACK) stack[sp++] = make_uint2(TRAV_SENTINEL, 0u);
+        if (T.y) SNK_PUSH(T);
+        if (G.y & 0xFF000000u) SNK_PUSH(G);
+        SNK_PUSH(make_uint2(TRAV_SENTINEL, 0u));
         const float4* M = reinterpret_cast<const float4*>(S.inst + slot);
         const float4 r0 = __ldg(M), r1 = __ldg(M + 1), r2 = __ldg(M + 2);
         const uint4 meta = __ldg(reinterpret_cast<const uint4*>(M + 3));
@@ -225,7 +237,7 @@ __device__ __forceinline__ void trace_ray(const TraceScene& S, float ox, float o
       bool finished = false;
       while (true) {
         if (sp == 0) { finished = true; break; }
-        G = stack[--sp];
+        G = stk[(--sp) * STRIDE];
         if (G.x == TRAV_SENTINEL) {
           setup_ray_space(r, ox, oy, oz, dx, dy, dz);
           in_blas = false;

@@ -86,7 +86,7 @@ def test_empty_and_degenerate_inputs(snk):
     assert h["t"][0] > 0 and h["t"][1] < 0 and h["t"][2] < 0
     # tmax before the wall → miss; tmin beyond it → miss
     rays["d"] = (0, 0, 1)
-    rays["tmax"] = [5.0, 13.4, 100.0]
+    rays["tmax"] = [5.0, 10.5, 100.0]
     rays["tmin"] = [0.0, 0.0, 13.6]
     h = pt.trace_rays(rays)
     assert (h["t"] < 0).all()
