@@ -523,6 +523,7 @@ struct Invocation {
     const vec3 rma = v3(f16_to_f32(F.g.rma[4 * px]), f16_to_f32(F.g.rma[4 * px + 1]), f16_to_f32(F.g.rma[4 * px + 2]));
     const uint32_t mat_flags = F.g.flags[px];
     float* out = &F.out_rgba[4 * px];
+    if (pass == 0) { float* dz = &F.direct_rgba[4 * px]; dz[0] = dz[1] = dz[2] = 0.0f; dz[3] = 1.0f; }
     if (mat_flags & MAT_FLAG_EMISSIVE) {
       if (pass == 0) { out[0] = albedo.x; out[1] = albedo.y; out[2] = albedo.z; out[3] = 1.0f; }
       return;

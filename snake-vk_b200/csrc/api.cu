@@ -192,6 +192,7 @@ void snkpt_destroy(SnkPt* ctx) {
                     &ctx->det3, &ctx->instances, &ctx->blas_of_instance, &ctx->emissive_idx, &ctx->tlas_nodes, &ctx->tlas_leaf_ids,
                     &ctx->inst_recs, &ctx->valid_slots, &ctx->q_rays, &ctx->q_hits, &ctx->q_work, &ctx->dev_counters};
   for (DevBuf* b : bufs) b->release();
+  for (auto& b : ctx->wave) b.release();
   for (auto& b : ctx->px) b.release();
   scratch_free(ctx->scratch_blas);
   scratch_free(ctx->scratch_tlas);
@@ -691,9 +692,19 @@ int snkpt_get_stats(SnkPt* ctx, SnkPtStats* out) {
   if (!ctx || !out) return SNKPT_E_INVALID;
   cudaSetDevice(ctx->device);
   if (ctx->gbuffer_valid && cudaEventQuery(ctx->ev[1]) == cudaSuccess) cudaEventElapsedTime(&ctx->stats.ms_primary, ctx->ev[0], ctx->ev[1]);
-  uint32_t c[4] = {0, 0, 0, 0};
-  if (cudaStreamSynchronize(ctx->stream) == cudaSuccess && cudaMemcpy(c, ctx->dev_counters.p, sizeof(c), cudaMemcpyDeviceToHost) == cudaSuccess)
+  uint32_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (cudaStreamSynchronize(ctx->stream) == cudaSuccess && cudaMemcpy(c, ctx->dev_counters.p, sizeof(c), cudaMemcpyDeviceToHost) == cudaSuccess) {
     ctx->stats.stack_overflows = c[0];
+    if (ctx->render_pending) {
+      ctx->stats.rays_shadow = ((uint64_t)c[3] << 32) | c[2];
+      ctx->stats.rays_secondary = ((uint64_t)c[5] << 32) | c[4];
+      cudaEventElapsedTime(&ctx->stats.ms_restir1, ctx->ev[2], ctx->ev[3]);
+      cudaEventElapsedTime(&ctx->stats.ms_restir2, ctx->ev[3], ctx->ev[4]);
+      cudaEventElapsedTime(&ctx->stats.ms_bounce, ctx->ev[4], ctx->ev[5]);
+      cudaEventElapsedTime(&ctx->stats.ms_total, ctx->ev[2], ctx->ev[5]);
+      ctx->render_pending = false;
+    }
+  }
   *out = ctx->stats;
   return SNKPT_OK;
 }
@@ -723,7 +734,7 @@ int snkpt_trace_rays(SnkPt* ctx, const SnkRay* rays, uint64_t count, uint32_t fl
     CK(cudaMemcpyAsync(ctx->q_rays.p, rays, sizeof(SnkRay) * count, cudaMemcpyHostToDevice, st));
     d_rays = ctx->q_rays.as<float4>(); d_hits = ctx->q_hits.as<SnkHit>();
   }
-  ctx->stats.kernel_launches += launch_trace(ctx->trace_scene(), d_rays, count, any, d_hits, nullptr, nullptr, st);
+  ctx->stats.kernel_launches += launch_trace(ctx->trace_scene(), d_rays, count, any, d_hits, nullptr, nullptr, nullptr, st);
   CK(cudaGetLastError());
   if (any) ctx->stats.rays_shadow = count; else ctx->stats.rays_secondary = count;
   if (!(flags & SNKPT_RAY_DEVICE_PTRS)) {

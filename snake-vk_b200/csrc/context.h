@@ -114,6 +114,7 @@ struct SnkPt {
   snk::PixelPlanes planes{};
   bool history_valid = false;
   bool gbuffer_valid = false;
+  bool render_pending = false;  // a frame was enqueued since the last stats read
   uint32_t accum_count = 0;
 
   // frame
@@ -123,6 +124,7 @@ struct SnkPt {
 
   // generic ray query scratch
   snk::DevBuf q_rays, q_hits, q_work;
+  snk::DevBuf wave[12];      // wavefront queues of the bounce stages (rays, hits, shading records)
   snk::DevBuf dev_counters;  // [0] traversal stack overflows, [1] shadow rays, [2..3] secondary rays (u64)
 
   SnkPtStats stats{};

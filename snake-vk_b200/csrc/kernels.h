@@ -7,8 +7,9 @@ namespace snk {
 // trace.cu — wavefront traversal over a ray queue
 // rays: 2 x float4 per ray (o,tmin | d,tmax). hits_aos: SnkHit records (20 B) or nullptr;
 // hits_soa / inst_soa: float4 (t,u,v,prim) + u32 planes or nullptr.
+// vis_out: 1.0 = unoccluded / 0.0 = occluded per ray (any-hit queues) or nullptr.
 int launch_trace(const TraceScene& S, const float4* rays, uint64_t n, bool any, SnkHit* hits_aos, float4* hits_soa,
-                 uint32_t* inst_soa, cudaStream_t st);
+                 uint32_t* inst_soa, float* vis_out, cudaStream_t st);
 int launch_count_work(const TraceScene& S, const float4* rays, const SnkHit* hits, uint64_t n, bool any, uint32_t* out3,
                       cudaStream_t st);
 
@@ -16,7 +17,7 @@ int launch_count_work(const TraceScene& S, const float4* rays, const SnkHit* hit
 int launch_primary(const TraceScene& S, const SceneDev& D, const FrameConsts& fc, const PixelPlanes& P, cudaStream_t st);
 
 // restir.cu / bounce.cu — RT::RecordRenderCmdBuf (Raytracing.cpp:227-267) in reference mode
-struct RenderCounters { unsigned long long rays_shadow, rays_secondary; };
+int launch_restir_passes(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st);
 int launch_reference_frame(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st);
 int launch_northstar_frame(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st);
 int launch_accumulate(const PixelPlanes& P, uint32_t npix, uint32_t count, cudaStream_t st);

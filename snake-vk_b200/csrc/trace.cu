@@ -16,7 +16,7 @@ constexpr int TRACE_THREADS = 128;
 template <bool ANY>
 __global__ void __launch_bounds__(TRACE_THREADS) k_trace(TraceScene S, const float4* __restrict__ rays, unsigned long long n,
                                                          SnkHit* __restrict__ hits_aos, float4* __restrict__ hits_soa,
-                                                         uint32_t* __restrict__ inst_soa) {
+                                                         uint32_t* __restrict__ inst_soa, float* __restrict__ vis_out) {
   SNK_DECLARE_TRAV_STACK(TRACE_THREADS);
   uint2* stk = snk_trav_stack + threadIdx.x;
   const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
@@ -32,6 +32,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(TraceScene S, const flo
       hits_soa[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
       inst_soa[i] = h.inst;
     }
+    if (vis_out) vis_out[i] = h.t >= 0.0f ? 0.0f : 1.0f;  // Shadow.rmiss:12 → 1 - float(hit)
   }
 }
 
@@ -105,10 +106,10 @@ static int trace_grid(uint64_t n) {
 }
 
 int launch_trace(const TraceScene& S, const float4* rays, uint64_t n, bool any, SnkHit* hits_aos, float4* hits_soa,
-                 uint32_t* inst_soa, cudaStream_t st) {
+                 uint32_t* inst_soa, float* vis_out, cudaStream_t st) {
   if (n == 0) return 0;
-  if (any) k_trace<true><<<trace_grid(n), TRACE_THREADS, 0, st>>>(S, rays, n, hits_aos, hits_soa, inst_soa);
-  else k_trace<false><<<trace_grid(n), TRACE_THREADS, 0, st>>>(S, rays, n, hits_aos, hits_soa, inst_soa);
+  if (any) k_trace<true><<<trace_grid(n), TRACE_THREADS, 0, st>>>(S, rays, n, hits_aos, hits_soa, inst_soa, vis_out);
+  else k_trace<false><<<trace_grid(n), TRACE_THREADS, 0, st>>>(S, rays, n, hits_aos, hits_soa, inst_soa, vis_out);
   return 1;
 }
 
