@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py — the path-tracing frame (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--mode reference|northstar] [--scene c2]
+
+A step = one frame of the pass on the C2 workload (261,122 triangles, 1920x1080): per-frame TLAS rebuild
+(TlasSystem::BuildTlas), primary visibility (replaces the raster G-buffer pass), ReSTIR DI pass 1 + 2 and the
+bounce stages (RT::RecordRenderCmdBuf). `value` = all rays traced by all ranks / max-over-ranks device time.
+N > 1 is sample-sharded (every rank renders the whole frame with its own seed; radiance is summed over NVLink
+with one NCCL all-reduce per frame = the accumulation step) → weak scaling. `--shard rows` renders contiguous
+row bands instead (strong scaling, no collective; halo rows are re-rendered locally).
+
+`--impl reference` times the CPU oracle (the reference cannot run here: SURVEY §8c) on a bounded crop of the
+same frame with all host threads; it is the only leg besides cpu_baseline that executes oracle/.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+METRIC, UNIT = "rays_per_second_frame_1080p", "Mrays/s"
+
+
+def make_scene(snk, name: str, width: int, height: int):
+    S = snk.scenes
+    if name == "c2":
+        return S.c2("instanced", width=width, height=height), "C2 instanced: floor + 204 icospheres = 261,122 tris, 205 instances, 16 point lights + dir light"
+    if name == "c2flat":
+        return S.c2("flat", width=width, height=height), "C2 flat: 261,122 tris in one BLAS, 16 point lights + dir light"
+    if name == "c2m":
+        return S.c2("flat", subdiv=4, width=width, height=height), "C2 flat subdiv 4: 1,044,482 tris in one BLAS"
+    if name == "c3":
+        return S.c3(width=width, height=height), "C3: C2 instanced + 854 emissive cubes (10,248 emissive tris)"
+    if name == "cornell":
+        return S.cornell(width, height, True), "C1 Cornell box, 32 tris"
+    raise SystemExit(f"unknown scene {name}")
+
+
+def frame_ubo(sc, f: int, seed_offset: int = 0):
+    """camera dolly 0.1 u/frame along +z; time_elapsed = 1000 f / 60 ms"""
+    pos = np.asarray(sc.camera.pos, np.float32) + np.float32(0.1 * f) * np.array([0, 0, 1], np.float32)
+    u = sc.ubo(f, cam_pos=pos)
+    if seed_offset:
+        u["time_elapsed"] = np.float32(float(u["time_elapsed"]) + 7919.0 * seed_offset)
+    return u
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])), mx.append(float(p[2])), power.append(float(p[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w": statistics.median(power),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        v = d.get("hbm_gbs") or d.get("hbm_gb_s")
+        if v:
+            return float(v), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ CPU oracle legs
+def oracle_sample(sc, mode: str, rows: tuple[int, int], frames: int, threads: int):
+    """time the CPU oracle on rows [rows) of `frames` consecutive frames; returns (rays, seconds)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_api as O
+    osc = O.OracleScene(sc)
+    fr = O.OracleFrame(osc)
+    prev = None
+    rays = 0
+    t_total = 0.0
+    for f in range(frames):
+        ubo = frame_ubo(sc, f)
+        fr.set(ubo, ubo if prev is None else prev, O.default_settings(mode=0 if mode == "reference" else 1))
+        t0 = time.perf_counter()
+        fr.gbuffer(rows=rows, threads=threads)
+        fr.render(rows=rows, threads=threads)
+        t_total += time.perf_counter() - t0
+        c, a = fr.ray_counts(reset=True)
+        rays += c + a + (rows[1] - rows[0]) * sc.width
+        prev = ubo
+    return rays, t_total
+
+
+def run_reference_arm(args, snk):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sc, desc = make_scene(snk, args.scene, args.width, args.height)
+    threads = os.cpu_count() or 1
+    rows_per_step = max(2, args.ref_rows)
+    y0 = args.height // 2 - rows_per_step // 2
+    rows = (y0, y0 + rows_per_step)
+    # warm-up + calibration
+    for _ in range(max(args.warmup, 1)):
+        oracle_sample(sc, args.mode, rows, 1, threads)
+    rays, secs = 0, 0.0
+    for _ in range(args.steps):
+        r, s = oracle_sample(sc, args.mode, rows, 2, threads)
+        rays += r
+        secs += s
+    v = rays / secs / 1e6
+    sample = f"rows [{rows[0]},{rows[1]}) of the {args.width}x{args.height} frame, 2 consecutive frames per step (frame 1 exercises temporal reuse)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": desc, "mode": args.mode, "resolution": [args.width, args.height]},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU oracle (restatement of the reference GLSL; the Vulkan reference cannot run headless here, SURVEY §8c)",
+    }))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+class CudaArray:
+    """__cuda_array_interface__ shim so torch can alias a library-owned device buffer (NCCL plumbing)"""
+
+    def __init__(self, ptr: int, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 3, "strides": None}
+
+
+def run_gpu_arm(args, snk):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this arm has no CPU path (use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    sc, desc = make_scene(snk, args.scene, args.width, args.height)
+    W, H = sc.width, sc.height
+    rows = (0, H)
+    if world > 1 and args.shard == "rows":
+        band = (H + world - 1) // world
+        rows = (rank * band, min(H, (rank + 1) * band))
+    pt = snk.PathTracer(W, H, device=local, rows=rows)
+    flat = pt.upload_scene(sc)
+    mode = snk.api.MODE_REFERENCE if args.mode == "reference" else snk.api.MODE_NORTHSTAR
+    settings = snk.api.default_settings(mode=mode)
+    stream = torch.cuda.current_stream().cuda_stream
+    seed_off = rank if (world > 1 and args.shard == "samples") else 0
+    rad = None
+    if world > 1 and args.shard == "samples":
+        ptr, nbytes = pt.device_ptr(0x102)
+        rad = torch.as_tensor(CudaArray(ptr, (H, W, 4)), device=f"cuda:{local}")
+
+    def step(f: int):
+        ubo = frame_ubo(sc, f, seed_off)
+        prev = frame_ubo(sc, f - 1, seed_off) if f > 0 else ubo
+        pt.build_tlas(stream)           # TlasSystem::BuildTlas — rebuilt every frame like the reference
+        pt.set_frame(ubo, prev)
+        pt.trace_primary(stream=stream)
+        pt.render(settings, stream)
+        if rad is not None:
+            dist.all_reduce(rad)        # accumulation step: sum of the per-GPU samples over NVLink
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    f = 0
+    for _ in range(args.warmup):
+        step(f)
+        f += 1
+    barrier()
+    st0 = pt.stats()
+    pt.set_profiling(1)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(f)
+        f += 1
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    st1 = pt.stats()
+    timings = pt.launch_timings()
+    rays = sum(int(st1[k]) - int(st0[k]) for k in ("total_rays_primary", "total_rays_shadow", "total_rays_secondary"))
+    launches = int(st1["kernel_launches"]) - int(st0["kernel_launches"])
+    if world > 1:
+        t = torch.tensor([ms_total, float(rays), float(launches)], device=f"cuda:{local}", dtype=torch.float64)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        ms_total, rays, launches = float(tmax[0]), float(t[1]), int(t[2])
+    value = rays / (ms_total * 1e-3) / 1e6
+
+    # ---- end to end through the C ABI with host buffers (rank-local; max over ranks)
+    import ctypes
+    out_host = torch.empty((rows[1] - rows[0], W, 4), dtype=torch.float16, pin_memory=True)
+    out_np = out_host.numpy()
+    n_inst = flat["instances"].shape[0]
+    h2d = 2 * 240 + 2 * flat["transforms"].nbytes + flat["instances"].nbytes + flat["blas_of_instance"].nbytes + flat["emissive_idx"].nbytes
+    d2h = out_np.nbytes
+    pt.set_profiling(0)
+
+    def e2e_step(f: int):
+        pt.set_transforms(flat["transforms"], flat["prev_transforms"])  # TransformBufferSystem: cur + prev, host → device
+        pt.set_instances(flat["instances"], flat["blas_of_instance"], flat["emissive_idx"])
+        step(f)
+        if rank == 0 or rad is None:
+            pt.read_output("f16", out_np)  # device → host: the RGBA16F image the engine would present
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step(f)
+        f += 1
+    barrier()
+    st2 = pt.stats()
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step(f)
+        f += 1
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0) * 0.0)
+    st3 = pt.stats()
+    e2e_rays = sum(int(st3[k]) - int(st2[k]) for k in ("total_rays_primary", "total_rays_shadow", "total_rays_secondary"))
+    if world > 1:
+        t = torch.tensor([e2e_ms, float(e2e_rays)], device=f"cuda:{local}", dtype=torch.float64)
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        e2e_ms, e2e_rays = float(tmax[0]), float(t[1])
+    e2e_value = e2e_rays / (e2e_ms * 1e-3) / 1e6
+
+    # ---- roofline of the dominant kernel: event durations from the timed region, algorithmic bytes from counted replays
+    per = {}
+    for r in timings:
+        nm = r["name"].decode()
+        d = per.setdefault(nm, {"ms": 0.0, "n": 0, "is_trace": int(r["is_trace"]), "units": 0})
+        d["ms"] += float(r["ms"])
+        d["n"] += 1
+        d["units"] += int(r["units"])
+    pt.set_profiling(2)
+    n_count = 2
+    for _ in range(n_count):
+        step(f)
+        f += 1
+    torch.cuda.synchronize()
+    counted = {}
+    for r in pt.launch_timings():
+        nm = r["name"].decode()
+        if int(r["is_trace"]):
+            d = counted.setdefault(nm, {"bytes": 0, "live": 0, "nodes": 0, "tris": 0, "insts": 0, "n": 0})
+            d["bytes"] += int(r["alg_bytes"]); d["live"] += int(r["live"]); d["nodes"] += int(r["nodes"])
+            d["tris"] += int(r["tris"]); d["insts"] += int(r["insts"]); d["n"] += 1
+    pt.set_profiling(0)
+    peak, peak_src = measured_peaks()
+    roof = None
+    breakdown = {k: {"ms_per_launch": v["ms"] / v["n"], "launches": v["n"], "share": v["ms"] / max(sum(x["ms"] for x in per.values()), 1e-9)}
+                 for k, v in per.items()}
+    trace_names = [k for k, v in per.items() if v["is_trace"] and k in counted]
+    if trace_names:
+        top = max(trace_names, key=lambda k: per[k]["ms"])
+        ms_launch = per[top]["ms"] / per[top]["n"]
+        c = counted[top]
+        bytes_launch = c["bytes"] / c["n"]
+        achieved = bytes_launch / (ms_launch * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "alg_bytes_per_launch": bytes_launch, "ms_per_launch": ms_launch,
+                "rays_per_launch": c["live"] / c["n"], "nodes_per_ray": c["nodes"] / max(c["live"], 1), "tris_per_ray": c["tris"] / max(c["live"], 1),
+                "instances_per_ray": c["insts"] / max(c["live"], 1),
+                "grays_per_s": c["live"] / c["n"] / (ms_launch * 1e-3) / 1e9,
+                "note": "L2-resident BVH: a fraction above the HBM line is legal (SURVEY §8d); traffic from profiles/ ncu capture"}
+        tr = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tr):
+            try:
+                roof["traffic"] = json.load(open(tr)).get(top)
+            except Exception:
+                pass
+
+    # ---- CPU baseline (rank 0, N = 1): the oracle on a bounded crop of the same frames
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        y0 = H // 2 - args.ref_rows // 2
+        r, s = oracle_sample(sc, args.mode, (y0, y0 + args.ref_rows), 2, threads)
+        cpu = {"value": r / s / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"rows [{y0},{y0 + args.ref_rows}) of the {W}x{H} frame, frames 0-1, {r} rays in {s:.1f} s (CPU restatement, oracle = cpu_restatement)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak" if (world == 1 or args.shard == "samples") else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc, "mode": args.mode, "resolution": [W, H], "rays_per_frame": rays / args.steps / world,
+                       "shard": args.shard if world > 1 else "none",
+                       "l2": "ray/hit queues (1.6 GB per frame) and per-pixel planes exceed the 126 MB L2 between iterations; the BVH itself is L2-resident by size"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / e2e_steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "kernels": breakdown,
+        }
+        print(json.dumps(line))
+    pt.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default="reference", choices=["reference", "northstar"])
+    ap.add_argument("--scene", default="c2")
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--shard", default="samples", choices=["samples", "rows"])
+    ap.add_argument("--ref-rows", type=int, default=8, help="rows of the frame the CPU oracle renders per sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    snk = importlib.import_module("snake-vk_b200")
+    if args.impl == "reference":
+        run_reference_arm(args, snk)
+    else:
+        run_gpu_arm(args, snk)
+
+
+if __name__ == "__main__":
+    main()

@@ -235,8 +235,20 @@ typedef struct SnkPtStats {
   float ms_primary, ms_restir1, ms_restir2, ms_bounce, ms_total; /* CUDA events of last frame */
   float ms_build_last;       /* last BLAS / TLAS build                            */
   uint32_t stack_overflows;  /* traversal-stack overflows since create (must be 0) */
-  uint32_t reserved[7];
-} SnkPtStats;
+  uint64_t total_rays_primary, total_rays_shadow, total_rays_secondary; /* since create, folded on the device per frame */
+} SnkPtStats; /* 112 B */
+
+/* one kernel launch of the last frame (snkpt_trace_primary .. snkpt_render) or of
+ * the last snkpt_trace_rays, timed with CUDA events on the launching stream */
+typedef struct SnkLaunchTiming {
+  char name[32];      /* kernel name, e.g. "trace_closest.B"                       */
+  float ms;           /* event-to-event duration of this launch                    */
+  uint32_t is_trace;  /* 1 = a traversal launch (units are rays)                   */
+  uint64_t units;     /* rays or pixels handed to the launch (incl. dead slots)    */
+  uint64_t live;      /* traversal launches at profiling level 2: rays with tmax >= tmin */
+  uint64_t nodes, tris, insts; /* level 2: SURVEY §8(d) algorithmic work of the launch */
+  uint64_t alg_bytes; /* level 2: 32·live + 16|4·live + 80·nodes + 48·tris + 64·insts  */
+} SnkLaunchTiming; /* 88 B */
 
 typedef struct SnkBlasInfo {
   uint32_t node_root;   /* index of the root wide node in the node pool          */
@@ -329,6 +341,14 @@ SNKPT_API int snkpt_write_reservoirs(SnkPt* ctx, uint32_t half, const SnkPixelRe
  * of half h: 0x110 + h) */
 SNKPT_API int snkpt_device_ptr(SnkPt* ctx, uint32_t what, void** ptr, size_t* bytes);
 SNKPT_API int snkpt_get_stats(SnkPt* ctx, SnkPtStats* out);
+/* level 0: off. 1: bracket every kernel launch with CUDA events (cheap; what
+ * bench.py runs with). 2: additionally run the work-counting diagnostic after
+ * every traversal launch (timings of those frames are then not representative).
+ * Records accumulate (up to 2048) until the next snkpt_set_profiling call or
+ * snkpt_get_launch_timings, which returns and clears them. */
+SNKPT_API int snkpt_set_profiling(SnkPt* ctx, uint32_t level);
+/* synchronises the context stream; returns up to `cap` records of the last frame */
+SNKPT_API int snkpt_get_launch_timings(SnkPt* ctx, SnkLaunchTiming* out, uint32_t cap, uint32_t* count);
 SNKPT_API int snkpt_synchronize(SnkPt* ctx);
 
 /* ---- ray queries --------------------------------------------------------------------- */

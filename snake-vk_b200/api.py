@@ -49,6 +49,7 @@ def load_library() -> C.CDLL:
         "snkpt_write_reservoirs": [vp, u32, vp, u32, u32], "snkpt_device_ptr": [vp, u32, vp, vp],
         "snkpt_get_stats": [vp, vp], "snkpt_synchronize": [vp], "snkpt_trace_rays": [vp, vp, u64, u32, vp, vp],
         "snkpt_count_work": [vp, vp, vp, u64, u32, vp, vp],
+        "snkpt_set_profiling": [vp, u32], "snkpt_get_launch_timings": [vp, vp, u32, vp],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -68,7 +69,7 @@ EXPORTS = ["snkpt_create", "snkpt_destroy", "snkpt_last_error", "snkpt_default_s
            "snkpt_set_materials", "snkpt_set_lights", "snkpt_set_transforms", "snkpt_set_instances", "snkpt_build_tlas",
            "snkpt_set_frame", "snkpt_trace_primary", "snkpt_render", "snkpt_accumulate", "snkpt_read_output", "snkpt_read_aux",
            "snkpt_aux_size", "snkpt_write_reservoirs", "snkpt_device_ptr", "snkpt_get_stats", "snkpt_synchronize",
-           "snkpt_trace_rays", "snkpt_count_work"]
+           "snkpt_trace_rays", "snkpt_count_work", "snkpt_set_profiling", "snkpt_get_launch_timings"]
 
 CONFIG_DTYPE = np.dtype([("width", "<u4"), ("height", "<u4"), ("device", "<i4"), ("max_instances", "<u4"),
                          ("max_transforms", "<u4"), ("max_materials", "<u4"), ("row_begin", "<u4"), ("row_end", "<u4"),
@@ -79,13 +80,18 @@ SETTINGS_DTYPE = np.dtype([("num_temporal", "<i4"), ("num_spatial", "<i4"), ("mo
 STATS_DTYPE = np.dtype([("rays_primary", "<u8"), ("rays_shadow", "<u8"), ("rays_secondary", "<u8"), ("kernel_launches", "<u8"),
                         ("blas_nodes", "<u8"), ("blas_tris", "<u8"), ("tlas_nodes", "<u8"), ("ms_primary", "<f4"),
                         ("ms_restir1", "<f4"), ("ms_restir2", "<f4"), ("ms_bounce", "<f4"), ("ms_total", "<f4"),
-                        ("ms_build_last", "<f4"), ("stack_overflows", "<u4"), ("reserved", "<u4", (7,))])
+                        ("ms_build_last", "<f4"), ("stack_overflows", "<u4"), ("total_rays_primary", "<u8"),
+                        ("total_rays_shadow", "<u8"), ("total_rays_secondary", "<u8")], align=True)
+assert STATS_DTYPE.itemsize == 112
 SUBMESH_DTYPE = np.dtype([("num_indices", "<u4"), ("num_vertices", "<u4"), ("base_vertex", "<u4"), ("base_index", "<u4"),
                           ("material_index", "<u4")])
 MESH_ENTRY_DTYPE = np.dtype([("data_start_indices_idx", "<u4"), ("data_start_vertex_idx", "<u4"), ("num_submeshes", "<u4"),
                              ("blas_id", "<u4", (64,))])
 BLAS_INFO_DTYPE = np.dtype([("node_root", "<u4"), ("node_count", "<u4"), ("tri_base", "<u4"), ("tri_count", "<u4"),
                             ("bounds_lo", "<f4", (3,)), ("bounds_hi", "<f4", (3,))])
+LAUNCH_TIMING_DTYPE = np.dtype([("name", "S32"), ("ms", "<f4"), ("is_trace", "<u4"), ("units", "<u8"), ("live", "<u8"),
+                                ("nodes", "<u8"), ("tris", "<u8"), ("insts", "<u8"), ("alg_bytes", "<u8")])
+assert LAUNCH_TIMING_DTYPE.itemsize == 88
 assert SETTINGS_DTYPE.itemsize == 64 and CONFIG_DTYPE.itemsize == 48 and SUBMESH_DTYPE.itemsize == 20
 
 MODE_REFERENCE, MODE_NORTHSTAR = 0, 1
@@ -248,6 +254,15 @@ class PathTracer:
         s = np.zeros((), STATS_DTYPE)
         self._ck(self.L.snkpt_get_stats(self.h, _p(s)), "snkpt_get_stats")
         return s
+
+    def set_profiling(self, level: int):
+        self._ck(self.L.snkpt_set_profiling(self.h, level), "snkpt_set_profiling")
+
+    def launch_timings(self) -> np.ndarray:
+        out = np.zeros(2048, LAUNCH_TIMING_DTYPE)
+        n = C.c_uint32()
+        self._ck(self.L.snkpt_get_launch_timings(self.h, _p(out), out.size, C.byref(n)), "snkpt_get_launch_timings")
+        return out[:n.value]
 
     # ---- ray queries
     def trace_rays(self, rays: np.ndarray, any_hit=False, flags=0) -> np.ndarray:

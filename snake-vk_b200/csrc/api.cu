@@ -77,6 +77,43 @@ static void derive_transform(const float* M, float* w2o12, float* nmat9, float* 
     for (int c = 0; c < 3; ++c) nmat9[r * 3 + c] = (float)i3[c][r];
 }
 
+// ---- per-launch profiling ---------------------------------------------------------------------
+namespace snk {
+void prof_reset(SnkPt*) {}  // records accumulate until read (snkpt_get_launch_timings) or re-armed (snkpt_set_profiling)
+int prof_begin(SnkPt* ctx, const char* name, uint64_t units, bool is_trace, bool any, cudaStream_t st) {
+  if (!ctx->profiling || ctx->prof_n >= PROF_MAX) return -1;
+  ProfRec& r = ctx->prof[ctx->prof_n];
+  if (!r.e0 && (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess)) return -1;
+  snprintf(r.name, sizeof(r.name), "%s", name);
+  r.units = units; r.is_trace = is_trace; r.any = any; r.counted = false;
+  cudaEventRecord(r.e0, st);
+  return ctx->prof_n++;
+}
+void prof_end(SnkPt* ctx, int rec, cudaStream_t st) {
+  if (rec >= 0) cudaEventRecord(ctx->prof[rec].e1, st);
+}
+int traced_launch(SnkPt* ctx, const char* name, const float4* rays, uint64_t n, bool any, SnkHit* hits_aos, float4* hits_soa,
+                  uint32_t* inst_soa, float* vis_out, cudaStream_t st) {
+  if (n == 0) return 0;
+  const bool count = ctx->profiling >= 2 && ctx->prof_n < PROF_MAX;
+  if (count && !hits_soa) {
+    // the work counter needs the reported hit distance of every ray
+    if (ctx->prof_hits.reserve(16 * n, false, st) == cudaSuccess) hits_soa = ctx->prof_hits.as<float4>();
+  }
+  const TraceScene S = ctx->trace_scene();
+  const int rec = prof_begin(ctx, name, n, true, any, st);
+  const int launches = launch_trace(S, rays, n, any, hits_aos, hits_soa, inst_soa, vis_out, st);
+  prof_end(ctx, rec, st);
+  if (count && rec >= 0 && hits_soa && ctx->prof_work.reserve(32 * PROF_MAX, false, st) == cudaSuccess) {
+    unsigned long long* sums = ctx->prof_work.as<unsigned long long>() + 4 * rec;
+    cudaMemsetAsync(sums, 0, 32, st);
+    launch_count_work_sum(S, rays, hits_soa, n, sums, st);
+    ctx->prof[rec].counted = true;
+  }
+  return launches;
+}
+}  // namespace snk
+
 TraceScene SnkPt::trace_scene() const {
   TraceScene S;
   S.tlas_nodes = tlas_nodes.as<uint4>();
@@ -197,6 +234,8 @@ void snkpt_destroy(SnkPt* ctx) {
   scratch_free(ctx->scratch_blas);
   scratch_free(ctx->scratch_tlas);
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  for (auto& r : ctx->prof) { if (r.e0) cudaEventDestroy(r.e0); if (r.e1) cudaEventDestroy(r.e1); }
+  ctx->prof_work.release(); ctx->prof_hits.release();
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -545,11 +584,15 @@ int snkpt_trace_primary(SnkPt* ctx, const float* jitter_xy, void* stream) {
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
   fill_frame_dims(ctx);
   ctx->fc.jx = jitter_xy ? jitter_xy[0] : 0.f; ctx->fc.jy = jitter_xy ? jitter_xy[1] : 0.f;
+  prof_reset(ctx);
   cudaEventRecord(ctx->ev[0], st);
+  const int rec = prof_begin(ctx, "primary", (uint64_t)ctx->W * (ctx->row1 - ctx->row0), false, false, st);
   ctx->stats.kernel_launches += launch_primary(ctx->trace_scene(), ctx->scene_dev(), ctx->fc, ctx->planes, st);
+  prof_end(ctx, rec, st);
   cudaEventRecord(ctx->ev[1], st);
   CK(cudaGetLastError());
   ctx->stats.rays_primary = (uint64_t)ctx->W * (ctx->row1 - ctx->row0);
+  ctx->stats.total_rays_primary += ctx->stats.rays_primary;
   ctx->gbuffer_valid = true;
   return SNKPT_OK;
 }
@@ -692,9 +735,11 @@ int snkpt_get_stats(SnkPt* ctx, SnkPtStats* out) {
   if (!ctx || !out) return SNKPT_E_INVALID;
   cudaSetDevice(ctx->device);
   if (ctx->gbuffer_valid && cudaEventQuery(ctx->ev[1]) == cudaSuccess) cudaEventElapsedTime(&ctx->stats.ms_primary, ctx->ev[0], ctx->ev[1]);
-  uint32_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (cudaStreamSynchronize(ctx->stream) == cudaSuccess && cudaMemcpy(c, ctx->dev_counters.p, sizeof(c), cudaMemcpyDeviceToHost) == cudaSuccess) {
+  uint32_t c[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (cudaDeviceSynchronize() == cudaSuccess && cudaMemcpy(c, ctx->dev_counters.p, sizeof(c), cudaMemcpyDeviceToHost) == cudaSuccess) {
     ctx->stats.stack_overflows = c[0];
+    ctx->stats.total_rays_shadow = ((uint64_t)c[9] << 32) | c[8];
+    ctx->stats.total_rays_secondary = ((uint64_t)c[11] << 32) | c[10];
     if (ctx->render_pending) {
       ctx->stats.rays_shadow = ((uint64_t)c[3] << 32) | c[2];
       ctx->stats.rays_secondary = ((uint64_t)c[5] << 32) | c[4];
@@ -706,6 +751,42 @@ int snkpt_get_stats(SnkPt* ctx, SnkPtStats* out) {
     }
   }
   *out = ctx->stats;
+  return SNKPT_OK;
+}
+
+int snkpt_set_profiling(SnkPt* ctx, uint32_t level) {
+  if (!ctx) return SNKPT_E_INVALID;
+  REQUIRE(level <= 2, SNKPT_E_INVALID, "snkpt_set_profiling: level");
+  ctx->profiling = level;
+  ctx->prof_n = 0;
+  return SNKPT_OK;
+}
+
+int snkpt_get_launch_timings(SnkPt* ctx, SnkLaunchTiming* out, uint32_t cap, uint32_t* count) {
+  if (!ctx || !count) return SNKPT_E_INVALID;
+  REQUIRE(out || cap == 0, SNKPT_E_INVALID, "snkpt_get_launch_timings: null output");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaDeviceSynchronize());  // launches may have been enqueued on a caller stream
+  std::vector<unsigned long long> work(4 * PROF_MAX, 0ull);
+  if (ctx->prof_work.p) CK(cudaMemcpy(work.data(), ctx->prof_work.p, 32 * PROF_MAX, cudaMemcpyDeviceToHost));
+  uint32_t n = 0;
+  for (int i = 0; i < ctx->prof_n && n < cap; ++i, ++n) {
+    const ProfRec& r = ctx->prof[i];
+    SnkLaunchTiming& o = out[n];
+    memset(&o, 0, sizeof(o));
+    memcpy(o.name, r.name, sizeof(o.name));
+    cudaEventElapsedTime(&o.ms, r.e0, r.e1);
+    o.is_trace = r.is_trace ? 1u : 0u;
+    o.units = r.units;
+    if (r.counted) {
+      o.live = work[4 * i]; o.nodes = work[4 * i + 1]; o.tris = work[4 * i + 2]; o.insts = work[4 * i + 3];
+      // ray in 32 B, hit out 16 B (closest) / 4 B (any), 80 B per node, 48 B per triangle record, 64 B per instance
+      o.alg_bytes = o.live * (32ull + (r.any ? 4ull : 16ull)) + 80ull * o.nodes + 48ull * o.tris + 64ull * o.insts;
+    }
+  }
+  *count = n;
+  ctx->prof_n = 0;
   return SNKPT_OK;
 }
 
@@ -734,7 +815,9 @@ int snkpt_trace_rays(SnkPt* ctx, const SnkRay* rays, uint64_t count, uint32_t fl
     CK(cudaMemcpyAsync(ctx->q_rays.p, rays, sizeof(SnkRay) * count, cudaMemcpyHostToDevice, st));
     d_rays = ctx->q_rays.as<float4>(); d_hits = ctx->q_hits.as<SnkHit>();
   }
-  ctx->stats.kernel_launches += launch_trace(ctx->trace_scene(), d_rays, count, any, d_hits, nullptr, nullptr, nullptr, st);
+  prof_reset(ctx);
+  ctx->stats.kernel_launches += traced_launch(ctx, any ? "trace_any.query" : "trace_closest.query", d_rays, count, any, d_hits, nullptr,
+                                              nullptr, nullptr, st);
   CK(cudaGetLastError());
   if (any) ctx->stats.rays_shadow = count; else ctx->stats.rays_secondary = count;
   if (!(flags & SNKPT_RAY_DEVICE_PTRS)) {

@@ -190,6 +190,12 @@ __global__ void __launch_bounds__(256) k_bounce_resolve(FrameConsts fc, PixelPla
   P.out16[px] = make_ushort4(f2h(out.x), f2h(out.y), f2h(out.z), f2h(1.0f));  // internal_render_image is RGBA16F
 }
 
+// frame counters [2..5] (shadow, closest as u64) are folded into the since-create totals [8..11]
+__global__ void k_fold_counters(unsigned long long* c) {
+  c[4] += c[1];
+  c[5] += c[2];
+}
+
 }  // namespace
 
 int launch_reference_frame(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st) {
@@ -213,18 +219,28 @@ int launch_reference_frame(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st) 
     B.col_b = ctx->wave[9].as<float4>(); B.cos_b = ctx->wave[10].as<float>(); B.vis_b = ctx->wave[11].as<float>();
     unsigned long long* c_shadow = reinterpret_cast<unsigned long long*>(ctx->dev_counters.as<uint32_t>() + 2);
     unsigned long long* c_closest = c_shadow + 1;
-    const TraceScene S = ctx->trace_scene();
     const SceneDev D = ctx->scene_dev();
+    int rec = prof_begin(ctx, "bounce_gen", npix, false, false, st);
     k_bounce_gen<<<(npix + 255) / 256, 256, 0, st>>>(fc, ctx->planes, B, npix, c_closest);
-    launches += 1 + launch_trace(S, B.rays_a, na, false, nullptr, B.hit_a, B.inst_a, nullptr, st);
+    prof_end(ctx, rec, st);
+    launches += 1 + traced_launch(ctx, "trace_closest.A", B.rays_a, na, false, nullptr, B.hit_a, B.inst_a, nullptr, st);
+    rec = prof_begin(ctx, "bounce_shade.A", na, false, false, st);
     k_bounce_shade<0><<<(unsigned)((na + 255) / 256), 256, 0, st>>>(D, fc, ctx->planes, B, npix, c_shadow);
-    launches += 1 + launch_trace(S, B.rays_a, na, true, nullptr, nullptr, nullptr, B.vis_a, st);
-    launches += launch_trace(S, B.rays_b, nb, false, nullptr, B.hit_b, B.inst_b, nullptr, st);
+    prof_end(ctx, rec, st);
+    launches += 1 + traced_launch(ctx, "trace_any.A", B.rays_a, na, true, nullptr, nullptr, nullptr, B.vis_a, st);
+    launches += traced_launch(ctx, "trace_closest.B", B.rays_b, nb, false, nullptr, B.hit_b, B.inst_b, nullptr, st);
+    rec = prof_begin(ctx, "bounce_shade.B", nb, false, false, st);
     k_bounce_shade<1><<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(D, fc, ctx->planes, B, npix, c_shadow);
-    launches += 1 + launch_trace(S, B.rays_b, nb, true, nullptr, nullptr, nullptr, B.vis_b, st);
+    prof_end(ctx, rec, st);
+    launches += 1 + traced_launch(ctx, "trace_any.B", B.rays_b, nb, true, nullptr, nullptr, nullptr, B.vis_b, st);
   }
-  k_bounce_resolve<<<(npix + 255) / 256, 256, 0, st>>>(fc, ctx->planes, B, npix, bounce ? 1 : 0);
-  ++launches;
+  {
+    const int rec = prof_begin(ctx, "bounce_resolve", npix, false, false, st);
+    k_bounce_resolve<<<(npix + 255) / 256, 256, 0, st>>>(fc, ctx->planes, B, npix, bounce ? 1 : 0);
+    prof_end(ctx, rec, st);
+  }
+  k_fold_counters<<<1, 1, 0, st>>>(reinterpret_cast<unsigned long long*>(ctx->dev_counters.as<uint32_t>()));
+  launches += 2;
   cudaEventRecord(ctx->ev[5], st);
   ctx->stats.kernel_launches += launches;
   ctx->render_pending = true;

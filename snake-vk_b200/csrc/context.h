@@ -41,6 +41,15 @@ struct DevBuf {
 
 struct BlasSrc { uint32_t index_offset, vertex_offset, num_tris; };
 
+// one timed kernel launch (snkpt_set_profiling / snkpt_get_launch_timings)
+struct ProfRec {
+  char name[32];
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  uint64_t units = 0;
+  bool is_trace = false, any = false, counted = false;
+};
+constexpr int PROF_MAX = 2048;
+
 // per-frame constants handed to the kernels by value
 struct FrameConsts {
   float ivp[16];        // inverse(view) * inverse(proj) hoisted (Util.glsl:3), float64 rounded once
@@ -129,6 +138,13 @@ struct SnkPt {
 
   SnkPtStats stats{};
   cudaEvent_t ev[8] = {};
+
+  // per-launch profiling
+  uint32_t profiling = 0;
+  std::vector<snk::ProfRec> prof = std::vector<snk::ProfRec>(snk::PROF_MAX);
+  int prof_n = 0;
+  snk::DevBuf prof_work;  // 4 x u64 per record: live rays, nodes, leaf records, instances
+  snk::DevBuf prof_hits;  // level 2: hit distances of any-hit launches
 
   snk::TraceScene trace_scene() const;
   snk::SceneDev scene_dev() const;

@@ -12,6 +12,17 @@ int launch_trace(const TraceScene& S, const float4* rays, uint64_t n, bool any, 
                  uint32_t* inst_soa, float* vis_out, cudaStream_t st);
 int launch_count_work(const TraceScene& S, const float4* rays, const SnkHit* hits, uint64_t n, bool any, uint32_t* out3,
                       cudaStream_t st);
+// sums {live rays, nodes, leaf records, instances} of a whole queue into sums4 (hits as float4 with t in .x)
+int launch_count_work_sum(const TraceScene& S, const float4* rays, const float4* hits_soa, uint64_t n, unsigned long long* sums4,
+                          cudaStream_t st);
+
+// api.cu — per-launch profiling (no-ops at level 0)
+void prof_reset(SnkPt* ctx);
+int prof_begin(SnkPt* ctx, const char* name, uint64_t units, bool is_trace, bool any, cudaStream_t st);
+void prof_end(SnkPt* ctx, int rec, cudaStream_t st);
+// launch_trace bracketed by a profiling record; at level 2 also counts the queue's algorithmic work
+int traced_launch(SnkPt* ctx, const char* name, const float4* rays, uint64_t n, bool any, SnkHit* hits_aos, float4* hits_soa,
+                  uint32_t* inst_soa, float* vis_out, cudaStream_t st);
 
 // gbuffer.cu — primary visibility (replaces GBufferPass::RecordCommandBuffer, GBufferPass.cpp:70-196)
 int launch_primary(const TraceScene& S, const SceneDev& D, const FrameConsts& fc, const PixelPlanes& P, cudaStream_t st);

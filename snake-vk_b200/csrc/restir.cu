@@ -412,11 +412,15 @@ int launch_restir_passes(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st) {
   int launches = 0;
   cudaEventRecord(ctx->ev[2], st);
   if (!(s.flags & SNKPT_RT_NO_RESTIR)) {
+    const int rec = prof_begin(ctx, "restir_pass1", (uint64_t)fc.W * (fc.row1 - fc.row0), false, false, st);
     k_restir_pass1<<<grid, RT_THREADS, 0, st>>>(ctx->trace_scene(), ctx->scene_dev(), f, ctx->planes, rp, counter);
+    prof_end(ctx, rec, st);
     ++launches;
   }
   cudaEventRecord(ctx->ev[3], st);
+  const int rec2 = prof_begin(ctx, "restir_pass2", (uint64_t)fc.W * (fc.row1 - fc.row0), false, false, st);
   k_restir_pass2<<<grid, RT_THREADS, 0, st>>>(ctx->trace_scene(), ctx->scene_dev(), f, ctx->planes, rp, counter);
+  prof_end(ctx, rec2, st);
   ++launches;
   cudaEventRecord(ctx->ev[4], st);
   return launches;

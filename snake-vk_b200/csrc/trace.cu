@@ -28,10 +28,8 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(TraceScene S, const flo
       SnkHit o; o.t = h.t; o.u = h.u; o.v = h.v; o.prim = h.prim; o.inst = h.inst;
       hits_aos[i] = o;
     }
-    if (hits_soa) {
-      hits_soa[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
-      inst_soa[i] = h.inst;
-    }
+    if (hits_soa) hits_soa[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+    if (inst_soa) inst_soa[i] = h.inst;
     if (vis_out) vis_out[i] = h.t >= 0.0f ? 0.0f : 1.0f;  // Shadow.rmiss:12 → 1 - float(hit)
   }
 }
@@ -97,6 +95,44 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_count_work(TraceScene S, cons
   out3[3 * i] = nodes; out3[3 * i + 1] = recs; out3[3 * i + 2] = insts;
 }
 
+// whole-queue sums of the same quantities (profiling level 2)
+__global__ void __launch_bounds__(TRACE_THREADS) k_count_work_sum(TraceScene S, const float4* __restrict__ rays,
+                                                                  const float4* __restrict__ hits, unsigned long long n,
+                                                                  unsigned long long* __restrict__ sums4) {
+  const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long v[4] = {0, 0, 0, 0};
+  if (i < n) {
+    const float4 a = __ldg(rays + 2 * i), b = __ldg(rays + 2 * i + 1);
+    if (b.w >= a.w && S.tlas_node_count) {
+      const float ht = hits[i].x;
+      const float tend = ht >= 0.f ? ht : b.w;
+      uint32_t nodes = 0, recs = 0, insts = 0;
+      RaySpace r;
+      setup_ray_space(r, a.x, a.y, a.z, b.x, b.y, b.z);
+      uint32_t leaf[64];
+      int ln = 0;
+      count_subtree(r, S.tlas_nodes, 0u, a.w, tend, nodes, insts, leaf, ln, 64);
+      for (int k = 0; k < ln; ++k) {
+        const uint32_t slot = S.tlas_leaf_ids[leaf[k]];
+        const float4* M = reinterpret_cast<const float4*>(S.inst + slot);
+        const float4 r0 = M[0], r1 = M[1], r2 = M[2];
+        RaySpace o;
+        setup_ray_space(o, r0.x * a.x + r0.y * a.y + r0.z * a.z + r0.w, r1.x * a.x + r1.y * a.y + r1.z * a.z + r1.w,
+                        r2.x * a.x + r2.y * a.y + r2.z * a.z + r2.w, r0.x * b.x + r0.y * b.y + r0.z * b.z,
+                        r1.x * b.x + r1.y * b.y + r1.z * b.z, r2.x * b.x + r2.y * b.y + r2.z * b.z);
+        int unused = 0;
+        count_subtree(o, S.blas_nodes, S.inst[slot].blas_root, a.w, tend, nodes, recs, nullptr, unused, 0);
+      }
+      v[0] = 1; v[1] = nodes; v[2] = recs; v[3] = insts;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xFFFFFFFFu, v[k], o);
+    if ((threadIdx.x & 31) == 0 && v[k]) atomicAdd(sums4 + k, v[k]);
+  }
+}
+
 }  // namespace
 
 static int trace_grid(uint64_t n) {
@@ -118,6 +154,13 @@ int launch_count_work(const TraceScene& S, const float4* rays, const SnkHit* hit
   (void)any;
   if (n == 0) return 0;
   k_count_work<<<(unsigned)((n + TRACE_THREADS - 1) / TRACE_THREADS), TRACE_THREADS, 0, st>>>(S, rays, hits, n, out3);
+  return 1;
+}
+
+int launch_count_work_sum(const TraceScene& S, const float4* rays, const float4* hits_soa, uint64_t n, unsigned long long* sums4,
+                          cudaStream_t st) {
+  if (n == 0) return 0;
+  k_count_work_sum<<<(unsigned)((n + TRACE_THREADS - 1) / TRACE_THREADS), TRACE_THREADS, 0, st>>>(S, rays, hits_soa, n, sums4);
   return 1;
 }
 
