@@ -1,0 +1,149 @@
+"""Generates the committed fixtures under tests/golden/. Run in the authoring container
+(needs /root/reference for the glm-backed part and the shipped meshes):
+
+    python tools/make_golden.py
+
+  glm_vectors.npz     outputs of the reference's vendored glm (oracle/_ref/libsnkref_glm.so, compiled
+                      against /root/reference/Core/extern/glm) for the host-side matrix producers:
+                      projection, view, TRS, instance 3x4, inverse, normal matrix + determinant, spherical
+  shipped_meshes.json facts parsed from Core/res/meshes/{cube,sphere}.glb (counts, bounds) and, for the
+                      sphere, analytic-vs-mesh hit statistics of the brute-force intersector
+  trace_cornell.npz   seeded rays + brute-force closest / any hits on C1 (oracle)
+  frame_small.npz     3 consecutive reference-mode frames of the small test scene (oracle):
+                      prim ids, depth, both reservoir halves, direct, radiance, ray counts
+"""
+import ctypes as C
+import importlib
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import oracle_api as O  # noqa: E402
+
+snk_scenes = importlib.import_module("snake-vk_b200.scenes")
+assets = importlib.import_module("snake-vk_b200.assets")
+GOLD = os.path.join(ROOT, "tests", "golden")
+REF = "/root/reference"
+
+
+def fp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def glm_vectors():
+    L = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libsnkref_glm.so"))
+    L.ref_projection.argtypes = [C.c_float] * 4 + [C.c_void_p]
+    L.ref_spherical.argtypes = [C.c_float, C.c_float, C.c_void_p]
+    rng = np.random.default_rng(0x5EED)
+    proj_in = np.array([[90, 16 / 9, 0.1, 2500], [90, 1.0, 0.1, 2500], [60, 4 / 3, 0.05, 100], [120, 2.0, 1.0, 10000]], np.float32)
+    proj_out = np.zeros((len(proj_in), 16), np.float32)
+    for i, p in enumerate(proj_in):
+        L.ref_projection(*[C.c_float(float(x)) for x in p], fp(proj_out[i]))
+    n = 16
+    pos = rng.uniform(-20, 20, (n, 3)).astype(np.float32)
+    fwd = rng.normal(size=(n, 3)).astype(np.float32)
+    fwd /= np.linalg.norm(fwd, axis=1, keepdims=True)
+    fwd[0] = (0, 0, 1)
+    fwd[1] = (0.0, -0.05, 1.0) / np.linalg.norm((0.0, -0.05, 1.0))
+    view_out = np.zeros((n, 16), np.float32)
+    for i in range(n):
+        L.ref_view(fp(pos[i]), fp(fwd[i]), fp(view_out[i]))
+    euler = rng.uniform(0, 360, (n, 3)).astype(np.float32)
+    scale = rng.uniform(0.1, 3, (n, 3)).astype(np.float32)
+    euler[0] = 0
+    scale[0] = 1
+    trs_out = np.zeros((n, 16), np.float32)
+    inst_out = np.zeros((n, 12), np.float32)
+    inv_out = np.zeros((n, 16), np.float32)
+    nm_out = np.zeros((n, 9), np.float32)
+    det_out = np.zeros(n, np.float32)
+    mul_out = np.zeros((n, 16), np.float32)
+    for i in range(n):
+        L.ref_trs(fp(pos[i]), fp(euler[i]), fp(scale[i]), fp(trs_out[i]))
+        L.ref_instance_transform(fp(trs_out[i]), fp(inst_out[i]))
+        L.ref_inverse(fp(trs_out[i]), fp(inv_out[i]))
+        L.ref_normal_matrix_det(fp(trs_out[i]), fp(nm_out[i]), fp(det_out[i:i + 1]))
+        L.ref_mul(fp(proj_out[i % len(proj_out)]), fp(view_out[i]), fp(mul_out[i]))
+    sph_in = np.array([[0.8, 0.9], [0.0, 0.0], [1.0, 2.0], [3.0, 0.3]], np.float32)
+    sph_out = np.zeros((len(sph_in), 3), np.float32)
+    for i, (t, p) in enumerate(sph_in):
+        L.ref_spherical(C.c_float(float(t)), C.c_float(float(p)), fp(sph_out[i]))
+    np.savez_compressed(os.path.join(GOLD, "glm_vectors.npz"), proj_in=proj_in, proj_out=proj_out, pos=pos, fwd=fwd, view_out=view_out,
+                        euler=euler, scale=scale, trs_out=trs_out, inst_out=inst_out, inv_out=inv_out, nm_out=nm_out, det_out=det_out,
+                        mul_out=mul_out, sph_in=sph_in, sph_out=sph_out)
+
+
+def shipped_meshes():
+    out = {}
+    for name in ("cube", "sphere"):
+        m = assets.load_glb(os.path.join(REF, "Core", "res", "meshes", f"{name}.glb"))
+        out[name] = {"num_vertices": int(m.positions.shape[0]), "num_triangles": int(m.num_tris),
+                     "bounds_lo": m.positions.min(0).tolist(), "bounds_hi": m.positions.max(0).tolist(),
+                     "num_submeshes": int(m.submeshes.shape[0])}
+        if name == "sphere":
+            # rays from outside towards the origin region: mesh hit vs analytic unit sphere
+            rng = np.random.default_rng(3)
+            n = 4000
+            rays = np.zeros(n, snk_scenes.RAY_DTYPE)
+            o = rng.normal(size=(n, 3))
+            o = 4 * o / np.linalg.norm(o, axis=1, keepdims=True)
+            tgt = rng.uniform(-0.6, 0.6, (n, 3))
+            d = tgt - o
+            d /= np.linalg.norm(d, axis=1, keepdims=True)
+            rays["o"], rays["d"], rays["tmin"], rays["tmax"] = o.astype(np.float32), d.astype(np.float32), 0.0, 100.0
+            sc = snk_scenes.Scene("sphere", 8, 8, [m], [snk_scenes.Entity(0, np.eye(4, dtype=np.float32), [0])],
+                                  snk_scenes.make_materials([((0.8, 0.8, 0.8), 0.5, 0.0, 0)]), snk_scenes.Camera((0, 0, -4), (0, 0, 1)))
+            h = O.OracleScene(sc).trace(rays, brute=True)
+            b = np.einsum("ij,ij->i", o, d)
+            t_an = -b - np.sqrt(b * b - (np.einsum("ij,ij->i", o, o) - 1.0))
+            assert (h["t"] > 0).all()
+            out[name]["analytic_max_abs_dt"] = float(np.abs(h["t"] - t_an).max())  # faceting error of a 960-tri sphere
+    json.dump(out, open(os.path.join(GOLD, "shipped_meshes.json"), "w"), indent=1)
+
+
+def trace_cornell():
+    sc = snk_scenes.cornell(64, 64)
+    rng = np.random.default_rng(11)
+    n = 4000
+    rays = np.zeros(n, snk_scenes.RAY_DTYPE)
+    rays["o"] = rng.uniform((0, 0, -2), (5.5, 5.5, 5.5), (n, 3)).astype(np.float32)
+    d = rng.normal(size=(n, 3))
+    rays["d"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    rays["tmin"], rays["tmax"] = 0.001, 1000.0
+    osc = O.OracleScene(sc)
+    np.savez_compressed(os.path.join(GOLD, "trace_cornell.npz"), rays=rays, closest=osc.trace(rays, brute=True),
+                        any=osc.trace(rays, any_hit=True, brute=True)["t"] >= 0)
+
+
+def frame_small():
+    sc = snk_scenes.small_test_scene(48, 32)
+    osc = O.OracleScene(sc)
+    fr = O.OracleFrame(osc)
+    prev = None
+    out = {}
+    for f in range(3):
+        pos = np.asarray(sc.camera.pos, np.float32) + np.asarray((0.05, 0.0, 0.1), np.float32) * f
+        ubo = sc.ubo(f, cam_pos=pos)
+        fr.set(ubo, ubo if prev is None else prev, O.default_settings())
+        fr.gbuffer()
+        fr.render()
+        prev = ubo
+        for name in ("prim", "inst", "depth", "reservoirs_temporal", "reservoirs_final", "direct", "radiance"):
+            out[f"f{f}_{name}"] = fr.read(name)
+        out[f"f{f}_rays"] = np.array(fr.ray_counts(reset=True), np.uint64)
+    np.savez_compressed(os.path.join(GOLD, "frame_small.npz"), **out)
+
+
+if __name__ == "__main__":
+    O.build_oracle()
+    glm_vectors()
+    shipped_meshes()
+    trace_cornell()
+    frame_small()
+    for f in sorted(os.listdir(GOLD)):
+        print(f, os.path.getsize(os.path.join(GOLD, f)))
