@@ -102,7 +102,9 @@ int traced_launch(SnkPt* ctx, const char* name, const float4* rays, uint64_t n, 
   }
   const TraceScene S = ctx->trace_scene();
   const int rec = prof_begin(ctx, name, n, true, any, st);
-  const int launches = launch_trace(S, rays, n, any, hits_aos, hits_soa, inst_soa, vis_out, st);
+  // every launch draws from its own ticket word (launches of one frame may overlap on different streams later)
+  unsigned long long* ticket = ctx->dev_counters.as<unsigned long long>() + 16 + (ctx->ticket_rr++ & 15u);
+  const int launches = launch_trace(S, rays, n, any, hits_aos, hits_soa, inst_soa, vis_out, ticket, st);
   prof_end(ctx, rec, st);
   if (count && rec >= 0 && hits_soa && ctx->prof_work.reserve(32 * PROF_MAX, false, st) == cudaSuccess) {
     unsigned long long* sums = ctx->prof_work.as<unsigned long long>() + 4 * rec;
@@ -123,6 +125,7 @@ TraceScene SnkPt::trace_scene() const {
   S.inst = inst_recs.as<SnkInstRec>();
   S.overflow = dev_counters.as<uint32_t>();
   S.tlas_node_count = (tlas_built && tlas_prims) ? 1u : 0u;
+  S.spill = trav_spill.as<uint2>();
   return S;
 }
 
@@ -210,8 +213,9 @@ int snkpt_create(const SnkPtConfig* cfg, SnkPt** out) {
     if (e2 == cudaSuccess) e2 = cudaMemsetAsync(ctx->lights.p, 0, sizeof(SnkLightData), ctx->stream);
     if (e2 == cudaSuccess) e2 = ctx->materials.reserve(sizeof(SnkMaterial) * ctx->max_materials, false, ctx->stream);
     if (e2 == cudaSuccess) e2 = cudaMemsetAsync(ctx->materials.p, 0, sizeof(SnkMaterial) * ctx->max_materials, ctx->stream);
-    if (e2 == cudaSuccess) e2 = ctx->dev_counters.reserve(256, false, ctx->stream);
-    if (e2 == cudaSuccess) e2 = cudaMemsetAsync(ctx->dev_counters.p, 0, 256, ctx->stream);
+    if (e2 == cudaSuccess) e2 = ctx->dev_counters.reserve(512, false, ctx->stream);
+    if (e2 == cudaSuccess) e2 = cudaMemsetAsync(ctx->dev_counters.p, 0, 512, ctx->stream);
+    if (e2 == cudaSuccess) e2 = ctx->trav_spill.reserve(trace_spill_bytes(), false, ctx->stream);
     if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(ctx->stream);
     if (e2 != cudaSuccess) { ctx->err = cudaGetErrorString(e2); rc = SNKPT_E_CUDA; }
   }
@@ -227,7 +231,7 @@ void snkpt_destroy(SnkPt* ctx) {
   DevBuf* bufs[] = {&ctx->positions, &ctx->normals, &ctx->tangents, &ctx->uvs, &ctx->indices, &ctx->blas_nodes, &ctx->blas_tris,
                     &ctx->d_blas, &ctx->materials, &ctx->lights, &ctx->transforms, &ctx->prev_transforms, &ctx->normal_mats,
                     &ctx->det3, &ctx->instances, &ctx->blas_of_instance, &ctx->emissive_idx, &ctx->tlas_nodes, &ctx->tlas_leaf_ids,
-                    &ctx->inst_recs, &ctx->valid_slots, &ctx->q_rays, &ctx->q_hits, &ctx->q_work, &ctx->dev_counters};
+                    &ctx->inst_recs, &ctx->valid_slots, &ctx->q_rays, &ctx->q_hits, &ctx->q_work, &ctx->dev_counters, &ctx->trav_spill};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : ctx->wave) b.release();
   for (auto& b : ctx->px) b.release();

@@ -134,7 +134,11 @@ struct SnkPt {
   // generic ray query scratch
   snk::DevBuf q_rays, q_hits, q_work;
   snk::DevBuf wave[12];      // wavefront queues of the bounce stages (rays, hits, shading records)
-  snk::DevBuf dev_counters;  // [0] traversal stack overflows, [1] shadow rays, [2..3] secondary rays (u64)
+  // u32 view: [0] traversal stack overflows, [2..3] shadow rays of the frame, [4..5] closest-hit rays, [8..11] since-create
+  // totals; u64 view [16..31]: ray tickets of the persistent traversal launches
+  snk::DevBuf dev_counters;
+  snk::DevBuf trav_spill;    // global overflow of the short traversal stacks (traverse.cuh)
+  uint32_t ticket_rr = 0;
 
   SnkPtStats stats{};
   cudaEvent_t ev[8] = {};

@@ -8,8 +8,10 @@ namespace snk {
 // rays: 2 x float4 per ray (o,tmin | d,tmax). hits_aos: SnkHit records (20 B) or nullptr;
 // hits_soa / inst_soa: float4 (t,u,v,prim) + u32 planes or nullptr.
 // vis_out: 1.0 = unoccluded / 0.0 = occluded per ray (any-hit queues) or nullptr.
+// ticket: device u64 the persistent kernel draws ray indices from (zeroed by the launcher)
 int launch_trace(const TraceScene& S, const float4* rays, uint64_t n, bool any, SnkHit* hits_aos, float4* hits_soa,
-                 uint32_t* inst_soa, float* vis_out, cudaStream_t st);
+                 uint32_t* inst_soa, float* vis_out, unsigned long long* ticket, cudaStream_t st);
+size_t trace_spill_bytes();
 int launch_count_work(const TraceScene& S, const float4* rays, const SnkHit* hits, uint64_t n, bool any, uint32_t* out3,
                       cudaStream_t st);
 // sums {live rays, nodes, leaf records, instances} of a whole queue into sums4 (hits as float4 with t in .x)

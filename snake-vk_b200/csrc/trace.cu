@@ -7,6 +7,8 @@
 // vkCmdTraceRaysKHR (Core/src/rendering/Raytracing.cpp:253, :260).
 #include "kernels.h"
 
+#include <cstdlib>
+
 namespace snk {
 
 namespace {
@@ -31,6 +33,79 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_trace(TraceScene S, const flo
     if (hits_soa) hits_soa[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
     if (inst_soa) inst_soa[i] = h.inst;
     if (vis_out) vis_out[i] = h.t >= 0.0f ? 0.0f : 1.0f;  // Shadow.rmiss:12 → 1 - float(hit)
+  }
+}
+
+// ---- persistent wavefront kernel with dynamic ray fetch ----------------------------------------------------
+// One warp keeps 32 traversal state machines; lanes whose ray finished pull the next ray index from a global
+// ticket (one atomic per warp and refill) instead of idling until the slowest lane of the warp is done
+// (the static kernel above ran at 7.4 of 32 active lanes on the bounce queues, profiles/r01a_prof_trace.txt).
+// A refill is triggered once the warp has accumulated PT_LOST_MAX idle lane-iterations beyond PT_IDLE_OK per
+// iteration (Aila & Laine 2009 / Ylitie et al. 2017 dynamic fetch). Results are written per ray index, so the
+// output is independent of the fetch order.
+constexpr int PT_IDLE_OK = 4;
+constexpr int PT_LOST_MAX = 16;
+constexpr int PT_CTAS_PER_SM = 8;
+
+template <bool ANY>
+__global__ void __launch_bounds__(TRACE_THREADS, PT_CTAS_PER_SM)
+k_trace_pt(TraceScene S, const float4* __restrict__ rays, unsigned long long n, unsigned long long* __restrict__ ticket,
+           SnkHit* __restrict__ hits_aos, float4* __restrict__ hits_soa, uint32_t* __restrict__ inst_soa, float* __restrict__ vis_out) {
+  __shared__ uint2 sm_stack[SHORT_STACK * TRACE_THREADS];
+  const uint32_t lane = threadIdx.x & 31u;
+  const StackRef stk{sm_stack + threadIdx.x,
+                     S.spill + ((size_t)blockIdx.x * (TRACE_THREADS / 32) + (threadIdx.x >> 5)) * (SPILL_STACK * 32) + lane};
+  Trav t;
+  bool active = false, exhausted = false;
+  unsigned long long idx = 0;
+  auto write_result = [&](unsigned long long i, const HitRec& h) {
+    if (hits_aos) { SnkHit o; o.t = h.t; o.u = h.u; o.v = h.v; o.prim = h.prim; o.inst = h.inst; hits_aos[i] = o; }
+    if (hits_soa) hits_soa[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
+    if (inst_soa) inst_soa[i] = h.inst;
+    if (vis_out) vis_out[i] = h.t >= 0.0f ? 0.0f : 1.0f;  // Shadow.rmiss:12 → 1 - float(hit)
+  };
+  while (true) {
+    // ---- refill: every lane without a ray takes the next index; dead slots (tmax <= tmin) resolve at once
+    for (int round = 0; round < 4; ++round) {
+      const uint32_t need = __ballot_sync(0xFFFFFFFFu, !active);
+      if (need == 0u || exhausted) break;
+      const uint32_t cnt = __popc(need);
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(ticket, (unsigned long long)cnt);
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      if (!active) {
+        const unsigned long long i = base + __popc(need & ((1u << lane) - 1u));
+        if (i < n) {
+          const float4 a = __ldg(rays + 2 * i), b = __ldg(rays + 2 * i + 1);
+          trav_begin(t, a, b);
+          if (b.w > a.w && S.tlas_node_count) { active = true; idx = i; }
+          else write_result(i, t.best);
+        }
+      }
+      if (base + cnt >= n) exhausted = true;
+    }
+    if (__ballot_sync(0xFFFFFFFFu, active) == 0u) {
+      if (exhausted) break;
+      continue;
+    }
+    // ---- traverse; the three phases are warp-synchronous (the ballots reconverge all 32 lanes per iteration)
+    int lost = 0;
+    while (true) {
+      if (active && trav_wants_node(t)) trav_node<TRACE_THREADS>(S, t, stk);
+      __syncwarp();
+      bool done = false;
+      if (active && t.T.y) done = trav_leaf<ANY, TRACE_THREADS>(S, t, stk);
+      __syncwarp();
+      if (active && !done && t.T.y == 0u && (t.G.y & 0xFF000000u) == 0u) done = trav_pop<TRACE_THREADS>(t, stk);
+      if (done) { write_result(idx, t.best); active = false; }
+      const uint32_t live = __ballot_sync(0xFFFFFFFFu, active);
+      if (live == 0u) break;
+      if (!exhausted) {
+        lost += (32 - __popc(live)) - PT_IDLE_OK;
+        if (lost < 0) lost = 0;
+        if (lost >= PT_LOST_MAX) break;
+      }
+    }
   }
 }
 
@@ -141,11 +216,21 @@ static int trace_grid(uint64_t n) {
   return (int)(blocks < persistent ? (blocks ? blocks : 1) : persistent);
 }
 
+size_t trace_spill_bytes() { return (size_t)148 * PT_CTAS_PER_SM * (TRACE_THREADS / 32) * SPILL_STACK * 32 * sizeof(uint2); }
+
 int launch_trace(const TraceScene& S, const float4* rays, uint64_t n, bool any, SnkHit* hits_aos, float4* hits_soa,
-                 uint32_t* inst_soa, float* vis_out, cudaStream_t st) {
+                 uint32_t* inst_soa, float* vis_out, unsigned long long* ticket, cudaStream_t st) {
   if (n == 0) return 0;
-  if (any) k_trace<true><<<trace_grid(n), TRACE_THREADS, 0, st>>>(S, rays, n, hits_aos, hits_soa, inst_soa, vis_out);
-  else k_trace<false><<<trace_grid(n), TRACE_THREADS, 0, st>>>(S, rays, n, hits_aos, hits_soa, inst_soa, vis_out);
+  static const bool use_static = getenv("SNKPT_TRACE_STATIC") != nullptr;  // A/B switch for profiles/ evidence
+  if (use_static || !ticket || !S.spill) {
+    if (any) k_trace<true><<<trace_grid(n), TRACE_THREADS, 0, st>>>(S, rays, n, hits_aos, hits_soa, inst_soa, vis_out);
+    else k_trace<false><<<trace_grid(n), TRACE_THREADS, 0, st>>>(S, rays, n, hits_aos, hits_soa, inst_soa, vis_out);
+    return 1;
+  }
+  cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st);
+  const int grid = trace_grid(n);
+  if (any) k_trace_pt<true><<<grid, TRACE_THREADS, 0, st>>>(S, rays, n, ticket, hits_aos, hits_soa, inst_soa, vis_out);
+  else k_trace_pt<false><<<grid, TRACE_THREADS, 0, st>>>(S, rays, n, ticket, hits_aos, hits_soa, inst_soa, vis_out);
   return 1;
 }
 

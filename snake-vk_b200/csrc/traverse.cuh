@@ -27,6 +27,7 @@ struct TraceScene {
   const SnkInstRec* inst;         // indexed by instance slot
   uint32_t* overflow;             // device counter: traversal stack overflows (must stay 0)
   uint32_t tlas_node_count;       // 0 = nothing to hit
+  uint2* spill;                   // global overflow area of the short stacks (persistent kernels), SPILL_STACK x 32 per warp
 };
 
 struct HitRec {
@@ -250,6 +251,174 @@ __device__ __forceinline__ void trace_ray(const TraceScene& S, float ox, float o
       if (finished) break;
     }
   }
+}
+
+// ---- state-machine form (persistent wavefront kernels) ---------------------------------------------------
+// Same traversal as trace_ray, cut into three warp-synchronous phases per iteration so that (a) lanes
+// reconverge every iteration, (b) each phase runs with as many lanes as possible and (c) a warp can swap
+// finished rays for new ones between iterations (dynamic fetch):
+//   node phase  lanes with an inner-node hit pending open the nearest child (5 x 128-bit node load, 8 box tests)
+//   leaf phase  lanes with leaf records pending take ONE record: a triangle test in a BLAS, an instance entry in the TLAS
+//   pop phase   lanes whose group is exhausted pop the stack (a sentinel pops back to world space)
+// Stack: SHORT_STACK entries per lane in shared memory (interleaved by thread), deeper entries in a per-warp
+// global spill area (interleaved by lane) that stays L1/L2 resident.
+constexpr int SHORT_STACK = 8;
+constexpr int SPILL_STACK = 40;
+
+struct StackRef {
+  uint2* sm;  // this thread's column of the shared short stack (stride = CTA threads)
+  uint2* gl;  // this lane's column of the warp's spill area (stride = 32)
+};
+
+struct Trav {
+  float ox, oy, oz, tmin, dx, dy, dz;  // world-space ray
+  float tcur;                          // tmax, shrinking to the closest hit
+  float tmax;
+  RaySpace r;                          // current space (world in the TLAS, object in a BLAS)
+  uint2 G, T;                          // pending node group / leaf-record group
+  int sp;
+  uint32_t cur_inst;
+  bool in_blas, tri_ready;             // tri_ready: the Woop constants of r are valid for the current space
+  HitRec best;
+};
+
+template <int STRIDE>
+__device__ __forceinline__ void stk_push(const StackRef& s, int& sp, uint2 v, uint32_t* overflow) {
+  if (sp < SHORT_STACK) s.sm[sp * STRIDE] = v;
+  else if (sp < SHORT_STACK + SPILL_STACK) s.gl[(sp - SHORT_STACK) * 32] = v;
+  else atomicAdd(overflow, 1u);
+  sp += sp < SHORT_STACK + SPILL_STACK ? 1 : 0;
+}
+template <int STRIDE>
+__device__ __forceinline__ uint2 stk_pop(const StackRef& s, int& sp) {
+  --sp;
+  return sp < SHORT_STACK ? s.sm[sp * STRIDE] : s.gl[(sp - SHORT_STACK) * 32];
+}
+
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// box-test part of the ray space: origin, reciprocal direction, octant. The reciprocal only feeds the
+// (padded, conservative) box tests, so the 1-ulp approximation is enough.
+__device__ __forceinline__ void setup_box_space(RaySpace& r, float ox, float oy, float oz, float dx, float dy, float dz) {
+  r.ox = ox; r.oy = oy; r.oz = oz; r.dx = dx; r.dy = dy; r.dz = dz;
+  const float cx = fabsf(dx) > 1e-20f ? dx : copysignf(1e-20f, dx);
+  const float cy = fabsf(dy) > 1e-20f ? dy : copysignf(1e-20f, dy);
+  const float cz = fabsf(dz) > 1e-20f ? dz : copysignf(1e-20f, dz);
+  r.idx = rcp_approx(cx); r.idy = rcp_approx(cy); r.idz = rcp_approx(cz);
+  const uint32_t oct = (r.idx < 0.f ? 1u : 0u) | (r.idy < 0.f ? 2u : 0u) | (r.idz < 0.f ? 4u : 0u);
+  r.octinv = 7u - oct;
+}
+// triangle-test part (Woop et al. 2013 dominant axis + shear), bit-identical to oracle/snk_scene.h ray_pre
+__device__ __forceinline__ void setup_tri_space(RaySpace& r) {
+  const float dx = r.dx, dy = r.dy, dz = r.dz;
+  const float ax = fabsf(dx), ay = fabsf(dy), az = fabsf(dz);
+  int kz = 0;
+  if (ay > ax) kz = 1;
+  if (az > (kz == 0 ? ax : ay)) kz = 2;
+  int kx = kz + 1; if (kx == 3) kx = 0;
+  int ky = kx + 1; if (ky == 3) ky = 0;
+  const float dkz = sel3(dx, dy, dz, kz);
+  if (dkz < 0.0f) { const int t = kx; kx = ky; ky = t; }
+  r.kx = kx; r.ky = ky; r.kz = kz;
+  r.Sx = __fdiv_rn(sel3(dx, dy, dz, kx), dkz);
+  r.Sy = __fdiv_rn(sel3(dx, dy, dz, ky), dkz);
+  r.Sz = __fdiv_rn(1.0f, dkz);
+}
+
+__device__ __forceinline__ void trav_begin(Trav& t, float4 a, float4 b) {
+  t.ox = a.x; t.oy = a.y; t.oz = a.z; t.tmin = a.w; t.dx = b.x; t.dy = b.y; t.dz = b.z; t.tcur = b.w; t.tmax = b.w;
+  setup_box_space(t.r, a.x, a.y, a.z, b.x, b.y, b.z);
+  t.G = make_uint2(0u, 0x80000000u);
+  t.T = make_uint2(0u, 0u);
+  t.sp = 0; t.cur_inst = 0; t.in_blas = false; t.tri_ready = false;
+  t.best.t = -1.0f; t.best.u = 0.f; t.best.v = 0.f; t.best.prim = 0xFFFFFFFFu; t.best.inst = 0xFFFFFFFFu;
+}
+
+__device__ __forceinline__ bool trav_wants_node(const Trav& t) { return t.T.y == 0u && (t.G.y & 0xFF000000u) != 0u; }
+
+// node phase (call with the lanes for which trav_wants_node holds)
+template <int STRIDE>
+__device__ __forceinline__ void trav_node(const TraceScene& S, Trav& t, const StackRef& stk) {
+  const uint4* nodes = t.in_blas ? S.blas_nodes : S.tlas_nodes;
+  const uint32_t hits_imask = t.G.y;
+  const uint32_t bit = 31u - __clz(hits_imask);
+  t.G.y &= ~(1u << bit);
+  if (t.G.y & 0xFF000000u) stk_push<STRIDE>(stk, t.sp, t.G, S.overflow);
+  const uint32_t slot = (bit - 24u) ^ t.r.octinv;
+  const uint32_t rel = __popc(hits_imask & ~(0xFFFFFFFFu << slot) & 0xFFu);
+  uint4 n0, n1, n2, n3, n4;
+  load_node(nodes, t.G.x + rel, n0, n1, n2, n3, n4);
+  const uint32_t hm = intersect_node(t.r, n0, n1, n2, n3, n4, t.tmin, t.tcur);
+  t.G = make_uint2(n1.x, (hm & 0xFF000000u) | (n0.w >> 24));
+  t.T = make_uint2(n1.y, hm & 0x00FFFFFFu);
+}
+
+// leaf phase (call with the lanes that have t.T.y != 0): one record. Returns true when an ANY ray is done.
+template <bool ANY, int STRIDE>
+__device__ __forceinline__ bool trav_leaf(const TraceScene& S, Trav& t, const StackRef& stk) {
+  const uint32_t bit = __ffs(t.T.y) - 1;
+  t.T.y &= ~(1u << bit);
+  bool done = false;
+  if (!t.in_blas) {
+    // TLAS leaf record → enter the instance
+    const uint32_t slot = __ldg(S.tlas_leaf_ids + t.T.x + bit);
+    if (t.T.y) stk_push<STRIDE>(stk, t.sp, t.T, S.overflow);
+    if (t.G.y & 0xFF000000u) stk_push<STRIDE>(stk, t.sp, t.G, S.overflow);
+    stk_push<STRIDE>(stk, t.sp, make_uint2(TRAV_SENTINEL, 0u), S.overflow);
+    const float4* M = reinterpret_cast<const float4*>(S.inst + slot);
+    const float4 r0 = __ldg(M), r1 = __ldg(M + 1), r2 = __ldg(M + 2);
+    const uint4 meta = __ldg(reinterpret_cast<const uint4*>(M + 3));
+    // o' = ((m0*x + m1*y) + m2*z) + m3 ; d' = (m0*x + m1*y) + m2*z   (unfused, as the oracle)
+    const float oox = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0.x, t.ox), __fmul_rn(r0.y, t.oy)), __fmul_rn(r0.z, t.oz)), r0.w);
+    const float ooy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r1.x, t.ox), __fmul_rn(r1.y, t.oy)), __fmul_rn(r1.z, t.oz)), r1.w);
+    const float ooz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2.x, t.ox), __fmul_rn(r2.y, t.oy)), __fmul_rn(r2.z, t.oz)), r2.w);
+    const float odx = __fadd_rn(__fadd_rn(__fmul_rn(r0.x, t.dx), __fmul_rn(r0.y, t.dy)), __fmul_rn(r0.z, t.dz));
+    const float ody = __fadd_rn(__fadd_rn(__fmul_rn(r1.x, t.dx), __fmul_rn(r1.y, t.dy)), __fmul_rn(r1.z, t.dz));
+    const float odz = __fadd_rn(__fadd_rn(__fmul_rn(r2.x, t.dx), __fmul_rn(r2.y, t.dy)), __fmul_rn(r2.z, t.dz));
+    setup_box_space(t.r, oox, ooy, ooz, odx, ody, odz);
+    t.in_blas = true; t.tri_ready = false;
+    t.cur_inst = meta.y;
+    t.G = make_uint2(meta.x, 0x80000000u);
+    t.T = make_uint2(0u, 0u);
+  } else {
+    if (!t.tri_ready) { setup_tri_space(t.r); t.tri_ready = true; }
+    const float4* tp = S.tris + 3ull * (t.T.x + bit);
+    const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
+    float th, u, v;
+    if (tri_test(t.r, p0, p1, p2, th, u, v) && th > t.tmin && th < t.tmax) {
+      const uint32_t prim = __float_as_uint(p0.w);
+      bool take;
+      if (ANY) take = true;
+      else take = t.best.t < 0.0f || th < t.best.t ||
+                  (th == t.best.t && (t.cur_inst < t.best.inst || (t.cur_inst == t.best.inst && prim < t.best.prim)));
+      if (take) {
+        t.best.t = th; t.best.u = u; t.best.v = v; t.best.prim = prim; t.best.inst = t.cur_inst;
+        t.tcur = th;
+        done = ANY;
+      }
+    }
+  }
+  return done;
+}
+
+// pop phase (call with lanes that have neither leaf records nor inner hits pending). Returns true when the
+// stack is empty, i.e. the ray is finished.
+template <int STRIDE>
+__device__ __forceinline__ bool trav_pop(Trav& t, const StackRef& stk) {
+  if (t.sp == 0) return true;
+  uint2 e = stk_pop<STRIDE>(stk, t.sp);
+  if (e.x == TRAV_SENTINEL) {
+    // leave the instance: back to world space (no triangles are tested in the TLAS, so only the box part)
+    setup_box_space(t.r, t.ox, t.oy, t.oz, t.dx, t.dy, t.dz);
+    t.in_blas = false; t.tri_ready = false;
+    e = make_uint2(0u, 0u);
+  }
+  if (e.y & 0xFF000000u) t.G = e;
+  else { t.T = e; t.G = make_uint2(0u, 0u); }
+  return false;
 }
 
 }  // namespace snk

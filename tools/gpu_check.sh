@@ -16,10 +16,12 @@ for w in $WHAT; do
     benchref) timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; cat $OUT/bench_ref.json;;
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches.csv \
         python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/launches_bench.log 2>&1; echo "launches rc=$?";;
-    ncu) timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_trace -s 4 -c 4 -f -o $OUT/prof_trace \
-        python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_trace.log 2>&1; echo "ncu rc=$?";;
-    ncurestir) timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_restir -s 2 -c 2 -f -o $OUT/prof_restir \
-        python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_restir.log 2>&1; echo "ncu rc=$?";;
+    ncu) timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_trace -s ${NCU_SKIP:-4} -c ${NCU_COUNT:-4} -f -o $OUT/prof_trace \
+        python tools/quick_bench.py ${SCENES:-c2} > $OUT/ncu_trace.log 2>&1; echo "ncu rc=$?";;
+    quick) timeout 600 python tools/quick_bench.py ${SCENES:-c2 c2flat} > $OUT/quick.log 2>&1; echo "quick rc=$?"; cat $OUT/quick.log;;
+    quickstatic) SNKPT_TRACE_STATIC=1 timeout 600 python tools/quick_bench.py ${SCENES:-c2} > $OUT/quick_static.log 2>&1; cat $OUT/quick_static.log;;
+    ncurestir) timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_restir -s 4 -c 2 -f -o $OUT/prof_restir \
+        python tools/quick_bench.py ${SCENES:-c2} > $OUT/ncu_restir.log 2>&1; echo "ncu rc=$?";;
   esac
 done
 ls -la $OUT
