@@ -18,23 +18,32 @@ namespace {
 constexpr float PRIMARY_TMIN = 0.1f;  // CameraComponent.h:11 z_near
 constexpr float PRIMARY_TMAX = 10000.0f;
 
-__global__ void __launch_bounds__(128) k_primary(TraceScene S, SceneDev D, FrameConsts fc, PixelPlanes P) {
-  // 16x8 pixel tile per CTA, 8x4 per warp (coherent primary rays)
-  SNK_DECLARE_TRAV_STACK(128);
+constexpr int PRIMARY_CTAS_PER_SM = 6;
+
+__global__ void __launch_bounds__(128, PRIMARY_CTAS_PER_SM) k_primary(TraceScene S, SceneDev D, FrameConsts fc, PixelPlanes P) {
+  // persistent CTAs walk 16x8 pixel tiles, 8x4 pixels per warp (coherent primary rays)
+  __shared__ uint2 sm_stack[SHORT_STACK * 128];
   const uint32_t t = threadIdx.x, w = t >> 5, l = t & 31;
-  const uint32_t x = blockIdx.x * 16 + (w & 1) * 8 + (l & 7);
-  const uint32_t y = fc.row0 + blockIdx.y * 8 + (w >> 1) * 4 + (l >> 3);
-  if (x >= fc.W || y >= fc.row1) return;
-  const size_t px = (size_t)y * fc.W + x;
+  const StackRef stk{sm_stack + t, S.spill + ((size_t)blockIdx.x * 4 + w) * (SPILL_STACK * 32) + l};
+  const uint32_t tiles_x = (fc.W + 15u) / 16u, n_tiles = tiles_x * ((fc.row1 - fc.row0 + 7u) / 8u);
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  const uint32_t x = (tile % tiles_x) * 16 + (w & 1) * 8 + (l & 7);
+  const uint32_t y = fc.row0 + (tile / tiles_x) * 8 + (w >> 1) * 4 + (l >> 3);
+  const bool in_range = x < fc.W && y < fc.row1;
+  const size_t px = in_range ? (size_t)y * fc.W + x : 0;
+  if (in_range) {
   P.prev_normal[px] = P.normal[px];
   P.prev_depth[px] = P.depth[px];
+  }
 
   const float u = (((float)x + 0.5f) + fc.jx) / (float)fc.W, v = (((float)y + 0.5f) + fc.jy) / (float)fc.H;
   const vec3 cam = v3(fc.cam_pos[0], fc.cam_pos[1], fc.cam_pos[2]);
   const vec3 far = world_pos_from_depth(fc.ivp, 1.0f, u, v);
   const vec3 d = normalize(far - cam);
   HitRec h;
-  trace_ray<false, 128>(S, cam.x, cam.y, cam.z, PRIMARY_TMIN, d.x, d.y, d.z, PRIMARY_TMAX, snk_trav_stack + t, h);
+  trace_warp_body<false, 128>(S, make_float4(cam.x, cam.y, cam.z, PRIMARY_TMIN), make_float4(d.x, d.y, d.z, in_range ? PRIMARY_TMAX : -1.0f),
+                              stk, h);
+  if (!in_range) continue;
   P.prim[px] = h.prim; P.inst[px] = h.inst; P.hit_t[px] = h.t;
   if (h.t < 0.0f) {
     P.bary[px] = make_float2(0.f, 0.f);
@@ -44,7 +53,7 @@ __global__ void __launch_bounds__(128) k_primary(TraceScene S, SceneDev D, Frame
     P.depth[px] = 1.0f;
     P.motion[px] = make_ushort2(0, 0);
     P.flags[px] = 0;
-    return;
+    continue;
   }
   P.bary[px] = make_float2(h.u, h.v);
   const SnkInstanceData in = D.instances[h.inst];
@@ -75,6 +84,7 @@ __global__ void __launch_bounds__(128) k_primary(TraceScene S, SceneDev D, Frame
   P.normal[px] = make_ushort4(f2h(n.x), f2h(n.y), f2h(n.z), f2h(1.0f));
   P.rma[px] = make_ushort4(f2h(m->roughness), f2h(m->metallic), f2h(m->ao), f2h(1.0f));
   P.flags[px] = (uint16_t)m->flags;
+  }
 }
 
 __global__ void k_accumulate(const float4* __restrict__ radiance, float4* __restrict__ accum, ushort4* __restrict__ out16,
@@ -93,7 +103,8 @@ __global__ void k_accumulate(const float4* __restrict__ radiance, float4* __rest
 
 int launch_primary(const TraceScene& S, const SceneDev& D, const FrameConsts& fc, const PixelPlanes& P, cudaStream_t st) {
   if (fc.row1 <= fc.row0) return 0;
-  dim3 grid((fc.W + 15) / 16, (fc.row1 - fc.row0 + 7) / 8);
+  const uint32_t n_tiles = ((fc.W + 15) / 16) * ((fc.row1 - fc.row0 + 7) / 8);
+  const uint32_t grid = n_tiles < 148u * PRIMARY_CTAS_PER_SM ? n_tiles : 148u * PRIMARY_CTAS_PER_SM;
   k_primary<<<grid, 128, 0, st>>>(S, D, fc, P);
   return 1;
 }

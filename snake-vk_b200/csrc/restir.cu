@@ -37,17 +37,26 @@ struct Px {
 };
 
 struct Tracer {
-  const TraceScene& S;
-  uint2* stk;
+  const TraceScene* S;  // CTA-shared copy of the kernel parameter (the tracer is a real call, see traverse.cuh)
+  uint2 *sm_col, *gl_col;
   unsigned long long n_any;
   __device__ __forceinline__ float shadow(bool valid, vec3 ro, vec3 rd, float max_dist) {  // RayGen.rgen:101-121
-    HitRec h;
-    trace_ray<true, RT_THREADS>(S, ro.x, ro.y, ro.z, 0.001f, rd.x, rd.y, rd.z, valid ? max_dist : -1.0f, stk, h);
-    __syncwarp();
+    const float hit = trace_warp_any<RT_THREADS>(S, ro.x, ro.y, ro.z, 0.001f, rd.x, rd.y, rd.z, valid ? max_dist : -1.0f, sm_col, gl_col);
     if (valid) ++n_any;
-    return 1.0f - (h.t >= 0.0f ? 1.0f : 0.0f);
+    return 1.0f - hit;
   }
 };
+
+// persistent CTAs: RT_CTAS_PER_SM x 148 CTAs walk the 16x8 pixel tiles of the band
+constexpr int RT_CTAS_PER_SM = 4;
+#define SNK_RT_PROLOGUE()                                                                                              \
+  __shared__ uint2 sm_stack[SHORT_STACK * RT_THREADS];                                                                 \
+  __shared__ TraceScene sS;                                                                                            \
+  if (threadIdx.x == 0) sS = S;                                                                                        \
+  __syncthreads();                                                                                                     \
+  Tracer T{&sS, sm_stack + threadIdx.x,                                                                                \
+           S.spill + ((size_t)blockIdx.x * (RT_THREADS / 32) + (threadIdx.x >> 5)) * (SPILL_STACK * 32) + (threadIdx.x & 31u), 0ull}; \
+  const uint32_t tiles_x = (fc.W + 15u) / 16u, n_tiles = tiles_x * ((fc.row1 - fc.row0 + 7u) / 8u)
 
 __device__ __forceinline__ Px load_px(const FrameConsts& fc, const PixelPlanes& P, uint32_t x, uint32_t y, bool in_range) {
   Px q;
@@ -218,21 +227,21 @@ __device__ vec3 prev_normal_bilinear(const PixelPlanes& P, int W, int H, float u
   return top * (1.0f - b) + bot * b;
 }
 
-__device__ __forceinline__ void tile_xy(const FrameConsts& fc, uint32_t& x, uint32_t& y, bool& in_range) {
+__device__ __forceinline__ void tile_xy(const FrameConsts& fc, uint32_t tile, uint32_t tiles_x, uint32_t& x, uint32_t& y, bool& in_range) {
   const uint32_t t = threadIdx.x, w = t >> 5, l = t & 31;
-  x = blockIdx.x * 16 + (w & 1) * 8 + (l & 7);
-  y = fc.row0 + blockIdx.y * 8 + (w >> 1) * 4 + (l >> 3);
+  x = (tile % tiles_x) * 16 + (w & 1) * 8 + (l & 7);
+  y = fc.row0 + (tile / tiles_x) * 8 + (w >> 1) * 4 + (l >> 3);
   in_range = x < fc.W && y < fc.row1;
 }
 
 // ---- pass 1: WriteInitialReservoirs (RayGen.rgen:411-468) --------------------------------------------------
-__global__ void __launch_bounds__(RT_THREADS) k_restir_pass1(TraceScene S, SceneDev D, FrameConsts fc, PixelPlanes P, RestirParams rp,
-                                                             unsigned long long* ray_counter) {
-  SNK_DECLARE_TRAV_STACK(RT_THREADS);
+__global__ void __launch_bounds__(RT_THREADS, RT_CTAS_PER_SM) k_restir_pass1(TraceScene S, SceneDev D, FrameConsts fc, PixelPlanes P,
+                                                                             RestirParams rp, unsigned long long* ray_counter) {
+  SNK_RT_PROLOGUE();
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
   uint32_t x, y; bool in_range;
-  tile_xy(fc, x, y, in_range);
+  tile_xy(fc, tile, tiles_x, x, y, in_range);
   const Px q = load_px(fc, P, x, y, in_range);
-  Tracer T{S, snk_trav_stack + threadIdx.x, 0ull};
   const ResPlanes half0{P.res[0][0], P.res[0][1], P.res[0][2]}, half1{P.res[1][0], P.res[1][1], P.res[1][2]};
   Reservoir pixel, temporal;
   init_reservoir(pixel);
@@ -280,6 +289,7 @@ __global__ void __launch_bounds__(RT_THREADS) k_restir_pass1(TraceScene S, Scene
   }
   // quirk 4: without usable history the EMPTY temporal reservoir is written (initial candidates are dropped)
   if (in_range && !(P.flags[(size_t)y * fc.W + x] & SNKPT_MAT_FLAG_EMISSIVE)) store_reservoir(half1, (size_t)y * fc.W + x, temporal);
+  }
   // ray statistics: one atomic per warp
   unsigned long long n = T.n_any;
   for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, o);
@@ -304,13 +314,13 @@ __device__ void find_neighbour(const Px& q, float sx, float sy, float radius, fl
 }
 
 // ---- pass 2 (direct part) ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RT_THREADS) k_restir_pass2(TraceScene S, SceneDev D, FrameConsts fc, PixelPlanes P, RestirParams rp,
-                                                             unsigned long long* ray_counter) {
-  SNK_DECLARE_TRAV_STACK(RT_THREADS);
+__global__ void __launch_bounds__(RT_THREADS, RT_CTAS_PER_SM) k_restir_pass2(TraceScene S, SceneDev D, FrameConsts fc, PixelPlanes P,
+                                                                             RestirParams rp, unsigned long long* ray_counter) {
+  SNK_RT_PROLOGUE();
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
   uint32_t x, y; bool in_range;
-  tile_xy(fc, x, y, in_range);
+  tile_xy(fc, tile, tiles_x, x, y, in_range);
   const Px q = load_px(fc, P, x, y, in_range);
-  Tracer T{S, snk_trav_stack + threadIdx.x, 0ull};
   const ResPlanes half0{P.res[0][0], P.res[0][1], P.res[0][2]}, half1{P.res[1][0], P.res[1][1], P.res[1][2]};
   const size_t px = in_range ? (size_t)y * fc.W + x : 0;
   const bool restir = !(rp.flags & SNKPT_RT_NO_RESTIR);
@@ -395,6 +405,7 @@ __global__ void __launch_bounds__(RT_THREADS) k_restir_pass2(TraceScene S, Scene
     if (on) light += radiance;
   }
   if (in_range) P.direct[px] = make_float4(light.x, light.y, light.z, 1.0f);
+  }
   unsigned long long n = T.n_any;
   for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xFFFFFFFFu, n, o);
   if ((threadIdx.x & 31) == 0 && n) atomicAdd(ray_counter, n);
@@ -404,7 +415,8 @@ __global__ void __launch_bounds__(RT_THREADS) k_restir_pass2(TraceScene S, Scene
 
 int launch_restir_passes(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st) {
   const FrameConsts& fc = ctx->fc;
-  dim3 grid((fc.W + 15) / 16, (fc.row1 - fc.row0 + 7) / 8);
+  const uint32_t n_tiles = ((fc.W + 15) / 16) * ((fc.row1 - fc.row0 + 7) / 8);
+  const uint32_t grid = n_tiles < 148u * RT_CTAS_PER_SM ? n_tiles : 148u * RT_CTAS_PER_SM;
   RestirParams rp{s.num_temporal_resamples, s.num_spatial_resamples, s.ris_iters, s.m_cap, s.neighbour_radius, s.normal_threshold, s.flags};
   unsigned long long* counter = reinterpret_cast<unsigned long long*>(ctx->dev_counters.as<uint32_t>() + 2);
   FrameConsts f = fc;

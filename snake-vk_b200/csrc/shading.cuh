@@ -62,7 +62,7 @@ __device__ __forceinline__ float geometry_smith(vec3 v, vec3 l, vec3 n, float ro
   const float ggx1 = geometry_schlick_ggx(n_dot_l, roughness);
   return ggx2 * ggx1;
 }
-__device__ __forceinline__ vec3 cook_torrance_brdf(vec3 light_pos, vec3 surface_pos, vec3 v, vec3 f0, vec3 n, float roughness, float metallic) {
+static __device__ __noinline__ vec3 cook_torrance_brdf(vec3 light_pos, vec3 surface_pos, vec3 v, vec3 f0, vec3 n, float roughness, float metallic) {
   const vec3 frag_to_light = light_pos - surface_pos;
   const vec3 l = normalize(frag_to_light);
   const vec3 h = normalize(v + l);
@@ -77,7 +77,7 @@ __device__ __forceinline__ vec3 cook_torrance_brdf(vec3 light_pos, vec3 surface_
   kd *= 1.0f - metallic;
   return (kd / PI_GLSL + specular) * n_dot_l;
 }
-__device__ __forceinline__ vec3 calc_directional_light(vec3 ldir, vec3 lcol, vec3 v, vec3 f0, vec3 n, float roughness, float metallic, vec3 albedo) {
+static __device__ __noinline__ vec3 calc_directional_light(vec3 ldir, vec3 lcol, vec3 v, vec3 f0, vec3 n, float roughness, float metallic, vec3 albedo) {
   const vec3 l = ldir;
   const vec3 h = normalize(v + l);
   const vec3 f = fresnel_schlick(gmax(dot(h, v), 0.0f), f0);
@@ -139,7 +139,7 @@ __device__ __forceinline__ SnkInstanceData load_instance(const SceneDev& D, uint
 // point on an emissive triangle: shared head of RayGen.rgen:241-251 and :258-268.
 // bary = (bx, by, 1-bx-by) weights of (ti.x, ti.y, ti.z) — NOT the hit-attribute convention.
 struct TriPoint { vec3 p, n, emissive; };
-__device__ __forceinline__ TriPoint triangle_point(const SceneDev& D, uint32_t obj, uint32_t tri, float bx, float by) {
+static __device__ __noinline__ TriPoint triangle_point(const SceneDev& D, uint32_t obj, uint32_t tri, float bx, float by) {
   const SnkInstanceData in = load_instance(D, obj);
   uint32_t ia, ib, ic;
   tri_indices(D, in, tri, ia, ib, ic);

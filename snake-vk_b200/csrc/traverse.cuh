@@ -421,4 +421,35 @@ __device__ __forceinline__ bool trav_pop(Trav& t, const StackRef& stk) {
   return false;
 }
 
+// ---- warp-synchronous inline tracer (shading kernels) --------------------------------------------------------
+// The lanes of a warp that are converged at the call trace one ray each through the same three phases;
+// lanes without a ray pass tmax <= tmin. NOT inlined: the ReSTIR kernels call it from up to 11 program
+// points, and the inlined copies (13 K SASS instructions per kernel) stalled 70-80 % of all issue slots on
+// instruction-cache misses (profiles/r01c_prof_restir.txt).
+template <bool ANY, int STRIDE>
+__device__ __forceinline__ void trace_warp_body(const TraceScene& S, float4 a, float4 b, const StackRef& stk, HitRec& best) {
+  const uint32_t warp = __activemask();
+  Trav t;
+  trav_begin(t, a, b);
+  bool active = b.w > a.w && S.tlas_node_count != 0u;
+  while (__ballot_sync(warp, active)) {
+    if (active && trav_wants_node(t)) trav_node<STRIDE>(S, t, stk);
+    __syncwarp(warp);
+    bool done = false;
+    if (active && t.T.y) done = trav_leaf<ANY, STRIDE>(S, t, stk);
+    __syncwarp(warp);
+    if (active && !done && t.T.y == 0u && (t.G.y & 0xFF000000u) == 0u) done = trav_pop<STRIDE>(t, stk);
+    if (done) active = false;
+  }
+  best = t.best;
+}
+// returns 1.0 when a hit exists in (tmin, tmax), else 0.0 (RayGen.rgen:101-121 ShadowTest → payload.hit)
+template <int STRIDE>
+__device__ __noinline__ float trace_warp_any(const TraceScene* S, float ox, float oy, float oz, float tmin, float dx, float dy, float dz,
+                                             float tmax, uint2* sm_col, uint2* gl_col) {
+  HitRec h;
+  trace_warp_body<true, STRIDE>(*S, make_float4(ox, oy, oz, tmin), make_float4(dx, dy, dz, tmax), StackRef{sm_col, gl_col}, h);
+  return h.t >= 0.0f ? 1.0f : 0.0f;
+}
+
 }  // namespace snk

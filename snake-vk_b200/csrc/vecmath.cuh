@@ -48,9 +48,11 @@ __device__ __forceinline__ float gclamp(float x, float lo, float hi) { return gm
 __device__ __forceinline__ float fract(float x) { return x - floorf(x); }
 __device__ __forceinline__ float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
 __device__ __forceinline__ vec3 mix(vec3 a, vec3 b, float t) { return v3(mixf(a.x, b.x, t), mixf(a.y, b.y, t), mixf(a.z, b.z, t)); }
-__device__ __forceinline__ float sin_c(float x) { return (float)sin((double)x); }
-__device__ __forceinline__ float cos_c(float x) { return (float)cos((double)x); }
-__device__ __forceinline__ float tan_c(float x) { return (float)tan((double)x); }
+// real calls, not inlined: each float64 sin / cos / tan expands to ~300 SASS instructions and the shading kernels
+// use them at dozens of program points; inlined they overflow the 32 KB instruction cache (profiles/r01c_prof_restir.txt)
+static __device__ __noinline__ float sin_c(float x) { return (float)sin((double)x); }
+static __device__ __noinline__ float cos_c(float x) { return (float)cos((double)x); }
+static __device__ __noinline__ float tan_c(float x) { return (float)tan((double)x); }
 __device__ __forceinline__ float pow5(float x) { const float x2 = x * x; return (x2 * x2) * x; }
 
 // GLSL `M * vec4(p, 1)`.xyz for a column-major mat4
