@@ -15,31 +15,11 @@ namespace {
 
 constexpr int TRACE_THREADS = 128;
 
-template <bool ANY>
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace(TraceScene S, const float4* __restrict__ rays, unsigned long long n,
-                                                         SnkHit* __restrict__ hits_aos, float4* __restrict__ hits_soa,
-                                                         uint32_t* __restrict__ inst_soa, float* __restrict__ vis_out) {
-  SNK_DECLARE_TRAV_STACK(TRACE_THREADS);
-  uint2* stk = snk_trav_stack + threadIdx.x;
-  const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
-  for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float4 a = __ldg(rays + 2 * i), b = __ldg(rays + 2 * i + 1);
-    HitRec h;
-    trace_ray<ANY, TRACE_THREADS>(S, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, stk, h);
-    if (hits_aos) {
-      SnkHit o; o.t = h.t; o.u = h.u; o.v = h.v; o.prim = h.prim; o.inst = h.inst;
-      hits_aos[i] = o;
-    }
-    if (hits_soa) hits_soa[i] = make_float4(h.t, h.u, h.v, __uint_as_float(h.prim));
-    if (inst_soa) inst_soa[i] = h.inst;
-    if (vis_out) vis_out[i] = h.t >= 0.0f ? 0.0f : 1.0f;  // Shadow.rmiss:12 → 1 - float(hit)
-  }
-}
-
 // ---- persistent wavefront kernel with dynamic ray fetch ----------------------------------------------------
 // One warp keeps 32 traversal state machines; lanes whose ray finished pull the next ray index from a global
 // ticket (one atomic per warp and refill) instead of idling until the slowest lane of the warp is done
-// (the static kernel above ran at 7.4 of 32 active lanes on the bounce queues, profiles/r01a_prof_trace.txt).
+// (the first, static one-ray-per-thread kernel ran at 7.4 of 32 active lanes on the bounce queues,
+// profiles/r01a_prof_trace.txt).
 // A refill is triggered once the warp has accumulated PT_LOST_MAX idle lane-iterations beyond PT_IDLE_OK per
 // iteration (Aila & Laine 2009 / Ylitie et al. 2017 dynamic fetch). Results are written per ray index, so the
 // output is independent of the fetch order.
@@ -221,12 +201,7 @@ size_t trace_spill_bytes() { return (size_t)148 * PT_CTAS_PER_SM * (TRACE_THREAD
 int launch_trace(const TraceScene& S, const float4* rays, uint64_t n, bool any, SnkHit* hits_aos, float4* hits_soa,
                  uint32_t* inst_soa, float* vis_out, unsigned long long* ticket, cudaStream_t st) {
   if (n == 0) return 0;
-  static const bool use_static = getenv("SNKPT_TRACE_STATIC") != nullptr;  // A/B switch for profiles/ evidence
-  if (use_static || !ticket || !S.spill) {
-    if (any) k_trace<true><<<trace_grid(n), TRACE_THREADS, 0, st>>>(S, rays, n, hits_aos, hits_soa, inst_soa, vis_out);
-    else k_trace<false><<<trace_grid(n), TRACE_THREADS, 0, st>>>(S, rays, n, hits_aos, hits_soa, inst_soa, vis_out);
-    return 1;
-  }
+  if (!ticket || !S.spill) return 0;
   cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), st);
   const int grid = trace_grid(n);
   if (any) k_trace_pt<true><<<grid, TRACE_THREADS, 0, st>>>(S, rays, n, ticket, hits_aos, hits_soa, inst_soa, vis_out);

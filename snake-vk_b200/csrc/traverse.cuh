@@ -35,14 +35,11 @@ struct HitRec {
   uint32_t prim, inst;
 };
 
-// Traversal stack: TRAV_STACK 8-byte entries per thread, kept in SHARED memory and interleaved by thread
-// (entry e of thread t lives at stk[e * STRIDE], STRIDE = CTA size) so a warp's pushes / pops are
-// conflict-free 64-bit accesses. Deliberately not a local-memory array: ptxas keeps the local-frame base
-// in a uniform register across the divergent traversal loop, and lanes that leave the loop early were
-// observed (compute-sanitizer, k_primary on C2) to overwrite that register while others still traverse.
-constexpr int TRAV_STACK = 32;
-constexpr uint32_t TRAV_SENTINEL = 0xFFFFFFFFu;
-#define SNK_DECLARE_TRAV_STACK(threads) __shared__ uint2 snk_trav_stack[snk::TRAV_STACK * (threads)]
+// Traversal stack entries are 8 bytes; the top SHORT_STACK entries of every thread live in SHARED memory,
+// interleaved by thread (entry e of thread t at stk[e * STRIDE], STRIDE = CTA size) so a warp's pushes / pops
+// are conflict-free 64-bit accesses; deeper entries spill to a per-warp global area. Deliberately not a
+// local-memory array: an earlier version saw lanes that left the divergent loop early clobber the uniform
+// register holding the local-frame base (compute-sanitizer, k_primary on C2).
 constexpr float BOX_PAD = 1.000004f;
 
 struct RaySpace {
@@ -115,8 +112,17 @@ __device__ __forceinline__ uint32_t byte_of(uint32_t lo_word, uint32_t hi_word, 
   return ((s < 4 ? lo_word : hi_word) >> ((s & 3) * 8)) & 0xFFu;
 }
 
+// replicate the sign bit of each byte over the byte (0x80 -> 0xFF)
+__device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) {
+  uint32_t v;
+  asm("prmt.b32 %0, %1, 0x0, 0x0000BA98;" : "=r"(v) : "r"(x));
+  return v;
+}
+
 // intersect the 8 quantised child boxes of one node; returns the hit mask
-// (bits 24..31: inner children in octant order, bits 0..23: leaf records)
+// (bits 24..31: inner children in octant order, bits 0..23: leaf records). Branch-free: the per-child bit
+// position / bit pattern are derived four children at a time from the meta bytes (Ylitie et al. 2017), an
+// empty slot has meta 0 and contributes no bits whatever its box test says.
 __device__ __forceinline__ uint32_t intersect_node(const RaySpace& r, const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3,
                                                    const uint4 n4, float tmin, float tmax) {
   const float px = __uint_as_float(n0.x), py = __uint_as_float(n0.y), pz = __uint_as_float(n0.z);
@@ -126,23 +132,28 @@ __device__ __forceinline__ uint32_t intersect_node(const RaySpace& r, const uint
   const float bx = (px - r.ox) * r.idx, by = (py - r.oy) * r.idy, bz = (pz - r.oz) * r.idz;
   // near / far plane words per axis
   const bool nx = r.idx < 0.f, ny = r.idy < 0.f, nz = r.idz < 0.f;
-  const uint32_t xn0 = nx ? n3.z : n2.x, xn1 = nx ? n3.w : n2.y, xf0 = nx ? n2.x : n3.z, xf1 = nx ? n2.y : n3.w;
-  const uint32_t yn0 = ny ? n4.x : n2.z, yn1 = ny ? n4.y : n2.w, yf0 = ny ? n2.z : n4.x, yf1 = ny ? n2.w : n4.y;
-  const uint32_t zn0 = nz ? n4.z : n3.x, zn1 = nz ? n4.w : n3.y, zf0 = nz ? n3.x : n4.z, zf1 = nz ? n3.y : n4.w;
+  const uint32_t xn[2] = {nx ? n3.z : n2.x, nx ? n3.w : n2.y}, xf[2] = {nx ? n2.x : n3.z, nx ? n2.y : n3.w};
+  const uint32_t yn[2] = {ny ? n4.x : n2.z, ny ? n4.y : n2.w}, yf[2] = {ny ? n2.z : n4.x, ny ? n2.w : n4.y};
+  const uint32_t zn[2] = {nz ? n4.z : n3.x, nz ? n4.w : n3.y}, zf[2] = {nz ? n3.x : n4.z, nz ? n3.y : n4.w};
+  const uint32_t octinv4 = r.octinv * 0x01010101u;
   uint32_t hitmask = 0;
 #pragma unroll
-  for (int s = 0; s < 8; ++s) {
-    const uint32_t meta = byte_of(n1.z, n1.w, s);
-    if (meta == 0) continue;
-    const float tx0 = fmaf((float)byte_of(xn0, xn1, s), ax, bx), tx1 = fmaf((float)byte_of(xf0, xf1, s), ax, bx);
-    const float ty0 = fmaf((float)byte_of(yn0, yn1, s), ay, by), ty1 = fmaf((float)byte_of(yf0, yf1, s), ay, by);
-    const float tz0 = fmaf((float)byte_of(zn0, zn1, s), az, bz), tz1 = fmaf((float)byte_of(zf0, zf1, s), az, bz);
-    const float tn = fmaxf(fmaxf(tx0, ty0), fmaxf(tz0, tmin));
-    const float tf = fminf(fminf(tx1, ty1), fminf(tz1, tmax));
-    if (tn <= tf * BOX_PAD) {
-      const uint32_t idx = meta & 0x1Fu;
-      if ((meta & 0x18u) == 0x18u) hitmask |= 1u << (idx ^ r.octinv);  // inner: 24 + (slot ^ octinv)
-      else hitmask |= (meta >> 5) << idx;                               // leaf: unary count at its record offset
+  for (int h = 0; h < 2; ++h) {
+    const uint32_t meta4 = h ? n1.w : n1.z;
+    const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+    const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+    const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
+    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int sh = 8 * j;
+      const float tx0 = fmaf((float)((xn[h] >> sh) & 0xFFu), ax, bx), tx1 = fmaf((float)((xf[h] >> sh) & 0xFFu), ax, bx);
+      const float ty0 = fmaf((float)((yn[h] >> sh) & 0xFFu), ay, by), ty1 = fmaf((float)((yf[h] >> sh) & 0xFFu), ay, by);
+      const float tz0 = fmaf((float)((zn[h] >> sh) & 0xFFu), az, bz), tz1 = fmaf((float)((zf[h] >> sh) & 0xFFu), az, bz);
+      const float tn = fmaxf(fmaxf(tx0, ty0), fmaxf(tz0, tmin));
+      const float tf = fminf(fminf(tx1, ty1), fminf(tz1, tmax));
+      const uint32_t bits = ((child_bits4 >> sh) & 0xFFu) << ((bit_index4 >> sh) & 0xFFu);
+      hitmask |= (tn <= tf * BOX_PAD) ? bits : 0u;
     }
   }
   return hitmask;
@@ -152,105 +163,6 @@ __device__ __forceinline__ void load_node(const uint4* __restrict__ nodes, uint3
                                           uint4& n4) {
   const uint4* p = nodes + 5ull * idx;
   n0 = __ldg(p); n1 = __ldg(p + 1); n2 = __ldg(p + 2); n3 = __ldg(p + 3); n4 = __ldg(p + 4);
-}
-
-// ANY: return on the first valid hit (gl_RayFlagsTerminateOnFirstHitEXT)
-#define SNK_PUSH(val)                                              \
-  do {                                                             \
-    if (sp < TRAV_STACK) stk[(sp++) * STRIDE] = (val);             \
-    else atomicAdd(S.overflow, 1u);                                \
-  } while (0)
-
-template <bool ANY, int STRIDE>
-__device__ __forceinline__ void trace_ray(const TraceScene& S, float ox, float oy, float oz, float tmin, float dx, float dy, float dz,
-                                          float tmax, uint2* __restrict__ stk, HitRec& best) {
-  best.t = -1.0f; best.u = 0.f; best.v = 0.f; best.prim = 0xFFFFFFFFu; best.inst = 0xFFFFFFFFu;
-  if (S.tlas_node_count == 0) return;
-  float tcur = tmax;  // shrinks to the closest hit found so far
-  RaySpace r;
-  setup_ray_space(r, ox, oy, oz, dx, dy, dz);
-  int sp = 0;
-  bool in_blas = false;
-  uint32_t cur_inst = 0;
-  const uint4* nodes = S.tlas_nodes;
-  uint2 G = make_uint2(0u, 0x80000000u);
-  while (true) {
-    uint2 T = make_uint2(0u, 0u);
-    if (G.y & 0xFF000000u) {
-      const uint32_t hits_imask = G.y;
-      const uint32_t bit = 31u - __clz(hits_imask);
-      G.y &= ~(1u << bit);
-      if (G.y & 0xFF000000u) SNK_PUSH(G);
-      const uint32_t slot = (bit - 24u) ^ r.octinv;
-      const uint32_t rel = __popc(hits_imask & ~(0xFFFFFFFFu << slot) & 0xFFu);
-      uint4 n0, n1, n2, n3, n4;
-      load_node(nodes, G.x + rel, n0, n1, n2, n3, n4);
-      const uint32_t hm = intersect_node(r, n0, n1, n2, n3, n4, tmin, tcur);
-      G = make_uint2(n1.x, (hm & 0xFF000000u) | (n0.w >> 24));
-      T = make_uint2(n1.y, hm & 0x00FFFFFFu);
-    } else {
-      T = G;
-      G = make_uint2(0u, 0u);
-    }
-    while (T.y) {
-      const uint32_t bit = __ffs(T.y) - 1;
-      T.y &= ~(1u << bit);
-      if (!in_blas) {
-        // TLAS leaf record → enter the instance
-        const uint32_t slot = __ldg(S.tlas_leaf_ids + T.x + bit);
-        if (T.y) SNK_PUSH(T);
-        if (G.y & 0xFF000000u) SNK_PUSH(G);
-        SNK_PUSH(make_uint2(TRAV_SENTINEL, 0u));
-        const float4* M = reinterpret_cast<const float4*>(S.inst + slot);
-        const float4 r0 = __ldg(M), r1 = __ldg(M + 1), r2 = __ldg(M + 2);
-        const uint4 meta = __ldg(reinterpret_cast<const uint4*>(M + 3));
-        // o' = ((m0*x + m1*y) + m2*z) + m3 ; d' = (m0*x + m1*y) + m2*z   (unfused, as the oracle)
-        const float oox = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0.x, ox), __fmul_rn(r0.y, oy)), __fmul_rn(r0.z, oz)), r0.w);
-        const float ooy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r1.x, ox), __fmul_rn(r1.y, oy)), __fmul_rn(r1.z, oz)), r1.w);
-        const float ooz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2.x, ox), __fmul_rn(r2.y, oy)), __fmul_rn(r2.z, oz)), r2.w);
-        const float odx = __fadd_rn(__fadd_rn(__fmul_rn(r0.x, dx), __fmul_rn(r0.y, dy)), __fmul_rn(r0.z, dz));
-        const float ody = __fadd_rn(__fadd_rn(__fmul_rn(r1.x, dx), __fmul_rn(r1.y, dy)), __fmul_rn(r1.z, dz));
-        const float odz = __fadd_rn(__fadd_rn(__fmul_rn(r2.x, dx), __fmul_rn(r2.y, dy)), __fmul_rn(r2.z, dz));
-        setup_ray_space(r, oox, ooy, ooz, odx, ody, odz);
-        in_blas = true;
-        cur_inst = meta.y;
-        nodes = S.blas_nodes;
-        G = make_uint2(meta.x, 0x80000000u);
-        T = make_uint2(0u, 0u);
-        break;
-      }
-      const float4* tp = S.tris + 3ull * (T.x + bit);
-      const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
-      float t, u, v;
-      if (tri_test(r, p0, p1, p2, t, u, v) && t > tmin && t < tmax) {
-        const uint32_t prim = __float_as_uint(p0.w);
-        bool take;
-        if (ANY) take = true;
-        else take = best.t < 0.0f || t < best.t || (t == best.t && (cur_inst < best.inst || (cur_inst == best.inst && prim < best.prim)));
-        if (take) {
-          best.t = t; best.u = u; best.v = v; best.prim = prim; best.inst = cur_inst;
-          if (ANY) return;
-          tcur = t;
-        }
-      }
-    }
-    if ((G.y & 0xFF000000u) == 0u) {
-      bool finished = false;
-      while (true) {
-        if (sp == 0) { finished = true; break; }
-        G = stk[(--sp) * STRIDE];
-        if (G.x == TRAV_SENTINEL) {
-          setup_ray_space(r, ox, oy, oz, dx, dy, dz);
-          in_blas = false;
-          nodes = S.tlas_nodes;
-          G = make_uint2(0u, 0u);
-          continue;
-        }
-        break;
-      }
-      if (finished) break;
-    }
-  }
 }
 
 // ---- state-machine form (persistent wavefront kernels) ---------------------------------------------------
@@ -276,7 +188,7 @@ struct Trav {
   float tmax;
   RaySpace r;                          // current space (world in the TLAS, object in a BLAS)
   uint2 G, T;                          // pending node group / leaf-record group
-  int sp;
+  int sp, blas_sp;                     // blas_sp: stack height at instance entry (leaving = popping down to it)
   uint32_t cur_inst;
   bool in_blas, tri_ready;             // tri_ready: the Woop constants of r are valid for the current space
   HitRec best;
@@ -333,7 +245,7 @@ __device__ __forceinline__ void trav_begin(Trav& t, float4 a, float4 b) {
   setup_box_space(t.r, a.x, a.y, a.z, b.x, b.y, b.z);
   t.G = make_uint2(0u, 0x80000000u);
   t.T = make_uint2(0u, 0u);
-  t.sp = 0; t.cur_inst = 0; t.in_blas = false; t.tri_ready = false;
+  t.sp = 0; t.blas_sp = 0; t.cur_inst = 0; t.in_blas = false; t.tri_ready = false;
   t.best.t = -1.0f; t.best.u = 0.f; t.best.v = 0.f; t.best.prim = 0xFFFFFFFFu; t.best.inst = 0xFFFFFFFFu;
 }
 
@@ -367,7 +279,7 @@ __device__ __forceinline__ bool trav_leaf(const TraceScene& S, Trav& t, const St
     const uint32_t slot = __ldg(S.tlas_leaf_ids + t.T.x + bit);
     if (t.T.y) stk_push<STRIDE>(stk, t.sp, t.T, S.overflow);
     if (t.G.y & 0xFF000000u) stk_push<STRIDE>(stk, t.sp, t.G, S.overflow);
-    stk_push<STRIDE>(stk, t.sp, make_uint2(TRAV_SENTINEL, 0u), S.overflow);
+    t.blas_sp = t.sp;
     const float4* M = reinterpret_cast<const float4*>(S.inst + slot);
     const float4 r0 = __ldg(M), r1 = __ldg(M + 1), r2 = __ldg(M + 2);
     const uint4 meta = __ldg(reinterpret_cast<const uint4*>(M + 3));
@@ -408,14 +320,13 @@ __device__ __forceinline__ bool trav_leaf(const TraceScene& S, Trav& t, const St
 // stack is empty, i.e. the ray is finished.
 template <int STRIDE>
 __device__ __forceinline__ bool trav_pop(Trav& t, const StackRef& stk) {
-  if (t.sp == 0) return true;
-  uint2 e = stk_pop<STRIDE>(stk, t.sp);
-  if (e.x == TRAV_SENTINEL) {
+  if (t.in_blas && t.sp == t.blas_sp) {
     // leave the instance: back to world space (no triangles are tested in the TLAS, so only the box part)
     setup_box_space(t.r, t.ox, t.oy, t.oz, t.dx, t.dy, t.dz);
     t.in_blas = false; t.tri_ready = false;
-    e = make_uint2(0u, 0u);
   }
+  if (t.sp == 0) return true;
+  const uint2 e = stk_pop<STRIDE>(stk, t.sp);
   if (e.y & 0xFF000000u) t.G = e;
   else { t.T = e; t.G = make_uint2(0u, 0u); }
   return false;
