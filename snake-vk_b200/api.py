@@ -22,7 +22,8 @@ class SnkError(RuntimeError):
 
 
 def lib_path() -> str:
-    return os.path.join(_HERE, "libsnkpt.so")
+    # SNKPT_LIB_VARIANT selects a tuning build (snake-vk_b200/Makefile VARIANT=...); default = the product library
+    return os.path.join(_HERE, f"libsnkpt{os.environ.get('SNKPT_LIB_VARIANT', '')}.so")
 
 
 def load_library() -> C.CDLL:

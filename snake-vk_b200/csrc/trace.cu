@@ -23,9 +23,18 @@ constexpr int TRACE_THREADS = 128;
 // A refill is triggered once the warp has accumulated PT_LOST_MAX idle lane-iterations beyond PT_IDLE_OK per
 // iteration (Aila & Laine 2009 / Ylitie et al. 2017 dynamic fetch). Results are written per ray index, so the
 // output is independent of the fetch order.
-constexpr int PT_IDLE_OK = 4;
-constexpr int PT_LOST_MAX = 16;
-constexpr int PT_CTAS_PER_SM = 8;
+#ifndef SNK_PT_IDLE_OK
+#define SNK_PT_IDLE_OK 4
+#endif
+#ifndef SNK_PT_LOST_MAX
+#define SNK_PT_LOST_MAX 16
+#endif
+#ifndef SNK_PT_CTAS
+#define SNK_PT_CTAS 8
+#endif
+constexpr int PT_IDLE_OK = SNK_PT_IDLE_OK;
+constexpr int PT_LOST_MAX = SNK_PT_LOST_MAX;
+constexpr int PT_CTAS_PER_SM = SNK_PT_CTAS;
 
 template <bool ANY>
 __global__ void __launch_bounds__(TRACE_THREADS, PT_CTAS_PER_SM)
@@ -71,13 +80,7 @@ k_trace_pt(TraceScene S, const float4* __restrict__ rays, unsigned long long n, 
     // ---- traverse; the three phases are warp-synchronous (the ballots reconverge all 32 lanes per iteration)
     int lost = 0;
     while (true) {
-      if (active && trav_wants_node(t)) trav_node<TRACE_THREADS>(S, t, stk);
-      __syncwarp();
-      bool done = false;
-      if (active && t.T.y) done = trav_leaf<ANY, TRACE_THREADS>(S, t, stk);
-      __syncwarp();
-      if (active && !done && t.T.y == 0u && (t.G.y & 0xFF000000u) == 0u) done = trav_pop<TRACE_THREADS>(t, stk);
-      if (done) { write_result(idx, t.best); active = false; }
+      if (trav_step<ANY, TRACE_THREADS>(S, t, stk, active, 0xFFFFFFFFu)) { write_result(idx, t.best); active = false; }
       const uint32_t live = __ballot_sync(0xFFFFFFFFu, active);
       if (live == 0u) break;
       if (!exhausted) {
@@ -192,11 +195,11 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_count_work_sum(TraceScene S, 
 
 static int trace_grid(uint64_t n) {
   const uint64_t blocks = (n + TRACE_THREADS - 1) / TRACE_THREADS;
-  const uint64_t persistent = 148ull * 8ull;
+  const uint64_t persistent = 148ull * PT_CTAS_PER_SM;
   return (int)(blocks < persistent ? (blocks ? blocks : 1) : persistent);
 }
 
-size_t trace_spill_bytes() { return (size_t)148 * PT_CTAS_PER_SM * (TRACE_THREADS / 32) * SPILL_STACK * 32 * sizeof(uint2); }
+size_t trace_spill_bytes() { return (size_t)148 * 8 * /* the largest persistent grid: 8 CTAs per SM */ (TRACE_THREADS / 32) * SPILL_STACK * 32 * sizeof(uint2); }
 
 int launch_trace(const TraceScene& S, const float4* rays, uint64_t n, bool any, SnkHit* hits_aos, float4* hits_soa,
                  uint32_t* inst_soa, float* vis_out, unsigned long long* ticket, cudaStream_t st) {

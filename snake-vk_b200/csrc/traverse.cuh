@@ -185,7 +185,6 @@ struct StackRef {
 struct Trav {
   float ox, oy, oz, tmin, dx, dy, dz;  // world-space ray
   float tcur;                          // tmax, shrinking to the closest hit
-  float tmax;
   RaySpace r;                          // current space (world in the TLAS, object in a BLAS)
   uint2 G, T;                          // pending node group / leaf-record group
   int sp, blas_sp;                     // blas_sp: stack height at instance entry (leaving = popping down to it)
@@ -241,7 +240,7 @@ __device__ __forceinline__ void setup_tri_space(RaySpace& r) {
 }
 
 __device__ __forceinline__ void trav_begin(Trav& t, float4 a, float4 b) {
-  t.ox = a.x; t.oy = a.y; t.oz = a.z; t.tmin = a.w; t.dx = b.x; t.dy = b.y; t.dz = b.z; t.tcur = b.w; t.tmax = b.w;
+  t.ox = a.x; t.oy = a.y; t.oz = a.z; t.tmin = a.w; t.dx = b.x; t.dy = b.y; t.dz = b.z; t.tcur = b.w;
   setup_box_space(t.r, a.x, a.y, a.z, b.x, b.y, b.z);
   t.G = make_uint2(0u, 0x80000000u);
   t.T = make_uint2(0u, 0u);
@@ -249,63 +248,92 @@ __device__ __forceinline__ void trav_begin(Trav& t, float4 a, float4 b) {
   t.best.t = -1.0f; t.best.u = 0.f; t.best.v = 0.f; t.best.prim = 0xFFFFFFFFu; t.best.inst = 0xFFFFFFFFu;
 }
 
-__device__ __forceinline__ bool trav_wants_node(const Trav& t) { return t.T.y == 0u && (t.G.y & 0xFF000000u) != 0u; }
+#ifndef SNK_TRI_MIN
+#define SNK_TRI_MIN 0  // triangle phase runs when at least this many lanes have a record pending (or nobody opened a node)
+#endif
 
-// node phase (call with the lanes for which trav_wants_node holds)
-template <int STRIDE>
-__device__ __forceinline__ void trav_node(const TraceScene& S, Trav& t, const StackRef& stk) {
-  const uint4* nodes = t.in_blas ? S.blas_nodes : S.tlas_nodes;
-  const uint32_t hits_imask = t.G.y;
-  const uint32_t bit = 31u - __clz(hits_imask);
-  t.G.y &= ~(1u << bit);
-  if (t.G.y & 0xFF000000u) stk_push<STRIDE>(stk, t.sp, t.G, S.overflow);
-  const uint32_t slot = (bit - 24u) ^ t.r.octinv;
-  const uint32_t rel = __popc(hits_imask & ~(0xFFFFFFFFu << slot) & 0xFFu);
-  uint4 n0, n1, n2, n3, n4;
-  load_node(nodes, t.G.x + rel, n0, n1, n2, n3, n4);
-  const uint32_t hm = intersect_node(t.r, n0, n1, n2, n3, n4, t.tmin, t.tcur);
-  t.G = make_uint2(n1.x, (hm & 0xFF000000u) | (n0.w >> 24));
-  t.T = make_uint2(n1.y, hm & 0x00FFFFFFu);
-}
-
-// leaf phase (call with the lanes that have t.T.y != 0): one record. Returns true when an ANY ray is done.
+// One warp-synchronous iteration for the lanes in `warp` (all of them must call it together):
+//   1. pick the node to open: TLAS lanes with an instance record pending enter the instance (transform the
+//      ray, node = BLAS root); lanes with an inner hit pending take the nearest child of their group
+//   2. common node phase: 5 x 128-bit load + 8 quantised box tests -> new inner-hit group G and leaf group T
+//   3. triangle phase: BLAS lanes with leaf records pending test ONE triangle (watertight, bit-exact with the oracle)
+//   4. pop phase: lanes with nothing pending pop the stack; popping below the instance-entry height returns
+//      to world space; an empty stack finishes the ray
+// Returns true when this lane's ray is finished (stack empty, or first hit for ANY).
 template <bool ANY, int STRIDE>
-__device__ __forceinline__ bool trav_leaf(const TraceScene& S, Trav& t, const StackRef& stk) {
-  const uint32_t bit = __ffs(t.T.y) - 1;
-  t.T.y &= ~(1u << bit);
+__device__ __forceinline__ bool trav_step(const TraceScene& S, Trav& t, const StackRef& stk, bool active, uint32_t warp) {
+  // ---- 1
+  uint32_t node_idx = 0;
+  const uint4* nodes = S.blas_nodes;
+  bool open = false;
+  if (active) {
+    if (t.T.y != 0u && !t.in_blas) {
+      const uint32_t bit = __ffs(t.T.y) - 1;
+      t.T.y &= ~(1u << bit);
+      const uint32_t slot = __ldg(S.tlas_leaf_ids + t.T.x + bit);
+      if (t.T.y) stk_push<STRIDE>(stk, t.sp, t.T, S.overflow);
+      if (t.G.y & 0xFF000000u) stk_push<STRIDE>(stk, t.sp, t.G, S.overflow);
+      t.blas_sp = t.sp;
+      const float4* M = reinterpret_cast<const float4*>(S.inst + slot);
+      const float4 r0 = __ldg(M), r1 = __ldg(M + 1), r2 = __ldg(M + 2);
+      const uint4 meta = __ldg(reinterpret_cast<const uint4*>(M + 3));
+      // o' = ((m0*x + m1*y) + m2*z) + m3 ; d' = (m0*x + m1*y) + m2*z   (unfused, as the oracle)
+      const float oox = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0.x, t.ox), __fmul_rn(r0.y, t.oy)), __fmul_rn(r0.z, t.oz)), r0.w);
+      const float ooy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r1.x, t.ox), __fmul_rn(r1.y, t.oy)), __fmul_rn(r1.z, t.oz)), r1.w);
+      const float ooz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2.x, t.ox), __fmul_rn(r2.y, t.oy)), __fmul_rn(r2.z, t.oz)), r2.w);
+      const float odx = __fadd_rn(__fadd_rn(__fmul_rn(r0.x, t.dx), __fmul_rn(r0.y, t.dy)), __fmul_rn(r0.z, t.dz));
+      const float ody = __fadd_rn(__fadd_rn(__fmul_rn(r1.x, t.dx), __fmul_rn(r1.y, t.dy)), __fmul_rn(r1.z, t.dz));
+      const float odz = __fadd_rn(__fadd_rn(__fmul_rn(r2.x, t.dx), __fmul_rn(r2.y, t.dy)), __fmul_rn(r2.z, t.dz));
+      setup_box_space(t.r, oox, ooy, ooz, odx, ody, odz);
+      t.in_blas = true; t.tri_ready = false;
+      t.cur_inst = meta.y;
+      node_idx = meta.x;
+      open = true;
+    } else if (t.T.y == 0u && (t.G.y & 0xFF000000u) != 0u) {
+      const uint32_t hits_imask = t.G.y;
+      const uint32_t bit = 31u - __clz(hits_imask);
+      t.G.y &= ~(1u << bit);
+      if (t.G.y & 0xFF000000u) stk_push<STRIDE>(stk, t.sp, t.G, S.overflow);
+      const uint32_t slot = (bit - 24u) ^ t.r.octinv;
+      node_idx = t.G.x + __popc(hits_imask & ~(0xFFFFFFFFu << slot) & 0xFFu);
+      nodes = t.in_blas ? S.blas_nodes : S.tlas_nodes;
+      open = true;
+    }
+  }
+  __syncwarp(warp);
+  // ---- 2
+  if (open) {
+    uint4 n0, n1, n2, n3, n4;
+    load_node(nodes, node_idx, n0, n1, n2, n3, n4);
+    const uint32_t hm = intersect_node(t.r, n0, n1, n2, n3, n4, t.tmin, t.tcur);
+    t.G = make_uint2(n1.x, (hm & 0xFF000000u) | (n0.w >> 24));
+    t.T = make_uint2(n1.y, hm & 0x00FFFFFFu);
+  }
+  // ---- 3
   bool done = false;
-  if (!t.in_blas) {
-    // TLAS leaf record → enter the instance
-    const uint32_t slot = __ldg(S.tlas_leaf_ids + t.T.x + bit);
-    if (t.T.y) stk_push<STRIDE>(stk, t.sp, t.T, S.overflow);
-    if (t.G.y & 0xFF000000u) stk_push<STRIDE>(stk, t.sp, t.G, S.overflow);
-    t.blas_sp = t.sp;
-    const float4* M = reinterpret_cast<const float4*>(S.inst + slot);
-    const float4 r0 = __ldg(M), r1 = __ldg(M + 1), r2 = __ldg(M + 2);
-    const uint4 meta = __ldg(reinterpret_cast<const uint4*>(M + 3));
-    // o' = ((m0*x + m1*y) + m2*z) + m3 ; d' = (m0*x + m1*y) + m2*z   (unfused, as the oracle)
-    const float oox = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0.x, t.ox), __fmul_rn(r0.y, t.oy)), __fmul_rn(r0.z, t.oz)), r0.w);
-    const float ooy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r1.x, t.ox), __fmul_rn(r1.y, t.oy)), __fmul_rn(r1.z, t.oz)), r1.w);
-    const float ooz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2.x, t.ox), __fmul_rn(r2.y, t.oy)), __fmul_rn(r2.z, t.oz)), r2.w);
-    const float odx = __fadd_rn(__fadd_rn(__fmul_rn(r0.x, t.dx), __fmul_rn(r0.y, t.dy)), __fmul_rn(r0.z, t.dz));
-    const float ody = __fadd_rn(__fadd_rn(__fmul_rn(r1.x, t.dx), __fmul_rn(r1.y, t.dy)), __fmul_rn(r1.z, t.dz));
-    const float odz = __fadd_rn(__fadd_rn(__fmul_rn(r2.x, t.dx), __fmul_rn(r2.y, t.dy)), __fmul_rn(r2.z, t.dz));
-    setup_box_space(t.r, oox, ooy, ooz, odx, ody, odz);
-    t.in_blas = true; t.tri_ready = false;
-    t.cur_inst = meta.y;
-    t.G = make_uint2(meta.x, 0x80000000u);
-    t.T = make_uint2(0u, 0u);
+  const bool has_tri = active && t.in_blas && t.T.y != 0u;
+  bool tri_go = has_tri;
+  if (SNK_TRI_MIN > 1) {
+    const uint32_t n_tri = __popc(__ballot_sync(warp, has_tri)), n_open = __popc(__ballot_sync(warp, open));
+    tri_go = has_tri && (n_tri >= SNK_TRI_MIN || n_open == 0u);
   } else {
+    __syncwarp(warp);
+  }
+  if (tri_go) {
+    const uint32_t bit = __ffs(t.T.y) - 1;
+    t.T.y &= ~(1u << bit);
     if (!t.tri_ready) { setup_tri_space(t.r); t.tri_ready = true; }
     const float4* tp = S.tris + 3ull * (t.T.x + bit);
     const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
     float th, u, v;
-    if (tri_test(t.r, p0, p1, p2, th, u, v) && th > t.tmin && th < t.tmax) {
+    if (tri_test(t.r, p0, p1, p2, th, u, v) && th > t.tmin) {
+      // tcur == tmax until the first hit, afterwards the closest distance so far: a hit must be strictly inside
+      // (tmin, tmax); at the current closest distance the lower (instance, primitive) wins
       const uint32_t prim = __float_as_uint(p0.w);
       bool take;
-      if (ANY) take = true;
-      else take = t.best.t < 0.0f || th < t.best.t ||
-                  (th == t.best.t && (t.cur_inst < t.best.inst || (t.cur_inst == t.best.inst && prim < t.best.prim)));
+      if (ANY) take = th < t.tcur;
+      else take = th < t.tcur || (th == t.tcur && t.best.t >= 0.0f &&
+                                  (t.cur_inst < t.best.inst || (t.cur_inst == t.best.inst && prim < t.best.prim)));
       if (take) {
         t.best.t = th; t.best.u = u; t.best.v = v; t.best.prim = prim; t.best.inst = t.cur_inst;
         t.tcur = th;
@@ -313,23 +341,22 @@ __device__ __forceinline__ bool trav_leaf(const TraceScene& S, Trav& t, const St
       }
     }
   }
-  return done;
-}
-
-// pop phase (call with lanes that have neither leaf records nor inner hits pending). Returns true when the
-// stack is empty, i.e. the ray is finished.
-template <int STRIDE>
-__device__ __forceinline__ bool trav_pop(Trav& t, const StackRef& stk) {
-  if (t.in_blas && t.sp == t.blas_sp) {
-    // leave the instance: back to world space (no triangles are tested in the TLAS, so only the box part)
-    setup_box_space(t.r, t.ox, t.oy, t.oz, t.dx, t.dy, t.dz);
-    t.in_blas = false; t.tri_ready = false;
+  __syncwarp(warp);
+  // ---- 4
+  if (active && !done && t.T.y == 0u && (t.G.y & 0xFF000000u) == 0u) {
+    if (t.in_blas && t.sp == t.blas_sp) {
+      // leave the instance: back to world space (no triangles are tested in the TLAS, so only the box part)
+      setup_box_space(t.r, t.ox, t.oy, t.oz, t.dx, t.dy, t.dz);
+      t.in_blas = false; t.tri_ready = false;
+    }
+    if (t.sp == 0) done = true;
+    else {
+      const uint2 e = stk_pop<STRIDE>(stk, t.sp);
+      if (e.y & 0xFF000000u) t.G = e;
+      else { t.T = e; t.G = make_uint2(0u, 0u); }
+    }
   }
-  if (t.sp == 0) return true;
-  const uint2 e = stk_pop<STRIDE>(stk, t.sp);
-  if (e.y & 0xFF000000u) t.G = e;
-  else { t.T = e; t.G = make_uint2(0u, 0u); }
-  return false;
+  return done;
 }
 
 // ---- warp-synchronous inline tracer (shading kernels) --------------------------------------------------------
@@ -344,13 +371,7 @@ __device__ __forceinline__ void trace_warp_body(const TraceScene& S, float4 a, f
   trav_begin(t, a, b);
   bool active = b.w > a.w && S.tlas_node_count != 0u;
   while (__ballot_sync(warp, active)) {
-    if (active && trav_wants_node(t)) trav_node<STRIDE>(S, t, stk);
-    __syncwarp(warp);
-    bool done = false;
-    if (active && t.T.y) done = trav_leaf<ANY, STRIDE>(S, t, stk);
-    __syncwarp(warp);
-    if (active && !done && t.T.y == 0u && (t.G.y & 0xFF000000u) == 0u) done = trav_pop<STRIDE>(t, stk);
-    if (done) active = false;
+    if (trav_step<ANY, STRIDE>(S, t, stk, active, warp)) active = false;
   }
   best = t.best;
 }
