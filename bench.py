@@ -192,11 +192,17 @@ def run_gpu_arm(args, snk):
     sc, desc = make_scene(snk, args.scene, args.width, args.height)
     W, H = sc.width, sc.height
     rows = (0, H)
+    bands = None
     if world > 1 and args.shard == "rows":
-        band = (H + world - 1) // world
-        rows = (rank * band, min(H, (rank + 1) * band))
+        bands = snk.sharding.RowBands(H, world)
+        rows = bands.band(rank)
     pt = snk.PathTracer(W, H, device=local, rows=rows)
     flat = pt.upload_scene(sc)
+    res_planes = None
+    if bands is not None:
+        pt.set_halo(bands.pass1_halo, bands.gbuffer_halo)
+        # the three SoA planes of the FINAL reservoirs (buffer half 0), aliased for the NCCL halo exchange
+        res_planes = [torch.as_tensor(CudaArray(pt.device_ptr(0x110 + k)[0], (H, W, 4)), device=f"cuda:{local}") for k in range(3)]
     mode = snk.api.MODE_REFERENCE if args.mode == "reference" else snk.api.MODE_NORTHSTAR
     settings = snk.api.default_settings(mode=mode)
     stream = torch.cuda.current_stream().cuda_stream
@@ -215,6 +221,8 @@ def run_gpu_arm(args, snk):
         pt.render(settings, stream)
         if rad is not None:
             dist.all_reduce(rad)        # accumulation step: sum of the per-GPU samples over NVLink
+        if res_planes is not None:
+            snk.sharding.exchange_final(bands, rank, res_planes, dist)  # final-reservoir halos to the band neighbours
 
     def barrier():
         if world > 1:
@@ -343,10 +351,11 @@ def run_gpu_arm(args, snk):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        y0 = H // 2 - args.ref_rows // 2
-        r, s = oracle_sample(sc, args.mode, (y0, y0 + args.ref_rows), 2, threads)
+        nrows = min(H, 16 * args.ref_rows)
+        y0 = H // 2 - nrows // 2
+        r, s = oracle_sample(sc, args.mode, (y0, y0 + nrows), 2, threads)
         cpu = {"value": r / s / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"rows [{y0},{y0 + args.ref_rows}) of the {W}x{H} frame, frames 0-1, {r} rays in {s:.1f} s (CPU restatement, oracle = cpu_restatement)"}
+               "sample": f"rows [{y0},{y0 + nrows}) of the {W}x{H} frame, frames 0-1, {r} rays in {s:.1f} s (CPU restatement, oracle = cpu_restatement)"}
 
     if rank == 0:
         line = {
@@ -376,7 +385,7 @@ def main():
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
     ap.add_argument("--shard", default="samples", choices=["samples", "rows"])
-    ap.add_argument("--ref-rows", type=int, default=8, help="rows of the frame the CPU oracle renders per sample")
+    ap.add_argument("--ref-rows", type=int, default=16, help="rows of the frame the CPU oracle renders per reference-arm step (cpu_baseline: 16x)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     snk = importlib.import_module("snake-vk_b200")

@@ -273,6 +273,14 @@ SNKPT_API void snkpt_default_settings(SnkRtSettings* s);
  * per-pixel state and raises prev_frame_invalid for the next frame */
 SNKPT_API int snkpt_resize(SnkPt* ctx, uint32_t width, uint32_t height);
 SNKPT_API int snkpt_set_rows(SnkPt* ctx, uint32_t row_begin, uint32_t row_end);
+/* Row-band sharding (one band per GPU). The band [row_begin,row_end) is what pass 2, the bounce
+ * stages and the output cover. Reservoir pass 1 additionally covers `pass1_halo` rows above and below the band
+ * (spatial reuse reads temporal reservoirs up to neighbour_radius rows away) and the G-buffer `gbuffer_halo`
+ * rows (pass 1 on the halo reads prev-frame normals / history one motion vector further). With
+ * pass1_halo >= radius, gbuffer_halo >= pass1_halo + max motion + 1 and the FINAL reservoirs (buffer half 0)
+ * of rows [band ± (pass1_halo + max motion)] exchanged between band neighbours after every frame, a band
+ * renders bit-identically to the same rows of a whole-frame context. Defaults 0, 0 (whole frame). */
+SNKPT_API int snkpt_set_halo(SnkPt* ctx, uint32_t pass1_halo, uint32_t gbuffer_halo);
 /* invalidates temporal history (SceneInfoBufferSystem m_prev_frame_invalid) */
 SNKPT_API int snkpt_reset_history(SnkPt* ctx);
 

@@ -82,6 +82,11 @@ ORACLE_API void snkor_frame_render(void* fp, uint32_t y0, uint32_t y1, int threa
   if (y1 == 0) y1 = f.g.h;
   render_reference(f, y0, y1, threads);
 }
+ORACLE_API void snkor_frame_render_pass(void* fp, uint32_t pass, uint32_t y0, uint32_t y1, int threads) {
+  Frame& f = *(Frame*)fp;
+  if (y1 == 0) y1 = f.g.h;
+  render_reference_pass(f, pass, y0, y1, threads);
+}
 // what: same numbering as SNKPT_AUX_* (include/snkpt.h)
 ORACLE_API int snkor_frame_read(void* fp, uint32_t what, void* dst, size_t bytes) {
   Frame& f = *(Frame*)fp;

@@ -562,6 +562,17 @@ struct Invocation {
 };
 
 // RT::RecordRenderCmdBuf (Raytracing.cpp:227-267): pass 1 over all pixels, barrier, pass 2
+// one pass of RT::RecordRenderCmdBuf over rows [y0,y1): pass 1 = initial + temporal reservoirs,
+// pass 0 = spatial reuse, shading and bounce rays (Raytracing.cpp:250-260)
+inline void render_reference_pass(Frame& F, uint32_t pass, uint32_t y0, uint32_t y1, int threads) {
+  F.ivp = inv_view_proj(F.ubo);
+  parallel_rows(y0, y1, threads, [&](uint32_t y) {
+    uint64_t nc = 0, na = 0;
+    for (uint32_t x = 0; x < F.g.w; ++x) { Invocation inv(F, x, y); inv.main(pass); nc += inv.n_closest; na += inv.n_any; }
+    F.rays_closest += nc; F.rays_any += na;
+  });
+}
+
 inline void render_reference(Frame& F, uint32_t y0, uint32_t y1, int threads) {
   F.ivp = inv_view_proj(F.ubo);
   for (uint32_t pass = 1;; pass = 0) {

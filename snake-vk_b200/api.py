@@ -39,7 +39,7 @@ def load_library() -> C.CDLL:
     vp, u32, u64, sz, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_size_t, C.c_int
     sig = {
         "snkpt_create": [vp, vp], "snkpt_default_settings": [vp], "snkpt_resize": [vp, u32, u32],
-        "snkpt_set_rows": [vp, u32, u32], "snkpt_reset_history": [vp],
+        "snkpt_set_rows": [vp, u32, u32], "snkpt_set_halo": [vp, u32, u32], "snkpt_reset_history": [vp],
         "snkpt_upload_mesh": [vp, vp, vp, vp, vp, u32, vp, u32, vp, u32, vp, vp],
         "snkpt_update_positions": [vp, vp, vp, u32], "snkpt_refit_blas": [vp, u32, vp], "snkpt_rebuild_blas": [vp, u32, vp],
         "snkpt_set_materials": [vp, vp, u32, u32], "snkpt_set_lights": [vp, vp, sz],
@@ -65,7 +65,7 @@ def load_library() -> C.CDLL:
     return L
 
 
-EXPORTS = ["snkpt_create", "snkpt_destroy", "snkpt_last_error", "snkpt_default_settings", "snkpt_resize", "snkpt_set_rows",
+EXPORTS = ["snkpt_create", "snkpt_destroy", "snkpt_last_error", "snkpt_default_settings", "snkpt_resize", "snkpt_set_rows", "snkpt_set_halo",
            "snkpt_reset_history", "snkpt_upload_mesh", "snkpt_update_positions", "snkpt_refit_blas", "snkpt_rebuild_blas",
            "snkpt_set_materials", "snkpt_set_lights", "snkpt_set_transforms", "snkpt_set_instances", "snkpt_build_tlas",
            "snkpt_set_frame", "snkpt_trace_primary", "snkpt_render", "snkpt_accumulate", "snkpt_read_output", "snkpt_read_aux",
@@ -212,6 +212,13 @@ class PathTracer:
 
     def synchronize(self):
         self._ck(self.L.snkpt_synchronize(self.h), "snkpt_synchronize")
+
+    def set_rows(self, row_begin: int, row_end: int):
+        self._ck(self.L.snkpt_set_rows(self.h, row_begin, row_end), "snkpt_set_rows")
+        self.rows = (row_begin, row_end or self.height)
+
+    def set_halo(self, pass1_halo: int, gbuffer_halo: int):
+        self._ck(self.L.snkpt_set_halo(self.h, pass1_halo, gbuffer_halo), "snkpt_set_halo")
 
     def reset_history(self):
         self._ck(self.L.snkpt_reset_history(self.h), "snkpt_reset_history")

@@ -277,6 +277,13 @@ int snkpt_set_rows(SnkPt* ctx, uint32_t row_begin, uint32_t row_end) {
   return SNKPT_OK;
 }
 
+int snkpt_set_halo(SnkPt* ctx, uint32_t pass1_halo, uint32_t gbuffer_halo) {
+  if (!ctx) return SNKPT_E_INVALID;
+  REQUIRE(gbuffer_halo >= pass1_halo, SNKPT_E_INVALID, "snkpt_set_halo: the G-buffer halo must cover the pass-1 halo");
+  ctx->halo_pass1 = pass1_halo; ctx->halo_gbuffer = gbuffer_halo;
+  return SNKPT_OK;
+}
+
 int snkpt_reset_history(SnkPt* ctx) {
   if (!ctx) return SNKPT_E_INVALID;
   ctx->history_valid = false;
@@ -579,6 +586,11 @@ int snkpt_set_frame(SnkPt* ctx, const SnkCommonUBO* cur, const SnkCommonUBO* pre
 static void fill_frame_dims(SnkPt* ctx) {
   ctx->fc.W = ctx->W; ctx->fc.H = ctx->H; ctx->fc.row0 = ctx->row0; ctx->fc.row1 = ctx->row1;
 }
+// band widened by `halo` rows on both sides, clamped to the image
+static void widen_rows(const SnkPt* ctx, uint32_t halo, uint32_t& r0, uint32_t& r1) {
+  r0 = ctx->row0 > halo ? ctx->row0 - halo : 0u;
+  r1 = ctx->row1 + halo < ctx->H ? ctx->row1 + halo : ctx->H;
+}
 
 int snkpt_trace_primary(SnkPt* ctx, const float* jitter_xy, void* stream) {
   if (!ctx) return SNKPT_E_INVALID;
@@ -590,12 +602,14 @@ int snkpt_trace_primary(SnkPt* ctx, const float* jitter_xy, void* stream) {
   ctx->fc.jx = jitter_xy ? jitter_xy[0] : 0.f; ctx->fc.jy = jitter_xy ? jitter_xy[1] : 0.f;
   prof_reset(ctx);
   cudaEventRecord(ctx->ev[0], st);
-  const int rec = prof_begin(ctx, "primary", (uint64_t)ctx->W * (ctx->row1 - ctx->row0), false, false, st);
-  ctx->stats.kernel_launches += launch_primary(ctx->trace_scene(), ctx->scene_dev(), ctx->fc, ctx->planes, st);
+  FrameConsts fg = ctx->fc;
+  widen_rows(ctx, ctx->halo_gbuffer, fg.row0, fg.row1);
+  const int rec = prof_begin(ctx, "primary", (uint64_t)ctx->W * (fg.row1 - fg.row0), false, false, st);
+  ctx->stats.kernel_launches += launch_primary(ctx->trace_scene(), ctx->scene_dev(), fg, ctx->planes, st);
   prof_end(ctx, rec, st);
   cudaEventRecord(ctx->ev[1], st);
   CK(cudaGetLastError());
-  ctx->stats.rays_primary = (uint64_t)ctx->W * (ctx->row1 - ctx->row0);
+  ctx->stats.rays_primary = (uint64_t)ctx->W * (fg.row1 - fg.row0);
   ctx->stats.total_rays_primary += ctx->stats.rays_primary;
   ctx->gbuffer_valid = true;
   return SNKPT_OK;

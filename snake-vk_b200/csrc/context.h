@@ -95,6 +95,7 @@ struct SnkPt {
   cudaStream_t stream = nullptr;
   std::string err;
   uint32_t W = 0, H = 0, row0 = 0, row1 = 0;
+  uint32_t halo_pass1 = 0, halo_gbuffer = 0;  // extra rows around the band (snkpt_set_halo)
   uint32_t max_instances = 4096, max_transforms = 4096, max_materials = 4096;
 
   // mesh pools

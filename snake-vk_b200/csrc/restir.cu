@@ -417,15 +417,22 @@ int launch_restir_passes(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st) {
   const FrameConsts& fc = ctx->fc;
   const uint32_t n_tiles = ((fc.W + 15) / 16) * ((fc.row1 - fc.row0 + 7) / 8);
   const uint32_t grid = n_tiles < 148u * RT_CTAS_PER_SM ? n_tiles : 148u * RT_CTAS_PER_SM;
+  // pass 1 also covers the halo rows whose temporal reservoirs this band's spatial reuse reads (snkpt_set_halo)
+  FrameConsts f1 = fc;
+  f1.row0 = fc.row0 > ctx->halo_pass1 ? fc.row0 - ctx->halo_pass1 : 0u;
+  f1.row1 = fc.row1 + ctx->halo_pass1 < fc.H ? fc.row1 + ctx->halo_pass1 : fc.H;
+  const uint32_t n_tiles1 = ((fc.W + 15) / 16) * ((f1.row1 - f1.row0 + 7) / 8);
+  const uint32_t grid1 = n_tiles1 < 148u * RT_CTAS_PER_SM ? n_tiles1 : 148u * RT_CTAS_PER_SM;
   RestirParams rp{s.num_temporal_resamples, s.num_spatial_resamples, s.ris_iters, s.m_cap, s.neighbour_radius, s.normal_threshold, s.flags};
   unsigned long long* counter = reinterpret_cast<unsigned long long*>(ctx->dev_counters.as<uint32_t>() + 2);
   FrameConsts f = fc;
   f.prev_frame_invalid = (fc.prev_frame_invalid || !ctx->history_valid) ? 1u : 0u;
+  f1.prev_frame_invalid = f.prev_frame_invalid;
   int launches = 0;
   cudaEventRecord(ctx->ev[2], st);
   if (!(s.flags & SNKPT_RT_NO_RESTIR)) {
-    const int rec = prof_begin(ctx, "restir_pass1", (uint64_t)fc.W * (fc.row1 - fc.row0), false, false, st);
-    k_restir_pass1<<<grid, RT_THREADS, 0, st>>>(ctx->trace_scene(), ctx->scene_dev(), f, ctx->planes, rp, counter);
+    const int rec = prof_begin(ctx, "restir_pass1", (uint64_t)fc.W * (f1.row1 - f1.row0), false, false, st);
+    k_restir_pass1<<<grid1, RT_THREADS, 0, st>>>(ctx->trace_scene(), ctx->scene_dev(), f1, ctx->planes, rp, counter);
     prof_end(ctx, rec, st);
     ++launches;
   }

@@ -41,6 +41,7 @@ def lib() -> C.CDLL:
         L.snkor_frame_set.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.snkor_frame_gbuffer.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_uint32, C.c_uint32, C.c_int]
         L.snkor_frame_render.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]
+        L.snkor_frame_render_pass.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
         L.snkor_frame_read.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]
         L.snkor_frame_write_reservoirs.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32]
         L.snkor_frame_ray_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
@@ -133,6 +134,9 @@ class OracleFrame:
 
     def render(self, rows=(0, 0), threads=8):
         lib().snkor_frame_render(self.h, rows[0], rows[1], threads)
+
+    def render_pass(self, pass_: int, rows=(0, 0), threads=8):
+        lib().snkor_frame_render_pass(self.h, pass_, rows[0], rows[1], threads)
 
     def read(self, name: str) -> np.ndarray:
         what, dt, ch = AUX[name]

@@ -18,6 +18,8 @@ for w in $WHAT; do
         python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/launches_bench.log 2>&1; echo "launches rc=$?";;
     ncu) timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_trace -s ${NCU_SKIP:-4} -c ${NCU_COUNT:-4} -f -o $OUT/prof_trace \
         python tools/quick_bench.py ${SCENES:-c2} > $OUT/ncu_trace.log 2>&1; echo "ncu rc=$?";;
+    bench2) for sh in samples rows; do timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29511 \
+        bench.py --gpus ${NGPU:-2} --steps 20 --warmup 3 --shard $sh > $OUT/bench_${NGPU:-2}gpu_$sh.json 2> $OUT/bench_${NGPU:-2}gpu_$sh.err; echo "bench2 $sh rc=$?"; cat $OUT/bench_${NGPU:-2}gpu_$sh.json; tail -3 $OUT/bench_${NGPU:-2}gpu_$sh.err; done;;
     quick) timeout 600 python tools/quick_bench.py ${SCENES:-c2 c2flat} > $OUT/quick.log 2>&1; echo "quick rc=$?"; cat $OUT/quick.log;;
     quickstatic) SNKPT_TRACE_STATIC=1 timeout 600 python tools/quick_bench.py ${SCENES:-c2} > $OUT/quick_static.log 2>&1; cat $OUT/quick_static.log;;
     ncurestir) timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_restir -s 4 -c 2 -f -o $OUT/prof_restir \
