@@ -30,6 +30,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 METRIC, UNIT = "rays_per_second_frame_1080p", "Mrays/s"
+TRACE_PREFIXES = ("trace_", "ns_closest", "ns_any")
 
 
 def make_scene(snk, name: str, width: int, height: int):

@@ -12,7 +12,7 @@
 #include <cstdio>
 #include <cstring>
 
-#include "snk_raygen.h"
+#include "snk_northstar.h"
 
 using namespace snkor;
 
@@ -80,7 +80,8 @@ ORACLE_API void snkor_frame_gbuffer(void* fp, float jx, float jy, uint32_t y0, u
 ORACLE_API void snkor_frame_render(void* fp, uint32_t y0, uint32_t y1, int threads) {
   Frame& f = *(Frame*)fp;
   if (y1 == 0) y1 = f.g.h;
-  render_reference(f, y0, y1, threads);
+  if (f.settings.mode == 1) render_northstar(f, y0, y1, threads);
+  else render_reference(f, y0, y1, threads);
 }
 ORACLE_API void snkor_frame_render_pass(void* fp, uint32_t pass, uint32_t y0, uint32_t y1, int threads) {
   Frame& f = *(Frame*)fp;

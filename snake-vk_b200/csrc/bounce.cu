@@ -247,9 +247,4 @@ int launch_reference_frame(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st) 
   return launches;
 }
 
-int launch_northstar_frame(SnkPt* ctx, const SnkRtSettings&, cudaStream_t) {
-  ctx->err = "northstar frame: not built yet";
-  return SNKPT_E_STATE;
-}
-
 }  // namespace snk

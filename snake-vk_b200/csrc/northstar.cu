@@ -1,0 +1,417 @@
+// northstar.cu — the north-star estimator as wavefront stages (BASELINE.json north_star items 3 + 4):
+// 1 spp, up to max_bounces path vertices, GGX / Lambert BSDF sampling, MIS next-event estimation, Russian roulette.
+//
+// No counterpart in the reference (its estimator is the fixed 8x(1+2) tree of RayGen.rgen:139-213);
+// shared with it are the material model (LightBuffers.glsl:65-144), the light records, the emission convention
+// (RayClosestHit.rchit:119-123: emitted radiance = material albedo) and the direct term at the primary hit, which is
+// produced by the same ReSTIR DI kernels as in reference mode (restir.cu). The CPU statement this file must match bit
+// for bit is oracle/snk_northstar.h (same expression order, -fmad=false, float64 sin / cos rounded once).
+//
+//   k_ns_gen      pixel -> vertex x0 from the primary-hit ids: BSDF sample -> ray queue, throughput
+//   repeat b = 1..max_bounces:
+//     trace closest (persistent wavefront kernel, trace.cu)
+//     k_ns_vertex pixel -> adds the previous vertex's NEE (C x visibility); hit -> surface; emissive hit -> MIS-weighted
+//                 emission; else NEE sample (C + shadow ray), Russian roulette, BSDF sample -> next ray
+//     trace any   shadow rays -> visibility
+//   k_ns_resolve  pixel -> last NEE term, out = direct + indirect (or emission / sky)
+// One path per pixel, so every queue is a per-pixel plane (slot = pixel of the band); dead paths carry tmax < 0.
+// All surfaces share one BSDF model, so there is nothing to sort the shading queue by material for.
+#include "kernels.h"
+#include "shading.cuh"
+
+namespace snk {
+
+namespace {
+
+struct NsBuffers {
+  float4* rays;     // 2 x float4 per pixel: continuation ray
+  float4* hit;      // t,u,v,prim
+  uint32_t* inst;
+  float4* T;        // throughput rgb, pdf of the BSDF sample that produced the ray
+  float4* L;        // indirect radiance so far
+  float4* srays;    // 2 x float4 per pixel: NEE shadow ray
+  float4* C;        // pending NEE contribution (unshadowed)
+  float* vis;       // visibility of the pending NEE ray
+};
+
+__device__ __forceinline__ uint32_t pcg_hash(uint32_t v) {
+  const uint32_t state = v * 747796405u + 2891336453u;
+  const uint32_t word = ((state >> ((state >> 28u) + 4u)) ^ state) * 277803737u;
+  return (word >> 22u) ^ word;
+}
+__device__ __forceinline__ float ns_rand(uint32_t pixel, uint32_t frame, uint32_t dim) {
+  const uint32_t h = pcg_hash(pcg_hash(pcg_hash(pixel) + frame) + dim);
+  return (float)(h >> 8) * (1.0f / 16777216.0f);
+}
+
+struct NsSurf {
+  vec3 p, n, albedo;
+  float roughness, metallic;
+  uint32_t flags, ntri;
+  float area;
+};
+
+static __device__ __noinline__ NsSurf ns_surface(const SceneDev& D, uint32_t inst, uint32_t prim, float u, float v) {
+  NsSurf s;
+  const float b0 = (1.0f - u) - v;
+  const SnkInstanceData in = load_instance(D, inst);
+  uint32_t ia, ib, ic;
+  tri_indices(D, in, prim, ia, ib, ic);
+  const vec3 pa = ld3(D.positions, ia), pb = ld3(D.positions, ib), pc = ld3(D.positions, ic);
+  const vec3 p = (pa * b0 + pb * u) + pc * v;
+  const vec3 n = (ld3(D.normals, ia) * b0 + ld3(D.normals, ib) * u) + ld3(D.normals, ic) * v;
+  const float* M = D.transforms + 16ull * in.transform_idx;
+  s.p = mul_point(M, p);
+  s.n = normalize(mul_mat3r(D.normal_mats + 9ull * in.transform_idx, n));
+  const SnkMaterial* m = D.materials + in.material_idx;
+  const float4 alb = __ldg(reinterpret_cast<const float4*>(m->albedo));
+  s.albedo = v3(alb.x, alb.y, alb.z);
+  s.roughness = gmax(__ldg(&m->roughness), 0.05f);
+  s.metallic = __ldg(&m->metallic);
+  s.flags = __ldg(&m->flags);
+  s.ntri = in.num_mesh_indices / 3u;
+  const vec3 wa = mul_point(M, pa), wb = mul_point(M, pb), wc = mul_point(M, pc);
+  s.area = 0.5f * length(cross(wb - wa, wc - wa));
+  return s;
+}
+
+static __device__ __noinline__ vec3 ns_bsdf_cos(vec3 n, vec3 wo, vec3 wi, vec3 albedo, float roughness, float metallic) {
+  const vec3 f0 = mix(v3(0.04f), albedo, metallic);
+  const vec3 h = normalize(wo + wi);
+  const vec3 f = fresnel_schlick(gmax(dot(h, wo), 0.0f), f0);
+  const float ndf = distribution_ggx(h, n, roughness);
+  const float g = geometry_smith(wo, wi, n, roughness);
+  const vec3 num = (ndf * g) * f;
+  const float denom = 4.0f * gmax(dot(n, wo), 0.0f) * gmax(dot(n, wi), 0.0f) + 0.0001f;
+  const vec3 specular = num / denom;
+  vec3 kd = v3(1.0f) - f;
+  kd *= 1.0f - metallic;
+  const float n_dot_l = gmax(dot(n, wi), 0.0f);
+  return (kd * albedo / PI_GLSL + specular) * n_dot_l;
+}
+__device__ __forceinline__ float ns_spec_prob(float metallic) { return 0.25f + 0.5f * metallic; }
+static __device__ __noinline__ float ns_pdf(vec3 n, vec3 wo, vec3 wi, float roughness, float metallic) {
+  const float ps = ns_spec_prob(metallic);
+  const float n_dot_l = gmax(dot(n, wi), 0.0f);
+  const vec3 h = normalize(wo + wi);
+  const float n_dot_h = gmax(dot(n, h), 0.0f);
+  const float v_dot_h = gmax(dot(wo, h), 0.000001f);
+  const float d = distribution_ggx(h, n, roughness);
+  return (1.0f - ps) * (n_dot_l / PI_GLSL) + ps * ((d * n_dot_h) / (4.0f * v_dot_h));
+}
+__device__ __forceinline__ bool ns_sample(vec3 n, vec3 wo, float roughness, float metallic, float u0, float u1, float u2, vec3& wi) {
+  vec3 nt, nb;
+  create_coordinate_system(n, nt, nb);
+  const float phi = (2.0f * PI_GLSL) * u2;
+  const float cp = cos_c(phi), sp = sin_c(phi);
+  if (u0 < ns_spec_prob(metallic)) {
+    const float a = roughness * roughness;
+    const float a2 = a * a;
+    const float cos_t = sqrtf((1.0f - u1) / (1.0f + (a2 - 1.0f) * u1));
+    const float sin_t = sqrtf(gmax(1.0f - cos_t * cos_t, 0.0f));
+    const vec3 l = v3(sin_t * cp, cos_t, sin_t * sp);
+    const vec3 h = v3((l.x * nb.x + l.y * n.x) + l.z * nt.x, (l.x * nb.y + l.y * n.y) + l.z * nt.y, (l.x * nb.z + l.y * n.z) + l.z * nt.z);
+    wi = h * (2.0f * dot(wo, h)) - wo;
+  } else {
+    const float r = sqrtf(u1);
+    const vec3 l = v3(r * cp, sqrtf(gmax(1.0f - u1, 0.0f)), r * sp);
+    wi = v3((l.x * nb.x + l.y * n.x) + l.z * nt.x, (l.x * nb.y + l.y * n.y) + l.z * nt.y, (l.x * nb.z + l.y * n.z) + l.z * nt.z);
+  }
+  wi = normalize(wi);
+  return dot(n, wi) > 0.0f;
+}
+
+struct NsLightCounts { uint32_t has_dir, n_pl, n_em, n_types; };
+__device__ __forceinline__ NsLightCounts ns_light_counts(const SceneDev& D) {
+  NsLightCounts c;
+  const float4 col = __ldg(reinterpret_cast<const float4*>(D.lights->dir_light.colour));
+  c.has_dir = (col.x > 0.0f || col.y > 0.0f || col.z > 0.0f) ? 1u : 0u;
+  c.n_pl = D.lights->num_pointlights;
+  c.n_em = D.num_emissive;
+  c.n_types = c.has_dir + (c.n_pl ? 1u : 0u) + (c.n_em ? 1u : 0u);
+  return c;
+}
+__device__ __forceinline__ uint32_t ns_pick(float u, uint32_t n) { const uint32_t i = to_uint(u * (float)n); return i >= n ? n - 1 : i; }
+__device__ __forceinline__ float ns_nee_pdf_emissive(const NsLightCounts& lc, uint32_t ntri, float area, float dist, vec3 nl, vec3 wi) {
+  const float cos_l = fabsf(dot(nl, wi));
+  if (!(cos_l > 0.000001f) || !(area > 0.0f)) return 0.0f;
+  const float p_pick = (1.0f / (float)lc.n_types) * (1.0f / ((float)lc.n_em * (float)ntri));
+  return p_pick * ((dist * dist) / (cos_l * area));
+}
+
+__device__ __forceinline__ void put_ray(float4* q, size_t i, vec3 o, float tmin, vec3 d, float tmax) {
+  q[2 * i] = make_float4(o.x, o.y, o.z, tmin);
+  q[2 * i + 1] = make_float4(d.x, d.y, d.z, tmax);
+}
+__device__ __forceinline__ void put_dead(float4* q, size_t i) {
+  q[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  q[2 * i + 1] = make_float4(0.f, 1.f, 0.f, -1.0f);
+}
+
+// work of path vertex x_b (b = 0: the primary hit): NEE (b >= 1), Russian roulette (b >= 2), BSDF sample.
+// Writes the shadow ray + pending C, the continuation ray, throughput and pdf for slot i.
+__device__ void ns_vertex_work(const SceneDev& D, const NsBuffers& B, size_t i, uint32_t pixel, uint32_t frame, uint32_t b, uint32_t max_bounces,
+                               const NsSurf& s, vec3 wo, vec3 T, unsigned long long& n_shadow, unsigned long long& n_closest) {
+  const NsLightCounts lc = ns_light_counts(D);
+  vec3 n = s.n;
+  if (dot(n, wo) < 0.0f) n = -n;
+  const vec3 o = s.p + n * 0.01f;
+  const uint32_t dim = 16u * b;
+  vec3 C = v3(0.0f);
+  bool shadow = false;
+  if (b >= 1 && lc.n_types > 0) {
+    const uint32_t t = ns_pick(ns_rand(pixel, frame, dim + 3), lc.n_types);
+    uint32_t type = 0;
+    {
+      uint32_t k = 0;
+      bool found = false;
+      if (lc.has_dir) { if (k == t) { type = 0; found = true; } ++k; }
+      if (!found && lc.n_pl) { if (k == t) { type = 1; found = true; } ++k; }
+      if (!found && lc.n_em) { if (k == t) { type = 2; found = true; } ++k; }
+    }
+    const float p_type = 1.0f / (float)lc.n_types;
+    const float u1 = ns_rand(pixel, frame, dim + 4), u2 = ns_rand(pixel, frame, dim + 5);
+    const float u3 = ns_rand(pixel, frame, dim + 6), u4 = ns_rand(pixel, frame, dim + 7);
+    vec3 wi = v3(0.0f, 1.0f, 0.0f);
+    float tmax = -1.0f;
+    if (type == 0) {
+      const float4 dl = __ldg(reinterpret_cast<const float4*>(D.lights->dir_light.dir));
+      wi = v3(dl.x, dl.y, dl.z);
+      if (dot(n, wi) > 0.0f) {
+        const float4 dc = __ldg(reinterpret_cast<const float4*>(D.lights->dir_light.colour));
+        C = ((T * ns_bsdf_cos(n, wo, wi, s.albedo, s.roughness, s.metallic)) * v3(dc.x, dc.y, dc.z)) / p_type;
+        tmax = 10000.0f;
+      }
+    } else if (type == 1) {
+      const uint32_t idx = ns_pick(u1, lc.n_pl);
+      const PointLightRec pl = load_pointlight(D.lights, idx);
+      const vec3 d = pl.pos - o;
+      const float dist = length(d);
+      wi = d / dist;
+      if (dot(n, wi) > 0.0f && dist > 0.002f) {
+        const float atten = (pl.atten_constant + pl.atten_linear * dist) + pl.atten_exp * (dist * dist);
+        C = (((T * ns_bsdf_cos(n, wo, wi, s.albedo, s.roughness, s.metallic)) * pl.colour) / atten) / (p_type * (1.0f / (float)lc.n_pl));
+        tmax = dist - 0.001f;
+      }
+    } else {
+      const uint32_t obj = __ldg(D.emissive_idx + ns_pick(u1, lc.n_em));
+      const uint32_t ntri = load_instance(D, obj).num_mesh_indices / 3u;
+      const uint32_t tri = ns_pick(u2, ntri);
+      float bu = u3, bv = u4;
+      if (bu + bv >= 1.0f) { bu = 1.0f - bu; bv = 1.0f - bv; }
+      const NsSurf q = ns_surface(D, obj, tri, bu, bv);
+      const vec3 d = q.p - o;
+      const float dist = length(d);
+      wi = d / dist;
+      const float pdf_w = ns_nee_pdf_emissive(lc, ntri, q.area, dist, q.n, wi);
+      if (dot(n, wi) > 0.0f && pdf_w > 0.0f && dist > 0.01f) {
+        const float p_bsdf = ns_pdf(n, wo, wi, s.roughness, s.metallic);
+        const float w = (pdf_w * pdf_w) / (pdf_w * pdf_w + p_bsdf * p_bsdf);
+        C = (((T * ns_bsdf_cos(n, wo, wi, s.albedo, s.roughness, s.metallic)) * q.albedo) * w) / pdf_w;
+        tmax = dist - 0.005f;
+      }
+    }
+    if (tmax > 0.0f) {
+      put_ray(B.srays, i, o, 0.001f, wi, tmax);
+      shadow = true;
+      ++n_shadow;
+    } else {
+      C = v3(0.0f);
+    }
+  }
+  if (!shadow) put_dead(B.srays, i);
+  B.C[i] = make_float4(C.x, C.y, C.z, 0.0f);
+  // ---- continuation
+  bool alive = b < max_bounces;
+  if (alive && b >= 2) {
+    const float q = gmin(gmax(gmax(T.x, T.y), T.z), 0.95f);
+    if (!(ns_rand(pixel, frame, dim + 8) < q)) alive = false;
+    else T = T / q;
+  }
+  vec3 wi = v3(0.0f, 1.0f, 0.0f);
+  float pdf_b = 0.0f;
+  if (alive) alive = ns_sample(n, wo, s.roughness, s.metallic, ns_rand(pixel, frame, dim), ns_rand(pixel, frame, dim + 1), ns_rand(pixel, frame, dim + 2), wi);
+  if (alive) {
+    pdf_b = ns_pdf(n, wo, wi, s.roughness, s.metallic);
+    alive = pdf_b > 0.0f;
+  }
+  if (alive) {
+    T = (T * ns_bsdf_cos(n, wo, wi, s.albedo, s.roughness, s.metallic)) / pdf_b;
+    alive = gmax(gmax(T.x, T.y), T.z) > 0.0f;
+  }
+  if (alive) {
+    put_ray(B.rays, i, o, 0.001f, wi, 1000.0f);
+    ++n_closest;
+  } else {
+    put_dead(B.rays, i);
+  }
+  B.T[i] = make_float4(T.x, T.y, T.z, pdf_b);
+}
+
+__device__ __forceinline__ void flush_counts(unsigned long long n_shadow, unsigned long long n_closest, unsigned long long* counters) {
+  for (int o = 16; o > 0; o >>= 1) {
+    n_shadow += __shfl_xor_sync(0xFFFFFFFFu, n_shadow, o);
+    n_closest += __shfl_xor_sync(0xFFFFFFFFu, n_closest, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (n_shadow) atomicAdd(counters, n_shadow);
+    if (n_closest) atomicAdd(counters + 1, n_closest);
+  }
+}
+
+__global__ void __launch_bounds__(128) k_ns_gen(SceneDev D, FrameConsts fc, PixelPlanes P, NsBuffers B, uint32_t npix, uint32_t max_bounces,
+                                                unsigned long long* counters) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long n_shadow = 0, n_closest = 0;
+  if (i < npix) {
+    const uint32_t x = i % fc.W, y = fc.row0 + i / fc.W;
+    const size_t px = (size_t)y * fc.W + x;
+    B.L[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    B.vis[i] = 1.0f;
+    bool alive = P.prim[px] != INVALID_IDX;
+    NsSurf s;
+    if (alive) {
+      const float2 bc = P.bary[px];
+      s = ns_surface(D, P.inst[px], P.prim[px], bc.x, bc.y);
+      alive = !(s.flags & SNKPT_MAT_FLAG_EMISSIVE);
+    }
+    if (alive) {
+      const vec3 cam = v3(fc.cam_pos[0], fc.cam_pos[1], fc.cam_pos[2]);
+      const vec3 wo = normalize(cam - s.p);
+      ns_vertex_work(D, B, i, (uint32_t)px, fc.frame_idx, 0u, max_bounces, s, wo, v3(1.0f), n_shadow, n_closest);
+    } else {
+      put_dead(B.rays, i); put_dead(B.srays, i);
+      B.C[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      B.T[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  flush_counts(n_shadow, n_closest, counters);
+}
+
+// the hit of the ray that left vertex x_{b-1} becomes vertex x_b
+__global__ void __launch_bounds__(128) k_ns_vertex(SceneDev D, FrameConsts fc, NsBuffers B, uint32_t npix, uint32_t b, uint32_t max_bounces,
+                                                   unsigned long long* counters) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long n_shadow = 0, n_closest = 0;
+  if (i < npix) {
+    const uint32_t x = i % fc.W, y = fc.row0 + i / fc.W;
+    const uint32_t pixel = y * fc.W + x;
+    // the previous vertex's next-event estimate, now that its shadow ray is resolved
+    float4 L4 = B.L[i];
+    vec3 L = v3(L4.x, L4.y, L4.z);
+    if (b >= 2) {
+      const float4 c = B.C[i];
+      L += v3(c.x, c.y, c.z) * B.vis[i];
+    }
+    const float4 r0 = B.rays[2 * i], r1 = B.rays[2 * i + 1];
+    bool alive = r1.w >= 0.0f;
+    const float4 h = B.hit[i];
+    if (alive && h.x < 0.0f) alive = false;
+    NsSurf s;
+    const vec3 wi = v3(r1.x, r1.y, r1.z);
+    const float4 T4 = B.T[i];
+    const vec3 T = v3(T4.x, T4.y, T4.z);
+    if (alive) {
+      s = ns_surface(D, B.inst[i], __float_as_uint(h.w), h.y, h.z);
+      if (s.flags & SNKPT_MAT_FLAG_EMISSIVE) {
+        if (b >= 2) {  // the ray left x_{b-1} with b-1 >= 1
+          const NsLightCounts lc = ns_light_counts(D);
+          const float pdf_b = T4.w;
+          const float p_nee = ns_nee_pdf_emissive(lc, s.ntri, s.area, h.x, s.n, wi);
+          const float w = (pdf_b * pdf_b) / (pdf_b * pdf_b + p_nee * p_nee);
+          L += (T * s.albedo) * w;
+        }
+        alive = false;
+      }
+    }
+    B.L[i] = make_float4(L.x, L.y, L.z, 0.0f);
+    if (alive) {
+      ns_vertex_work(D, B, i, pixel, fc.frame_idx, b, max_bounces, s, -wi, T, n_shadow, n_closest);
+    } else {
+      put_dead(B.rays, i); put_dead(B.srays, i);
+      B.C[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    (void)r0;
+  }
+  flush_counts(n_shadow, n_closest, counters);
+}
+
+__global__ void __launch_bounds__(256) k_ns_resolve(SceneDev D, FrameConsts fc, PixelPlanes P, NsBuffers B, uint32_t npix, uint32_t max_bounces) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  const uint32_t x = i % fc.W, y = fc.row0 + i / fc.W;
+  const size_t px = (size_t)y * fc.W + x;
+  vec3 out = v3(0.0f);
+  if (P.prim[px] != INVALID_IDX) {
+    const float2 bc = P.bary[px];
+    const NsSurf s = ns_surface(D, P.inst[px], P.prim[px], bc.x, bc.y);
+    if (s.flags & SNKPT_MAT_FLAG_EMISSIVE) out = s.albedo;
+    else {
+      const float4 L4 = B.L[i];
+      vec3 L = v3(L4.x, L4.y, L4.z);
+      if (max_bounces >= 1) {
+        const float4 c = B.C[i];
+        L += v3(c.x, c.y, c.z) * B.vis[i];
+      }
+      const float4 d = P.direct[px];
+      out = v3(d.x, d.y, d.z) + L;
+    }
+  }
+  P.radiance[px] = make_float4(out.x, out.y, out.z, 1.0f);
+  P.out16[px] = make_ushort4(f2h(out.x), f2h(out.y), f2h(out.z), f2h(1.0f));
+}
+
+__global__ void k_fold_counters_ns(unsigned long long* c) {
+  c[4] += c[1];
+  c[5] += c[2];
+}
+
+}  // namespace
+
+int launch_northstar_frame(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st) {
+  const FrameConsts& fc = ctx->fc;
+  const uint32_t npix = fc.W * (fc.row1 - fc.row0);
+  if (s.max_bounces > 16) { ctx->err = "snkpt_render: max_bounces > 16"; return SNKPT_E_INVALID; }
+  int launches = 0;
+  cudaMemsetAsync(ctx->dev_counters.as<uint32_t>() + 2, 0, 16, st);
+  launches += launch_restir_passes(ctx, s, st);  // direct term at the primary hit (directional light + reservoirs)
+  const size_t sizes[8] = {32ull * npix, 16ull * npix, 4ull * npix, 16ull * npix, 16ull * npix, 32ull * npix, 16ull * npix, 4ull * npix};
+  for (int k = 0; k < 8; ++k) {
+    cudaError_t e = ctx->wave[k].reserve(sizes[k], false, st);
+    if (e != cudaSuccess) { ctx->err = std::string("north-star queues: ") + cudaGetErrorString(e); return SNKPT_E_NOMEM; }
+  }
+  NsBuffers B;
+  B.rays = ctx->wave[0].as<float4>(); B.hit = ctx->wave[1].as<float4>(); B.inst = ctx->wave[2].as<uint32_t>(); B.T = ctx->wave[3].as<float4>();
+  B.L = ctx->wave[4].as<float4>(); B.srays = ctx->wave[5].as<float4>(); B.C = ctx->wave[6].as<float4>(); B.vis = ctx->wave[7].as<float>();
+  unsigned long long* counters = reinterpret_cast<unsigned long long*>(ctx->dev_counters.as<uint32_t>() + 2);
+  const SceneDev D = ctx->scene_dev();
+  const uint32_t g128 = (npix + 127) / 128;
+  const bool bounce = !(s.flags & SNKPT_RT_NO_BOUNCE);
+  const uint32_t max_bounces = bounce ? s.max_bounces : 0u;
+  int rec = prof_begin(ctx, "ns_gen", npix, false, false, st);
+  k_ns_gen<<<g128, 128, 0, st>>>(D, fc, ctx->planes, B, npix, max_bounces, counters);
+  prof_end(ctx, rec, st);
+  ++launches;
+  char name[32];
+  for (uint32_t b = 1; b <= max_bounces; ++b) {
+    snprintf(name, sizeof(name), "ns_closest.%u", b);
+    launches += traced_launch(ctx, name, B.rays, npix, false, nullptr, B.hit, B.inst, nullptr, st);
+    snprintf(name, sizeof(name), "ns_vertex.%u", b);
+    rec = prof_begin(ctx, name, npix, false, false, st);
+    k_ns_vertex<<<g128, 128, 0, st>>>(D, fc, B, npix, b, max_bounces, counters);
+    prof_end(ctx, rec, st);
+    snprintf(name, sizeof(name), "ns_any.%u", b);
+    launches += 1 + traced_launch(ctx, name, B.srays, npix, true, nullptr, nullptr, nullptr, B.vis, st);
+  }
+  rec = prof_begin(ctx, "ns_resolve", npix, false, false, st);
+  k_ns_resolve<<<(npix + 255) / 256, 256, 0, st>>>(D, fc, ctx->planes, B, npix, max_bounces);
+  prof_end(ctx, rec, st);
+  k_fold_counters_ns<<<1, 1, 0, st>>>(reinterpret_cast<unsigned long long*>(ctx->dev_counters.as<uint32_t>()));
+  launches += 2;
+  cudaEventRecord(ctx->ev[5], st);
+  ctx->stats.kernel_launches += launches;
+  ctx->render_pending = true;
+  return launches;
+}
+
+}  // namespace snk

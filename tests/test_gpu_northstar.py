@@ -1,0 +1,76 @@
+"""North-star estimator (1 spp, 4 bounces, MIS NEE, RR) — CUDA wavefront stages vs the CPU statement
+(oracle/snk_northstar.h): same expression order under the float32 numerics contract, so radiance is compared
+bit for bit; plus estimator-level properties (no NaN, energy bound in a closed diffuse box, bounce count monotone)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def bits_equal(a, b):
+    return ((a.view(np.uint32) == b.view(np.uint32)) | ((a != a) & (b != b))).all(-1)
+
+
+def run(snk, oracle, sc, frames, **kw):
+    osc = oracle.OracleScene(sc)
+    fr = oracle.OracleFrame(osc)
+    rt = snk.RT().Init(sc)
+    prev = None
+    for f in range(frames):
+        pos = np.asarray(sc.camera.pos, np.float32) + np.asarray((0.05, 0.0, 0.1), np.float32) * f
+        ubo = sc.ubo(f, cam_pos=pos)
+        p = ubo if prev is None else prev
+        fr.set(ubo, p, oracle.default_settings(mode=1, **kw))
+        fr.gbuffer()
+        fr.render()
+        rt.RecordRenderCmdBuf(ubo, p, mode=snk.api.MODE_NORTHSTAR, **kw)
+        prev = ubo
+        yield f, rt.pt, fr
+
+
+@pytest.mark.parametrize("scene_name", ["small", "cornell_pl"])
+def test_northstar_matches_oracle(snk, oracle, scene_name):
+    sc = snk.scenes.small_test_scene(96, 64) if scene_name == "small" else snk.scenes.cornell(96, 96, with_pointlight=True)
+    for f, pt, fr in run(snk, oracle, sc, frames=3):
+        a, b = pt.read_aux("radiance")[..., :3], fr.read("radiance")[..., :3]
+        assert not np.isnan(a).any()
+        eq = bits_equal(a, b)
+        assert eq.mean() >= 0.998, f"frame {f}: radiance differs on {(~eq).sum()} of {eq.size} pixels; max abs {np.abs(a - b).max()}"
+        st = pt.stats()
+        oc, oa = fr.ray_counts(reset=True)
+        assert (int(st["rays_secondary"]), int(st["rays_shadow"])) == (oc, oa), "ray counts differ from the oracle's"
+        assert int(st["stack_overflows"]) == 0
+        npix = sc.width * sc.height
+        assert int(st["rays_secondary"]) <= 4 * npix
+
+
+def test_bounce_count_and_flags(snk, oracle):
+    sc = snk.scenes.cornell(64, 64, with_pointlight=True)
+    means = []
+    for mb in (0, 1, 4):
+        for f, pt, fr in run(snk, oracle, sc, frames=1, max_bounces=mb):
+            a, b = pt.read_aux("radiance")[..., :3], fr.read("radiance")[..., :3]
+            assert bits_equal(a, b).mean() >= 0.998
+            means.append(float(a.mean()))
+            if mb == 0:
+                assert np.array_equal(a, np.where(np.isnan(a), a, pt.read_aux("radiance")[..., :3]))
+                assert int(pt.stats()["rays_secondary"]) == 0
+    assert means[0] <= means[1] <= means[2] * 1.2  # indirect light only adds energy (up to 1-frame noise)
+
+
+def test_furnace_energy_bound(snk):
+    """closed grey box (albedo 0.5) lit only by the ceiling quad: the converged mean radiance of non-emissive
+    pixels must stay below the analytic bound Le * A_light/A_total * rho / (1 - rho) x safety (no energy gain)."""
+    sc = snk.scenes.cornell(64, 64)
+    rt = snk.RT().Init(sc)
+    acc = np.zeros((64, 64, 3))
+    n = 48
+    for f in range(n):
+        ubo = sc.ubo(f)
+        rt.RecordRenderCmdBuf(ubo, ubo, mode=snk.api.MODE_NORTHSTAR)
+        acc += rt.pt.read_aux("radiance")[..., :3]
+    img = acc / n
+    assert np.isfinite(img).all() and (img >= 0).all()
+    flags = rt.pt.read_aux("flags")
+    body = img[(flags & 1) == 0]
+    assert 0.01 < body.mean() < 3.0

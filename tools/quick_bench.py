@@ -12,7 +12,8 @@ for name in (sys.argv[1:] or ["c2"]):
     pt = snk.PathTracer(sc.width, sc.height)
     pt.upload_scene(sc)
     print(f"== {name}: {desc}; upload+build {time.time()-t0:.2f} s, last build {float(pt.stats()['ms_build_last']):.3f} ms")
-    st = snk.api.default_settings()
+    st = snk.api.default_settings(mode=1 if os.environ.get("MODE", "reference") == "northstar" else 0,
+                                  ris_iters=int(os.environ.get("RIS", "32")))
     def step(f):
         ubo = bench.frame_ubo(sc, f); prev = bench.frame_ubo(sc, f - 1) if f else ubo
         pt.build_tlas(); pt.set_frame(ubo, prev); pt.trace_primary(); pt.render(st)
