@@ -5,7 +5,11 @@
 
 A step = one frame of the pass on the C2 workload (261,122 triangles, 1920x1080): per-frame TLAS rebuild
 (TlasSystem::BuildTlas), primary visibility (replaces the raster G-buffer pass), ReSTIR DI pass 1 + 2 and the
-bounce stages (RT::RecordRenderCmdBuf). `value` = all rays traced by all ranks / max-over-ranks device time.
+path stages. Two estimators (never mix them in one number): `--mode northstar` (default; BASELINE.json's
+metric: 1 spp, 4 bounces + ReSTIR DI) and `--mode reference` (the reference's own frame, RT::RecordRenderCmdBuf: ReSTIR
++ the 8x(1+2) BounceDiffuse tree, <= 65 rays/pixel — the parity-tested restatement of the reference's shaders); the
+mode not selected is measured too and reported under `other_mode`.
+`value` = all rays traced by all ranks / max-over-ranks device time.
 N > 1 is sample-sharded (every rank renders the whole frame with its own seed; radiance is summed over NVLink
 with one NCCL all-reduce per frame = the accumulation step) → weak scaling. `--shard rows` renders contiguous
 row bands instead (strong scaling, no collective; halo rows are re-rendered locally).
@@ -204,149 +208,161 @@ def run_gpu_arm(args, snk):
         pt.set_halo(bands.pass1_halo, bands.gbuffer_halo)
         # the three SoA planes of the FINAL reservoirs (buffer half 0), aliased for the NCCL halo exchange
         res_planes = [torch.as_tensor(CudaArray(pt.device_ptr(0x110 + k)[0], (H, W, 4)), device=f"cuda:{local}") for k in range(3)]
-    mode = snk.api.MODE_REFERENCE if args.mode == "reference" else snk.api.MODE_NORTHSTAR
-    settings = snk.api.default_settings(mode=mode)
     stream = torch.cuda.current_stream().cuda_stream
     seed_off = rank if (world > 1 and args.shard == "samples") else 0
     rad = None
     if world > 1 and args.shard == "samples":
         ptr, nbytes = pt.device_ptr(0x102)
         rad = torch.as_tensor(CudaArray(ptr, (H, W, 4)), device=f"cuda:{local}")
-
-    def step(f: int):
-        ubo = frame_ubo(sc, f, seed_off)
-        prev = frame_ubo(sc, f - 1, seed_off) if f > 0 else ubo
-        pt.build_tlas(stream)           # TlasSystem::BuildTlas — rebuilt every frame like the reference
-        pt.set_frame(ubo, prev)
-        pt.trace_primary(stream=stream)
-        pt.render(settings, stream)
-        if rad is not None:
-            dist.all_reduce(rad)        # accumulation step: sum of the per-GPU samples over NVLink
-        if res_planes is not None:
-            snk.sharding.exchange_final(bands, rank, res_planes, dist)  # final-reservoir halos to the band neighbours
+    peak, peak_src = measured_peaks()
+    RAYS = ("total_rays_primary", "total_rays_shadow", "total_rays_secondary")
+    frame_no = [0]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    f = 0
-    for _ in range(args.warmup):
-        step(f)
-        f += 1
-    barrier()
-    st0 = pt.stats()
-    pt.set_profiling(1)
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for _ in range(args.steps):
-        step(f)
-        f += 1
-    e1.record()
-    barrier()
-    ms_total = e0.elapsed_time(e1)
-    clk = clocks.stop() if rank == 0 else None
-    st1 = pt.stats()
-    timings = pt.launch_timings()
-    rays = sum(int(st1[k]) - int(st0[k]) for k in ("total_rays_primary", "total_rays_shadow", "total_rays_secondary"))
-    launches = int(st1["kernel_launches"]) - int(st0["kernel_launches"])
-    if world > 1:
-        t = torch.tensor([ms_total, float(rays), float(launches)], device=f"cuda:{local}", dtype=torch.float64)
+    def reduce_max_sum(vals):
+        """[time-like, additive...] -> max over ranks of the first, sum of the rest"""
+        if world == 1:
+            return vals
+        t = torch.tensor(vals, device=f"cuda:{local}", dtype=torch.float64)
         tmax = t.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        ms_total, rays, launches = float(tmax[0]), float(t[1]), int(t[2])
-    value = rays / (ms_total * 1e-3) / 1e6
+        return [float(tmax[0])] + [float(v) for v in t[1:]]
 
-    # ---- end to end through the C ABI with host buffers (rank-local; max over ranks)
-    import ctypes
-    out_host = torch.empty((rows[1] - rows[0], W, 4), dtype=torch.float16, pin_memory=True)
-    out_np = out_host.numpy()
-    n_inst = flat["instances"].shape[0]
-    h2d = 2 * 240 + 2 * flat["transforms"].nbytes + flat["instances"].nbytes + flat["blas_of_instance"].nbytes + flat["emissive_idx"].nbytes
-    d2h = out_np.nbytes
-    pt.set_profiling(0)
+    def measure(mode_name: str, with_e2e: bool):
+        mode = snk.api.MODE_REFERENCE if mode_name == "reference" else snk.api.MODE_NORTHSTAR
+        settings = snk.api.default_settings(mode=mode)
 
-    def e2e_step(f: int):
-        pt.set_transforms(flat["transforms"], flat["prev_transforms"])  # TransformBufferSystem: cur + prev, host → device
-        pt.set_instances(flat["instances"], flat["blas_of_instance"], flat["emissive_idx"])
-        step(f)
-        if rank == 0 or rad is None:
-            pt.read_output("f16", out_np)  # device → host: the RGBA16F image the engine would present
+        def step():
+            f = frame_no[0]
+            frame_no[0] += 1
+            ubo = frame_ubo(sc, f, seed_off)
+            prev = frame_ubo(sc, f - 1, seed_off) if f > 0 else ubo
+            pt.build_tlas(stream)           # TlasSystem::BuildTlas — rebuilt every frame like the reference
+            pt.set_frame(ubo, prev)
+            pt.trace_primary(stream=stream)
+            pt.render(settings, stream)
+            if rad is not None:
+                dist.all_reduce(rad)        # accumulation step: sum of the per-GPU samples over NVLink
+            if res_planes is not None:
+                snk.sharding.exchange_final(bands, rank, res_planes, dist)  # final-reservoir halos to the band neighbours
 
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        e2e_step(f)
-        f += 1
-    barrier()
-    st2 = pt.stats()
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(e2e_steps):
-        e2e_step(f)
-        f += 1
-    e1.record()
-    barrier()
-    e2e_ms = max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0) * 0.0)
-    st3 = pt.stats()
-    e2e_rays = sum(int(st3[k]) - int(st2[k]) for k in ("total_rays_primary", "total_rays_shadow", "total_rays_secondary"))
-    if world > 1:
-        t = torch.tensor([e2e_ms, float(e2e_rays)], device=f"cuda:{local}", dtype=torch.float64)
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        e2e_ms, e2e_rays = float(tmax[0]), float(t[1])
-    e2e_value = e2e_rays / (e2e_ms * 1e-3) / 1e6
+        pt.set_profiling(0)
+        for _ in range(args.warmup):
+            step()
+        barrier()
+        st0 = pt.stats()
+        pt.set_profiling(1)
+        clocks = ClockSampler(local)
+        if rank == 0:
+            clocks.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        barrier()
+        ms_total = e0.elapsed_time(e1)
+        clk = clocks.stop() if rank == 0 else None
+        st1 = pt.stats()
+        timings = pt.launch_timings()
+        rays = sum(int(st1[k]) - int(st0[k]) for k in RAYS)
+        launches = int(st1["kernel_launches"]) - int(st0["kernel_launches"])
+        ms_total, rays, launches = reduce_max_sum([ms_total, float(rays), float(launches)])
+        res = {"value": rays / (ms_total * 1e-3) / 1e6, "ms_per_step": ms_total / args.steps, "rays_per_frame": rays / args.steps / world,
+               "gpu_launches": int(launches), "clocks": clk}
 
-    # ---- roofline of the dominant kernel: event durations from the timed region, algorithmic bytes from counted replays
-    per = {}
-    for r in timings:
-        nm = r["name"].decode()
-        d = per.setdefault(nm, {"ms": 0.0, "n": 0, "is_trace": int(r["is_trace"]), "units": 0})
-        d["ms"] += float(r["ms"])
-        d["n"] += 1
-        d["units"] += int(r["units"])
-    pt.set_profiling(2)
-    n_count = 2
-    for _ in range(n_count):
-        step(f)
-        f += 1
-    torch.cuda.synchronize()
-    counted = {}
-    for r in pt.launch_timings():
-        nm = r["name"].decode()
-        if int(r["is_trace"]):
-            d = counted.setdefault(nm, {"bytes": 0, "live": 0, "nodes": 0, "tris": 0, "insts": 0, "n": 0})
-            d["bytes"] += int(r["alg_bytes"]); d["live"] += int(r["live"]); d["nodes"] += int(r["nodes"])
-            d["tris"] += int(r["tris"]); d["insts"] += int(r["insts"]); d["n"] += 1
-    pt.set_profiling(0)
-    peak, peak_src = measured_peaks()
-    roof = None
-    breakdown = {k: {"ms_per_launch": v["ms"] / v["n"], "launches": v["n"], "share": v["ms"] / max(sum(x["ms"] for x in per.values()), 1e-9)}
-                 for k, v in per.items()}
-    trace_names = [k for k, v in per.items() if v["is_trace"] and k in counted]
-    if trace_names:
-        top = max(trace_names, key=lambda k: per[k]["ms"])
-        ms_launch = per[top]["ms"] / per[top]["n"]
-        c = counted[top]
-        bytes_launch = c["bytes"] / c["n"]
-        achieved = bytes_launch / (ms_launch * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "alg_bytes_per_launch": bytes_launch, "ms_per_launch": ms_launch,
-                "rays_per_launch": c["live"] / c["n"], "nodes_per_ray": c["nodes"] / max(c["live"], 1), "tris_per_ray": c["tris"] / max(c["live"], 1),
-                "instances_per_ray": c["insts"] / max(c["live"], 1),
-                "grays_per_s": c["live"] / c["n"] / (ms_launch * 1e-3) / 1e9,
-                "note": "L2-resident BVH: a fraction above the HBM line is legal (SURVEY §8d); traffic from profiles/ ncu capture"}
-        tr = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tr):
-            try:
-                roof["traffic"] = json.load(open(tr)).get(top)
-            except Exception:
-                pass
+        # ---- end to end through the C ABI with host buffers (rank-local; max over ranks)
+        if with_e2e:
+            out_host = torch.empty((rows[1] - rows[0], W, 4), dtype=torch.float16, pin_memory=True)
+            out_np = out_host.numpy()
+            h2d = 2 * 240 + 2 * flat["transforms"].nbytes + flat["instances"].nbytes + flat["blas_of_instance"].nbytes + flat["emissive_idx"].nbytes
+            pt.set_profiling(0)
+
+            def e2e_step():
+                pt.set_transforms(flat["transforms"], flat["prev_transforms"])  # TransformBufferSystem: cur + prev, host → device
+                pt.set_instances(flat["instances"], flat["blas_of_instance"], flat["emissive_idx"])
+                step()
+                if rank == 0 or rad is None:
+                    pt.read_output("f16", out_np)  # device → host: the RGBA16F image the engine would present
+
+            e2e_steps = max(3, min(args.steps, 10))
+            for _ in range(2):
+                e2e_step()
+            barrier()
+            st2 = pt.stats()
+            e0.record()
+            for _ in range(e2e_steps):
+                e2e_step()
+            e1.record()
+            barrier()
+            e2e_ms = e0.elapsed_time(e1)
+            st3 = pt.stats()
+            e2e_rays = sum(int(st3[k]) - int(st2[k]) for k in RAYS)
+            e2e_ms, e2e_rays = reduce_max_sum([e2e_ms, float(e2e_rays)])
+            res["e2e"] = {"value": e2e_rays / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms / e2e_steps,
+                          "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(out_np.nbytes)}
+
+        # ---- roofline of the dominant traversal launch: event durations from the timed region, algorithmic bytes
+        # from counted replays of the following frames (profiling level 2)
+        per = {}
+        for r in timings:
+            d = per.setdefault(r["name"].decode(), {"ms": 0.0, "n": 0, "is_trace": int(r["is_trace"])})
+            d["ms"] += float(r["ms"])
+            d["n"] += 1
+        pt.set_profiling(2)
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        counted = {}
+        for r in pt.launch_timings():
+            if int(r["is_trace"]):
+                d = counted.setdefault(r["name"].decode(), {"bytes": 0, "live": 0, "nodes": 0, "tris": 0, "insts": 0, "n": 0})
+                d["bytes"] += int(r["alg_bytes"]); d["live"] += int(r["live"]); d["nodes"] += int(r["nodes"])
+                d["tris"] += int(r["tris"]); d["insts"] += int(r["insts"]); d["n"] += 1
+        pt.set_profiling(0)
+        tot_ms = max(sum(x["ms"] for x in per.values()), 1e-9)
+        res["kernels"] = {k: {"ms_per_launch": round(v["ms"] / v["n"], 4), "share": round(v["ms"] / tot_ms, 4)} for k, v in per.items()}
+        res["roofline"] = None
+        trace_names = [k for k, v in per.items() if v["is_trace"] and k in counted]
+        if trace_names:
+            top = max(trace_names, key=lambda k: per[k]["ms"])
+            ms_launch = per[top]["ms"] / per[top]["n"]
+            c = counted[top]
+            bytes_launch = c["bytes"] / c["n"]
+            achieved = bytes_launch / (ms_launch * 1e-3) / 1e9
+            # all traversal launches of the frame together (same kernel, different queues)
+            all_bytes = sum(counted[k]["bytes"] / counted[k]["n"] for k in trace_names)
+            all_ms = sum(per[k]["ms"] / per[k]["n"] for k in trace_names)
+            all_live = sum(counted[k]["live"] / counted[k]["n"] for k in trace_names)
+            roof = {"bound": "hbm", "kernel": f"k_trace_pt ({top})", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "peak_source": peak_src, "alg_bytes_per_launch": bytes_launch, "ms_per_launch": ms_launch,
+                    "rays_per_launch": c["live"] / c["n"], "nodes_per_ray": c["nodes"] / max(c["live"], 1), "tris_per_ray": c["tris"] / max(c["live"], 1),
+                    "instances_per_ray": c["insts"] / max(c["live"], 1), "grays_per_s": c["live"] / c["n"] / (ms_launch * 1e-3) / 1e9,
+                    "all_traversal_launches": {"achieved": all_bytes / (all_ms * 1e-3) / 1e9, "ms_per_frame": all_ms,
+                                               "grays_per_s": all_live / (all_ms * 1e-3) / 1e9},
+                    "note": "algorithmic bytes = 32+16|4 per ray + 80/node + 48/triangle record + 64/instance (SURVEY §8d); the BVH is L1/L2 "
+                            "resident, the kernel is instruction-issue bound (profiles/), so the HBM fraction is context, not the limiter"}
+            tr = os.path.join(ROOT, "profiles", "traffic.json")
+            if os.path.exists(tr):
+                try:
+                    roof["traffic"] = json.load(open(tr)).get(top)
+                except Exception:
+                    pass
+            res["roofline"] = roof
+        return res
+
+    main_res = measure(args.mode, with_e2e=True)
+    other = "reference" if args.mode == "northstar" else "northstar"
+    other_res = None
+    if not args.single_mode:
+        pt.reset_history()
+        other_res = measure(other, with_e2e=False)
 
     # ---- CPU baseline (rank 0, N = 1): the oracle on a bounded crop of the same frames
     cpu = None
@@ -360,15 +376,21 @@ def run_gpu_arm(args, snk):
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "metric": METRIC, "value": main_res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": main_res["ms_per_step"], "higher_is_better": True,
             "scaling": "weak" if (world == 1 or args.shard == "samples") else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc, "mode": args.mode, "resolution": [W, H], "rays_per_frame": rays / args.steps / world,
+            "config": {"workload": desc, "mode": args.mode, "resolution": [W, H], "rays_per_frame": main_res["rays_per_frame"],
+                       "estimator": ("1 spp, 4 bounces (GGX/Lambert sampling, MIS NEE, RR from bounce 2) + ReSTIR DI (32+32 candidates, temporal 1, spatial 3)"
+                                     if args.mode == "northstar" else "the reference's own frame: ReSTIR DI pass 1 + 2 and the 8x(1+2) BounceDiffuse tree (<= 65 rays/pixel)"),
                        "shard": args.shard if world > 1 else "none",
-                       "l2": "ray/hit queues (1.6 GB per frame) and per-pixel planes exceed the 126 MB L2 between iterations; the BVH itself is L2-resident by size"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / e2e_steps, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu, "kernels": breakdown,
+                       "l2": "per-pixel planes, reservoirs and ray queues (0.4-1.8 GB per frame) exceed the 126 MB L2 between iterations; the BVH itself is cache resident by size"},
+            "e2e": main_res.get("e2e"), "gpu_launches": main_res["gpu_launches"], "clocks": main_res["clocks"], "roofline": main_res["roofline"],
+            "cpu_baseline": cpu, "kernels": main_res["kernels"],
         }
+        if other_res is not None:
+            line["other_mode"] = {"mode": other, "value": other_res["value"], "unit": UNIT, "ms_per_step": other_res["ms_per_step"],
+                                  "rays_per_frame": other_res["rays_per_frame"], "roofline": other_res["roofline"], "kernels": other_res["kernels"],
+                                  "clocks": other_res["clocks"]}
         print(json.dumps(line))
     pt.close()
     if world > 1:
@@ -381,7 +403,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default="reference", choices=["reference", "northstar"])
+    ap.add_argument("--mode", default="northstar", choices=["reference", "northstar"],
+                    help="northstar = BASELINE.json's metric (1 spp, 4 bounces + ReSTIR DI); reference = the reference's own frame")
+    ap.add_argument("--single-mode", action="store_true", help="do not also measure the other estimator mode")
     ap.add_argument("--scene", default="c2")
     ap.add_argument("--width", type=int, default=1920)
     ap.add_argument("--height", type=int, default=1080)
