@@ -26,6 +26,7 @@ struct BuildScratch {
   uint32_t* flags = nullptr;                             // arrival counters (n-1)
   uint32_t* queue = nullptr;                             // binary node handled by wide node w
   uint32_t* counters = nullptr;                          // 16 words, see bvh_build.cu
+  uint32_t* digit_total = nullptr;                       // 256 words: per-digit totals / bases of the current sort pass
   uint32_t hist_blocks = 0;
 };
 
