@@ -235,6 +235,7 @@ void snkpt_destroy(SnkPt* ctx) {
   for (DevBuf* b : bufs) b->release();
   for (auto& b : ctx->wave) b.release();
   for (auto& b : ctx->px) b.release();
+  for (auto& r : ctx->blas_refit) refit_free(r);
   scratch_free(ctx->scratch_blas);
   scratch_free(ctx->scratch_tlas);
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -423,15 +424,37 @@ int snkpt_rebuild_blas(SnkPt* ctx, uint32_t blas_id, void* stream) {
   if (last) { ctx->n_blas_nodes = old.node_root; ctx->n_blas_tris = old.tri_base; }
   int rc = build_blas(ctx, blas_id, true, st);
   if (rc) return rc;
+  if (blas_id < ctx->blas_refit.size()) refit_free(ctx->blas_refit[blas_id]);  // topology changed
   ctx->stats.blas_nodes = ctx->n_blas_nodes; ctx->stats.blas_tris = ctx->n_blas_tris;
   ctx->tlas_built = false;
   return upload_blas_table(ctx, st);
 }
 
 int snkpt_refit_blas(SnkPt* ctx, uint32_t blas_id, void* stream) {
-  // topology-preserving refit is scheduled with the C5 row; until then a refit request is served by a full rebuild,
-  // which is always correct (the reference itself never updates a BLAS, TLAS.cpp:63)
-  return snkpt_rebuild_blas(ctx, blas_id, stream);
+  if (!ctx) return SNKPT_E_INVALID;
+  REQUIRE(blas_id < ctx->blas.size(), SNKPT_E_INVALID, "snkpt_refit_blas: bad id");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  SnkBlasInfo& info = ctx->blas[blas_id];
+  if (info.tri_count == 0) return SNKPT_OK;
+  if (ctx->blas_refit.size() < ctx->blas.size()) ctx->blas_refit.resize(ctx->blas.size());
+  RefitState& r = ctx->blas_refit[blas_id];
+  const BlasSrc src = ctx->blas_src[blas_id];
+  cudaEventRecord(ctx->ev[6], st);
+  const int n = launch_refit(r, ctx->blas_nodes.as<SnkNode8>(), info.node_root, info.node_count, ctx->blas_tris.as<SnkTri>(), info.tri_base,
+                             info.tri_count, ctx->positions.as<float>(), ctx->indices.as<uint32_t>(), src.index_offset, src.vertex_offset, st);
+  REQUIRE(n >= 0, SNKPT_E_NOMEM, "snkpt_refit_blas: out of device memory");
+  ctx->stats.kernel_launches += n;
+  cudaEventRecord(ctx->ev[7], st);
+  float4 box[2];
+  CK(cudaMemcpyAsync(box, r.node_box, sizeof(box), cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  cudaEventElapsedTime(&ctx->stats.ms_build_last, ctx->ev[6], ctx->ev[7]);
+  info.bounds_lo[0] = box[0].x; info.bounds_lo[1] = box[0].y; info.bounds_lo[2] = box[0].z;
+  info.bounds_hi[0] = box[1].x; info.bounds_hi[1] = box[1].y; info.bounds_hi[2] = box[1].z;
+  ctx->tlas_built = false;  // instance boxes derive from the BLAS bounds
+  return upload_blas_table(ctx, st);
 }
 
 // ---- scene buffers -----------------------------------------------------------------------------------

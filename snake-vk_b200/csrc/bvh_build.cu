@@ -398,6 +398,22 @@ __device__ __forceinline__ int quant_exp(float extent) {
   return be < 1 ? 1 : (be > 254 ? 254 : be);
 }
 
+// conservative 8-bit quantisation of one child box against the node grid (origin nlo, biased exponents be):
+// floor / ceil, then nudged until the planes as the traversal dequantises them really enclose the child
+__device__ __forceinline__ void quantise_child(const float4 nlo, const int* be, const float4 clo, const float4 chi, uint8_t* ql, uint8_t* qh) {
+  const float base3[3] = {nlo.x, nlo.y, nlo.z};
+  const float lo3[3] = {clo.x, clo.y, clo.z}, hi3[3] = {chi.x, chi.y, chi.z};
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const float scale = __uint_as_float((uint32_t)be[k] << 23), inv = __uint_as_float((uint32_t)(254 - be[k]) << 23);
+    float fl = floorf((lo3[k] - base3[k]) * inv), fh = ceilf((hi3[k] - base3[k]) * inv);
+    fl = fminf(fmaxf(fl, 0.f), 255.f); fh = fminf(fmaxf(fh, 0.f), 255.f);
+    if (fl > 0.f && base3[k] + fl * scale > lo3[k]) fl -= 1.f;
+    if (fh < 255.f && base3[k] + fh * scale < hi3[k]) fh += 1.f;
+    ql[k] = (uint8_t)fl; qh[k] = (uint8_t)fh;
+  }
+}
+
 __device__ void process_wide_node(const CollapseArgs& a, uint32_t w, int b) {
   // ---- choose up to 8 children by repeatedly opening the largest one
   int ch[8];
@@ -480,8 +496,6 @@ __device__ void process_wide_node(const CollapseArgs& a, uint32_t w, int b) {
   SnkNode8 nd;
   nd.px = nlo.x; nd.py = nlo.y; nd.pz = nlo.z;
   int be[3] = {quant_exp(nhi.x - nlo.x), quant_exp(nhi.y - nlo.y), quant_exp(nhi.z - nlo.z)};
-  float inv[3];
-  for (int k = 0; k < 3; ++k) inv[k] = __uint_as_float((uint32_t)(254 - be[k]) << 23);  // 2^-(be-127)
   nd.imask = 0;
   nd.child_base = a.node_offset + child_base;
   nd.tri_base = a.leaf_offset + rec_base;
@@ -493,20 +507,8 @@ __device__ void process_wide_node(const CollapseArgs& a, uint32_t w, int b) {
       nd.qlox[s] = nd.qloy[s] = nd.qloz[s] = 255; nd.qhix[s] = nd.qhiy[s] = nd.qhiz[s] = 0;  // inverted: never hit
       continue;
     }
-    const float l3[3] = {lo[i].x - nlo.x, lo[i].y - nlo.y, lo[i].z - nlo.z};
-    const float h3[3] = {hi[i].x - nlo.x, hi[i].y - nlo.y, hi[i].z - nlo.z};
     uint8_t ql[3], qh[3];
-    for (int k = 0; k < 3; ++k) {
-      const float scale = __uint_as_float((uint32_t)be[k] << 23);
-      float fl = floorf(l3[k] * inv[k]), fh = ceilf(h3[k] * inv[k]);
-      fl = fminf(fmaxf(fl, 0.f), 255.f); fh = fminf(fmaxf(fh, 0.f), 255.f);
-      // make sure the dequantised planes (evaluated as the traversal does) really enclose the child
-      const float base = k == 0 ? nlo.x : (k == 1 ? nlo.y : nlo.z);
-      const float cl = k == 0 ? lo[i].x : (k == 1 ? lo[i].y : lo[i].z), chh = k == 0 ? hi[i].x : (k == 1 ? hi[i].y : hi[i].z);
-      if (fl > 0.f && base + fl * scale > cl) fl -= 1.f;
-      if (fh < 255.f && base + fh * scale < chh) fh += 1.f;
-      ql[k] = (uint8_t)fl; qh[k] = (uint8_t)fh;
-    }
+    quantise_child(nlo, be, lo[i], hi[i], ql, qh);
     nd.qlox[s] = ql[0]; nd.qloy[s] = ql[1]; nd.qloz[s] = ql[2];
     nd.qhix[s] = qh[0]; nd.qhiy[s] = qh[1]; nd.qhiz[s] = qh[2];
     if (cnt[i] > LEAF_MAX) {
@@ -557,6 +559,93 @@ __global__ void __launch_bounds__(128) k_collapse(CollapseArgs a) {
   }
 }
 
+// ---- topology-preserving refit of a built BVH8 (animated vertices) -------------------------------------------
+// (no reference counterpart: the reference never updates a BLAS, TLAS.cpp:63 — BASELINE config "build + refit sweep")
+// k_refit_parents  once per BLAS: parent index of every wide node
+// k_refit_tris     rewrites the 48-B triangle records from the current vertex positions (record keeps its primitive id)
+// k_refit_nodes    bottom-up: a thread starts at every node without inner children, recomputes the child boxes
+//                  (leaf slots from their records, inner slots from the boxes their children left in node_box),
+//                  re-quantises the node in place and climbs to the parent when it is the last child to arrive
+__global__ void k_refit_parents(const SnkNode8* __restrict__ nodes, uint32_t node_root, uint32_t node_count, uint32_t* __restrict__ parent) {
+  const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= node_count) return;
+  const SnkNode8& nd = nodes[node_root + w];
+  if (w == 0) parent[0] = EMPTY;
+  const uint32_t n_inner = __popc((uint32_t)nd.imask);
+  for (uint32_t k = 0; k < n_inner; ++k) parent[nd.child_base - node_root + k] = w;
+}
+
+__global__ void k_refit_tris(SnkTri* __restrict__ tris, uint32_t tri_base, uint32_t tri_count, const float* __restrict__ positions,
+                             const uint32_t* __restrict__ indices, uint32_t index_offset, uint32_t vertex_offset) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= tri_count) return;
+  float4* t = reinterpret_cast<float4*>(tris + tri_base + i);
+  const uint32_t prim = __float_as_uint(t[0].w);
+  const uint32_t* ip = indices + index_offset + 3ull * prim;
+  const uint32_t ia = ip[0] + vertex_offset, ib = ip[1] + vertex_offset, ic = ip[2] + vertex_offset;
+  t[0] = make_float4(positions[3ull * ia], positions[3ull * ia + 1], positions[3ull * ia + 2], __uint_as_float(prim));
+  t[1] = make_float4(positions[3ull * ib], positions[3ull * ib + 1], positions[3ull * ib + 2], 0.f);
+  t[2] = make_float4(positions[3ull * ic], positions[3ull * ic + 1], positions[3ull * ic + 2], 0.f);
+}
+
+__global__ void k_refit_nodes(SnkNode8* __restrict__ nodes, uint32_t node_root, uint32_t node_count, const SnkTri* __restrict__ tris,
+                              const uint32_t* __restrict__ parent, uint32_t* __restrict__ arrive, float4* __restrict__ node_box) {
+  uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= node_count) return;
+  if (nodes[node_root + w].imask != 0) return;  // only nodes without inner children start a climb
+  while (true) {
+    SnkNode8 nd = nodes[node_root + w];
+    float4 lo[8], hi[8];
+    float4 nlo = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, 0), nhi = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, 0);
+    uint32_t inner_rank = 0;
+    for (int s = 0; s < 8; ++s) {
+      const uint32_t meta = nd.meta[s];
+      if (meta == 0) continue;
+      if ((meta & 0x18u) == 0x18u) {
+        const uint32_t c = nd.child_base - node_root + inner_rank++;
+        lo[s] = __ldcg(&node_box[2ull * c]); hi[s] = __ldcg(&node_box[2ull * c + 1]);
+      } else {
+        const uint32_t first = nd.tri_base + (meta & 31u), cnt = __popc(meta >> 5);
+        float4 l = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, 0), h = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, 0);
+        for (uint32_t k = 0; k < cnt; ++k) {
+          const float4* t = reinterpret_cast<const float4*>(tris + first + k);
+          for (int v = 0; v < 3; ++v) {
+            const float4 p = t[v];
+            l = make_float4(fminf(l.x, p.x), fminf(l.y, p.y), fminf(l.z, p.z), 0);
+            h = make_float4(fmaxf(h.x, p.x), fmaxf(h.y, p.y), fmaxf(h.z, p.z), 0);
+          }
+        }
+        lo[s] = make_float4(pad_dn(l.x), pad_dn(l.y), pad_dn(l.z), 0);
+        hi[s] = make_float4(pad_up(h.x), pad_up(h.y), pad_up(h.z), 0);
+      }
+      nlo = make_float4(fminf(nlo.x, lo[s].x), fminf(nlo.y, lo[s].y), fminf(nlo.z, lo[s].z), 0);
+      nhi = make_float4(fmaxf(nhi.x, hi[s].x), fmaxf(nhi.y, hi[s].y), fmaxf(nhi.z, hi[s].z), 0);
+    }
+    nd.px = nlo.x; nd.py = nlo.y; nd.pz = nlo.z;
+    const int be[3] = {quant_exp(nhi.x - nlo.x), quant_exp(nhi.y - nlo.y), quant_exp(nhi.z - nlo.z)};
+    nd.ex = (uint8_t)be[0]; nd.ey = (uint8_t)be[1]; nd.ez = (uint8_t)be[2];
+    for (int s = 0; s < 8; ++s) {
+      if (nd.meta[s] == 0) continue;
+      uint8_t ql[3], qh[3];
+      quantise_child(nlo, be, lo[s], hi[s], ql, qh);
+      nd.qlox[s] = ql[0]; nd.qloy[s] = ql[1]; nd.qloz[s] = ql[2];
+      nd.qhix[s] = qh[0]; nd.qhiy[s] = qh[1]; nd.qhiz[s] = qh[2];
+    }
+    const uint4* src = reinterpret_cast<const uint4*>(&nd);
+    uint4* dst = reinterpret_cast<uint4*>(nodes + node_root + w);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) dst[k] = src[k];
+    node_box[2ull * w] = nlo; node_box[2ull * w + 1] = nhi;
+    const uint32_t par = parent[w];
+    if (par == EMPTY) return;
+    __threadfence();
+    const uint32_t need = __popc((uint32_t)nodes[node_root + par].imask);
+    if (atomicAdd(&arrive[par], 1u) + 1u < need) return;  // not the last child: the last one continues
+    __threadfence();
+    w = par;
+  }
+}
+
 template <class T>
 cudaError_t alloc(T*& p, size_t count) {
   return cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
@@ -590,6 +679,25 @@ cudaError_t scratch_reserve(BuildScratch& s, uint32_t n) {
   s.capacity = (uint32_t)cap;
   return cudaSuccess;
 }
+
+int launch_refit(RefitState& r, SnkNode8* nodes, uint32_t node_root, uint32_t node_count, SnkTri* tris, uint32_t tri_base, uint32_t tri_count,
+                 const float* positions, const uint32_t* indices, uint32_t index_offset, uint32_t vertex_offset, cudaStream_t st) {
+  int launches = 0;
+  if (r.node_count != node_count || !r.parent) {
+    cudaFree(r.parent); cudaFree(r.arrive); cudaFree(r.node_box);
+    r = RefitState();
+    if (alloc(r.parent, node_count) != cudaSuccess || alloc(r.arrive, node_count) != cudaSuccess || alloc(r.node_box, 2ull * node_count) != cudaSuccess)
+      return -1;
+    r.node_count = node_count;
+    k_refit_parents<<<(node_count + 255) / 256, 256, 0, st>>>(nodes, node_root, node_count, r.parent);
+    ++launches;
+  }
+  cudaMemsetAsync(r.arrive, 0, sizeof(uint32_t) * node_count, st);
+  if (tri_count) { k_refit_tris<<<(tri_count + 255) / 256, 256, 0, st>>>(tris, tri_base, tri_count, positions, indices, index_offset, vertex_offset); ++launches; }
+  k_refit_nodes<<<(node_count + 127) / 128, 128, 0, st>>>(nodes, node_root, node_count, tris, r.parent, r.arrive, r.node_box);
+  return launches + 1;
+}
+void refit_free(RefitState& r) { cudaFree(r.parent); cudaFree(r.arrive); cudaFree(r.node_box); r = RefitState(); }
 
 void launch_triangle_bounds(BuildScratch& s, const float* positions, const uint32_t* indices, uint32_t index_offset,
                             uint32_t vertex_offset, uint32_t n, cudaStream_t st) {

@@ -43,6 +43,19 @@ struct BuildOutput {
   uint32_t leaf_offset;    // absolute index of the first free leaf record
 };
 
+// side arrays of a topology-preserving refit, kept per BLAS after its first refit
+struct RefitState {
+  uint32_t node_count = 0;
+  uint32_t* parent = nullptr;   // parent wide node (relative index), EMPTY for the root
+  uint32_t* arrive = nullptr;   // arrival counters of the bottom-up pass
+  float4* node_box = nullptr;   // 2 x float4 per node: its float box (read by the parent)
+};
+// rewrites the triangle records from `positions` and refits / re-quantises every node bottom-up; node_box[0..1] then
+// holds the root box. Returns the number of kernels launched, -1 on allocation failure.
+int launch_refit(RefitState& r, SnkNode8* nodes, uint32_t node_root, uint32_t node_count, SnkTri* tris, uint32_t tri_base, uint32_t tri_count,
+                 const float* positions, const uint32_t* indices, uint32_t index_offset, uint32_t vertex_offset, cudaStream_t st);
+void refit_free(RefitState& r);
+
 // triangle AABBs of one submesh -> s.prim_lo / s.prim_hi (+ centroid bounds in s.counters)
 void launch_triangle_bounds(BuildScratch& s, const float* positions, const uint32_t* indices, uint32_t index_offset,
                             uint32_t vertex_offset, uint32_t n, cudaStream_t st);

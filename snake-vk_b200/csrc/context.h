@@ -105,6 +105,7 @@ struct SnkPt {
   uint32_t n_blas_nodes = 0, n_blas_tris = 0;
   std::vector<SnkBlasInfo> blas;
   std::vector<snk::BlasSrc> blas_src;
+  std::vector<snk::RefitState> blas_refit;  // side arrays of refitted BLASes (empty until the first refit)
   snk::BuildScratch scratch_blas, scratch_tlas;
 
   // scene mirrors (host + device)
