@@ -569,7 +569,7 @@ int snkpt_build_tlas(SnkPt* ctx, void* stream) {
   CK(cudaMemcpyAsync(ctx->valid_slots.p, valid.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, st));
   BuildScratch& s = ctx->scratch_tlas;
   launch_instance_bounds(s, ctx->transforms.as<float>(), ctx->instances.as<SnkInstanceData>(), ctx->blas_of_instance.as<uint32_t>(),
-                         ctx->d_blas.as<SnkBlasInfo>(), ctx->valid_slots.as<uint32_t>(), n, st);
+                         ctx->d_blas.as<SnkBlasInfo>(), ctx->blas_nodes.as<SnkNode8>(), ctx->valid_slots.as<uint32_t>(), n, st);
   BuildOutput out;
   out.nodes = ctx->tlas_nodes.as<SnkNode8>(); out.node_offset = 0; out.node_capacity = ctx->max_instances;
   out.tris = nullptr; out.leaf_ids = ctx->tlas_leaf_ids.as<uint32_t>(); out.leaf_remap = ctx->valid_slots.as<uint32_t>(); out.leaf_offset = 0;

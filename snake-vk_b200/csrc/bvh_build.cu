@@ -98,10 +98,31 @@ __global__ void k_triangle_bounds(const float* __restrict__ positions, const uin
   reduce_centroid_bounds(cx, cy, cz, valid, counters);
 }
 
+// dequantised box of child slot s of a wide node (exactly the planes the traversal tests)
+__device__ __forceinline__ void child_box(const SnkNode8& nd, int s, float* lo, float* hi) {
+  const float sx = __uint_as_float((uint32_t)nd.ex << 23), sy = __uint_as_float((uint32_t)nd.ey << 23), sz = __uint_as_float((uint32_t)nd.ez << 23);
+  lo[0] = nd.px + (float)nd.qlox[s] * sx; lo[1] = nd.py + (float)nd.qloy[s] * sy; lo[2] = nd.pz + (float)nd.qloz[s] * sz;
+  hi[0] = nd.px + (float)nd.qhix[s] * sx; hi[1] = nd.py + (float)nd.qhiy[s] * sy; hi[2] = nd.pz + (float)nd.qhiz[s] * sz;
+}
+__device__ __forceinline__ void grow_by_transformed_box(const float* __restrict__ M, const float* blo, const float* bhi, float* lo, float* hi) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    const float x = (c & 1) ? bhi[0] : blo[0], y = (c & 2) ? bhi[1] : blo[1], z = (c & 4) ? bhi[2] : blo[2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const float w = M[r] * x + M[4 + r] * y + M[8 + r] * z + M[12 + r];
+      lo[r] = fminf(lo[r], w); hi[r] = fmaxf(hi[r], w);
+    }
+  }
+}
+
+// World AABB of an instance = union of the transformed boxes of the BLAS's depth-2 children (up to 64 boxes)
+// rather than of its root box: the transformed root box of a rotated mesh is up to sqrt(3) too wide per axis,
+// which on C2 made every ray enter ~6 instances it could not hit.
 __global__ void k_instance_bounds(const float* __restrict__ transforms, const SnkInstanceData* __restrict__ inst,
                                   const uint32_t* __restrict__ blas_of_instance, const SnkBlasInfo* __restrict__ blas,
-                                  const uint32_t* __restrict__ valid_slots, uint32_t n, float4* __restrict__ prim_lo,
-                                  float4* __restrict__ prim_hi, uint32_t* counters) {
+                                  const SnkNode8* __restrict__ blas_nodes, const uint32_t* __restrict__ valid_slots, uint32_t n,
+                                  float4* __restrict__ prim_lo, float4* __restrict__ prim_hi, uint32_t* counters) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = i < n;
   float cx = 0, cy = 0, cz = 0;
@@ -110,14 +131,25 @@ __global__ void k_instance_bounds(const float* __restrict__ transforms, const Sn
     const SnkBlasInfo b = blas[blas_of_instance[slot]];
     const float* M = transforms + 16ull * inst[slot].transform_idx;
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const float x = (c & 1) ? b.bounds_hi[0] : b.bounds_lo[0], y = (c & 2) ? b.bounds_hi[1] : b.bounds_lo[1],
-                  z = (c & 4) ? b.bounds_hi[2] : b.bounds_lo[2];
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const float w = M[r] * x + M[4 + r] * y + M[8 + r] * z + M[12 + r];
-        lo[r] = fminf(lo[r], w); hi[r] = fmaxf(hi[r], w);
+    const SnkNode8& root = blas_nodes[b.node_root];
+    uint32_t inner_rank = 0;
+    for (int s = 0; s < 8; ++s) {
+      const uint32_t meta = root.meta[s];
+      if (meta == 0) continue;
+      float blo[3], bhi[3];
+      child_box(root, s, blo, bhi);
+      if ((meta & 0x18u) == 0x18u) {
+        const SnkNode8& ch = blas_nodes[root.child_base + inner_rank++];
+        for (int s2 = 0; s2 < 8; ++s2) {
+          if (ch.meta[s2] == 0) continue;
+          float clo[3], chi[3];
+          child_box(ch, s2, clo, chi);
+          // the grandchild lies inside the child box as well: intersect (both are conservative)
+          for (int k = 0; k < 3; ++k) { clo[k] = fmaxf(clo[k], blo[k]); chi[k] = fminf(chi[k], bhi[k]); }
+          grow_by_transformed_box(M, clo, chi, lo, hi);
+        }
+      } else {
+        grow_by_transformed_box(M, blo, bhi, lo, hi);
       }
     }
     // instance boxes are transformed in float32: widen by a relative 1e-5 so they stay conservative
@@ -706,10 +738,10 @@ void launch_triangle_bounds(BuildScratch& s, const float* positions, const uint3
 }
 
 void launch_instance_bounds(BuildScratch& s, const float* transforms_cm, const SnkInstanceData* inst,
-                            const uint32_t* blas_of_instance, const SnkBlasInfo* blas, const uint32_t* valid_slots, uint32_t n,
-                            cudaStream_t st) {
+                            const uint32_t* blas_of_instance, const SnkBlasInfo* blas, const SnkNode8* blas_nodes, const uint32_t* valid_slots,
+                            uint32_t n, cudaStream_t st) {
   k_init<<<1, 32, 0, st>>>(s.counters, s.queue);
-  if (n) k_instance_bounds<<<(n + 255) / 256, 256, 0, st>>>(transforms_cm, inst, blas_of_instance, blas, valid_slots, n, s.prim_lo, s.prim_hi, s.counters);
+  if (n) k_instance_bounds<<<(n + 255) / 256, 256, 0, st>>>(transforms_cm, inst, blas_of_instance, blas, blas_nodes, valid_slots, n, s.prim_lo, s.prim_hi, s.counters);
 }
 
 int launch_build(BuildScratch& s, uint32_t n, const BuildOutput& out, const float* positions, const uint32_t* indices,

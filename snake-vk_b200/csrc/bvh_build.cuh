@@ -61,8 +61,8 @@ void launch_triangle_bounds(BuildScratch& s, const float* positions, const uint3
                             uint32_t vertex_offset, uint32_t n, cudaStream_t st);
 // world AABBs of n instances (primitive i = slot valid_slots[i]) -> s.prim_lo / s.prim_hi
 void launch_instance_bounds(BuildScratch& s, const float* transforms_cm, const SnkInstanceData* inst,
-                            const uint32_t* blas_of_instance, const SnkBlasInfo* blas, const uint32_t* valid_slots, uint32_t n,
-                            cudaStream_t st);
+                            const uint32_t* blas_of_instance, const SnkBlasInfo* blas, const SnkNode8* blas_nodes, const uint32_t* valid_slots,
+                            uint32_t n, cudaStream_t st);
 // generic build over s.prim_lo/hi. Returns the number of kernels launched. After completion s.counters[0] holds
 // the number of wide nodes written, s.counters[1] the number of leaf records, s.counters[4] an overflow flag.
 int launch_build(BuildScratch& s, uint32_t n, const BuildOutput& out, const float* positions, const uint32_t* indices,

@@ -48,7 +48,10 @@ struct Tracer {
 };
 
 // persistent CTAs: RT_CTAS_PER_SM x 148 CTAs walk the 16x8 pixel tiles of the band
-constexpr int RT_CTAS_PER_SM = 4;
+#ifndef SNK_RT_CTAS
+#define SNK_RT_CTAS 8
+#endif
+constexpr int RT_CTAS_PER_SM = SNK_RT_CTAS;
 #define SNK_RT_PROLOGUE()                                                                                              \
   __shared__ uint2 sm_stack[SHORT_STACK * RT_THREADS];                                                                 \
   __shared__ TraceScene sS;                                                                                            \
