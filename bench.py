@@ -175,6 +175,11 @@ def run_reference_arm(args, snk):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def kname(rec) -> str:
+    """kernel name of a launch-timing record (fixed 32-byte field, NUL terminated)"""
+    return bytes(rec["name"]).split(b"\0", 1)[0].decode()
+
+
 class CudaArray:
     """__cuda_array_interface__ shim so torch can alias a library-owned device buffer (NCCL plumbing)"""
 
@@ -312,7 +317,7 @@ def run_gpu_arm(args, snk):
         # from counted replays of the following frames (profiling level 2)
         per = {}
         for r in timings:
-            d = per.setdefault(r["name"].decode(), {"ms": 0.0, "n": 0, "is_trace": int(r["is_trace"])})
+            d = per.setdefault(kname(r), {"ms": 0.0, "n": 0, "is_trace": int(r["is_trace"])})
             d["ms"] += float(r["ms"])
             d["n"] += 1
         pt.set_profiling(2)
@@ -322,7 +327,7 @@ def run_gpu_arm(args, snk):
         counted = {}
         for r in pt.launch_timings():
             if int(r["is_trace"]):
-                d = counted.setdefault(r["name"].decode(), {"bytes": 0, "live": 0, "nodes": 0, "tris": 0, "insts": 0, "n": 0})
+                d = counted.setdefault(kname(r), {"bytes": 0, "live": 0, "nodes": 0, "tris": 0, "insts": 0, "n": 0})
                 d["bytes"] += int(r["alg_bytes"]); d["live"] += int(r["live"]); d["nodes"] += int(r["nodes"])
                 d["tris"] += int(r["tris"]); d["insts"] += int(r["insts"]); d["n"] += 1
         pt.set_profiling(0)

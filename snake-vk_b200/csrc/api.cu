@@ -84,6 +84,7 @@ int prof_begin(SnkPt* ctx, const char* name, uint64_t units, bool is_trace, bool
   if (!ctx->profiling || ctx->prof_n >= PROF_MAX) return -1;
   ProfRec& r = ctx->prof[ctx->prof_n];
   if (!r.e0 && (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess)) return -1;
+  memset(r.name, 0, sizeof(r.name));
   snprintf(r.name, sizeof(r.name), "%s", name);
   r.units = units; r.is_trace = is_trace; r.any = any; r.counted = false;
   cudaEventRecord(r.e0, st);
