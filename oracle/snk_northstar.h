@@ -136,6 +136,8 @@ inline vec3 ns_indirect(Frame& F, Invocation& inv, uint32_t x, uint32_t y) {
   const uint32_t pixel = (uint32_t)px, frame = F.ubo.frame_idx;
   const NsLightCounts lc = ns_light_counts(sc);
   const uint32_t max_bounces = F.settings.max_bounces;
+  // with the reservoir passes switched off the path does its own next-event estimation at x0 (plain path tracer)
+  const uint32_t nee_from = (F.settings.flags & RT_NO_RESTIR) ? 0u : 1u;
   vec3 L = v3(0.0f);
   if (F.g.prim[px] == INVALID) return L;
   NsSurf s = ns_surface(sc, F.g.inst[px], F.g.prim[px], F.g.bary[2 * px], F.g.bary[2 * px + 1]);
@@ -150,8 +152,8 @@ inline vec3 ns_indirect(Frame& F, Invocation& inv, uint32_t x, uint32_t y) {
     if (dot(n, wo) < 0.0f) n = -n;
     const vec3 o = s.p + n * 0.01f;
     const uint32_t dim = 16u * b;
-    // ---- next-event estimation (x0's direct light comes from the ReSTIR passes)
-    if (b >= 1 && lc.n_types > 0) {
+    // ---- next-event estimation (x0's direct light comes from the ReSTIR passes unless they are off)
+    if (b >= nee_from && lc.n_types > 0) {
       uint32_t t = ns_pick(ns_rand(pixel, frame, dim + 3), lc.n_types);
       // map the t-th present type to 0 = directional, 1 = point, 2 = emissive
       uint32_t type = 0;
@@ -227,8 +229,8 @@ inline vec3 ns_indirect(Frame& F, Invocation& inv, uint32_t x, uint32_t y) {
     if (h.t < 0.0f) break;
     s = ns_surface(sc, h.inst, h.prim, h.u, h.v);
     if (s.flags & MAT_FLAG_EMISSIVE) {
-      // BSDF sampling found a light: counted from x1 on (x0's direct light is the ReSTIR term), MIS against NEE
-      if (b >= 1) {
+      // BSDF sampling found a light: counted from the first NEE vertex on (x0's direct light is the ReSTIR term), MIS against NEE
+      if (b >= nee_from) {
         const float p_nee = ns_nee_pdf_emissive(lc, s.ntri, s.area, h.t, s.n, wi);
         const float w = (pdf_b * pdf_b) / (pdf_b * pdf_b + p_nee * p_nee);
         L += (T * s.albedo) * w;
@@ -240,20 +242,8 @@ inline vec3 ns_indirect(Frame& F, Invocation& inv, uint32_t x, uint32_t y) {
   return L;
 }
 
-// north-star frame over rows [y0,y1): reference ReSTIR passes for the direct term, then one path per pixel
-inline void render_northstar(Frame& F, uint32_t y0, uint32_t y1, int threads) {
-  F.ivp = inv_view_proj(F.ubo);
-  const uint32_t saved = F.settings.flags;
-  F.settings.flags |= RT_NO_BOUNCE;
-  for (uint32_t pass = 1;; pass = 0) {
-    parallel_rows(y0, y1, threads, [&](uint32_t y) {
-      uint64_t nc = 0, na = 0;
-      for (uint32_t x = 0; x < F.g.w; ++x) { Invocation inv(F, x, y); inv.main(pass); nc += inv.n_closest; na += inv.n_any; }
-      F.rays_closest += nc; F.rays_any += na;
-    });
-    if (pass == 0) break;
-  }
-  F.settings.flags = saved;
+// path stage of rows [y0,y1): out = direct + indirect
+inline void render_northstar_paths(Frame& F, uint32_t y0, uint32_t y1, int threads) {
   parallel_rows(y0, y1, threads, [&](uint32_t y) {
     uint64_t nc = 0, na = 0;
     for (uint32_t x = 0; x < F.g.w; ++x) {
@@ -270,6 +260,25 @@ inline void render_northstar(Frame& F, uint32_t y0, uint32_t y1, int threads) {
     }
     F.rays_closest += nc; F.rays_any += na;
   });
+}
+
+}  // namespace snkor
+
+#include "snk_restir_ns.h"
+
+namespace snkor {
+
+// north-star frame over rows [y0,y1): ReSTIR DI stages (snk_restir_ns.h) for the direct term, then one path per pixel
+inline void render_northstar(Frame& F, uint32_t y0, uint32_t y1, int threads) {
+  F.ivp = inv_view_proj(F.ubo);
+  if (F.settings.flags & RT_NO_RESTIR) {
+    parallel_rows(y0, y1, threads, [&](uint32_t y) {
+      for (uint32_t x = 0; x < F.g.w; ++x) { float* d = &F.direct_rgba[4 * ((size_t)y * F.g.w + x)]; d[0] = d[1] = d[2] = 0.0f; d[3] = 1.0f; }
+    });
+  } else {
+    render_restir_ns(F, F.rs, !F.ubo.prev_frame_invalid, y0, y1, F.ns_halo, threads);
+  }
+  render_northstar_paths(F, y0, y1, threads);
 }
 
 }  // namespace snkor

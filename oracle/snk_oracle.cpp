@@ -83,6 +83,7 @@ ORACLE_API void snkor_frame_render(void* fp, uint32_t y0, uint32_t y1, int threa
   if (f.settings.mode == 1) render_northstar(f, y0, y1, threads);
   else render_reference(f, y0, y1, threads);
 }
+ORACLE_API void snkor_frame_set_halo(void* fp, uint32_t halo) { ((Frame*)fp)->ns_halo = halo; }
 ORACLE_API void snkor_frame_render_pass(void* fp, uint32_t pass, uint32_t y0, uint32_t y1, int threads) {
   Frame& f = *(Frame*)fp;
   if (y1 == 0) y1 = f.g.h;

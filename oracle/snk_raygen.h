@@ -125,8 +125,21 @@ inline vec3 calc_pointlight(const Pointlight& light, vec3 v, vec3 f0, vec3 world
 // ---- frame state -----------------------------------------------------------------------
 struct Payload { vec3 colour{0, 0, 0}, normal{0, 0, 0}; float distance = -1.0f, roughness = 0.0f; uint32_t mat_flags = 0; };
 
+// scratch planes of the north-star ReSTIR stages (snk_restir_ns.h)
+struct RsScratch {
+  std::vector<float> phat;  // 2 / px: p^ of the initial samples
+  std::vector<float> vis;   // 3 / px
+  std::vector<Ray> rays;    // 3 / px
+  std::vector<float> C;     // 9 / px: final unshadowed contributions (pl, em, dir)
+  void resize(size_t n) {
+    phat.assign(2 * n, 0.0f); vis.assign(3 * n, 1.0f); rays.assign(3 * n, Ray{{0, 0, 0}, 0.0f, {0, 1, 0}, -1.0f}); C.assign(9 * n, 0.0f);
+  }
+};
+
 struct Frame {
   const Scene* sc = nullptr;
+  RsScratch rs;
+  uint32_t ns_halo = 0;  // rows around the rendered band that also run the initial + temporal stages
   CommonUBO ubo{}, prev_ubo{};
   RtSettings settings{};
   GBuffer g;

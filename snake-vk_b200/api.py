@@ -311,7 +311,7 @@ class RT:
 
     def RecordRenderCmdBuf(self, ubo, prev_ubo, settings: "RT.RtSettings | None" = None, mode=MODE_REFERENCE, **extra):
         st = settings or RT.RtSettings()
-        s = default_settings(num_temporal=st.num_temporal_resamples, num_spatial=st.num_spatial_resamples, mode=mode, **extra)
+        s = default_settings(**{**dict(num_temporal=st.num_temporal_resamples, num_spatial=st.num_spatial_resamples, mode=mode), **extra})
         self.pt.set_frame(ubo, prev_ubo)
         self.pt.trace_primary()
         self.pt.render(s)

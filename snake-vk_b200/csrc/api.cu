@@ -477,6 +477,7 @@ int snkpt_set_lights(SnkPt* ctx, const void* light_data, size_t bytes) {
   CK(cudaSetDevice(ctx->device));
   CK(cudaMemcpyAsync(ctx->lights.p, light_data, bytes, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
+  ctx->num_pointlights = L->num_pointlights;
   return SNKPT_OK;
 }
 
@@ -599,6 +600,17 @@ int snkpt_set_frame(SnkPt* ctx, const SnkCommonUBO* cur, const SnkCommonUBO* pre
       pv[c * 4 + r] = s;
     }
   REQUIRE(invert4(pv, inv), SNKPT_E_INVALID, "snkpt_set_frame: proj*view is singular");
+  {
+    double pv2[16], inv2[16];
+    for (int c = 0; c < 4; ++c)
+      for (int r = 0; r < 4; ++r) {
+        double s = 0.0;
+        for (int k = 0; k < 4; ++k) s += (double)ctx->prev_ubo.proj[k * 4 + r] * (double)ctx->prev_ubo.view[c * 4 + k];
+        pv2[c * 4 + r] = s;
+      }
+    const bool ok = invert4(pv2, inv2);
+    for (int i = 0; i < 16; ++i) fc.prev_ivp[i] = ok ? (float)inv2[i] : (float)inv[i];
+  }
   for (int i = 0; i < 16; ++i) { fc.ivp[i] = (float)inv[i]; fc.proj_view[i] = cur->proj_view[i]; fc.prev_proj_view[i] = ctx->prev_ubo.proj_view[i]; }
   for (int i = 0; i < 3; ++i) fc.cam_pos[i] = cur->cam_pos[i];
   fc.time_elapsed = cur->time_elapsed; fc.delta_time = cur->delta_time;
@@ -650,6 +662,8 @@ int snkpt_render(SnkPt* ctx, const SnkRtSettings* settings, void* stream) {
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
   fill_frame_dims(ctx);
+  if (ctx->history_mode != settings->mode) ctx->history_valid = false;
+  ctx->history_mode = settings->mode;
   int rc = settings->mode == SNKPT_MODE_REFERENCE ? launch_reference_frame(ctx, *settings, st) : launch_northstar_frame(ctx, *settings, st);
   if (rc < 0) return rc;
   CK(cudaGetLastError());

@@ -53,6 +53,7 @@ constexpr int PROF_MAX = 2048;
 // per-frame constants handed to the kernels by value
 struct FrameConsts {
   float ivp[16];        // inverse(view) * inverse(proj) hoisted (Util.glsl:3), float64 rounded once
+  float prev_ivp[16];   // the same of the previous frame's UBO (north-star temporal reuse: previous world position)
   float proj_view[16];
   float prev_proj_view[16];
   float cam_pos[3];
@@ -112,7 +113,7 @@ struct SnkPt {
   std::vector<SnkInstanceData> h_instances;
   std::vector<uint32_t> h_blas_of_instance;
   std::vector<float> h_transforms, h_prev_transforms;
-  uint32_t num_instances = 0, num_emissive = 0;
+  uint32_t num_instances = 0, num_emissive = 0, num_pointlights = 0;
   snk::DevBuf materials, lights, transforms, prev_transforms, normal_mats, det3, instances, blas_of_instance, emissive_idx;
 
   // TLAS
@@ -124,6 +125,7 @@ struct SnkPt {
   snk::DevBuf px[32];
   snk::PixelPlanes planes{};
   bool history_valid = false;
+  uint32_t history_mode = 0;    // estimator that wrote the reservoir history (the two modes' reservoirs are not interchangeable)
   bool gbuffer_valid = false;
   bool render_pending = false;  // a frame was enqueued since the last stats read
   uint32_t accum_count = 0;

@@ -33,6 +33,8 @@ int launch_primary(const TraceScene& S, const SceneDev& D, const FrameConsts& fc
 int launch_restir_passes(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st);
 int launch_reference_frame(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st);
 int launch_northstar_frame(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st);
+// restir_ns.cu — north-star ReSTIR DI stages (initial / temporal / spatial + final evaluation / resolve) → planes.direct
+int launch_restir_ns(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st);
 int launch_accumulate(const PixelPlanes& P, uint32_t npix, uint32_t count, cudaStream_t st);
 
 }  // namespace snk

@@ -1,0 +1,133 @@
+// northstar.cuh — device helpers shared by the north-star stages (northstar.cu: path vertices; restir_ns.cu: ReSTIR DI).
+// CPU statement: oracle/snk_northstar.h (same expression order, -fmad=false).
+#pragma once
+#include "shading.cuh"
+
+namespace snk {
+
+__device__ __forceinline__ uint32_t pcg_hash(uint32_t v) {
+  const uint32_t state = v * 747796405u + 2891336453u;
+  const uint32_t word = ((state >> ((state >> 28u) + 4u)) ^ state) * 277803737u;
+  return (word >> 22u) ^ word;
+}
+__device__ __forceinline__ float ns_rand(uint32_t pixel, uint32_t frame, uint32_t dim) {
+  const uint32_t h = pcg_hash(pcg_hash(pcg_hash(pixel) + frame) + dim);
+  return (float)(h >> 8) * (1.0f / 16777216.0f);
+}
+
+struct NsSurf {
+  vec3 p, n, albedo;
+  float roughness, metallic;
+  uint32_t flags, ntri;
+  float area;
+};
+
+static __device__ __noinline__ NsSurf ns_surface(const SceneDev& D, uint32_t inst, uint32_t prim, float u, float v) {
+  NsSurf s;
+  const float b0 = (1.0f - u) - v;
+  const SnkInstanceData in = load_instance(D, inst);
+  uint32_t ia, ib, ic;
+  tri_indices(D, in, prim, ia, ib, ic);
+  const vec3 pa = ld3(D.positions, ia), pb = ld3(D.positions, ib), pc = ld3(D.positions, ic);
+  const vec3 p = (pa * b0 + pb * u) + pc * v;
+  const vec3 n = (ld3(D.normals, ia) * b0 + ld3(D.normals, ib) * u) + ld3(D.normals, ic) * v;
+  const float* M = D.transforms + 16ull * in.transform_idx;
+  s.p = mul_point(M, p);
+  s.n = normalize(mul_mat3r(D.normal_mats + 9ull * in.transform_idx, n));
+  const SnkMaterial* m = D.materials + in.material_idx;
+  const float4 alb = __ldg(reinterpret_cast<const float4*>(m->albedo));
+  s.albedo = v3(alb.x, alb.y, alb.z);
+  s.roughness = gmax(__ldg(&m->roughness), 0.05f);
+  s.metallic = __ldg(&m->metallic);
+  s.flags = __ldg(&m->flags);
+  s.ntri = in.num_mesh_indices / 3u;
+  const vec3 wa = mul_point(M, pa), wb = mul_point(M, pb), wc = mul_point(M, pc);
+  s.area = 0.5f * length(cross(wb - wa, wc - wa));
+  return s;
+}
+
+static __device__ __noinline__ vec3 ns_bsdf_cos(vec3 n, vec3 wo, vec3 wi, vec3 albedo, float roughness, float metallic) {
+  const vec3 f0 = mix(v3(0.04f), albedo, metallic);
+  const vec3 h = normalize(wo + wi);
+  const vec3 f = fresnel_schlick(gmax(dot(h, wo), 0.0f), f0);
+  const float ndf = distribution_ggx(h, n, roughness);
+  const float g = geometry_smith(wo, wi, n, roughness);
+  const vec3 num = (ndf * g) * f;
+  const float denom = 4.0f * gmax(dot(n, wo), 0.0f) * gmax(dot(n, wi), 0.0f) + 0.0001f;
+  const vec3 specular = num / denom;
+  vec3 kd = v3(1.0f) - f;
+  kd *= 1.0f - metallic;
+  const float n_dot_l = gmax(dot(n, wi), 0.0f);
+  return (kd * albedo / PI_GLSL + specular) * n_dot_l;
+}
+__device__ __forceinline__ float ns_spec_prob(float metallic) { return 0.25f + 0.5f * metallic; }
+static __device__ __noinline__ float ns_pdf(vec3 n, vec3 wo, vec3 wi, float roughness, float metallic) {
+  const float ps = ns_spec_prob(metallic);
+  const float n_dot_l = gmax(dot(n, wi), 0.0f);
+  const vec3 h = normalize(wo + wi);
+  const float n_dot_h = gmax(dot(n, h), 0.0f);
+  const float v_dot_h = gmax(dot(wo, h), 0.000001f);
+  const float d = distribution_ggx(h, n, roughness);
+  return (1.0f - ps) * (n_dot_l / PI_GLSL) + ps * ((d * n_dot_h) / (4.0f * v_dot_h));
+}
+__device__ __forceinline__ bool ns_sample(vec3 n, vec3 wo, float roughness, float metallic, float u0, float u1, float u2, vec3& wi) {
+  vec3 nt, nb;
+  create_coordinate_system(n, nt, nb);
+  const float phi = (2.0f * PI_GLSL) * u2;
+  const float cp = cos_c(phi), sp = sin_c(phi);
+  if (u0 < ns_spec_prob(metallic)) {
+    const float a = roughness * roughness;
+    const float a2 = a * a;
+    const float cos_t = sqrtf((1.0f - u1) / (1.0f + (a2 - 1.0f) * u1));
+    const float sin_t = sqrtf(gmax(1.0f - cos_t * cos_t, 0.0f));
+    const vec3 l = v3(sin_t * cp, cos_t, sin_t * sp);
+    const vec3 h = v3((l.x * nb.x + l.y * n.x) + l.z * nt.x, (l.x * nb.y + l.y * n.y) + l.z * nt.y, (l.x * nb.z + l.y * n.z) + l.z * nt.z);
+    wi = h * (2.0f * dot(wo, h)) - wo;
+  } else {
+    const float r = sqrtf(u1);
+    const vec3 l = v3(r * cp, sqrtf(gmax(1.0f - u1, 0.0f)), r * sp);
+    wi = v3((l.x * nb.x + l.y * n.x) + l.z * nt.x, (l.x * nb.y + l.y * n.y) + l.z * nt.y, (l.x * nb.z + l.y * n.z) + l.z * nt.z);
+  }
+  wi = normalize(wi);
+  return dot(n, wi) > 0.0f;
+}
+
+struct NsLightCounts { uint32_t has_dir, n_pl, n_em, n_types; };
+__device__ __forceinline__ NsLightCounts ns_light_counts(const SceneDev& D) {
+  NsLightCounts c;
+  const float4 col = __ldg(reinterpret_cast<const float4*>(D.lights->dir_light.colour));
+  c.has_dir = (col.x > 0.0f || col.y > 0.0f || col.z > 0.0f) ? 1u : 0u;
+  c.n_pl = D.lights->num_pointlights;
+  c.n_em = D.num_emissive;
+  c.n_types = c.has_dir + (c.n_pl ? 1u : 0u) + (c.n_em ? 1u : 0u);
+  return c;
+}
+__device__ __forceinline__ uint32_t ns_pick(float u, uint32_t n) { const uint32_t i = to_uint(u * (float)n); return i >= n ? n - 1 : i; }
+__device__ __forceinline__ float ns_nee_pdf_emissive(const NsLightCounts& lc, uint32_t ntri, float area, float dist, vec3 nl, vec3 wi) {
+  const float cos_l = fabsf(dot(nl, wi));
+  if (!(cos_l > 0.000001f) || !(area > 0.0f)) return 0.0f;
+  const float p_pick = (1.0f / (float)lc.n_types) * (1.0f / ((float)lc.n_em * (float)ntri));
+  return p_pick * ((dist * dist) / (cos_l * area));
+}
+
+__device__ __forceinline__ void put_ray(float4* q, size_t i, vec3 o, float tmin, vec3 d, float tmax) {
+  q[2 * i] = make_float4(o.x, o.y, o.z, tmin);
+  q[2 * i + 1] = make_float4(d.x, d.y, d.z, tmax);
+}
+__device__ __forceinline__ void put_dead(float4* q, size_t i) {
+  q[2 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  q[2 * i + 1] = make_float4(0.f, 1.f, 0.f, -1.0f);
+}
+
+__device__ __forceinline__ void flush_counts(unsigned long long n_shadow, unsigned long long n_closest, unsigned long long* counters) {
+  for (int o = 16; o > 0; o >>= 1) {
+    n_shadow += __shfl_xor_sync(0xFFFFFFFFu, n_shadow, o);
+    n_closest += __shfl_xor_sync(0xFFFFFFFFu, n_closest, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (n_shadow) atomicAdd(counters, n_shadow);
+    if (n_closest) atomicAdd(counters + 1, n_closest);
+  }
+}
+
+}  // namespace snk

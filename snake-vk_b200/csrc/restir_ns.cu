@@ -1,0 +1,434 @@
+// restir_ns.cu — north-star ReSTIR DI (BASELINE.json north_star item 4) as separate wavefront stages:
+//
+//   k_rs_initial   candidate generation (RIS over point lights / emissive triangles) -> reservoir (half 1) + shadow ray
+//   [trace any]    persistent wavefront traversal kernel (trace.cu), one launch per light type present
+//   k_rs_temporal  visibility of the initial sample, temporal reuse at the motion-vector-reprojected pixel -> half 1
+//   k_rs_spatial   spatial reuse with the bias-correcting MIS weight -> half 0 (next frame's history);
+//                  final contributions on the exact primary-hit surface + 3 shadow rays (point, emissive, directional)
+//   [trace any]
+//   k_rs_resolve   direct = sum of contribution x visibility -> planes.direct
+//
+// Data contract kept from the reference: the 48-B PixelReservoir (two independent reservoirs per pixel) staged as
+// three 16-B SoA planes per buffer half (RayGen.rgen:53-76, EditorLayer.cpp:299-302), RT::RtSettings and the shader
+// constants (Raytracing.h:13-16, RayGen.rgen:95-97, :435, :488, :491). The estimator itself is restated in
+// oracle/snk_restir_ns.h (which lists how it differs from the reference's biased passes); this file must match that
+// statement bit for bit: same expression order, -fmad=false, PCG-hash random numbers, no trigonometry.
+// No shadow ray is traced inside a shading kernel: every ray goes through the wavefront traversal kernel.
+#include "kernels.h"
+#include "northstar.cuh"
+
+namespace snk {
+
+namespace {
+
+constexpr uint32_t RS_DIM_INITIAL = 0x1000u, RS_DIM_TEMPORAL = 0x2000u, RS_DIM_SPATIAL = 0x3000u;
+__device__ __forceinline__ uint32_t rs_seed(uint32_t pixel, uint32_t frame) { return pcg_hash(pcg_hash(pixel) + frame); }
+__device__ __forceinline__ float rs_rand(uint32_t h0, uint32_t dim) { return (float)(pcg_hash(h0 + dim) >> 8) * (1.0f / 16777216.0f); }
+
+struct RsParams {
+  int32_t num_temporal, num_spatial;
+  uint32_t ris_iters, m_cap;
+  float radius, normal_threshold;
+  uint32_t history_ok;
+  uint32_t npix_frame;  // W * H: plane stride of the scratch queues
+};
+// scratch queues, indexed by full-frame pixel (plane k of pixel px at k * npix_frame + px)
+struct RsBuffers {
+  float4* rays;   // 3 planes x 2 float4
+  float* vis;     // 3 planes
+  float2* phat;   // p^ of the initial samples
+  float4* C;      // 3 planes: final unshadowed contributions
+};
+
+struct RsSurf {
+  vec3 n, wo, o, albedo;
+  float roughness, metallic;
+};
+struct RsEval { vec3 C, wi; float tmax; };
+__device__ __forceinline__ float rs_phat(const RsEval& e) { return e.tmax > 0.0f ? (e.C.x + e.C.y) + e.C.z : 0.0f; }
+
+__device__ __forceinline__ bool px_shaded(const PixelPlanes& P, size_t px) {
+  return P.prim[px] != INVALID_IDX && !(P.flags[px] & SNKPT_MAT_FLAG_EMISSIVE);
+}
+__device__ __forceinline__ vec3 px_normal(const ushort4* plane, size_t px) {
+  const ushort4 n = plane[px];
+  return v3(h2f(n.x), h2f(n.y), h2f(n.z));
+}
+// G-buffer surface of a shaded pixel (oracle: rs_gsurf)
+__device__ __forceinline__ void rs_gsurf(const FrameConsts& fc, const PixelPlanes& P, uint32_t x, uint32_t y, RsSurf& s, vec3& pos, vec3& n_raw) {
+  const size_t px = (size_t)y * fc.W + x;
+  n_raw = px_normal(P.normal, px);
+  const float u = ((float)x + 0.5f) / (float)fc.W, v = ((float)y + 0.5f) / (float)fc.H;
+  pos = world_pos_from_depth(fc.ivp, P.depth[px], u, v);
+  const char4 a = P.albedo[px];
+  const ushort4 r = P.rma[px];
+  s.albedo = v3(snorm8_2f(a.x), snorm8_2f(a.y), snorm8_2f(a.z));
+  s.roughness = gmax(h2f(r.x), 0.05f);
+  s.metallic = h2f(r.y);
+  const vec3 cam = v3(fc.cam_pos[0], fc.cam_pos[1], fc.cam_pos[2]);
+  s.wo = normalize(cam - pos);
+  s.n = n_raw;
+  if (dot(s.n, s.wo) < 0.0f) s.n = -s.n;
+  s.o = pos + s.n * 0.01f;
+}
+__device__ __forceinline__ RsSurf rs_xsurf(const NsSurf& h, vec3 cam) {
+  RsSurf s;
+  s.albedo = h.albedo; s.roughness = h.roughness; s.metallic = h.metallic;
+  s.wo = normalize(cam - h.p);
+  s.n = h.n;
+  if (dot(s.n, s.wo) < 0.0f) s.n = -s.n;
+  s.o = h.p + s.n * 0.01f;
+  return s;
+}
+static __device__ __noinline__ RsEval rs_eval_pl(const RsSurf& s, const PointLightRec& pl) {
+  RsEval e; e.C = v3(0.0f); e.wi = v3(0.0f, 1.0f, 0.0f); e.tmax = -1.0f;
+  const vec3 d = pl.pos - s.o;
+  const float dist = length(d);
+  if (!(dist > 0.002f)) return e;
+  const vec3 wi = d / dist;
+  if (!(dot(s.n, wi) > 0.0f)) return e;
+  const float atten = (pl.atten_constant + pl.atten_linear * dist) + pl.atten_exp * (dist * dist);
+  e.C = (ns_bsdf_cos(s.n, s.wo, wi, s.albedo, s.roughness, s.metallic) * pl.colour) / atten;
+  e.wi = wi; e.tmax = dist - 0.001f;
+  return e;
+}
+static __device__ __noinline__ RsEval rs_eval_em(const RsSurf& s, const NsSurf& q) {
+  RsEval e; e.C = v3(0.0f); e.wi = v3(0.0f, 1.0f, 0.0f); e.tmax = -1.0f;
+  const vec3 d = q.p - s.o;
+  const float dist = length(d);
+  if (!(dist > 0.01f)) return e;
+  const vec3 wi = d / dist;
+  const float cos_l = fabsf(dot(q.n, wi));
+  if (!(dot(s.n, wi) > 0.0f) || !(cos_l > 0.000001f)) return e;
+  e.C = ((ns_bsdf_cos(s.n, s.wo, wi, s.albedo, s.roughness, s.metallic) * q.albedo) * cos_l) / (dist * dist);
+  e.wi = wi; e.tmax = dist - 0.005f;
+  return e;
+}
+__device__ __forceinline__ bool rs_em_valid(const SceneDev& D, uint32_t obj, uint32_t tri) {
+  return obj < D.num_instances && tri < load_instance(D, obj).num_mesh_indices / 3u;
+}
+__device__ __forceinline__ void rs_empty(Reservoir& r) { init_reservoir(r); }
+
+__device__ __forceinline__ void pixel_of(const FrameConsts& fc, uint32_t i, uint32_t& x, uint32_t& y, size_t& px) {
+  x = i % fc.W; y = fc.row0 + i / fc.W;
+  px = (size_t)y * fc.W + x;
+}
+
+// ---- stage 1 ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_rs_initial(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, RsBuffers B, uint32_t npix,
+                                                    unsigned long long* counters) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long n_shadow = 0;
+  if (i < npix) {
+    uint32_t x, y; size_t px;
+    pixel_of(fc, i, x, y, px);
+    const size_t np = rp.npix_frame;
+    Reservoir r; rs_empty(r);
+    float p_sel_pl = 0.0f, p_sel_em = 0.0f;
+    bool ray_pl = false, ray_em = false;
+    const uint32_t n_pl = D.lights->num_pointlights, n_em = D.num_emissive;
+    if (px_shaded(P, px)) {
+      RsSurf s; vec3 pos, n_raw;
+      rs_gsurf(fc, P, x, y, s, pos, n_raw);
+      const uint32_t h0 = rs_seed((uint32_t)px, fc.frame_idx);
+      const uint32_t iters = rp.ris_iters;
+      if (n_pl > 0) {
+        const bool all = n_pl <= iters;
+        const uint32_t m = all ? n_pl : iters;
+        RsEval e_sel; e_sel.C = v3(0.0f); e_sel.wi = v3(0.0f, 1.0f, 0.0f); e_sel.tmax = -1.0f;
+        for (uint32_t c = 0; c < m; ++c) {
+          const uint32_t idx = all ? c : ns_pick(rs_rand(h0, RS_DIM_INITIAL + 2u * c), n_pl);
+          const RsEval e = rs_eval_pl(s, load_pointlight(D.lights, idx));
+          const float p_hat = rs_phat(e);
+          const float w = p_hat * (float)n_pl;
+          r.w_sum_pl += w;
+          if (w > 0.0f && rs_rand(h0, RS_DIM_INITIAL + 2u * c + 1u) * r.w_sum_pl < w) { r.pl_idx = idx; p_sel_pl = p_hat; e_sel = e; }
+        }
+        r.pl_m = m;
+        if (r.pl_idx != INVALID_IDX) {
+          r.w_pl = (r.w_sum_pl / (float)r.pl_m) / p_sel_pl;
+          put_ray(B.rays, px, s.o, 0.001f, e_sel.wi, e_sel.tmax);
+          ray_pl = true;
+          ++n_shadow;
+        }
+      }
+      if (n_em > 0) {
+        RsEval e_sel; e_sel.C = v3(0.0f); e_sel.wi = v3(0.0f, 1.0f, 0.0f); e_sel.tmax = -1.0f;
+        for (uint32_t c = 0; c < iters; ++c) {
+          const uint32_t d = RS_DIM_INITIAL + 0x800u + 5u * c;
+          const uint32_t obj = __ldg(D.emissive_idx + ns_pick(rs_rand(h0, d), n_em));
+          const uint32_t ntri = load_instance(D, obj).num_mesh_indices / 3u;
+          const uint32_t tri = ns_pick(rs_rand(h0, d + 1u), ntri);
+          float bu = rs_rand(h0, d + 2u), bv = rs_rand(h0, d + 3u);
+          if (bu + bv >= 1.0f) { bu = 1.0f - bu; bv = 1.0f - bv; }
+          const NsSurf q = ns_surface(D, obj, tri, bu, bv);
+          const RsEval e = rs_eval_em(s, q);
+          const float p_hat = rs_phat(e);
+          const float w = (p_hat * ((float)n_em * (float)ntri)) * q.area;
+          r.w_sum_em += w;
+          if (w > 0.0f && rs_rand(h0, d + 4u) * r.w_sum_em < w) { r.obj = obj; r.tri = tri; r.bx = bu; r.by = bv; p_sel_em = p_hat; e_sel = e; }
+        }
+        r.m_em = iters;
+        if (r.obj != INVALID_IDX) {
+          r.w_em = (r.w_sum_em / (float)r.m_em) / p_sel_em;
+          put_ray(B.rays, np + px, s.o, 0.001f, e_sel.wi, e_sel.tmax);
+          ray_em = true;
+          ++n_shadow;
+        }
+      }
+    }
+    if (n_pl > 0 && !ray_pl) put_dead(B.rays, px);
+    if (n_em > 0 && !ray_em) put_dead(B.rays, np + px);
+    B.phat[px] = make_float2(p_sel_pl, p_sel_em);
+    const ResPlanes half1{P.res[1][0], P.res[1][1], P.res[1][2]};
+    store_reservoir(half1, px, r);
+  }
+  flush_counts(n_shadow, 0ull, counters);
+}
+
+// ---- stage 2 ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_rs_temporal(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, RsBuffers B, uint32_t npix) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  uint32_t x, y; size_t px;
+  pixel_of(fc, i, x, y, px);
+  if (!px_shaded(P, px)) return;  // stage 1 wrote the empty reservoir
+  const size_t np = rp.npix_frame;
+  const ResPlanes half0{P.res[0][0], P.res[0][1], P.res[0][2]}, half1{P.res[1][0], P.res[1][1], P.res[1][2]};
+  RsSurf s; vec3 pos, n_raw;
+  rs_gsurf(fc, P, x, y, s, pos, n_raw);
+  Reservoir r = load_reservoir(half1, px);
+  const float2 ph0 = B.phat[px];
+  float p_pl = ph0.x, p_em = ph0.y;
+  const uint32_t n_pl = D.lights->num_pointlights;
+  if (n_pl > 0 && B.vis[px] == 0.0f) { r.w_sum_pl = 0.0f; r.w_pl = 0.0f; }
+  if (D.num_emissive > 0 && B.vis[np + px] == 0.0f) { r.w_sum_em = 0.0f; r.w_em = 0.0f; }
+  if (rp.history_ok && rp.num_temporal != 0) {
+    const ushort2 mv = P.motion[px];
+    const float hx = ((float)x + 0.5f) / (float)fc.W + h2f(mv.x), hy = ((float)y + 0.5f) / (float)fc.H + h2f(mv.y);
+    if ((hx > 0.0f && hy > 0.0f) && (hx < 1.0f && hy < 1.0f)) {
+      uint32_t qx = to_uint(hx * (float)fc.W), qy = to_uint(hy * (float)fc.H);
+      if (qx > fc.W - 1) qx = fc.W - 1;
+      if (qy > fc.H - 1) qy = fc.H - 1;
+      const size_t qp = (size_t)qy * fc.W + qx;
+      const vec3 pn = px_normal(P.prev_normal, qp);
+      const vec3 ppos = world_pos_from_depth(fc.prev_ivp, P.prev_depth[qp], ((float)qx + 0.5f) / (float)fc.W, ((float)qy + 0.5f) / (float)fc.H);
+      const vec3 cam = v3(fc.cam_pos[0], fc.cam_pos[1], fc.cam_pos[2]);
+      const vec3 dp = ppos - pos;
+      const float tol = 0.02f * length(cam - pos) + 0.02f;
+      if (dot(pn, n_raw) > rp.normal_threshold && length(dp) < tol) {
+        Reservoir h = load_reservoir(half0, qp);
+        const uint32_t h0 = rs_seed((uint32_t)px, fc.frame_idx);
+        if (h.pl_m > rp.m_cap * r.pl_m) h.pl_m = rp.m_cap * r.pl_m;
+        if (h.m_em > rp.m_cap * r.m_em) h.m_em = rp.m_cap * r.m_em;
+        if (h.pl_idx < n_pl) {
+          const float ph = rs_phat(rs_eval_pl(s, load_pointlight(D.lights, h.pl_idx)));
+          const float w = (ph * h.w_pl) * (float)h.pl_m;
+          r.w_sum_pl += w;
+          if (w > 0.0f && rs_rand(h0, RS_DIM_TEMPORAL) * r.w_sum_pl < w) { r.pl_idx = h.pl_idx; p_pl = ph; }
+        }
+        r.pl_m += h.pl_m;
+        if (rs_em_valid(D, h.obj, h.tri)) {
+          const NsSurf q = ns_surface(D, h.obj, h.tri, h.bx, h.by);
+          const float ph = rs_phat(rs_eval_em(s, q));
+          const float w = (ph * h.w_em) * (float)h.m_em;
+          r.w_sum_em += w;
+          if (w > 0.0f && rs_rand(h0, RS_DIM_TEMPORAL + 1u) * r.w_sum_em < w) { r.obj = h.obj; r.tri = h.tri; r.bx = h.bx; r.by = h.by; p_em = ph; }
+        }
+        r.m_em += h.m_em;
+      }
+    }
+  }
+  r.w_pl = (r.pl_idx != INVALID_IDX && p_pl > 0.0f && r.pl_m > 0) ? (r.w_sum_pl / (float)r.pl_m) / p_pl : 0.0f;
+  r.w_em = (r.obj != INVALID_IDX && p_em > 0.0f && r.m_em > 0) ? (r.w_sum_em / (float)r.m_em) / p_em : 0.0f;
+  store_reservoir(half1, px, r);
+}
+
+// ---- stage 3 ---------------------------------------------------------------------------------------------------------
+constexpr int RS_MAXN = 9;  // this pixel + up to 8 neighbours
+
+__global__ void __launch_bounds__(128) k_rs_spatial(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, RsBuffers B, uint32_t npix,
+                                                    unsigned long long* counters) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long n_shadow = 0;
+  if (i < npix) {
+    uint32_t x, y; size_t px;
+    pixel_of(fc, i, x, y, px);
+    const size_t np = rp.npix_frame;
+    const ResPlanes half0{P.res[0][0], P.res[0][1], P.res[0][2]}, half1{P.res[1][0], P.res[1][1], P.res[1][2]};
+    Reservoir out; rs_empty(out);
+    vec3 C0 = v3(0.0f), C1 = v3(0.0f), C2 = v3(0.0f);
+    bool ray0 = false, ray1 = false, ray2 = false;
+    const uint32_t n_pl = D.lights->num_pointlights, n_em = D.num_emissive;
+    if (px_shaded(P, px)) {
+      RsSurf s; vec3 pos, n_raw;
+      rs_gsurf(fc, P, x, y, s, pos, n_raw);
+      const uint32_t h0 = rs_seed((uint32_t)px, fc.frame_idx);
+      uint32_t cpx[RS_MAXN];  // contributing pixels (x | y << 16): slot 0 = this pixel, then the accepted neighbours
+      int nc = 0;
+      cpx[nc++] = x | (y << 16);
+      int ns = rp.num_spatial;
+      if (ns > RS_MAXN - 1) ns = RS_MAXN - 1;
+      const float t_q = P.hit_t[px];
+      for (int k = 0; k < ns; ++k) {
+        const float ua = rs_rand(h0, RS_DIM_SPATIAL + 2u * (uint32_t)k), ub = rs_rand(h0, RS_DIM_SPATIAL + 2u * (uint32_t)k + 1u);
+        const int ox = (int)((ua * 2.0f - 1.0f) * rp.radius), oy = (int)((ub * 2.0f - 1.0f) * rp.radius);
+        const int qx = (int)x + ox, qy = (int)y + oy;
+        if ((ox == 0 && oy == 0) || qx < 0 || qy < 0 || qx >= (int)fc.W || qy >= (int)fc.H) continue;
+        const size_t qp = (size_t)qy * fc.W + qx;
+        if (!px_shaded(P, qp)) continue;
+        if (!(dot(px_normal(P.normal, qp), n_raw) >= rp.normal_threshold)) continue;
+        if (!(fabsf(P.hit_t[qp] - t_q) <= 0.1f * t_q)) continue;
+        cpx[nc++] = (uint32_t)qx | ((uint32_t)qy << 16);
+      }
+      int src_pl = -1, src_em = -1;
+      float p_pl = 0.0f, p_em = 0.0f;
+      uint32_t m_pl[RS_MAXN], m_em[RS_MAXN];
+      for (int j = 0; j < nc; ++j) {
+        const Reservoir c = load_reservoir(half1, (size_t)(cpx[j] >> 16) * fc.W + (cpx[j] & 0xFFFFu));
+        m_pl[j] = c.pl_m; m_em[j] = c.m_em;
+        if (c.pl_idx < n_pl) {
+          const float ph = rs_phat(rs_eval_pl(s, load_pointlight(D.lights, c.pl_idx)));
+          const float w = (ph * c.w_pl) * (float)c.pl_m;
+          out.w_sum_pl += w;
+          if (w > 0.0f && rs_rand(h0, RS_DIM_SPATIAL + 0x100u + 2u * (uint32_t)j) * out.w_sum_pl < w) { out.pl_idx = c.pl_idx; p_pl = ph; src_pl = j; }
+        }
+        out.pl_m += c.pl_m;
+        if (rs_em_valid(D, c.obj, c.tri)) {
+          const NsSurf q = ns_surface(D, c.obj, c.tri, c.bx, c.by);
+          const float ph = rs_phat(rs_eval_em(s, q));
+          const float w = (ph * c.w_em) * (float)c.m_em;
+          out.w_sum_em += w;
+          if (w > 0.0f && rs_rand(h0, RS_DIM_SPATIAL + 0x100u + 2u * (uint32_t)j + 1u) * out.w_sum_em < w) {
+            out.obj = c.obj; out.tri = c.tri; out.bx = c.bx; out.by = c.by; p_em = ph; src_em = j;
+          }
+        }
+        out.m_em += c.m_em;
+      }
+      // MIS weight of the selected sample: m_s(y) = p^_s(y) / sum_j p^_j(y) M_j (p^_j on pixel j's G-buffer surface)
+      if (src_pl >= 0 || src_em >= 0) {
+        float num_pl = 0.0f, den_pl = 0.0f, num_em = 0.0f, den_em = 0.0f;
+        NsSurf q;
+        if (src_em >= 0) q = ns_surface(D, out.obj, out.tri, out.bx, out.by);
+        const PointLightRec pl = load_pointlight(D.lights, src_pl >= 0 ? out.pl_idx : 0u);
+        for (int j = 0; j < nc; ++j) {
+          float ph_pl = p_pl, ph_em = p_em;
+          if (j > 0) {
+            RsSurf sj; vec3 pj, nj;
+            rs_gsurf(fc, P, cpx[j] & 0xFFFFu, cpx[j] >> 16, sj, pj, nj);
+            if (src_pl >= 0) ph_pl = rs_phat(rs_eval_pl(sj, pl));
+            if (src_em >= 0) ph_em = rs_phat(rs_eval_em(sj, q));
+          }
+          if (src_pl >= 0) { den_pl += ph_pl * (float)m_pl[j]; if (j == src_pl) num_pl = ph_pl; }
+          if (src_em >= 0) { den_em += ph_em * (float)m_em[j]; if (j == src_em) num_em = ph_em; }
+        }
+        if (src_pl >= 0) out.w_pl = (den_pl > 0.0f && p_pl > 0.0f) ? (out.w_sum_pl * (num_pl / den_pl)) / p_pl : 0.0f;
+        if (src_em >= 0) out.w_em = (den_em > 0.0f && p_em > 0.0f) ? (out.w_sum_em * (num_em / den_em)) / p_em : 0.0f;
+      }
+      // final contributions on the exact primary-hit surface
+      const float2 bc = P.bary[px];
+      const NsSurf hs = ns_surface(D, P.inst[px], P.prim[px], bc.x, bc.y);
+      const vec3 cam = v3(fc.cam_pos[0], fc.cam_pos[1], fc.cam_pos[2]);
+      const RsSurf xs = rs_xsurf(hs, cam);
+      if (out.pl_idx != INVALID_IDX && out.w_pl > 0.0f) {
+        const RsEval e = rs_eval_pl(xs, load_pointlight(D.lights, out.pl_idx));
+        if (e.tmax > 0.0f) {
+          C0 = e.C * out.w_pl;
+          put_ray(B.rays, px, xs.o, 0.001f, e.wi, e.tmax);
+          ray0 = true; ++n_shadow;
+        }
+      }
+      if (out.obj != INVALID_IDX && out.w_em > 0.0f) {
+        const NsSurf q = ns_surface(D, out.obj, out.tri, out.bx, out.by);
+        const RsEval e = rs_eval_em(xs, q);
+        if (e.tmax > 0.0f) {
+          C1 = e.C * out.w_em;
+          put_ray(B.rays, np + px, xs.o, 0.001f, e.wi, e.tmax);
+          ray1 = true; ++n_shadow;
+        }
+      }
+      {
+        const float4 dl = __ldg(reinterpret_cast<const float4*>(D.lights->dir_light.dir));
+        const float4 dc = __ldg(reinterpret_cast<const float4*>(D.lights->dir_light.colour));
+        const vec3 wi = v3(dl.x, dl.y, dl.z), col = v3(dc.x, dc.y, dc.z);
+        if ((col.x > 0.0f || col.y > 0.0f || col.z > 0.0f) && dot(xs.n, wi) > 0.0f) {
+          C2 = ns_bsdf_cos(xs.n, xs.wo, wi, xs.albedo, xs.roughness, xs.metallic) * col;
+          put_ray(B.rays, 2 * np + px, xs.o, 0.001f, wi, 10000.0f);
+          ray2 = true; ++n_shadow;
+        }
+      }
+    }
+    store_reservoir(half0, px, out);
+    if (n_pl > 0 && !ray0) put_dead(B.rays, px);
+    if (n_em > 0 && !ray1) put_dead(B.rays, np + px);
+    if (!ray2) put_dead(B.rays, 2 * np + px);
+    B.C[px] = make_float4(C0.x, C0.y, C0.z, 0.0f);
+    B.C[np + px] = make_float4(C1.x, C1.y, C1.z, 0.0f);
+    B.C[2 * np + px] = make_float4(C2.x, C2.y, C2.z, 0.0f);
+  }
+  flush_counts(n_shadow, 0ull, counters);
+}
+
+__global__ void __launch_bounds__(256) k_rs_resolve(FrameConsts fc, PixelPlanes P, RsBuffers B, uint32_t npix, uint32_t npix_frame, uint32_t has_pl,
+                                                    uint32_t has_em) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npix) return;
+  const size_t px = (size_t)fc.row0 * fc.W + i, np = npix_frame;
+  const float4 c0 = B.C[px], c1 = B.C[np + px], c2 = B.C[2 * np + px];
+  const float v0 = has_pl ? B.vis[px] : 1.0f, v1 = has_em ? B.vis[np + px] : 1.0f, v2 = B.vis[2 * np + px];
+  P.direct[px] = make_float4((c0.x * v0 + c1.x * v1) + c2.x * v2, (c0.y * v0 + c1.y * v1) + c2.y * v2, (c0.z * v0 + c1.z * v1) + c2.z * v2, 1.0f);
+}
+
+}  // namespace
+
+int launch_restir_ns(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st) {
+  const FrameConsts& fc = ctx->fc;
+  const uint32_t npix_frame = fc.W * fc.H;
+  const size_t sizes[4] = {96ull * npix_frame, 12ull * npix_frame, 8ull * npix_frame, 48ull * npix_frame};
+  for (int k = 0; k < 4; ++k) {
+    cudaError_t e = ctx->wave[8 + k].reserve(sizes[k], false, st);
+    if (e != cudaSuccess) { ctx->err = std::string("north-star ReSTIR queues: ") + cudaGetErrorString(e); return SNKPT_E_NOMEM; }
+  }
+  RsBuffers B;
+  B.rays = ctx->wave[8].as<float4>(); B.vis = ctx->wave[9].as<float>(); B.phat = ctx->wave[10].as<float2>(); B.C = ctx->wave[11].as<float4>();
+  // stages 1-2 also cover the halo rows whose temporal reservoirs this band's spatial reuse reads (snkpt_set_halo)
+  FrameConsts f1 = fc;
+  f1.row0 = fc.row0 > ctx->halo_pass1 ? fc.row0 - ctx->halo_pass1 : 0u;
+  f1.row1 = fc.row1 + ctx->halo_pass1 < fc.H ? fc.row1 + ctx->halo_pass1 : fc.H;
+  const uint32_t npix1 = fc.W * (f1.row1 - f1.row0), npix = fc.W * (fc.row1 - fc.row0);
+  RsParams rp{s.num_temporal_resamples, s.num_spatial_resamples, s.ris_iters, s.m_cap, s.neighbour_radius, s.normal_threshold,
+              (fc.prev_frame_invalid || !ctx->history_valid) ? 0u : 1u, npix_frame};
+  unsigned long long* counters = reinterpret_cast<unsigned long long*>(ctx->dev_counters.as<uint32_t>() + 2);
+  const SceneDev D = ctx->scene_dev();
+  // light counts as of the last snkpt_set_lights / snkpt_set_instances (host mirrors)
+  const bool has_pl = ctx->num_pointlights > 0, has_em = ctx->num_emissive > 0;
+  int launches = 0;
+  cudaEventRecord(ctx->ev[2], st);
+  int rec = prof_begin(ctx, "rs_initial", npix1, false, false, st);
+  k_rs_initial<<<(npix1 + 127) / 128, 128, 0, st>>>(D, f1, ctx->planes, rp, B, npix1, counters);
+  prof_end(ctx, rec, st);
+  ++launches;
+  const size_t off1 = (size_t)f1.row0 * fc.W, off = (size_t)fc.row0 * fc.W;
+  if (has_pl) launches += traced_launch(ctx, "rs_any.init_pl", B.rays + 2 * off1, npix1, true, nullptr, nullptr, nullptr, B.vis + off1, st);
+  if (has_em) launches += traced_launch(ctx, "rs_any.init_em", B.rays + 2 * (npix_frame + off1), npix1, true, nullptr, nullptr, nullptr, B.vis + npix_frame + off1, st);
+  rec = prof_begin(ctx, "rs_temporal", npix1, false, false, st);
+  k_rs_temporal<<<(npix1 + 127) / 128, 128, 0, st>>>(D, f1, ctx->planes, rp, B, npix1);
+  prof_end(ctx, rec, st);
+  ++launches;
+  cudaEventRecord(ctx->ev[3], st);
+  rec = prof_begin(ctx, "rs_spatial", npix, false, false, st);
+  k_rs_spatial<<<(npix + 127) / 128, 128, 0, st>>>(D, fc, ctx->planes, rp, B, npix, counters);
+  prof_end(ctx, rec, st);
+  ++launches;
+  if (has_pl) launches += traced_launch(ctx, "rs_any.final_pl", B.rays + 2 * off, npix, true, nullptr, nullptr, nullptr, B.vis + off, st);
+  if (has_em) launches += traced_launch(ctx, "rs_any.final_em", B.rays + 2 * (npix_frame + off), npix, true, nullptr, nullptr, nullptr, B.vis + npix_frame + off, st);
+  launches += traced_launch(ctx, "rs_any.final_dir", B.rays + 2 * (2ull * npix_frame + off), npix, true, nullptr, nullptr, nullptr, B.vis + 2ull * npix_frame + off, st);
+  rec = prof_begin(ctx, "rs_resolve", npix, false, false, st);
+  k_rs_resolve<<<(npix + 255) / 256, 256, 0, st>>>(fc, ctx->planes, B, npix, npix_frame, has_pl ? 1u : 0u, has_em ? 1u : 0u);
+  prof_end(ctx, rec, st);
+  ++launches;
+  cudaEventRecord(ctx->ev[4], st);
+  return launches;
+}
+
+}  // namespace snk

@@ -41,6 +41,7 @@ def lib() -> C.CDLL:
         L.snkor_frame_set.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.snkor_frame_gbuffer.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_uint32, C.c_uint32, C.c_int]
         L.snkor_frame_render.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]
+        L.snkor_frame_set_halo.argtypes = [C.c_void_p, C.c_uint32]
         L.snkor_frame_render_pass.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]
         L.snkor_frame_read.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]
         L.snkor_frame_write_reservoirs.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32]
@@ -134,6 +135,10 @@ class OracleFrame:
 
     def render(self, rows=(0, 0), threads=8):
         lib().snkor_frame_render(self.h, rows[0], rows[1], threads)
+
+    def set_halo(self, halo: int):
+        """north-star mode: rows around the rendered band that also run the initial + temporal reservoir stages"""
+        lib().snkor_frame_set_halo(self.h, int(halo))
 
     def render_pass(self, pass_: int, rows=(0, 0), threads=8):
         lib().snkor_frame_render_pass(self.h, pass_, rows[0], rows[1], threads)

@@ -370,3 +370,57 @@ def test_reservoirs_round_trip(snk, oracle):
     r2["w_sum_pl"] += 1
     fr.write_reservoirs(0, r2)
     assert np.array_equal(fr.read("reservoirs_final")["w_sum_pl"], r2["w_sum_pl"])
+
+
+# ---- north-star ReSTIR DI (oracle/snk_restir_ns.h): estimator-level properties of the CPU statement -------------------------
+def _ns_mean(O, sc, osc, n, **kw):
+    fr = O.OracleFrame(osc)
+    acc = np.zeros((sc.height, sc.width, 3))
+    for f in range(n):
+        ubo = sc.ubo(f)
+        fr.set(ubo, ubo, O.default_settings(mode=1, max_bounces=0, **kw))
+        fr.gbuffer()
+        fr.render()
+        acc += fr.read("radiance")[..., :3]
+    body = (fr.read("flags") & 1) == 0
+    return (acc / n)[body].mean(0), fr
+
+
+def test_ns_restir_initial_ris_is_unbiased(snk, oracle):
+    """initial RIS + visibility (no reuse) and temporal-only reuse have the plain path tracer's expectation"""
+    O = oracle
+    sc = snk.scenes.cornell(48, 48, with_pointlight=True)
+    osc = O.OracleScene(sc)
+    plain, _ = _ns_mean(O, sc, osc, 128, flags=1)
+    ris, _ = _ns_mean(O, sc, osc, 128, num_temporal=0, num_spatial=0)
+    tmp, _ = _ns_mean(O, sc, osc, 128, num_temporal=1, num_spatial=0)
+    assert np.all(np.abs(ris - plain) / plain < 0.015), (ris, plain)
+    assert np.all(np.abs(tmp - plain) / plain < 0.02), (tmp, plain)
+
+
+def test_ns_restir_full_reuse_bias_is_bounded_and_variance_drops(snk, oracle):
+    O = oracle
+    sc = snk.scenes.cornell(48, 48, with_pointlight=True)
+    osc = O.OracleScene(sc)
+    plain, _ = _ns_mean(O, sc, osc, 96, flags=1)
+    full, fr = _ns_mean(O, sc, osc, 96)
+    assert np.all(np.abs(full - plain) / plain < 0.10), (full, plain)
+    # reservoir bookkeeping after 96 static frames: M saturates at (1 + m_cap) x M_initial summed over <= 4 contributors
+    res = fr.read("reservoirs_final")
+    body = (fr.read("flags") & 1) == 0
+    m_init = 2  # cornell(with_pointlight=True): point lights are enumerated (n_pl <= ris_iters)
+    n_pl = int(np.frombuffer(sc.flatten()["lights"], np.uint32, 1, 96)[0])
+    assert res["pl_m"][body].max() <= 4 * (1 + 20) * max(n_pl, m_init)
+    assert np.isfinite(res["w_pl"]).all() and (res["w_pl"] >= 0).all() and np.isfinite(res["w_em"]).all() and (res["w_em"] >= 0).all()
+    # single-frame noise of the direct term: temporal reuse must cut the variance of initial RIS several times
+    # (spatial reuse with a radius of more than half this 48-px image is not expected to: see the header of snk_restir_ns.h)
+    def frame_var(**kw):
+        frq = O.OracleFrame(osc)
+        imgs = []
+        for f in range(24):
+            ubo = sc.ubo(f)
+            frq.set(ubo, ubo, O.default_settings(mode=1, max_bounces=0, **kw))
+            frq.gbuffer(); frq.render()
+            imgs.append(frq.read("direct")[..., :3].copy())
+        return np.stack(imgs[8:]).var(0)[body].mean()
+    assert frame_var(num_spatial=0) < 0.5 * frame_var(num_temporal=0, num_spatial=0)

@@ -36,6 +36,12 @@ def test_northstar_matches_oracle(snk, oracle, scene_name):
         assert not np.isnan(a).any()
         eq = bits_equal(a, b)
         assert eq.mean() >= 0.998, f"frame {f}: radiance differs on {(~eq).sum()} of {eq.size} pixels; max abs {np.abs(a - b).max()}"
+        for half in ("reservoirs_temporal", "reservoirs_final"):
+            ra, rb = pt.read_aux(half), fr.read(half)
+            same = ra.view(np.uint8).reshape(ra.shape + (48,))[..., :44] == rb.view(np.uint8).reshape(rb.shape + (48,))[..., :44]
+            assert same.all(-1).mean() >= 0.998, f"frame {f}: {half} differs on {(~same.all(-1)).sum()} pixels"
+        da, db = pt.read_aux("direct")[..., :3], fr.read("direct")[..., :3]
+        assert bits_equal(da, db).mean() >= 0.998
         st = pt.stats()
         oc, oa = fr.ray_counts(reset=True)
         assert (int(st["rays_secondary"]), int(st["rays_shadow"])) == (oc, oa), "ray counts differ from the oracle's"
@@ -56,6 +62,45 @@ def test_bounce_count_and_flags(snk, oracle):
                 assert np.array_equal(a, np.where(np.isnan(a), a, pt.read_aux("radiance")[..., :3]))
                 assert int(pt.stats()["rays_secondary"]) == 0
     assert means[0] <= means[1] <= means[2] * 1.2  # indirect light only adds energy (up to 1-frame noise)
+
+
+@pytest.mark.parametrize("kw", [dict(flags=1), dict(num_temporal=0, num_spatial=0), dict(num_temporal=1, num_spatial=0),
+                                dict(num_temporal=0, num_spatial=6), dict(ris_iters=4, m_cap=3, neighbour_radius=8.0)])
+def test_restir_settings_match_oracle(snk, oracle, kw):
+    """north-star ReSTIR DI stages under other settings (flags=1: reservoir passes off = plain path tracer with NEE at x0;
+    ris_iters < number of point lights exercises the random-candidate branch), emissive + point lights (small scene)"""
+    sc = snk.scenes.small_test_scene(80, 48)
+    for f, pt, fr in run(snk, oracle, sc, frames=3, **kw):
+        a, b = pt.read_aux("radiance")[..., :3], fr.read("radiance")[..., :3]
+        eq = bits_equal(a, b)
+        assert eq.mean() >= 0.998, f"{kw} frame {f}: {(~eq).sum()} pixels differ"
+        st = pt.stats()
+        oc, oa = fr.ray_counts(reset=True)
+        assert (int(st["rays_secondary"]), int(st["rays_shadow"])) == (oc, oa)
+
+
+def test_restir_mean_close_to_plain_path_tracer(snk):
+    """the ReSTIR'd direct term must agree with the plain path tracer (NEE at x0) up to the visibility bias of
+    reuse without shadow rays in the MIS weights (oracle/snk_restir_ns.h header): |bias| < 10 % of the frame mean,
+    and exactly the same expectation with reuse off (initial RIS + visibility only: < 2 % at 96 frames)"""
+    sc = snk.scenes.cornell(64, 64, with_pointlight=True)
+
+    def mean_image(**kw):
+        rt = snk.RT().Init(sc)
+        acc = np.zeros((64, 64, 3))
+        n = 96
+        for f in range(n):
+            ubo = sc.ubo(f)
+            rt.RecordRenderCmdBuf(ubo, ubo, mode=snk.api.MODE_NORTHSTAR, max_bounces=0, **kw)
+            acc += rt.pt.read_aux("radiance")[..., :3]
+        body = (rt.pt.read_aux("flags") & 1) == 0
+        return (acc / n)[body].mean(0)
+
+    plain = mean_image(flags=1)
+    initial_only = mean_image(num_temporal=0, num_spatial=0)
+    full = mean_image()
+    assert np.all(np.abs(initial_only - plain) / plain < 0.02), (initial_only, plain)
+    assert np.all(np.abs(full - plain) / plain < 0.10), (full, plain)
 
 
 def test_furnace_energy_bound(snk):
