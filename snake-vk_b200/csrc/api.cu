@@ -86,7 +86,7 @@ int prof_begin(SnkPt* ctx, const char* name, uint64_t units, bool is_trace, bool
   if (!r.e0 && (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess)) return -1;
   memset(r.name, 0, sizeof(r.name));
   snprintf(r.name, sizeof(r.name), "%s", name);
-  r.units = units; r.is_trace = is_trace; r.any = any; r.counted = false;
+  r.units = units; r.is_trace = is_trace; r.any = any; r.counted = false; r.queue = false;
   cudaEventRecord(r.e0, st);
   return ctx->prof_n++;
 }
@@ -107,10 +107,45 @@ int traced_launch(SnkPt* ctx, const char* name, const float4* rays, uint64_t n, 
   unsigned long long* ticket = ctx->dev_counters.as<unsigned long long>() + 16 + (ctx->ticket_rr++ & 15u);
   const int launches = launch_trace(S, rays, n, any, hits_aos, hits_soa, inst_soa, vis_out, ticket, st);
   prof_end(ctx, rec, st);
-  if (count && rec >= 0 && hits_soa && ctx->prof_work.reserve(32 * PROF_MAX, false, st) == cudaSuccess) {
-    unsigned long long* sums = ctx->prof_work.as<unsigned long long>() + 4 * rec;
-    cudaMemsetAsync(sums, 0, 32, st);
+  if (count && rec >= 0 && hits_soa && ctx->prof_work.reserve(64 * PROF_MAX, false, st) == cudaSuccess) {
+    unsigned long long* sums = ctx->prof_work.as<unsigned long long>() + 8 * rec;
+    cudaMemsetAsync(sums, 0, 64, st);
     launch_count_work_sum(S, rays, hits_soa, n, sums, st);
+    ctx->prof[rec].counted = true;
+  }
+  return launches;
+}
+
+// ---- compact ray-reference queues of the frame (trace_q.cu) ----
+// dev_counters u32 view [64 + 2k] = entries appended to queue k, [65 + 2k] = ticket of its traversal launch
+RefQueue ref_queue(SnkPt* ctx, int k, uint32_t cap) {
+  RefQueue q;
+  q.refs = ctx->wave_refs.as<uint32_t>();
+  q.count = ctx->dev_counters.as<uint32_t>() + 64 + 2 * k;
+  q.ticket = q.count + 1;
+  q.cap = cap;
+  return q;
+}
+int reserve_ref_queues(SnkPt* ctx, uint32_t cap, cudaStream_t st) {
+  const cudaError_t e = ctx->wave_refs.reserve(4ull * cap, false, st);
+  if (e != cudaSuccess) { ctx->err = std::string("ray reference queue: ") + cudaGetErrorString(e); return SNKPT_E_NOMEM; }
+  return SNKPT_OK;
+}
+void reset_ref_queues(SnkPt* ctx, cudaStream_t st) { cudaMemsetAsync(ctx->dev_counters.as<uint32_t>() + 64, 0, 64, st); }
+
+int traced_launch_q(SnkPt* ctx, const char* name, const TraceSegs& segs, const RefQueue& q, cudaStream_t st) {
+  const bool count = ctx->profiling >= 2 && ctx->prof_n < PROF_MAX;
+  float* prof_t = nullptr;
+  if (count && ctx->prof_hits.reserve(4ull * q.cap, false, st) == cudaSuccess) prof_t = ctx->prof_hits.as<float>();
+  const TraceScene S = ctx->trace_scene();
+  const int rec = prof_begin(ctx, name, q.cap, true, false, st);
+  const int launches = launch_trace_q(S, segs, q, prof_t, st);
+  prof_end(ctx, rec, st);
+  if (rec >= 0) ctx->prof[rec].queue = true;
+  if (count && rec >= 0 && prof_t && ctx->prof_work.reserve(64 * PROF_MAX, false, st) == cudaSuccess) {
+    unsigned long long* sums = ctx->prof_work.as<unsigned long long>() + 8 * rec;
+    cudaMemsetAsync(sums, 0, 64, st);
+    launch_count_work_q(S, segs, q, prof_t, sums, st);
     ctx->prof[rec].counted = true;
   }
   return launches;
@@ -214,8 +249,8 @@ int snkpt_create(const SnkPtConfig* cfg, SnkPt** out) {
     if (e2 == cudaSuccess) e2 = cudaMemsetAsync(ctx->lights.p, 0, sizeof(SnkLightData), ctx->stream);
     if (e2 == cudaSuccess) e2 = ctx->materials.reserve(sizeof(SnkMaterial) * ctx->max_materials, false, ctx->stream);
     if (e2 == cudaSuccess) e2 = cudaMemsetAsync(ctx->materials.p, 0, sizeof(SnkMaterial) * ctx->max_materials, ctx->stream);
-    if (e2 == cudaSuccess) e2 = ctx->dev_counters.reserve(512, false, ctx->stream);
-    if (e2 == cudaSuccess) e2 = cudaMemsetAsync(ctx->dev_counters.p, 0, 512, ctx->stream);
+    if (e2 == cudaSuccess) e2 = ctx->dev_counters.reserve(1024, false, ctx->stream);
+    if (e2 == cudaSuccess) e2 = cudaMemsetAsync(ctx->dev_counters.p, 0, 1024, ctx->stream);
     if (e2 == cudaSuccess) e2 = ctx->trav_spill.reserve(trace_spill_bytes(), false, ctx->stream);
     if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(ctx->stream);
     if (e2 != cudaSuccess) { ctx->err = cudaGetErrorString(e2); rc = SNKPT_E_CUDA; }
@@ -232,7 +267,8 @@ void snkpt_destroy(SnkPt* ctx) {
   DevBuf* bufs[] = {&ctx->positions, &ctx->normals, &ctx->tangents, &ctx->uvs, &ctx->indices, &ctx->blas_nodes, &ctx->blas_tris,
                     &ctx->d_blas, &ctx->materials, &ctx->lights, &ctx->transforms, &ctx->prev_transforms, &ctx->normal_mats,
                     &ctx->det3, &ctx->instances, &ctx->blas_of_instance, &ctx->emissive_idx, &ctx->tlas_nodes, &ctx->tlas_leaf_ids,
-                    &ctx->inst_recs, &ctx->valid_slots, &ctx->q_rays, &ctx->q_hits, &ctx->q_work, &ctx->dev_counters, &ctx->trav_spill};
+                    &ctx->inst_recs, &ctx->valid_slots, &ctx->q_rays, &ctx->q_hits, &ctx->q_work, &ctx->dev_counters, &ctx->trav_spill,
+                    &ctx->wave_refs, &ctx->prof_work, &ctx->prof_hits};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : ctx->wave) b.release();
   for (auto& b : ctx->px) b.release();
@@ -824,8 +860,8 @@ int snkpt_get_launch_timings(SnkPt* ctx, SnkLaunchTiming* out, uint32_t cap, uin
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
   CK(cudaDeviceSynchronize());  // launches may have been enqueued on a caller stream
-  std::vector<unsigned long long> work(4 * PROF_MAX, 0ull);
-  if (ctx->prof_work.p) CK(cudaMemcpy(work.data(), ctx->prof_work.p, 32 * PROF_MAX, cudaMemcpyDeviceToHost));
+  std::vector<unsigned long long> work(8 * PROF_MAX, 0ull);
+  if (ctx->prof_work.p) CK(cudaMemcpy(work.data(), ctx->prof_work.p, 64 * PROF_MAX, cudaMemcpyDeviceToHost));
   uint32_t n = 0;
   for (int i = 0; i < ctx->prof_n && n < cap; ++i, ++n) {
     const ProfRec& r = ctx->prof[i];
@@ -836,9 +872,13 @@ int snkpt_get_launch_timings(SnkPt* ctx, SnkLaunchTiming* out, uint32_t cap, uin
     o.is_trace = r.is_trace ? 1u : 0u;
     o.units = r.units;
     if (r.counted) {
-      o.live = work[4 * i]; o.nodes = work[4 * i + 1]; o.tris = work[4 * i + 2]; o.insts = work[4 * i + 3];
-      // ray in 32 B, hit out 16 B (closest) / 4 B (any), 80 B per node, 48 B per triangle record, 64 B per instance
-      o.alg_bytes = o.live * (32ull + (r.any ? 4ull : 16ull)) + 80ull * o.nodes + 48ull * o.tris + 64ull * o.insts;
+      o.live = work[8 * i]; o.nodes = work[8 * i + 1]; o.tris = work[8 * i + 2]; o.insts = work[8 * i + 3];
+      // ray in 32 B, hit out 16 B (closest) / 4 B (any), 80 B per node, 48 B per triangle record, 64 B per instance;
+      // a queue launch (trace_q.cu) mixes both kinds and also reads the 4-B reference and writes the 4-B instance plane
+      const uint64_t n_any = r.queue ? work[8 * i + 4] : (r.any ? o.live : 0ull);
+      o.alg_bytes = o.live * (32ull + (r.queue ? 4ull : 0ull)) + n_any * 4ull + (o.live - n_any) * (r.queue ? 20ull : 16ull) + 80ull * o.nodes +
+                    48ull * o.tris + 64ull * o.insts;
+      if (r.queue) o.units = o.live;
     }
   }
   *count = n;

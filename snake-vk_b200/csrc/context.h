@@ -46,7 +46,7 @@ struct ProfRec {
   char name[32];
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   uint64_t units = 0;
-  bool is_trace = false, any = false, counted = false;
+  bool is_trace = false, any = false, counted = false, queue = false;
 };
 constexpr int PROF_MAX = 2048;
 
@@ -138,6 +138,7 @@ struct SnkPt {
   // generic ray query scratch
   snk::DevBuf q_rays, q_hits, q_work;
   snk::DevBuf wave[12];      // wavefront queues of the bounce stages (rays, hits, shading records)
+  snk::DevBuf wave_refs;     // compact ray-reference queue of the north-star frame (trace_q.cu)
   // u32 view: [0] traversal stack overflows, [2..3] shadow rays of the frame, [4..5] closest-hit rays, [8..11] since-create
   // totals; u64 view [16..31]: ray tickets of the persistent traversal launches
   snk::DevBuf dev_counters;

@@ -18,6 +18,18 @@ int launch_count_work(const TraceScene& S, const float4* rays, const SnkHit* hit
 int launch_count_work_sum(const TraceScene& S, const float4* rays, const float4* hits_soa, uint64_t n, unsigned long long* sums4,
                           cudaStream_t st);
 
+// trace_q.cu — queue traversal: drains a compact queue of ray references (closest-hit and any-hit rays of several
+// segments mixed); prof_t (optional) receives the reported hit distance per queue position
+int launch_trace_q(const TraceScene& S, const TraceSegs& segs, const RefQueue& q, float* prof_t, cudaStream_t st);
+int launch_count_work_q(const TraceScene& S, const TraceSegs& segs, const RefQueue& q, const float* prof_t, unsigned long long* sums8,
+                        cudaStream_t st);
+// launch_trace_q bracketed by a profiling record (+ counted replay at level 2)
+int traced_launch_q(SnkPt* ctx, const char* name, const TraceSegs& segs, const RefQueue& q, cudaStream_t st);
+// queue k (0..7) of the frame: refs in ctx->wave_refs, counters in dev_counters; all eight are reset by reset_ref_queues
+RefQueue ref_queue(SnkPt* ctx, int k, uint32_t cap);
+int reserve_ref_queues(SnkPt* ctx, uint32_t cap, cudaStream_t st);
+void reset_ref_queues(SnkPt* ctx, cudaStream_t st);
+
 // api.cu — per-launch profiling (no-ops at level 0)
 void prof_reset(SnkPt* ctx);
 int prof_begin(SnkPt* ctx, const char* name, uint64_t units, bool is_trace, bool any, cudaStream_t st);
@@ -34,7 +46,10 @@ int launch_restir_passes(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st);
 int launch_reference_frame(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st);
 int launch_northstar_frame(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st);
 // restir_ns.cu — north-star ReSTIR DI stages (initial / temporal / spatial + final evaluation / resolve) → planes.direct
-int launch_restir_ns(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st);
+int restir_ns_prepare(SnkPt* ctx, TraceSegs& segs, cudaStream_t st);
+int restir_ns_initial(SnkPt* ctx, const SnkRtSettings& s, const RefQueue& q, cudaStream_t st);
+int restir_ns_reuse(SnkPt* ctx, const SnkRtSettings& s, const RefQueue& q, cudaStream_t st);
+int restir_ns_resolve(SnkPt* ctx, cudaStream_t st);
 int launch_accumulate(const PixelPlanes& P, uint32_t npix, uint32_t count, cudaStream_t st);
 
 }  // namespace snk

@@ -37,7 +37,7 @@ struct NsBuffers {
 // work of path vertex x_b (b = 0: the primary hit): NEE (b >= 1), Russian roulette (b >= 2), BSDF sample.
 // Writes the shadow ray + pending C, the continuation ray, throughput and pdf for slot i.
 __device__ void ns_vertex_work(const SceneDev& D, const NsBuffers& B, size_t i, uint32_t pixel, uint32_t frame, uint32_t b, uint32_t max_bounces,
-                               uint32_t nee_from, const NsSurf& s, vec3 wo, vec3 T, unsigned long long& n_shadow, unsigned long long& n_closest) {
+                               uint32_t nee_from, const NsSurf& s, vec3 wo, vec3 T, bool& has_shadow, bool& has_closest) {
   const NsLightCounts lc = ns_light_counts(D);
   vec3 n = s.n;
   if (dot(n, wo) < 0.0f) n = -n;
@@ -100,12 +100,12 @@ __device__ void ns_vertex_work(const SceneDev& D, const NsBuffers& B, size_t i, 
     if (tmax > 0.0f) {
       put_ray(B.srays, i, o, 0.001f, wi, tmax);
       shadow = true;
-      ++n_shadow;
     } else {
       C = v3(0.0f);
     }
   }
-  if (!shadow) put_dead(B.srays, i);
+  if (!shadow) B.vis[i] = 1.0f;  // no shadow ray: the pending contribution is zero and counts as unoccluded
+  has_shadow = shadow;
   B.C[i] = make_float4(C.x, C.y, C.z, 0.0f);
   // ---- continuation
   bool alive = b < max_bounces;
@@ -125,19 +125,16 @@ __device__ void ns_vertex_work(const SceneDev& D, const NsBuffers& B, size_t i, 
     T = (T * ns_bsdf_cos(n, wo, wi, s.albedo, s.roughness, s.metallic)) / pdf_b;
     alive = gmax(gmax(T.x, T.y), T.z) > 0.0f;
   }
-  if (alive) {
-    put_ray(B.rays, i, o, 0.001f, wi, 1000.0f);
-    ++n_closest;
-  } else {
-    put_dead(B.rays, i);
-  }
+  if (alive) put_ray(B.rays, i, o, 0.001f, wi, 1000.0f);
+  else put_dead_dir(B.rays, i);
+  has_closest = alive;
   B.T[i] = make_float4(T.x, T.y, T.z, pdf_b);
 }
 
 __global__ void __launch_bounds__(128) k_ns_gen(SceneDev D, FrameConsts fc, PixelPlanes P, NsBuffers B, uint32_t npix, uint32_t max_bounces,
-                                                uint32_t nee_from, unsigned long long* counters) {
+                                                uint32_t nee_from, unsigned long long* counters, uint32_t* q_refs, uint32_t* q_count) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned long long n_shadow = 0, n_closest = 0;
+  bool has_shadow = false, has_closest = false;
   if (i < npix) {
     const uint32_t x = i % fc.W, y = fc.row0 + i / fc.W;
     const size_t px = (size_t)y * fc.W + x;
@@ -153,21 +150,22 @@ __global__ void __launch_bounds__(128) k_ns_gen(SceneDev D, FrameConsts fc, Pixe
     if (alive) {
       const vec3 cam = v3(fc.cam_pos[0], fc.cam_pos[1], fc.cam_pos[2]);
       const vec3 wo = normalize(cam - s.p);
-      ns_vertex_work(D, B, i, (uint32_t)px, fc.frame_idx, 0u, max_bounces, nee_from, s, wo, v3(1.0f), n_shadow, n_closest);
+      ns_vertex_work(D, B, i, (uint32_t)px, fc.frame_idx, 0u, max_bounces, nee_from, s, wo, v3(1.0f), has_shadow, has_closest);
     } else {
-      put_dead(B.rays, i); put_dead(B.srays, i);
+      put_dead_dir(B.rays, i);
       B.C[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       B.T[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
-  flush_counts(n_shadow, n_closest, counters);
+  q_append3(q_refs, q_count, has_closest, make_ref(SEG_NS_CLOSEST, i), has_shadow, make_ref(SEG_NS_SHADOW, i), false, 0u);
+  flush_counts(has_shadow ? 1ull : 0ull, has_closest ? 1ull : 0ull, counters);
 }
 
 // the hit of the ray that left vertex x_{b-1} becomes vertex x_b
 __global__ void __launch_bounds__(128) k_ns_vertex(SceneDev D, FrameConsts fc, NsBuffers B, uint32_t npix, uint32_t b, uint32_t max_bounces,
-                                                   uint32_t nee_from, unsigned long long* counters) {
+                                                   uint32_t nee_from, unsigned long long* counters, uint32_t* q_refs, uint32_t* q_count) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned long long n_shadow = 0, n_closest = 0;
+  bool has_shadow = false, has_closest = false;
   if (i < npix) {
     const uint32_t x = i % fc.W, y = fc.row0 + i / fc.W;
     const uint32_t pixel = y * fc.W + x;
@@ -178,7 +176,7 @@ __global__ void __launch_bounds__(128) k_ns_vertex(SceneDev D, FrameConsts fc, N
       const float4 c = B.C[i];
       L += v3(c.x, c.y, c.z) * B.vis[i];
     }
-    const float4 r0 = B.rays[2 * i], r1 = B.rays[2 * i + 1];
+    const float4 r1 = B.rays[2 * i + 1];
     bool alive = r1.w >= 0.0f;
     const float4 h = B.hit[i];
     if (alive && h.x < 0.0f) alive = false;
@@ -201,14 +199,14 @@ __global__ void __launch_bounds__(128) k_ns_vertex(SceneDev D, FrameConsts fc, N
     }
     B.L[i] = make_float4(L.x, L.y, L.z, 0.0f);
     if (alive) {
-      ns_vertex_work(D, B, i, pixel, fc.frame_idx, b, max_bounces, nee_from, s, -wi, T, n_shadow, n_closest);
+      ns_vertex_work(D, B, i, pixel, fc.frame_idx, b, max_bounces, nee_from, s, -wi, T, has_shadow, has_closest);
     } else {
-      put_dead(B.rays, i); put_dead(B.srays, i);
+      if (r1.w >= 0.0f) put_dead_dir(B.rays, i);
       B.C[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    (void)r0;
   }
-  flush_counts(n_shadow, n_closest, counters);
+  q_append3(q_refs, q_count, has_closest, make_ref(SEG_NS_CLOSEST, i), has_shadow, make_ref(SEG_NS_SHADOW, i), false, 0u);
+  flush_counts(has_shadow ? 1ull : 0ull, has_closest ? 1ull : 0ull, counters);
 }
 
 __global__ void __launch_bounds__(256) k_ns_resolve(SceneDev D, FrameConsts fc, PixelPlanes P, NsBuffers B, uint32_t npix, uint32_t max_bounces,
@@ -246,52 +244,75 @@ __global__ void k_fold_counters_ns(unsigned long long* c) {
 
 int launch_northstar_frame(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st) {
   const FrameConsts& fc = ctx->fc;
-  const uint32_t npix = fc.W * (fc.row1 - fc.row0);
+  const uint32_t npix = fc.W * (fc.row1 - fc.row0), npix_frame = fc.W * fc.H;
   if (s.max_bounces > 16) { ctx->err = "snkpt_render: max_bounces > 16"; return SNKPT_E_INVALID; }
+  if (npix_frame > REF_SLOT_MASK) { ctx->err = "snkpt_render: more than 2^28 pixels"; return SNKPT_E_INVALID; }
   int launches = 0;
   cudaMemsetAsync(ctx->dev_counters.as<uint32_t>() + 2, 0, 16, st);
   // direct term at the primary hit: the ReSTIR DI stages (restir_ns.cu); switched off, the path does its own
   // next-event estimation at x0 instead (plain path tracer, the unbiased yardstick of the statistical tests)
   const uint32_t nee_from = (s.flags & SNKPT_RT_NO_RESTIR) ? 0u : 1u;
-  if (nee_from) {
-    const int rc = launch_restir_ns(ctx, s, st);
-    if (rc < 0) return rc;
-    launches += rc;
-  } else {
-    cudaEventRecord(ctx->ev[2], st);
-    cudaMemsetAsync(ctx->planes.direct + (size_t)fc.row0 * fc.W, 0, 16ull * npix, st);
-    cudaEventRecord(ctx->ev[3], st);
-    cudaEventRecord(ctx->ev[4], st);
-  }
   const size_t sizes[8] = {32ull * npix, 16ull * npix, 4ull * npix, 16ull * npix, 16ull * npix, 32ull * npix, 16ull * npix, 4ull * npix};
   for (int k = 0; k < 8; ++k) {
     cudaError_t e = ctx->wave[k].reserve(sizes[k], false, st);
     if (e != cudaSuccess) { ctx->err = std::string("north-star queues: ") + cudaGetErrorString(e); return SNKPT_E_NOMEM; }
   }
+  // one compact reference queue per traversal launch; the largest (launch 2) holds 3 ReSTIR + 2 path rays per pixel
+  const uint32_t qcap = 5u * npix_frame;
+  int rc = reserve_ref_queues(ctx, qcap, st);
+  if (rc < 0) return rc;
+  reset_ref_queues(ctx, st);
   NsBuffers B;
   B.rays = ctx->wave[0].as<float4>(); B.hit = ctx->wave[1].as<float4>(); B.inst = ctx->wave[2].as<uint32_t>(); B.T = ctx->wave[3].as<float4>();
   B.L = ctx->wave[4].as<float4>(); B.srays = ctx->wave[5].as<float4>(); B.C = ctx->wave[6].as<float4>(); B.vis = ctx->wave[7].as<float>();
+  TraceSegs segs{};
+  if (nee_from) {
+    rc = restir_ns_prepare(ctx, segs, st);
+    if (rc < 0) return rc;
+  }
+  segs.s[SEG_NS_CLOSEST] = TraceSeg{B.rays, B.hit, B.inst, nullptr, 0u, 0u};
+  segs.s[SEG_NS_SHADOW] = TraceSeg{B.srays, nullptr, nullptr, B.vis, 1u, 0u};
   unsigned long long* counters = reinterpret_cast<unsigned long long*>(ctx->dev_counters.as<uint32_t>() + 2);
   const SceneDev D = ctx->scene_dev();
   const uint32_t g128 = (npix + 127) / 128;
   const bool bounce = !(s.flags & SNKPT_RT_NO_BOUNCE);
   const uint32_t max_bounces = bounce ? s.max_bounces : 0u;
+  // Every traversal launch drains ONE queue that all stages ready at that point have appended to:
+  //   queue 0: ReSTIR initial-candidate shadow rays + the path's first continuation ray (+ its NEE ray without ReSTIR)
+  //   queue 1: ReSTIR final shadow rays + NEE ray of vertex 1 + continuation ray 2
+  //   queue b: NEE ray of vertex b + continuation ray b+1
+  cudaEventRecord(ctx->ev[2], st);
+  int q = 0;
+  RefQueue Q = ref_queue(ctx, q, qcap);
+  if (nee_from) launches += restir_ns_initial(ctx, s, Q, st);
   int rec = prof_begin(ctx, "ns_gen", npix, false, false, st);
-  k_ns_gen<<<g128, 128, 0, st>>>(D, fc, ctx->planes, B, npix, max_bounces, nee_from, counters);
+  k_ns_gen<<<g128, 128, 0, st>>>(D, fc, ctx->planes, B, npix, max_bounces, nee_from, counters, Q.refs, Q.count);
   prof_end(ctx, rec, st);
   ++launches;
-  if (!nee_from) launches += traced_launch(ctx, "ns_any.0", B.srays, npix, true, nullptr, nullptr, nullptr, B.vis, st);
   char name[32];
+  snprintf(name, sizeof(name), "trace.q%d", q);
+  launches += traced_launch_q(ctx, name, segs, Q, st);
+  Q = ref_queue(ctx, ++q, qcap);
+  if (nee_from) launches += restir_ns_reuse(ctx, s, Q, st);
+  else { cudaEventRecord(ctx->ev[3], st); }
   for (uint32_t b = 1; b <= max_bounces; ++b) {
-    snprintf(name, sizeof(name), "ns_closest.%u", b);
-    launches += traced_launch(ctx, name, B.rays, npix, false, nullptr, B.hit, B.inst, nullptr, st);
+    if (q >= 8) { ctx->err = "snkpt_render: max_bounces > 7 needs more reference queues"; return SNKPT_E_INVALID; }
     snprintf(name, sizeof(name), "ns_vertex.%u", b);
     rec = prof_begin(ctx, name, npix, false, false, st);
-    k_ns_vertex<<<g128, 128, 0, st>>>(D, fc, B, npix, b, max_bounces, nee_from, counters);
+    k_ns_vertex<<<g128, 128, 0, st>>>(D, fc, B, npix, b, max_bounces, nee_from, counters, Q.refs, Q.count);
     prof_end(ctx, rec, st);
-    snprintf(name, sizeof(name), "ns_any.%u", b);
-    launches += 1 + traced_launch(ctx, name, B.srays, npix, true, nullptr, nullptr, nullptr, B.vis, st);
+    snprintf(name, sizeof(name), "trace.q%d", q);
+    launches += 1 + traced_launch_q(ctx, name, segs, Q, st);
+    if (b == 1) cudaEventRecord(ctx->ev[4], st);
+    Q = ref_queue(ctx, ++q, qcap);
   }
+  if (max_bounces == 0) {
+    // no path vertices: the ReSTIR final rays still have to be traced
+    if (nee_from) { snprintf(name, sizeof(name), "trace.q%d", q); launches += traced_launch_q(ctx, name, segs, Q, st); }
+    cudaEventRecord(ctx->ev[4], st);
+  }
+  if (nee_from) launches += restir_ns_resolve(ctx, st);
+  else cudaMemsetAsync(ctx->planes.direct + (size_t)fc.row0 * fc.W, 0, 16ull * npix, st);
   rec = prof_begin(ctx, "ns_resolve", npix, false, false, st);
   k_ns_resolve<<<(npix + 255) / 256, 256, 0, st>>>(D, fc, ctx->planes, B, npix, max_bounces, nee_from);
   prof_end(ctx, rec, st);

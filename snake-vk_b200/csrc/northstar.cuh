@@ -119,6 +119,29 @@ __device__ __forceinline__ void put_dead(float4* q, size_t i) {
   q[2 * i + 1] = make_float4(0.f, 1.f, 0.f, -1.0f);
 }
 
+// ---- compact ray-reference queue (trace_q.cu): segments of the north-star frame
+constexpr uint32_t SEG_RS_PL = 0u, SEG_RS_EM = 1u, SEG_RS_DIR = 2u, SEG_NS_CLOSEST = 3u, SEG_NS_SHADOW = 4u;
+__device__ __forceinline__ uint32_t make_ref(uint32_t seg, size_t slot) { return (seg << REF_SLOT_BITS) | (uint32_t)slot; }
+// warp-aggregated append of up to three references per lane (one atomic per warp); every lane of the warp must call it.
+// The warp's references land segment by segment, so a traversal warp that takes 32 consecutive entries mostly gets
+// rays of one kind from neighbouring pixels.
+__device__ __forceinline__ void q_append3(uint32_t* refs, uint32_t* count, bool h0, uint32_t r0, bool h1, uint32_t r1, bool h2, uint32_t r2) {
+  const uint32_t m0 = __ballot_sync(0xFFFFFFFFu, h0), m1 = __ballot_sync(0xFFFFFFFFu, h1), m2 = __ballot_sync(0xFFFFFFFFu, h2);
+  const uint32_t n0 = __popc(m0), n1 = __popc(m1), tot = n0 + n1 + __popc(m2);
+  if (tot == 0u) return;
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t base = 0;
+  if (lane == 0) base = atomicAdd(count, tot);
+  base = __shfl_sync(0xFFFFFFFFu, base, 0);
+  const uint32_t below = (1u << lane) - 1u;
+  if (h0) refs[base + __popc(m0 & below)] = r0;
+  if (h1) refs[base + n0 + __popc(m1 & below)] = r1;
+  if (h2) refs[base + n0 + n1 + __popc(m2 & below)] = r2;
+}
+
+// marks a path as ended: only the tmax word of the slot is read back by the next vertex stage
+__device__ __forceinline__ void put_dead_dir(float4* q, size_t i) { q[2 * i + 1] = make_float4(0.f, 1.f, 0.f, -1.0f); }
+
 __device__ __forceinline__ void flush_counts(unsigned long long n_shadow, unsigned long long n_closest, unsigned long long* counters) {
   for (int o = 16; o > 0; o >>= 1) {
     n_shadow += __shfl_xor_sync(0xFFFFFFFFu, n_shadow, o);

@@ -116,16 +116,17 @@ __device__ __forceinline__ void pixel_of(const FrameConsts& fc, uint32_t i, uint
 
 // ---- stage 1 ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_rs_initial(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, RsBuffers B, uint32_t npix,
-                                                    unsigned long long* counters) {
+                                                    unsigned long long* counters, uint32_t* q_refs, uint32_t* q_count) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long n_shadow = 0;
+  bool ray_pl = false, ray_em = false;
+  size_t px = 0;
   if (i < npix) {
-    uint32_t x, y; size_t px;
+    uint32_t x, y;
     pixel_of(fc, i, x, y, px);
     const size_t np = rp.npix_frame;
     Reservoir r; rs_empty(r);
     float p_sel_pl = 0.0f, p_sel_em = 0.0f;
-    bool ray_pl = false, ray_em = false;
     const uint32_t n_pl = D.lights->num_pointlights, n_em = D.num_emissive;
     if (px_shaded(P, px)) {
       RsSurf s; vec3 pos, n_raw;
@@ -177,12 +178,14 @@ __global__ void __launch_bounds__(128) k_rs_initial(SceneDev D, FrameConsts fc, 
         }
       }
     }
-    if (n_pl > 0 && !ray_pl) put_dead(B.rays, px);
-    if (n_em > 0 && !ray_em) put_dead(B.rays, np + px);
+    // no shadow ray: the (empty) sample counts as unoccluded
+    if (n_pl > 0 && !ray_pl) B.vis[px] = 1.0f;
+    if (n_em > 0 && !ray_em) B.vis[np + px] = 1.0f;
     B.phat[px] = make_float2(p_sel_pl, p_sel_em);
     const ResPlanes half1{P.res[1][0], P.res[1][1], P.res[1][2]};
     store_reservoir(half1, px, r);
   }
+  q_append3(q_refs, q_count, ray_pl, make_ref(SEG_RS_PL, px), ray_em, make_ref(SEG_RS_EM, px), false, 0u);
   flush_counts(n_shadow, 0ull, counters);
 }
 
@@ -248,17 +251,18 @@ __global__ void __launch_bounds__(128) k_rs_temporal(SceneDev D, FrameConsts fc,
 constexpr int RS_MAXN = 9;  // this pixel + up to 8 neighbours
 
 __global__ void __launch_bounds__(128) k_rs_spatial(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, RsBuffers B, uint32_t npix,
-                                                    unsigned long long* counters) {
+                                                    unsigned long long* counters, uint32_t* q_refs, uint32_t* q_count) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long n_shadow = 0;
+  bool ray0 = false, ray1 = false, ray2 = false;
+  size_t px = 0;
   if (i < npix) {
-    uint32_t x, y; size_t px;
+    uint32_t x, y;
     pixel_of(fc, i, x, y, px);
     const size_t np = rp.npix_frame;
     const ResPlanes half0{P.res[0][0], P.res[0][1], P.res[0][2]}, half1{P.res[1][0], P.res[1][1], P.res[1][2]};
     Reservoir out; rs_empty(out);
     vec3 C0 = v3(0.0f), C1 = v3(0.0f), C2 = v3(0.0f);
-    bool ray0 = false, ray1 = false, ray2 = false;
     const uint32_t n_pl = D.lights->num_pointlights, n_em = D.num_emissive;
     if (px_shaded(P, px)) {
       RsSurf s; vec3 pos, n_raw;
@@ -359,13 +363,14 @@ __global__ void __launch_bounds__(128) k_rs_spatial(SceneDev D, FrameConsts fc, 
       }
     }
     store_reservoir(half0, px, out);
-    if (n_pl > 0 && !ray0) put_dead(B.rays, px);
-    if (n_em > 0 && !ray1) put_dead(B.rays, np + px);
-    if (!ray2) put_dead(B.rays, 2 * np + px);
+    if (n_pl > 0 && !ray0) B.vis[px] = 1.0f;
+    if (n_em > 0 && !ray1) B.vis[np + px] = 1.0f;
+    if (!ray2) B.vis[2 * np + px] = 1.0f;
     B.C[px] = make_float4(C0.x, C0.y, C0.z, 0.0f);
     B.C[np + px] = make_float4(C1.x, C1.y, C1.z, 0.0f);
     B.C[2 * np + px] = make_float4(C2.x, C2.y, C2.z, 0.0f);
   }
+  q_append3(q_refs, q_count, ray0, make_ref(SEG_RS_PL, px), ray1, make_ref(SEG_RS_EM, px), ray2, make_ref(SEG_RS_DIR, px));
   flush_counts(n_shadow, 0ull, counters);
 }
 
@@ -381,54 +386,81 @@ __global__ void __launch_bounds__(256) k_rs_resolve(FrameConsts fc, PixelPlanes 
 
 }  // namespace
 
-int launch_restir_ns(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st) {
+namespace {
+struct RsLaunch {
+  RsBuffers B;
+  FrameConsts f1;  // stages 1-2 also cover the halo rows whose temporal reservoirs this band's spatial reuse reads (snkpt_set_halo)
+  uint32_t npix1, npix, npix_frame;
+  RsParams rp;
+};
+RsLaunch rs_launch(SnkPt* ctx, const SnkRtSettings& s) {
   const FrameConsts& fc = ctx->fc;
-  const uint32_t npix_frame = fc.W * fc.H;
+  RsLaunch L;
+  L.npix_frame = fc.W * fc.H;
+  L.B.rays = ctx->wave[8].as<float4>(); L.B.vis = ctx->wave[9].as<float>(); L.B.phat = ctx->wave[10].as<float2>(); L.B.C = ctx->wave[11].as<float4>();
+  L.f1 = fc;
+  L.f1.row0 = fc.row0 > ctx->halo_pass1 ? fc.row0 - ctx->halo_pass1 : 0u;
+  L.f1.row1 = fc.row1 + ctx->halo_pass1 < fc.H ? fc.row1 + ctx->halo_pass1 : fc.H;
+  L.npix1 = fc.W * (L.f1.row1 - L.f1.row0);
+  L.npix = fc.W * (fc.row1 - fc.row0);
+  L.rp = RsParams{s.num_temporal_resamples, s.num_spatial_resamples, s.ris_iters, s.m_cap, s.neighbour_radius, s.normal_threshold,
+                  (fc.prev_frame_invalid || !ctx->history_valid) ? 0u : 1u, L.npix_frame};
+  return L;
+}
+}  // namespace
+
+// scratch planes + the three shadow-ray segments (slot = full-frame pixel)
+int restir_ns_prepare(SnkPt* ctx, TraceSegs& segs, cudaStream_t st) {
+  const uint32_t npix_frame = ctx->fc.W * ctx->fc.H;
   const size_t sizes[4] = {96ull * npix_frame, 12ull * npix_frame, 8ull * npix_frame, 48ull * npix_frame};
   for (int k = 0; k < 4; ++k) {
     cudaError_t e = ctx->wave[8 + k].reserve(sizes[k], false, st);
     if (e != cudaSuccess) { ctx->err = std::string("north-star ReSTIR queues: ") + cudaGetErrorString(e); return SNKPT_E_NOMEM; }
   }
-  RsBuffers B;
-  B.rays = ctx->wave[8].as<float4>(); B.vis = ctx->wave[9].as<float>(); B.phat = ctx->wave[10].as<float2>(); B.C = ctx->wave[11].as<float4>();
-  // stages 1-2 also cover the halo rows whose temporal reservoirs this band's spatial reuse reads (snkpt_set_halo)
-  FrameConsts f1 = fc;
-  f1.row0 = fc.row0 > ctx->halo_pass1 ? fc.row0 - ctx->halo_pass1 : 0u;
-  f1.row1 = fc.row1 + ctx->halo_pass1 < fc.H ? fc.row1 + ctx->halo_pass1 : fc.H;
-  const uint32_t npix1 = fc.W * (f1.row1 - f1.row0), npix = fc.W * (fc.row1 - fc.row0);
-  RsParams rp{s.num_temporal_resamples, s.num_spatial_resamples, s.ris_iters, s.m_cap, s.neighbour_radius, s.normal_threshold,
-              (fc.prev_frame_invalid || !ctx->history_valid) ? 0u : 1u, npix_frame};
+  float4* rays = ctx->wave[8].as<float4>();
+  float* vis = ctx->wave[9].as<float>();
+  for (uint32_t k = 0; k < 3; ++k) segs.s[SEG_RS_PL + k] = TraceSeg{rays + 2ull * k * npix_frame, nullptr, nullptr, vis + (size_t)k * npix_frame, 1u, 0u};
+  return SNKPT_OK;
+}
+
+// stage 1: candidate generation; appends the shadow rays of the initial samples to q
+int restir_ns_initial(SnkPt* ctx, const SnkRtSettings& s, const RefQueue& q, cudaStream_t st) {
+  const RsLaunch L = rs_launch(ctx, s);
+  unsigned long long* counters = reinterpret_cast<unsigned long long*>(ctx->dev_counters.as<uint32_t>() + 2);
+  const int rec = prof_begin(ctx, "rs_initial", L.npix1, false, false, st);
+  k_rs_initial<<<(L.npix1 + 127) / 128, 128, 0, st>>>(ctx->scene_dev(), L.f1, ctx->planes, L.rp, L.B, L.npix1, counters, q.refs, q.count);
+  prof_end(ctx, rec, st);
+  return 1;
+}
+
+// stages 2-3 (after the initial shadow rays are resolved): temporal reuse, spatial reuse + final evaluation; appends
+// the final shadow rays (point, emissive, directional) to q
+int restir_ns_reuse(SnkPt* ctx, const SnkRtSettings& s, const RefQueue& q, cudaStream_t st) {
+  const RsLaunch L = rs_launch(ctx, s);
   unsigned long long* counters = reinterpret_cast<unsigned long long*>(ctx->dev_counters.as<uint32_t>() + 2);
   const SceneDev D = ctx->scene_dev();
+  int rec = prof_begin(ctx, "rs_temporal", L.npix1, false, false, st);
+  k_rs_temporal<<<(L.npix1 + 127) / 128, 128, 0, st>>>(D, L.f1, ctx->planes, L.rp, L.B, L.npix1);
+  prof_end(ctx, rec, st);
+  cudaEventRecord(ctx->ev[3], st);
+  rec = prof_begin(ctx, "rs_spatial", L.npix, false, false, st);
+  k_rs_spatial<<<(L.npix + 127) / 128, 128, 0, st>>>(D, ctx->fc, ctx->planes, L.rp, L.B, L.npix, counters, q.refs, q.count);
+  prof_end(ctx, rec, st);
+  return 2;
+}
+
+// direct = sum of final contribution x visibility
+int restir_ns_resolve(SnkPt* ctx, cudaStream_t st) {
+  const FrameConsts& fc = ctx->fc;
+  const uint32_t npix = fc.W * (fc.row1 - fc.row0), npix_frame = fc.W * fc.H;
+  RsBuffers B;
+  B.rays = ctx->wave[8].as<float4>(); B.vis = ctx->wave[9].as<float>(); B.phat = ctx->wave[10].as<float2>(); B.C = ctx->wave[11].as<float4>();
   // light counts as of the last snkpt_set_lights / snkpt_set_instances (host mirrors)
   const bool has_pl = ctx->num_pointlights > 0, has_em = ctx->num_emissive > 0;
-  int launches = 0;
-  cudaEventRecord(ctx->ev[2], st);
-  int rec = prof_begin(ctx, "rs_initial", npix1, false, false, st);
-  k_rs_initial<<<(npix1 + 127) / 128, 128, 0, st>>>(D, f1, ctx->planes, rp, B, npix1, counters);
-  prof_end(ctx, rec, st);
-  ++launches;
-  const size_t off1 = (size_t)f1.row0 * fc.W, off = (size_t)fc.row0 * fc.W;
-  if (has_pl) launches += traced_launch(ctx, "rs_any.init_pl", B.rays + 2 * off1, npix1, true, nullptr, nullptr, nullptr, B.vis + off1, st);
-  if (has_em) launches += traced_launch(ctx, "rs_any.init_em", B.rays + 2 * (npix_frame + off1), npix1, true, nullptr, nullptr, nullptr, B.vis + npix_frame + off1, st);
-  rec = prof_begin(ctx, "rs_temporal", npix1, false, false, st);
-  k_rs_temporal<<<(npix1 + 127) / 128, 128, 0, st>>>(D, f1, ctx->planes, rp, B, npix1);
-  prof_end(ctx, rec, st);
-  ++launches;
-  cudaEventRecord(ctx->ev[3], st);
-  rec = prof_begin(ctx, "rs_spatial", npix, false, false, st);
-  k_rs_spatial<<<(npix + 127) / 128, 128, 0, st>>>(D, fc, ctx->planes, rp, B, npix, counters);
-  prof_end(ctx, rec, st);
-  ++launches;
-  if (has_pl) launches += traced_launch(ctx, "rs_any.final_pl", B.rays + 2 * off, npix, true, nullptr, nullptr, nullptr, B.vis + off, st);
-  if (has_em) launches += traced_launch(ctx, "rs_any.final_em", B.rays + 2 * (npix_frame + off), npix, true, nullptr, nullptr, nullptr, B.vis + npix_frame + off, st);
-  launches += traced_launch(ctx, "rs_any.final_dir", B.rays + 2 * (2ull * npix_frame + off), npix, true, nullptr, nullptr, nullptr, B.vis + 2ull * npix_frame + off, st);
-  rec = prof_begin(ctx, "rs_resolve", npix, false, false, st);
+  const int rec = prof_begin(ctx, "rs_resolve", npix, false, false, st);
   k_rs_resolve<<<(npix + 255) / 256, 256, 0, st>>>(fc, ctx->planes, B, npix, npix_frame, has_pl ? 1u : 0u, has_em ? 1u : 0u);
   prof_end(ctx, rec, st);
-  ++launches;
-  cudaEventRecord(ctx->ev[4], st);
-  return launches;
+  return 1;
 }
 
 }  // namespace snk

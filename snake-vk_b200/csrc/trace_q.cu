@@ -1,0 +1,187 @@
+// trace_q.cu — queue traversal: ONE persistent launch serves every ray the frame has ready at that point.
+//
+// The north-star frame used to launch the persistent traversal kernel once per ray kind and bounce
+// (11 launches on C2: rs_any.init_pl … ns_any.4, profiles/r01n_quick_northstar.txt); the late ones carried
+// 50-300 k live rays in 2 M slots and ran at 0.2-0.8 Grays/s because a ray's latency, not throughput, set their
+// duration. Here the shading stages append 32-bit ray references (segment << 28 | slot) of their LIVE rays to a
+// compact queue (warp-aggregated atomics, northstar.cuh:q_append3), and one launch of k_trace_q drains the queue:
+// closest-hit and any-hit rays of different stages mixed in one warp (the kind is a per-lane flag), results written
+// to the slot of the ray's own segment — so the output does not depend on queue order.
+// Replaces the driver side of vkCmdTraceRaysKHR (Core/src/rendering/Raytracing.cpp:253, :260) like trace.cu.
+#include "kernels.h"
+
+namespace snk {
+
+namespace {
+
+constexpr int TQ_THREADS = 128;
+#ifndef SNK_TQ_CTAS
+#define SNK_TQ_CTAS 8
+#endif
+#ifndef SNK_TQ_VOTE
+#define SNK_TQ_VOTE 0  // 0: node + triangle + pop every iteration (trav_step); 1: one voted phase per iteration (trav_vote_step) — measured 20 % slower (r01r)
+#endif
+#ifndef SNK_TQ_REFILL_MIN
+#define SNK_TQ_REFILL_MIN 8  // idle lanes that trigger a refill
+#endif
+
+__global__ void __launch_bounds__(TQ_THREADS, SNK_TQ_CTAS)
+k_trace_q(TraceScene S, TraceSegs segs, const uint32_t* __restrict__ refs, const uint32_t* __restrict__ count_ptr,
+          uint32_t* __restrict__ ticket, float* __restrict__ prof_t) {
+  __shared__ uint2 sm_stack[SHORT_STACK * TQ_THREADS];
+  const uint32_t lane = threadIdx.x & 31u;
+  const StackRef stk{sm_stack + threadIdx.x,
+                     S.spill + ((size_t)blockIdx.x * (TQ_THREADS / 32) + (threadIdx.x >> 5)) * (SPILL_STACK * 32) + lane};
+  const uint32_t n = __ldcg(count_ptr);
+  if (n == 0u || S.tlas_node_count == 0u) {
+    // nothing to hit: every queued ray misses
+    for (uint32_t q = blockIdx.x * TQ_THREADS + threadIdx.x; q < n; q += gridDim.x * TQ_THREADS) {
+      const uint32_t ref = __ldg(refs + q);
+      const TraceSeg& sg = segs.s[ref >> REF_SLOT_BITS];
+      const uint32_t slot = ref & REF_SLOT_MASK;
+      if (sg.vis) sg.vis[slot] = 1.0f;
+      if (sg.hit) sg.hit[slot] = make_float4(-1.0f, 0.f, 0.f, __uint_as_float(0xFFFFFFFFu));
+      if (sg.inst) sg.inst[slot] = 0xFFFFFFFFu;
+      if (prof_t) prof_t[q] = -1.0f;
+    }
+    return;
+  }
+  Trav t;
+  bool active = false, exhausted = false, any = false;
+  uint32_t qpos = 0;
+  while (true) {
+    // ---- refill: lanes without a ray take the next queue entries (one atomic per warp)
+    const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);
+    if (!exhausted && __popc(idle) >= SNK_TQ_REFILL_MIN) {
+      const uint32_t cnt = __popc(idle);
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(ticket, cnt);
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      if (!active) {
+        const uint32_t q = base + __popc(idle & ((1u << lane) - 1u));
+        if (q < n) {
+          const uint32_t ref = __ldg(refs + q);
+          const TraceSeg& sg = segs.s[ref >> REF_SLOT_BITS];
+          const float4* rp = sg.rays + 2ull * (ref & REF_SLOT_MASK);
+          const float4 a = __ldcg(rp), b = __ldcg(rp + 1);
+          trav_begin(t, a, b);
+          any = sg.any != 0u;
+          qpos = q;
+          active = true;  // the producers only queue live rays (tmax > tmin)
+        }
+      }
+      if (base + cnt >= n) exhausted = true;
+    }
+    if (__ballot_sync(0xFFFFFFFFu, active) == 0u) {
+      if (exhausted) break;
+      continue;
+    }
+#if SNK_TQ_VOTE
+    const bool finished = trav_vote_step<TQ_THREADS>(S, t, stk, active, any);
+#else
+    const bool finished = trav_step_impl<TQ_THREADS>(S, t, stk, active, 0xFFFFFFFFu, any);
+#endif
+    if (finished) {
+      const uint32_t ref = __ldg(refs + qpos);
+      const TraceSeg& sg = segs.s[ref >> REF_SLOT_BITS];
+      const uint32_t slot = ref & REF_SLOT_MASK;
+      if (any) {
+        sg.vis[slot] = t.best.t >= 0.0f ? 0.0f : 1.0f;  // Shadow.rmiss:12 → 1 - float(hit)
+      } else {
+        sg.hit[slot] = make_float4(t.best.t, t.best.u, t.best.v, __uint_as_float(t.best.prim));
+        sg.inst[slot] = t.best.inst;
+      }
+      if (prof_t) prof_t[qpos] = t.best.t;
+      active = false;
+    }
+  }
+}
+
+// Diagnostic replay (profiling level 2): order-independent work of every queued ray, as k_count_work_sum (trace.cu);
+// sums8 = {live rays, nodes, leaf records, instances, any-hit rays among the live ones}.
+__device__ void count_subtree_q(const RaySpace& r0, const uint4* __restrict__ nodes, uint32_t root, float tmin, float tend, uint32_t& n_nodes,
+                                uint32_t& leaf_bits_total, uint32_t* leaf_out, int& leaf_n, int leaf_cap) {
+  RaySpace r = r0;
+  r.octinv = 0;
+  uint32_t st[64];
+  int sp = 0;
+  st[sp++] = root;
+  while (sp) {
+    const uint32_t ni = st[--sp];
+    uint4 n0, n1, n2, n3, n4;
+    load_node(nodes, ni, n0, n1, n2, n3, n4);
+    ++n_nodes;
+    const uint32_t hm = intersect_node(r, n0, n1, n2, n3, n4, tmin, tend);
+    const uint32_t imask = n0.w >> 24;
+    for (uint32_t s = 0; s < 8; ++s)
+      if (hm & (1u << (24 + s))) { if (sp < 64) st[sp++] = n1.x + __popc(imask & ((1u << s) - 1u)); }
+    uint32_t tb = hm & 0x00FFFFFFu;
+    leaf_bits_total += __popc(tb);
+    while (leaf_out && tb) {
+      const uint32_t bit = __ffs(tb) - 1;
+      tb &= tb - 1;
+      if (leaf_n < leaf_cap) leaf_out[leaf_n++] = n1.y + bit;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TQ_THREADS) k_count_work_q(TraceScene S, TraceSegs segs, const uint32_t* __restrict__ refs,
+                                                             const uint32_t* __restrict__ count_ptr, const float* __restrict__ prof_t,
+                                                             unsigned long long* __restrict__ sums8) {
+  const uint32_t n = __ldcg(count_ptr);
+  unsigned long long v[5] = {0, 0, 0, 0, 0};
+  for (uint32_t q = blockIdx.x * TQ_THREADS + threadIdx.x; q < n; q += gridDim.x * TQ_THREADS) {
+    const uint32_t ref = refs[q];
+    const TraceSeg& sg = segs.s[ref >> REF_SLOT_BITS];
+    const float4* rp = sg.rays + 2ull * (ref & REF_SLOT_MASK);
+    const float4 a = rp[0], b = rp[1];
+    if (!(b.w >= a.w) || !S.tlas_node_count) continue;
+    const float ht = prof_t[q];
+    const float tend = ht >= 0.f ? ht : b.w;
+    uint32_t nodes = 0, recs = 0, insts = 0;
+    RaySpace r;
+    setup_ray_space(r, a.x, a.y, a.z, b.x, b.y, b.z);
+    uint32_t leaf[64];
+    int ln = 0;
+    count_subtree_q(r, S.tlas_nodes, 0u, a.w, tend, nodes, insts, leaf, ln, 64);
+    for (int k = 0; k < ln; ++k) {
+      const uint32_t slot = S.tlas_leaf_ids[leaf[k]];
+      const float4* M = reinterpret_cast<const float4*>(S.inst + slot);
+      const float4 r0 = M[0], r1 = M[1], r2 = M[2];
+      RaySpace o;
+      setup_ray_space(o, r0.x * a.x + r0.y * a.y + r0.z * a.z + r0.w, r1.x * a.x + r1.y * a.y + r1.z * a.z + r1.w,
+                      r2.x * a.x + r2.y * a.y + r2.z * a.z + r2.w, r0.x * b.x + r0.y * b.y + r0.z * b.z,
+                      r1.x * b.x + r1.y * b.y + r1.z * b.z, r2.x * b.x + r2.y * b.y + r2.z * b.z);
+      int unused = 0;
+      count_subtree_q(o, S.blas_nodes, S.inst[slot].blas_root, a.w, tend, nodes, recs, nullptr, unused, 0);
+    }
+    v[0] += 1; v[1] += nodes; v[2] += recs; v[3] += insts; v[4] += sg.any ? 1 : 0;
+  }
+#pragma unroll
+  for (int k = 0; k < 5; ++k) {
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xFFFFFFFFu, v[k], o);
+    if ((threadIdx.x & 31) == 0 && v[k]) atomicAdd(sums8 + k, v[k]);
+  }
+}
+
+}  // namespace
+
+int launch_trace_q(const TraceScene& S, const TraceSegs& segs, const RefQueue& q, float* prof_t, cudaStream_t st) {
+  if (!q.refs || !q.count || !q.ticket || !S.spill || q.cap == 0) return 0;
+  // persistent grid; a queue that cannot fill it gets one CTA per 128 possible entries
+  const uint64_t blocks = ((uint64_t)q.cap + TQ_THREADS - 1) / TQ_THREADS;
+  const uint64_t persistent = 148ull * SNK_TQ_CTAS;
+  const int grid = (int)(blocks < persistent ? blocks : persistent);
+  k_trace_q<<<grid, TQ_THREADS, 0, st>>>(S, segs, q.refs, q.count, q.ticket, prof_t);
+  return 1;
+}
+
+int launch_count_work_q(const TraceScene& S, const TraceSegs& segs, const RefQueue& q, const float* prof_t, unsigned long long* sums8,
+                        cudaStream_t st) {
+  if (!q.refs || !q.count || q.cap == 0 || !prof_t) return 0;
+  const uint64_t blocks = ((uint64_t)q.cap + TQ_THREADS - 1) / TQ_THREADS;
+  k_count_work_q<<<(unsigned)(blocks < 148ull * 16 ? blocks : 148ull * 16), TQ_THREADS, 0, st>>>(S, segs, q.refs, q.count, prof_t, sums8);
+  return 1;
+}
+
+}  // namespace snk

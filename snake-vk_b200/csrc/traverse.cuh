@@ -30,6 +30,25 @@ struct TraceScene {
   uint2* spill;                   // global overflow area of the short stacks (persistent kernels), SPILL_STACK x 32 per warp
 };
 
+// queue traversal (trace_q.cu): a ray reference = segment << REF_SLOT_BITS | slot; a segment names the ray plane the
+// slot indexes and where that ray's result goes (closest: hit + inst planes; any: visibility plane)
+constexpr uint32_t REF_SLOT_BITS = 28u, REF_SLOT_MASK = (1u << REF_SLOT_BITS) - 1u;
+constexpr int TRACE_MAX_SEGS = 8;
+struct TraceSeg {
+  const float4* rays;  // 2 x float4 per slot (o,tmin | d,tmax)
+  float4* hit;         // closest: t,u,v,prim
+  uint32_t* inst;      // closest: instance custom index
+  float* vis;          // any: 1 = unoccluded, 0 = occluded
+  uint32_t any, pad;
+};
+struct TraceSegs { TraceSeg s[TRACE_MAX_SEGS]; };
+struct RefQueue {
+  uint32_t* refs;    // compact list of ray references
+  uint32_t* count;   // device counter the producers append through
+  uint32_t* ticket;  // device counter the traversal kernel draws from
+  uint32_t cap;      // capacity in references
+};
+
 struct HitRec {
   float t, u, v;
   uint32_t prim, inst;
@@ -119,10 +138,68 @@ __device__ __forceinline__ uint32_t sign_extend_s8x4(uint32_t x) {
   return v;
 }
 
+// float 1 + q * 2^-15 of byte `k` of `w` (q = 0..255): the byte is dropped into mantissa bits 8..15 of 1.0f with ONE
+// PRMT on the ALU pipe. The 48 I2F.U8 per node this replaces run on the quarter-rate XU pipe, which ncu showed as the
+// busiest pipe of the traversal kernel (58 % of peak, profiles/r01q_prof_traceq.txt).
+#ifndef SNK_NODE_PRMT
+#define SNK_NODE_PRMT 0  // measured (r01r): no gain over I2F.U8 — the kernel is bound by issue slots, not by the XU pipe — and 6 more instructions per node
+#endif
+template <int K>
+__device__ __forceinline__ float byte_to_unit_float(uint32_t w) {
+  uint32_t v;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(v) : "r"(w), "r"(0x3F800000u), "n"(0x7604 | (K << 4)));
+  return __uint_as_float(v);
+}
+
 // intersect the 8 quantised child boxes of one node; returns the hit mask
 // (bits 24..31: inner children in octant order, bits 0..23: leaf records). Branch-free: the per-child bit
 // position / bit pattern are derived four children at a time from the meta bytes (Ylitie et al. 2017), an
 // empty slot has meta 0 and contributes no bits whatever its box test says.
+// Plane distance: t = q * a + b with a = step / d, b = (origin - o) / d is evaluated as f(q) * A + B with
+// f(q) = 1 + q * 2^-15, A = 2^15 a, B = b - A. B carries one extra rounding of at most 2^-24 |B| <= 2^-24 |b| + 2^-9 |a|;
+// the second term (1/512 of a quantisation step) is covered by moving near planes down and far planes up by
+// 2^-22 |A| = 2^-7 |a| per axis, the first by the relative BOX_PAD as before. The tests only have to be conservative.
+#if SNK_NODE_PRMT
+__device__ __forceinline__ uint32_t intersect_node(const RaySpace& r, const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3,
+                                                   const uint4 n4, float tmin, float tmax) {
+  const float px = __uint_as_float(n0.x), py = __uint_as_float(n0.y), pz = __uint_as_float(n0.z);
+  // step * 2^15: exponent bytes + 15
+  const float sx = __uint_as_float(((n0.w & 0xFFu) + 15u) << 23), sy = __uint_as_float((((n0.w >> 8) & 0xFFu) + 15u) << 23),
+              sz = __uint_as_float((((n0.w >> 16) & 0xFFu) + 15u) << 23);
+  const float ax = sx * r.idx, ay = sy * r.idy, az = sz * r.idz;
+  const float bx = fmaf(px - r.ox, r.idx, -ax), by = fmaf(py - r.oy, r.idy, -ay), bz = fmaf(pz - r.oz, r.idz, -az);
+  const float ex = fabsf(ax) * 2.384185791015625e-07f, ey = fabsf(ay) * 2.384185791015625e-07f, ez = fabsf(az) * 2.384185791015625e-07f;
+  const float bxn = bx - ex, bxf = bx + ex, byn = by - ey, byf = by + ey, bzn = bz - ez, bzf = bz + ez;
+  // near / far plane words per axis
+  const bool nx = r.idx < 0.f, ny = r.idy < 0.f, nz = r.idz < 0.f;
+  const uint32_t xn[2] = {nx ? n3.z : n2.x, nx ? n3.w : n2.y}, xf[2] = {nx ? n2.x : n3.z, nx ? n2.y : n3.w};
+  const uint32_t yn[2] = {ny ? n4.x : n2.z, ny ? n4.y : n2.w}, yf[2] = {ny ? n2.z : n4.x, ny ? n2.w : n4.y};
+  const uint32_t zn[2] = {nz ? n4.z : n3.x, nz ? n4.w : n3.y}, zf[2] = {nz ? n3.x : n4.z, nz ? n3.y : n4.w};
+  const uint32_t octinv4 = r.octinv * 0x01010101u;
+  uint32_t hitmask = 0;
+#define SNK_CHILD(J)                                                                                                          \
+  {                                                                                                                           \
+    const float tx0 = fmaf(byte_to_unit_float<J>(xn[h]), ax, bxn), tx1 = fmaf(byte_to_unit_float<J>(xf[h]), ax, bxf);           \
+    const float ty0 = fmaf(byte_to_unit_float<J>(yn[h]), ay, byn), ty1 = fmaf(byte_to_unit_float<J>(yf[h]), ay, byf);           \
+    const float tz0 = fmaf(byte_to_unit_float<J>(zn[h]), az, bzn), tz1 = fmaf(byte_to_unit_float<J>(zf[h]), az, bzf);           \
+    const float tn = fmaxf(fmaxf(tx0, ty0), fmaxf(tz0, tmin));                                                                \
+    const float tf = fminf(fminf(tx1, ty1), fminf(tz1, tmax));                                                                \
+    const uint32_t bits = ((child_bits4 >> (8 * J)) & 0xFFu) << ((bit_index4 >> (8 * J)) & 0xFFu);                            \
+    hitmask |= (tn <= tf * BOX_PAD) ? bits : 0u;                                                                              \
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const uint32_t meta4 = h ? n1.w : n1.z;
+    const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+    const uint32_t inner_mask4 = sign_extend_s8x4(is_inner4 << 3);
+    const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
+    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+    SNK_CHILD(0) SNK_CHILD(1) SNK_CHILD(2) SNK_CHILD(3)
+  }
+#undef SNK_CHILD
+  return hitmask;
+}
+#else
 __device__ __forceinline__ uint32_t intersect_node(const RaySpace& r, const uint4 n0, const uint4 n1, const uint4 n2, const uint4 n3,
                                                    const uint4 n4, float tmin, float tmax) {
   const float px = __uint_as_float(n0.x), py = __uint_as_float(n0.y), pz = __uint_as_float(n0.z);
@@ -158,6 +235,7 @@ __device__ __forceinline__ uint32_t intersect_node(const RaySpace& r, const uint
   }
   return hitmask;
 }
+#endif
 
 __device__ __forceinline__ void load_node(const uint4* __restrict__ nodes, uint32_t idx, uint4& n0, uint4& n1, uint4& n2, uint4& n3,
                                           uint4& n4) {
@@ -260,8 +338,8 @@ __device__ __forceinline__ void trav_begin(Trav& t, float4 a, float4 b) {
 //   4. pop phase: lanes with nothing pending pop the stack; popping below the instance-entry height returns
 //      to world space; an empty stack finishes the ray
 // Returns true when this lane's ray is finished (stack empty, or first hit for ANY).
-template <bool ANY, int STRIDE>
-__device__ __forceinline__ bool trav_step(const TraceScene& S, Trav& t, const StackRef& stk, bool active, uint32_t warp) {
+template <int STRIDE>
+__device__ __forceinline__ bool trav_step_impl(const TraceScene& S, Trav& t, const StackRef& stk, bool active, uint32_t warp, const bool ANY) {
   // ---- 1
   uint32_t node_idx = 0;
   const uint4* nodes = S.blas_nodes;
@@ -346,6 +424,115 @@ __device__ __forceinline__ bool trav_step(const TraceScene& S, Trav& t, const St
   if (active && !done && t.T.y == 0u && (t.G.y & 0xFF000000u) == 0u) {
     if (t.in_blas && t.sp == t.blas_sp) {
       // leave the instance: back to world space (no triangles are tested in the TLAS, so only the box part)
+      setup_box_space(t.r, t.ox, t.oy, t.oz, t.dx, t.dy, t.dz);
+      t.in_blas = false; t.tri_ready = false;
+    }
+    if (t.sp == 0) done = true;
+    else {
+      const uint2 e = stk_pop<STRIDE>(stk, t.sp);
+      if (e.y & 0xFF000000u) t.G = e;
+      else { t.T = e; t.G = make_uint2(0u, 0u); }
+    }
+  }
+  return done;
+}
+
+template <bool ANY, int STRIDE>
+__device__ __forceinline__ bool trav_step(const TraceScene& S, Trav& t, const StackRef& stk, bool active, uint32_t warp) {
+  return trav_step_impl<STRIDE>(S, t, stk, active, warp, ANY);
+}
+
+// ---- phase-voting form (queue traversal kernel, trace_q.cu) ------------------------------------------------------------
+// trav_step runs its node / triangle / instance-entry code every iteration with whatever subset of lanes wants
+// it: ncu (profiles/r01m_prof_trace.txt) shows 13-14 of 32 threads active per issued instruction at ~78 % issue
+// utilisation, i.e. the kernel is bound by issue slots spent on mostly-empty phases. Here every lane names the ONE
+// phase it needs next and the warp executes only the phase with the most takers; the others wait (they cost no
+// issue slots) until their phase wins the vote. Invariant between calls: an active lane has an inner-node group
+// (G) or a leaf-record group (T) pending.
+enum : uint32_t { WANT_NONE = 0u, WANT_ENTER = 1u, WANT_NODE = 2u, WANT_TRI = 3u };
+
+#ifndef SNK_VOTE_TRI_BIAS
+#define SNK_VOTE_TRI_BIAS 0  // the triangle phase also runs when it has at least (node takers - bias) takers
+#endif
+
+template <int STRIDE>
+__device__ __forceinline__ bool trav_vote_step(const TraceScene& S, Trav& t, const StackRef& stk, bool active, bool any) {
+  constexpr uint32_t FULL = 0xFFFFFFFFu;
+  uint32_t want = WANT_NONE;
+  if (active) want = t.T.y != 0u ? (t.in_blas ? WANT_TRI : WANT_ENTER) : WANT_NODE;
+  const int n_node = __popc(__ballot_sync(FULL, want == WANT_NODE));
+  const int n_tri = __popc(__ballot_sync(FULL, want == WANT_TRI));
+  const int n_enter = __popc(__ballot_sync(FULL, want == WANT_ENTER));
+  uint32_t phase;
+  if (n_node >= n_tri + SNK_VOTE_TRI_BIAS && n_node >= n_enter) phase = WANT_NODE;
+  else if (n_tri >= n_enter) phase = WANT_TRI;
+  else phase = WANT_ENTER;
+  bool done = false;
+  const bool mine = want == phase;
+  if (phase == WANT_NODE) {
+    if (mine) {
+      const uint32_t hits_imask = t.G.y;
+      const uint32_t bit = 31u - __clz(hits_imask);
+      t.G.y &= ~(1u << bit);
+      if (t.G.y & 0xFF000000u) stk_push<STRIDE>(stk, t.sp, t.G, S.overflow);
+      const uint32_t slot = (bit - 24u) ^ t.r.octinv;
+      const uint32_t node_idx = t.G.x + __popc(hits_imask & ~(0xFFFFFFFFu << slot) & 0xFFu);
+      const uint4* nodes = t.in_blas ? S.blas_nodes : S.tlas_nodes;
+      uint4 n0, n1, n2, n3, n4;
+      load_node(nodes, node_idx, n0, n1, n2, n3, n4);
+      const uint32_t hm = intersect_node(t.r, n0, n1, n2, n3, n4, t.tmin, t.tcur);
+      t.G = make_uint2(n1.x, (hm & 0xFF000000u) | (n0.w >> 24));
+      t.T = make_uint2(n1.y, hm & 0x00FFFFFFu);
+    }
+  } else if (phase == WANT_TRI) {
+    if (mine) {
+      const uint32_t bit = __ffs(t.T.y) - 1;
+      t.T.y &= ~(1u << bit);
+      if (!t.tri_ready) { setup_tri_space(t.r); t.tri_ready = true; }
+      const float4* tp = S.tris + 3ull * (t.T.x + bit);
+      const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
+      float th, u, v;
+      if (tri_test(t.r, p0, p1, p2, th, u, v) && th > t.tmin) {
+        const uint32_t prim = __float_as_uint(p0.w);
+        const bool take = th < t.tcur || (!any && th == t.tcur && t.best.t >= 0.0f &&
+                                          (t.cur_inst < t.best.inst || (t.cur_inst == t.best.inst && prim < t.best.prim)));
+        if (take) {
+          t.best.t = th; t.best.u = u; t.best.v = v; t.best.prim = prim; t.best.inst = t.cur_inst;
+          t.tcur = th;
+          done = any;
+        }
+      }
+    }
+  } else {
+    if (mine) {
+      // enter one instance: the rest of the leaf group and the pending inner group go on the stack, the ray moves
+      // to object space and the BLAS root becomes the pending inner group (one inner bit, empty child mask)
+      const uint32_t bit = __ffs(t.T.y) - 1;
+      t.T.y &= ~(1u << bit);
+      const uint32_t slot = __ldg(S.tlas_leaf_ids + t.T.x + bit);
+      if (t.T.y) stk_push<STRIDE>(stk, t.sp, t.T, S.overflow);
+      if (t.G.y & 0xFF000000u) stk_push<STRIDE>(stk, t.sp, t.G, S.overflow);
+      t.blas_sp = t.sp;
+      const float4* M = reinterpret_cast<const float4*>(S.inst + slot);
+      const float4 r0 = __ldg(M), r1 = __ldg(M + 1), r2 = __ldg(M + 2);
+      const uint4 meta = __ldg(reinterpret_cast<const uint4*>(M + 3));
+      const float oox = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0.x, t.ox), __fmul_rn(r0.y, t.oy)), __fmul_rn(r0.z, t.oz)), r0.w);
+      const float ooy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r1.x, t.ox), __fmul_rn(r1.y, t.oy)), __fmul_rn(r1.z, t.oz)), r1.w);
+      const float ooz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2.x, t.ox), __fmul_rn(r2.y, t.oy)), __fmul_rn(r2.z, t.oz)), r2.w);
+      const float odx = __fadd_rn(__fadd_rn(__fmul_rn(r0.x, t.dx), __fmul_rn(r0.y, t.dy)), __fmul_rn(r0.z, t.dz));
+      const float ody = __fadd_rn(__fadd_rn(__fmul_rn(r1.x, t.dx), __fmul_rn(r1.y, t.dy)), __fmul_rn(r1.z, t.dz));
+      const float odz = __fadd_rn(__fadd_rn(__fmul_rn(r2.x, t.dx), __fmul_rn(r2.y, t.dy)), __fmul_rn(r2.z, t.dz));
+      setup_box_space(t.r, oox, ooy, ooz, odx, ody, odz);
+      t.in_blas = true; t.tri_ready = false;
+      t.cur_inst = meta.y;
+      t.G = make_uint2(meta.x, 0x01000000u);
+      t.T = make_uint2(0u, 0u);
+    }
+  }
+  __syncwarp(FULL);
+  // pop: lanes of the executed phase that have nothing pending any more
+  if (mine && !done && t.T.y == 0u && (t.G.y & 0xFF000000u) == 0u) {
+    if (t.in_blas && t.sp == t.blas_sp) {
       setup_box_space(t.r, t.ox, t.oy, t.oz, t.dx, t.dy, t.dz);
       t.in_blas = false; t.tri_ready = false;
     }
