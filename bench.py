@@ -345,13 +345,13 @@ def run_gpu_arm(args, snk):
             all_bytes = sum(counted[k]["bytes"] / counted[k]["n"] for k in trace_names)
             all_ms = sum(per[k]["ms"] / per[k]["n"] for k in trace_names)
             all_live = sum(counted[k]["live"] / counted[k]["n"] for k in trace_names)
-            roof = {"bound": "hbm", "kernel": f"k_trace_pt ({top})", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            roof = {"bound": "hbm", "kernel": f"{'k_trace_q' if top.startswith('trace.q') else 'k_trace_pt'} ({top})", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": None, "peak_source": peak_src, "alg_bytes_per_launch": bytes_launch, "ms_per_launch": ms_launch,
                     "rays_per_launch": c["live"] / c["n"], "nodes_per_ray": c["nodes"] / max(c["live"], 1), "tris_per_ray": c["tris"] / max(c["live"], 1),
                     "instances_per_ray": c["insts"] / max(c["live"], 1), "grays_per_s": c["live"] / c["n"] / (ms_launch * 1e-3) / 1e9,
                     "all_traversal_launches": {"achieved": all_bytes / (all_ms * 1e-3) / 1e9, "ms_per_frame": all_ms,
                                                "grays_per_s": all_live / (all_ms * 1e-3) / 1e9},
-                    "note": "algorithmic bytes = 32+16|4 per ray + 80/node + 48/triangle record + 64/instance (SURVEY §8d); the BVH is L1/L2 "
+                    "note": "algorithmic bytes = 32+16|4 per ray (+4 reference, +4 instance plane in queue launches) + 80/node + 48/triangle record + 64/instance (SURVEY §8d); the BVH is L1/L2 "
                             "resident, the kernel is instruction-issue bound (profiles/), so the HBM fraction is context, not the limiter"}
             tr = os.path.join(ROOT, "profiles", "traffic.json")
             if os.path.exists(tr):

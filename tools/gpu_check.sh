@@ -16,8 +16,8 @@ for w in $WHAT; do
     benchref) timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err; cat $OUT/bench_ref.json;;
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches.csv \
         python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/launches_bench.log 2>&1; echo "launches rc=$?";;
-    ncu) timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_trace -s ${NCU_SKIP:-4} -c ${NCU_COUNT:-4} -f -o $OUT/prof_trace \
-        python tools/quick_bench.py ${SCENES:-c2} > $OUT/ncu_trace.log 2>&1; echo "ncu rc=$?";;
+    ncu) timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_trace -s ${NCU_SKIP:-10} -c ${NCU_COUNT:-5} -f -o $OUT/prof_trace \
+        env MODE=northstar FRAMES=2 python tools/quick_bench.py ${SCENES:-c2} > $OUT/ncu_trace.log 2>&1; echo "ncu rc=$?";;
     bench2) for sh in samples rows; do timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node ${NGPU:-2} --master-addr 127.0.0.1 --master-port 29511 \
         bench.py --gpus ${NGPU:-2} --steps 20 --warmup 3 --shard $sh > $OUT/bench_${NGPU:-2}gpu_$sh.json 2> $OUT/bench_${NGPU:-2}gpu_$sh.err; echo "bench2 $sh rc=$?"; cat $OUT/bench_${NGPU:-2}gpu_$sh.json; tail -3 $OUT/bench_${NGPU:-2}gpu_$sh.err; done;;
     quick) timeout 600 python tools/quick_bench.py ${SCENES:-c2 c2flat} > $OUT/quick.log 2>&1; echo "quick rc=$?"; cat $OUT/quick.log;;

@@ -71,7 +71,7 @@ def ncu(name):
     print(open(f"profiles/{tag}_{name}.txt").read())
 
 launches()
-for n in ("prof_trace", "prof_restir"):
+for n in ("prof_trace", "prof_traceq", "prof_restir", "prof_shade"):
     ncu(n)
 for n in ("bench.json", "bench_ref.json", "gpu.txt", "pytest_gpu.log", "smoke.log"):
     p = os.path.join(src, n)
