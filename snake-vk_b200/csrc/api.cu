@@ -131,7 +131,8 @@ int reserve_ref_queues(SnkPt* ctx, uint32_t cap, cudaStream_t st) {
   if (e != cudaSuccess) { ctx->err = std::string("ray reference queue: ") + cudaGetErrorString(e); return SNKPT_E_NOMEM; }
   return SNKPT_OK;
 }
-void reset_ref_queues(SnkPt* ctx, cudaStream_t st) { cudaMemsetAsync(ctx->dev_counters.as<uint32_t>() + 64, 0, 64, st); }
+// 24 queues (u32 [64..112)) and the per-stage path-list counters of northstar.cu (u32 [112..136))
+void reset_ref_queues(SnkPt* ctx, cudaStream_t st) { cudaMemsetAsync(ctx->dev_counters.as<uint32_t>() + 64, 0, 4 * (136 - 64), st); }
 
 int traced_launch_q(SnkPt* ctx, const char* name, const TraceSegs& segs, const RefQueue& q, cudaStream_t st) {
   const bool count = ctx->profiling >= 2 && ctx->prof_n < PROF_MAX;
@@ -176,6 +177,7 @@ SceneDev SnkPt::scene_dev() const {
   D.lights = lights.as<SnkLightData>();
   D.emissive_idx = emissive_idx.as<uint32_t>();
   D.num_emissive = num_emissive; D.num_instances = num_instances;
+  D.em_table = em_table.as<float4>(); D.em_base_of_obj = em_base_of_obj.as<uint32_t>(); D.em_base = em_base.as<uint32_t>();
   return D;
 }
 
@@ -268,7 +270,7 @@ void snkpt_destroy(SnkPt* ctx) {
                     &ctx->d_blas, &ctx->materials, &ctx->lights, &ctx->transforms, &ctx->prev_transforms, &ctx->normal_mats,
                     &ctx->det3, &ctx->instances, &ctx->blas_of_instance, &ctx->emissive_idx, &ctx->tlas_nodes, &ctx->tlas_leaf_ids,
                     &ctx->inst_recs, &ctx->valid_slots, &ctx->q_rays, &ctx->q_hits, &ctx->q_work, &ctx->dev_counters, &ctx->trav_spill,
-                    &ctx->wave_refs, &ctx->prof_work, &ctx->prof_hits};
+                    &ctx->wave_refs, &ctx->wave_paths, &ctx->prof_work, &ctx->prof_hits, &ctx->em_table, &ctx->em_base_of_obj, &ctx->em_base};
   for (DevBuf* b : bufs) b->release();
   for (auto& b : ctx->wave) b.release();
   for (auto& b : ctx->px) b.release();
@@ -568,6 +570,20 @@ int snkpt_set_instances(SnkPt* ctx, const SnkInstanceData* instances, const uint
     CK(cudaMemcpyAsync(ctx->blas_of_instance.p, blas_of_instance, 4 * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
   }
   if (num_emissive) CK(cudaMemcpyAsync(ctx->emissive_idx.p, emissive_idx, 4 * (size_t)num_emissive, cudaMemcpyHostToDevice, ctx->stream));
+  // emissive-triangle table: record ranges per emissive-list entry (the first entry of an instance listed twice wins)
+  std::vector<uint32_t> base_of_obj(ctx->max_instances, SNKPT_INVALID_INDEX), base(num_emissive ? num_emissive : 1, 0u);
+  uint32_t total = 0;
+  for (uint32_t k = 0; k < num_emissive; ++k) {
+    base[k] = total;
+    if (base_of_obj[emissive_idx[k]] == SNKPT_INVALID_INDEX) base_of_obj[emissive_idx[k]] = total;
+    total += instances[emissive_idx[k]].num_mesh_indices / 3u;
+  }
+  ctx->num_emissive_tris = total;
+  CK(ctx->em_base_of_obj.reserve(4 * (size_t)ctx->max_instances, false, ctx->stream));
+  CK(ctx->em_base.reserve(4 * (size_t)ctx->max_instances, false, ctx->stream));
+  CK(ctx->em_table.reserve(192ull * (total ? total : 1), false, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->em_base_of_obj.p, base_of_obj.data(), 4 * (size_t)ctx->max_instances, cudaMemcpyHostToDevice, ctx->stream));
+  if (num_emissive) CK(cudaMemcpyAsync(ctx->em_base.p, base.data(), 4 * (size_t)num_emissive, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->tlas_built = false;
   return SNKPT_OK;

@@ -87,6 +87,11 @@ struct SceneDev {
   const SnkLightData* lights;
   const uint32_t* emissive_idx;
   uint32_t num_emissive, num_instances;
+  // emissive-triangle table of the north-star stages (northstar.cuh:EmTri): record em_base_of_obj[obj] + tri, or
+  // em_base_of_obj[obj] == 0xFFFFFFFF when the instance is not in the emissive list
+  const float4* em_table;
+  const uint32_t* em_base_of_obj;
+  const uint32_t* em_base;  // per emissive-list entry k: first record of emissive_idx[k]
 };
 
 }  // namespace snk
@@ -115,6 +120,8 @@ struct SnkPt {
   std::vector<float> h_transforms, h_prev_transforms;
   uint32_t num_instances = 0, num_emissive = 0, num_pointlights = 0;
   snk::DevBuf materials, lights, transforms, prev_transforms, normal_mats, det3, instances, blas_of_instance, emissive_idx;
+  snk::DevBuf em_table, em_base_of_obj, em_base;  // emissive-triangle table (rebuilt every north-star frame)
+  uint32_t num_emissive_tris = 0;
 
   // TLAS
   snk::DevBuf tlas_nodes, tlas_leaf_ids, inst_recs, valid_slots;
@@ -139,6 +146,7 @@ struct SnkPt {
   snk::DevBuf q_rays, q_hits, q_work;
   snk::DevBuf wave[12];      // wavefront queues of the bounce stages (rays, hits, shading records)
   snk::DevBuf wave_refs;     // compact ray-reference queue of the north-star frame (trace_q.cu)
+  snk::DevBuf wave_paths;    // compact lists of the paths alive after each vertex stage (northstar.cu)
   // u32 view: [0] traversal stack overflows, [2..3] shadow rays of the frame, [4..5] closest-hit rays, [8..11] since-create
   // totals; u64 view [16..31]: ray tickets of the persistent traversal launches
   snk::DevBuf dev_counters;

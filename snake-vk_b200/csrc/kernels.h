@@ -25,7 +25,8 @@ int launch_count_work_q(const TraceScene& S, const TraceSegs& segs, const RefQue
                         cudaStream_t st);
 // launch_trace_q bracketed by a profiling record (+ counted replay at level 2)
 int traced_launch_q(SnkPt* ctx, const char* name, const TraceSegs& segs, const RefQueue& q, cudaStream_t st);
-// queue k (0..7) of the frame: refs in ctx->wave_refs, counters in dev_counters; all eight are reset by reset_ref_queues
+// queue k (0..23) of the frame: refs in ctx->wave_refs (shared: a queue is drained before the next one is filled), counters in
+// dev_counters; all are reset by reset_ref_queues
 RefQueue ref_queue(SnkPt* ctx, int k, uint32_t cap);
 int reserve_ref_queues(SnkPt* ctx, uint32_t cap, cudaStream_t st);
 void reset_ref_queues(SnkPt* ctx, cudaStream_t st);
@@ -47,6 +48,7 @@ int launch_reference_frame(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st);
 int launch_northstar_frame(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st);
 // restir_ns.cu — north-star ReSTIR DI stages (initial / temporal / spatial + final evaluation / resolve) → planes.direct
 int restir_ns_prepare(SnkPt* ctx, TraceSegs& segs, cudaStream_t st);
+int build_emissive_table(SnkPt* ctx, cudaStream_t st);
 int restir_ns_initial(SnkPt* ctx, const SnkRtSettings& s, const RefQueue& q, cudaStream_t st);
 int restir_ns_reuse(SnkPt* ctx, const SnkRtSettings& s, const RefQueue& q, cudaStream_t st);
 int restir_ns_resolve(SnkPt* ctx, cudaStream_t st);

@@ -85,7 +85,7 @@ __device__ void ns_vertex_work(const SceneDev& D, const NsBuffers& B, size_t i, 
       const uint32_t tri = ns_pick(u2, ntri);
       float bu = u3, bv = u4;
       if (bu + bv >= 1.0f) { bu = 1.0f - bu; bv = 1.0f - bv; }
-      const NsSurf q = ns_surface(D, obj, tri, bu, bv);
+      const NsSurf q = ns_surface_em(D, obj, tri, bu, bv);
       const vec3 d = q.p - o;
       const float dist = length(d);
       wi = d / dist;
@@ -132,7 +132,8 @@ __device__ void ns_vertex_work(const SceneDev& D, const NsBuffers& B, size_t i, 
 }
 
 __global__ void __launch_bounds__(128) k_ns_gen(SceneDev D, FrameConsts fc, PixelPlanes P, NsBuffers B, uint32_t npix, uint32_t max_bounces,
-                                                uint32_t nee_from, unsigned long long* counters, uint32_t* q_refs, uint32_t* q_count) {
+                                                uint32_t nee_from, unsigned long long* counters, uint32_t* q_refs, uint32_t* q_count,
+                                                uint32_t* paths_out, uint32_t* paths_out_count) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool has_shadow = false, has_closest = false;
   if (i < npix) {
@@ -158,15 +159,22 @@ __global__ void __launch_bounds__(128) k_ns_gen(SceneDev D, FrameConsts fc, Pixe
     }
   }
   q_append3(q_refs, q_count, has_closest, make_ref(SEG_NS_CLOSEST, i), has_shadow, make_ref(SEG_NS_SHADOW, i), false, 0u);
+  q_append1(paths_out, paths_out_count, has_closest, i);
   flush_counts(has_shadow ? 1ull : 0ull, has_closest ? 1ull : 0ull, counters);
 }
 
-// the hit of the ray that left vertex x_{b-1} becomes vertex x_b
+// the hit of the ray that left vertex x_{b-1} becomes vertex x_b. One thread per path that is still alive (compact list
+// written by the previous stage): a path that ended keeps its last pending next-event term in C / vis, which k_ns_resolve
+// adds — the same sum, in the same order, as visiting the dead pixel here would give
 __global__ void __launch_bounds__(128) k_ns_vertex(SceneDev D, FrameConsts fc, NsBuffers B, uint32_t npix, uint32_t b, uint32_t max_bounces,
-                                                   uint32_t nee_from, unsigned long long* counters, uint32_t* q_refs, uint32_t* q_count) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+                                                   uint32_t nee_from, unsigned long long* counters, uint32_t* q_refs, uint32_t* q_count,
+                                                   const uint32_t* paths_in, const uint32_t* paths_in_count, uint32_t* paths_out,
+                                                   uint32_t* paths_out_count) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   bool has_shadow = false, has_closest = false;
-  if (i < npix) {
+  uint32_t i = 0;
+  if (j < npix && j < __ldcg(paths_in_count)) {
+    i = paths_in[j];
     const uint32_t x = i % fc.W, y = fc.row0 + i / fc.W;
     const uint32_t pixel = y * fc.W + x;
     // the previous vertex's next-event estimate, now that its shadow ray is resolved
@@ -206,6 +214,7 @@ __global__ void __launch_bounds__(128) k_ns_vertex(SceneDev D, FrameConsts fc, N
     }
   }
   q_append3(q_refs, q_count, has_closest, make_ref(SEG_NS_CLOSEST, i), has_shadow, make_ref(SEG_NS_SHADOW, i), false, 0u);
+  q_append1(paths_out, paths_out_count, has_closest, i);
   flush_counts(has_shadow ? 1ull : 0ull, has_closest ? 1ull : 0ull, counters);
 }
 
@@ -261,6 +270,10 @@ int launch_northstar_frame(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st) 
   const uint32_t qcap = 5u * npix_frame;
   int rc = reserve_ref_queues(ctx, qcap, st);
   if (rc < 0) return rc;
+  // compact lists of the paths alive after each vertex stage (ping-pong) + one counter per stage
+  if (ctx->wave_paths.reserve(8ull * npix, false, st) != cudaSuccess) { ctx->err = "north-star path lists: out of memory"; return SNKPT_E_NOMEM; }
+  uint32_t* paths[2] = {ctx->wave_paths.as<uint32_t>(), ctx->wave_paths.as<uint32_t>() + npix};
+  uint32_t* path_count = ctx->dev_counters.as<uint32_t>() + 112;
   reset_ref_queues(ctx, st);
   NsBuffers B;
   B.rays = ctx->wave[0].as<float4>(); B.hit = ctx->wave[1].as<float4>(); B.inst = ctx->wave[2].as<uint32_t>(); B.T = ctx->wave[3].as<float4>();
@@ -282,11 +295,12 @@ int launch_northstar_frame(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st) 
   //   queue 1: ReSTIR final shadow rays + NEE ray of vertex 1 + continuation ray 2
   //   queue b: NEE ray of vertex b + continuation ray b+1
   cudaEventRecord(ctx->ev[2], st);
+  launches += build_emissive_table(ctx, st);
   int q = 0;
   RefQueue Q = ref_queue(ctx, q, qcap);
   if (nee_from) launches += restir_ns_initial(ctx, s, Q, st);
   int rec = prof_begin(ctx, "ns_gen", npix, false, false, st);
-  k_ns_gen<<<g128, 128, 0, st>>>(D, fc, ctx->planes, B, npix, max_bounces, nee_from, counters, Q.refs, Q.count);
+  k_ns_gen<<<g128, 128, 0, st>>>(D, fc, ctx->planes, B, npix, max_bounces, nee_from, counters, Q.refs, Q.count, paths[0], path_count);
   prof_end(ctx, rec, st);
   ++launches;
   char name[32];
@@ -296,10 +310,10 @@ int launch_northstar_frame(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st) 
   if (nee_from) launches += restir_ns_reuse(ctx, s, Q, st);
   else { cudaEventRecord(ctx->ev[3], st); }
   for (uint32_t b = 1; b <= max_bounces; ++b) {
-    if (q >= 8) { ctx->err = "snkpt_render: max_bounces > 7 needs more reference queues"; return SNKPT_E_INVALID; }
     snprintf(name, sizeof(name), "ns_vertex.%u", b);
     rec = prof_begin(ctx, name, npix, false, false, st);
-    k_ns_vertex<<<g128, 128, 0, st>>>(D, fc, B, npix, b, max_bounces, nee_from, counters, Q.refs, Q.count);
+    k_ns_vertex<<<g128, 128, 0, st>>>(D, fc, B, npix, b, max_bounces, nee_from, counters, Q.refs, Q.count, paths[(b - 1) & 1], path_count + (b - 1),
+                                      paths[b & 1], path_count + b);
     prof_end(ctx, rec, st);
     snprintf(name, sizeof(name), "trace.q%d", q);
     launches += 1 + traced_launch_q(ctx, name, segs, Q, st);

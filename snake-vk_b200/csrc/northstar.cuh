@@ -46,6 +46,38 @@ static __device__ __noinline__ NsSurf ns_surface(const SceneDev& D, uint32_t ins
   return s;
 }
 
+// ---- emissive-triangle table ------------------------------------------------------------------------------------
+// Light sampling evaluates ns_surface on 32 random emissive triangles per pixel; through the scene buffers that is ~60
+// dependent 4-byte gathers per candidate (instance record, 3 indices, 3 positions, 3 normals, mat4, normal matrix,
+// material) — ncu: 81 % excessive sectors, IPC 1.4 on C3 (profiles/r01t_prof_shade.txt). k_build_em_table (restir_ns.cu)
+// flattens everything ns_surface needs about one emissive triangle into ONE 192-byte record per frame; the lookup
+// below is 12 x 128-bit loads and evaluates the SAME expressions in the same order, so results are bit-identical.
+constexpr int EM_REC_F4 = 12;
+//  r0 pa.xyz area | r1 pb.xyz albedo.r | r2 pc.xyz albedo.g | r3 na.xyz albedo.b | r4 nb.xyz roughness | r5 nc.xyz metallic
+//  r6 M[0..2] flags | r7 M[4..6] ntri | r8 M[8..10] A[8] | r9 M[12..14] - | r10 A[0..2] A[6] | r11 A[3..5] A[7]
+static __device__ __noinline__ NsSurf ns_surface_em(const SceneDev& D, uint32_t obj, uint32_t tri, float u, float v) {
+  const uint32_t base = __ldg(D.em_base_of_obj + obj);
+  if (base == INVALID_IDX) return ns_surface(D, obj, tri, u, v);
+  const float4* r = D.em_table + (size_t)EM_REC_F4 * (base + tri);
+  const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3), r4 = __ldg(r + 4), r5 = __ldg(r + 5);
+  const float4 r6 = __ldg(r + 6), r7 = __ldg(r + 7), r8 = __ldg(r + 8), r9 = __ldg(r + 9), r10 = __ldg(r + 10), r11 = __ldg(r + 11);
+  NsSurf s;
+  const float b0 = (1.0f - u) - v;
+  const vec3 p = (v3(r0.x, r0.y, r0.z) * b0 + v3(r1.x, r1.y, r1.z) * u) + v3(r2.x, r2.y, r2.z) * v;
+  const vec3 n = (v3(r3.x, r3.y, r3.z) * b0 + v3(r4.x, r4.y, r4.z) * u) + v3(r5.x, r5.y, r5.z) * v;
+  s.p = v3(((r6.x * p.x + r7.x * p.y) + r8.x * p.z) + r9.x, ((r6.y * p.x + r7.y * p.y) + r8.y * p.z) + r9.y,
+           ((r6.z * p.x + r7.z * p.y) + r8.z * p.z) + r9.z);
+  s.n = normalize(v3((r10.x * n.x + r10.y * n.y) + r10.z * n.z, (r11.x * n.x + r11.y * n.y) + r11.z * n.z,
+                     (r10.w * n.x + r11.w * n.y) + r8.w * n.z));
+  s.albedo = v3(r1.w, r2.w, r3.w);
+  s.roughness = r4.w;
+  s.metallic = r5.w;
+  s.flags = __float_as_uint(r6.w);
+  s.ntri = __float_as_uint(r7.w);
+  s.area = r0.w;
+  return s;
+}
+
 static __device__ __noinline__ vec3 ns_bsdf_cos(vec3 n, vec3 wo, vec3 wi, vec3 albedo, float roughness, float metallic) {
   const vec3 f0 = mix(v3(0.04f), albedo, metallic);
   const vec3 h = normalize(wo + wi);
@@ -137,6 +169,16 @@ __device__ __forceinline__ void q_append3(uint32_t* refs, uint32_t* count, bool 
   if (h0) refs[base + __popc(m0 & below)] = r0;
   if (h1) refs[base + n0 + __popc(m1 & below)] = r1;
   if (h2) refs[base + n0 + n1 + __popc(m2 & below)] = r2;
+}
+
+__device__ __forceinline__ void q_append1(uint32_t* list, uint32_t* count, bool h, uint32_t v) {
+  const uint32_t m = __ballot_sync(0xFFFFFFFFu, h);
+  if (m == 0u) return;
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t base = 0;
+  if (lane == 0) base = atomicAdd(count, __popc(m));
+  base = __shfl_sync(0xFFFFFFFFu, base, 0);
+  if (h) list[base + __popc(m & ((1u << lane) - 1u))] = v;
 }
 
 // marks a path as ended: only the tmax word of the slot is read back by the next vertex stage

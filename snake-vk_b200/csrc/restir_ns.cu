@@ -114,6 +114,42 @@ __device__ __forceinline__ void pixel_of(const FrameConsts& fc, uint32_t i, uint
   px = (size_t)y * fc.W + x;
 }
 
+// ---- emissive-triangle table (northstar.cuh): one block per emissive-list entry ------------------------------------------
+__global__ void __launch_bounds__(128) k_build_em_table(SceneDev D, float4* __restrict__ table) {
+  const uint32_t k = blockIdx.x;
+  const uint32_t obj = __ldg(D.emissive_idx + k);
+  const uint32_t base = __ldg(D.em_base + k);
+  const SnkInstanceData in = load_instance(D, obj);
+  const uint32_t ntri = in.num_mesh_indices / 3u;
+  const float* M = D.transforms + 16ull * in.transform_idx;
+  const float* A = D.normal_mats + 9ull * in.transform_idx;
+  const SnkMaterial* m = D.materials + in.material_idx;
+  const float4 alb = __ldg(reinterpret_cast<const float4*>(m->albedo));
+  const float roughness = gmax(__ldg(&m->roughness), 0.05f), metallic = __ldg(&m->metallic);
+  const uint32_t flags = __ldg(&m->flags);
+  for (uint32_t tri = threadIdx.x; tri < ntri; tri += blockDim.x) {
+    uint32_t ia, ib, ic;
+    tri_indices(D, in, tri, ia, ib, ic);
+    const vec3 pa = ld3(D.positions, ia), pb = ld3(D.positions, ib), pc = ld3(D.positions, ic);
+    const vec3 na = ld3(D.normals, ia), nb = ld3(D.normals, ib), nc = ld3(D.normals, ic);
+    const vec3 wa = mul_point(M, pa), wb = mul_point(M, pb), wc = mul_point(M, pc);
+    const float area = 0.5f * length(cross(wb - wa, wc - wa));  // as ns_surface
+    float4* r = table + (size_t)EM_REC_F4 * (base + tri);
+    r[0] = make_float4(pa.x, pa.y, pa.z, area);
+    r[1] = make_float4(pb.x, pb.y, pb.z, alb.x);
+    r[2] = make_float4(pc.x, pc.y, pc.z, alb.y);
+    r[3] = make_float4(na.x, na.y, na.z, alb.z);
+    r[4] = make_float4(nb.x, nb.y, nb.z, roughness);
+    r[5] = make_float4(nc.x, nc.y, nc.z, metallic);
+    r[6] = make_float4(M[0], M[1], M[2], __uint_as_float(flags));
+    r[7] = make_float4(M[4], M[5], M[6], __uint_as_float(ntri));
+    r[8] = make_float4(M[8], M[9], M[10], A[8]);
+    r[9] = make_float4(M[12], M[13], M[14], 0.0f);
+    r[10] = make_float4(A[0], A[1], A[2], A[6]);
+    r[11] = make_float4(A[3], A[4], A[5], A[7]);
+  }
+}
+
 // ---- stage 1 ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) k_rs_initial(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, RsBuffers B, uint32_t npix,
                                                     unsigned long long* counters, uint32_t* q_refs, uint32_t* q_count) {
@@ -158,11 +194,11 @@ __global__ void __launch_bounds__(128) k_rs_initial(SceneDev D, FrameConsts fc, 
         for (uint32_t c = 0; c < iters; ++c) {
           const uint32_t d = RS_DIM_INITIAL + 0x800u + 5u * c;
           const uint32_t obj = __ldg(D.emissive_idx + ns_pick(rs_rand(h0, d), n_em));
-          const uint32_t ntri = load_instance(D, obj).num_mesh_indices / 3u;
+          const uint32_t ntri = __ldg(&D.instances[obj].num_mesh_indices) / 3u;
           const uint32_t tri = ns_pick(rs_rand(h0, d + 1u), ntri);
           float bu = rs_rand(h0, d + 2u), bv = rs_rand(h0, d + 3u);
           if (bu + bv >= 1.0f) { bu = 1.0f - bu; bv = 1.0f - bv; }
-          const NsSurf q = ns_surface(D, obj, tri, bu, bv);
+          const NsSurf q = ns_surface_em(D, obj, tri, bu, bv);
           const RsEval e = rs_eval_em(s, q);
           const float p_hat = rs_phat(e);
           const float w = (p_hat * ((float)n_em * (float)ntri)) * q.area;
@@ -232,7 +268,7 @@ __global__ void __launch_bounds__(128) k_rs_temporal(SceneDev D, FrameConsts fc,
         }
         r.pl_m += h.pl_m;
         if (rs_em_valid(D, h.obj, h.tri)) {
-          const NsSurf q = ns_surface(D, h.obj, h.tri, h.bx, h.by);
+          const NsSurf q = ns_surface_em(D, h.obj, h.tri, h.bx, h.by);
           const float ph = rs_phat(rs_eval_em(s, q));
           const float w = (ph * h.w_em) * (float)h.m_em;
           r.w_sum_em += w;
@@ -299,7 +335,7 @@ __global__ void __launch_bounds__(128) k_rs_spatial(SceneDev D, FrameConsts fc, 
         }
         out.pl_m += c.pl_m;
         if (rs_em_valid(D, c.obj, c.tri)) {
-          const NsSurf q = ns_surface(D, c.obj, c.tri, c.bx, c.by);
+          const NsSurf q = ns_surface_em(D, c.obj, c.tri, c.bx, c.by);
           const float ph = rs_phat(rs_eval_em(s, q));
           const float w = (ph * c.w_em) * (float)c.m_em;
           out.w_sum_em += w;
@@ -313,7 +349,7 @@ __global__ void __launch_bounds__(128) k_rs_spatial(SceneDev D, FrameConsts fc, 
       if (src_pl >= 0 || src_em >= 0) {
         float num_pl = 0.0f, den_pl = 0.0f, num_em = 0.0f, den_em = 0.0f;
         NsSurf q;
-        if (src_em >= 0) q = ns_surface(D, out.obj, out.tri, out.bx, out.by);
+        if (src_em >= 0) q = ns_surface_em(D, out.obj, out.tri, out.bx, out.by);
         const PointLightRec pl = load_pointlight(D.lights, src_pl >= 0 ? out.pl_idx : 0u);
         for (int j = 0; j < nc; ++j) {
           float ph_pl = p_pl, ph_em = p_em;
@@ -343,7 +379,7 @@ __global__ void __launch_bounds__(128) k_rs_spatial(SceneDev D, FrameConsts fc, 
         }
       }
       if (out.obj != INVALID_IDX && out.w_em > 0.0f) {
-        const NsSurf q = ns_surface(D, out.obj, out.tri, out.bx, out.by);
+        const NsSurf q = ns_surface_em(D, out.obj, out.tri, out.bx, out.by);
         const RsEval e = rs_eval_em(xs, q);
         if (e.tmax > 0.0f) {
           C1 = e.C * out.w_em;
@@ -421,6 +457,15 @@ int restir_ns_prepare(SnkPt* ctx, TraceSegs& segs, cudaStream_t st) {
   float* vis = ctx->wave[9].as<float>();
   for (uint32_t k = 0; k < 3; ++k) segs.s[SEG_RS_PL + k] = TraceSeg{rays + 2ull * k * npix_frame, nullptr, nullptr, vis + (size_t)k * npix_frame, 1u, 0u};
   return SNKPT_OK;
+}
+
+// flattens the emissive triangles of this frame (transforms and materials as currently set) into the lookup table
+int build_emissive_table(SnkPt* ctx, cudaStream_t st) {
+  if (ctx->num_emissive == 0 || ctx->num_emissive_tris == 0) return 0;
+  const int rec = prof_begin(ctx, "em_table", ctx->num_emissive_tris, false, false, st);
+  k_build_em_table<<<ctx->num_emissive, 128, 0, st>>>(ctx->scene_dev(), ctx->em_table.as<float4>());
+  prof_end(ctx, rec, st);
+  return 1;
 }
 
 // stage 1: candidate generation; appends the shadow rays of the initial samples to q
