@@ -220,7 +220,9 @@ enum {
   SNKPT_AUX_ACCUM_F32 = 17,      /* 4×f32/pixel progressive mean                 */
   SNKPT_AUX_DIRECT_F32 = 18,     /* 4×f32/pixel direct part (dir light + ReSTIR) */
   SNKPT_AUX_TLAS_INSTANCES = 19, /* 80-B device instance records                 */
-  SNKPT_AUX_BLAS_TABLE = 20      /* SnkBlasInfo records                          */
+  SNKPT_AUX_BLAS_TABLE = 20,     /* SnkBlasInfo records                          */
+  SNKPT_AUX_TAA_HISTORY = 21,    /* 4×f16/pixel TAA history image                */
+  SNKPT_AUX_TAA_PREV_VELOCITY = 22 /* 2×f16/pixel velocity of the previous resolve */
 };
 
 enum { SNKPT_FMT_RGBA16F = 0, SNKPT_FMT_RGBA32F = 1 };
@@ -334,6 +336,15 @@ SNKPT_API int snkpt_trace_primary(SnkPt* ctx, const float* jitter_xy, void* stre
 SNKPT_API int snkpt_render(SnkPt* ctx, const SnkRtSettings* settings, void* stream);
 /* progressive mean of frame outputs in fp32 (no reference counterpart) */
 SNKPT_API int snkpt_accumulate(SnkPt* ctx, int reset, void* stream);
+/* TAA_ResolvePass::RecordCommandBuffer (Core/src/renderpasses/TAA_ResolvePass.cpp:39-56),
+ * enabled by RenderSettings::using_taa (Editor/src/EditorLayer.cpp:636-640): runs
+ * TAA_Resolve.comp (Core/res/shaders/TAA_Resolve.comp:1-85) on the RGBA16F output image
+ * of the last snkpt_render in place, against the history image and the G-buffer
+ * velocity plane, then does the pass's two blits (output -> history, velocity ->
+ * previous velocity). The first call after create / resize / snkpt_reset_history
+ * seeds the history with the current frame (the reference leaves it undefined).
+ * Whole frames only: returns SNKPT_E_STATE on a context that renders a row band. */
+SNKPT_API int snkpt_taa_resolve(SnkPt* ctx, void* stream);
 
 /* ---- readback ---------------------------------------------------------------------- */
 /* internal_render_image (EditorLayer.cpp:389-395): RGBA16F, linear, alpha 1.

@@ -13,6 +13,7 @@
 #include <cstring>
 
 #include "snk_northstar.h"
+#include "snk_taa.h"
 
 using namespace snkor;
 
@@ -190,6 +191,11 @@ ORACLE_API void snkor_pixel_scripted(void* fp, uint32_t x, uint32_t y, uint32_t 
 ORACLE_API void snkor_sizes(uint32_t* out8) {
   out8[0] = sizeof(InstanceData); out8[1] = sizeof(Material); out8[2] = sizeof(LightData); out8[3] = sizeof(CommonUBO);
   out8[4] = sizeof(PixelReservoir); out8[5] = sizeof(Ray); out8[6] = sizeof(Hit); out8[7] = sizeof(RtSettings);
+}
+// TAA_Resolve.comp on raw RGBA16F / RG16F planes (snk_taa.h)
+ORACLE_API void snkor_taa_resolve(uint32_t w, uint32_t h, const uint16_t* cur, const uint16_t* velocity, const uint16_t* history,
+                                  const uint16_t* prev_vel, uint16_t* out) {
+  taa_resolve(TaaImages{w, h, cur, velocity, history, prev_vel, out});
 }
 ORACLE_API int snkor_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
 

@@ -45,7 +45,7 @@ def load_library() -> C.CDLL:
         "snkpt_set_materials": [vp, vp, u32, u32], "snkpt_set_lights": [vp, vp, sz],
         "snkpt_set_transforms": [vp, vp, vp, u32, u32], "snkpt_set_instances": [vp, vp, vp, u32, vp, u32],
         "snkpt_build_tlas": [vp, vp], "snkpt_set_frame": [vp, vp, vp], "snkpt_trace_primary": [vp, vp, vp],
-        "snkpt_render": [vp, vp, vp], "snkpt_accumulate": [vp, i32, vp], "snkpt_read_output": [vp, vp, u32],
+        "snkpt_render": [vp, vp, vp], "snkpt_accumulate": [vp, i32, vp], "snkpt_taa_resolve": [vp, vp], "snkpt_read_output": [vp, vp, u32],
         "snkpt_read_aux": [vp, u32, vp, sz], "snkpt_aux_size": [vp, u32, vp],
         "snkpt_write_reservoirs": [vp, u32, vp, u32, u32], "snkpt_device_ptr": [vp, u32, vp, vp],
         "snkpt_get_stats": [vp, vp], "snkpt_synchronize": [vp], "snkpt_trace_rays": [vp, vp, u64, u32, vp, vp],
@@ -70,7 +70,7 @@ EXPORTS = ["snkpt_create", "snkpt_destroy", "snkpt_last_error", "snkpt_default_s
            "snkpt_set_materials", "snkpt_set_lights", "snkpt_set_transforms", "snkpt_set_instances", "snkpt_build_tlas",
            "snkpt_set_frame", "snkpt_trace_primary", "snkpt_render", "snkpt_accumulate", "snkpt_read_output", "snkpt_read_aux",
            "snkpt_aux_size", "snkpt_write_reservoirs", "snkpt_device_ptr", "snkpt_get_stats", "snkpt_synchronize",
-           "snkpt_trace_rays", "snkpt_count_work", "snkpt_set_profiling", "snkpt_get_launch_timings"]
+           "snkpt_trace_rays", "snkpt_count_work", "snkpt_set_profiling", "snkpt_get_launch_timings", "snkpt_taa_resolve"]
 
 CONFIG_DTYPE = np.dtype([("width", "<u4"), ("height", "<u4"), ("device", "<i4"), ("max_instances", "<u4"),
                          ("max_transforms", "<u4"), ("max_materials", "<u4"), ("row_begin", "<u4"), ("row_end", "<u4"),
@@ -103,7 +103,8 @@ AUX = dict(prim=(0, np.uint32, 1), inst=(1, np.uint32, 1), depth=(2, np.float32,
            albedo=(4, np.int8, 4), rma=(5, np.float16, 4), motion=(6, np.float16, 2), flags=(7, np.uint16, 1),
            prev_normal=(8, np.float16, 4), prev_depth=(9, np.float32, 1), reservoirs_final=(10, scenes.RESERVOIR_DTYPE, 1),
            reservoirs_temporal=(11, scenes.RESERVOIR_DTYPE, 1), hit_t=(14, np.float32, 1), bary=(15, np.float32, 2),
-           radiance=(16, np.float32, 4), accum=(17, np.float32, 4), direct=(18, np.float32, 4))
+           radiance=(16, np.float32, 4), accum=(17, np.float32, 4), direct=(18, np.float32, 4),
+           taa_history=(21, np.float16, 4), taa_prev_velocity=(22, np.float16, 2))
 
 
 def _p(a):
@@ -209,6 +210,10 @@ class PathTracer:
 
     def accumulate(self, reset=False, stream=None):
         self._ck(self.L.snkpt_accumulate(self.h, int(reset), stream), "snkpt_accumulate")
+
+    def taa_resolve(self, stream=None):
+        """TAA_ResolvePass::RecordCommandBuffer on the output image of the last render (include/snkpt.h)."""
+        self._ck(self.L.snkpt_taa_resolve(self.h, stream), "snkpt_taa_resolve")
 
     def synchronize(self):
         self._ck(self.L.snkpt_synchronize(self.h), "snkpt_synchronize")

@@ -184,7 +184,7 @@ SceneDev SnkPt::scene_dev() const {
 // ---- per-pixel planes ----------------------------------------------------------------------
 static int alloc_pixels(SnkPt* ctx) {
   const size_t n = (size_t)ctx->W * ctx->H;
-  const size_t sizes[] = {4, 8, 4, 8, 4, 2, 8, 4, 4, 4, 4, 8, 16, 16, 16, 16, 16, 16, 16, 16, 16, 8};
+  const size_t sizes[] = {4, 8, 4, 8, 4, 2, 8, 4, 4, 4, 4, 8, 16, 16, 16, 16, 16, 16, 16, 16, 16, 8, 8, 8, 4, 4};
   const int count = (int)(sizeof(sizes) / sizeof(sizes[0]));
   for (int i = 0; i < count; ++i) {
     ctx->px[i].release();
@@ -200,6 +200,8 @@ static int alloc_pixels(SnkPt* ctx) {
   for (int h = 0; h < 2; ++h) for (int k = 0; k < 3; ++k) P.res[h][k] = ctx->px[12 + h * 3 + k].as<float4>();
   P.radiance = ctx->px[18].as<float4>(); P.direct = ctx->px[19].as<float4>(); P.accum = ctx->px[20].as<float4>();
   P.out16 = ctx->px[21].as<ushort4>();
+  P.taa_hist[0] = ctx->px[22].as<ushort4>(); P.taa_hist[1] = ctx->px[23].as<ushort4>();
+  P.taa_prev_vel[0] = ctx->px[24].as<ushort2>(); P.taa_prev_vel[1] = ctx->px[25].as<ushort2>();
   // depth planes clear to 1.0 (GBufferPass.cpp:79); prim ids to "sky"; reservoirs to empty
   std::vector<float> ones(n, 1.0f);
   CK(cudaMemcpyAsync(P.depth, ones.data(), 4 * n, cudaMemcpyHostToDevice, ctx->stream));
@@ -217,6 +219,7 @@ static int alloc_pixels(SnkPt* ctx) {
   ctx->history_valid = false;
   ctx->gbuffer_valid = false;
   ctx->accum_count = 0;
+  ctx->taa_valid = false; ctx->taa_cur = 0;
   return SNKPT_OK;
 }
 
@@ -327,6 +330,7 @@ int snkpt_set_halo(SnkPt* ctx, uint32_t pass1_halo, uint32_t gbuffer_halo) {
 int snkpt_reset_history(SnkPt* ctx) {
   if (!ctx) return SNKPT_E_INVALID;
   ctx->history_valid = false;
+  ctx->taa_valid = false;
   return SNKPT_OK;
 }
 
@@ -579,6 +583,11 @@ int snkpt_set_instances(SnkPt* ctx, const SnkInstanceData* instances, const uint
     total += instances[emissive_idx[k]].num_mesh_indices / 3u;
   }
   ctx->num_emissive_tris = total;
+  // stored reservoir samples name (instance, triangle) pairs of the emissive list: a different list invalidates them
+  if (ctx->h_emissive != std::vector<uint32_t>(emissive_idx, emissive_idx + num_emissive)) {
+    if (!ctx->h_emissive.empty() || num_emissive) ctx->history_valid = false;
+    ctx->h_emissive.assign(emissive_idx, emissive_idx + num_emissive);
+  }
   CK(ctx->em_base_of_obj.reserve(4 * (size_t)ctx->max_instances, false, ctx->stream));
   CK(ctx->em_base.reserve(4 * (size_t)ctx->max_instances, false, ctx->stream));
   CK(ctx->em_table.reserve(192ull * (total ? total : 1), false, ctx->stream));
@@ -734,6 +743,32 @@ int snkpt_accumulate(SnkPt* ctx, int reset, void* stream) {
   return SNKPT_OK;
 }
 
+int snkpt_taa_resolve(SnkPt* ctx, void* stream) {
+  if (!ctx) return SNKPT_E_INVALID;
+  REQUIRE(ctx->gbuffer_valid, SNKPT_E_STATE, "snkpt_taa_resolve: render a frame first");
+  REQUIRE(ctx->row0 == 0 && ctx->row1 == ctx->H, SNKPT_E_STATE, "snkpt_taa_resolve: whole frames only (gather the row bands first)");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  const size_t n = (size_t)ctx->W * ctx->H;
+  PixelPlanes& P = ctx->planes;
+  const uint32_t cur = ctx->taa_cur, nxt = cur ^ 1u;
+  if (!ctx->taa_valid) {
+    // the reference never initialises the history images: define them as the current frame and its velocity
+    CK(cudaMemcpyAsync(P.taa_hist[cur], P.out16, 8 * n, cudaMemcpyDeviceToDevice, st));
+    CK(cudaMemcpyAsync(P.taa_prev_vel[cur], P.motion, 4 * n, cudaMemcpyDeviceToDevice, st));
+  }
+  const int rec = prof_begin(ctx, "taa_resolve", n, false, false, st);
+  ctx->stats.kernel_launches += launch_taa_resolve(P.out16, P.motion, P.taa_hist[cur], P.taa_prev_vel[cur], P.taa_hist[nxt], P.taa_prev_vel[nxt],
+                                                   ctx->W, ctx->H, st);
+  // the shader stores into the image it reads: the resolved frame becomes the output image (and stays the new history)
+  CK(cudaMemcpyAsync(P.out16, P.taa_hist[nxt], 8 * n, cudaMemcpyDeviceToDevice, st));
+  prof_end(ctx, rec, st);
+  CK(cudaGetLastError());
+  ctx->taa_cur = nxt;
+  ctx->taa_valid = true;
+  return SNKPT_OK;
+}
+
 // ---- readback ------------------------------------------------------------------------------------------------
 static int aux_desc(SnkPt* ctx, uint32_t what, const void** src, size_t* bytes) {
   const size_t n = (size_t)ctx->W * ctx->H;
@@ -759,6 +794,8 @@ static int aux_desc(SnkPt* ctx, uint32_t what, const void** src, size_t* bytes) 
     case SNKPT_AUX_TLAS_INSTANCES: *src = ctx->inst_recs.p; *bytes = sizeof(SnkInstRec) * (size_t)ctx->num_instances; break;
     case SNKPT_AUX_RESERVOIRS_FINAL:
     case SNKPT_AUX_RESERVOIRS_TEMPORAL: *src = nullptr; *bytes = 48 * n; break;
+    case SNKPT_AUX_TAA_HISTORY: *src = P.taa_hist[ctx->taa_cur]; *bytes = 8 * n; break;
+    case SNKPT_AUX_TAA_PREV_VELOCITY: *src = P.taa_prev_vel[ctx->taa_cur]; *bytes = 4 * n; break;
     case SNKPT_AUX_BLAS_TABLE: *src = nullptr; *bytes = sizeof(SnkBlasInfo) * ctx->blas.size(); break;
     default: return SNKPT_E_INVALID;
   }

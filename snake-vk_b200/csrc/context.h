@@ -73,6 +73,8 @@ struct PixelPlanes {
   float4* res[2][3];
   // images
   float4 *radiance, *direct, *accum; ushort4* out16;
+  // TAA (taa.cu): history ping-pong (RGBA16F) and the velocity of the previous resolve (RG16F)
+  ushort4* taa_hist[2]; ushort2* taa_prev_vel[2];
 };
 
 struct SceneDev {
@@ -116,7 +118,7 @@ struct SnkPt {
 
   // scene mirrors (host + device)
   std::vector<SnkInstanceData> h_instances;
-  std::vector<uint32_t> h_blas_of_instance;
+  std::vector<uint32_t> h_blas_of_instance, h_emissive;
   std::vector<float> h_transforms, h_prev_transforms;
   uint32_t num_instances = 0, num_emissive = 0, num_pointlights = 0;
   snk::DevBuf materials, lights, transforms, prev_transforms, normal_mats, det3, instances, blas_of_instance, emissive_idx;
@@ -136,6 +138,8 @@ struct SnkPt {
   bool gbuffer_valid = false;
   bool render_pending = false;  // a frame was enqueued since the last stats read
   uint32_t accum_count = 0;
+  bool taa_valid = false;       // the TAA history holds a resolved frame
+  uint32_t taa_cur = 0;         // ping-pong index of the current history / previous-velocity images
 
   // frame
   SnkCommonUBO ubo{}, prev_ubo{};

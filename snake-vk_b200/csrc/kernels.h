@@ -53,5 +53,8 @@ int restir_ns_initial(SnkPt* ctx, const SnkRtSettings& s, const RefQueue& q, cud
 int restir_ns_reuse(SnkPt* ctx, const SnkRtSettings& s, const RefQueue& q, cudaStream_t st);
 int restir_ns_resolve(SnkPt* ctx, cudaStream_t st);
 int launch_accumulate(const PixelPlanes& P, uint32_t npix, uint32_t count, cudaStream_t st);
+// taa.cu — TAA_Resolve.comp: resolved frame -> out (next history), this frame's velocity -> vel_out
+int launch_taa_resolve(const ushort4* cur, const ushort2* velocity, const ushort4* history, const ushort2* prev_vel, ushort4* out,
+                       ushort2* vel_out, uint32_t W, uint32_t H, cudaStream_t st);
 
 }  // namespace snk

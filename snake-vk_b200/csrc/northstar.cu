@@ -131,7 +131,7 @@ __device__ void ns_vertex_work(const SceneDev& D, const NsBuffers& B, size_t i, 
   B.T[i] = make_float4(T.x, T.y, T.z, pdf_b);
 }
 
-__global__ void __launch_bounds__(128) k_ns_gen(SceneDev D, FrameConsts fc, PixelPlanes P, NsBuffers B, uint32_t npix, uint32_t max_bounces,
+__global__ void __launch_bounds__(128, 8) k_ns_gen(SceneDev D, FrameConsts fc, PixelPlanes P, NsBuffers B, uint32_t npix, uint32_t max_bounces,
                                                 uint32_t nee_from, unsigned long long* counters, uint32_t* q_refs, uint32_t* q_count,
                                                 uint32_t* paths_out, uint32_t* paths_out_count) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;

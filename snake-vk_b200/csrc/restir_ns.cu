@@ -104,8 +104,10 @@ static __device__ __noinline__ RsEval rs_eval_em(const RsSurf& s, const NsSurf& 
   e.wi = wi; e.tmax = dist - 0.005f;
   return e;
 }
+// a stored emissive sample is usable when its instance is (still) in the emissive list — snkpt_set_instances drops the
+// reservoir history when that list changes — and the triangle exists
 __device__ __forceinline__ bool rs_em_valid(const SceneDev& D, uint32_t obj, uint32_t tri) {
-  return obj < D.num_instances && tri < load_instance(D, obj).num_mesh_indices / 3u;
+  return obj < D.num_instances && __ldg(D.em_base_of_obj + obj) != INVALID_IDX && tri < __ldg(&D.instances[obj].num_mesh_indices) / 3u;
 }
 __device__ __forceinline__ void rs_empty(Reservoir& r) { init_reservoir(r); }
 
@@ -151,7 +153,7 @@ __global__ void __launch_bounds__(128) k_build_em_table(SceneDev D, float4* __re
 }
 
 // ---- stage 1 ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_rs_initial(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, RsBuffers B, uint32_t npix,
+__global__ void __launch_bounds__(128, 6) k_rs_initial(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, RsBuffers B, uint32_t npix,
                                                     unsigned long long* counters, uint32_t* q_refs, uint32_t* q_count) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long n_shadow = 0;
@@ -226,7 +228,7 @@ __global__ void __launch_bounds__(128) k_rs_initial(SceneDev D, FrameConsts fc, 
 }
 
 // ---- stage 2 ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_rs_temporal(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, RsBuffers B, uint32_t npix) {
+__global__ void __launch_bounds__(128, 8) k_rs_temporal(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, RsBuffers B, uint32_t npix) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npix) return;
   uint32_t x, y; size_t px;
@@ -286,7 +288,7 @@ __global__ void __launch_bounds__(128) k_rs_temporal(SceneDev D, FrameConsts fc,
 // ---- stage 3 ---------------------------------------------------------------------------------------------------------
 constexpr int RS_MAXN = 9;  // this pixel + up to 8 neighbours
 
-__global__ void __launch_bounds__(128) k_rs_spatial(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, RsBuffers B, uint32_t npix,
+__global__ void __launch_bounds__(128, 5) k_rs_spatial(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, RsBuffers B, uint32_t npix,
                                                     unsigned long long* counters, uint32_t* q_refs, uint32_t* q_count) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long n_shadow = 0;

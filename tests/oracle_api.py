@@ -66,6 +66,8 @@ def lib() -> C.CDLL:
         L.snkor_pixel_scripted.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32]
         L.snkor_sizes.argtypes = [C.c_void_p]
         L.snkor_hardware_threads.restype = C.c_int
+        L.snkor_taa_resolve.argtypes = [C.c_uint32, C.c_uint32] + [C.c_void_p] * 5
+        L.snkor_taa_resolve.restype = None
         _LIB = L
     return _LIB
 
@@ -167,6 +169,17 @@ class OracleFrame:
         if getattr(self, "h", None):
             lib().snkor_frame_destroy(self.h)
             self.h = None
+
+
+def taa_resolve(cur: np.ndarray, velocity: np.ndarray, history: np.ndarray, prev_velocity: np.ndarray) -> np.ndarray:
+    """TAA_Resolve.comp (oracle/snk_taa.h) on (H, W, 4) / (H, W, 2) float16 images; returns the resolved frame."""
+    h, w = cur.shape[:2]
+    cur, history = np.ascontiguousarray(cur, np.float16), np.ascontiguousarray(history, np.float16)
+    velocity, prev_velocity = np.ascontiguousarray(velocity, np.float16), np.ascontiguousarray(prev_velocity, np.float16)
+    assert cur.shape == history.shape == (h, w, 4) and velocity.shape == prev_velocity.shape == (h, w, 2)
+    out = np.zeros_like(cur)
+    lib().snkor_taa_resolve(w, h, _p(cur), _p(velocity), _p(history), _p(prev_velocity), _p(out))
+    return out
 
 
 def camera_rays(scene, ubo, width=None, height=None) -> np.ndarray:

@@ -17,6 +17,8 @@ for name in (sys.argv[1:] or ["c2"]):
     def step(f):
         ubo = bench.frame_ubo(sc, f); prev = bench.frame_ubo(sc, f - 1) if f else ubo
         pt.build_tlas(); pt.set_frame(ubo, prev); pt.trace_primary(); pt.render(st)
+        if os.environ.get("TAA"):
+            pt.taa_resolve()
     for f in range(3):
         step(f)
     pt.synchronize()
