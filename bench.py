@@ -47,6 +47,9 @@ def make_scene(snk, name: str, width: int, height: int):
         return S.c2("flat", subdiv=4, width=width, height=height), "C2 flat subdiv 4: 1,044,482 tris in one BLAS"
     if name == "c3":
         return S.c3(width=width, height=height), "C3: C2 instanced + 854 emissive cubes (10,248 emissive tris)"
+    if name in ("c4", "c4flat"):
+        v = "flat" if name == "c4flat" else "instanced"
+        return S.c4(v, width=width, height=height), f"C4 {v}: floor + 2343 icospheres = 2,999,042 tris" + (" in one BLAS" if v == "flat" else ", 2344 instances")
     if name == "cornell":
         return S.cornell(width, height, True), "C1 Cornell box, 32 tris"
     raise SystemExit(f"unknown scene {name}")

@@ -7,7 +7,8 @@ import bench
 snk = importlib.import_module("snake-vk_b200")
 frames = int(os.environ.get("FRAMES", "6"))
 for name in (sys.argv[1:] or ["c2"]):
-    sc, desc = bench.make_scene(snk, name, 1920, 1080)
+    w, h = (3840, 2160) if name.startswith("c4") else (1920, 1080)  # C4 is the 4K config
+    sc, desc = bench.make_scene(snk, name, w, h)
     t0 = time.time()
     pt = snk.PathTracer(sc.width, sc.height)
     pt.upload_scene(sc)
