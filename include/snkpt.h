@@ -309,6 +309,13 @@ SNKPT_API int snkpt_set_materials(SnkPt* ctx, const SnkMaterial* materials, uint
                                   uint32_t count);
 /* LightBufferSystem::UpdateLightSSBO (LightBufferSystem.cpp:65-108); `bytes`
  * may stop after the last used point light */
+/* Texture2DAsset upload + GlobalTextureBufferManager slot (Core/src/assets/ResourceBufferManagers.cpp:12-62; the
+ * `textures[4096]` descriptor array of TexMatBuffers.glsl): RGBA8 texels of the base level, row-major, top row first.
+ * srgb != 0 = VK_FORMAT_R8G8B8A8_SRGB as base-colour textures are created (AssetLoader.cpp:570). Sampled with linear
+ * filter + repeat addressing (Images.cpp:18-22) through Material::albedo_tex_idx by the hit shading
+ * (RayClosestHit.rchit:115-116) and the G-buffer (GBuffer.frag:57-58). width == 0 frees the slot. Normal / roughness /
+ * metallic / ao maps are not sampled by the ray-tracing shaders and are not uploaded. */
+SNKPT_API int snkpt_set_texture(SnkPt* ctx, uint32_t tex_idx, uint32_t width, uint32_t height, const void* rgba8, uint32_t srgb);
 SNKPT_API int snkpt_set_lights(SnkPt* ctx, const void* light_data, size_t bytes);
 /* TransformBufferSystem::UpdateTransformBuffer (TransformBufferSystem.h:92-122) */
 SNKPT_API int snkpt_set_transforms(SnkPt* ctx, const float* cur_mat4, const float* prev_mat4,

@@ -144,8 +144,9 @@ inline void fill_gbuffer(const Scene& sc, const CommonUBO& cur, const CommonUBO&
       const float mx = (pclip.x / pclip.w - clip.x / clip.w) * 0.5f, my = (pclip.y / pclip.w - clip.y / clip.w) * 0.5f;
       g.motion[2 * px] = f32_to_f16(mx); g.motion[2 * px + 1] = f32_to_f16(my);
       const Material& m = sc.materials[in.material_idx];
-      g.albedo[4 * px] = f32_to_snorm8(m.albedo[0]); g.albedo[4 * px + 1] = f32_to_snorm8(m.albedo[1]);
-      g.albedo[4 * px + 2] = f32_to_snorm8(m.albedo[2]); g.albedo[4 * px + 3] = 127;
+      const vec3 alb = sc.albedo_at(m, ia, ib, ic, b0, b1, b2);  // GBuffer.frag:56-58
+      g.albedo[4 * px] = f32_to_snorm8(alb.x); g.albedo[4 * px + 1] = f32_to_snorm8(alb.y);
+      g.albedo[4 * px + 2] = f32_to_snorm8(alb.z); g.albedo[4 * px + 3] = 127;
       g.normal[4 * px] = f32_to_f16(n.x); g.normal[4 * px + 1] = f32_to_f16(n.y);
       g.normal[4 * px + 2] = f32_to_f16(n.z); g.normal[4 * px + 3] = f32_to_f16(1.0f);
       g.rma[4 * px] = f32_to_f16(m.roughness); g.rma[4 * px + 1] = f32_to_f16(m.metallic);

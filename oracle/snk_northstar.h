@@ -51,7 +51,9 @@ inline NsSurf ns_surface(const Scene& sc, uint32_t inst, uint32_t prim, float u,
   s.p = mul_point(M, p);
   s.n = normalize(mul(sc.normal_matrix[in.transform_idx], n));
   const Material& m = sc.materials[in.material_idx];
-  s.albedo = v3(m.albedo[0], m.albedo[1], m.albedo[2]);
+  // emitted radiance is the material albedo alone (as RayGen.rgen:270 and the emissive-triangle sampling); the albedo
+  // texture modulates reflecting surfaces only
+  s.albedo = (m.flags & MAT_FLAG_EMISSIVE) ? v3(m.albedo[0], m.albedo[1], m.albedo[2]) : sc.albedo_at(m, ia, ib, ic, b0, u, v);
   s.roughness = gmax(m.roughness, 0.05f);
   s.metallic = m.metallic;
   s.flags = m.flags;

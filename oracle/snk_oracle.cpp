@@ -46,6 +46,18 @@ ORACLE_API void* snkor_scene_create(const float* positions, const float* normals
   return sc;
 }
 ORACLE_API void snkor_scene_destroy(void* s) { delete (Scene*)s; }
+// albedo texture `idx` (RGBA8, `srgb` != 0: R8G8B8A8_SRGB) — snk_scene.h:Texture
+ORACLE_API void snkor_scene_set_texture(void* s, uint32_t idx, uint32_t w, uint32_t h, const uint8_t* rgba, uint32_t srgb) {
+  Scene& sc = *(Scene*)s;
+  if (sc.textures.size() <= idx) sc.textures.resize(idx + 1);
+  Texture& t = sc.textures[idx];
+  t.w = w; t.h = h; t.srgb = srgb;
+  t.rgba.assign(rgba, rgba + 4 * (size_t)w * h);
+}
+ORACLE_API void snkor_sample_texture(void* s, uint32_t idx, float u, float v, float* out3) {
+  const vec3 c = sample_texture_rgb(((Scene*)s)->textures[idx], u, v);
+  out3[0] = c.x; out3[1] = c.y; out3[2] = c.z;
+}
 
 // flags: bit0 = any-hit, bit1 = brute force (no BVH)
 ORACLE_API void snkor_trace(void* s, const Ray* rays, uint64_t n, uint32_t flags, Hit* hits, int threads) {

@@ -203,7 +203,7 @@ struct Invocation {
     const vec3 pos = mul_point(sc.transforms[in.transform_idx], p);             // rchit:110
     n = normalize(mul(sc.normal_matrix[in.transform_idx], n));                  // rchit:111
     const Material& m = sc.materials[in.material_idx];                          // rchit:113
-    const vec3 albedo = v3(m.albedo[0], m.albedo[1], m.albedo[2]);              // rchit:114 (untextured)
+    const vec3 albedo = sc.albedo_at(m, ia, ib, ic, b0, b1, b2);                // rchit:100-116
     payload.mat_flags = m.flags;                                                // rchit:118
     if (m.flags & MAT_FLAG_EMISSIVE) { payload.colour = albedo; payload.distance = h.t; return; }  // rchit:119-123
     const vec3 v = normalize(-rd);                                              // rchit:127

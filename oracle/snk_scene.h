@@ -207,8 +207,40 @@ struct Blas {  // one per distinct (index_offset, vertex_offset, num_indices)
   Box bounds;
 };
 
+// Albedo textures (the `textures[]` descriptor array of TexMatBuffers.glsl, sampled by RayClosestHit.rchit:115-116 and
+// GBuffer.frag:57-58). RGBA8; base-colour textures are created R8G8B8A8_SRGB (AssetLoader.cpp:570, AssetManager.cpp:37),
+// sampler = linear filter + repeat addressing (Images.cpp:18-22). A ray-tracing stage has no derivatives, so `texture()`
+// reads the base level; GBuffer.frag's implicit-LOD fetch is restated at the base level too (DEVIATION: the mip the
+// rasteriser would pick is implementation-defined). Filter arithmetic: float32, taps summed left to right (unpinned).
+struct Texture {
+  uint32_t w = 0, h = 0, srgb = 0;
+  std::vector<uint8_t> rgba;
+};
+inline float srgb8_to_linear(uint32_t c) {  // sRGB EOTF evaluated in float64, rounded once
+  const double x = (double)c / 255.0;
+  return (float)(x <= 0.04045 ? x / 12.92 : pow((x + 0.055) / 1.055, 2.4));
+}
+inline vec3 sample_texture_rgb(const Texture& t, float s, float tt) {
+  const float u = s * (float)t.w - 0.5f, v = tt * (float)t.h - 0.5f;
+  const float fu = floorf(u), fv = floorf(v);
+  const float a = u - fu, b = v - fv;
+  auto wrap = [](float f, uint32_t n) { long long i = (long long)f % (long long)n; return (uint32_t)(i < 0 ? i + (long long)n : i); };
+  const uint32_t x0 = wrap(fu, t.w), x1 = wrap(fu + 1.0f, t.w), y0 = wrap(fv, t.h), y1 = wrap(fv + 1.0f, t.h);
+  const float w00 = (1.0f - a) * (1.0f - b), w10 = a * (1.0f - b), w01 = (1.0f - a) * b, w11 = a * b;
+  float out[3];
+  for (int c = 0; c < 3; ++c) {
+    auto tex = [&](uint32_t x, uint32_t y) {
+      const uint32_t q = t.rgba[((size_t)y * t.w + x) * 4 + c];
+      return t.srgb ? srgb8_to_linear(q) : (float)q / 255.0f;
+    };
+    out[c] = ((tex(x0, y0) * w00 + tex(x1, y0) * w10) + tex(x0, y1) * w01) + tex(x1, y1) * w11;
+  }
+  return v3(out[0], out[1], out[2]);
+}
+
 struct Scene {
   std::vector<float> positions, normals, uvs;  // global SoA buffers (MeshBufferManager)
+  std::vector<Texture> textures;
   std::vector<uint32_t> indices;
   std::vector<InstanceData> instances;
   std::vector<mat4> transforms, prev_transforms;
@@ -227,6 +259,16 @@ struct Scene {
 
   vec3 pos(uint32_t i) const { return v3(positions[3 * i], positions[3 * i + 1], positions[3 * i + 2]); }
   vec3 nrm(uint32_t i) const { return v3(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]); }
+  // material albedo times the albedo texture at the interpolated texcoord (rchit:100-116; weights b0,b1,b2 of the 3 vertices)
+  vec3 albedo_at(const Material& m, uint32_t ia, uint32_t ib, uint32_t ic, float b0, float b1, float b2) const {
+    vec3 albedo = v3(m.albedo[0], m.albedo[1], m.albedo[2]);
+    if (m.albedo_tex_idx != 0xFFFFFFFFu && m.albedo_tex_idx < textures.size() && textures[m.albedo_tex_idx].w && uvs.size() >= 2 * (size_t)positions.size() / 3) {
+      const float tu = (uvs[2 * ia] * b0 + uvs[2 * ib] * b1) + uvs[2 * ic] * b2;
+      const float tv = (uvs[2 * ia + 1] * b0 + uvs[2 * ib + 1] * b1) + uvs[2 * ic + 1] * b2;
+      albedo = albedo * sample_texture_rgb(textures[m.albedo_tex_idx], tu, tv);
+    }
+    return albedo;
+  }
 
   void tri_indices(const InstanceData& in, uint32_t prim, uint32_t& a, uint32_t& b, uint32_t& c) const {
     // indices.i[prim + offset/3] + ivec3(vertex_offset)  (RayClosestHit.rchit:91)

@@ -42,7 +42,7 @@ def load_library() -> C.CDLL:
         "snkpt_set_rows": [vp, u32, u32], "snkpt_set_halo": [vp, u32, u32], "snkpt_reset_history": [vp],
         "snkpt_upload_mesh": [vp, vp, vp, vp, vp, u32, vp, u32, vp, u32, vp, vp],
         "snkpt_update_positions": [vp, vp, vp, u32], "snkpt_refit_blas": [vp, u32, vp], "snkpt_rebuild_blas": [vp, u32, vp],
-        "snkpt_set_materials": [vp, vp, u32, u32], "snkpt_set_lights": [vp, vp, sz],
+        "snkpt_set_materials": [vp, vp, u32, u32], "snkpt_set_texture": [vp, u32, u32, u32, vp, u32], "snkpt_set_lights": [vp, vp, sz],
         "snkpt_set_transforms": [vp, vp, vp, u32, u32], "snkpt_set_instances": [vp, vp, vp, u32, vp, u32],
         "snkpt_build_tlas": [vp, vp], "snkpt_set_frame": [vp, vp, vp], "snkpt_trace_primary": [vp, vp, vp],
         "snkpt_render": [vp, vp, vp], "snkpt_accumulate": [vp, i32, vp], "snkpt_taa_resolve": [vp, vp], "snkpt_read_output": [vp, vp, u32],
@@ -70,7 +70,7 @@ EXPORTS = ["snkpt_create", "snkpt_destroy", "snkpt_last_error", "snkpt_default_s
            "snkpt_set_materials", "snkpt_set_lights", "snkpt_set_transforms", "snkpt_set_instances", "snkpt_build_tlas",
            "snkpt_set_frame", "snkpt_trace_primary", "snkpt_render", "snkpt_accumulate", "snkpt_read_output", "snkpt_read_aux",
            "snkpt_aux_size", "snkpt_write_reservoirs", "snkpt_device_ptr", "snkpt_get_stats", "snkpt_synchronize",
-           "snkpt_trace_rays", "snkpt_count_work", "snkpt_set_profiling", "snkpt_get_launch_timings", "snkpt_taa_resolve"]
+           "snkpt_trace_rays", "snkpt_count_work", "snkpt_set_profiling", "snkpt_get_launch_timings", "snkpt_taa_resolve", "snkpt_set_texture"]
 
 CONFIG_DTYPE = np.dtype([("width", "<u4"), ("height", "<u4"), ("device", "<i4"), ("max_instances", "<u4"),
                          ("max_transforms", "<u4"), ("max_materials", "<u4"), ("row_begin", "<u4"), ("row_end", "<u4"),
@@ -187,12 +187,23 @@ class PathTracer:
         for m, (i0, v0, b0) in zip(scene.meshes, flat["mesh_entries"]):
             e = self.upload_mesh(m)
             assert (int(e["data_start_indices_idx"]), int(e["data_start_vertex_idx"]), int(e["blas_id"][0])) == (i0, v0, b0)
+        for i, (texels, srgb) in enumerate(getattr(scene, "textures", [])):
+            self.set_texture(i, texels, srgb)
         self.set_materials(flat["materials"])
         self.set_lights(flat["lights"])
         self.set_transforms(flat["transforms"], flat["prev_transforms"])
         self.set_instances(flat["instances"], flat["blas_of_instance"], flat["emissive_idx"])
         self.build_tlas()
         return flat
+
+    def set_texture(self, idx: int, rgba8: np.ndarray | None, srgb: bool = True):
+        """Texture2DAsset upload into slot `idx` of the albedo texture table (None frees the slot)."""
+        if rgba8 is None:
+            self._ck(self.L.snkpt_set_texture(self.h, idx, 0, 0, None, 0), "snkpt_set_texture")
+            return
+        t = np.ascontiguousarray(rgba8, np.uint8)
+        assert t.ndim == 3 and t.shape[2] == 4
+        self._ck(self.L.snkpt_set_texture(self.h, idx, t.shape[1], t.shape[0], _p(t), int(bool(srgb))), "snkpt_set_texture")
 
     # ---- frame
     def set_frame(self, cur: np.ndarray, prev: np.ndarray | None = None):

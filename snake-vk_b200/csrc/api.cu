@@ -177,6 +177,7 @@ SceneDev SnkPt::scene_dev() const {
   D.lights = lights.as<SnkLightData>();
   D.emissive_idx = emissive_idx.as<uint32_t>();
   D.num_emissive = num_emissive; D.num_instances = num_instances;
+  D.textures = tex_table.as<TexDev>(); D.srgb_lut = srgb_lut.as<float>(); D.num_textures = (uint32_t)h_tex.size();
   D.em_table = em_table.as<float4>(); D.em_base_of_obj = em_base_of_obj.as<uint32_t>(); D.em_base = em_base.as<uint32_t>();
   return D;
 }
@@ -273,7 +274,8 @@ void snkpt_destroy(SnkPt* ctx) {
                     &ctx->d_blas, &ctx->materials, &ctx->lights, &ctx->transforms, &ctx->prev_transforms, &ctx->normal_mats,
                     &ctx->det3, &ctx->instances, &ctx->blas_of_instance, &ctx->emissive_idx, &ctx->tlas_nodes, &ctx->tlas_leaf_ids,
                     &ctx->inst_recs, &ctx->valid_slots, &ctx->q_rays, &ctx->q_hits, &ctx->q_work, &ctx->dev_counters, &ctx->trav_spill,
-                    &ctx->wave_refs, &ctx->wave_paths, &ctx->prof_work, &ctx->prof_hits, &ctx->em_table, &ctx->em_base_of_obj, &ctx->em_base};
+                    &ctx->wave_refs, &ctx->wave_paths, &ctx->prof_work, &ctx->prof_hits, &ctx->em_table, &ctx->em_base_of_obj, &ctx->em_base, &ctx->tex_table, &ctx->srgb_lut};
+  for (auto& b : ctx->tex_data) b.release();
   for (DevBuf* b : bufs) b->release();
   for (auto& b : ctx->wave) b.release();
   for (auto& b : ctx->px) b.release();
@@ -506,6 +508,40 @@ int snkpt_set_materials(SnkPt* ctx, const SnkMaterial* materials, uint32_t first
   REQUIRE(materials && (uint64_t)first + count <= ctx->max_materials, SNKPT_E_INVALID, "snkpt_set_materials: range");
   CK(cudaSetDevice(ctx->device));
   CK(cudaMemcpyAsync(ctx->materials.as<SnkMaterial>() + first, materials, sizeof(SnkMaterial) * count, cudaMemcpyHostToDevice, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return SNKPT_OK;
+}
+
+int snkpt_set_texture(SnkPt* ctx, uint32_t tex_idx, uint32_t width, uint32_t height, const void* rgba8, uint32_t srgb) {
+  if (!ctx) return SNKPT_E_INVALID;
+  REQUIRE(tex_idx < 4096, SNKPT_E_INVALID, "snkpt_set_texture: index (the descriptor array has 4096 slots)");
+  REQUIRE((width == 0 && height == 0) || (rgba8 && width <= 16384 && height <= 16384 && width && height), SNKPT_E_INVALID, "snkpt_set_texture: size / null texels");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(ctx->stream));
+  if (ctx->h_tex.size() <= tex_idx) { ctx->h_tex.resize(tex_idx + 1, TexDev{nullptr, 0, 0, 0, 0}); ctx->tex_data.resize(tex_idx + 1); }
+  DevBuf& buf = ctx->tex_data[tex_idx];
+  buf.release();
+  TexDev& td = ctx->h_tex[tex_idx];
+  td = TexDev{nullptr, 0, 0, 0, 0};
+  if (width) {
+    const size_t bytes = 4ull * width * height;
+    CK(buf.reserve(bytes, false, ctx->stream));
+    CK(cudaMemcpyAsync(buf.p, rgba8, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    td = TexDev{buf.as<uchar4>(), width, height, srgb ? 1u : 0u, 0u};
+  }
+  if (!ctx->srgb_lut.p) {
+    // sRGB EOTF in float64, rounded once (oracle/snk_scene.h:srgb8_to_linear evaluates the same expression)
+    float lut[256];
+    for (int c = 0; c < 256; ++c) {
+      const double x = (double)c / 255.0;
+      lut[c] = (float)(x <= 0.04045 ? x / 12.92 : pow((x + 0.055) / 1.055, 2.4));
+    }
+    CK(ctx->srgb_lut.reserve(sizeof(lut), false, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->srgb_lut.p, lut, sizeof(lut), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+  }
+  CK(ctx->tex_table.reserve(sizeof(TexDev) * 4096, false, ctx->stream));
+  CK(cudaMemcpyAsync(ctx->tex_table.p, ctx->h_tex.data(), sizeof(TexDev) * ctx->h_tex.size(), cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaStreamSynchronize(ctx->stream));
   return SNKPT_OK;
 }

@@ -77,6 +77,9 @@ struct PixelPlanes {
   ushort4* taa_hist[2]; ushort2* taa_prev_vel[2];
 };
 
+// one entry of the albedo texture table (snkpt_set_texture): RGBA8 texels, base level only
+struct TexDev { const uchar4* texels; uint32_t w, h, srgb, pad; };
+
 struct SceneDev {
   const float *positions, *normals, *uvs;
   const uint32_t* indices;
@@ -94,6 +97,10 @@ struct SceneDev {
   const float4* em_table;
   const uint32_t* em_base_of_obj;
   const uint32_t* em_base;  // per emissive-list entry k: first record of emissive_idx[k]
+  // albedo textures (TexMatBuffers.glsl `textures[]`): table indexed by Material::albedo_tex_idx, sRGB decode table
+  const TexDev* textures;
+  const float* srgb_lut;
+  uint32_t num_textures;
 };
 
 }  // namespace snk
@@ -122,6 +129,9 @@ struct SnkPt {
   std::vector<float> h_transforms, h_prev_transforms;
   uint32_t num_instances = 0, num_emissive = 0, num_pointlights = 0;
   snk::DevBuf materials, lights, transforms, prev_transforms, normal_mats, det3, instances, blas_of_instance, emissive_idx;
+  snk::DevBuf tex_table, srgb_lut;  // albedo textures
+  std::vector<snk::DevBuf> tex_data;
+  std::vector<snk::TexDev> h_tex;
   snk::DevBuf em_table, em_base_of_obj, em_base;  // emissive-triangle table (rebuilt every north-star frame)
   uint32_t num_emissive_tris = 0;
 

@@ -9,7 +9,7 @@
 // thread moves its own texel to the prev planes before overwriting it.
 // Compiled with -fmad=false (see vecmath.cuh).
 #include "kernels.h"
-#include "vecmath.cuh"
+#include "shading.cuh"
 
 namespace snk {
 
@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(128, PRIMARY_CTAS_PER_SM) k_primary(TraceScene
   const float mx = (pclip.x / pclip.w - clip.x / clip.w) * 0.5f, my = (pclip.y / pclip.w - clip.y / clip.w) * 0.5f;
   P.motion[px] = make_ushort2(f2h(mx), f2h(my));
   const SnkMaterial* m = D.materials + in.material_idx;
-  const float4 alb = *reinterpret_cast<const float4*>(m->albedo);
+  const vec3 alb = albedo_at(D, m, ia, ib, ic, b0, b1, b2);  // GBuffer.frag:56-58
   P.albedo[px] = make_char4(f2snorm8(alb.x), f2snorm8(alb.y), f2snorm8(alb.z), 127);
   P.normal[px] = make_ushort4(f2h(n.x), f2h(n.y), f2h(n.z), f2h(1.0f));
   P.rma[px] = make_ushort4(f2h(m->roughness), f2h(m->metallic), f2h(m->ao), f2h(1.0f));

@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(128, 8) k_ns_gen(SceneDev D, FrameConsts fc, P
 // the hit of the ray that left vertex x_{b-1} becomes vertex x_b. One thread per path that is still alive (compact list
 // written by the previous stage): a path that ended keeps its last pending next-event term in C / vis, which k_ns_resolve
 // adds — the same sum, in the same order, as visiting the dead pixel here would give
-__global__ void __launch_bounds__(128) k_ns_vertex(SceneDev D, FrameConsts fc, NsBuffers B, uint32_t npix, uint32_t b, uint32_t max_bounces,
+__global__ void __launch_bounds__(128, 6) k_ns_vertex(SceneDev D, FrameConsts fc, NsBuffers B, uint32_t npix, uint32_t b, uint32_t max_bounces,
                                                    uint32_t nee_from, unsigned long long* counters, uint32_t* q_refs, uint32_t* q_count,
                                                    const uint32_t* paths_in, const uint32_t* paths_in_count, uint32_t* paths_out,
                                                    uint32_t* paths_out_count) {
@@ -226,10 +226,12 @@ __global__ void __launch_bounds__(256) k_ns_resolve(SceneDev D, FrameConsts fc, 
   const size_t px = (size_t)y * fc.W + x;
   vec3 out = v3(0.0f);
   if (P.prim[px] != INVALID_IDX) {
-    const float2 bc = P.bary[px];
-    const NsSurf s = ns_surface(D, P.inst[px], P.prim[px], bc.x, bc.y);
-    if (s.flags & SNKPT_MAT_FLAG_EMISSIVE) out = s.albedo;
-    else {
+    // an emissive primary hit shows its emission = the material albedo (what ns_surface returns for it)
+    const SnkMaterial* m = D.materials + __ldg(&D.instances[P.inst[px]].material_idx);
+    if (__ldg(&m->flags) & SNKPT_MAT_FLAG_EMISSIVE) {
+      const float4 alb = __ldg(reinterpret_cast<const float4*>(m->albedo));
+      out = v3(alb.x, alb.y, alb.z);
+    } else {
       const float4 L4 = B.L[i];
       vec3 L = v3(L4.x, L4.y, L4.z);
       if (max_bounces >= nee_from) {

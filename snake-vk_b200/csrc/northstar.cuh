@@ -35,11 +35,16 @@ static __device__ __noinline__ NsSurf ns_surface(const SceneDev& D, uint32_t ins
   s.p = mul_point(M, p);
   s.n = normalize(mul_mat3r(D.normal_mats + 9ull * in.transform_idx, n));
   const SnkMaterial* m = D.materials + in.material_idx;
-  const float4 alb = __ldg(reinterpret_cast<const float4*>(m->albedo));
-  s.albedo = v3(alb.x, alb.y, alb.z);
+  s.flags = __ldg(&m->flags);
+  // emitted radiance is the material albedo alone (RayGen.rgen:270, emissive table); the texture modulates reflectors only
+  if (s.flags & SNKPT_MAT_FLAG_EMISSIVE) {
+    const float4 alb = __ldg(reinterpret_cast<const float4*>(m->albedo));
+    s.albedo = v3(alb.x, alb.y, alb.z);
+  } else {
+    s.albedo = albedo_at(D, m, ia, ib, ic, b0, u, v);
+  }
   s.roughness = gmax(__ldg(&m->roughness), 0.05f);
   s.metallic = __ldg(&m->metallic);
-  s.flags = __ldg(&m->flags);
   s.ntri = in.num_mesh_indices / 3u;
   const vec3 wa = mul_point(M, pa), wb = mul_point(M, pb), wc = mul_point(M, pc);
   s.area = 0.5f * length(cross(wb - wa, wc - wa));

@@ -136,6 +136,48 @@ __device__ __forceinline__ SnkInstanceData load_instance(const SceneDev& D, uint
   return r;
 }
 
+// ---- albedo texture (RayClosestHit.rchit:100-116, GBuffer.frag:56-58) ---------------------------------------------------
+// bilinear, repeat addressing, base level, sRGB decode through a 256-entry table (CPU statement: oracle/snk_scene.h
+// sample_texture_rgb — same float32 expressions in the same order)
+__device__ __forceinline__ uint32_t tex_wrap(float f, uint32_t n) {
+  long long i = (long long)f % (long long)n;
+  return (uint32_t)(i < 0 ? i + (long long)n : i);
+}
+static __device__ __noinline__ vec3 sample_texture_rgb(const SceneDev& D, uint32_t tex, float s, float t) {
+  const TexDev td = D.textures[tex];
+  const float u = s * (float)td.w - 0.5f, v = t * (float)td.h - 0.5f;
+  const float fu = floorf(u), fv = floorf(v);
+  const float a = u - fu, b = v - fv;
+  const uint32_t x0 = tex_wrap(fu, td.w), x1 = tex_wrap(fu + 1.0f, td.w), y0 = tex_wrap(fv, td.h), y1 = tex_wrap(fv + 1.0f, td.h);
+  const float w00 = (1.0f - a) * (1.0f - b), w10 = a * (1.0f - b), w01 = (1.0f - a) * b, w11 = a * b;
+  const uchar4 t00 = __ldg(td.texels + (size_t)y0 * td.w + x0), t10 = __ldg(td.texels + (size_t)y0 * td.w + x1);
+  const uchar4 t01 = __ldg(td.texels + (size_t)y1 * td.w + x0), t11 = __ldg(td.texels + (size_t)y1 * td.w + x1);
+  vec3 c;
+  if (td.srgb) {
+    const float* L = D.srgb_lut;
+    c.x = ((__ldg(L + t00.x) * w00 + __ldg(L + t10.x) * w10) + __ldg(L + t01.x) * w01) + __ldg(L + t11.x) * w11;
+    c.y = ((__ldg(L + t00.y) * w00 + __ldg(L + t10.y) * w10) + __ldg(L + t01.y) * w01) + __ldg(L + t11.y) * w11;
+    c.z = ((__ldg(L + t00.z) * w00 + __ldg(L + t10.z) * w10) + __ldg(L + t01.z) * w01) + __ldg(L + t11.z) * w11;
+  } else {
+    c.x = (((float)t00.x / 255.0f * w00 + (float)t10.x / 255.0f * w10) + (float)t01.x / 255.0f * w01) + (float)t11.x / 255.0f * w11;
+    c.y = (((float)t00.y / 255.0f * w00 + (float)t10.y / 255.0f * w10) + (float)t01.y / 255.0f * w01) + (float)t11.y / 255.0f * w11;
+    c.z = (((float)t00.z / 255.0f * w00 + (float)t10.z / 255.0f * w10) + (float)t01.z / 255.0f * w01) + (float)t11.z / 255.0f * w11;
+  }
+  return c;
+}
+// material albedo times the albedo texture at the interpolated texcoord (weights b0, b1, b2 of vertices ia, ib, ic)
+__device__ __forceinline__ vec3 albedo_at(const SceneDev& D, const SnkMaterial* m, uint32_t ia, uint32_t ib, uint32_t ic, float b0, float b1, float b2) {
+  const float4 alb = __ldg(reinterpret_cast<const float4*>(m->albedo));
+  vec3 albedo = v3(alb.x, alb.y, alb.z);
+  const uint32_t tex = __ldg(&m->albedo_tex_idx);
+  if (tex != INVALID_IDX && tex < D.num_textures && D.uvs != nullptr && D.textures[tex].w != 0u) {
+    const float tu = (__ldg(D.uvs + 2ull * ia) * b0 + __ldg(D.uvs + 2ull * ib) * b1) + __ldg(D.uvs + 2ull * ic) * b2;
+    const float tv = (__ldg(D.uvs + 2ull * ia + 1) * b0 + __ldg(D.uvs + 2ull * ib + 1) * b1) + __ldg(D.uvs + 2ull * ic + 1) * b2;
+    albedo = albedo * sample_texture_rgb(D, tex, tu, tv);
+  }
+  return albedo;
+}
+
 // point on an emissive triangle: shared head of RayGen.rgen:241-251 and :258-268.
 // bary = (bx, by, 1-bx-by) weights of (ti.x, ti.y, ti.z) — NOT the hit-attribute convention.
 struct TriPoint { vec3 p, n, emissive; };
@@ -188,8 +230,7 @@ __device__ __forceinline__ HitShade shade_hit(const SceneDev& D, vec3 ldir, vec3
   const vec3 pos = mul_point(D.transforms + 16ull * in.transform_idx, p);
   n = normalize(mul_mat3r(D.normal_mats + 9ull * in.transform_idx, n));
   const SnkMaterial* m = D.materials + in.material_idx;
-  const float4 alb = __ldg(reinterpret_cast<const float4*>(m->albedo));
-  const vec3 albedo = v3(alb.x, alb.y, alb.z);
+  const vec3 albedo = albedo_at(D, m, ia, ib, ic, b0, b1, b2);
   const float roughness = __ldg(&m->roughness), metallic = __ldg(&m->metallic);
   o.mat_flags = __ldg(&m->flags);
   o.distance = t;

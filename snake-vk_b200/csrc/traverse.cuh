@@ -252,7 +252,10 @@ __device__ __forceinline__ void load_node(const uint4* __restrict__ nodes, uint3
 //   pop phase   lanes whose group is exhausted pop the stack (a sentinel pops back to world space)
 // Stack: SHORT_STACK entries per lane in shared memory (interleaved by thread), deeper entries in a per-warp
 // global spill area (interleaved by lane) that stays L1/L2 resident.
-constexpr int SHORT_STACK = 8;
+#ifndef SNK_SHORT_STACK
+#define SNK_SHORT_STACK 8
+#endif
+constexpr int SHORT_STACK = SNK_SHORT_STACK;
 constexpr int SPILL_STACK = 40;
 
 struct StackRef {

@@ -290,6 +290,7 @@ class Scene:
     dir_light_colour: tuple = (0.0, 0.0, 0.0)
     dir_light_spherical: tuple = (0.0, 0.0)
     pointlights: np.ndarray = field(default_factory=lambda: np.zeros((0, 12), F32))  # colour4,pos4,exp,lin,const,pad
+    textures: list = field(default_factory=list)  # [(rgba8 (H, W, 4) uint8, srgb flag)], indexed by Material.tex[0]
 
     # ---- what the reference's buffer systems would produce
     def flatten(self) -> dict:
@@ -507,6 +508,28 @@ def c5_soup(n_tris: int, seed=0x5EED0005) -> Mesh:
     scale = rng.uniform(0.5, 2.0, n)
     euler = rng.uniform(0, 360.0, (n, 3))
     return merge_meshes([sphere] * n, [trs(pos[i], euler[i], (scale[i],) * 3) for i in range(n)])
+
+
+def textured_test_scene(width=96, height=64, seed=11) -> Scene:
+    """small_test_scene with albedo textures: planar texcoords that leave [0,1] (repeat addressing), one sRGB
+    power-of-two texture and one UNORM texture of odd size (RayClosestHit.rchit:100-116, GBuffer.frag:56-58)."""
+    sc = small_test_scene(width, height, seed=seed)
+    rng = np.random.default_rng(seed)
+    for m in sc.meshes:
+        p = m.positions
+        m.uvs = np.ascontiguousarray(np.stack([p[:, 0] * 0.37 + p[:, 2] * 0.11 + 0.25, p[:, 1] * 0.29 - p[:, 2] * 0.23 + 0.5], -1), F32)
+    t0 = rng.integers(0, 256, (8, 16, 4), dtype=np.uint8)
+    yy, xx = np.mgrid[0:8, 0:16]
+    t0[(xx // 2 + yy // 2) % 2 == 0, :3] //= 4  # checker: strong contrast so that filtering errors show
+    t1 = rng.integers(0, 256, (7, 5, 4), dtype=np.uint8)
+    sc.textures = [(t0, 1), (t1, 0)]
+    mats = sc.materials.copy()
+    for i in range(mats.shape[0]):
+        if not (int(mats["flags"][i]) & MAT_FLAG_EMISSIVE or i % 3 == 2):
+            mats["tex"][i, 0] = i % 2
+    mats["tex"][mats.shape[0] - 1, 0] = 1  # also on the last material whatever it is (an emissive one keeps its plain albedo as emission)
+    sc.materials = mats
+    return sc
 
 
 def small_test_scene(width=96, height=64, seed=7, n_spheres=6, with_emissive=True) -> Scene:

@@ -68,6 +68,10 @@ def lib() -> C.CDLL:
         L.snkor_hardware_threads.restype = C.c_int
         L.snkor_taa_resolve.argtypes = [C.c_uint32, C.c_uint32] + [C.c_void_p] * 5
         L.snkor_taa_resolve.restype = None
+        L.snkor_scene_set_texture.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32]
+        L.snkor_scene_set_texture.restype = None
+        L.snkor_sample_texture.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_void_p]
+        L.snkor_sample_texture.restype = None
         _LIB = L
     return _LIB
 
@@ -107,6 +111,14 @@ class OracleScene:
             _p(f["positions"]), _p(f["normals"]), _p(f["uvs"]), f["positions"].shape[0], _p(f["indices"]), f["indices"].size,
             _p(f["instances"]), f["instances"].shape[0], _p(f["transforms"]), _p(f["prev_transforms"]), f["transforms"].shape[0],
             _p(f["materials"]), f["materials"].shape[0], _p(lights), lights.size, _p(f["emissive_idx"]), f["emissive_idx"].size)
+        for i, (texels, srgb) in enumerate(getattr(scene, "textures", [])):
+            t = np.ascontiguousarray(texels, np.uint8)
+            lib().snkor_scene_set_texture(self.h, i, t.shape[1], t.shape[0], _p(t), int(bool(srgb)))
+
+    def sample_texture(self, idx: int, u: float, v: float) -> np.ndarray:
+        out = np.zeros(3, np.float32)
+        lib().snkor_sample_texture(self.h, idx, u, v, _p(out))
+        return out
 
     def trace(self, rays: np.ndarray, any_hit=False, brute=False, threads=8) -> np.ndarray:
         rays = np.ascontiguousarray(rays)

@@ -424,3 +424,51 @@ def test_ns_restir_full_reuse_bias_is_bounded_and_variance_drops(snk, oracle):
             imgs.append(frq.read("direct")[..., :3].copy())
         return np.stack(imgs[8:]).var(0)[body].mean()
     assert frame_var(num_spatial=0) < 0.5 * frame_var(num_temporal=0, num_spatial=0)
+
+
+# ---- albedo textures (oracle/snk_scene.h:sample_texture_rgb; RayClosestHit.rchit:115-116, GBuffer.frag:57-58) ----------
+def test_texture_sampling_known_answers(snk, oracle):
+    sc = snk.scenes.textured_test_scene(32, 24)
+    osc = oracle.OracleScene(sc)
+    t0, t1 = sc.textures[0][0], sc.textures[1][0]
+    h0, w0 = t0.shape[:2]
+    h1, w1 = t1.shape[:2]
+
+    def eotf(c):
+        x = c / 255.0
+        return np.float32(x / 12.92 if x <= 0.04045 else ((x + 0.055) / 1.055) ** 2.4)
+
+    # texel centres return the texel itself (weights 1,0,0,0): sRGB decoded for texture 0, /255 for texture 1
+    for (x, y) in [(0, 0), (5, 3), (15, 7)]:
+        got = osc.sample_texture(0, (x + 0.5) / w0, (y + 0.5) / h0)
+        assert np.array_equal(got, np.array([eotf(int(c)) for c in t0[y, x, :3]], np.float32))
+    for (x, y) in [(0, 0), (4, 6), (2, 3)]:
+        got = osc.sample_texture(1, (x + 0.5) / w1, (y + 0.5) / h1)
+        assert np.array_equal(got, (t1[y, x, :3].astype(np.float32) / np.float32(255.0)))
+    # repeat addressing: one period away is the same texel; u = 0 blends the last and first column half / half
+    assert np.array_equal(osc.sample_texture(1, (2 + 0.5) / w1 + 3.0, (3 + 0.5) / h1 - 2.0), osc.sample_texture(1, (2 + 0.5) / w1, (3 + 0.5) / h1))
+    edge = osc.sample_texture(1, 0.0, (3 + 0.5) / h1)
+    want = (t1[3, w1 - 1, :3].astype(np.float32) / np.float32(255)) * np.float32(0.5) + (t1[3, 0, :3].astype(np.float32) / np.float32(255)) * np.float32(0.5)
+    assert np.allclose(edge, want, rtol=0, atol=1e-7)
+    # midpoint between two texels of a row = their mean
+    mid = osc.sample_texture(1, 2.0 / w1, (3 + 0.5) / h1)
+    want = (t1[3, 1, :3].astype(np.float32) + t1[3, 2, :3].astype(np.float32)) / np.float32(255) * np.float32(0.5)
+    assert np.allclose(mid, want, rtol=0, atol=1e-6)
+
+
+def test_textures_change_the_frame(snk, oracle):
+    sc = snk.scenes.textured_test_scene(48, 32)
+    plain = snk.scenes.textured_test_scene(48, 32)
+    plain.textures = []
+    outs = []
+    for s in (sc, plain):
+        fr = oracle.OracleFrame(oracle.OracleScene(s))
+        ubo = s.ubo(0)
+        fr.set(ubo, ubo, oracle.default_settings())
+        fr.gbuffer()
+        fr.render()
+        outs.append((fr.read("albedo").copy(), fr.read("radiance").copy()))
+    assert not np.array_equal(outs[0][0], outs[1][0]), "the G-buffer albedo must see the texture"
+    assert not np.array_equal(outs[0][1], outs[1][1])
+    hit = fr.read("prim") != 0xFFFFFFFF
+    assert (outs[0][0][hit][:, :3].astype(np.int32) <= outs[1][0][hit][:, :3].astype(np.int32) + 1).all(), "texture values are <= 1: albedo can only get darker"
