@@ -283,6 +283,8 @@ void snkpt_destroy(SnkPt* ctx) {
   scratch_free(ctx->scratch_blas);
   scratch_free(ctx->scratch_tlas);
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+  if (ctx->ev_stage) cudaEventDestroy(ctx->ev_stage);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   for (auto& r : ctx->prof) { if (r.e0) cudaEventDestroy(r.e0); if (r.e1) cudaEventDestroy(r.e1); }
   ctx->prof_work.release(); ctx->prof_hits.release();
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -638,10 +640,22 @@ int snkpt_build_tlas(SnkPt* ctx, void* stream) {
   if (!ctx) return SNKPT_E_INVALID;
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
-  // BLAS::GenerateInstance (TLAS.cpp:188-200): one record per instance slot that references a BLAS
-  std::vector<SnkInstRec> recs(ctx->num_instances);
-  std::vector<uint32_t> valid;
-  valid.reserve(ctx->num_instances);
+  // BLAS::GenerateInstance (TLAS.cpp:188-200): one record per instance slot that references a BLAS.
+  // The records are staged in pinned host memory owned by the context so that the upload is a true asynchronous copy:
+  // no stream synchronisation per frame (the host may run a frame ahead of the GPU). ev_stage guards the reuse.
+  const size_t need = (sizeof(SnkInstRec) + 4) * (size_t)ctx->max_instances;
+  if (ctx->h_stage_bytes < need) {
+    if (ctx->h_stage) { CK(cudaStreamSynchronize(st)); cudaFreeHost(ctx->h_stage); ctx->h_stage = nullptr; ctx->h_stage_bytes = 0; }
+    CK(cudaMallocHost(&ctx->h_stage, need));
+    ctx->h_stage_bytes = need;
+    if (!ctx->ev_stage) CK(cudaEventCreateWithFlags(&ctx->ev_stage, cudaEventDisableTiming));
+  } else if (ctx->stage_in_flight) {
+    CK(cudaEventSynchronize(ctx->ev_stage));
+  }
+  ctx->stage_in_flight = false;
+  SnkInstRec* recs = reinterpret_cast<SnkInstRec*>(ctx->h_stage);
+  uint32_t* valid = reinterpret_cast<uint32_t*>(recs + ctx->max_instances);
+  uint32_t n = 0;
   float nm[9], det;
   for (uint32_t i = 0; i < ctx->num_instances; ++i) {
     SnkInstRec& r = recs[i];
@@ -652,9 +666,8 @@ int snkpt_build_tlas(SnkPt* ctx, void* stream) {
     REQUIRE((size_t)t * 16 + 16 <= ctx->h_transforms.size(), SNKPT_E_STATE, "snkpt_build_tlas: instance references a transform that was never set");
     derive_transform(ctx->h_transforms.data() + 16 * (size_t)t, r.w2o, nm, &det);
     r.blas_root = ctx->blas[b].node_root; r.custom_idx = i; r.blas_id = b; r.flags = 0;
-    valid.push_back(i);
+    valid[n++] = i;
   }
-  const uint32_t n = (uint32_t)valid.size();
   CK(ctx->inst_recs.reserve(sizeof(SnkInstRec) * (size_t)(ctx->max_instances), false, st));
   CK(ctx->valid_slots.reserve(4 * (size_t)ctx->max_instances, false, st));
   CK(ctx->tlas_nodes.reserve(sizeof(SnkNode8) * (size_t)(ctx->max_instances + 1), false, st));
@@ -664,8 +677,10 @@ int snkpt_build_tlas(SnkPt* ctx, void* stream) {
   ctx->tlas_built = true;
   if (n == 0) return SNKPT_OK;
   cudaEventRecord(ctx->ev[6], st);
-  CK(cudaMemcpyAsync(ctx->inst_recs.p, recs.data(), sizeof(SnkInstRec) * recs.size(), cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(ctx->valid_slots.p, valid.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->inst_recs.p, recs, sizeof(SnkInstRec) * (size_t)ctx->num_instances, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->valid_slots.p, valid, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+  CK(cudaEventRecord(ctx->ev_stage, st));
+  ctx->stage_in_flight = true;
   BuildScratch& s = ctx->scratch_tlas;
   launch_instance_bounds(s, ctx->transforms.as<float>(), ctx->instances.as<SnkInstanceData>(), ctx->blas_of_instance.as<uint32_t>(),
                          ctx->d_blas.as<SnkBlasInfo>(), ctx->blas_nodes.as<SnkNode8>(), ctx->valid_slots.as<uint32_t>(), n, st);
@@ -674,10 +689,8 @@ int snkpt_build_tlas(SnkPt* ctx, void* stream) {
   out.tris = nullptr; out.leaf_ids = ctx->tlas_leaf_ids.as<uint32_t>(); out.leaf_remap = ctx->valid_slots.as<uint32_t>(); out.leaf_offset = 0;
   ctx->stats.kernel_launches += 2 + launch_build(s, n, out, nullptr, nullptr, 0, 0, st);
   cudaEventRecord(ctx->ev[7], st);
-  // the host copies above are consumed asynchronously: wait before `recs` / `valid` go out of scope
-  CK(cudaStreamSynchronize(st));
+  ctx->build_timing_pending = true;  // ms_build_last is read from ev[6..7] by snkpt_get_stats
   CK(cudaGetLastError());
-  cudaEventElapsedTime(&ctx->stats.ms_build_last, ctx->ev[6], ctx->ev[7]);
   return SNKPT_OK;
 }
 
@@ -916,6 +929,10 @@ int snkpt_get_stats(SnkPt* ctx, SnkPtStats* out) {
   if (!ctx || !out) return SNKPT_E_INVALID;
   cudaSetDevice(ctx->device);
   if (ctx->gbuffer_valid && cudaEventQuery(ctx->ev[1]) == cudaSuccess) cudaEventElapsedTime(&ctx->stats.ms_primary, ctx->ev[0], ctx->ev[1]);
+  if (ctx->build_timing_pending && cudaEventSynchronize(ctx->ev[7]) == cudaSuccess) {
+    cudaEventElapsedTime(&ctx->stats.ms_build_last, ctx->ev[6], ctx->ev[7]);
+    ctx->build_timing_pending = false;
+  }
   uint32_t c[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (cudaDeviceSynchronize() == cudaSuccess && cudaMemcpy(c, ctx->dev_counters.p, sizeof(c), cudaMemcpyDeviceToHost) == cudaSuccess) {
     ctx->stats.stack_overflows = c[0];

@@ -175,10 +175,8 @@ __device__ __forceinline__ unsigned long long expand21(unsigned long long x) {
   return x;
 }
 
-__global__ void k_morton(const float4* __restrict__ prim_lo, const float4* __restrict__ prim_hi, uint32_t n,
-                         const uint32_t* __restrict__ counters, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+__device__ __forceinline__ unsigned long long morton_key(const float4* __restrict__ prim_lo, const float4* __restrict__ prim_hi, uint32_t i,
+                                                         const uint32_t* __restrict__ counters) {
   const float lx = ord2f(counters[C_BOUNDS]), ly = ord2f(counters[C_BOUNDS + 1]), lz = ord2f(counters[C_BOUNDS + 2]);
   const float hx = ord2f(counters[C_BOUNDS + 3]), hy = ord2f(counters[C_BOUNDS + 4]), hz = ord2f(counters[C_BOUNDS + 5]);
   const float4 a = prim_lo[i], b = prim_hi[i];
@@ -187,7 +185,13 @@ __global__ void k_morton(const float4* __restrict__ prim_lo, const float4* __res
   const float qx = fminf(fmaxf((0.5f * (a.x + b.x) - lx) * sx, 0.f), 2097151.f);
   const float qy = fminf(fmaxf((0.5f * (a.y + b.y) - ly) * sy, 0.f), 2097151.f);
   const float qz = fminf(fmaxf((0.5f * (a.z + b.z) - lz) * sz, 0.f), 2097151.f);
-  keys[i] = (expand21((unsigned long long)qx) << 2) | (expand21((unsigned long long)qy) << 1) | expand21((unsigned long long)qz);
+  return (expand21((unsigned long long)qx) << 2) | (expand21((unsigned long long)qy) << 1) | expand21((unsigned long long)qz);
+}
+__global__ void k_morton(const float4* __restrict__ prim_lo, const float4* __restrict__ prim_hi, uint32_t n,
+                         const uint32_t* __restrict__ counters, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  keys[i] = morton_key(prim_lo, prim_hi, i, counters);
   vals[i] = i;
 }
 
@@ -320,10 +324,8 @@ __device__ __forceinline__ int delta(const unsigned long long* __restrict__ keys
   return __clzll((long long)(a ^ b));
 }
 
-__global__ void k_karras(const unsigned long long* __restrict__ keys, int n, int* __restrict__ left, int* __restrict__ right,
-                         int* __restrict__ parent, int* __restrict__ first, int* __restrict__ last) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n - 1) return;
+__device__ __forceinline__ void karras_node(const unsigned long long* __restrict__ keys, int n, int i, int* __restrict__ left,
+                                            int* __restrict__ right, int* __restrict__ parent, int* __restrict__ first, int* __restrict__ last) {
   const int d = (delta(keys, n, i, i + 1) - delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
   const int dmin = delta(keys, n, i, i - d);
   int lmax = 2;
@@ -347,13 +349,17 @@ __global__ void k_karras(const unsigned long long* __restrict__ keys, int n, int
   first[i] = lo; last[i] = hi;
   if (i == 0) parent[0] = -1;
 }
+__global__ void k_karras(const unsigned long long* __restrict__ keys, int n, int* __restrict__ left, int* __restrict__ right,
+                         int* __restrict__ parent, int* __restrict__ first, int* __restrict__ last) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  karras_node(keys, n, i, left, right, parent, first, last);
+}
 
-__global__ void k_refit_binary(const float4* __restrict__ prim_lo, const float4* __restrict__ prim_hi,
-                               const uint32_t* __restrict__ sorted_prims, int n, const int* __restrict__ left,
-                               const int* __restrict__ right, const int* __restrict__ parent, float4* bb_lo, float4* bb_hi,
-                               uint32_t* flags) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
+__device__ __forceinline__ void refit_from_leaf(const float4* __restrict__ prim_lo, const float4* __restrict__ prim_hi,
+                                                const uint32_t* __restrict__ sorted_prims, int n, int k, const int* __restrict__ left,
+                                                const int* __restrict__ right, const int* __restrict__ parent, float4* bb_lo, float4* bb_hi,
+                                                uint32_t* flags) {
   const uint32_t p = sorted_prims[k];
   int node = n - 1 + k;
   float4 lo = prim_lo[p], hi = prim_hi[p];
@@ -372,6 +378,14 @@ __global__ void k_refit_binary(const float4* __restrict__ prim_lo, const float4*
     node = par;
     par = parent[node];
   }
+}
+__global__ void k_refit_binary(const float4* __restrict__ prim_lo, const float4* __restrict__ prim_hi,
+                               const uint32_t* __restrict__ sorted_prims, int n, const int* __restrict__ left,
+                               const int* __restrict__ right, const int* __restrict__ parent, float4* bb_lo, float4* bb_hi,
+                               uint32_t* flags) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  refit_from_leaf(prim_lo, prim_hi, sorted_prims, n, k, left, right, parent, bb_lo, bb_hi, flags);
 }
 
 // ---- collapse to 8-wide nodes ---------------------------------------------------------------
@@ -591,6 +605,72 @@ __global__ void __launch_bounds__(128) k_collapse(CollapseArgs a) {
   }
 }
 
+// ---- whole build in ONE CTA for small inputs (the per-frame TLAS: TlasSystem::BuildTlas rebuilds <= 4096 instances every
+// frame, TlasSystem.cpp:27-49). The general path above needs 37 launches (8 radix passes x 4 + Morton, Karras, refit,
+// collapse ...) and was launch-latency bound: 0.38 ms for the 205 instances of C2. Here: Morton codes -> bitonic sort of
+// (key, index) pairs in shared memory -> Karras hierarchy -> bottom-up boxes -> level-synchronous collapse, with
+// __syncthreads() where the general path has kernel boundaries or grid syncs.
+constexpr int SMALL_MAX = 4096, SMALL_THREADS = 1024;
+__global__ void __launch_bounds__(SMALL_THREADS) k_build_small(const float4* __restrict__ prim_lo, const float4* __restrict__ prim_hi, int n,
+                                                               uint32_t* counters, unsigned long long* keys_g, uint32_t* vals_g, int* left,
+                                                               int* right, int* parent, int* first, int* last, float4* bb_lo, float4* bb_hi,
+                                                               uint32_t* flags, CollapseArgs a) {
+  __shared__ unsigned long long sk[SMALL_MAX];
+  __shared__ uint32_t sv[SMALL_MAX];
+  const int t = threadIdx.x;
+  int np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  for (int i = t; i < np2; i += SMALL_THREADS) {
+    sk[i] = i < n ? morton_key(prim_lo, prim_hi, (uint32_t)i, counters) : ~0ull;
+    sv[i] = (uint32_t)i;
+  }
+  for (int i = t; i < n; i += SMALL_THREADS) flags[i] = 0u;
+  __syncthreads();
+  // bitonic sort by (key, index): the index breaks ties the way the stable radix sort of the general path does
+  for (int k = 2; k <= np2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = t; i < np2; i += SMALL_THREADS) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long ka = sk[i], kb = sk[ixj];
+          const uint32_t va = sv[i], vb = sv[ixj];
+          const bool a_gt_b = ka > kb || (ka == kb && va > vb);
+          const bool up = (i & k) == 0;
+          if (a_gt_b == up) { sk[i] = kb; sk[ixj] = ka; sv[i] = vb; sv[ixj] = va; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = t; i < n; i += SMALL_THREADS) { keys_g[i] = sk[i]; vals_g[i] = sv[i]; }
+  if (n > 1) {
+    for (int i = t; i < n - 1; i += SMALL_THREADS) karras_node(sk, n, i, left, right, parent, first, last);
+  } else if (t == 0) {
+    parent[0] = -1;  // the only leaf is the root
+  }
+  __threadfence();
+  __syncthreads();
+  for (int k = t; k < n; k += SMALL_THREADS) refit_from_leaf(prim_lo, prim_hi, vals_g, n, k, left, right, parent, bb_lo, bb_hi, flags);
+  __threadfence();
+  __syncthreads();
+  // collapse, level by level (queue[0] = binary root and counters[C_NODES] = 1 were set by k_init)
+  volatile uint32_t& s_end = *reinterpret_cast<volatile uint32_t*>(&sk[0]);  // the keys are dead by now (static smem is at its 48 KB limit)
+  uint32_t begin = 0, end = 1;
+  while (begin < end) {
+    for (uint32_t w = begin + t; w < end; w += SMALL_THREADS) process_wide_node(a, w, (int)a.queue[w]);
+    __threadfence();
+    __syncthreads();
+    if (t == 0) {
+      const uint32_t total = *((volatile uint32_t*)&a.counters[C_NODES]);
+      s_end = total < a.node_capacity ? total : a.node_capacity;
+    }
+    __syncthreads();
+    begin = end;
+    end = s_end;
+    __syncthreads();
+  }
+}
+
 // ---- topology-preserving refit of a built BVH8 (animated vertices) -------------------------------------------
 // (no reference counterpart: the reference never updates a BLAS, TLAS.cpp:63 — BASELINE config "build + refit sweep")
 // k_refit_parents  once per BLAS: parent index of every wide node
@@ -749,6 +829,19 @@ int launch_build(BuildScratch& s, uint32_t n, const BuildOutput& out, const floa
   int launches = 0;
   if (n == 0) return 0;
   const uint32_t g = (n + 255) / 256;
+#ifndef SNK_NO_SMALL_BUILD
+  if (n <= (uint32_t)SMALL_MAX) {
+    const uint32_t cap = out.node_capacity < n ? out.node_capacity : n;
+    CollapseArgs a;
+    a.n = (int)n; a.left = s.left; a.right = s.right; a.first = s.first; a.last = s.last; a.bb_lo = s.bb_lo; a.bb_hi = s.bb_hi;
+    a.sorted_prims = s.vals[0]; a.queue = s.queue; a.counters = s.counters; a.nodes = out.nodes; a.node_offset = out.node_offset;
+    a.node_capacity = cap; a.tris = out.tris; a.leaf_ids = out.leaf_ids; a.leaf_remap = out.leaf_remap; a.leaf_offset = out.leaf_offset;
+    a.positions = positions; a.indices = indices; a.index_offset = index_offset; a.vertex_offset = vertex_offset;
+    k_build_small<<<1, SMALL_THREADS, 0, st>>>(s.prim_lo, s.prim_hi, (int)n, s.counters, s.keys[0], s.vals[0], s.left, s.right, s.parent, s.first,
+                                              s.last, s.bb_lo, s.bb_hi, s.flags, a);
+    return 1;
+  }
+#endif
   k_morton<<<g, 256, 0, st>>>(s.prim_lo, s.prim_hi, n, s.counters, s.keys[0], s.vals[0]); ++launches;
   int cur = 0;
   if (n > 1) {

@@ -139,6 +139,10 @@ struct SnkPt {
   snk::DevBuf tlas_nodes, tlas_leaf_ids, inst_recs, valid_slots;
   uint32_t tlas_prims = 0;
   bool tlas_built = false;
+  void* h_stage = nullptr;       // pinned staging of the per-frame instance records (snkpt_build_tlas)
+  size_t h_stage_bytes = 0;
+  cudaEvent_t ev_stage = nullptr;
+  bool stage_in_flight = false, build_timing_pending = false;
 
   // per pixel
   snk::DevBuf px[32];
