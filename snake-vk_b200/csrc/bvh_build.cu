@@ -20,7 +20,17 @@ constexpr int SORT_THREADS = 256;
 constexpr int SORT_ITEMS = 16;                                  // keys per thread
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;            // 4096 keys per CTA
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int LEAF_MAX = 3;                                     // triangles per leaf slot
+#ifndef SNK_LEAF_MAX_BLAS
+#define SNK_LEAF_MAX_BLAS 2
+#endif
+#ifndef SNK_LEAF_MAX_TLAS
+#define SNK_LEAF_MAX_TLAS 1
+#endif
+// primitives per leaf slot (<= 3: the slot's meta byte holds a unary count). Triangles: 3. Instances: 1 — entering an
+// instance costs a ray transform plus at least the BLAS root test, so every instance gets its own box test first
+// (with 3 per slot a ray entered 5.1 instances on C2, with 1 it enters 2.6: frame 8.08 -> 7.52 ms; 2 instead of 3 triangles per
+// slot: 7.29 ms, 1: 7.27 ms with 30 % more nodes — profiles/r02d_variants_leaf_size.txt).
+constexpr int LEAF_MAX_BLAS = SNK_LEAF_MAX_BLAS, LEAF_MAX_TLAS = SNK_LEAF_MAX_TLAS;
 
 enum { C_NODES = 0, C_LEAVES = 1, C_DONE = 2, C_TICKET = 3, C_OVERFLOW = 4, C_BOUNDS = 8 };
 
@@ -180,8 +190,14 @@ __device__ __forceinline__ unsigned long long morton_key(const float4* __restric
   const float lx = ord2f(counters[C_BOUNDS]), ly = ord2f(counters[C_BOUNDS + 1]), lz = ord2f(counters[C_BOUNDS + 2]);
   const float hx = ord2f(counters[C_BOUNDS + 3]), hy = ord2f(counters[C_BOUNDS + 4]), hz = ord2f(counters[C_BOUNDS + 5]);
   const float4 a = prim_lo[i], b = prim_hi[i];
+#ifdef SNK_MORTON_UNIFORM
+  // one scale for the three axes (cubic cells): a flat scene does not spend its top bits on the short axis
+  const float ext = fmaxf(fmaxf(hx - lx, hy - ly), hz - lz);
+  const float sx = ext > 0.f ? 2097152.0f / ext : 0.f, sy = sx, sz = sx;
+#else
   const float sx = hx > lx ? 2097152.0f / (hx - lx) : 0.f, sy = hy > ly ? 2097152.0f / (hy - ly) : 0.f,
               sz = hz > lz ? 2097152.0f / (hz - lz) : 0.f;
+#endif
   const float qx = fminf(fmaxf((0.5f * (a.x + b.x) - lx) * sx, 0.f), 2097151.f);
   const float qy = fminf(fmaxf((0.5f * (a.y + b.y) - ly) * sy, 0.f), 2097151.f);
   const float qz = fminf(fmaxf((0.5f * (a.z + b.z) - lz) * sz, 0.f), 2097151.f);
@@ -405,6 +421,7 @@ struct CollapseArgs {
   const float* positions;
   const uint32_t* indices;
   uint32_t index_offset, vertex_offset;
+  int leaf_max;
 };
 
 __device__ __forceinline__ float half_area(float4 lo, float4 hi) {
@@ -474,7 +491,7 @@ __device__ void process_wide_node(const CollapseArgs& a, uint32_t w, int b) {
     cnt[0] = node_count(a, l); cnt[1] = node_count(a, r);
     area[0] = half_area(a.bb_lo[l], a.bb_hi[l]); area[1] = half_area(a.bb_lo[r], a.bb_hi[r]);
     for (int phase = 0; phase < 2; ++phase) {
-      const int min_open = phase == 0 ? LEAF_MAX + 1 : 2;
+      const int min_open = phase == 0 ? a.leaf_max + 1 : 2;
       while (m < 8) {
         int best = -1; float barea = -1.f;
         for (int i = 0; i < m; ++i)
@@ -529,7 +546,7 @@ __device__ void process_wide_node(const CollapseArgs& a, uint32_t w, int b) {
   // ---- allocate inner children + leaf records
   int n_inner = 0, n_leafrec = 0;
   for (int i = 0; i < m; ++i) {
-    if (cnt[i] > LEAF_MAX) ++n_inner; else n_leafrec += cnt[i];
+    if (cnt[i] > a.leaf_max) ++n_inner; else n_leafrec += cnt[i];
   }
   uint32_t child_base = 0, rec_base = 0;
   if (n_inner) child_base = atomicAdd(&a.counters[C_NODES], (uint32_t)n_inner);
@@ -557,7 +574,7 @@ __device__ void process_wide_node(const CollapseArgs& a, uint32_t w, int b) {
     quantise_child(nlo, be, lo[i], hi[i], ql, qh);
     nd.qlox[s] = ql[0]; nd.qloy[s] = ql[1]; nd.qloz[s] = ql[2];
     nd.qhix[s] = qh[0]; nd.qhiy[s] = qh[1]; nd.qhiz[s] = qh[2];
-    if (cnt[i] > LEAF_MAX) {
+    if (cnt[i] > a.leaf_max) {
       if (inner_rank < (uint32_t)n_inner) {
         nd.imask |= (uint8_t)(1u << s);
         nd.meta[s] = (uint8_t)((1u << 5) | (24u + s));
@@ -837,6 +854,7 @@ int launch_build(BuildScratch& s, uint32_t n, const BuildOutput& out, const floa
     a.sorted_prims = s.vals[0]; a.queue = s.queue; a.counters = s.counters; a.nodes = out.nodes; a.node_offset = out.node_offset;
     a.node_capacity = cap; a.tris = out.tris; a.leaf_ids = out.leaf_ids; a.leaf_remap = out.leaf_remap; a.leaf_offset = out.leaf_offset;
     a.positions = positions; a.indices = indices; a.index_offset = index_offset; a.vertex_offset = vertex_offset;
+    a.leaf_max = out.tris ? LEAF_MAX_BLAS : LEAF_MAX_TLAS;
     k_build_small<<<1, SMALL_THREADS, 0, st>>>(s.prim_lo, s.prim_hi, (int)n, s.counters, s.keys[0], s.vals[0], s.left, s.right, s.parent, s.first,
                                               s.last, s.bb_lo, s.bb_hi, s.flags, a);
     return 1;
@@ -867,6 +885,7 @@ int launch_build(BuildScratch& s, uint32_t n, const BuildOutput& out, const floa
   a.sorted_prims = s.vals[cur]; a.queue = s.queue; a.counters = s.counters; a.nodes = out.nodes; a.node_offset = out.node_offset;
   a.node_capacity = cap; a.tris = out.tris; a.leaf_ids = out.leaf_ids; a.leaf_remap = out.leaf_remap; a.leaf_offset = out.leaf_offset;
   a.positions = positions; a.indices = indices; a.index_offset = index_offset; a.vertex_offset = vertex_offset;
+    a.leaf_max = out.tris ? LEAF_MAX_BLAS : LEAF_MAX_TLAS;
   {
     static int ctas_per_sm = 0, sms = 0;
     if (!ctas_per_sm) {
