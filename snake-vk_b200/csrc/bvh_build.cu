@@ -114,15 +114,16 @@ __device__ __forceinline__ void child_box(const SnkNode8& nd, int s, float* lo, 
   lo[0] = nd.px + (float)nd.qlox[s] * sx; lo[1] = nd.py + (float)nd.qloy[s] * sy; lo[2] = nd.pz + (float)nd.qloz[s] * sz;
   hi[0] = nd.px + (float)nd.qhix[s] * sx; hi[1] = nd.py + (float)nd.qhiy[s] * sy; hi[2] = nd.pz + (float)nd.qhiz[s] * sz;
 }
+// world AABB of an object-space box under the affine map M (column-major mat4): centre M*c, half extent |M|*e — the
+// same box as transforming the 8 corners, at a quarter of the arithmetic (the caller pads the result)
 __device__ __forceinline__ void grow_by_transformed_box(const float* __restrict__ M, const float* blo, const float* bhi, float* lo, float* hi) {
+  const float cx = 0.5f * (blo[0] + bhi[0]), cy = 0.5f * (blo[1] + bhi[1]), cz = 0.5f * (blo[2] + bhi[2]);
+  const float ex = 0.5f * (bhi[0] - blo[0]), ey = 0.5f * (bhi[1] - blo[1]), ez = 0.5f * (bhi[2] - blo[2]);
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const float x = (c & 1) ? bhi[0] : blo[0], y = (c & 2) ? bhi[1] : blo[1], z = (c & 4) ? bhi[2] : blo[2];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const float w = M[r] * x + M[4 + r] * y + M[8 + r] * z + M[12 + r];
-      lo[r] = fminf(lo[r], w); hi[r] = fmaxf(hi[r], w);
-    }
+  for (int r = 0; r < 3; ++r) {
+    const float c = M[r] * cx + M[4 + r] * cy + M[8 + r] * cz + M[12 + r];
+    const float e = fabsf(M[r]) * ex + fabsf(M[4 + r]) * ey + fabsf(M[8 + r]) * ez;
+    lo[r] = fminf(lo[r], c - e); hi[r] = fmaxf(hi[r], c + e);
   }
 }
 
@@ -634,19 +635,19 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_build_small(const float4* __r
                                                                uint32_t* flags, CollapseArgs a) {
   __shared__ unsigned long long sk[SMALL_MAX];
   __shared__ uint32_t sv[SMALL_MAX];
-  const int t = threadIdx.x;
+  const int t = threadIdx.x, NT = blockDim.x;  // launched with as many threads as there are elements to sort (128..1024)
   int np2 = 1;
   while (np2 < n) np2 <<= 1;
-  for (int i = t; i < np2; i += SMALL_THREADS) {
+  for (int i = t; i < np2; i += NT) {
     sk[i] = i < n ? morton_key(prim_lo, prim_hi, (uint32_t)i, counters) : ~0ull;
     sv[i] = (uint32_t)i;
   }
-  for (int i = t; i < n; i += SMALL_THREADS) flags[i] = 0u;
+  for (int i = t; i < n; i += NT) flags[i] = 0u;
   __syncthreads();
   // bitonic sort by (key, index): the index breaks ties the way the stable radix sort of the general path does
   for (int k = 2; k <= np2; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = t; i < np2; i += SMALL_THREADS) {
+      for (int i = t; i < np2; i += NT) {
         const int ixj = i ^ j;
         if (ixj > i) {
           const unsigned long long ka = sk[i], kb = sk[ixj];
@@ -659,22 +660,22 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_build_small(const float4* __r
       __syncthreads();
     }
   }
-  for (int i = t; i < n; i += SMALL_THREADS) { keys_g[i] = sk[i]; vals_g[i] = sv[i]; }
+  for (int i = t; i < n; i += NT) { keys_g[i] = sk[i]; vals_g[i] = sv[i]; }
   if (n > 1) {
-    for (int i = t; i < n - 1; i += SMALL_THREADS) karras_node(sk, n, i, left, right, parent, first, last);
+    for (int i = t; i < n - 1; i += NT) karras_node(sk, n, i, left, right, parent, first, last);
   } else if (t == 0) {
     parent[0] = -1;  // the only leaf is the root
   }
   __threadfence();
   __syncthreads();
-  for (int k = t; k < n; k += SMALL_THREADS) refit_from_leaf(prim_lo, prim_hi, vals_g, n, k, left, right, parent, bb_lo, bb_hi, flags);
+  for (int k = t; k < n; k += NT) refit_from_leaf(prim_lo, prim_hi, vals_g, n, k, left, right, parent, bb_lo, bb_hi, flags);
   __threadfence();
   __syncthreads();
   // collapse, level by level (queue[0] = binary root and counters[C_NODES] = 1 were set by k_init)
   volatile uint32_t& s_end = *reinterpret_cast<volatile uint32_t*>(&sk[0]);  // the keys are dead by now (static smem is at its 48 KB limit)
   uint32_t begin = 0, end = 1;
   while (begin < end) {
-    for (uint32_t w = begin + t; w < end; w += SMALL_THREADS) process_wide_node(a, w, (int)a.queue[w]);
+    for (uint32_t w = begin + t; w < end; w += NT) process_wide_node(a, w, (int)a.queue[w]);
     __threadfence();
     __syncthreads();
     if (t == 0) {
@@ -855,7 +856,9 @@ int launch_build(BuildScratch& s, uint32_t n, const BuildOutput& out, const floa
     a.node_capacity = cap; a.tris = out.tris; a.leaf_ids = out.leaf_ids; a.leaf_remap = out.leaf_remap; a.leaf_offset = out.leaf_offset;
     a.positions = positions; a.indices = indices; a.index_offset = index_offset; a.vertex_offset = vertex_offset;
     a.leaf_max = out.tris ? LEAF_MAX_BLAS : LEAF_MAX_TLAS;
-    k_build_small<<<1, SMALL_THREADS, 0, st>>>(s.prim_lo, s.prim_hi, (int)n, s.counters, s.keys[0], s.vals[0], s.left, s.right, s.parent, s.first,
+    uint32_t threads = 128;
+    while (threads < n && threads < (uint32_t)SMALL_THREADS) threads <<= 1;
+    k_build_small<<<1, threads, 0, st>>>(s.prim_lo, s.prim_hi, (int)n, s.counters, s.keys[0], s.vals[0], s.left, s.right, s.parent, s.first,
                                               s.last, s.bb_lo, s.bb_hi, s.flags, a);
     return 1;
   }
