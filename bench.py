@@ -216,7 +216,11 @@ def run_gpu_arm(args, snk):
         pt.set_halo(bands.pass1_halo, bands.gbuffer_halo)
         # the three SoA planes of the FINAL reservoirs (buffer half 0), aliased for the NCCL halo exchange
         res_planes = [torch.as_tensor(CudaArray(pt.device_ptr(0x110 + k)[0], (H, W, 4)), device=f"cuda:{local}") for k in range(3)]
-    stream = torch.cuda.current_stream().cuda_stream
+    # one explicit stream for the frames, the timing events and the NCCL calls: the library enqueues on the stream it is given
+    # (and its small uploads follow the frame's stream), so events recorded on this stream bracket exactly the work timed
+    work = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(work)
+    stream = work.cuda_stream
     seed_off = rank if (world > 1 and args.shard == "samples") else 0
     rad = None
     if world > 1 and args.shard == "samples":
@@ -287,26 +291,41 @@ def run_gpu_arm(args, snk):
 
         # ---- end to end through the C ABI with host buffers (rank-local; max over ranks)
         if with_e2e:
-            out_host = torch.empty((rows[1] - rows[0], W, 4), dtype=torch.float16, pin_memory=True)
-            out_np = out_host.numpy()
+            # two page-locked images: frame k is copied out (own copy stream) while frame k+1 renders, the way the engine's
+            # frames in flight present one frame while recording the next; every step still lands one finished image on the host
+            out_host = [torch.empty((rows[1] - rows[0], W, 4), dtype=torch.float16, pin_memory=True) for _ in range(2)]
+            out_np = out_host[0].numpy()
+            out_nps = [t.numpy() for t in out_host]
             h2d = 2 * 240 + 2 * flat["transforms"].nbytes + flat["instances"].nbytes + flat["blas_of_instance"].nbytes + flat["emissive_idx"].nbytes
             pt.set_profiling(0)
+            reads = rank == 0 or rad is None
+            kk = [0]
 
             def e2e_step():
+                k = kk[0]
+                kk[0] += 1
                 pt.set_transforms(flat["transforms"], flat["prev_transforms"])  # TransformBufferSystem: cur + prev, host → device
                 pt.set_instances(flat["instances"], flat["blas_of_instance"], flat["emissive_idx"])
                 step()
-                if rank == 0 or rad is None:
-                    pt.read_output("f16", out_np)  # device → host: the RGBA16F image the engine would present
+                if reads:
+                    pt.read_output_async(out_nps[k % 2], slot=k % 2)  # device → host: the RGBA16F image the engine would present
+                    if k:
+                        pt.wait_output((k - 1) % 2)                   # the previous frame is now on the host
+
+            def e2e_drain():
+                if reads and kk[0]:
+                    pt.wait_output((kk[0] - 1) % 2)
 
             e2e_steps = max(3, min(args.steps, 10))
             for _ in range(2):
                 e2e_step()
+            e2e_drain()
             barrier()
             st2 = pt.stats()
             e0.record()
             for _ in range(e2e_steps):
                 e2e_step()
+            e2e_drain()
             e1.record()
             barrier()
             e2e_ms = e0.elapsed_time(e1)

@@ -357,6 +357,12 @@ SNKPT_API int snkpt_taa_resolve(SnkPt* ctx, void* stream);
 /* internal_render_image (EditorLayer.cpp:389-395): RGBA16F, linear, alpha 1.
  * Copies rows [row_begin,row_end) × width into dst (device→host, synchronous). */
 SNKPT_API int snkpt_read_output(SnkPt* ctx, void* dst, uint32_t format);
+/* The same copy without blocking: enqueued behind the frame on the context's copy stream, so it overlaps the next
+ * frame (whose kernels wait for it before they overwrite the image). dst should be page-locked. slot = 0 / 1: two reads may
+ * be in flight; snkpt_read_output_wait(slot) returns when that read has landed (the engine presents frame N while N+1 renders,
+ * as the reference's frames in flight do, EditorLayer.cpp:563-665). */
+SNKPT_API int snkpt_read_output_async(SnkPt* ctx, void* dst, uint32_t format, uint32_t slot);
+SNKPT_API int snkpt_read_output_wait(SnkPt* ctx, uint32_t slot);
 SNKPT_API int snkpt_read_aux(SnkPt* ctx, uint32_t what, void* dst, size_t bytes);
 SNKPT_API int snkpt_aux_size(SnkPt* ctx, uint32_t what, size_t* bytes);
 /* overwrite a reservoir half from an AoS host array (tests, halo import) */

@@ -45,7 +45,7 @@ def load_library() -> C.CDLL:
         "snkpt_set_materials": [vp, vp, u32, u32], "snkpt_set_texture": [vp, u32, u32, u32, vp, u32], "snkpt_set_lights": [vp, vp, sz],
         "snkpt_set_transforms": [vp, vp, vp, u32, u32], "snkpt_set_instances": [vp, vp, vp, u32, vp, u32],
         "snkpt_build_tlas": [vp, vp], "snkpt_set_frame": [vp, vp, vp], "snkpt_trace_primary": [vp, vp, vp],
-        "snkpt_render": [vp, vp, vp], "snkpt_accumulate": [vp, i32, vp], "snkpt_taa_resolve": [vp, vp], "snkpt_read_output": [vp, vp, u32],
+        "snkpt_render": [vp, vp, vp], "snkpt_accumulate": [vp, i32, vp], "snkpt_taa_resolve": [vp, vp], "snkpt_read_output": [vp, vp, u32], "snkpt_read_output_async": [vp, vp, u32, u32], "snkpt_read_output_wait": [vp, u32],
         "snkpt_read_aux": [vp, u32, vp, sz], "snkpt_aux_size": [vp, u32, vp],
         "snkpt_write_reservoirs": [vp, u32, vp, u32, u32], "snkpt_device_ptr": [vp, u32, vp, vp],
         "snkpt_get_stats": [vp, vp], "snkpt_synchronize": [vp], "snkpt_trace_rays": [vp, vp, u64, u32, vp, vp],
@@ -70,7 +70,7 @@ EXPORTS = ["snkpt_create", "snkpt_destroy", "snkpt_last_error", "snkpt_default_s
            "snkpt_set_materials", "snkpt_set_lights", "snkpt_set_transforms", "snkpt_set_instances", "snkpt_build_tlas",
            "snkpt_set_frame", "snkpt_trace_primary", "snkpt_render", "snkpt_accumulate", "snkpt_read_output", "snkpt_read_aux",
            "snkpt_aux_size", "snkpt_write_reservoirs", "snkpt_device_ptr", "snkpt_get_stats", "snkpt_synchronize",
-           "snkpt_trace_rays", "snkpt_count_work", "snkpt_set_profiling", "snkpt_get_launch_timings", "snkpt_taa_resolve", "snkpt_set_texture"]
+           "snkpt_trace_rays", "snkpt_count_work", "snkpt_set_profiling", "snkpt_get_launch_timings", "snkpt_taa_resolve", "snkpt_set_texture", "snkpt_read_output_async", "snkpt_read_output_wait"]
 
 CONFIG_DTYPE = np.dtype([("width", "<u4"), ("height", "<u4"), ("device", "<i4"), ("max_instances", "<u4"),
                          ("max_transforms", "<u4"), ("max_materials", "<u4"), ("row_begin", "<u4"), ("row_end", "<u4"),
@@ -247,6 +247,13 @@ class PathTracer:
             out = np.empty((nrows, self.width, 4), dt)
         self._ck(self.L.snkpt_read_output(self.h, _p(out), 0 if fmt == "f16" else 1), "snkpt_read_output")
         return out
+
+    def read_output_async(self, out: np.ndarray, slot: int = 0, fmt="f16"):
+        """enqueue the read-back of the frame rendered last into `out` (page-locked host memory) without blocking"""
+        self._ck(self.L.snkpt_read_output_async(self.h, _p(out), 0 if fmt == "f16" else 1, slot), "snkpt_read_output_async")
+
+    def wait_output(self, slot: int = 0):
+        self._ck(self.L.snkpt_read_output_wait(self.h, slot), "snkpt_read_output_wait")
 
     def read_aux(self, name: str) -> np.ndarray:
         what, dt, ch = AUX[name]

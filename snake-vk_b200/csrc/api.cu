@@ -224,6 +224,53 @@ static int alloc_pixels(SnkPt* ctx) {
   return SNKPT_OK;
 }
 
+// ---- asynchronous small uploads ---------------------------------------------------------------------------------
+static cudaStream_t work_stream(SnkPt* ctx) { return ctx->work_stream ? ctx->work_stream : ctx->stream; }
+// a frame call on another stream than the previous one: order it after everything enqueued so far (uploads, earlier frames)
+static void note_stream(SnkPt* ctx, cudaStream_t st) {
+  cudaStream_t prev = work_stream(ctx);
+  if (prev != st) {
+    if (!ctx->ev_frame_done) cudaEventCreateWithFlags(&ctx->ev_frame_done, cudaEventDisableTiming);
+    cudaEventRecord(ctx->ev_frame_done, prev);
+    cudaStreamWaitEvent(st, ctx->ev_frame_done, 0);
+  }
+  ctx->work_stream = st;
+}
+
+static int upload_async(SnkPt* ctx, void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return SNKPT_OK;
+  cudaStream_t st = work_stream(ctx);
+  if (bytes > SnkPt::RING_CHUNK_BYTES) {  // large and rare: plain copy, caller's memory must outlive it
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));
+    return SNKPT_OK;
+  }
+  if (!ctx->ring) {
+    CK(cudaMallocHost((void**)&ctx->ring, SnkPt::RING_CHUNK_BYTES * SnkPt::RING_CHUNKS));
+    for (int i = 0; i < SnkPt::RING_CHUNKS; ++i) CK(cudaEventCreateWithFlags(&ctx->ring_ev[i], cudaEventDisableTiming));
+  }
+  if (ctx->ring_used + bytes > SnkPt::RING_CHUNK_BYTES) {
+    // leave the chunk: everything copied out of it so far is ordered before this event
+    CK(cudaEventRecord(ctx->ring_ev[ctx->ring_cur], st));
+    ctx->ring_armed[ctx->ring_cur] = true;
+    ctx->ring_cur = (ctx->ring_cur + 1) % SnkPt::RING_CHUNKS;
+    if (ctx->ring_armed[ctx->ring_cur]) { CK(cudaEventSynchronize(ctx->ring_ev[ctx->ring_cur])); ctx->ring_armed[ctx->ring_cur] = false; }
+    ctx->ring_used = 0;
+  }
+  uint8_t* slot = ctx->ring + (size_t)ctx->ring_cur * SnkPt::RING_CHUNK_BYTES + ctx->ring_used;
+  memcpy(slot, src, bytes);
+  CK(cudaMemcpyAsync(dst, slot, bytes, cudaMemcpyHostToDevice, st));
+  ctx->ring_used += (bytes + 255) & ~(size_t)255;
+  return SNKPT_OK;
+}
+
+namespace snk {
+void wait_readback(SnkPt* ctx, cudaStream_t st) {
+  for (int k = 0; k < 2; ++k)
+    if (ctx->read_pending[k]) cudaStreamWaitEvent(st, ctx->ev_read_done[k], 0);
+}
+}  // namespace snk
+
 extern "C" {
 
 int snkpt_create(const SnkPtConfig* cfg, SnkPt** out) {
@@ -284,6 +331,11 @@ void snkpt_destroy(SnkPt* ctx) {
   scratch_free(ctx->scratch_tlas);
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   if (ctx->ev_stage) cudaEventDestroy(ctx->ev_stage);
+  if (ctx->ring) cudaFreeHost(ctx->ring);
+  for (auto& ev : ctx->ring_ev) if (ev) cudaEventDestroy(ev);
+  for (auto& ev : ctx->ev_read_done) if (ev) cudaEventDestroy(ev);
+  if (ctx->ev_frame_done) cudaEventDestroy(ctx->ev_frame_done);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   for (auto& r : ctx->prof) { if (r.e0) cudaEventDestroy(r.e0); if (r.e1) cudaEventDestroy(r.e1); }
   ctx->prof_work.release(); ctx->prof_hits.release();
@@ -509,8 +561,8 @@ int snkpt_set_materials(SnkPt* ctx, const SnkMaterial* materials, uint32_t first
   if (!ctx) return SNKPT_E_INVALID;
   REQUIRE(materials && (uint64_t)first + count <= ctx->max_materials, SNKPT_E_INVALID, "snkpt_set_materials: range");
   CK(cudaSetDevice(ctx->device));
-  CK(cudaMemcpyAsync(ctx->materials.as<SnkMaterial>() + first, materials, sizeof(SnkMaterial) * count, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  int rc = upload_async(ctx, ctx->materials.as<SnkMaterial>() + first, materials, sizeof(SnkMaterial) * count);
+  if (rc) return rc;
   return SNKPT_OK;
 }
 
@@ -555,8 +607,8 @@ int snkpt_set_lights(SnkPt* ctx, const void* light_data, size_t bytes) {
   REQUIRE(L->num_pointlights <= SNKPT_MAX_POINTLIGHTS && 112 + (size_t)L->num_pointlights * 48 <= bytes, SNKPT_E_INVALID,
           "snkpt_set_lights: point-light count exceeds the supplied bytes");
   CK(cudaSetDevice(ctx->device));
-  CK(cudaMemcpyAsync(ctx->lights.p, light_data, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  int rc = upload_async(ctx, ctx->lights.p, light_data, bytes);
+  if (rc) return rc;
   ctx->num_pointlights = L->num_pointlights;
   return SNKPT_OK;
 }
@@ -575,11 +627,11 @@ int snkpt_set_transforms(SnkPt* ctx, const float* cur, const float* prev, uint32
   CK(ctx->det3.reserve(4 * (size_t)ctx->max_transforms, true, ctx->stream));
   std::vector<float> nm(9 * (size_t)count), det(count), w2o(12);
   for (uint32_t i = 0; i < count; ++i) derive_transform(cur + 16 * (size_t)i, w2o.data(), nm.data() + 9 * (size_t)i, &det[i]);
-  CK(cudaMemcpyAsync(ctx->transforms.as<float>() + 16 * (size_t)first, cur, 64 * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->prev_transforms.as<float>() + 16 * (size_t)first, prev ? prev : cur, 64 * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->normal_mats.as<float>() + 9 * (size_t)first, nm.data(), 36 * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->det3.as<float>() + first, det.data(), 4 * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  int rc = upload_async(ctx, ctx->transforms.as<float>() + 16 * (size_t)first, cur, 64 * (size_t)count);
+  if (!rc) rc = upload_async(ctx, ctx->prev_transforms.as<float>() + 16 * (size_t)first, prev ? prev : cur, 64 * (size_t)count);
+  if (!rc) rc = upload_async(ctx, ctx->normal_mats.as<float>() + 9 * (size_t)first, nm.data(), 36 * (size_t)count);
+  if (!rc) rc = upload_async(ctx, ctx->det3.as<float>() + first, det.data(), 4 * (size_t)count);
+  if (rc) return rc;
   ctx->tlas_built = false;
   return SNKPT_OK;
 }
@@ -607,11 +659,13 @@ int snkpt_set_instances(SnkPt* ctx, const SnkInstanceData* instances, const uint
   CK(ctx->instances.reserve(sizeof(SnkInstanceData) * (size_t)ctx->max_instances, false, ctx->stream));
   CK(ctx->blas_of_instance.reserve(4 * (size_t)ctx->max_instances, false, ctx->stream));
   CK(ctx->emissive_idx.reserve(4 * (size_t)ctx->max_instances, false, ctx->stream));
+  int rc = SNKPT_OK;
   if (count) {
-    CK(cudaMemcpyAsync(ctx->instances.p, instances, sizeof(SnkInstanceData) * count, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->blas_of_instance.p, blas_of_instance, 4 * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+    rc = upload_async(ctx, ctx->instances.p, instances, sizeof(SnkInstanceData) * count);
+    if (!rc) rc = upload_async(ctx, ctx->blas_of_instance.p, blas_of_instance, 4 * (size_t)count);
   }
-  if (num_emissive) CK(cudaMemcpyAsync(ctx->emissive_idx.p, emissive_idx, 4 * (size_t)num_emissive, cudaMemcpyHostToDevice, ctx->stream));
+  if (!rc && num_emissive) rc = upload_async(ctx, ctx->emissive_idx.p, emissive_idx, 4 * (size_t)num_emissive);
+  if (rc) return rc;
   // emissive-triangle table: record ranges per emissive-list entry (the first entry of an instance listed twice wins)
   std::vector<uint32_t> base_of_obj(ctx->max_instances, SNKPT_INVALID_INDEX), base(num_emissive ? num_emissive : 1, 0u);
   uint32_t total = 0;
@@ -629,9 +683,9 @@ int snkpt_set_instances(SnkPt* ctx, const SnkInstanceData* instances, const uint
   CK(ctx->em_base_of_obj.reserve(4 * (size_t)ctx->max_instances, false, ctx->stream));
   CK(ctx->em_base.reserve(4 * (size_t)ctx->max_instances, false, ctx->stream));
   CK(ctx->em_table.reserve(192ull * (total ? total : 1), false, ctx->stream));
-  CK(cudaMemcpyAsync(ctx->em_base_of_obj.p, base_of_obj.data(), 4 * (size_t)ctx->max_instances, cudaMemcpyHostToDevice, ctx->stream));
-  if (num_emissive) CK(cudaMemcpyAsync(ctx->em_base.p, base.data(), 4 * (size_t)num_emissive, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  rc = upload_async(ctx, ctx->em_base_of_obj.p, base_of_obj.data(), 4 * (size_t)ctx->max_instances);
+  if (!rc && num_emissive) rc = upload_async(ctx, ctx->em_base.p, base.data(), 4 * (size_t)num_emissive);
+  if (rc) return rc;
   ctx->tlas_built = false;
   return SNKPT_OK;
 }
@@ -640,6 +694,7 @@ int snkpt_build_tlas(SnkPt* ctx, void* stream) {
   if (!ctx) return SNKPT_E_INVALID;
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  note_stream(ctx, st);
   // BLAS::GenerateInstance (TLAS.cpp:188-200): one record per instance slot that references a BLAS.
   // The records are staged in pinned host memory owned by the context so that the upload is a true asynchronous copy:
   // no stream synchronisation per frame (the host may run a frame ahead of the GPU). ev_stage guards the reuse.
@@ -744,6 +799,7 @@ int snkpt_trace_primary(SnkPt* ctx, const float* jitter_xy, void* stream) {
   REQUIRE(ctx->tlas_built, SNKPT_E_STATE, "snkpt_trace_primary: call snkpt_build_tlas first");
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  note_stream(ctx, st);
   fill_frame_dims(ctx);
   ctx->fc.jx = jitter_xy ? jitter_xy[0] : 0.f; ctx->fc.jy = jitter_xy ? jitter_xy[1] : 0.f;
   prof_reset(ctx);
@@ -771,6 +827,7 @@ int snkpt_render(SnkPt* ctx, const SnkRtSettings* settings, void* stream) {
   REQUIRE(settings->num_spatial_resamples >= 0 && settings->num_spatial_resamples <= 64, SNKPT_E_INVALID, "snkpt_render: num_spatial_resamples");
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  note_stream(ctx, st);
   fill_frame_dims(ctx);
   if (ctx->history_mode != settings->mode) ctx->history_valid = false;
   ctx->history_mode = settings->mode;
@@ -785,7 +842,9 @@ int snkpt_accumulate(SnkPt* ctx, int reset, void* stream) {
   if (!ctx) return SNKPT_E_INVALID;
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  note_stream(ctx, st);
   if (reset) ctx->accum_count = 0;
+  wait_readback(ctx, st);
   ctx->stats.kernel_launches += launch_accumulate(ctx->planes, ctx->W * ctx->H, ctx->accum_count, st);
   ctx->accum_count++;
   CK(cudaGetLastError());
@@ -798,6 +857,7 @@ int snkpt_taa_resolve(SnkPt* ctx, void* stream) {
   REQUIRE(ctx->row0 == 0 && ctx->row1 == ctx->H, SNKPT_E_STATE, "snkpt_taa_resolve: whole frames only (gather the row bands first)");
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  note_stream(ctx, st);
   const size_t n = (size_t)ctx->W * ctx->H;
   PixelPlanes& P = ctx->planes;
   const uint32_t cur = ctx->taa_cur, nxt = cur ^ 1u;
@@ -806,6 +866,7 @@ int snkpt_taa_resolve(SnkPt* ctx, void* stream) {
     CK(cudaMemcpyAsync(P.taa_hist[cur], P.out16, 8 * n, cudaMemcpyDeviceToDevice, st));
     CK(cudaMemcpyAsync(P.taa_prev_vel[cur], P.motion, 4 * n, cudaMemcpyDeviceToDevice, st));
   }
+  wait_readback(ctx, st);
   const int rec = prof_begin(ctx, "taa_resolve", n, false, false, st);
   ctx->stats.kernel_launches += launch_taa_resolve(P.out16, P.motion, P.taa_hist[cur], P.taa_prev_vel[cur], P.taa_hist[nxt], P.taa_prev_vel[nxt],
                                                    ctx->W, ctx->H, st);
@@ -867,6 +928,7 @@ int snkpt_read_aux(SnkPt* ctx, uint32_t what, void* dst, size_t bytes) {
   REQUIRE(dst && bytes >= need, SNKPT_E_INVALID, "snkpt_read_aux: destination too small");
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaStreamSynchronize(work_stream(ctx)));
   if (what == SNKPT_AUX_BLAS_TABLE) { memcpy(dst, ctx->blas.data(), need); return SNKPT_OK; }
   if (what == SNKPT_AUX_RESERVOIRS_FINAL || what == SNKPT_AUX_RESERVOIRS_TEMPORAL) {
     // SoA planes → the reference's 48-B AoS record
@@ -907,10 +969,42 @@ int snkpt_read_output(SnkPt* ctx, void* dst, uint32_t format) {
   if (!ctx) return SNKPT_E_INVALID;
   REQUIRE(dst && format <= SNKPT_FMT_RGBA32F, SNKPT_E_INVALID, "snkpt_read_output: arguments");
   CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = work_stream(ctx);
   const size_t off = (size_t)ctx->row0 * ctx->W, cnt = (size_t)(ctx->row1 - ctx->row0) * ctx->W;
-  if (format == SNKPT_FMT_RGBA16F) CK(cudaMemcpyAsync(dst, ctx->planes.out16 + off, 8 * cnt, cudaMemcpyDeviceToHost, ctx->stream));
-  else CK(cudaMemcpyAsync(dst, ctx->planes.radiance + off, 16 * cnt, cudaMemcpyDeviceToHost, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  if (format == SNKPT_FMT_RGBA16F) CK(cudaMemcpyAsync(dst, ctx->planes.out16 + off, 8 * cnt, cudaMemcpyDeviceToHost, st));
+  else CK(cudaMemcpyAsync(dst, ctx->planes.radiance + off, 16 * cnt, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return SNKPT_OK;
+}
+
+int snkpt_read_output_async(SnkPt* ctx, void* dst, uint32_t format, uint32_t slot) {
+  if (!ctx) return SNKPT_E_INVALID;
+  REQUIRE(dst && format <= SNKPT_FMT_RGBA32F && slot < 2, SNKPT_E_INVALID, "snkpt_read_output_async: arguments");
+  CK(cudaSetDevice(ctx->device));
+  if (!ctx->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) CK(cudaEventCreateWithFlags(&ctx->ev_read_done[k], cudaEventDisableTiming));
+    if (!ctx->ev_frame_done) CK(cudaEventCreateWithFlags(&ctx->ev_frame_done, cudaEventDisableTiming));
+  }
+  // the copy starts when everything enqueued on the frame's stream so far is done and runs beside the next frame; kernels that
+  // overwrite the image wait for it (snk::wait_readback)
+  CK(cudaEventRecord(ctx->ev_frame_done, work_stream(ctx)));
+  CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_frame_done, 0));
+  const size_t off = (size_t)ctx->row0 * ctx->W, cnt = (size_t)(ctx->row1 - ctx->row0) * ctx->W;
+  if (format == SNKPT_FMT_RGBA16F) CK(cudaMemcpyAsync(dst, ctx->planes.out16 + off, 8 * cnt, cudaMemcpyDeviceToHost, ctx->copy_stream));
+  else CK(cudaMemcpyAsync(dst, ctx->planes.radiance + off, 16 * cnt, cudaMemcpyDeviceToHost, ctx->copy_stream));
+  CK(cudaEventRecord(ctx->ev_read_done[slot], ctx->copy_stream));
+  ctx->read_pending[slot] = true;
+  return SNKPT_OK;
+}
+
+int snkpt_read_output_wait(SnkPt* ctx, uint32_t slot) {
+  if (!ctx) return SNKPT_E_INVALID;
+  REQUIRE(slot < 2, SNKPT_E_INVALID, "snkpt_read_output_wait: slot");
+  if (!ctx->read_pending[slot]) return SNKPT_OK;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaEventSynchronize(ctx->ev_read_done[slot]));
+  ctx->read_pending[slot] = false;
   return SNKPT_OK;
 }
 
@@ -996,6 +1090,8 @@ int snkpt_synchronize(SnkPt* ctx) {
   if (!ctx) return SNKPT_E_INVALID;
   CK(cudaSetDevice(ctx->device));
   CK(cudaStreamSynchronize(ctx->stream));
+  CK(cudaStreamSynchronize(work_stream(ctx)));
+  if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));
   CK(cudaGetLastError());
   return SNKPT_OK;
 }

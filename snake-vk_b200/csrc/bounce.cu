@@ -235,6 +235,7 @@ int launch_reference_frame(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st) 
     launches += 1 + traced_launch(ctx, "trace_any.B", B.rays_b, nb, true, nullptr, nullptr, nullptr, B.vis_b, st);
   }
   {
+    wait_readback(ctx, st);  // the resolve overwrites the output image
     const int rec = prof_begin(ctx, "bounce_resolve", npix, false, false, st);
     k_bounce_resolve<<<(npix + 255) / 256, 256, 0, st>>>(fc, ctx->planes, B, npix, bounce ? 1 : 0);
     prof_end(ctx, rec, st);

@@ -139,6 +139,20 @@ struct SnkPt {
   snk::DevBuf tlas_nodes, tlas_leaf_ids, inst_recs, valid_slots;
   uint32_t tlas_prims = 0;
   bool tlas_built = false;
+  // small per-frame uploads (transforms, instances, lights, materials) go through a ring of pinned chunks and are enqueued
+  // on the stream the frame runs on: no stream synchronisation per call, ordering with the frame's kernels by stream order
+  static constexpr int RING_CHUNKS = 8;
+  static constexpr size_t RING_CHUNK_BYTES = 1u << 20;
+  uint8_t* ring = nullptr;
+  int ring_cur = 0;
+  size_t ring_used = 0;
+  cudaEvent_t ring_ev[RING_CHUNKS] = {};
+  bool ring_armed[RING_CHUNKS] = {};
+  cudaStream_t work_stream = nullptr;  // stream of the last frame call (snkpt_build_tlas / trace_primary / render), default: `stream`
+  // asynchronous read-back of the output image (snkpt_read_output_async): own copy stream, two slots
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t ev_frame_done = nullptr, ev_read_done[2] = {};
+  bool read_pending[2] = {false, false};
   void* h_stage = nullptr;       // pinned staging of the per-frame instance records (snkpt_build_tlas)
   size_t h_stage_bytes = 0;
   cudaEvent_t ev_stage = nullptr;

@@ -31,6 +31,9 @@ RefQueue ref_queue(SnkPt* ctx, int k, uint32_t cap);
 int reserve_ref_queues(SnkPt* ctx, uint32_t cap, cudaStream_t st);
 void reset_ref_queues(SnkPt* ctx, cudaStream_t st);
 
+// api.cu — a kernel about to overwrite the output image first waits for pending asynchronous read-backs of it
+void wait_readback(SnkPt* ctx, cudaStream_t st);
+
 // api.cu — per-launch profiling (no-ops at level 0)
 void prof_reset(SnkPt* ctx);
 int prof_begin(SnkPt* ctx, const char* name, uint64_t units, bool is_trace, bool any, cudaStream_t st);

@@ -329,6 +329,7 @@ int launch_northstar_frame(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st) 
   }
   if (nee_from) launches += restir_ns_resolve(ctx, st);
   else cudaMemsetAsync(ctx->planes.direct + (size_t)fc.row0 * fc.W, 0, 16ull * npix, st);
+  wait_readback(ctx, st);  // the resolve overwrites the output image
   rec = prof_begin(ctx, "ns_resolve", npix, false, false, st);
   k_ns_resolve<<<(npix + 255) / 256, 256, 0, st>>>(D, fc, ctx->planes, B, npix, max_bounces, nee_from);
   prof_end(ctx, rec, st);

@@ -119,3 +119,14 @@ def test_furnace_energy_bound(snk):
     flags = rt.pt.read_aux("flags")
     body = img[(flags & 1) == 0]
     assert 0.01 < body.mean() < 3.0
+
+
+def test_deep_paths_use_one_queue_per_bounce(snk, oracle):
+    """max_bounces beyond the default: every bounce gets its own reference queue / counter (24 per frame) and stays bit-exact"""
+    sc = snk.scenes.cornell(48, 48, with_pointlight=True)
+    for f, pt, fr in run(snk, oracle, sc, frames=2, max_bounces=12):
+        a, b = pt.read_aux("radiance")[..., :3], fr.read("radiance")[..., :3]
+        assert bits_equal(a, b).mean() >= 0.998
+        st = pt.stats()
+        oc, oa = fr.ray_counts(reset=True)
+        assert (int(st["rays_secondary"]), int(st["rays_shadow"])) == (oc, oa)
