@@ -338,6 +338,13 @@ SNKPT_API int snkpt_set_frame(SnkPt* ctx, const SnkCommonUBO* cur, const SnkComm
  * normal/depth to the prev planes, then fills the G-buffer with primary rays.
  * jitter = sub-pixel offset in pixels (NULL = pixel centres). */
 SNKPT_API int snkpt_trace_primary(SnkPt* ctx, const float* jitter_xy, void* stream);
+/* GetFrameJitter (Core/headers/rendering/RenderCommon.h:39-60): Halton(2,3) - 0.5 over round(8 * (output_w / internal_w)^2)
+ * phases, the push constant GBufferPass hands GBuffer.vert (GBufferPass.cpp:136). GBuffer.vert:90-95 moves the raster
+ * position by (jitter * w - 0.5) / resolution in clip space = jitter / 2 pixels (minus a 0.25 / w pixel term that depends on
+ * the vertex depth); a camera ray cannot carry a per-vertex term, so the equivalent ray offset handed to
+ * snkpt_trace_primary is -jitter / 2 pixels (DEVIATION: the 0.25 / w term is dropped). out_pixels receives that offset. */
+SNKPT_API void snkpt_frame_jitter(uint32_t frame_idx, uint32_t internal_render_width, uint32_t output_render_width,
+                                  float* out_jitter_xy, float* out_pixels_xy);
 /* RT::RecordRenderCmdBuf (Raytracing.cpp:227-267): reservoir pass 1, pass 2,
  * shading and bounce rays; writes the output image */
 SNKPT_API int snkpt_render(SnkPt* ctx, const SnkRtSettings* settings, void* stream);

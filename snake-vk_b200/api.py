@@ -57,6 +57,8 @@ def load_library() -> C.CDLL:
         fn.argtypes = args
         fn.restype = C.c_int
     L.snkpt_default_settings.restype = None
+    L.snkpt_frame_jitter.argtypes = [u32, u32, u32, vp, vp]
+    L.snkpt_frame_jitter.restype = None
     L.snkpt_destroy.argtypes = [vp]
     L.snkpt_destroy.restype = None
     L.snkpt_last_error.argtypes = [vp]
@@ -70,7 +72,7 @@ EXPORTS = ["snkpt_create", "snkpt_destroy", "snkpt_last_error", "snkpt_default_s
            "snkpt_set_materials", "snkpt_set_lights", "snkpt_set_transforms", "snkpt_set_instances", "snkpt_build_tlas",
            "snkpt_set_frame", "snkpt_trace_primary", "snkpt_render", "snkpt_accumulate", "snkpt_read_output", "snkpt_read_aux",
            "snkpt_aux_size", "snkpt_write_reservoirs", "snkpt_device_ptr", "snkpt_get_stats", "snkpt_synchronize",
-           "snkpt_trace_rays", "snkpt_count_work", "snkpt_set_profiling", "snkpt_get_launch_timings", "snkpt_taa_resolve", "snkpt_set_texture", "snkpt_read_output_async", "snkpt_read_output_wait"]
+           "snkpt_trace_rays", "snkpt_count_work", "snkpt_set_profiling", "snkpt_get_launch_timings", "snkpt_taa_resolve", "snkpt_set_texture", "snkpt_read_output_async", "snkpt_read_output_wait", "snkpt_frame_jitter"]
 
 CONFIG_DTYPE = np.dtype([("width", "<u4"), ("height", "<u4"), ("device", "<i4"), ("max_instances", "<u4"),
                          ("max_transforms", "<u4"), ("max_materials", "<u4"), ("row_begin", "<u4"), ("row_end", "<u4"),
@@ -109,6 +111,13 @@ AUX = dict(prim=(0, np.uint32, 1), inst=(1, np.uint32, 1), depth=(2, np.float32,
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def frame_jitter(frame_idx: int, internal_width: int, output_width: int | None = None):
+    """GetFrameJitter (RenderCommon.h:50-59) → (push-constant jitter, equivalent camera-ray offset in pixels)."""
+    j, px = np.zeros(2, np.float32), np.zeros(2, np.float32)
+    load_library().snkpt_frame_jitter(frame_idx, internal_width, output_width or internal_width, _p(j), _p(px))
+    return j, px
 
 
 def default_settings(**kw) -> np.ndarray:

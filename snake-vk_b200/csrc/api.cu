@@ -793,6 +793,27 @@ static void widen_rows(const SnkPt* ctx, uint32_t halo, uint32_t& r0, uint32_t& 
   r1 = ctx->row1 + halo < ctx->H ? ctx->row1 + halo : ctx->H;
 }
 
+static float halton(unsigned idx, unsigned base) {  // RenderCommon.h:39-48
+  float f = 1.f, r = 0.f;
+  while (idx > 0) {
+    f *= (float)base;
+    r += (float)(idx % base) / f;
+    idx /= base;
+  }
+  return r;
+}
+void snkpt_frame_jitter(uint32_t frame_idx, uint32_t internal_render_width, uint32_t output_render_width, float* out_jitter_xy, float* out_pixels_xy) {
+  float jx = 0.f, jy = 0.f;
+  if (internal_render_width != 0 && output_render_width != 0) {  // RenderCommon.h:50-59
+    const float scale_ratio = (float)output_render_width / (float)internal_render_width;
+    const unsigned phases = (unsigned)(8 * scale_ratio * scale_ratio + 0.5f);
+    const unsigned idx = (frame_idx % (phases ? phases : 1u)) + 1;
+    jx = halton(idx, 2) - 0.5f; jy = halton(idx, 3) - 0.5f;
+  }
+  if (out_jitter_xy) { out_jitter_xy[0] = jx; out_jitter_xy[1] = jy; }
+  if (out_pixels_xy) { out_pixels_xy[0] = -0.5f * jx; out_pixels_xy[1] = -0.5f * jy; }
+}
+
 int snkpt_trace_primary(SnkPt* ctx, const float* jitter_xy, void* stream) {
   if (!ctx) return SNKPT_E_INVALID;
   REQUIRE(ctx->frame_set, SNKPT_E_STATE, "snkpt_trace_primary: call snkpt_set_frame first");

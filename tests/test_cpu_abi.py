@@ -54,3 +54,24 @@ def test_light_blob_layout(snk):
     assert int(blob[96:100].view(np.uint32)[0]) == 16 and int(blob[100:104].view(np.uint32)[0]) == 0
     d = blob[16:28].view(np.float32)
     assert abs(float(np.linalg.norm(d)) - 1.0) < 1e-6
+
+
+def test_frame_jitter_halton_sequence(snk):
+    """GetFrameJitter (RenderCommon.h:39-60): Halton(2,3) - 0.5, 8 phases at native resolution, 32 at half resolution"""
+    def halton(i, b):
+        f, r = 1.0, 0.0
+        while i > 0:
+            f *= b
+            r += (i % b) / f
+            i //= b
+        return r
+    seq = [snk.api.frame_jitter(f, 1920)[0] for f in range(17)]
+    for f, j in enumerate(seq):
+        k = f % 8 + 1
+        assert abs(float(j[0]) - (halton(k, 2) - 0.5)) < 1e-6 and abs(float(j[1]) - (halton(k, 3) - 0.5)) < 1e-6
+    assert np.array_equal(seq[0], seq[8]) and not np.array_equal(seq[0], seq[1])
+    assert np.array_equal(snk.api.frame_jitter(0, 960, 1920)[0], snk.api.frame_jitter(32, 960, 1920)[0])      # 32 phases when upscaling 2x
+    assert not np.array_equal(snk.api.frame_jitter(0, 960, 1920)[0], snk.api.frame_jitter(8, 960, 1920)[0])
+    j, px = snk.api.frame_jitter(3, 1920)
+    assert np.array_equal(px, np.float32(-0.5) * j)
+    assert np.array_equal(snk.api.frame_jitter(5, 0, 1920)[0], np.zeros(2, np.float32))
