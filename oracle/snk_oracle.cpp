@@ -80,6 +80,8 @@ ORACLE_API void* snkor_frame_create(void* scene, uint32_t w, uint32_t h) {
   return f;
 }
 ORACLE_API void snkor_frame_destroy(void* f) { delete (Frame*)f; }
+// animated scenes: the frame state (reservoirs, G-buffer history) lives on while the scene buffers of the next frame replace the old ones
+ORACLE_API void snkor_frame_set_scene(void* f, void* scene) { ((Frame*)f)->sc = (Scene*)scene; }
 ORACLE_API void snkor_frame_set(void* fp, const CommonUBO* cur, const CommonUBO* prev, const RtSettings* st) {
   Frame& f = *(Frame*)fp;
   f.ubo = *cur; f.prev_ubo = *prev;

@@ -6,5 +6,5 @@ fails loudly when the CUDA library has not been built: there is no CPU fallback.
 The directory name has a hyphen, so import it with
 `importlib.import_module("snake-vk_b200")`.
 """
-from . import scenes, sharding  # noqa: F401
+from . import scenes, sharding, frontend  # noqa: F401
 from .api import RT, PathTracer, SnkError, load_library, lib_path  # noqa: F401

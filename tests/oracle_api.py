@@ -38,6 +38,7 @@ def lib() -> C.CDLL:
         L.snkor_frame_create.restype = C.c_void_p
         L.snkor_frame_create.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
         L.snkor_frame_destroy.argtypes = [C.c_void_p]
+        L.snkor_frame_set_scene.argtypes = [C.c_void_p, C.c_void_p]
         L.snkor_frame_set.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.snkor_frame_gbuffer.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_uint32, C.c_uint32, C.c_int]
         L.snkor_frame_render.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_int]
