@@ -390,6 +390,28 @@ SNKPT_API int snkpt_set_profiling(SnkPt* ctx, uint32_t level);
 SNKPT_API int snkpt_get_launch_timings(SnkPt* ctx, SnkLaunchTiming* out, uint32_t cap, uint32_t* count);
 SNKPT_API int snkpt_synchronize(SnkPt* ctx);
 
+/* ---- particle collision pass --------------------------------------------
+ * The reference's ParticleSystem (Core/src/scene/ParticleSystem.cpp:224-299) on the same acceleration structures:
+ * per sub-step cell keys (Particle.comp:51-55), key sort, start indices (:77-85), ray-traced collision update
+ * (ParticleUpdate.rgen / .rchit), copy back. */
+typedef struct SnkParticle {      /* Particle.glsl:3-7 */
+  float position_radius[4];
+  float velocity[4];              /* w: 0 = asleep, 1 = awake */
+  float colour[4];
+} SnkParticle;                    /* 48 B */
+typedef struct SnkPhysicsParams { /* PhysicsParamsUBO, Core/headers/scene/ParticleSystem.h:16-24 */
+  float particle_restitution, timestep, friction_coefficient, repulsion_factor, penetration_slop, restitution_slop, sleep_threshold;
+} SnkPhysicsParams;
+SNKPT_API void snkpt_particles_default_params(SnkPhysicsParams* p);
+/* ParticleSystem::InitBuffers + InitParticles (:14-222): allocates `count` particles; init != 0 runs Particle.comp's Init */
+SNKPT_API int snkpt_particles_create(SnkPt* ctx, uint32_t count, int init);
+SNKPT_API int snkpt_particles_write(SnkPt* ctx, const SnkParticle* src, uint32_t first, uint32_t count);
+SNKPT_API int snkpt_particles_read(SnkPt* ctx, SnkParticle* dst, uint32_t first, uint32_t count);
+/* ParticleSystem::UpdateParticles: `substeps` sub-steps (the reference runs 3 per frame) against the current TLAS and the
+ * current / previous transforms; params NULL = defaults. rays_traced (optional) receives the rays of this call after a sync. */
+SNKPT_API int snkpt_particles_update(SnkPt* ctx, const SnkPhysicsParams* params, uint32_t substeps, void* stream);
+SNKPT_API int snkpt_particles_rays(SnkPt* ctx, uint64_t* rays_traced);
+
 /* ---- ray queries --------------------------------------------------------------------- */
 /* traceRayEXT semantics (closest hit in (tmin,tmax), watertight, no culling;
  * ties broken towards the lowest (inst, prim)) over the current TLAS. Used by

@@ -13,6 +13,7 @@
 #include <cstring>
 
 #include "snk_northstar.h"
+#include "snk_particles.h"
 #include "snk_taa.h"
 
 using namespace snkor;
@@ -205,6 +206,26 @@ ORACLE_API void snkor_pixel_scripted(void* fp, uint32_t x, uint32_t y, uint32_t 
 ORACLE_API void snkor_sizes(uint32_t* out8) {
   out8[0] = sizeof(InstanceData); out8[1] = sizeof(Material); out8[2] = sizeof(LightData); out8[3] = sizeof(CommonUBO);
   out8[4] = sizeof(PixelReservoir); out8[5] = sizeof(Ray); out8[6] = sizeof(Hit); out8[7] = sizeof(RtSettings);
+}
+// particle collision pass (snk_particles.h): Particle.comp Init, `substeps` sub-steps of ParticleSystem::UpdateParticles
+ORACLE_API void snkor_particles_init(Particle* p, uint32_t n) {
+  std::vector<Particle> v(n);
+  ptcl_init(v);
+  memcpy(p, v.data(), sizeof(Particle) * n);
+}
+ORACLE_API uint64_t snkor_particles_update(void* scene, Particle* p, uint32_t n, const PhysicsParams* prm, int substeps, int threads) {
+  std::vector<Particle> v(p, p + n);
+  const uint64_t rays = ptcl_update(*(Scene*)scene, v, prm ? *prm : PhysicsParams(), substeps, threads);
+  memcpy(p, v.data(), sizeof(Particle) * n);
+  return rays;
+}
+ORACLE_API void snkor_particles_grid(const Particle* p, uint32_t n, CellKeyEntry* keys, uint32_t* start) {
+  std::vector<Particle> v(p, p + n);
+  std::vector<CellKeyEntry> k;
+  std::vector<uint32_t> s;
+  ptcl_build_grid(v, k, s);
+  memcpy(keys, k.data(), sizeof(CellKeyEntry) * n);
+  memcpy(start, s.data(), 4 * (size_t)n);
 }
 // TAA_Resolve.comp on raw RGBA16F / RG16F planes (snk_taa.h)
 ORACLE_API void snkor_taa_resolve(uint32_t w, uint32_t h, const uint16_t* cur, const uint16_t* velocity, const uint16_t* history,

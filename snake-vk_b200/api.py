@@ -46,6 +46,8 @@ def load_library() -> C.CDLL:
         "snkpt_set_transforms": [vp, vp, vp, u32, u32], "snkpt_set_instances": [vp, vp, vp, u32, vp, u32],
         "snkpt_build_tlas": [vp, vp], "snkpt_set_frame": [vp, vp, vp], "snkpt_trace_primary": [vp, vp, vp],
         "snkpt_render": [vp, vp, vp], "snkpt_accumulate": [vp, i32, vp], "snkpt_taa_resolve": [vp, vp], "snkpt_read_output": [vp, vp, u32], "snkpt_read_output_async": [vp, vp, u32, u32], "snkpt_read_output_wait": [vp, u32],
+        "snkpt_particles_create": [vp, u32, i32], "snkpt_particles_write": [vp, vp, u32, u32], "snkpt_particles_read": [vp, vp, u32, u32],
+        "snkpt_particles_update": [vp, vp, u32, vp], "snkpt_particles_rays": [vp, vp],
         "snkpt_read_aux": [vp, u32, vp, sz], "snkpt_aux_size": [vp, u32, vp],
         "snkpt_write_reservoirs": [vp, u32, vp, u32, u32], "snkpt_device_ptr": [vp, u32, vp, vp],
         "snkpt_get_stats": [vp, vp], "snkpt_synchronize": [vp], "snkpt_trace_rays": [vp, vp, u64, u32, vp, vp],
@@ -57,6 +59,8 @@ def load_library() -> C.CDLL:
         fn.argtypes = args
         fn.restype = C.c_int
     L.snkpt_default_settings.restype = None
+    L.snkpt_particles_default_params.argtypes = [vp]
+    L.snkpt_particles_default_params.restype = None
     L.snkpt_frame_jitter.argtypes = [u32, u32, u32, vp, vp]
     L.snkpt_frame_jitter.restype = None
     L.snkpt_destroy.argtypes = [vp]
@@ -72,7 +76,8 @@ EXPORTS = ["snkpt_create", "snkpt_destroy", "snkpt_last_error", "snkpt_default_s
            "snkpt_set_materials", "snkpt_set_lights", "snkpt_set_transforms", "snkpt_set_instances", "snkpt_build_tlas",
            "snkpt_set_frame", "snkpt_trace_primary", "snkpt_render", "snkpt_accumulate", "snkpt_read_output", "snkpt_read_aux",
            "snkpt_aux_size", "snkpt_write_reservoirs", "snkpt_device_ptr", "snkpt_get_stats", "snkpt_synchronize",
-           "snkpt_trace_rays", "snkpt_count_work", "snkpt_set_profiling", "snkpt_get_launch_timings", "snkpt_taa_resolve", "snkpt_set_texture", "snkpt_read_output_async", "snkpt_read_output_wait", "snkpt_frame_jitter"]
+           "snkpt_trace_rays", "snkpt_count_work", "snkpt_set_profiling", "snkpt_get_launch_timings", "snkpt_taa_resolve", "snkpt_set_texture", "snkpt_read_output_async", "snkpt_read_output_wait", "snkpt_frame_jitter", "snkpt_particles_default_params",
+           "snkpt_particles_create", "snkpt_particles_write", "snkpt_particles_read", "snkpt_particles_update", "snkpt_particles_rays"]
 
 CONFIG_DTYPE = np.dtype([("width", "<u4"), ("height", "<u4"), ("device", "<i4"), ("max_instances", "<u4"),
                          ("max_transforms", "<u4"), ("max_materials", "<u4"), ("row_begin", "<u4"), ("row_end", "<u4"),
@@ -111,6 +116,21 @@ AUX = dict(prim=(0, np.uint32, 1), inst=(1, np.uint32, 1), depth=(2, np.float32,
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+PARTICLE_DTYPE = np.dtype([("position_radius", "<f4", (4,)), ("velocity", "<f4", (4,)), ("colour", "<f4", (4,))])
+PHYSICS_DTYPE = np.dtype([(k, "<f4") for k in ("particle_restitution", "timestep", "friction_coefficient", "repulsion_factor", "penetration_slop",
+                                               "restitution_slop", "sleep_threshold")])
+assert PARTICLE_DTYPE.itemsize == 48 and PHYSICS_DTYPE.itemsize == 28
+
+
+def physics_params(**kw) -> np.ndarray:
+    """PhysicsParamsUBO defaults (Core/headers/scene/ParticleSystem.h:16-24)"""
+    p = np.zeros((), PHYSICS_DTYPE)
+    load_library().snkpt_particles_default_params(_p(p))
+    for k, v in kw.items():
+        p[k] = v
+    return p
 
 
 def frame_jitter(frame_idx: int, internal_width: int, output_width: int | None = None):
@@ -230,6 +250,30 @@ class PathTracer:
 
     def accumulate(self, reset=False, stream=None):
         self._ck(self.L.snkpt_accumulate(self.h, int(reset), stream), "snkpt_accumulate")
+
+    # ---- particle collision pass (ParticleSystem)
+    def particles_create(self, count: int, init=True):
+        self._ck(self.L.snkpt_particles_create(self.h, count, int(init)), "snkpt_particles_create")
+        self.num_particles = count
+
+    def particles_write(self, particles: np.ndarray, first=0):
+        a = np.ascontiguousarray(particles)
+        assert a.dtype == PARTICLE_DTYPE
+        self._ck(self.L.snkpt_particles_write(self.h, _p(a), first, a.size), "snkpt_particles_write")
+
+    def particles_read(self) -> np.ndarray:
+        out = np.zeros(self.num_particles, PARTICLE_DTYPE)
+        self._ck(self.L.snkpt_particles_read(self.h, _p(out), 0, out.size), "snkpt_particles_read")
+        return out
+
+    def particles_update(self, params: np.ndarray | None = None, substeps=3, stream=None):
+        p = None if params is None else np.ascontiguousarray(params)
+        self._ck(self.L.snkpt_particles_update(self.h, _p(p), substeps, stream), "snkpt_particles_update")
+
+    def particles_rays(self) -> int:
+        v = C.c_uint64(0)
+        self._ck(self.L.snkpt_particles_rays(self.h, C.byref(v)), "snkpt_particles_rays")
+        return v.value
 
     def taa_resolve(self, stream=None):
         """TAA_ResolvePass::RecordCommandBuffer on the output image of the last render (include/snkpt.h)."""

@@ -329,6 +329,9 @@ void snkpt_destroy(SnkPt* ctx) {
   for (auto& r : ctx->blas_refit) refit_free(r);
   scratch_free(ctx->scratch_blas);
   scratch_free(ctx->scratch_tlas);
+  scratch_free(ctx->scratch_ptcl);
+  for (auto& b : ctx->ptcl) b.release();
+  ctx->ptcl_start.release(); ctx->ptcl_rays.release();
   for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
   if (ctx->ev_stage) cudaEventDestroy(ctx->ev_stage);
   if (ctx->ring) cudaFreeHost(ctx->ring);
@@ -1114,6 +1117,85 @@ int snkpt_synchronize(SnkPt* ctx) {
   CK(cudaStreamSynchronize(work_stream(ctx)));
   if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));
   CK(cudaGetLastError());
+  return SNKPT_OK;
+}
+
+// ---- particle collision pass -------------------------------------------------------------------------------------
+void snkpt_particles_default_params(SnkPhysicsParams* p) {
+  if (!p) return;
+  p->particle_restitution = 0.2f; p->timestep = 1.f / 120.f; p->friction_coefficient = 0.5f; p->repulsion_factor = 0.08f;
+  p->penetration_slop = 0.005f; p->restitution_slop = 0.05f; p->sleep_threshold = 0.05f;
+}
+
+int snkpt_particles_create(SnkPt* ctx, uint32_t count, int init) {
+  if (!ctx) return SNKPT_E_INVALID;
+  REQUIRE(count > 0 && count <= (1u << 24), SNKPT_E_INVALID, "snkpt_particles_create: 1 .. 2^24 particles");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = work_stream(ctx);
+  CK(cudaStreamSynchronize(st));
+  for (int k = 0; k < 2; ++k) CK(ctx->ptcl[k].reserve(sizeof(SnkParticle) * (size_t)count, false, st));
+  CK(ctx->ptcl_start.reserve(4ull * count, false, st));
+  CK(ctx->ptcl_rays.reserve(8, false, st));
+  CK(cudaMemsetAsync(ctx->ptcl_rays.p, 0, 8, st));
+  CK(scratch_reserve(ctx->scratch_ptcl, count));
+  ctx->num_particles = count;
+  ctx->ptcl_cur = 0;
+  CK(cudaMemsetAsync(ctx->ptcl[0].p, 0, sizeof(SnkParticle) * (size_t)count, st));
+  if (init) ctx->stats.kernel_launches += launch_particles_init(ctx->ptcl[0].as<SnkParticle>(), count, st);
+  CK(cudaStreamSynchronize(st));
+  CK(cudaGetLastError());
+  return SNKPT_OK;
+}
+
+int snkpt_particles_write(SnkPt* ctx, const SnkParticle* src, uint32_t first, uint32_t count) {
+  if (!ctx) return SNKPT_E_INVALID;
+  REQUIRE(src && (uint64_t)first + count <= ctx->num_particles, SNKPT_E_INVALID, "snkpt_particles_write: range");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = work_stream(ctx);
+  CK(cudaMemcpyAsync(ctx->ptcl[ctx->ptcl_cur].as<SnkParticle>() + first, src, sizeof(SnkParticle) * (size_t)count, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
+  return SNKPT_OK;
+}
+
+int snkpt_particles_read(SnkPt* ctx, SnkParticle* dst, uint32_t first, uint32_t count) {
+  if (!ctx) return SNKPT_E_INVALID;
+  REQUIRE(dst && (uint64_t)first + count <= ctx->num_particles, SNKPT_E_INVALID, "snkpt_particles_read: range");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = work_stream(ctx);
+  CK(cudaMemcpyAsync(dst, ctx->ptcl[ctx->ptcl_cur].as<SnkParticle>() + first, sizeof(SnkParticle) * (size_t)count, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return SNKPT_OK;
+}
+
+int snkpt_particles_update(SnkPt* ctx, const SnkPhysicsParams* params, uint32_t substeps, void* stream) {
+  if (!ctx) return SNKPT_E_INVALID;
+  REQUIRE(ctx->num_particles > 0, SNKPT_E_STATE, "snkpt_particles_update: call snkpt_particles_create first");
+  REQUIRE(ctx->tlas_built, SNKPT_E_STATE, "snkpt_particles_update: call snkpt_build_tlas first");
+  REQUIRE(substeps >= 1 && substeps <= 64, SNKPT_E_INVALID, "snkpt_particles_update: substeps");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  note_stream(ctx, st);
+  SnkPhysicsParams prm;
+  if (params) prm = *params; else snkpt_particles_default_params(&prm);
+  REQUIRE(prm.timestep > 0.f, SNKPT_E_INVALID, "snkpt_particles_update: timestep");
+  for (uint32_t s = 0; s < substeps; ++s) {
+    const uint32_t cur = ctx->ptcl_cur;
+    ctx->stats.kernel_launches += launch_particles_substep(ctx, ctx->ptcl[cur].as<SnkParticle>(), ctx->ptcl[cur ^ 1].as<SnkParticle>(), ctx->num_particles,
+                                                           ctx->ptcl_start.as<uint32_t>(), prm, ctx->ptcl_rays.as<unsigned long long>(), st);
+    ctx->ptcl_cur = cur ^ 1;  // the reference copies the result buffer back; here the two buffers swap roles
+  }
+  CK(cudaGetLastError());
+  return SNKPT_OK;
+}
+
+int snkpt_particles_rays(SnkPt* ctx, uint64_t* rays_traced) {
+  if (!ctx || !rays_traced) return SNKPT_E_INVALID;
+  REQUIRE(ctx->num_particles > 0, SNKPT_E_STATE, "snkpt_particles_rays: no particles");
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaStreamSynchronize(work_stream(ctx)));
+  unsigned long long v = 0;
+  CK(cudaMemcpy(&v, ctx->ptcl_rays.p, 8, cudaMemcpyDeviceToHost));
+  *rays_traced = v;
   return SNKPT_OK;
 }
 

@@ -842,6 +842,23 @@ void launch_instance_bounds(BuildScratch& s, const float* transforms_cm, const S
   if (n) k_instance_bounds<<<(n + 255) / 256, 256, 0, st>>>(transforms_cm, inst, blas_of_instance, blas, blas_nodes, valid_slots, n, s.prim_lo, s.prim_hi, s.counters);
 }
 
+// stable LSD radix sort of the (key, value) pairs in s.keys[cur] / s.vals[cur] over the low `bits` key bits; `cur` names the
+// buffer that holds the result. Also used by the particle pass (particles.cu) for its cell keys.
+int launch_sort_pairs(BuildScratch& s, uint32_t n, int bits, int& cur, cudaStream_t st) {
+  int launches = 0;
+  if (n <= 1) return 0;
+  const uint32_t nb = (n + SORT_TILE - 1) / SORT_TILE;
+  for (int shift = 0; shift < bits; shift += 8) {
+    k_sort_hist<<<nb, SORT_THREADS, 0, st>>>(s.keys[cur], n, shift, s.block_hist, nb);
+    k_scan_rows<<<256, 256, 0, st>>>(s.block_hist, nb, s.digit_total);
+    k_scan_digits<<<1, 256, 0, st>>>(s.digit_total);
+    k_sort_scatter<<<nb, SORT_THREADS, 0, st>>>(s.keys[cur], s.vals[cur], n, shift, s.block_hist, nb, s.digit_total, s.keys[cur ^ 1], s.vals[cur ^ 1]);
+    cur ^= 1;
+    launches += 4;
+  }
+  return launches;
+}
+
 int launch_build(BuildScratch& s, uint32_t n, const BuildOutput& out, const float* positions, const uint32_t* indices,
                  uint32_t index_offset, uint32_t vertex_offset, cudaStream_t st) {
   int launches = 0;

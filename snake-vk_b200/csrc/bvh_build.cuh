@@ -63,6 +63,8 @@ void launch_triangle_bounds(BuildScratch& s, const float* positions, const uint3
 void launch_instance_bounds(BuildScratch& s, const float* transforms_cm, const SnkInstanceData* inst,
                             const uint32_t* blas_of_instance, const SnkBlasInfo* blas, const SnkNode8* blas_nodes, const uint32_t* valid_slots,
                             uint32_t n, cudaStream_t st);
+// stable LSD radix sort of s.keys[cur] / s.vals[cur] over the low `bits` key bits (8 bits per pass); updates `cur`
+int launch_sort_pairs(BuildScratch& s, uint32_t n, int bits, int& cur, cudaStream_t st);
 // generic build over s.prim_lo/hi. Returns the number of kernels launched. After completion s.counters[0] holds
 // the number of wide nodes written, s.counters[1] the number of leaf records, s.counters[4] an overflow flag.
 int launch_build(BuildScratch& s, uint32_t n, const BuildOutput& out, const float* positions, const uint32_t* indices,

@@ -121,7 +121,10 @@ struct SnkPt {
   std::vector<SnkBlasInfo> blas;
   std::vector<snk::BlasSrc> blas_src;
   std::vector<snk::RefitState> blas_refit;  // side arrays of refitted BLASes (empty until the first refit)
-  snk::BuildScratch scratch_blas, scratch_tlas;
+  snk::BuildScratch scratch_blas, scratch_tlas, scratch_ptcl;
+  // particle pass (particles.cu): two particle buffers (ping-pong), cell start table, ray counter
+  snk::DevBuf ptcl[2], ptcl_start, ptcl_rays;
+  uint32_t num_particles = 0, ptcl_cur = 0;
 
   // scene mirrors (host + device)
   std::vector<SnkInstanceData> h_instances;

@@ -31,6 +31,11 @@ RefQueue ref_queue(SnkPt* ctx, int k, uint32_t cap);
 int reserve_ref_queues(SnkPt* ctx, uint32_t cap, cudaStream_t st);
 void reset_ref_queues(SnkPt* ctx, cudaStream_t st);
 
+// particles.cu — Particle.comp Init; one sub-step of ParticleSystem::UpdateParticles (keys, sort, start indices, update): P -> out
+int launch_particles_init(SnkParticle* P, uint32_t n, cudaStream_t st);
+int launch_particles_substep(SnkPt* ctx, const SnkParticle* P, SnkParticle* out, uint32_t n, uint32_t* cell_start, const SnkPhysicsParams& prm,
+                             unsigned long long* ray_counter, cudaStream_t st);
+
 // api.cu — a kernel about to overwrite the output image first waits for pending asynchronous read-backs of it
 void wait_readback(SnkPt* ctx, cudaStream_t st);
 

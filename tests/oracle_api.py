@@ -69,6 +69,12 @@ def lib() -> C.CDLL:
         L.snkor_hardware_threads.restype = C.c_int
         L.snkor_taa_resolve.argtypes = [C.c_uint32, C.c_uint32] + [C.c_void_p] * 5
         L.snkor_taa_resolve.restype = None
+        L.snkor_particles_init.argtypes = [C.c_void_p, C.c_uint32]
+        L.snkor_particles_init.restype = None
+        L.snkor_particles_update.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_int]
+        L.snkor_particles_update.restype = C.c_uint64
+        L.snkor_particles_grid.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
+        L.snkor_particles_grid.restype = None
         L.snkor_scene_set_texture.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32]
         L.snkor_scene_set_texture.restype = None
         L.snkor_sample_texture.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_void_p]
@@ -182,6 +188,32 @@ class OracleFrame:
         if getattr(self, "h", None):
             lib().snkor_frame_destroy(self.h)
             self.h = None
+
+
+PARTICLE_DTYPE = np.dtype([("position_radius", "<f4", (4,)), ("velocity", "<f4", (4,)), ("colour", "<f4", (4,))])
+
+
+def particles_init(n: int) -> np.ndarray:
+    """Particle.comp Init (oracle/snk_particles.h)"""
+    p = np.zeros(n, PARTICLE_DTYPE)
+    lib().snkor_particles_init(_p(p), n)
+    return p
+
+
+def particles_update(osc: "OracleScene", particles: np.ndarray, params: np.ndarray | None = None, substeps=3, threads=8):
+    """ParticleSystem::UpdateParticles on the CPU; returns (particles after the sub-steps, rays traced)"""
+    p = np.ascontiguousarray(particles).copy()
+    prm = None if params is None else np.ascontiguousarray(params)
+    rays = lib().snkor_particles_update(osc.h, _p(p), p.size, _p(prm), substeps, threads)
+    return p, int(rays)
+
+
+def particles_grid(particles: np.ndarray):
+    p = np.ascontiguousarray(particles)
+    keys = np.zeros((p.size, 2), np.uint32)
+    start = np.zeros(p.size, np.uint32)
+    lib().snkor_particles_grid(_p(p), p.size, _p(keys), _p(start))
+    return keys, start
 
 
 def taa_resolve(cur: np.ndarray, velocity: np.ndarray, history: np.ndarray, prev_velocity: np.ndarray) -> np.ndarray:
