@@ -78,6 +78,13 @@ def glm_vectors():
                         mul_out=mul_out, sph_in=sph_in, sph_out=sph_out)
 
 
+def shipped_scene():
+    """facts of the scene file the editor's project template ships (Editor/res/project-template/res/scenes/my_scene.json)"""
+    s = assets.load_scene(os.path.join(REF, "Editor", "res", "project-template", "res", "scenes", "my_scene.json"))
+    json.dump({"_source": "facts parsed from Editor/res/project-template/res/scenes/my_scene.json by snake-vk_b200.assets.load_scene "
+                          "(tools/make_golden.py:shipped_scene)", "scene": s}, open(os.path.join(GOLD, "shipped_scene.json"), "w"), indent=1)
+
+
 def shipped_meshes():
     out = {}
     for name in ("cube", "sphere"):
@@ -143,6 +150,7 @@ if __name__ == "__main__":
     O.build_oracle()
     glm_vectors()
     shipped_meshes()
+    shipped_scene()
     trace_cornell()
     frame_small()
     for f in sorted(os.listdir(GOLD)):
