@@ -18,7 +18,10 @@ namespace {
 constexpr float PRIMARY_TMIN = 0.1f;  // CameraComponent.h:11 z_near
 constexpr float PRIMARY_TMAX = 10000.0f;
 
-constexpr int PRIMARY_CTAS_PER_SM = 6;
+#ifndef SNK_PRIMARY_CTAS
+#define SNK_PRIMARY_CTAS 6
+#endif
+constexpr int PRIMARY_CTAS_PER_SM = SNK_PRIMARY_CTAS;
 
 __global__ void __launch_bounds__(128, PRIMARY_CTAS_PER_SM) k_primary(TraceScene S, SceneDev D, FrameConsts fc, PixelPlanes P) {
   // persistent CTAs walk 16x8 pixel tiles, 8x4 pixels per warp (coherent primary rays)
