@@ -628,6 +628,9 @@ __global__ void __launch_bounds__(128) k_collapse(CollapseArgs a) {
 // collapse ...) and was launch-latency bound: 0.38 ms for the 205 instances of C2. Here: Morton codes -> bitonic sort of
 // (key, index) pairs in shared memory -> Karras hierarchy -> bottom-up boxes -> level-synchronous collapse, with
 // __syncthreads() where the general path has kernel boundaries or grid syncs.
+#ifndef SNK_SMALL_PLOC
+#define SNK_SMALL_PLOC 0  // measured (profiles/r02p_variants_ploc.txt): nodes per ray 15.0 -> 14.2 but triangles per ray 4.0 -> 4.6; C2 frame 7.29 -> 7.43 ms, C4 40.9 -> 40.1 ms: not adopted
+#endif
 constexpr int SMALL_MAX = 4096, SMALL_THREADS = 1024;
 __global__ void __launch_bounds__(SMALL_THREADS) k_build_small(const float4* __restrict__ prim_lo, const float4* __restrict__ prim_hi, int n,
                                                                uint32_t* counters, unsigned long long* keys_g, uint32_t* vals_g, int* left,
@@ -673,6 +676,192 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_build_small(const float4* __r
   __syncthreads();
   // collapse, level by level (queue[0] = binary root and counters[C_NODES] = 1 were set by k_init)
   volatile uint32_t& s_end = *reinterpret_cast<volatile uint32_t*>(&sk[0]);  // the keys are dead by now (static smem is at its 48 KB limit)
+  uint32_t begin = 0, end = 1;
+  while (begin < end) {
+    for (uint32_t w = begin + t; w < end; w += NT) process_wide_node(a, w, (int)a.queue[w]);
+    __threadfence();
+    __syncthreads();
+    if (t == 0) {
+      const uint32_t total = *((volatile uint32_t*)&a.counters[C_NODES]);
+      s_end = total < a.node_capacity ? total : a.node_capacity;
+    }
+    __syncthreads();
+    begin = end;
+    end = s_end;
+    __syncthreads();
+  }
+}
+
+// ---- the same single-CTA build with a better binary tree: PLOC (parallel locally-ordered clustering, Meister & Bittner 2018)
+// over the Morton-sorted primitives instead of the Karras hierarchy. Every round each cluster finds the neighbour within
+// PLOC_RADIUS positions whose union with it has the smallest area, mutual pairs merge, the list is compacted in order. The tree
+// is close to a full-sweep SAH tree. Built to test whether the LBVH costs the instanced scenes node visits (both their TLAS and
+// their <= 4096-triangle BLASes are built here): it does not pay on these scenes (see SNK_SMALL_PLOC), so it is an option. Internal ids are handed out from n-2 downwards by rank,
+// so the last merge is node 0 (the root) and the build is deterministic. Afterwards the leaves are renumbered so that every
+// subtree covers a contiguous range of the (re-ordered) primitive list, which is what the collapse expects.
+#ifndef SNK_PLOC_RADIUS
+#define SNK_PLOC_RADIUS 12
+#endif
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t* scr, uint32_t& total) {
+  const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5, nw = (blockDim.x + 31u) >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= (uint32_t)o) inc += x;
+  }
+  if (lane == 31) scr[wid] = inc;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t w = lane < nw ? scr[lane] : 0u;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t x = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= (uint32_t)o) w += x;
+    }
+    scr[lane] = w;
+  }
+  __syncthreads();
+  const uint32_t base = wid ? scr[wid - 1] : 0u;
+  total = scr[nw - 1];
+  __syncthreads();
+  return base + inc - v;
+}
+
+__global__ void __launch_bounds__(SMALL_THREADS) k_build_small_ploc(const float4* __restrict__ prim_lo, const float4* __restrict__ prim_hi, int n,
+                                                                    uint32_t* counters, uint32_t* vals_g, uint32_t* vals_out, int* left, int* right,
+                                                                    int* parent, int* first, int* last, float4* bb_lo, float4* bb_hi, uint32_t* flags,
+                                                                    CollapseArgs a) {
+  __shared__ unsigned long long sk[SMALL_MAX];
+  __shared__ uint32_t sv[SMALL_MAX];
+  const int t = threadIdx.x, NT = blockDim.x;
+  int np2 = 1;
+  while (np2 < n) np2 <<= 1;
+  for (int i = t; i < np2; i += NT) {
+    sk[i] = i < n ? morton_key(prim_lo, prim_hi, (uint32_t)i, counters) : ~0ull;
+    sv[i] = (uint32_t)i;
+  }
+  __syncthreads();
+  for (int k = 2; k <= np2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = t; i < np2; i += NT) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long ka = sk[i], kb = sk[ixj];
+          const uint32_t va = sv[i], vb = sv[ixj];
+          const bool a_gt_b = ka > kb || (ka == kb && va > vb);
+          const bool up = (i & k) == 0;
+          if (a_gt_b == up) { sk[i] = kb; sk[ixj] = ka; sv[i] = vb; sv[ixj] = va; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // leaves: node n-1+i = sorted primitive i
+  for (int i = t; i < n; i += NT) {
+    const uint32_t prim = sv[i];
+    vals_g[i] = prim;
+    bb_lo[n - 1 + i] = prim_lo[prim];
+    bb_hi[n - 1 + i] = prim_hi[prim];
+  }
+  __syncthreads();
+  if (n == 1) {
+    if (t == 0) { parent[0] = -1; vals_out[0] = vals_g[0]; }
+  } else {
+    // shared memory from here on: two cluster lists in the key array, neighbour / flag / scan scratch in the value array
+    uint32_t* cl = reinterpret_cast<uint32_t*>(sk);
+    uint32_t* cl2 = cl + SMALL_MAX;
+    uint16_t* nb = reinterpret_cast<uint16_t*>(sv);
+    uint8_t* fl = reinterpret_cast<uint8_t*>(nb + SMALL_MAX);
+    uint32_t* scr = reinterpret_cast<uint32_t*>(fl + SMALL_MAX);
+    for (int i = t; i < n; i += NT) cl[i] = (uint32_t)(n - 1 + i);
+    __syncthreads();
+    int c = n, next = n - 2;
+    auto node_size = [&](int node) { return node >= n - 1 ? 1 : last[node]; };
+    while (c > 1) {
+      for (int i = t; i < c; i += NT) {
+        const float4 lo = bb_lo[cl[i]], hi = bb_hi[cl[i]];
+        const int j0 = i - SNK_PLOC_RADIUS < 0 ? 0 : i - SNK_PLOC_RADIUS, j1 = i + SNK_PLOC_RADIUS > c - 1 ? c - 1 : i + SNK_PLOC_RADIUS;
+        float best_area = FLT_MAX;
+        int best = -1;
+        for (int j = j0; j <= j1; ++j) {
+          if (j == i) continue;
+          const float4 l2 = bb_lo[cl[j]], h2 = bb_hi[cl[j]];
+          const float ar = half_area(make_float4(fminf(lo.x, l2.x), fminf(lo.y, l2.y), fminf(lo.z, l2.z), 0.f),
+                                     make_float4(fmaxf(hi.x, h2.x), fmaxf(hi.y, h2.y), fmaxf(hi.z, h2.z), 0.f));
+          if (ar < best_area) { best_area = ar; best = j; }
+        }
+        if (best < 0) best = i + 1 < c ? i + 1 : i - 1;  // non-finite boxes: keep the list shrinking
+        nb[i] = (uint16_t)best;
+      }
+      __syncthreads();
+      for (int i = t; i < c; i += NT) {
+        const int j = nb[i];
+        fl[i] = nb[j] == i ? (i < j ? 1 : 2) : 0;  // 1: merges with its partner here, 2: absorbed by the partner, 0: stays
+      }
+      __syncthreads();
+      const int per = (c + NT - 1) / NT, lo_i = t * per < c ? t * per : c, hi_i = lo_i + per < c ? lo_i + per : c;
+      uint32_t n_lead = 0, n_keep = 0;
+      for (int i = lo_i; i < hi_i; ++i) { n_lead += fl[i] == 1; n_keep += fl[i] != 2; }
+      uint32_t tot_lead, tot_keep;
+      uint32_t ex_lead = block_excl_scan(n_lead, scr, tot_lead);
+      uint32_t ex_keep = block_excl_scan(n_keep, scr, tot_keep);
+      for (int i = lo_i; i < hi_i; ++i) {
+        if (fl[i] == 1) {
+          const int id = next - (int)(ex_lead++);
+          const int ca = (int)cl[i], cb = (int)cl[nb[i]];
+          left[id] = ca; right[id] = cb;
+          parent[ca] = id; parent[cb] = id;
+          const float4 l1 = bb_lo[ca], h1 = bb_hi[ca], l2 = bb_lo[cb], h2 = bb_hi[cb];
+          bb_lo[id] = make_float4(fminf(l1.x, l2.x), fminf(l1.y, l2.y), fminf(l1.z, l2.z), 0.f);
+          bb_hi[id] = make_float4(fmaxf(h1.x, h2.x), fmaxf(h1.y, h2.y), fmaxf(h1.z, h2.z), 0.f);
+          last[id] = node_size(ca) + node_size(cb);  // subtree size for now; becomes the range end below
+          cl2[ex_keep++] = (uint32_t)id;
+        } else if (fl[i] == 0) {
+          cl2[ex_keep++] = cl[i];
+        }
+      }
+      next -= (int)tot_lead;
+      c = (int)tot_keep;
+      uint32_t* tmp = cl; cl = cl2; cl2 = tmp;
+      __threadfence_block();
+      __syncthreads();
+    }
+    if (t == 0) parent[0] = -1;
+    __syncthreads();
+    // position of every leaf in a depth-first order: sum of the sizes of the left siblings on the way to the root
+    for (int i = t; i < n; i += NT) {
+      int node = n - 1 + i, pos = 0, p;
+      while ((p = parent[node]) >= 0) {
+        if (right[p] == node) pos += node_size(left[p]);
+        node = p;
+      }
+      flags[i] = (uint32_t)pos;
+    }
+    __syncthreads();
+    for (int i = t; i < n; i += NT) {
+      const uint32_t pos = flags[i], prim = vals_g[i];
+      vals_out[pos] = prim;
+      bb_lo[n - 1 + pos] = prim_lo[prim];
+      bb_hi[n - 1 + pos] = prim_hi[prim];
+    }
+    for (int k = t; k < n - 1; k += NT) {
+      const int l = left[k], r = right[k];
+      if (l >= n - 1) left[k] = n - 1 + (int)flags[l - (n - 1)];
+      if (r >= n - 1) right[k] = n - 1 + (int)flags[r - (n - 1)];
+    }
+    __syncthreads();
+    for (int k = t; k < n - 1; k += NT) {
+      int node = k;
+      while (node < n - 1) node = left[node];
+      const int f = node - (n - 1), sz = last[k];
+      first[k] = f;
+      last[k] = f + sz - 1;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  volatile uint32_t& s_end = *reinterpret_cast<volatile uint32_t*>(&sv[SMALL_MAX - 1]);
   uint32_t begin = 0, end = 1;
   while (begin < end) {
     for (uint32_t w = begin + t; w < end; w += NT) process_wide_node(a, w, (int)a.queue[w]);
@@ -875,8 +1064,14 @@ int launch_build(BuildScratch& s, uint32_t n, const BuildOutput& out, const floa
     a.leaf_max = out.tris ? LEAF_MAX_BLAS : LEAF_MAX_TLAS;
     uint32_t threads = 128;
     while (threads < n && threads < (uint32_t)SMALL_THREADS) threads <<= 1;
+#if SNK_SMALL_PLOC
+    a.sorted_prims = s.vals[1];
+    k_build_small_ploc<<<1, threads, 0, st>>>(s.prim_lo, s.prim_hi, (int)n, s.counters, s.vals[0], s.vals[1], s.left, s.right, s.parent, s.first, s.last,
+                                               s.bb_lo, s.bb_hi, s.flags, a);
+#else
     k_build_small<<<1, threads, 0, st>>>(s.prim_lo, s.prim_hi, (int)n, s.counters, s.keys[0], s.vals[0], s.left, s.right, s.parent, s.first,
                                               s.last, s.bb_lo, s.bb_hi, s.flags, a);
+#endif
     return 1;
   }
 #endif
