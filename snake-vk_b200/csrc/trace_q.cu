@@ -21,6 +21,9 @@ constexpr int TQ_THREADS = 128;
 #ifndef SNK_TQ_VOTE
 #define SNK_TQ_VOTE 0  // 0: node + triangle + pop every iteration (trav_step); 1: one voted phase per iteration (trav_vote_step) — measured 20 % slower (r01r)
 #endif
+#ifndef SNK_TQ_CACHE_WORLD
+#define SNK_TQ_CACHE_WORLD 1  // world-space 1/d and octant kept in shared memory for leaving an instance: +1-2 % (profiles/r02r_variants_tri_reps_world_cache.txt)
+#endif
 #ifndef SNK_TQ_REFILL_MIN
 #define SNK_TQ_REFILL_MIN 8  // idle lanes that trigger a refill
 #endif
@@ -29,9 +32,15 @@ __global__ void __launch_bounds__(TQ_THREADS, SNK_TQ_CTAS)
 k_trace_q(TraceScene S, TraceSegs segs, const uint32_t* __restrict__ refs, const uint32_t* __restrict__ count_ptr,
           uint32_t* __restrict__ ticket, float* __restrict__ prof_t) {
   __shared__ uint2 sm_stack[SHORT_STACK * TQ_THREADS];
+#if SNK_TQ_CACHE_WORLD
+  __shared__ float4 sm_world[TQ_THREADS];
+#endif
   const uint32_t lane = threadIdx.x & 31u;
-  const StackRef stk{sm_stack + threadIdx.x,
-                     S.spill + ((size_t)blockIdx.x * (TQ_THREADS / 32) + (threadIdx.x >> 5)) * (SPILL_STACK * 32) + lane};
+  StackRef stk{sm_stack + threadIdx.x,
+               S.spill + ((size_t)blockIdx.x * (TQ_THREADS / 32) + (threadIdx.x >> 5)) * (SPILL_STACK * 32) + lane};
+#if SNK_TQ_CACHE_WORLD
+  stk.world = sm_world + threadIdx.x;
+#endif
   const uint32_t n = __ldcg(count_ptr);
   if (n == 0u || S.tlas_node_count == 0u) {
     // nothing to hit: every queued ray misses
@@ -65,6 +74,9 @@ k_trace_q(TraceScene S, TraceSegs segs, const uint32_t* __restrict__ refs, const
           const float4* rp = sg.rays + 2ull * (ref & REF_SLOT_MASK);
           const float4 a = __ldcg(rp), b = __ldcg(rp + 1);
           trav_begin(t, a, b);
+#if SNK_TQ_CACHE_WORLD
+          sm_world[threadIdx.x] = make_float4(t.r.idx, t.r.idy, t.r.idz, __uint_as_float(t.r.octinv));
+#endif
           any = sg.any != 0u;
           qpos = q;
           active = true;  // the producers only queue live rays (tmax > tmin)

@@ -261,6 +261,7 @@ constexpr int SPILL_STACK = 40;
 struct StackRef {
   uint2* sm;  // this thread's column of the shared short stack (stride = CTA threads)
   uint2* gl;  // this lane's column of the warp's spill area (stride = 32)
+  float4* world = nullptr;  // optional: this thread's cached world-space box constants (1/d.xyz, octant) for leaving an instance
 };
 
 struct Trav {
@@ -329,6 +330,9 @@ __device__ __forceinline__ void trav_begin(Trav& t, float4 a, float4 b) {
   t.best.t = -1.0f; t.best.u = 0.f; t.best.v = 0.f; t.best.prim = 0xFFFFFFFFu; t.best.inst = 0xFFFFFFFFu;
 }
 
+#ifndef SNK_TRI_REPS
+#define SNK_TRI_REPS 1  // triangle records a lane may test per iteration (2: -5 %, 3: -8 %, profiles/r02r_variants_tri_reps_world_cache.txt)
+#endif
 #ifndef SNK_TRI_MIN
 #define SNK_TRI_MIN 0  // triangle phase runs when at least this many lanes have a record pending (or nobody opened a node)
 #endif
@@ -400,34 +404,47 @@ __device__ __forceinline__ bool trav_step_impl(const TraceScene& S, Trav& t, con
   } else {
     __syncwarp(warp);
   }
-  if (tri_go) {
-    const uint32_t bit = __ffs(t.T.y) - 1;
-    t.T.y &= ~(1u << bit);
-    if (!t.tri_ready) { setup_tri_space(t.r); t.tri_ready = true; }
-    const float4* tp = S.tris + 3ull * (t.T.x + bit);
-    const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
-    float th, u, v;
-    if (tri_test(t.r, p0, p1, p2, th, u, v) && th > t.tmin) {
-      // tcur == tmax until the first hit, afterwards the closest distance so far: a hit must be strictly inside
-      // (tmin, tmax); at the current closest distance the lower (instance, primitive) wins
-      const uint32_t prim = __float_as_uint(p0.w);
-      bool take;
-      if (ANY) take = th < t.tcur;
-      else take = th < t.tcur || (th == t.tcur && t.best.t >= 0.0f &&
-                                  (t.cur_inst < t.best.inst || (t.cur_inst == t.best.inst && prim < t.best.prim)));
-      if (take) {
-        t.best.t = th; t.best.u = u; t.best.v = v; t.best.prim = prim; t.best.inst = t.cur_inst;
-        t.tcur = th;
-        done = ANY;
+#pragma unroll 1
+  for (int rep = 0; rep < SNK_TRI_REPS; ++rep) {
+    // SNK_TRI_REPS > 1: lanes with more records pending test another one in the same iteration
+    const bool go = rep == 0 ? tri_go : (active && !done && t.in_blas && t.T.y != 0u);
+    if (rep && __ballot_sync(warp, go) == 0u) break;
+    if (go) {
+      const uint32_t bit = __ffs(t.T.y) - 1;
+      t.T.y &= ~(1u << bit);
+      if (!t.tri_ready) { setup_tri_space(t.r); t.tri_ready = true; }
+      const float4* tp = S.tris + 3ull * (t.T.x + bit);
+      const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
+      float th, u, v;
+      if (tri_test(t.r, p0, p1, p2, th, u, v) && th > t.tmin) {
+        // tcur == tmax until the first hit, afterwards the closest distance so far: a hit must be strictly inside
+        // (tmin, tmax); at the current closest distance the lower (instance, primitive) wins
+        const uint32_t prim = __float_as_uint(p0.w);
+        bool take;
+        if (ANY) take = th < t.tcur;
+        else take = th < t.tcur || (th == t.tcur && t.best.t >= 0.0f &&
+                                    (t.cur_inst < t.best.inst || (t.cur_inst == t.best.inst && prim < t.best.prim)));
+        if (take) {
+          t.best.t = th; t.best.u = u; t.best.v = v; t.best.prim = prim; t.best.inst = t.cur_inst;
+          t.tcur = th;
+          done = ANY;
+        }
       }
     }
+    __syncwarp(warp);
   }
-  __syncwarp(warp);
   // ---- 4
   if (active && !done && t.T.y == 0u && (t.G.y & 0xFF000000u) == 0u) {
     if (t.in_blas && t.sp == t.blas_sp) {
-      // leave the instance: back to world space (no triangles are tested in the TLAS, so only the box part)
-      setup_box_space(t.r, t.ox, t.oy, t.oz, t.dx, t.dy, t.dz);
+      // leave the instance: back to world space (no triangles are tested in the TLAS, so only the box part); kernels that
+      // cache the world-space constants in shared memory reload them instead of recomputing three reciprocals
+      if (stk.world) {
+        const float4 w = *stk.world;
+        t.r.ox = t.ox; t.r.oy = t.oy; t.r.oz = t.oz; t.r.dx = t.dx; t.r.dy = t.dy; t.r.dz = t.dz;
+        t.r.idx = w.x; t.r.idy = w.y; t.r.idz = w.z; t.r.octinv = __float_as_uint(w.w);
+      } else {
+        setup_box_space(t.r, t.ox, t.oy, t.oz, t.dx, t.dy, t.dz);
+      }
       t.in_blas = false; t.tri_ready = false;
     }
     if (t.sp == 0) done = true;
