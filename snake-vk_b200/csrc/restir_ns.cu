@@ -288,7 +288,10 @@ __global__ void __launch_bounds__(128, 8) k_rs_temporal(SceneDev D, FrameConsts 
 // ---- stage 3 ---------------------------------------------------------------------------------------------------------
 constexpr int RS_MAXN = 9;  // this pixel + up to 8 neighbours
 
-__global__ void __launch_bounds__(128, 5) k_rs_spatial(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, RsBuffers B, uint32_t npix,
+#ifndef SNK_RS_SPATIAL_CTAS
+#define SNK_RS_SPATIAL_CTAS 5
+#endif
+__global__ void __launch_bounds__(128, SNK_RS_SPATIAL_CTAS) k_rs_spatial(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, RsBuffers B, uint32_t npix,
                                                     unsigned long long* counters, uint32_t* q_refs, uint32_t* q_count) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long n_shadow = 0;
