@@ -134,10 +134,11 @@ __device__ void ns_vertex_work(const SceneDev& D, const NsBuffers& B, size_t i, 
 __global__ void __launch_bounds__(128, 8) k_ns_gen(SceneDev D, FrameConsts fc, PixelPlanes P, NsBuffers B, uint32_t npix, uint32_t max_bounces,
                                                 uint32_t nee_from, unsigned long long* counters, uint32_t* q_refs, uint32_t* q_count,
                                                 uint32_t* paths_out, uint32_t* paths_out_count) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   bool has_shadow = false, has_closest = false;
-  if (i < npix) {
-    const uint32_t x = i % fc.W, y = fc.row0 + i / fc.W;
+  uint32_t x, y, i = 0;
+  if (stage_pixel(fc, t, x, y)) {
+    i = (y - fc.row0) * fc.W + x;  // slot of the per-pixel path planes (band-relative pixel index)
     const size_t px = (size_t)y * fc.W + x;
     B.L[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     B.vis[i] = 1.0f;
@@ -302,7 +303,7 @@ int launch_northstar_frame(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st) 
   RefQueue Q = ref_queue(ctx, q, qcap);
   if (nee_from) launches += restir_ns_initial(ctx, s, Q, st);
   int rec = prof_begin(ctx, "ns_gen", npix, false, false, st);
-  k_ns_gen<<<g128, 128, 0, st>>>(D, fc, ctx->planes, B, npix, max_bounces, nee_from, counters, Q.refs, Q.count, paths[0], path_count);
+  k_ns_gen<<<(stage_threads(fc.W, fc.row1 - fc.row0) + 127) / 128, 128, 0, st>>>(D, fc, ctx->planes, B, npix, max_bounces, nee_from, counters, Q.refs, Q.count, paths[0], path_count);
   prof_end(ctx, rec, st);
   ++launches;
   char name[32];

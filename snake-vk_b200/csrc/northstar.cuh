@@ -166,6 +166,32 @@ __device__ __forceinline__ void put_dead(float4* q, size_t i) {
   q[2 * i + 1] = make_float4(0.f, 1.f, 0.f, -1.0f);
 }
 
+// ---- thread -> pixel mapping of the per-pixel north-star stages: a warp covers an 8x4 pixel tile of the band instead of 32
+// pixels of one row. The rays a warp appends to the queue (and the paths it lists) then start from a compact patch, and the
+// neighbour gathers of the spatial-reuse stage get 2-D locality. Storage stays indexed by pixel, so results do not change.
+#ifndef SNK_TILE_PIXELS
+#define SNK_TILE_PIXELS 0  // measured (profiles/r02w_variants_tile_pixels.txt): C2 7.19 -> 7.11 ms, C3 14.05 -> 13.96 ms, but C4 39.7 -> 40.2 ms (trace.q2 +20 % at 4K): a wash, rows kept
+#endif
+__device__ __forceinline__ bool stage_pixel(const FrameConsts& fc, uint32_t t, uint32_t& x, uint32_t& y) {
+#if SNK_TILE_PIXELS
+  const uint32_t tiles_x = (fc.W + 7u) >> 3;
+  const uint32_t tile = t >> 5, lane = t & 31u;
+  x = (tile % tiles_x) * 8u + (lane & 7u);
+  y = fc.row0 + (tile / tiles_x) * 4u + (lane >> 3);
+  return x < fc.W && y < fc.row1;
+#else
+  x = t % fc.W; y = fc.row0 + t / fc.W;
+  return y < fc.row1;
+#endif
+}
+inline uint32_t stage_threads(uint32_t W, uint32_t rows) {
+#if SNK_TILE_PIXELS
+  return ((W + 7u) / 8u) * ((rows + 3u) / 4u) * 32u;
+#else
+  return W * rows;
+#endif
+}
+
 // ---- compact ray-reference queue (trace_q.cu): segments of the north-star frame
 constexpr uint32_t SEG_RS_PL = 0u, SEG_RS_EM = 1u, SEG_RS_DIR = 2u, SEG_NS_CLOSEST = 3u, SEG_NS_SHADOW = 4u;
 __device__ __forceinline__ uint32_t make_ref(uint32_t seg, size_t slot) { return (seg << REF_SLOT_BITS) | (uint32_t)slot; }

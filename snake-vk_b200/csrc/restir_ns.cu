@@ -111,9 +111,11 @@ __device__ __forceinline__ bool rs_em_valid(const SceneDev& D, uint32_t obj, uin
 }
 __device__ __forceinline__ void rs_empty(Reservoir& r) { init_reservoir(r); }
 
-__device__ __forceinline__ void pixel_of(const FrameConsts& fc, uint32_t i, uint32_t& x, uint32_t& y, size_t& px) {
-  x = i % fc.W; y = fc.row0 + i / fc.W;
-  px = (size_t)y * fc.W + x;
+// thread -> pixel (northstar.cuh:stage_pixel); false outside the band
+__device__ __forceinline__ bool pixel_of(const FrameConsts& fc, uint32_t t, uint32_t& x, uint32_t& y, size_t& px) {
+  const bool ok = stage_pixel(fc, t, x, y);
+  px = ok ? (size_t)y * fc.W + x : 0;
+  return ok;
 }
 
 // ---- emissive-triangle table (northstar.cuh): one block per emissive-list entry ------------------------------------------
@@ -159,9 +161,8 @@ __global__ void __launch_bounds__(128, 6) k_rs_initial(SceneDev D, FrameConsts f
   unsigned long long n_shadow = 0;
   bool ray_pl = false, ray_em = false;
   size_t px = 0;
-  if (i < npix) {
-    uint32_t x, y;
-    pixel_of(fc, i, x, y, px);
+  uint32_t x, y;
+  if (pixel_of(fc, i, x, y, px)) {
     const size_t np = rp.npix_frame;
     Reservoir r; rs_empty(r);
     float p_sel_pl = 0.0f, p_sel_em = 0.0f;
@@ -230,9 +231,8 @@ __global__ void __launch_bounds__(128, 6) k_rs_initial(SceneDev D, FrameConsts f
 // ---- stage 2 ---------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, 8) k_rs_temporal(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, RsBuffers B, uint32_t npix) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= npix) return;
   uint32_t x, y; size_t px;
-  pixel_of(fc, i, x, y, px);
+  if (!pixel_of(fc, i, x, y, px)) return;
   if (!px_shaded(P, px)) return;  // stage 1 wrote the empty reservoir
   const size_t np = rp.npix_frame;
   const ResPlanes half0{P.res[0][0], P.res[0][1], P.res[0][2]}, half1{P.res[1][0], P.res[1][1], P.res[1][2]};
@@ -297,9 +297,8 @@ __global__ void __launch_bounds__(128, SNK_RS_SPATIAL_CTAS) k_rs_spatial(SceneDe
   unsigned long long n_shadow = 0;
   bool ray0 = false, ray1 = false, ray2 = false;
   size_t px = 0;
-  if (i < npix) {
-    uint32_t x, y;
-    pixel_of(fc, i, x, y, px);
+  uint32_t x, y;
+  if (pixel_of(fc, i, x, y, px)) {
     const size_t np = rp.npix_frame;
     const ResPlanes half0{P.res[0][0], P.res[0][1], P.res[0][2]}, half1{P.res[1][0], P.res[1][1], P.res[1][2]};
     Reservoir out; rs_empty(out);
@@ -478,7 +477,7 @@ int restir_ns_initial(SnkPt* ctx, const SnkRtSettings& s, const RefQueue& q, cud
   const RsLaunch L = rs_launch(ctx, s);
   unsigned long long* counters = reinterpret_cast<unsigned long long*>(ctx->dev_counters.as<uint32_t>() + 2);
   const int rec = prof_begin(ctx, "rs_initial", L.npix1, false, false, st);
-  k_rs_initial<<<(L.npix1 + 127) / 128, 128, 0, st>>>(ctx->scene_dev(), L.f1, ctx->planes, L.rp, L.B, L.npix1, counters, q.refs, q.count);
+  k_rs_initial<<<(stage_threads(L.f1.W, L.f1.row1 - L.f1.row0) + 127) / 128, 128, 0, st>>>(ctx->scene_dev(), L.f1, ctx->planes, L.rp, L.B, L.npix1, counters, q.refs, q.count);
   prof_end(ctx, rec, st);
   return 1;
 }
@@ -490,11 +489,11 @@ int restir_ns_reuse(SnkPt* ctx, const SnkRtSettings& s, const RefQueue& q, cudaS
   unsigned long long* counters = reinterpret_cast<unsigned long long*>(ctx->dev_counters.as<uint32_t>() + 2);
   const SceneDev D = ctx->scene_dev();
   int rec = prof_begin(ctx, "rs_temporal", L.npix1, false, false, st);
-  k_rs_temporal<<<(L.npix1 + 127) / 128, 128, 0, st>>>(D, L.f1, ctx->planes, L.rp, L.B, L.npix1);
+  k_rs_temporal<<<(stage_threads(L.f1.W, L.f1.row1 - L.f1.row0) + 127) / 128, 128, 0, st>>>(D, L.f1, ctx->planes, L.rp, L.B, L.npix1);
   prof_end(ctx, rec, st);
   cudaEventRecord(ctx->ev[3], st);
   rec = prof_begin(ctx, "rs_spatial", L.npix, false, false, st);
-  k_rs_spatial<<<(L.npix + 127) / 128, 128, 0, st>>>(D, ctx->fc, ctx->planes, L.rp, L.B, L.npix, counters, q.refs, q.count);
+  k_rs_spatial<<<(stage_threads(ctx->fc.W, ctx->fc.row1 - ctx->fc.row0) + 127) / 128, 128, 0, st>>>(D, ctx->fc, ctx->planes, L.rp, L.B, L.npix, counters, q.refs, q.count);
   prof_end(ctx, rec, st);
   return 2;
 }
