@@ -136,7 +136,9 @@ inline void fill_gbuffer(const Scene& sc, const CommonUBO& cur, const CommonUBO&
       const vec3 p = (sc.pos(ia) * b0 + sc.pos(ib) * b1) + sc.pos(ic) * b2;
       const vec3 n0 = (sc.nrm(ia) * b0 + sc.nrm(ib) * b1) + sc.nrm(ic) * b2;
       const vec3 world = mul_point(sc.transforms[in.transform_idx], p);
-      const vec3 n = normalize(mul(sc.normal_matrix[in.transform_idx], n0));
+      const Material& mat_n = sc.materials[in.material_idx];
+      vec3 n = normalize(mul(sc.normal_matrix[in.transform_idx], n0));
+      { vec3 nm; if (sc.mapped_normal(mat_n, sc.transforms[in.transform_idx], ia, ib, ic, b0, b1, b2, nm)) n = nm; }  // GBuffer.frag:48-52
       const vec4 clip = mul_vec4(cur.proj_view, vec4{world.x, world.y, world.z, 1.0f});
       const vec3 pworld = mul_point(sc.prev_transforms[in.transform_idx], p);
       const vec4 pclip = mul_vec4(prev.proj_view, vec4{pworld.x, pworld.y, pworld.z, 1.0f});

@@ -55,6 +55,9 @@ ORACLE_API void snkor_scene_set_texture(void* s, uint32_t idx, uint32_t w, uint3
   t.w = w; t.h = h; t.srgb = srgb;
   t.rgba.assign(rgba, rgba + 4 * (size_t)w * h);
 }
+ORACLE_API void snkor_scene_set_tangents(void* s, const float* tangents, uint32_t num_vertices) {
+  ((Scene*)s)->tangents.assign(tangents, tangents + 3 * (size_t)num_vertices);
+}
 ORACLE_API void snkor_sample_texture(void* s, uint32_t idx, float u, float v, float* out3) {
   const vec3 c = sample_texture_rgb(((Scene*)s)->textures[idx], u, v);
   out3[0] = c.x; out3[1] = c.y; out3[2] = c.z;

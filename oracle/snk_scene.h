@@ -239,7 +239,7 @@ inline vec3 sample_texture_rgb(const Texture& t, float s, float tt) {
 }
 
 struct Scene {
-  std::vector<float> positions, normals, uvs;  // global SoA buffers (MeshBufferManager)
+  std::vector<float> positions, normals, uvs, tangents;  // global SoA buffers (MeshBufferManager)
   std::vector<Texture> textures;
   std::vector<uint32_t> indices;
   std::vector<InstanceData> instances;
@@ -259,6 +259,30 @@ struct Scene {
 
   vec3 pos(uint32_t i) const { return v3(positions[3 * i], positions[3 * i + 1], positions[3 * i + 2]); }
   vec3 nrm(uint32_t i) const { return v3(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2]); }
+  // GBuffer.vert:49-64 + GBuffer.frag:48-52: per-vertex TBN from the model matrix, interpolated by the hit's barycentrics, applied to
+  // the normal texture (UNORM, AssetLoader.cpp:570). Returns false when the material has no usable normal map.
+  bool mapped_normal(const Material& m, const mat4& M, uint32_t ia, uint32_t ib, uint32_t ic, float b0, float b1, float b2, vec3& out) const {
+    if (m.normal_tex_idx == 0xFFFFFFFFu || m.normal_tex_idx >= textures.size() || textures[m.normal_tex_idx].w == 0) return false;
+    if (tangents.size() < positions.size() || uvs.size() < 2 * positions.size() / 3) return false;
+    const uint32_t vi[3] = {ia, ib, ic};
+    const float w[3] = {b0, b1, b2};
+    vec3 T = v3(0.0f), B = v3(0.0f), N = v3(0.0f);
+    for (int k = 0; k < 3; ++k) {
+      const vec3 tv = v3(tangents[3 * vi[k]], tangents[3 * vi[k] + 1], tangents[3 * vi[k] + 2]), nv = nrm(vi[k]);
+      auto m3 = [&](vec3 v) { return v3((M.m[0] * v.x + M.m[4] * v.y) + M.m[8] * v.z, (M.m[1] * v.x + M.m[5] * v.y) + M.m[9] * v.z, (M.m[2] * v.x + M.m[6] * v.y) + M.m[10] * v.z); };
+      vec3 t = normalize(m3(tv));
+      const vec3 n = normalize(m3(nv));
+      t = normalize(t - n * dot(t, n));
+      const vec3 b = cross(n, t);
+      T = k == 0 ? t * w[k] : T + t * w[k]; B = k == 0 ? b * w[k] : B + b * w[k]; N = k == 0 ? n * w[k] : N + n * w[k];
+    }
+    const float tu = (uvs[2 * ia] * b0 + uvs[2 * ib] * b1) + uvs[2 * ic] * b2;
+    const float tv2 = (uvs[2 * ia + 1] * b0 + uvs[2 * ib + 1] * b1) + uvs[2 * ic + 1] * b2;
+    const vec3 c = sample_texture_rgb(textures[m.normal_tex_idx], tu, tv2);
+    const vec3 tn = normalize(c * 2.0f - v3(1.0f));
+    out = normalize((T * tn.x + B * tn.y) + N * tn.z);
+    return true;
+  }
   // material albedo times the albedo texture at the interpolated texcoord (rchit:100-116; weights b0,b1,b2 of the 3 vertices)
   vec3 albedo_at(const Material& m, uint32_t ia, uint32_t ib, uint32_t ic, float b0, float b1, float b2) const {
     vec3 albedo = v3(m.albedo[0], m.albedo[1], m.albedo[2]);

@@ -168,7 +168,7 @@ TraceScene SnkPt::trace_scene() const {
 
 SceneDev SnkPt::scene_dev() const {
   SceneDev D;
-  D.positions = positions.as<float>(); D.normals = normals.as<float>(); D.uvs = uvs.as<float>();
+  D.positions = positions.as<float>(); D.normals = normals.as<float>(); D.uvs = uvs.as<float>(); D.tangents = tangents.as<float>();
   D.indices = indices.as<uint32_t>();
   D.instances = instances.as<SnkInstanceData>();
   D.transforms = transforms.as<float>(); D.prev_transforms = prev_transforms.as<float>();

@@ -81,7 +81,7 @@ struct PixelPlanes {
 struct TexDev { const uchar4* texels; uint32_t w, h, srgb, pad; };
 
 struct SceneDev {
-  const float *positions, *normals, *uvs;
+  const float *positions, *normals, *uvs, *tangents;
   const uint32_t* indices;
   const SnkInstanceData* instances;
   const float* transforms;       // mat4 column-major

@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(128, PRIMARY_CTAS_PER_SM) k_primary(TraceScene
   const vec3 n0 = (na * b0 + nb * b1) + nc * b2;
   const float* M = D.transforms + 16ull * in.transform_idx;
   const vec3 world = mul_point(M, p);
-  const vec3 n = normalize(mul_mat3r(D.normal_mats + 9ull * in.transform_idx, n0));
+  const vec3 n = normalize(mul_mat3r(D.normal_mats + 9ull * in.transform_idx, n0));  // normal maps: k_gbuffer_normal_map below
   const float4 clip = mul_vec4(fc.proj_view, world.x, world.y, world.z, 1.0f);
   const vec3 pworld = mul_point(D.prev_transforms + 16ull * in.transform_idx, p);
   const float4 pclip = mul_vec4(fc.prev_proj_view, pworld.x, pworld.y, pworld.z, 1.0f);
@@ -109,7 +109,7 @@ int launch_primary(const TraceScene& S, const SceneDev& D, const FrameConsts& fc
   const uint32_t n_tiles = ((fc.W + 15) / 16) * ((fc.row1 - fc.row0 + 7) / 8);
   const uint32_t grid = n_tiles < 148u * PRIMARY_CTAS_PER_SM ? n_tiles : 148u * PRIMARY_CTAS_PER_SM;
   k_primary<<<grid, 128, 0, st>>>(S, D, fc, P);
-  return 1;
+  return 1 + (D.num_textures ? launch_gbuffer_normal_map(D, fc, P, st) : 0);
 }
 
 int launch_accumulate(const PixelPlanes& P, uint32_t npix, uint32_t count, cudaStream_t st) {

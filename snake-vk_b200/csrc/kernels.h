@@ -49,6 +49,8 @@ int traced_launch(SnkPt* ctx, const char* name, const float4* rays, uint64_t n, 
 
 // gbuffer.cu — primary visibility (replaces GBufferPass::RecordCommandBuffer, GBufferPass.cpp:70-196)
 int launch_primary(const TraceScene& S, const SceneDev& D, const FrameConsts& fc, const PixelPlanes& P, cudaStream_t st);
+// gbuffer_nm.cu — normal maps applied to the G-buffer normal plane (second pass, only when textures are set)
+int launch_gbuffer_normal_map(const SceneDev& D, const FrameConsts& fc, const PixelPlanes& P, cudaStream_t st);
 
 // restir.cu / bounce.cu — RT::RecordRenderCmdBuf (Raytracing.cpp:227-267) in reference mode
 int launch_restir_passes(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st);

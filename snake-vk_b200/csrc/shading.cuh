@@ -178,6 +178,31 @@ __device__ __forceinline__ vec3 albedo_at(const SceneDev& D, const SnkMaterial* 
   return albedo;
 }
 
+// GBuffer.vert:49-64 + GBuffer.frag:48-52: normal map through the interpolated per-vertex TBN (CPU statement: Scene::mapped_normal)
+static __device__ __noinline__ bool mapped_normal(const SceneDev& D, const SnkMaterial* m, const float* __restrict__ M, uint32_t ia, uint32_t ib, uint32_t ic,
+                                                  float b0, float b1, float b2, vec3& out) {
+  const uint32_t tex = __ldg(&m->normal_tex_idx);
+  if (tex == INVALID_IDX || tex >= D.num_textures || D.textures[tex].w == 0u || D.tangents == nullptr || D.uvs == nullptr) return false;
+  const uint32_t vi[3] = {ia, ib, ic};
+  const float w[3] = {b0, b1, b2};
+  vec3 T = v3(0.0f), B = v3(0.0f), N = v3(0.0f);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const vec3 tv = ld3(D.tangents, vi[k]), nv = ld3(D.normals, vi[k]);
+    vec3 t = normalize(v3((M[0] * tv.x + M[4] * tv.y) + M[8] * tv.z, (M[1] * tv.x + M[5] * tv.y) + M[9] * tv.z, (M[2] * tv.x + M[6] * tv.y) + M[10] * tv.z));
+    const vec3 n = normalize(v3((M[0] * nv.x + M[4] * nv.y) + M[8] * nv.z, (M[1] * nv.x + M[5] * nv.y) + M[9] * nv.z, (M[2] * nv.x + M[6] * nv.y) + M[10] * nv.z));
+    t = normalize(t - n * dot(t, n));
+    const vec3 b = cross(n, t);
+    T = k == 0 ? t * w[k] : T + t * w[k]; B = k == 0 ? b * w[k] : B + b * w[k]; N = k == 0 ? n * w[k] : N + n * w[k];
+  }
+  const float tu = (__ldg(D.uvs + 2ull * ia) * b0 + __ldg(D.uvs + 2ull * ib) * b1) + __ldg(D.uvs + 2ull * ic) * b2;
+  const float tv2 = (__ldg(D.uvs + 2ull * ia + 1) * b0 + __ldg(D.uvs + 2ull * ib + 1) * b1) + __ldg(D.uvs + 2ull * ic + 1) * b2;
+  const vec3 c = sample_texture_rgb(D, tex, tu, tv2);
+  const vec3 tn = normalize(c * 2.0f - v3(1.0f));
+  out = normalize((T * tn.x + B * tn.y) + N * tn.z);
+  return true;
+}
+
 // point on an emissive triangle: shared head of RayGen.rgen:241-251 and :258-268.
 // bary = (bx, by, 1-bx-by) weights of (ti.x, ti.y, ti.z) — NOT the hit-attribute convention.
 struct TriPoint { vec3 p, n, emissive; };

@@ -91,7 +91,7 @@ k_trace_q(TraceScene S, TraceSegs segs, const uint32_t* __restrict__ refs, const
 #if SNK_TQ_VOTE
     const bool finished = trav_vote_step<TQ_THREADS>(S, t, stk, active, any);
 #else
-    const bool finished = trav_step_impl<TQ_THREADS>(S, t, stk, active, 0xFFFFFFFFu, any);
+    const bool finished = trav_step_impl<TQ_THREADS, SNK_TQ_CACHE_WORLD != 0>(S, t, stk, active, 0xFFFFFFFFu, any);
 #endif
     if (finished) {
       const uint32_t ref = __ldg(refs + qpos);

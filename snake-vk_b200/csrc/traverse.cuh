@@ -345,7 +345,7 @@ __device__ __forceinline__ void trav_begin(Trav& t, float4 a, float4 b) {
 //   4. pop phase: lanes with nothing pending pop the stack; popping below the instance-entry height returns
 //      to world space; an empty stack finishes the ray
 // Returns true when this lane's ray is finished (stack empty, or first hit for ANY).
-template <int STRIDE>
+template <int STRIDE, bool CACHED_WORLD = false>
 __device__ __forceinline__ bool trav_step_impl(const TraceScene& S, Trav& t, const StackRef& stk, bool active, uint32_t warp, const bool ANY) {
   // ---- 1
   uint32_t node_idx = 0;
@@ -404,7 +404,7 @@ __device__ __forceinline__ bool trav_step_impl(const TraceScene& S, Trav& t, con
   } else {
     __syncwarp(warp);
   }
-#pragma unroll 1
+#pragma unroll
   for (int rep = 0; rep < SNK_TRI_REPS; ++rep) {
     // SNK_TRI_REPS > 1: lanes with more records pending test another one in the same iteration
     const bool go = rep == 0 ? tri_go : (active && !done && t.in_blas && t.T.y != 0u);
@@ -438,7 +438,7 @@ __device__ __forceinline__ bool trav_step_impl(const TraceScene& S, Trav& t, con
     if (t.in_blas && t.sp == t.blas_sp) {
       // leave the instance: back to world space (no triangles are tested in the TLAS, so only the box part); kernels that
       // cache the world-space constants in shared memory reload them instead of recomputing three reciprocals
-      if (stk.world) {
+      if (CACHED_WORLD) {
         const float4 w = *stk.world;
         t.r.ox = t.ox; t.r.oy = t.oy; t.r.oz = t.oz; t.r.dx = t.dx; t.r.dy = t.dy; t.r.dz = t.dz;
         t.r.idx = w.x; t.r.idy = w.y; t.r.idz = w.z; t.r.octinv = __float_as_uint(w.w);

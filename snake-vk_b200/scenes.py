@@ -522,11 +522,20 @@ def textured_test_scene(width=96, height=64, seed=11) -> Scene:
     yy, xx = np.mgrid[0:8, 0:16]
     t0[(xx // 2 + yy // 2) % 2 == 0, :3] //= 4  # checker: strong contrast so that filtering errors show
     t1 = rng.integers(0, 256, (7, 5, 4), dtype=np.uint8)
-    sc.textures = [(t0, 1), (t1, 0)]
+    # tangent-space normal map (UNORM): perturbations around +z, so that the mapped normal stays in the upper hemisphere
+    t2 = np.zeros((8, 8, 4), np.uint8)
+    t2[..., 0] = rng.integers(88, 168, (8, 8)); t2[..., 1] = rng.integers(88, 168, (8, 8)); t2[..., 2] = 235; t2[..., 3] = 255
+    sc.textures = [(t0, 1), (t1, 0), (t2, 0)]
+    for m in sc.meshes:  # tangents: any unit vector perpendicular-ish to the normal (GBuffer.vert orthonormalises it)
+        ref = np.where(np.abs(m.normals[:, 1:2]) < 0.9, np.float32([[0, 1, 0]]), np.float32([[1, 0, 0]]))
+        t = np.cross(ref, m.normals)
+        m.tangents = np.ascontiguousarray(t / np.linalg.norm(t, axis=1, keepdims=True), F32)
     mats = sc.materials.copy()
     for i in range(mats.shape[0]):
         if not (int(mats["flags"][i]) & MAT_FLAG_EMISSIVE or i % 3 == 2):
             mats["tex"][i, 0] = i % 2
+        if i % 2 == 0 and not int(mats["flags"][i]) & MAT_FLAG_EMISSIVE:
+            mats["tex"][i, 1] = 2  # normal_tex_idx
     mats["tex"][mats.shape[0] - 1, 0] = 1  # also on the last material whatever it is (an emissive one keeps its plain albedo as emission)
     sc.materials = mats
     return sc

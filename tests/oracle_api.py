@@ -77,6 +77,8 @@ def lib() -> C.CDLL:
         L.snkor_particles_grid.restype = None
         L.snkor_scene_set_texture.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32]
         L.snkor_scene_set_texture.restype = None
+        L.snkor_scene_set_tangents.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.snkor_scene_set_tangents.restype = None
         L.snkor_sample_texture.argtypes = [C.c_void_p, C.c_uint32, C.c_float, C.c_float, C.c_void_p]
         L.snkor_sample_texture.restype = None
         _LIB = L
@@ -121,6 +123,8 @@ class OracleScene:
         for i, (texels, srgb) in enumerate(getattr(scene, "textures", [])):
             t = np.ascontiguousarray(texels, np.uint8)
             lib().snkor_scene_set_texture(self.h, i, t.shape[1], t.shape[0], _p(t), int(bool(srgb)))
+        if "tangents" in f:
+            lib().snkor_scene_set_tangents(self.h, _p(f["tangents"]), f["tangents"].shape[0])
 
     def sample_texture(self, idx: int, u: float, v: float) -> np.ndarray:
         out = np.zeros(3, np.float32)

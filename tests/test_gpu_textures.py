@@ -27,9 +27,27 @@ def test_textured_frames_match_oracle(snk, oracle, mode):
         rt.RecordRenderCmdBuf(ubo, p, mode=mode)
         prev = ubo
         assert np.array_equal(rt.pt.read_aux("albedo"), fr.read("albedo")), f"frame {f}: G-buffer albedo differs"
+        na, nb = rt.pt.read_aux("normal").view(np.uint16), fr.read("normal").view(np.uint16)
+        assert np.array_equal(na, nb), f"frame {f}: G-buffer normal (normal map through the interpolated TBN) differs on {(na != nb).any(-1).sum()} pixels"
         a, b = rt.pt.read_aux("radiance")[..., :3], fr.read("radiance")[..., :3]
         eq = bits_equal(a, b)
         assert eq.mean() >= 0.998, f"mode {mode} frame {f}: radiance differs on {(~eq).sum()} pixels, max abs {np.abs(a - b).max()}"
+
+
+def test_normal_map_changes_the_gbuffer_normal(snk):
+    sc = snk.scenes.textured_test_scene(64, 48)
+    rt = snk.RT().Init(sc)
+    ubo = sc.ubo(0)
+    rt.RecordRenderCmdBuf(ubo, ubo, mode=0)
+    mapped = rt.pt.read_aux("normal").astype(np.float32)[..., :3]
+    rt.pt.set_texture(2, None)  # drop the normal map
+    rt.RecordRenderCmdBuf(ubo, ubo, mode=0)
+    plain = rt.pt.read_aux("normal").astype(np.float32)[..., :3]
+    hit = rt.pt.read_aux("prim") != 0xFFFFFFFF
+    assert not np.array_equal(mapped, plain)
+    assert np.allclose(np.linalg.norm(mapped[hit], axis=-1), 1.0, atol=2e-3), "mapped normals are unit vectors"
+    cosang = (mapped[hit] * plain[hit]).sum(-1)
+    assert cosang.min() > 0.5 and (cosang < 0.999).mean() > 0.2, "the map tilts the normal without flipping it"
 
 
 def test_texture_slot_release(snk):
