@@ -438,7 +438,7 @@ static int build_blas(SnkPt* ctx, uint32_t blas_id, bool fresh, cudaStream_t st)
   CK(cudaGetLastError());
   cudaEventElapsedTime(&ctx->stats.ms_build_last, ctx->ev[6], ctx->ev[7]);
   REQUIRE(counters[4] == 0, SNKPT_E_NOMEM, "BLAS build: node pool overflow");
-  REQUIRE(counters[2] == n && counters[1] == n, SNKPT_E_STATE, "BLAS build: not every primitive reached a leaf");
+  REQUIRE(counters[1] == n, SNKPT_E_STATE, "BLAS build: not every primitive reached a leaf");
   info.node_count = counters[0];
   info.tri_count = counters[1];
   info.bounds_lo[0] = root_lo.x; info.bounds_lo[1] = root_lo.y; info.bounds_lo[2] = root_lo.z;

@@ -384,10 +384,11 @@ __device__ __forceinline__ void refit_from_leaf(const float4* __restrict__ prim_
   int par = parent[node];
   while (par >= 0) {
     __threadfence();
-    if (atomicAdd(&flags[par], 1u) == 0u) return;  // first child to arrive stops; the second one continues
+    // the first child to arrive leaves its index (+1) and stops; the second one finds its sibling there and continues
+    const uint32_t seen = atomicExch(&flags[par], (uint32_t)node + 1u);
+    if (seen == 0u) return;
     __threadfence();
-    const int l = left[par], r = right[par];
-    const int other = (l == node) ? r : l;
+    const int other = (int)seen - 1;
     const float4 olo = __ldcg(&bb_lo[other]), ohi = __ldcg(&bb_hi[other]);
     lo = make_float4(fminf(lo.x, olo.x), fminf(lo.y, olo.y), fminf(lo.z, olo.z), 0.f);
     hi = make_float4(fmaxf(hi.x, ohi.x), fmaxf(hi.y, ohi.y), fmaxf(hi.z, ohi.z), 0.f);
@@ -604,6 +605,184 @@ __device__ void process_wide_node(const CollapseArgs& a, uint32_t w, int b) {
   }
 }
 
+// The same node construction by EIGHT lanes (an aligned octet of a warp, called by whole warps: four consecutive nodes w per warp): lane i owns child i
+// while the children are chosen and placed, lane s owns slot s when the node is written. The one-thread version above is a
+// ~3000-instruction serial chain with its 8x8 cost matrix in local memory, and because the collapse is level-synchronous its
+// LATENCY (x tree depth), not its throughput, set the build time: k_collapse was 1.76 of 2.96 ms at 3 M triangles
+// (profiles/r02y_build_breakdown.txt). Same children, same slots, same records as process_wide_node.
+__device__ void process_wide_node8(const CollapseArgs& a, uint32_t w, const bool active) {
+  const uint32_t lane = threadIdx.x & 31u, sub = lane & 7u, gshift = lane & 24u, gm = 0xFFu << gshift;
+  int ch = 0, cnt = 0;
+  float area = -1.f;
+  float4 lo = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, 0.f), hi = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, 0.f);
+  int m = 1;
+  if (!active) {
+    m = 0;  // an octet past the end of the level: no children, takes part in the warp-wide allocation only
+  } else if (a.n == 1) {
+    if (sub == 0) { cnt = 1; lo = a.bb_lo[0]; hi = a.bb_hi[0]; area = 0.f; }  // single leaf (node index n-1+0 = 0)
+  } else {
+    const int b = (int)a.queue[w];
+    m = 2;
+    // a lane also fetches the children of its child, so that opening it later costs one memory round trip, not two
+    int kid_l = 0, kid_r = 0;
+    if (sub < 2u) {
+      ch = sub ? a.right[b] : a.left[b];
+      if (ch < a.n - 1) { kid_l = a.left[ch]; kid_r = a.right[ch]; }
+      cnt = node_count(a, ch); lo = a.bb_lo[ch]; hi = a.bb_hi[ch]; area = half_area(lo, hi);
+    }
+    // ---- choose up to 8 children by repeatedly opening the largest one
+    for (int phase = 0; phase < 2; ++phase) {
+      const int min_open = phase == 0 ? a.leaf_max + 1 : 2;
+      while (m < 8) {
+        float key = ((int)sub < m && cnt >= min_open && area > -1.f) ? area : -1.f;
+        int bi = (int)sub;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          const float ok = __shfl_xor_sync(gm, key, o, 8);
+          const int oi = __shfl_xor_sync(gm, bi, o, 8);
+          if (ok > key || (ok == key && oi < bi)) { key = ok; bi = oi; }
+        }
+        if (key < 0.f) break;
+        const int cl = __shfl_sync(gm, kid_l, bi, 8), cr = __shfl_sync(gm, kid_r, bi, 8);
+        if ((int)sub == bi || (int)sub == m) {
+          ch = (int)sub == bi ? cl : cr;
+          if (ch < a.n - 1) { kid_l = a.left[ch]; kid_r = a.right[ch]; }
+          cnt = node_count(a, ch); lo = a.bb_lo[ch]; hi = a.bb_hi[ch]; area = half_area(lo, hi);
+        }
+        ++m;
+      }
+    }
+  }
+  const bool valid = (int)sub < m;
+  // ---- node box
+  float4 nlo = lo, nhi = hi;  // lanes without a child hold the empty box
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    nlo.x = fminf(nlo.x, __shfl_xor_sync(gm, nlo.x, o, 8)); nlo.y = fminf(nlo.y, __shfl_xor_sync(gm, nlo.y, o, 8));
+    nlo.z = fminf(nlo.z, __shfl_xor_sync(gm, nlo.z, o, 8));
+    nhi.x = fmaxf(nhi.x, __shfl_xor_sync(gm, nhi.x, o, 8)); nhi.y = fmaxf(nhi.y, __shfl_xor_sync(gm, nhi.y, o, 8));
+    nhi.z = fmaxf(nhi.z, __shfl_xor_sync(gm, nhi.z, o, 8));
+  }
+  // ---- octant-ordered slot assignment (greedy on the largest remaining cost; ties: lowest child, then lowest slot)
+  int my_slot = -1;
+  {
+    const float ccx = 0.5f * (nlo.x + nhi.x), ccy = 0.5f * (nlo.y + nhi.y), ccz = 0.5f * (nlo.z + nhi.z);
+    const float dx = 0.5f * (lo.x + hi.x) - ccx, dy = 0.5f * (lo.y + hi.y) - ccy, dz = 0.5f * (lo.z + hi.z) - ccz;
+    float cost[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) cost[s] = ((s & 1) ? dx : -dx) + ((s & 2) ? dy : -dy) + ((s & 4) ? dz : -dz);
+    uint32_t used_slots = 0;
+    for (int k = 0; k < m; ++k) {
+      // this lane's best free slot; a placed or childless lane bids -inf, a child with NaN costs bids -FLT_MAX on the first free slot
+      float lb = -FLT_MAX;
+      int ls = __ffs(~used_slots) - 1;
+#pragma unroll
+      for (int s = 0; s < 8; ++s)
+        if (!((used_slots >> s) & 1u) && cost[s] > lb) { lb = cost[s]; ls = s; }
+      if (!valid || my_slot >= 0) lb = -INFINITY;
+      int bi = (int)sub;
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        const float ob = __shfl_xor_sync(gm, lb, o, 8);
+        const int oi = __shfl_xor_sync(gm, bi, o, 8), os = __shfl_xor_sync(gm, ls, o, 8);
+        if (ob > lb || (ob == lb && oi < bi)) { lb = ob; bi = oi; ls = os; }
+      }
+      if ((int)sub == bi) my_slot = ls;
+      used_slots |= 1u << ls;
+    }
+  }
+  // ---- quantise (still one child per lane)
+  int be[3] = {quant_exp(nhi.x - nlo.x), quant_exp(nhi.y - nlo.y), quant_exp(nhi.z - nlo.z)};
+  uint32_t qa = 0, qb = 0;
+  if (valid) {
+    uint8_t ql[3], qh[3];
+    quantise_child(nlo, be, lo, hi, ql, qh);
+    qa = (uint32_t)ql[0] | ((uint32_t)ql[1] << 8) | ((uint32_t)ql[2] << 16);
+    qb = (uint32_t)qh[0] | ((uint32_t)qh[1] << 8) | ((uint32_t)qh[2] << 16);
+  }
+  // ---- transpose: lane s takes the child placed in slot s
+  int src = -1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int si = __shfl_sync(gm, my_slot, i, 8);
+    if (si == (int)sub) src = i;
+  }
+  const bool occ = src >= 0;
+  const int from = occ ? src : 0;
+  const int s_ch = __shfl_sync(gm, ch, from, 8), s_cnt = __shfl_sync(gm, cnt, from, 8);
+  uint32_t s_qa = __shfl_sync(gm, qa, from, 8), s_qb = __shfl_sync(gm, qb, from, 8);
+  if (!occ) { s_qa = 0x00FFFFFFu; s_qb = 0u; }  // inverted: never hit
+  // ---- allocate inner children + leaf records (ranks in slot order)
+  const bool is_inner = occ && s_cnt > a.leaf_max, is_leaf = occ && !is_inner;
+  uint32_t inner_mask = (__ballot_sync(gm, is_inner) >> gshift) & 0xFFu;
+  const uint32_t c1 = (__ballot_sync(gm, is_leaf && (s_cnt & 1)) >> gshift) & 0xFFu;
+  const uint32_t c2 = (__ballot_sync(gm, is_leaf && (s_cnt & 2)) >> gshift) & 0xFFu;
+  int n_inner = __popc(inner_mask);
+  const int n_leafrec = __popc(c1) + 2 * __popc(c2);
+  // one atomic per WARP and counter: every wide node bumping the same two words made the L2 atomic unit the bottleneck of the
+  // whole build (same-address atomics retire at ~1 per clock: 3 x 1.9 M of them = 2.6 of the 3.0 ms of k_collapse at 10 M triangles)
+  uint32_t child_base = 0, rec_base = 0;
+  {
+    uint32_t before_i = 0, before_l = 0, total_i = 0, total_l = 0;
+#pragma unroll
+    for (uint32_t g = 0; g < 4; ++g) {
+      const uint32_t gi = __shfl_sync(0xFFFFFFFFu, (uint32_t)n_inner, g * 8), gl = __shfl_sync(0xFFFFFFFFu, (uint32_t)n_leafrec, g * 8);
+      if (g * 8 < gshift) { before_i += gi; before_l += gl; }
+      total_i += gi; total_l += gl;
+    }
+    if (lane == 0u) {
+      if (total_i) child_base = atomicAdd(&a.counters[C_NODES], total_i);
+      if (total_l) rec_base = atomicAdd(&a.counters[C_LEAVES], total_l);
+    }
+    child_base = __shfl_sync(0xFFFFFFFFu, child_base, 0) + before_i;
+    rec_base = __shfl_sync(0xFFFFFFFFu, rec_base, 0) + before_l;
+  }
+  if (!active) return;
+  if (child_base + n_inner > a.node_capacity) {  // cannot happen with capacity >= n; flag and stop growing
+    if (sub == 0u) atomicExch(&a.counters[C_OVERFLOW], 1u);
+    n_inner = 0; inner_mask = 0;
+  }
+  const uint32_t below = (1u << sub) - 1u;
+  uint32_t meta = 0;
+  if (is_inner) {
+    if ((inner_mask >> sub) & 1u) {
+      meta = (1u << 5) | (24u + sub);
+      // work item of the child wide node (read by the next level, after the grid-wide barrier)
+      a.queue[child_base + __popc(inner_mask & below)] = (uint32_t)s_ch;
+    }
+  } else if (is_leaf) {
+    const uint32_t rec_off = __popc(c1 & below) + 2u * __popc(c2 & below);
+    const uint32_t unary = s_cnt == 1 ? 1u : (s_cnt == 2 ? 3u : 7u);
+    meta = (unary << 5) | rec_off;
+    emit_leaf_records(a, s_ch, a.leaf_offset + rec_base + rec_off);
+  }
+  // ---- write the node: lane 0 the 24-byte header, every lane the 7 bytes of its slot
+  uint8_t* np = reinterpret_cast<uint8_t*>(a.nodes + a.node_offset + w);
+  if (sub == 0u) {
+    const uint32_t ebits = (uint32_t)be[0] | ((uint32_t)be[1] << 8) | ((uint32_t)be[2] << 16) | (inner_mask << 24);
+    *reinterpret_cast<float4*>(np) = make_float4(nlo.x, nlo.y, nlo.z, __uint_as_float(ebits));
+    *reinterpret_cast<uint2*>(np + 16) = make_uint2(a.node_offset + child_base, a.leaf_offset + rec_base);
+  }
+  np[24 + sub] = (uint8_t)meta;
+  np[32 + sub] = (uint8_t)s_qa; np[40 + sub] = (uint8_t)(s_qa >> 8); np[48 + sub] = (uint8_t)(s_qa >> 16);
+  np[56 + sub] = (uint8_t)s_qb; np[64 + sub] = (uint8_t)(s_qb >> 8); np[72 + sub] = (uint8_t)(s_qb >> 16);
+}
+
+#ifndef SNK_COLLAPSE_OCTET
+#define SNK_COLLAPSE_OCTET 1  // 1: eight lanes per wide node (process_wide_node8); 0: one thread per node
+#endif
+// nodes [begin, end) of one level by `nthreads` threads of which this is number `tid` (whole warps call this together)
+__device__ __forceinline__ void process_level(const CollapseArgs& a, uint32_t begin, uint32_t end, uint32_t tid, uint32_t nthreads) {
+#if SNK_COLLAPSE_OCTET
+  for (uint32_t w0 = begin + ((tid & ~31u) >> 3); w0 < end; w0 += nthreads >> 3) {  // warp-uniform trip count
+    const uint32_t w = w0 + ((tid & 31u) >> 3);
+    process_wide_node8(a, w, w < end);
+  }
+#else
+  for (uint32_t w = begin + tid; w < end; w += nthreads) process_wide_node(a, w, (int)a.queue[w]);
+#endif
+}
+
 // Level-synchronous collapse in ONE cooperative launch: the wide nodes of a level occupy a contiguous index range
 // (children are allocated with an atomic bump, so level L+1 = everything allocated while level L was processed);
 // all threads process the level with converged warps, then the grid synchronises and moves to the next range.
@@ -614,7 +793,7 @@ __global__ void __launch_bounds__(128) k_collapse(CollapseArgs a) {
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
   uint32_t begin = 0, end = 1;
   while (begin < end) {
-    for (uint32_t w = begin + gtid; w < end; w += gsize) process_wide_node(a, w, (int)a.queue[w]);
+    process_level(a, begin, end, gtid, gsize);
     grid.sync();
     begin = end;
     const uint32_t total = *((volatile uint32_t*)&a.counters[C_NODES]);
@@ -678,7 +857,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_build_small(const float4* __r
   volatile uint32_t& s_end = *reinterpret_cast<volatile uint32_t*>(&sk[0]);  // the keys are dead by now (static smem is at its 48 KB limit)
   uint32_t begin = 0, end = 1;
   while (begin < end) {
-    for (uint32_t w = begin + t; w < end; w += NT) process_wide_node(a, w, (int)a.queue[w]);
+    process_level(a, begin, end, (uint32_t)t, (uint32_t)NT);
     __threadfence();
     __syncthreads();
     if (t == 0) {
@@ -864,7 +1043,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_build_small_ploc(const float4
   volatile uint32_t& s_end = *reinterpret_cast<volatile uint32_t*>(&sv[SMALL_MAX - 1]);
   uint32_t begin = 0, end = 1;
   while (begin < end) {
-    for (uint32_t w = begin + t; w < end; w += NT) process_wide_node(a, w, (int)a.queue[w]);
+    process_level(a, begin, end, (uint32_t)t, (uint32_t)NT);
     __threadfence();
     __syncthreads();
     if (t == 0) {
@@ -1110,7 +1289,7 @@ int launch_build(BuildScratch& s, uint32_t n, const BuildOutput& out, const floa
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_collapse, 128, 0);
       if (ctas_per_sm < 1) ctas_per_sm = 1;
     }
-    const uint32_t want = (cap + 127) / 128, resident = (uint32_t)(sms * ctas_per_sm);
+    const uint32_t want = (uint32_t)(((uint64_t)cap * (SNK_COLLAPSE_OCTET ? 8 : 1) + 127) / 128), resident = (uint32_t)(sms * ctas_per_sm);
     void* args[] = {&a};
     cudaLaunchCooperativeKernel((const void*)k_collapse, dim3(want < resident ? want : resident), dim3(128), args, 0, st);
     ++launches;
