@@ -167,14 +167,14 @@ def run_reference_arm(args, snk):
         secs += s
     v = rays / secs / 1e6
     sample = f"rows [{rows[0]},{rows[1]}) of the {args.width}x{args.height} frame, 2 consecutive frames per step (frame 1 exercises temporal reuse)"
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * secs / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": {"workload": desc, "mode": args.mode, "resolution": [args.width, args.height]},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "CPU oracle (restatement of the reference GLSL; the Vulkan reference cannot run headless here, SURVEY §8c)",
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -418,13 +418,28 @@ def run_gpu_arm(args, snk):
             line["other_mode"] = {"mode": other, "value": other_res["value"], "unit": UNIT, "ms_per_step": other_res["ms_per_step"],
                                   "rays_per_frame": other_res["rays_per_frame"], "roofline": other_res["roofline"], "kernels": other_res["kernels"],
                                   "clocks": other_res["clocks"]}
-        print(json.dumps(line))
+        emit(line)
     pt.close()
     if world > 1:
         dist.destroy_process_group()
 
 
+JSON_OUT = sys.stdout
+
+
+def emit(line):
+    """the ONE JSON line of the contract, on the process's real stdout"""
+    JSON_OUT.write(json.dumps(line) + "\n")
+    JSON_OUT.flush()
+
+
 def main():
+    # stdout carries the JSON line and nothing else: libraries print there too (NCCL's version banner under
+    # NCCL_DEBUG=VERSION, which the GPU boxes set), so file descriptor 1 is pointed at stderr for everything but emit()
+    global JSON_OUT
+    sys.stdout.flush()
+    JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
