@@ -11,7 +11,8 @@ metric: 1 spp, 4 bounces + ReSTIR DI) and `--mode reference` (the reference's ow
 mode not selected is measured too and reported under `other_mode`.
 `value` = all rays traced by all ranks / max-over-ranks device time.
 N > 1 is sample-sharded (every rank renders the whole frame with its own seed; radiance is summed over NVLink
-with one NCCL all-reduce per frame = the accumulation step) → weak scaling. `--shard rows` renders contiguous
+with one NCCL all-reduce per frame = the accumulation step, running on a second stream while the next frame
+renders; the timed region waits for all of them) → weak scaling. `--shard rows` renders contiguous
 row bands instead (strong scaling, no collective; halo rows are re-rendered locally).
 
 `--impl reference` times the CPU oracle (the reference cannot run here: SURVEY §8c) on a bounded crop of the
@@ -245,6 +246,28 @@ def run_gpu_arm(args, snk):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return [float(tmax[0])] + [float(v) for v in t[1:]]
 
+    # Sample sharding: frame f's radiance is copied to one of two accumulation images and summed over the ranks on a second
+    # stream while frame f+1 renders (the render never waits for NVLink); drain_samples() makes the timed stream wait for every
+    # all-reduce still in flight, so each timed region contains K frames AND their K all-reduces.
+    acc = [torch.empty_like(rad) for _ in range(2)] if rad is not None else None
+    comm = torch.cuda.Stream(device=local) if rad is not None else None
+    acc_done = [None, None]
+
+    def accumulate_samples(f):
+        k = f & 1
+        if acc_done[k] is not None:
+            work.wait_event(acc_done[k])    # the all-reduce that used this image two frames ago
+        acc[k].copy_(rad)
+        comm.wait_event(work.record_event())
+        with torch.cuda.stream(comm):
+            dist.all_reduce(acc[k])
+            acc_done[k] = comm.record_event()
+
+    def drain_samples():
+        for ev in acc_done:
+            if ev is not None:
+                work.wait_event(ev)
+
     def measure(mode_name: str, with_e2e: bool):
         mode = snk.api.MODE_REFERENCE if mode_name == "reference" else snk.api.MODE_NORTHSTAR
         settings = snk.api.default_settings(mode=mode)
@@ -259,13 +282,21 @@ def run_gpu_arm(args, snk):
             pt.trace_primary(stream=stream)
             pt.render(settings, stream)
             if rad is not None:
-                dist.all_reduce(rad)        # accumulation step: sum of the per-GPU samples over NVLink
+                accumulate_samples(f)       # accumulation step: sum of the per-GPU samples over NVLink
             if res_planes is not None:
                 snk.sharding.exchange_final(bands, rank, res_planes, dist)  # final-reservoir halos to the band neighbours
 
         pt.set_profiling(0)
         for _ in range(args.warmup):
             step()
+        if rad is not None and args.warmup:
+            # the pipelined accumulation image of the last warm-up frame = a plain all-reduce of that frame's radiance
+            drain_samples()
+            chk = rad.clone()
+            dist.all_reduce(chk)
+            torch.cuda.synchronize()
+            if not torch.allclose(acc[(frame_no[0] - 1) & 1], chk, rtol=1e-6, atol=0.0, equal_nan=True):
+                raise SystemExit("bench.py: overlapped sample accumulation differs from a direct all-reduce")
         barrier()
         st0 = pt.stats()
         pt.set_profiling(1)
@@ -277,6 +308,7 @@ def run_gpu_arm(args, snk):
         e0.record()
         for _ in range(args.steps):
             step()
+        drain_samples()
         e1.record()
         barrier()
         ms_total = e0.elapsed_time(e1)
@@ -313,6 +345,7 @@ def run_gpu_arm(args, snk):
                         pt.wait_output((k - 1) % 2)                   # the previous frame is now on the host
 
             def e2e_drain():
+                drain_samples()
                 if reads and kk[0]:
                     pt.wait_output((kk[0] - 1) % 2)
 
