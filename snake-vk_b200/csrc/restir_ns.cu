@@ -4,7 +4,8 @@
 //   [trace any]    persistent wavefront traversal kernel (trace.cu), one launch per light type present
 //   k_rs_temporal  visibility of the initial sample, temporal reuse at the motion-vector-reprojected pixel -> half 1
 //   k_rs_spatial   spatial reuse with the bias-correcting MIS weight -> half 0 (next frame's history);
-//                  final contributions on the exact primary-hit surface + 3 shadow rays (point, emissive, directional)
+//   k_rs_final     final contributions of that reservoir on the exact primary-hit surface + 3 shadow rays (point, emissive,
+//                  directional)
 //   [trace any]
 //   k_rs_resolve   direct = sum of contribution x visibility -> planes.direct
 //
@@ -288,22 +289,21 @@ __global__ void __launch_bounds__(128, 8) k_rs_temporal(SceneDev D, FrameConsts 
 // ---- stage 3 ---------------------------------------------------------------------------------------------------------
 constexpr int RS_MAXN = 9;  // this pixel + up to 8 neighbours
 
+#ifndef SNK_RS_PREFETCH
+#define SNK_RS_PREFETCH 0  // measured (profiles/r02z_variants_rs_prefetch.txt): rs_spatial 0.690 -> 0.811 ms with the prefetches: not adopted
+#endif
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #ifndef SNK_RS_SPATIAL_CTAS
 #define SNK_RS_SPATIAL_CTAS 5
 #endif
-__global__ void __launch_bounds__(128, SNK_RS_SPATIAL_CTAS) k_rs_spatial(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, RsBuffers B, uint32_t npix,
-                                                    unsigned long long* counters, uint32_t* q_refs, uint32_t* q_count) {
+__global__ void __launch_bounds__(128, SNK_RS_SPATIAL_CTAS) k_rs_spatial(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, uint32_t npix) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned long long n_shadow = 0;
-  bool ray0 = false, ray1 = false, ray2 = false;
   size_t px = 0;
   uint32_t x, y;
   if (pixel_of(fc, i, x, y, px)) {
-    const size_t np = rp.npix_frame;
     const ResPlanes half0{P.res[0][0], P.res[0][1], P.res[0][2]}, half1{P.res[1][0], P.res[1][1], P.res[1][2]};
     Reservoir out; rs_empty(out);
-    vec3 C0 = v3(0.0f), C1 = v3(0.0f), C2 = v3(0.0f);
-    const uint32_t n_pl = D.lights->num_pointlights, n_em = D.num_emissive;
+    const uint32_t n_pl = D.lights->num_pointlights;
     if (px_shaded(P, px)) {
       RsSurf s; vec3 pos, n_raw;
       rs_gsurf(fc, P, x, y, s, pos, n_raw);
@@ -313,6 +313,19 @@ __global__ void __launch_bounds__(128, SNK_RS_SPATIAL_CTAS) k_rs_spatial(SceneDe
       cpx[nc++] = x | (y << 16);
       int ns = rp.num_spatial;
       if (ns > RS_MAXN - 1) ns = RS_MAXN - 1;
+#if SNK_RS_PREFETCH
+      // the stage is a chain of dependent reads of the neighbours' planes (ncu r02s: issue slots 36 % busy, L1 hit 33 %); the
+      // neighbour positions depend only on the counter-based RNG, so their cache lines are requested before anything is consumed
+      for (int k = 0; k < ns; ++k) {
+        const float ua = rs_rand(h0, RS_DIM_SPATIAL + 2u * (uint32_t)k), ub = rs_rand(h0, RS_DIM_SPATIAL + 2u * (uint32_t)k + 1u);
+        const int qx = (int)x + (int)((ua * 2.0f - 1.0f) * rp.radius), qy = (int)y + (int)((ub * 2.0f - 1.0f) * rp.radius);
+        if (qx < 0 || qy < 0 || qx >= (int)fc.W || qy >= (int)fc.H) continue;
+        const size_t qp = (size_t)qy * fc.W + qx;
+        prefetch_l1(P.prim + qp); prefetch_l1(P.flags + qp); prefetch_l1(P.normal + qp); prefetch_l1(P.hit_t + qp);
+        prefetch_l1(half1.a + qp); prefetch_l1(half1.b + qp); prefetch_l1(half1.c + qp);
+        prefetch_l1(P.depth + qp); prefetch_l1(P.albedo + qp); prefetch_l1(P.rma + qp);
+      }
+#endif
       const float t_q = P.hit_t[px];
       for (int k = 0; k < ns; ++k) {
         const float ua = rs_rand(h0, RS_DIM_SPATIAL + 2u * (uint32_t)k), ub = rs_rand(h0, RS_DIM_SPATIAL + 2u * (uint32_t)k + 1u);
@@ -369,6 +382,30 @@ __global__ void __launch_bounds__(128, SNK_RS_SPATIAL_CTAS) k_rs_spatial(SceneDe
         if (src_pl >= 0) out.w_pl = (den_pl > 0.0f && p_pl > 0.0f) ? (out.w_sum_pl * (num_pl / den_pl)) / p_pl : 0.0f;
         if (src_em >= 0) out.w_em = (den_em > 0.0f && p_em > 0.0f) ? (out.w_sum_em * (num_em / den_em)) / p_em : 0.0f;
       }
+    }
+    store_reservoir(half0, px, out);
+  }
+}
+
+#ifndef SNK_RS_FINAL_CTAS
+#define SNK_RS_FINAL_CTAS 6
+#endif
+// final contributions of the reservoir the spatial stage just stored, on the exact primary-hit surface. Its own kernel: together
+// with the reuse loops the stage needed 96 registers AND 190 local-memory spill instructions (cuobjdump, r02z).
+__global__ void __launch_bounds__(128, SNK_RS_FINAL_CTAS) k_rs_final(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, RsBuffers B, uint32_t npix,
+                                                                     unsigned long long* counters, uint32_t* q_refs, uint32_t* q_count) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long n_shadow = 0;
+  bool ray0 = false, ray1 = false, ray2 = false;
+  size_t px = 0;
+  uint32_t x, y;
+  if (pixel_of(fc, i, x, y, px)) {
+    const size_t np = rp.npix_frame;
+    const ResPlanes half0{P.res[0][0], P.res[0][1], P.res[0][2]};
+    vec3 C0 = v3(0.0f), C1 = v3(0.0f), C2 = v3(0.0f);
+    const uint32_t n_pl = D.lights->num_pointlights, n_em = D.num_emissive;
+    if (px_shaded(P, px)) {
+      const Reservoir out = load_reservoir(half0, px);
       // final contributions on the exact primary-hit surface
       const float2 bc = P.bary[px];
       const NsSurf hs = ns_surface(D, P.inst[px], P.prim[px], bc.x, bc.y);
@@ -402,7 +439,6 @@ __global__ void __launch_bounds__(128, SNK_RS_SPATIAL_CTAS) k_rs_spatial(SceneDe
         }
       }
     }
-    store_reservoir(half0, px, out);
     if (n_pl > 0 && !ray0) B.vis[px] = 1.0f;
     if (n_em > 0 && !ray1) B.vis[np + px] = 1.0f;
     if (!ray2) B.vis[2 * np + px] = 1.0f;
@@ -493,9 +529,12 @@ int restir_ns_reuse(SnkPt* ctx, const SnkRtSettings& s, const RefQueue& q, cudaS
   prof_end(ctx, rec, st);
   cudaEventRecord(ctx->ev[3], st);
   rec = prof_begin(ctx, "rs_spatial", L.npix, false, false, st);
-  k_rs_spatial<<<(stage_threads(ctx->fc.W, ctx->fc.row1 - ctx->fc.row0) + 127) / 128, 128, 0, st>>>(D, ctx->fc, ctx->planes, L.rp, L.B, L.npix, counters, q.refs, q.count);
+  k_rs_spatial<<<(stage_threads(ctx->fc.W, ctx->fc.row1 - ctx->fc.row0) + 127) / 128, 128, 0, st>>>(D, ctx->fc, ctx->planes, L.rp, L.npix);
   prof_end(ctx, rec, st);
-  return 2;
+  rec = prof_begin(ctx, "rs_final", L.npix, false, false, st);
+  k_rs_final<<<(stage_threads(ctx->fc.W, ctx->fc.row1 - ctx->fc.row0) + 127) / 128, 128, 0, st>>>(D, ctx->fc, ctx->planes, L.rp, L.B, L.npix, counters, q.refs, q.count);
+  prof_end(ctx, rec, st);
+  return 3;
 }
 
 // direct = sum of final contribution x visibility
