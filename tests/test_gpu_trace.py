@@ -172,3 +172,68 @@ def test_refit_matches_rebuild_and_bruteforce(snk, oracle):
     assert hits_equal(pt.trace_rays(rays), got).all()
     assert int(pt.stats()["stack_overflows"]) == 0
     pt.close()
+
+
+def _soup(rng, n, spread, size):
+    """n random triangles: centres in [-spread, spread]^3, edge vectors of length ~size"""
+    c = rng.uniform(-spread, spread, (n, 1, 3))
+    p = (c + rng.normal(scale=size, size=(n, 3, 3))).reshape(-1, 3).astype(np.float32)
+    nrm = np.tile(np.float32([[0, 1, 0]]), (3 * n, 1))
+    return p, nrm, np.arange(3 * n, dtype=np.uint32)
+
+
+@pytest.mark.parametrize("case", ["n1", "n2", "n3", "n9", "n17", "n4096", "n4097", "identical", "coplanar_grid", "mixed_scale", "degenerate"])
+def test_builder_edge_cases_match_bruteforce(snk, oracle, case):
+    """BLAS sizes around the branches of the builder (single leaf, fewer primitives than the 8 slots of a wide node, the
+    one-CTA path's 4096-primitive limit and the first size of the general path), Morton-code duplicates (identical and
+    coincident primitives), primitives of very different size and zero-area triangles: every closest hit and every any-hit
+    answer equals the brute-force oracle's, bit for bit, for an identity and a rotated, non-uniformly scaled instance."""
+    S = snk.scenes
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(case.encode()))
+    if case.startswith("n"):
+        p, nrm, idx = _soup(rng, int(case[1:]), 4.0, 0.6)
+    elif case == "identical":  # 300 copies of the same triangle + a few others: equal Morton keys, equal boxes
+        p1, _, _ = _soup(rng, 1, 1.0, 1.5)
+        p2, _, _ = _soup(rng, 20, 4.0, 0.6)
+        p = np.concatenate([np.tile(p1, (300, 1)), p2]).astype(np.float32)
+        nrm = np.tile(np.float32([[0, 1, 0]]), (p.shape[0], 1)); idx = np.arange(p.shape[0], dtype=np.uint32)
+    elif case == "coplanar_grid":  # 32 x 32 quads in the plane y = 0.5: one Morton axis carries no information
+        g = np.arange(33, dtype=np.float32) * 0.25 - 4.0
+        xx, zz = np.meshgrid(g, g)
+        p = np.stack([xx.ravel(), np.full(xx.size, 0.5, np.float32), zz.ravel()], -1).astype(np.float32)
+        q = (np.arange(32)[:, None] * 33 + np.arange(32)[None, :]).ravel()
+        idx = np.stack([q, q + 1, q + 34, q, q + 34, q + 33], -1).astype(np.uint32).ravel()
+        nrm = np.tile(np.float32([[0, 1, 0]]), (p.shape[0], 1))
+    elif case == "mixed_scale":  # two huge triangles over 3000 tiny ones
+        pa, _, _ = _soup(rng, 3000, 4.0, 0.02)
+        pb = np.float32([[-6, -1, -6], [6, -1, -6], [0, -1, 7], [-6, 6, 0], [6, 6, 0], [0, -6, 0.5]])
+        p = np.concatenate([pa, pb]).astype(np.float32)
+        nrm = np.tile(np.float32([[0, 1, 0]]), (p.shape[0], 1)); idx = np.arange(p.shape[0], dtype=np.uint32)
+    else:  # degenerate: zero-area (collinear / point) triangles between ordinary ones
+        p, nrm, idx = _soup(rng, 64, 4.0, 0.6)
+        p = p.copy()
+        p[3:6] = p[3]                      # a point
+        p[9:12] = [p[9], p[9] + 1, p[9] + 2]  # collinear
+    mesh = S.Mesh.single(p, nrm, idx)
+    ents = [S.Entity(0, np.eye(4, dtype=np.float32), [0]), S.Entity(0, S.trs((1.5, -0.5, 2), (25, 50, 75), (1.3, 0.7, 1.1)), [0])]
+    sc = S.Scene(case, 32, 32, [mesh], ents, S.make_materials([((0.8, 0.8, 0.8), 0.5, 0.0, 0)]), S.Camera((0, 0, -20), (0, 0, 1)))
+    pt = snk.PathTracer(32, 32)
+    pt.upload_scene(sc)
+    rays = random_rays(rng, 6000, (-7, -7, -7), (7, 7, 7), S)
+    # half of the rays aim at a vertex of the mesh so that small inputs are hit at all
+    tgt = p[rng.integers(0, p.shape[0], 3000)] + rng.normal(scale=0.05, size=(3000, 3)).astype(np.float32)
+    d = tgt - rays["o"][:3000]
+    rays["d"][:3000] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    osc = oracle.OracleScene(sc)
+    ref = osc.trace(rays, brute=True)
+    got = pt.trace_rays(rays)
+    same = hits_equal(got, ref)
+    assert same.all(), f"{case}: {(~same).sum()} of {same.size} closest hits differ; first: {got[~same][:3]} vs {ref[~same][:3]}"
+    assert (ref["t"] >= 0).any()
+    got_any = pt.trace_rays(rays, any_hit=True)
+    assert np.array_equal(got_any["t"] >= 0, ref["t"] >= 0)
+    tbl = pt.blas_table()[0]
+    assert (tbl["bounds_lo"] <= p.min(0)).all() and (tbl["bounds_hi"] >= p.max(0)).all()
+    assert int(pt.stats()["stack_overflows"]) == 0
+    pt.close()
