@@ -171,10 +171,16 @@ __global__ void __launch_bounds__(128, 6) k_ns_vertex(SceneDev D, FrameConsts fc
                                                    uint32_t nee_from, unsigned long long* counters, uint32_t* q_refs, uint32_t* q_count,
                                                    const uint32_t* paths_in, const uint32_t* paths_in_count, uint32_t* paths_out,
                                                    uint32_t* paths_out_count) {
-  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  // grid-stride over the compact list: the host sizes the grid for the paths it EXPECTS to be alive at bounce b (it never reads
+  // the count back); 16 200 CTAs for the 100-300 k paths of the late bounces spent a third of the stage launching empty CTAs
+  uint32_t count = __ldcg(paths_in_count);
+  if (count > npix) count = npix;
+  unsigned long long n_shadow = 0, n_closest = 0;
+  for (uint32_t base = blockIdx.x * blockDim.x; base < count; base += gridDim.x * blockDim.x) {  // CTA-uniform trip count
+  const uint32_t j = base + threadIdx.x;
   bool has_shadow = false, has_closest = false;
   uint32_t i = 0;
-  if (j < npix && j < __ldcg(paths_in_count)) {
+  if (j < count) {
     i = paths_in[j];
     const uint32_t x = i % fc.W, y = fc.row0 + i / fc.W;
     const uint32_t pixel = y * fc.W + x;
@@ -216,7 +222,9 @@ __global__ void __launch_bounds__(128, 6) k_ns_vertex(SceneDev D, FrameConsts fc
   }
   q_append3(q_refs, q_count, has_closest, make_ref(SEG_NS_CLOSEST, i), has_shadow, make_ref(SEG_NS_SHADOW, i), false, 0u);
   q_append1(paths_out, paths_out_count, has_closest, i);
-  flush_counts(has_shadow ? 1ull : 0ull, has_closest ? 1ull : 0ull, counters);
+  n_shadow += has_shadow ? 1ull : 0ull; n_closest += has_closest ? 1ull : 0ull;
+  }
+  flush_counts(n_shadow, n_closest, counters);
 }
 
 __global__ void __launch_bounds__(256) k_ns_resolve(SceneDev D, FrameConsts fc, PixelPlanes P, NsBuffers B, uint32_t npix, uint32_t max_bounces,
@@ -315,7 +323,9 @@ int launch_northstar_frame(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st) 
   for (uint32_t b = 1; b <= max_bounces; ++b) {
     snprintf(name, sizeof(name), "ns_vertex.%u", b);
     rec = prof_begin(ctx, name, npix, false, false, st);
-    k_ns_vertex<<<g128, 128, 0, st>>>(D, fc, B, npix, b, max_bounces, nee_from, counters, Q.refs, Q.count, paths[(b - 1) & 1], path_count + (b - 1),
+    // expected survivors: everything at bounce 1, then a shrinking multiple of the resident grid (148 SMs x 6 CTAs)
+    const uint32_t g_cap = 148u * 6u * (b == 1 ? 32u : b == 2 ? 8u : b == 3 ? 4u : 2u);
+    k_ns_vertex<<<g128 < g_cap ? g128 : g_cap, 128, 0, st>>>(D, fc, B, npix, b, max_bounces, nee_from, counters, Q.refs, Q.count, paths[(b - 1) & 1], path_count + (b - 1),
                                       paths[b & 1], path_count + b);
     prof_end(ctx, rec, st);
     snprintf(name, sizeof(name), "trace.q%d", q);
