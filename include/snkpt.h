@@ -158,8 +158,7 @@ typedef struct SnkHit {
 enum {
   SNKPT_RAY_CLOSEST = 0u,
   SNKPT_RAY_ANY = 1u,          /* TerminateOnFirstHit|Opaque|SkipClosestHit    */
-  SNKPT_RAY_DEVICE_PTRS = 2u,  /* rays / hits already live in device memory    */
-  SNKPT_RAY_SORT_OCTANT = 4u   /* bin rays by direction octant before tracing  */
+  SNKPT_RAY_DEVICE_PTRS = 2u   /* rays / hits already live in device memory    */
 };
 
 /* ---- configuration -------------------------------------------------------- */
@@ -194,8 +193,7 @@ typedef struct SnkRtSettings {
 } SnkRtSettings;
 enum {
   SNKPT_RT_NO_RESTIR = 1u, /* skip both reservoir passes                         */
-  SNKPT_RT_NO_BOUNCE = 2u, /* skip BounceDiffuse / path continuation             */
-  SNKPT_RT_SORT_RAYS = 4u  /* octant-bin secondary rays before traversal         */
+  SNKPT_RT_NO_BOUNCE = 2u  /* skip BounceDiffuse / path continuation             */
 };
 
 /* what snkpt_read_aux / snkpt_device_ptr can name */
