@@ -292,6 +292,12 @@ class PathTracer:
     def reset_history(self):
         self._ck(self.L.snkpt_reset_history(self.h), "snkpt_reset_history")
 
+    def resize(self, width: int, height: int):
+        """window resize (EditorLayer.cpp:351-366, :415-423): every per-pixel resource is recreated, the history is invalid"""
+        self._ck(self.L.snkpt_resize(self.h, width, height), "snkpt_resize")
+        self.width, self.height = width, height
+        self.rows = (0, height)
+
     # ---- readback
     def read_output(self, fmt="f16", out: np.ndarray | None = None) -> np.ndarray:
         nrows = self.rows[1] - self.rows[0]

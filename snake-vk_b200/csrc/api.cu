@@ -366,9 +366,16 @@ int snkpt_resize(SnkPt* ctx, uint32_t width, uint32_t height) {
   if (!ctx) return SNKPT_E_INVALID;
   REQUIRE(width && height, SNKPT_E_INVALID, "snkpt_resize: zero extent");
   CK(cudaSetDevice(ctx->device));
+  // the planes are freed and reallocated: nothing that reads or writes them may still be in flight — frames on the caller's
+  // stream, uploads, asynchronous read-backs on the copy stream (EditorLayer.cpp:351-366 waits for the device as well)
+  CK(cudaStreamSynchronize(work_stream(ctx)));
+  if (ctx->copy_stream) CK(cudaStreamSynchronize(ctx->copy_stream));
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->W = width; ctx->H = height; ctx->row0 = 0; ctx->row1 = height;
-  return alloc_pixels(ctx);
+  const int rc = alloc_pixels(ctx);
+  if (rc) return rc;
+  CK(cudaStreamSynchronize(ctx->stream));  // the cleared planes are in place before a frame on any other stream starts
+  return SNKPT_OK;
 }
 
 int snkpt_set_rows(SnkPt* ctx, uint32_t row_begin, uint32_t row_end) {

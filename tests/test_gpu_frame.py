@@ -120,3 +120,46 @@ def test_async_uploads_and_readback_pipeline(snk, oracle):
     got.append(bufs[4 % 2].copy())
     for f in range(5):
         assert np.array_equal(want[f].view(np.uint16), got[f].view(np.uint16)), f"frame {f}"
+
+
+@pytest.mark.parametrize("mode", ["reference", "northstar"])
+def test_resize_equals_fresh_context(snk, oracle, mode):
+    """snkpt_resize (window resize, EditorLayer.cpp:351-366): all per-pixel state is recreated and the history is invalid, so the
+    frames after a resize equal those of a context created at the new size — image, reservoirs and ray counts, bit for bit —
+    and a read-back that was still in flight at the old size does not disturb it."""
+    mode_id = snk.api.MODE_REFERENCE if mode == "reference" else snk.api.MODE_NORTHSTAR
+    small, big = snk.scenes.small_test_scene(64, 48), snk.scenes.small_test_scene(96, 64)
+
+    def frames(rt, sc, n):
+        out, prev = [], None
+        for f in range(n):
+            ubo = sc.ubo(f)
+            rt.RecordRenderCmdBuf(ubo, ubo if prev is None else prev, mode=mode_id)
+            prev = ubo
+            st = rt.pt.stats()
+            out.append((rt.pt.read_output("f32").copy(), rt.pt.read_aux("reservoirs_final").copy(), rt.pt.read_aux("reservoirs_temporal").copy(),
+                        int(st["rays_secondary"]), int(st["rays_shadow"])))
+        return out
+
+    rt = snk.RT().Init(small)
+    frames(rt, small, 2)                      # history at the old size
+    pending = np.empty((48, 64, 4), np.float16)
+    rt.pt.read_output_async(pending, slot=0)  # still in flight when the resize arrives
+    rt.pt.resize(96, 64)
+    got = frames(rt, big, 3)
+    fresh = snk.RT().Init(big)
+    want = frames(fresh, big, 3)
+    for f, (g, w) in enumerate(zip(got, want)):
+        assert g[0].shape == (64, 96, 4)
+        assert np.array_equal(g[0].view(np.uint32), w[0].view(np.uint32)), f"frame {f} after the resize differs from a fresh context"
+        assert np.array_equal(g[1].view(np.uint8), w[1].view(np.uint8)) and np.array_equal(g[2].view(np.uint8), w[2].view(np.uint8))
+        assert g[3:] == w[3:]
+    # back to the first size: equal to what a fresh small context renders
+    rt.pt.resize(64, 48)
+    again = frames(rt, small, 2)
+    ref = frames(snk.RT().Init(small), small, 2)
+    for g, w in zip(again, ref):
+        assert np.array_equal(g[0].view(np.uint32), w[0].view(np.uint32))
+    with pytest.raises(snk.SnkError):
+        rt.pt.resize(0, 10)
+    rt.pt.close(); fresh.pt.close()
