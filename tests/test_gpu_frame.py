@@ -163,3 +163,78 @@ def test_resize_equals_fresh_context(snk, oracle, mode):
     with pytest.raises(snk.SnkError):
         rt.pt.resize(0, 10)
     rt.pt.close(); fresh.pt.close()
+
+
+def test_accumulate_rows_and_diagnostics(snk, oracle):
+    """the entry points without a reference call site of their own (second table): progressive accumulation,
+    a row band set after creation, raw plane pointers / sizes, per-launch timings and the order-independent work counters."""
+    sc = snk.scenes.small_test_scene(64, 48)
+    rt = snk.RT().Init(sc)
+    pt = rt.pt
+    pt.synchronize()
+    # ---- snkpt_accumulate: running mean in float32, in the kernel's own operation order
+    mean = None
+    prev = None
+    for f in range(4):
+        ubo = sc.ubo(f)
+        rt.RecordRenderCmdBuf(ubo, ubo if prev is None else prev, mode=snk.api.MODE_NORTHSTAR)
+        prev = ubo
+        pt.accumulate(reset=(f == 0))
+        r = pt.read_aux("radiance")
+        if f == 0:
+            mean = r.copy()
+        else:
+            mean = (mean + (r - mean) * np.float32(np.float32(1.0) / np.float32(f + 1))).astype(np.float32)
+        acc = pt.read_aux("accum")
+        assert np.array_equal(acc[..., :3].view(np.uint32), mean[..., :3].view(np.uint32)), f"accumulation after frame {f}"
+        out = pt.read_output("f16")
+        assert np.array_equal(out[..., :3], mean[..., :3].astype(np.float16))
+    # ---- raw pointers and sizes
+    p, n = pt.device_ptr(0x100)
+    assert p and n == 64 * 48 * 8
+    p, n = pt.device_ptr(0x101)
+    assert p and n == 64 * 48 * 16
+    assert pt.read_raw(20, snk.api.BLAS_INFO_DTYPE).size >= len(sc.meshes)  # snkpt_aux_size + snkpt_read_aux: one BLAS per submesh
+    # ---- per-launch timings (level 1) and work counters (level 2)
+    pt.set_profiling(2)
+    ubo = sc.ubo(4)
+    rt.RecordRenderCmdBuf(ubo, prev, mode=snk.api.MODE_NORTHSTAR)
+    recs = pt.launch_timings()
+    names = [r["name"].decode() for r in recs]
+    assert "primary" in names and any(nm.startswith("trace.q") for nm in names) and "ns_resolve" in names
+    assert all(r["ms"] > 0 for r in recs)
+    tr = [r for r in recs if r["is_trace"]]
+    st = pt.stats()
+    assert sum(int(r["live"]) for r in tr) == int(st["rays_shadow"]) + int(st["rays_secondary"])
+    assert all(int(r["nodes"]) >= int(r["live"]) for r in tr if r["live"])  # every live ray tests at least the TLAS root
+    assert pt.launch_timings().size == 0  # returned and cleared
+    pt.set_profiling(0)
+    # snkpt_count_work replays single rays: its sums equal the launch record of the same rays traced at level 2
+    rng = np.random.default_rng(3)
+    rays = np.zeros(5000, snk.scenes.RAY_DTYPE)
+    rays["o"] = rng.uniform((-8, 0.5, -8), (8, 6, 8), (5000, 3)).astype(np.float32)
+    d = rng.normal(size=(5000, 3)); rays["d"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    rays["tmin"], rays["tmax"] = 0.001, 1000.0
+    pt.set_profiling(2)
+    hits = pt.trace_rays(rays)
+    rec = [r for r in pt.launch_timings() if r["is_trace"]]
+    pt.set_profiling(0)
+    work = pt.count_work(rays, hits)
+    assert len(rec) == 1 and int(rec[0]["live"]) == 5000
+    assert (int(rec[0]["nodes"]), int(rec[0]["tris"]), int(rec[0]["insts"])) == tuple(int(v) for v in work.sum(0, dtype=np.uint64))
+    assert (work[:, 0] >= 1).all() and (work[hits["t"] >= 0, 1] >= 1).all()
+    # ---- snkpt_set_rows after creation: without ReSTIR every pixel is independent, so a band equals those rows of the frame
+    flags = snk.api.RT_NO_RESTIR
+    ubo = sc.ubo(7)
+    pt.reset_history()
+    rt.RecordRenderCmdBuf(ubo, ubo, mode=snk.api.MODE_NORTHSTAR, flags=flags)
+    full = pt.read_aux("radiance").copy()
+    pt.set_rows(10, 30)
+    pt.reset_history()
+    rt.RecordRenderCmdBuf(ubo, ubo, mode=snk.api.MODE_NORTHSTAR, flags=flags)
+    band = pt.read_aux("radiance")
+    assert np.array_equal(band[10:30].view(np.uint32), full[10:30].view(np.uint32))
+    assert pt.read_output("f16").shape == (20, 64, 4)
+    with pytest.raises(snk.SnkError):
+        pt.set_rows(30, 10)
+    pt.close()
