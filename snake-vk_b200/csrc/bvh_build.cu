@@ -16,8 +16,22 @@ namespace snk {
 namespace {
 
 constexpr uint32_t EMPTY = 0xFFFFFFFFu;
-constexpr int SORT_THREADS = 256;
-constexpr int SORT_ITEMS = 16;                                  // keys per thread
+// tile shape of the radix passes (profiles/r03f_variants_sort_shape.txt): 256 threads x 16 keys held 106 registers (25 % occupancy,
+// ncu r03e: issue slots 7 % busy); 512 x 8 at 64 registers is 5 % faster on a 10 M-key sort, the other shapes are within +-3 %
+#ifndef SNK_SORT_THREADS
+#define SNK_SORT_THREADS 512
+#endif
+#ifndef SNK_SORT_ITEMS
+#define SNK_SORT_ITEMS 8
+#endif
+#ifndef SNK_SORT_PREFETCH_VALS
+#define SNK_SORT_PREFETCH_VALS 0
+#endif
+#ifndef SNK_SORT_MIN_CTAS
+#define SNK_SORT_MIN_CTAS 2
+#endif
+constexpr int SORT_THREADS = SNK_SORT_THREADS;
+constexpr int SORT_ITEMS = SNK_SORT_ITEMS;                      // keys per thread
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;            // 4096 keys per CTA
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 #ifndef SNK_LEAF_MAX_BLAS
@@ -233,7 +247,7 @@ __global__ void k_morton(const float4* __restrict__ prim_lo, const float4* __res
 __global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const unsigned long long* __restrict__ keys, uint32_t n, int shift,
                                                             uint32_t* __restrict__ block_hist, uint32_t num_blocks) {
   __shared__ uint32_t sh[256];
-  sh[threadIdx.x] = 0;
+  for (int d = threadIdx.x; d < 256; d += SORT_THREADS) sh[d] = 0;
   __syncthreads();
   const uint32_t base = blockIdx.x * SORT_TILE;
 #pragma unroll 4
@@ -242,7 +256,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_hist(const unsigned long 
     if (idx < n) atomicAdd(&sh[(uint32_t)(keys[idx] >> shift) & 255u], 1u);
   }
   __syncthreads();
-  block_hist[threadIdx.x * num_blocks + blockIdx.x] = sh[threadIdx.x];
+  for (int d = threadIdx.x; d < 256; d += SORT_THREADS) block_hist[d * num_blocks + blockIdx.x] = sh[d];
 }
 
 // block_hist is digit-major: row d holds the count of digit d in every tile. Offsets = (number of keys with a
@@ -293,7 +307,7 @@ __global__ void __launch_bounds__(256) k_scan_digits(uint32_t* __restrict__ digi
   digit_total[threadIdx.x] = wbase + inc - v;
 }
 
-__global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const unsigned long long* __restrict__ keys_in,
+__global__ void __launch_bounds__(SORT_THREADS, SNK_SORT_MIN_CTAS) k_sort_scatter(const unsigned long long* __restrict__ keys_in,
                                                                const uint32_t* __restrict__ vals_in, uint32_t n, int shift,
                                                                const uint32_t* __restrict__ block_offsets, uint32_t num_blocks,
                                                                const uint32_t* __restrict__ digit_base,
@@ -306,12 +320,18 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const unsigned lo
   const uint32_t warp_base = blockIdx.x * SORT_TILE + wid * (SORT_ITEMS * 32);
   const uint32_t lt = (1u << lane) - 1u;
   unsigned long long key[SORT_ITEMS];
+#if SNK_SORT_PREFETCH_VALS
+  uint32_t val[SORT_ITEMS];  // fetched with the keys: phase 3 is a serial chain per warp and must not wait for a load per item
+#endif
   // phase 1: per-warp digit histogram (each warp owns a contiguous run of the tile → stable)
 #pragma unroll
   for (int it = 0; it < SORT_ITEMS; ++it) {
     const uint32_t idx = warp_base + it * 32 + lane;
     const bool valid = idx < n;
     key[it] = valid ? keys_in[idx] : ~0ull;
+#if SNK_SORT_PREFETCH_VALS
+    val[it] = valid ? vals_in[idx] : 0u;
+#endif
     const uint32_t d = valid ? ((uint32_t)(key[it] >> shift) & 255u) : 256u;
     const uint32_t peers = __match_any_sync(0xffffffffu, d);
     if (valid && (peers & lt) == 0) wh[wid][d] += __popc(peers);
@@ -319,8 +339,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const unsigned lo
   }
   __syncthreads();
   // phase 2: turn per-warp counts into running output positions
-  {
-    const uint32_t d = threadIdx.x;  // 256 threads, one digit each
+  for (uint32_t d = threadIdx.x; d < 256u; d += SORT_THREADS) {  // one digit per thread
     uint32_t run = digit_base[d] + block_offsets[d * num_blocks + blockIdx.x];
 #pragma unroll
     for (int w = 0; w < SORT_WARPS; ++w) {
@@ -345,7 +364,11 @@ __global__ void __launch_bounds__(SORT_THREADS) k_sort_scatter(const unsigned lo
     __syncwarp();
     if (valid) {
       keys_out[pos] = key[it];
+#if SNK_SORT_PREFETCH_VALS
+      vals_out[pos] = val[it];
+#else
       vals_out[pos] = vals_in[idx];
+#endif
     }
   }
 }
