@@ -373,6 +373,119 @@ __global__ void __launch_bounds__(SORT_THREADS, SNK_SORT_MIN_CTAS) k_sort_scatte
   }
 }
 
+// The same pass with the tile sorted in shared memory first: ranks are computed as above, but each (key, value) goes to its
+// tile-local sorted position, and a second sweep writes the tile out in that order — keys of one digit leave the CTA as one
+// contiguous run (16 keys = 128 B on average) instead of 32 unrelated 8-byte stores per warp instruction. ncu (r03e) had the
+// direct version at 40 % L2 throughput with 7 % issue-slot use: bound by L2 write transactions, not by DRAM bytes.
+#ifndef SNK_SORT_STAGED
+#define SNK_SORT_STAGED 1
+#endif
+constexpr size_t SORT_STAGED_SMEM = (size_t)SORT_TILE * 12 + (size_t)SORT_WARPS * 256 * 4 + 256 * 4 * 2 + 64;
+__global__ void __launch_bounds__(SORT_THREADS, SNK_SORT_MIN_CTAS) k_sort_scatter_staged(const unsigned long long* __restrict__ keys_in,
+                                                                      const uint32_t* __restrict__ vals_in, uint32_t n, int shift,
+                                                                      const uint32_t* __restrict__ block_offsets, uint32_t num_blocks,
+                                                                      const uint32_t* __restrict__ digit_base,
+                                                                      unsigned long long* __restrict__ keys_out,
+                                                                      uint32_t* __restrict__ vals_out) {
+  extern __shared__ __align__(16) unsigned char sort_smem[];
+  unsigned long long* skey = reinterpret_cast<unsigned long long*>(sort_smem);
+  uint32_t* sval = reinterpret_cast<uint32_t*>(skey + SORT_TILE);
+  uint32_t (*wh)[256] = reinterpret_cast<uint32_t (*)[256]>(sval + SORT_TILE);
+  uint32_t* tile_start = reinterpret_cast<uint32_t*>(wh + SORT_WARPS);  // first tile-local position of digit d
+  uint32_t* goff = tile_start + 256;                                    // global position of tile-local position j: goff[d] + j
+  uint32_t* warp_sums = goff + 256;
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int d = lane; d < 256; d += 32) wh[wid][d] = 0;
+  __syncwarp();
+  const uint32_t tile_base = blockIdx.x * SORT_TILE;
+  const uint32_t warp_base = tile_base + wid * (SORT_ITEMS * 32);
+  const uint32_t lt = (1u << lane) - 1u;
+  unsigned long long key[SORT_ITEMS];
+  uint32_t val[SORT_ITEMS];
+#pragma unroll
+  for (int it = 0; it < SORT_ITEMS; ++it) {
+    const uint32_t idx = warp_base + it * 32 + lane;
+    const bool valid = idx < n;
+    key[it] = valid ? keys_in[idx] : ~0ull;
+    val[it] = valid ? vals_in[idx] : 0u;
+  }
+  // phase 1: per-warp digit histogram (each warp owns a contiguous run of the tile -> stable)
+#pragma unroll
+  for (int it = 0; it < SORT_ITEMS; ++it) {
+    const bool valid = warp_base + it * 32 + lane < n;
+    const uint32_t d = valid ? ((uint32_t)(key[it] >> shift) & 255u) : 256u;
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    if (valid && (peers & lt) == 0) wh[wid][d] += __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  // phase 2: per-warp counts -> tile-local start positions; tile totals -> exclusive scan over the digits
+  uint32_t total = 0, d = threadIdx.x;
+  if (d < 256u) {
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; ++w) {
+      const uint32_t c = wh[w][d];
+      wh[w][d] = total;
+      total += c;
+    }
+  }
+  uint32_t inc = total;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31 && wid < 8) warp_sums[wid] = inc;
+  __syncthreads();
+  if (d < 256u) {
+    uint32_t before = 0;
+    for (uint32_t w = 0; w < wid; ++w) before += warp_sums[w];
+    const uint32_t start = before + inc - total;
+    tile_start[d] = start;
+    goff[d] = digit_base[d] + block_offsets[d * num_blocks + blockIdx.x] - start;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; ++w) wh[w][d] += start;
+  }
+  __syncthreads();
+  // phase 3: rank + move to the tile-local sorted position
+#pragma unroll
+  for (int it = 0; it < SORT_ITEMS; ++it) {
+    const bool valid = warp_base + it * 32 + lane < n;
+    const uint32_t dg = valid ? ((uint32_t)(key[it] >> shift) & 255u) : 256u;
+    const uint32_t peers = __match_any_sync(0xffffffffu, dg);
+    const uint32_t rank = __popc(peers & lt);
+    uint32_t pos = 0;
+    if (valid) pos = wh[wid][dg] + rank;
+    __syncwarp();
+    if (valid && rank == 0) wh[wid][dg] += __popc(peers);
+    __syncwarp();
+    if (valid) { skey[pos] = key[it]; sval[pos] = val[it]; }
+  }
+  __syncthreads();
+  // phase 4: write the tile out in sorted order
+  const uint32_t tile_n = n - tile_base < (uint32_t)SORT_TILE ? n - tile_base : (uint32_t)SORT_TILE;
+  for (uint32_t j = threadIdx.x; j < tile_n; j += SORT_THREADS) {
+    const unsigned long long k = skey[j];
+    const uint32_t g = goff[(uint32_t)(k >> shift) & 255u] + j;
+    keys_out[g] = k;
+    vals_out[g] = sval[j];
+  }
+}
+
+static void launch_sort_scatter(const unsigned long long* keys_in, const uint32_t* vals_in, uint32_t n, int shift, const uint32_t* block_offsets,
+                                uint32_t nb, const uint32_t* digit_base, unsigned long long* keys_out, uint32_t* vals_out, cudaStream_t st) {
+#if SNK_SORT_STAGED
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(k_sort_scatter_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORT_STAGED_SMEM);
+    configured = true;
+  }
+  k_sort_scatter_staged<<<nb, SORT_THREADS, SORT_STAGED_SMEM, st>>>(keys_in, vals_in, n, shift, block_offsets, nb, digit_base, keys_out, vals_out);
+#else
+  k_sort_scatter<<<nb, SORT_THREADS, 0, st>>>(keys_in, vals_in, n, shift, block_offsets, nb, digit_base, keys_out, vals_out);
+#endif
+}
+
 // ---- Karras 2012 ------------------------------------------------------------------------
 __device__ __forceinline__ int delta(const unsigned long long* __restrict__ keys, int n, int i, int j) {
   if (j < 0 || j >= n) return -1;
@@ -1260,7 +1373,7 @@ int launch_sort_pairs(BuildScratch& s, uint32_t n, int bits, int& cur, cudaStrea
     k_sort_hist<<<nb, SORT_THREADS, 0, st>>>(s.keys[cur], n, shift, s.block_hist, nb);
     k_scan_rows<<<256, 256, 0, st>>>(s.block_hist, nb, s.digit_total);
     k_scan_digits<<<1, 256, 0, st>>>(s.digit_total);
-    k_sort_scatter<<<nb, SORT_THREADS, 0, st>>>(s.keys[cur], s.vals[cur], n, shift, s.block_hist, nb, s.digit_total, s.keys[cur ^ 1], s.vals[cur ^ 1]);
+    launch_sort_scatter(s.keys[cur], s.vals[cur], n, shift, s.block_hist, nb, s.digit_total, s.keys[cur ^ 1], s.vals[cur ^ 1], st);
     cur ^= 1;
     launches += 4;
   }
@@ -1302,7 +1415,7 @@ int launch_build(BuildScratch& s, uint32_t n, const BuildOutput& out, const floa
       k_sort_hist<<<nb, SORT_THREADS, 0, st>>>(s.keys[cur], n, shift, s.block_hist, nb);
       k_scan_rows<<<256, 256, 0, st>>>(s.block_hist, nb, s.digit_total);
       k_scan_digits<<<1, 256, 0, st>>>(s.digit_total);
-      k_sort_scatter<<<nb, SORT_THREADS, 0, st>>>(s.keys[cur], s.vals[cur], n, shift, s.block_hist, nb, s.digit_total, s.keys[cur ^ 1], s.vals[cur ^ 1]);
+      launch_sort_scatter(s.keys[cur], s.vals[cur], n, shift, s.block_hist, nb, s.digit_total, s.keys[cur ^ 1], s.vals[cur ^ 1], st);
       cur ^= 1;
       launches += 4;
     }
