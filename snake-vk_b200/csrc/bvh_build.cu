@@ -475,10 +475,12 @@ __global__ void __launch_bounds__(SORT_THREADS, SNK_SORT_MIN_CTAS) k_sort_scatte
 static void launch_sort_scatter(const unsigned long long* keys_in, const uint32_t* vals_in, uint32_t n, int shift, const uint32_t* block_offsets,
                                 uint32_t nb, const uint32_t* digit_base, unsigned long long* keys_out, uint32_t* vals_out, cudaStream_t st) {
 #if SNK_SORT_STAGED
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};  // the opt-in to > 48 KB of dynamic shared memory is per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
     cudaFuncSetAttribute(k_sort_scatter_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORT_STAGED_SMEM);
-    configured = true;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
   }
   k_sort_scatter_staged<<<nb, SORT_THREADS, SORT_STAGED_SMEM, st>>>(keys_in, vals_in, n, shift, block_offsets, nb, digit_base, keys_out, vals_out);
 #else
