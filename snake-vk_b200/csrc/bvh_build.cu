@@ -943,7 +943,10 @@ __device__ __forceinline__ void process_level(const CollapseArgs& a, uint32_t be
 // all threads process the level with converged warps, then the grid synchronises and moves to the next range.
 // Earlier versions let thread w spin until its parent published node w: lanes of a warp received their work at
 // different times and ran the (long, serial) node construction one after the other — 2.5-2.9 of 4.2 ms at 3 M triangles.
-__global__ void __launch_bounds__(128) k_collapse(CollapseArgs a) {
+#ifndef SNK_COLLAPSE_CTAS
+#define SNK_COLLAPSE_CTAS 10  // 8 / 10 / 12 / 16 CTAs per SM: 4.48 / 4.48 / 4.53 / 4.63 ms at 10 M triangles (profiles/r03i_variants_collapse_occupancy.txt)
+#endif
+__global__ void __launch_bounds__(128, SNK_COLLAPSE_CTAS) k_collapse(CollapseArgs a) {
   cg::grid_group grid = cg::this_grid();
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
   uint32_t begin = 0, end = 1;
