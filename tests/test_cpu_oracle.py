@@ -472,3 +472,47 @@ def test_textures_change_the_frame(snk, oracle):
     assert not np.array_equal(outs[0][1], outs[1][1])
     hit = fr.read("prim") != 0xFFFFFFFF
     assert (outs[0][0][hit][:, :3].astype(np.int32) <= outs[1][0][hit][:, :3].astype(np.int32) + 1).all(), "texture values are <= 1: albedo can only get darker"
+
+
+def test_constants_equal_the_reference_source_text(snk, oracle):
+    """tests/golden/reference_source_facts.json holds constants read straight out of the reference's shader / header text
+    (tools/make_golden.py, first regex match with its line number). The oracle's literals, the ABI's default settings, the
+    layouts, the camera and the particle parameters must carry exactly those values; and where /root/reference is mounted the
+    fixture itself is re-derived from the sources, so it cannot go stale silently."""
+    import re
+    here = os.path.dirname(os.path.abspath(__file__))
+    facts = json.load(open(os.path.join(GOLD, "reference_source_facts.json")))
+    assert len(facts) >= 25
+    header = open(os.path.join(here, "..", "include", "snkpt.h")).read()
+    checked = 0
+    for f in facts:
+        kind, _, arg = f["use"].partition(":")
+        v = f["value"]
+        if kind == "setting":
+            for s in (snk.api.default_settings(), oracle.default_settings()):
+                assert np.float32(s[arg]) == np.float32(float(v)), (f["name"], s[arg], v)
+        elif kind == "oracle":
+            fname, _, template = arg.partition(":")
+            text = open(os.path.join(here, "..", "oracle", fname)).read()
+            assert template.format(v) in text, f"{f['name']}: oracle/{fname} does not contain {template.format(v)!r} ({f['file']}:{f['line']})"
+        elif kind == "layout":
+            if arg == "max_pointlights":
+                assert re.search(r"#define SNKPT_MAX_POINTLIGHTS %d\b" % int(v), header)
+                assert snk.scenes.LIGHT_TOTAL_BYTES == 112 + int(v) * 48 + 1024 * 64
+            else:
+                assert re.search(r"max_transforms; /\* 0 → %d " % int(v), header)
+        elif kind == "camera":
+            assert np.float32(getattr(snk.scenes.Camera((0, 0, 0), (0, 0, 1)), arg)) == np.float32(float(v))
+        elif kind == "physics":
+            assert np.float32(snk.api.physics_params()[arg]) == np.float32(float(v))
+        else:
+            assert kind == "text"
+            continue
+        checked += 1
+    assert checked >= 22
+    ref = "/root/reference"
+    if os.path.isdir(ref):  # not on the GPU box; here the fixture is proven fresh
+        for f in facts:
+            text = open(os.path.join(ref, f["file"]), encoding="utf-8", errors="replace").read()
+            m = re.search(f["regex"], text)
+            assert m and m.group(1) == f["value"] and text.count("\n", 0, m.start()) + 1 == f["line"], f["name"]

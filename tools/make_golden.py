@@ -146,8 +146,57 @@ def frame_small():
     np.savez_compressed(os.path.join(GOLD, "frame_small.npz"), **out)
 
 
+# (name, reference file, regex with ONE capture group, how the value is used here)
+SOURCE_FACTS = [
+    ("LIGHT_RIS_ITERS", "Core/res/shaders/RayGen.rgen", r"#define\s+LIGHT_RIS_ITERS\s+(\d+)u", "setting:ris_iters"),
+    ("M_CAP", "Core/res/shaders/RayGen.rgen", r"#define\s+M_CAP\s+(\d+)", "setting:m_cap"),
+    ("spatial neighbour radius (px)", "Core/res/shaders/RayGen.rgen", r"render_size \* FindNeighbourPixelCoord\(pixel_coord, ([0-9.]+),", "setting:neighbour_radius"),
+    ("spatial normal threshold", "Core/res/shaders/RayGen.rgen", r"if \(dot\(neighbour_normal, normal\) < ([0-9.]+)\) continue;", "setting:normal_threshold"),
+    ("temporal normal threshold", "Core/res/shaders/RayGen.rgen", r"if \(dot\(neighbour_normal, normal\) > ([0-9.]+)\) \{", "setting:normal_threshold"),
+    ("num_temporal_resamples", "Core/headers/rendering/Raytracing.h", r"int32_t num_temporal_resamples = (\d+);", "setting:num_temporal"),
+    ("num_spatial_resamples", "Core/headers/rendering/Raytracing.h", r"int32_t num_spatial_resamples = (\d+);", "setting:num_spatial"),
+    ("PI", "Core/res/shaders/LightBuffers.glsl", r"#define PI ([0-9.]+)", "oracle:snk_raygen.h:PI_GLSL = {}f"),
+    ("point-light WRS time factor", "Core/res/shaders/RayGen.rgen", r"fract\(weight\+common_ubo\.time_elapsed\*(0\.0009783) \+ rnd_seed\)", "oracle:snk_raygen.h:time() * {}f"),
+    ("emissive WRS time factor", "Core/res/shaders/RayGen.rgen", r"fract\(weight\+common_ubo\.time_elapsed\*(0\.000789) \+ rnd_seed\)", "oracle:snk_raygen.h:time() * {}f"),
+    ("light pick time factor", "Core/res/shaders/RayGen.rgen", r"fract\(common_ubo\.time_elapsed \* (0\.001197) \+ world_pos\.x", "oracle:snk_raygen.h:time() * {}f"),
+    ("bary seed x", "Core/res/shaders/RayGen.rgen", r"random\(sin\(i\*(27934\.3221)\+gl_LaunchIDEXT\.x\*293\.28\)", "oracle:snk_raygen.h:(float)i * {}f"),
+    ("bary seed y", "Core/res/shaders/RayGen.rgen", r"random\(sin\(i\*(12391\.8583)\+gl_LaunchIDEXT\.y\*983\.3399\)", "oracle:snk_raygen.h:(float)i * {}f"),
+    ("spatial seed", "Core/res/shaders/RayGen.rgen", r"vec2\(seed, -seed\) \+ sin\(i\*(13477\.3793)\)", "oracle:snk_raygen.h:(float)i * {}f"),
+    ("emissive point bias", "Core/res/shaders/RayGen.rgen", r"length\(surface_pos - \(p \+ point_normal \* ([0-9.]+)\)\)", "oracle:snk_raygen.h:* {}f"),
+    ("biased_pos rule", "Core/res/shaders/RayGen.rgen", r"vec3 biased_pos = ro \+ normal \* \((0\.01 \+ max\(length\(common_ubo\.cam_pos\.xyz - ro\) \* 0\.001, 0\.01\))\);", "text"),
+    ("rgen dir-light shadow tmax", "Core/res/shaders/RayGen.rgen", r"ShadowTest\(biased_pos, ssbo_light_data\.dir_light\.dir\.xyz, (\d+)\);", "oracle:snk_raygen.h:{}.0f"),
+    ("rchit dir-light shadow tmax", "Core/res/shaders/RayClosestHit.rchit", r"ShadowTest\(biased_pos, ssbo_light_data\.dir_light\.dir\.xyz, (\d+)\);", "oracle:snk_raygen.h:{}.0f"),
+    ("pointlights capacity", "Core/res/shaders/LightBuffers.glsl", r"Pointlight pointlights\[(\d+)\];", "layout:max_pointlights"),
+    ("transform capacity", "Core/headers/scene/TransformBufferSystem.h", r"CreateBuffer\(sizeof\(glm::mat4\) \* (\d+),", "layout:max_transforms"),
+    ("frames in flight", "Core/headers/core/VkContext.h", r"MAX_FRAMES_IN_FLIGHT = (\d+);", "text"),
+    ("z_near", "Core/headers/components/CameraComponent.h", r"float z_near = ([0-9.]+)f;", "camera:z_near"),
+    ("z_far", "Core/headers/components/CameraComponent.h", r"float z_far = ([0-9.]+)f;", "camera:z_far"),
+    ("projection fov rule", "Core/headers/components/CameraComponent.h", r"glm::perspective\(glm::radians\((fov \* 0\.5f)\), aspect_ratio, z_near, z_far\)", "text"),
+    ("particle_restitution", "Core/headers/scene/ParticleSystem.h", r"float particle_restitution = ([0-9.]+)f;", "physics:particle_restitution"),
+    ("friction_coefficient", "Core/headers/scene/ParticleSystem.h", r"float friction_coefficient = ([0-9.]+);", "physics:friction_coefficient"),
+    ("repulsion_factor", "Core/headers/scene/ParticleSystem.h", r"float repulsion_factor = ([0-9.]+)f;", "physics:repulsion_factor"),
+]
+
+
+def reference_source_facts():
+    """constants of the path read straight from the reference's shader / header text (first match, with its line number):
+    tests/test_cpu_oracle.py checks that the oracle, the ABI defaults and the layouts carry exactly these values"""
+    import re
+    facts = []
+    for name, rel, rx, use in SOURCE_FACTS:
+        text = open(os.path.join(REF, rel), encoding="utf-8", errors="replace").read()
+        m = re.search(rx, text)
+        assert m, f"reference source fact not found: {name} in {rel}"
+        facts.append({"name": name, "file": rel, "line": text.count("\n", 0, m.start()) + 1, "regex": rx, "value": m.group(1), "use": use})
+    json.dump(facts, open(os.path.join(GOLD, "reference_source_facts.json"), "w"), indent=1)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "source_facts":
+        reference_source_facts()
+        raise SystemExit(0)
     O.build_oracle()
+    reference_source_facts()
     glm_vectors()
     shipped_meshes()
     shipped_scene()
