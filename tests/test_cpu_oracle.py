@@ -516,3 +516,79 @@ def test_constants_equal_the_reference_source_text(snk, oracle):
             text = open(os.path.join(ref, f["file"]), encoding="utf-8", errors="replace").read()
             m = re.search(f["regex"], text)
             assert m and m.group(1) == f["value"] and text.count("\n", 0, m.start()) + 1 == f["line"], f["name"]
+
+
+def _glsl_layout(blocks, name, std140=False):
+    """(offsets of the flattened leaf members, size, alignment) of a GLSL block by the std430 / std140 rules"""
+    base = {"float": (4, 4), "uint": (4, 4), "int": (4, 4), "bool": (4, 4), "vec2": (8, 8), "vec3": (16, 12), "vec4": (16, 16), "mat4": (16, 64)}
+    up = lambda x, a: (x + a - 1) // a * a
+    offs, off, align = [], 0, 1
+    for typ, mname, count in blocks[name]["members"]:
+        if typ in base:
+            a, sz, inner = base[typ][0], base[typ][1], [("", 0)]
+        else:
+            inner, sz, a = _glsl_layout(blocks, typ, std140)
+            inner = [("." + n, o) for n, o in inner]
+        stride = up(sz, a)
+        if std140 and (count > 1 or typ not in base):
+            a = up(a, 16); stride = up(stride, 16)
+        off = up(off, a)
+        for k in range(count):
+            for n, o in inner:
+                offs.append((mname + (f"[{k}]" if count > 1 else "") + n, off + k * stride + o))
+        off += stride * count
+        align = max(align, a)
+    if std140:
+        align = up(align, 16)
+    return offs, up(off, align), align
+
+
+def test_wire_formats_equal_the_reference_glsl_layouts(snk, tmp_path):
+    """tests/golden/reference_layouts.json = member lists of the GLSL blocks of the data contract, parsed from the reference's shader
+    text. Laid out by the std430 (storage buffers) / std140 (CommonUBO) rules, every member offset and every size must equal
+    offsetof / sizeof of the C struct of the same name in include/snkpt.h (compiled here with gcc) and the numpy wire formats."""
+    import re, subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    blocks = json.load(open(os.path.join(GOLD, "reference_layouts.json")))
+    cname = {"PixelReservoir": "SnkPixelReservoir", "Material": "SnkMaterial", "InstanceData": "SnkInstanceData", "DirectionalLight": "SnkDirectionalLight",
+             "Pointlight": "SnkPointlight", "Spotlight": "SnkSpotlight", "LightData": "SnkLightData", "CommonUBO": "SnkCommonUBO"}
+    rename = {"emissive_triangle.object_instance_idx": "object_instance_idx", "emissive_triangle.triangle_idx": "triangle_idx",
+              "emissive_triangle.bary_coords": "bary"}
+    want = {}
+    for g, c in cname.items():
+        offs, size, _ = _glsl_layout(blocks, g, std140=(g == "CommonUBO"))
+        if g == "LightData":  # two elements of each array are enough to pin base and stride
+            offs = [(n, o) for n, o in offs if not re.search(r"\[(?!0\]|1\]|1023\])\d+\]", n)]
+        want[c] = ([(rename.get(n, n), o) for n, o in offs], size)
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "snkpt.h"', 'int main(void) {']
+    for c, (offs, size) in want.items():
+        src.append(f'  printf("{c} %zu\\n", sizeof({c}));')
+        for n, _ in offs:
+            src.append(f'  printf("{c}.{n} %zu\\n", offsetof({c}, {n}));')
+    src += ['  return 0;', '}']
+    cfile = tmp_path / "layouts.c"
+    cfile.write_text("\n".join(src))
+    exe = tmp_path / "layouts"
+    subprocess.run(["gcc", "-I", os.path.join(here, "..", "include"), str(cfile), "-o", str(exe)], check=True)
+    got = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    n_checked = 0
+    for c, (offs, size) in want.items():
+        assert int(got[c]) == size, f"sizeof({c}) = {got[c]}, the GLSL block is {size} bytes"
+        for n, o in offs:
+            assert int(got[f"{c}.{n}"]) == o, f"offsetof({c}, {n}) = {got[c + '.' + n]}, GLSL layout says {o}"
+            n_checked += 1
+    assert n_checked > 60
+    assert want["SnkPixelReservoir"][1] == 48 and want["SnkMaterial"][1] == 64 and want["SnkInstanceData"][1] == 20 and want["SnkCommonUBO"][1] == 240
+    assert want["SnkLightData"][1] == snk.scenes.LIGHT_TOTAL_BYTES
+    # the numpy wire formats of the harness
+    S = snk.scenes
+    for dt, c in ((S.RESERVOIR_DTYPE, "SnkPixelReservoir"), (S.UBO_DTYPE, "SnkCommonUBO"), (S.MATERIAL_DTYPE, "SnkMaterial")):
+        assert dt.itemsize == want[c][1]
+        for n, o in want[c][0]:
+            if n in dt.fields:
+                assert dt.fields[n][1] == o, (c, n)
+    ref = "/root/reference"
+    if os.path.isdir(ref):  # fixture freshness: the block headers are still where the fixture says
+        for g, b in blocks.items():
+            lines = open(os.path.join(ref, b["file"]), encoding="utf-8", errors="replace").read().split("\n")
+            assert g in lines[b["line"] - 1], (g, lines[b["line"] - 1])

@@ -191,12 +191,53 @@ def reference_source_facts():
     json.dump(facts, open(os.path.join(GOLD, "reference_source_facts.json"), "w"), indent=1)
 
 
+GLSL_BLOCKS = [
+    ("TriangleData", "Core/res/shaders/RayGen.rgen", r"struct\s+TriangleData\s*\{"),
+    ("PixelReservoir", "Core/res/shaders/RayGen.rgen", r"struct\s+PixelReservoir\s*\{"),
+    ("Material", "Core/res/shaders/TexMatBuffers.glsl", r"struct\s+Material\s*\{"),
+    ("InstanceData", "Core/res/shaders/RaytracingInstances.glsl", r"struct\s+InstanceData\s*\{"),
+    ("DirectionalLight", "Core/res/shaders/LightBuffers.glsl", r"struct\s+DirectionalLight\s*\{"),
+    ("Pointlight", "Core/res/shaders/LightBuffers.glsl", r"struct\s+Pointlight\s*\{"),
+    ("Spotlight", "Core/res/shaders/LightBuffers.glsl", r"struct\s+Spotlight\s*\{"),
+    ("LightData", "Core/res/shaders/LightBuffers.glsl", r"readonly\s+buffer\s+LightData\s*\{"),
+    ("CommonUBO", "Core/res/shaders/CommonUBO.glsl", r"uniform\s+CommonUBO\s*\{"),
+]
+
+
+def reference_layouts():
+    """member lists (type, name, array length) of the GLSL blocks that form the data contract of the path, parsed from the
+    reference's shader text; tests/test_cpu_oracle.py lays them out by the std430 / std140 rules and compares every offset with
+    the wire formats used here"""
+    import re
+    out = {}
+    for name, rel, rx in GLSL_BLOCKS:
+        text = open(os.path.join(REF, rel), encoding="utf-8", errors="replace").read()
+        m = re.search(rx, text)
+        assert m, f"GLSL block not found: {name}"
+        body = text[m.end():text.index("}", m.end())]
+        body = re.sub(r"//[^\n]*", "", body)
+        members = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            typ, rest = decl.split(None, 1)
+            for var in rest.split(","):
+                var = var.strip()
+                am = re.match(r"(\w+)\[(\d+)\]$", var)
+                members.append([typ, am.group(1), int(am.group(2))] if am else [typ, var, 1])
+        out[name] = {"file": rel, "line": text.count("\n", 0, m.start()) + 1, "members": members}
+    json.dump(out, open(os.path.join(GOLD, "reference_layouts.json"), "w"), indent=1)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "source_facts":
         reference_source_facts()
+        reference_layouts()
         raise SystemExit(0)
     O.build_oracle()
     reference_source_facts()
+    reference_layouts()
     glm_vectors()
     shipped_meshes()
     shipped_scene()
