@@ -175,6 +175,15 @@ SOURCE_FACTS = [
     ("particle_restitution", "Core/headers/scene/ParticleSystem.h", r"float particle_restitution = ([0-9.]+)f;", "physics:particle_restitution"),
     ("friction_coefficient", "Core/headers/scene/ParticleSystem.h", r"float friction_coefficient = ([0-9.]+);", "physics:friction_coefficient"),
     ("repulsion_factor", "Core/headers/scene/ParticleSystem.h", r"float repulsion_factor = ([0-9.]+)f;", "physics:repulsion_factor"),
+    ("TAA epsilon", "Core/res/shaders/TAA_Resolve.comp", r"#define FLT_EPS ([0-9.]+)f", "oracle:snk_taa.h:eps = {}f"),
+    ("TAA variance gamma", "Core/res/shaders/TAA_Resolve.comp", r"const float gamma = ([0-9.]+);", "oracle:snk_taa.h:gamma = {}f"),
+    ("TAA sample count", "Core/res/shaders/TAA_Resolve.comp", r"one_divided_by_sample_count = (1\.0 / 9\.0);", "text"),
+    ("TAA history weight", "Core/res/shaders/TAA_Resolve.comp", r"mix\(current_col, history_col, ([0-9.]+)\);", "oracle:snk_taa.h:, {}f);"),
+    ("TAA disocclusion ramp", "Core/res/shaders/TAA_Resolve.comp", r"clamp\(\(velocity_length - ([0-9.]+)\) \* 10\.0, 0\.0, 1\.0\)", "oracle:snk_taa.h:(velocity_length - {}f) * 10.0f"),
+    ("TAA initial extrema", "Core/res/shaders/TAA_Resolve.comp", r"vec3 min_col = vec3\(([0-9.]+)\);", "oracle:snk_taa.h:min_col = v3({}f)"),
+    ("particle DT", "Core/res/shaders/Particle.glsl", r"#define DT \((1\.0 / 120\.0)\)", "oracle:snk_particles.h:PTCL_DT = (float)({})"),
+    ("particle wall restitution", "Core/res/shaders/ParticleUpdate.rgen", r"const float restitution = ([0-9.]+);", "oracle:snk_particles.h:const float restitution = {}f;"),
+    ("particle mass", "Core/res/shaders/ParticleUpdate.rgen", r"const float mass = ([0-9.]+);", "oracle:snk_particles.h:const float mass = {}f;"),
 ]
 
 
