@@ -6,8 +6,10 @@
 // snake-vk_b200/ may link, import or execute this library.
 // PARITY UNPINNED: the reference (orangefrog45/Snake-VK) has no tests, golden
 // vectors or runnable headless path for this pass; the only
-// external anchor is glm (vendored under /root/reference/Core/extern/glm), used by
-// oracle/_ref to check the matrix helpers.
+// external anchors are glm (vendored under /root/reference/Core/extern/glm), used by
+// oracle/_ref to check the matrix helpers, and the reference's shader TEXT: constants,
+// block layouts and the pure shading functions executed by tools/glsl_exec.py
+// (tests/golden/reference_*.json, reference_shader_vectors.npz).
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -231,6 +233,11 @@ ORACLE_API void snkor_particles_grid(const Particle* p, uint32_t n, CellKeyEntry
   memcpy(start, s.data(), 4 * (size_t)n);
 }
 // TAA_Resolve.comp on raw RGBA16F / RG16F planes (snk_taa.h)
+ORACLE_API void snkor_taa_clip_aabb(const float* aabb_min, const float* aabb_max, const float* p4, const float* q4, float* out4) {
+  const vec4 r = taa_clip_aabb(v3(aabb_min[0], aabb_min[1], aabb_min[2]), v3(aabb_max[0], aabb_max[1], aabb_max[2]),
+                               vec4{p4[0], p4[1], p4[2], p4[3]}, vec4{q4[0], q4[1], q4[2], q4[3]});
+  out4[0] = r.x; out4[1] = r.y; out4[2] = r.z; out4[3] = r.w;
+}
 ORACLE_API void snkor_taa_resolve(uint32_t w, uint32_t h, const uint16_t* cur, const uint16_t* velocity, const uint16_t* history,
                                   const uint16_t* prev_vel, uint16_t* out) {
   taa_resolve(TaaImages{w, h, cur, velocity, history, prev_vel, out});

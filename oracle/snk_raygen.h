@@ -10,7 +10,9 @@
 // see snk_math.h for the numerics contract). Quirks of the reference
 //  are reproduced; the four places where the reference
 // would read out of bounds are guarded and marked DEVIATION.
-// PARITY UNPINNED: the reference ships no tests or golden vectors for this path.
+// PARITY: the reference ships no tests or golden vectors and cannot run here, so whole frames are UNPINNED. Pinned against
+// the reference's own text: the BRDF / light functions and the integer RNG (executed from the GLSL by tools/glsl_exec.py ->
+// tests/golden/reference_shader_vectors.npz), 36 constants and the block layouts (tests/golden/reference_*.json).
 #pragma once
 #include <atomic>
 

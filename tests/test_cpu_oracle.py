@@ -592,3 +592,52 @@ def test_wire_formats_equal_the_reference_glsl_layouts(snk, tmp_path):
         for g, b in blocks.items():
             lines = open(os.path.join(ref, b["file"]), encoding="utf-8", errors="replace").read().split("\n")
             assert g in lines[b["line"] - 1], (g, lines[b["line"] - 1])
+
+
+def test_oracle_equals_the_executed_reference_shader_text(oracle):
+    """tests/golden/reference_shader_vectors.npz: the reference's OWN FresnelSchlick / DistributionGGX / GeometrySmith /
+    CookTorranceBRDF / CalcPointlight / CalcDirectionalLight (LightBuffers.glsl:65-157), executed from the shader text in float32 by
+    tools/glsl_exec.py on 256 random configurations. The oracle's restatement must reproduce every value: same operations in the
+    same order, so the tolerance only covers pow() and the normalisation (1 / sqrt versus division)."""
+    L = oracle.lib()
+    g = np.load(os.path.join(GOLD, "reference_shader_vectors.npz"))
+    n_cases = g["n"].shape[0]
+    worst = 0.0
+    exact = 0
+    for i in range(n_cases):
+        a = [np.ascontiguousarray(g[k][i], np.float32) for k in ("n", "v", "l", "f0")]
+        out = np.zeros(8, np.float32)
+        L.snkor_brdf_eval(fp(a[0]), fp(a[1]), fp(a[2]), fp(a[3]), C.c_float(g["roughness"][i]), C.c_float(g["metallic"][i]), fp(out))
+        want = np.concatenate([g["ref_fresnel"][i], [g["ref_ggx"][i]], [g["ref_smith"][i]], g["ref_cook_torrance"][i]])
+        assert np.allclose(out, want, rtol=3e-6, atol=1e-9), (i, out, want)
+        pl = np.ascontiguousarray(g["pointlight"][i], np.float32)
+        alb, wp = np.ascontiguousarray(g["albedo"][i], np.float32), np.ascontiguousarray(g["world_pos"][i], np.float32)
+        o3 = np.zeros(3, np.float32)
+        L.snkor_calc_pointlight(fp(pl), fp(a[1]), fp(a[3]), fp(wp), fp(a[0]), C.c_float(g["roughness"][i]), C.c_float(g["metallic"][i]), fp(alb), fp(o3))
+        assert np.allclose(o3, g["ref_calc_pointlight"][i], rtol=5e-6, atol=1e-9), (i, o3, g["ref_calc_pointlight"][i])
+        ld = np.zeros(112, np.uint8)
+        ld[:32] = np.ascontiguousarray(g["dirlight"][i], np.float32).view(np.uint8)
+        o3d = np.zeros(3, np.float32)
+        L.snkor_calc_dirlight(fp(ld), fp(a[1]), fp(a[3]), fp(a[0]), C.c_float(g["roughness"][i]), C.c_float(g["metallic"][i]), fp(alb), fp(o3d))
+        assert np.allclose(o3d, g["ref_calc_dirlight"][i], rtol=5e-6, atol=1e-9), (i, o3d, g["ref_calc_dirlight"][i])
+        got = np.concatenate([out, o3, o3d]); ref = np.concatenate([want, g["ref_calc_pointlight"][i], g["ref_calc_dirlight"][i]])
+        exact += int((got.view(np.uint32) == ref.astype(np.float32).view(np.uint32)).sum())
+        nz = ref != 0
+        worst = max(worst, float(np.max(np.abs(got[nz] - ref[nz]) / np.abs(ref[nz]))) if nz.any() else 0.0)
+    assert g["ref_cook_torrance"].max() > 0.05 and (g["ref_calc_pointlight"] > 0).mean() > 0.5  # the vectors exercise lit configurations
+    assert exact > 0.9 * n_cases * 14, f"only {exact} of {n_cases * 14} values are bit-identical (worst relative difference {worst:.2e})"
+    # Util.glsl:23-57 — integer arithmetic: bit for bit
+    for x, want in zip(g["hash_in"], g["ref_hash"]):
+        assert L.snkor_hash(int(x)) == int(want)
+    got = np.array([L.snkor_random(float(x)) for x in g["random_in"]], np.float32)
+    assert np.array_equal(got.view(np.uint32), g["ref_random"].view(np.uint32))
+    assert g["ref_random"].min() >= 0.0 and g["ref_random"].max() < 1.0 and len(set(g["ref_random"].tolist())) > 200
+    # TAA_Resolve.comp:12-35 — clip_aabb: float32 + - * / in the shader's order: bit for bit
+    clipped = 0
+    for i in range(g["clip_p"].shape[0]):
+        a = [np.ascontiguousarray(g[k][i], np.float32) for k in ("clip_min", "clip_max", "clip_p", "clip_q")]
+        o4 = np.zeros(4, np.float32)
+        L.snkor_taa_clip_aabb(fp(a[0]), fp(a[1]), fp(a[2]), fp(a[3]), fp(o4))
+        assert np.array_equal(o4.view(np.uint32), g["ref_clip_aabb"][i].view(np.uint32)), (i, o4, g["ref_clip_aabb"][i])
+        clipped += int(not np.array_equal(o4, a[3]))
+    assert clipped > 100  # most history colours lie outside the box and are pulled in

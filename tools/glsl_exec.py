@@ -1,0 +1,135 @@
+"""Runs straight-line GLSL functions of the reference's shader text on the CPU, in float32, to produce golden vectors.
+
+The reference cannot execute here (no Vulkan device, no GLSL compiler), but its pure shading functions are plain expression
+code. `load_functions(path, names)` reads the shader file where it lies under /root/reference, turns each named function into a
+Python function by a mechanical rewrite (declarations lose their type, swizzles become slices, the GLSL built-ins map to float32
+numpy helpers with the same operation order) and returns them. Nothing of the shader text is stored in this repository: the
+generator (tools/make_golden.py) commits only the numeric input / output vectors.
+
+Supported subset: functions whose body is a sequence of declarations, assignments, compound assignments, single-statement `if`s and
+one return; scalar / vec3 / vec4 float arithmetic and 32-bit unsigned arithmetic; struct parameters and the `ssbo_light_data` block as attribute access; the built-ins listed in BUILTINS.
+"""
+import re
+import types
+
+import numpy as np
+
+F = np.float32
+
+
+def _vec(n):
+    def ctor(*a):
+        parts = []
+        for x in a:
+            parts.extend(np.asarray(x, F).reshape(-1).tolist())
+        if len(parts) == 1:
+            parts = parts * n
+        assert len(parts) == n, (n, a)
+        return np.array(parts, F)
+    return ctor
+
+
+def _dot(a, b):
+    a, b = np.asarray(a, F), np.asarray(b, F)
+    s = F(a[0] * b[0])
+    for k in range(1, a.shape[0]):
+        s = F(s + F(a[k] * b[k]))
+    return s
+
+
+def _length(a):
+    return F(np.sqrt(_dot(a, a)))
+
+
+BUILTINS = {
+    "vec2": _vec(2), "vec3": _vec(3), "vec4": _vec(4),
+    "dot": _dot, "length": _length,
+    # normalize() is implementation-defined in GLSL; GPUs evaluate x * inversesqrt(dot(x, x)), which is also the oracle's contract
+    "normalize": lambda a: (np.asarray(a, F) * F(F(1.0) / F(np.sqrt(_dot(a, a))))).astype(F),
+    "max": lambda a, b: np.maximum(np.asarray(a, F), np.asarray(b, F)).astype(F)[()],
+    "min": lambda a, b: np.minimum(np.asarray(a, F), np.asarray(b, F)).astype(F)[()],
+    "clamp": lambda x, lo, hi: np.minimum(np.maximum(np.asarray(x, F), F(lo)), F(hi)).astype(F)[()],
+    "pow": lambda a, b: np.power(np.asarray(a, F), F(b)).astype(F)[()],
+    "mix": lambda a, b, t: (np.asarray(a, F) * (F(1.0) - F(t)) + np.asarray(b, F) * F(t)).astype(F),
+    "sqrt": lambda a: np.sqrt(np.asarray(a, F)).astype(F)[()],
+    "abs": lambda a: np.abs(np.asarray(a, F)).astype(F)[()],
+}
+_TYPES = r"(?:float|int|uint|bool|vec[234]|ivec[234]|uvec[234]|mat[34])"
+_SWIZZLE = {"xyz": "[:3]", "rgb": "[:3]", "xy": "[:2]", "x": "[0]", "y": "[1]", "z": "[2]", "w": "[3]", "r": "[0]", "g": "[1]", "b": "[2]"}
+
+
+class U32(int):
+    """GLSL uint: 32-bit wrap-around on every operation the hash functions use"""
+    def _w(self, v): return U32(int(v) & 0xFFFFFFFF)
+    def __add__(self, o): return self._w(int(self) + int(o))
+    def __xor__(self, o): return self._w(int(self) ^ int(o))
+    def __and__(self, o): return self._w(int(self) & int(o))
+    def __or__(self, o): return self._w(int(self) | int(o))
+    def __lshift__(self, o): return self._w(int(self) << int(o))
+    def __rshift__(self, o): return self._w(int(self) >> int(o))
+    __iadd__, __ixor__, __iand__, __ior__ = __add__, __xor__, __and__, __or__
+
+
+BUILTINS.update({
+    "floatBitsToUint": lambda f: U32(int(np.asarray(f, F).view(np.uint32))),
+    "uintBitsToFloat": lambda u: np.asarray(int(u) & 0xFFFFFFFF, np.uint32).view(F)[()],
+    "fract": lambda a: (np.asarray(a, F) - np.floor(np.asarray(a, F))).astype(F)[()],
+})
+
+
+def _expr(e):
+    # unsigned literals (10u, 0x007FFFFFu) become wrap-around integers
+    e = re.sub(r"\b(0x[0-9A-Fa-f]+|\d+)u\b", r"U32(\1)", e)
+    e = re.sub(r"\b(\d+\.\d*|\.\d+)f\b", r"\1", e)  # 0.5f
+    # swizzles after an identifier, `)` or `]` (never inside a float literal)
+    return re.sub(r"(?<=[A-Za-z_0-9\)\]])\.(xyz|rgb|xy|x|y|z|w|r|g|b)\b(?!\s*\()", lambda m: _SWIZZLE[m.group(1)], e)
+
+
+def _translate(name, params, body):
+    args = []
+    for p in params.split(","):
+        p = p.strip()
+        if p:
+            args.append(p.split()[-1])
+    lines = [f"def {name}({', '.join(args)}):"]
+    body = re.sub(r"//[^\n]*", "", body)
+    for st in body.split(";"):
+        st = " ".join(st.split())
+        if not st:
+            continue
+        assert not re.match(r"(for|while|switch|else)\b", st), f"{name}: control flow is outside the supported subset: {st}"
+        prefix = ""
+        if st.startswith("if"):  # single-statement form only: if (cond) statement;
+            i = st.index("(")
+            depth, j = 1, i + 1
+            while depth:
+                depth += {"(": 1, ")": -1}.get(st[j], 0)
+                j += 1
+            prefix, st = f"if {_expr(st[i + 1:j - 1])}: ", st[j:].strip()
+            assert st and not st.startswith("{"), f"{name}: only single-statement if is supported"
+        st = re.sub(rf"^(?:const\s+)?{_TYPES}\s+(?=\w+\s*=)", "", st)
+        lines.append("    " + prefix + _expr(st))
+    return "\n".join(lines)
+
+
+def load_functions(path, names, defines=None):
+    """-> dict name -> python function, plus the `defines` found in the file (object-like macros with a numeric value)"""
+    text = open(path, encoding="utf-8", errors="replace").read()
+    env = dict(BUILTINS)
+    env["U32"] = U32
+    for m in re.finditer(r"^#define\s+(\w+)\s+([0-9.]+)f?\s*$", text, re.M):
+        env[m.group(1)] = F(float(m.group(2)))
+    env.update(defines or {})
+    for name in names:
+        m = re.search(rf"^\s*{_TYPES}\s+{name}\s*\(([^)]*)\)\s*\{{", text, re.M)
+        assert m, f"{name} not found in {path}"
+        depth, i = 1, m.end()
+        while depth:
+            depth += {"{": 1, "}": -1}.get(text[i], 0)
+            i += 1
+        exec(_translate(name, m.group(1), text[m.end():i - 1]), env)  # noqa: S102 - the input is the reference shader, read-only
+    return env
+
+
+def namespace(**kw):
+    return types.SimpleNamespace(**kw)

@@ -239,14 +239,78 @@ def reference_layouts():
     json.dump(out, open(os.path.join(GOLD, "reference_layouts.json"), "w"), indent=1)
 
 
+def reference_shader_vectors():
+    """the reference's own BRDF / light functions (Core/res/shaders/LightBuffers.glsl:65-157), executed from the shader text by
+    tools/glsl_exec.py in float32 on 256 random surface / light configurations -> tests/golden/reference_shader_vectors.npz"""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import glsl_exec as G
+    names = ["FresnelSchlick", "DistributionGGX", "GeometrySchlickGGX", "GeometrySmith", "CookTorranceBRDF", "CalcDirectionalLight", "CalcPointlight"]
+    env = G.load_functions(os.path.join(REF, "Core/res/shaders/LightBuffers.glsl"), names)
+    rng = np.random.default_rng(20261018)
+    n_cases = 256
+    f32 = np.float32
+
+    def unit(v):
+        return (v / np.linalg.norm(v, axis=-1, keepdims=True)).astype(f32)
+
+    n = unit(rng.normal(size=(n_cases, 3)))
+    # view and light directions in the upper hemisphere of n (a few grazing ones included)
+    v = unit(n * rng.uniform(0.02, 1.0, (n_cases, 1)) + 0.8 * rng.normal(size=(n_cases, 3)))
+    l = unit(n * rng.uniform(0.02, 1.0, (n_cases, 1)) + 0.8 * rng.normal(size=(n_cases, 3)))
+    rough = rng.uniform(0.05, 1.0, n_cases).astype(f32)
+    metal = rng.uniform(0.0, 1.0, n_cases).astype(f32)
+    albedo = rng.uniform(0.0, 1.0, (n_cases, 3)).astype(f32)
+    f0 = (f32(0.04) * (f32(1.0) - metal[:, None]) + albedo * metal[:, None]).astype(f32)
+    world_pos = rng.uniform(-5, 5, (n_cases, 3)).astype(f32)
+    pl = np.zeros((n_cases, 12), f32)  # colour4, pos4, exp, linear, constant, pad
+    pl[:, 0:3] = rng.uniform(0, 20, (n_cases, 3)); pl[:, 3] = 1
+    pl[:, 4:7] = world_pos + l * rng.uniform(0.3, 8.0, (n_cases, 1)).astype(f32); pl[:, 7] = 1
+    pl[:, 8:11] = rng.uniform(0.01, 1.0, (n_cases, 3))
+    dl = np.zeros((n_cases, 8), f32)  # colour4, dir4 of the directional light
+    dl[:, 0:3] = rng.uniform(0, 5, (n_cases, 3)); dl[:, 3] = 1
+    dl[:, 4:7] = l; dl[:, 7] = 0
+    out = dict(n=n, v=v, l=l, roughness=rough, metallic=metal, albedo=albedo, f0=f0, world_pos=world_pos, pointlight=pl, dirlight=dl)
+    res = {k: [] for k in ("fresnel", "ggx", "smith", "cook_torrance", "calc_pointlight", "calc_dirlight")}
+    for i in range(n_cases):
+        h = env["normalize"](v[i] + l[i])
+        res["fresnel"].append(env["FresnelSchlick"](env["max"](env["dot"](h, v[i]), 0.0), f0[i]))
+        res["ggx"].append(env["DistributionGGX"](h, n[i], rough[i]))
+        res["smith"].append(env["GeometrySmith"](v[i], l[i], n[i], rough[i]))
+        res["cook_torrance"].append(env["CookTorranceBRDF"](l[i], np.zeros(3, f32), v[i], f0[i], n[i], rough[i], metal[i]))
+        light = G.namespace(colour=pl[i, 0:4], pos=pl[i, 4:8], atten_exp=pl[i, 8], atten_linear=pl[i, 9], atten_constant=pl[i, 10])
+        res["calc_pointlight"].append(env["CalcPointlight"](light, v[i], f0[i], world_pos[i], n[i], rough[i], metal[i], albedo[i]))
+        env["ssbo_light_data"] = G.namespace(dir_light=G.namespace(colour=dl[i, 0:4], dir=dl[i, 4:8]))
+        res["calc_dirlight"].append(env["CalcDirectionalLight"](v[i], f0[i], n[i], rough[i], metal[i], albedo[i]))
+    for k, vals in res.items():
+        out["ref_" + k] = np.asarray(vals, f32)
+    # Util.glsl:23-57: integer hash, float construction, random(float) — bit-exact by nature
+    util = G.load_functions(os.path.join(REF, "Core/res/shaders/Util.glsl"), ["hash", "floatConstruct", "random"])
+    hx = np.concatenate([np.array([0, 1, 2, 0x7FFFFFFF, 0x80000000, 0xFFFFFFFF], np.uint32), rng.integers(0, 2 ** 32, 250, dtype=np.uint64).astype(np.uint32)])
+    out["hash_in"] = hx
+    out["ref_hash"] = np.array([int(util["hash"](G.U32(int(x)))) for x in hx], np.uint32)
+    rx = np.concatenate([np.array([0.0, -0.0, 1.0, 0.5, 1e-30, 123456.789], f32), rng.normal(scale=100.0, size=250).astype(f32)])
+    out["random_in"] = rx
+    out["ref_random"] = np.array([util["random"](x) for x in rx], f32)
+    # TAA_Resolve.comp:12-35: clip_aabb (history colour clipped towards the neighbourhood box)
+    taa = G.load_functions(os.path.join(REF, "Core/res/shaders/TAA_Resolve.comp"), ["clip_aabb"])
+    lo = rng.uniform(0, 1, (n_cases, 3)).astype(f32); hi = (lo + rng.uniform(0, 1, (n_cases, 3))).astype(f32)
+    p4 = np.concatenate([(lo + (hi - lo) * rng.uniform(0, 1, (n_cases, 3))).astype(f32), np.ones((n_cases, 1), f32)], 1)
+    q4 = np.concatenate([rng.uniform(-1, 3, (n_cases, 3)).astype(f32), np.ones((n_cases, 1), f32)], 1)
+    out.update(clip_min=lo, clip_max=hi, clip_p=p4, clip_q=q4)
+    out["ref_clip_aabb"] = np.asarray([taa["clip_aabb"](lo[i], hi[i], p4[i], q4[i]) for i in range(n_cases)], f32)
+    np.savez_compressed(os.path.join(GOLD, "reference_shader_vectors.npz"), **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "source_facts":
         reference_source_facts()
         reference_layouts()
+        reference_shader_vectors()
         raise SystemExit(0)
     O.build_oracle()
     reference_source_facts()
     reference_layouts()
+    reference_shader_vectors()
     glm_vectors()
     shipped_meshes()
     shipped_scene()
