@@ -13,6 +13,13 @@
 
 namespace snkor {
 
+// GBuffer.frag:41-43 CalcVelocity: UV-space delta from the current to the previous clip position (x 0.5: NDC -> UV)
+inline void calc_velocity(const vec4& cur_clip, const vec4& old_clip, float& mx, float& my) {
+  mx = (old_clip.x / old_clip.w - cur_clip.x / cur_clip.w) * 0.5f;
+  my = (old_clip.y / old_clip.w - cur_clip.y / cur_clip.w) * 0.5f;
+}
+
+
 // ---- storage formats -------------------------------------------------------------
 inline uint16_t f32_to_f16(float f) {  // round to nearest even, IEEE binary16
   uint32_t x = f2u(f);
@@ -143,7 +150,8 @@ inline void fill_gbuffer(const Scene& sc, const CommonUBO& cur, const CommonUBO&
       const vec3 pworld = mul_point(sc.prev_transforms[in.transform_idx], p);
       const vec4 pclip = mul_vec4(prev.proj_view, vec4{pworld.x, pworld.y, pworld.z, 1.0f});
       g.depth[px] = clip.z / clip.w;
-      const float mx = (pclip.x / pclip.w - clip.x / clip.w) * 0.5f, my = (pclip.y / pclip.w - clip.y / clip.w) * 0.5f;
+      float mx, my;
+      calc_velocity(clip, pclip, mx, my);
       g.motion[2 * px] = f32_to_f16(mx); g.motion[2 * px + 1] = f32_to_f16(my);
       const Material& m = sc.materials[in.material_idx];
       const vec3 alb = sc.albedo_at(m, ia, ib, ic, b0, b1, b2);  // GBuffer.frag:56-58

@@ -233,6 +233,15 @@ ORACLE_API void snkor_particles_grid(const Particle* p, uint32_t n, CellKeyEntry
   memcpy(start, s.data(), 4 * (size_t)n);
 }
 // TAA_Resolve.comp on raw RGBA16F / RG16F planes (snk_taa.h)
+ORACLE_API void snkor_calc_velocity(const float* cur4, const float* old4, float* out2) {
+  calc_velocity(vec4{cur4[0], cur4[1], cur4[2], cur4[3]}, vec4{old4[0], old4[1], old4[2], old4[3]}, out2[0], out2[1]);
+}
+ORACLE_API uint32_t snkor_ptcl_cell_key(int cx, int cy, int cz, uint32_t num_particles) { return ptcl_cell_key(cx, cy, cz, num_particles); }
+ORACLE_API void snkor_ptcl_cell_pos(const float* pos3, int* out3) {
+  Particle p{};
+  p.position_radius[0] = pos3[0]; p.position_radius[1] = pos3[1]; p.position_radius[2] = pos3[2];
+  ptcl_cell_pos(p, out3[0], out3[1], out3[2]);
+}
 ORACLE_API void snkor_taa_clip_aabb(const float* aabb_min, const float* aabb_max, const float* p4, const float* q4, float* out4) {
   const vec4 r = taa_clip_aabb(v3(aabb_min[0], aabb_min[1], aabb_min[2]), v3(aabb_max[0], aabb_max[1], aabb_max[2]),
                                vec4{p4[0], p4[1], p4[2], p4[3]}, vec4{q4[0], q4[1], q4[2], q4[3]});

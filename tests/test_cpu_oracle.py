@@ -641,3 +641,17 @@ def test_oracle_equals_the_executed_reference_shader_text(oracle):
         assert np.array_equal(o4.view(np.uint32), g["ref_clip_aabb"][i].view(np.uint32)), (i, o4, g["ref_clip_aabb"][i])
         clipped += int(not np.array_equal(o4, a[3]))
     assert clipped > 100  # most history colours lie outside the box and are pulled in
+    # Particle.glsl:14-16, :30-32 — cell position (truncation) and key (int32 wrap-around, unsigned modulo): exact
+    L.snkor_ptcl_cell_key.restype = C.c_uint32
+    for i in range(g["ptcl_pos"].shape[0]):
+        cell = np.zeros(3, np.int32)
+        L.snkor_ptcl_cell_pos(fp(np.ascontiguousarray(g["ptcl_pos"][i], np.float32)), fp(cell))
+        assert np.array_equal(cell, g["ref_cell_pos"][i]), (i, cell, g["ref_cell_pos"][i])
+        key = L.snkor_ptcl_cell_key(int(cell[0]), int(cell[1]), int(cell[2]), C.c_uint32(int(g["cell_count"][i])))
+        assert key == int(g["ref_cell_key"][i]), (i, key, g["ref_cell_key"][i])
+    assert (g["ref_cell_pos"] < 0).any() and len(set(g["ref_cell_key"].tolist())) > 100
+    # GBuffer.frag:41-43 — CalcVelocity: bit for bit
+    for i in range(g["clip_cur"].shape[0]):
+        o2 = np.zeros(2, np.float32)
+        L.snkor_calc_velocity(fp(np.ascontiguousarray(g["clip_cur"][i], np.float32)), fp(np.ascontiguousarray(g["clip_old"][i], np.float32)), fp(o2))
+        assert np.array_equal(o2.view(np.uint32), g["ref_velocity"][i].view(np.uint32)), (i, o2, g["ref_velocity"][i])

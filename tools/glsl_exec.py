@@ -70,7 +70,32 @@ class U32(int):
     __iadd__, __ixor__, __iand__, __ior__ = __add__, __xor__, __and__, __or__
 
 
+class I32(int):
+    """GLSL int: 32-bit two's-complement wrap-around; mixed with a uint it converts to uint (GLSL 4.60 section 4.1.10)"""
+    @staticmethod
+    def _w(v):
+        v = int(v) & 0xFFFFFFFF
+        return I32(v - (1 << 32) if v & 0x80000000 else v)
+    def __mul__(self, o): return U32(int(self) & 0xFFFFFFFF) * o if isinstance(o, U32) else I32._w(int(self) * int(o))
+    def __xor__(self, o): return U32(int(self) & 0xFFFFFFFF) ^ o if isinstance(o, U32) else I32._w(int(self) ^ int(o))
+    def __mod__(self, o):
+        assert isinstance(o, U32), "only int % uint is needed"
+        return U32((int(self) & 0xFFFFFFFF) % int(o))
+
+
+def _ivec(n):
+    def ctor(*a):
+        parts = []
+        for x in a:
+            parts.extend(np.asarray(x).reshape(-1).tolist())
+        assert len(parts) == n
+        return tuple(I32._w(int(np.trunc(v))) for v in parts)  # float -> int conversion truncates
+    return ctor
+
+
+U32.__mod__ = lambda self, o: U32(int(self) % int(o))
 BUILTINS.update({
+    "ivec2": _ivec(2), "ivec3": _ivec(3),
     "floatBitsToUint": lambda f: U32(int(np.asarray(f, F).view(np.uint32))),
     "uintBitsToFloat": lambda u: np.asarray(int(u) & 0xFFFFFFFF, np.uint32).view(F)[()],
     "fract": lambda a: (np.asarray(a, F) - np.floor(np.asarray(a, F))).astype(F)[()],

@@ -298,6 +298,19 @@ def reference_shader_vectors():
     q4 = np.concatenate([rng.uniform(-1, 3, (n_cases, 3)).astype(f32), np.ones((n_cases, 1), f32)], 1)
     out.update(clip_min=lo, clip_max=hi, clip_p=p4, clip_q=q4)
     out["ref_clip_aabb"] = np.asarray([taa["clip_aabb"](lo[i], hi[i], p4[i], q4[i]) for i in range(n_cases)], f32)
+    # Particle.glsl:14-16, :30-32: spatial-hash cell of a particle and its key (int32 wrap-around, unsigned modulo)
+    ptcl = G.load_functions(os.path.join(REF, "Core/res/shaders/Particle.glsl"), ["GetCellKey", "GetParticleCellPos"])
+    ppos = np.concatenate([rng.uniform(-300, 300, (200, 3)), rng.uniform(-2, 2, (56, 3))]).astype(f32)
+    cells = np.array([ptcl["GetParticleCellPos"](G.namespace(position_radius=np.append(ppos[i], f32(0.1)))) for i in range(n_cases)], np.int32)
+    counts = rng.choice([1, 2, 1000, 100000, 131072, 999983], n_cases).astype(np.uint32)
+    out.update(ptcl_pos=ppos, ref_cell_pos=cells, cell_count=counts)
+    out["ref_cell_key"] = np.array([int(ptcl["GetCellKey"](tuple(G.I32(int(c)) for c in cells[i]), G.U32(int(counts[i])))) for i in range(n_cases)], np.uint32)
+    # GBuffer.frag:41-43: CalcVelocity (motion vector from the current and the previous clip-space position)
+    gb = G.load_functions(os.path.join(REF, "Core/res/shaders/GBuffer.frag"), ["CalcVelocity"])
+    cur = np.concatenate([rng.uniform(-3, 3, (n_cases, 3)), rng.uniform(0.1, 50, (n_cases, 1))], 1).astype(f32)
+    old = (cur + rng.normal(scale=0.05, size=(n_cases, 4))).astype(f32)
+    out.update(clip_cur=cur, clip_old=old)
+    out["ref_velocity"] = np.asarray([gb["CalcVelocity"](cur[i], old[i]) for i in range(n_cases)], f32)
     np.savez_compressed(os.path.join(GOLD, "reference_shader_vectors.npz"), **out)
 
 
