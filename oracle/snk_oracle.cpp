@@ -233,6 +233,13 @@ ORACLE_API void snkor_particles_grid(const Particle* p, uint32_t n, CellKeyEntry
   memcpy(start, s.data(), 4 * (size_t)n);
 }
 // TAA_Resolve.comp on raw RGBA16F / RG16F planes (snk_taa.h)
+ORACLE_API void snkor_hemisphere_helpers(const float* n3, float r1, float r2, float* nt3, float* nb3, float* sample3) {
+  vec3 nt, nb;
+  Invocation::create_coordinate_system(v3(n3[0], n3[1], n3[2]), nt, nb);
+  const vec3 s = Invocation::uniform_sample_hemisphere(r1, r2);
+  nt3[0] = nt.x; nt3[1] = nt.y; nt3[2] = nt.z; nb3[0] = nb.x; nb3[1] = nb.y; nb3[2] = nb.z;
+  sample3[0] = s.x; sample3[1] = s.y; sample3[2] = s.z;
+}
 ORACLE_API void snkor_calc_velocity(const float* cur4, const float* old4, float* out2) {
   calc_velocity(vec4{cur4[0], cur4[1], cur4[2], cur4[3]}, vec4{old4[0], old4[1], old4[2], old4[3]}, out2[0], out2[1]);
 }

@@ -650,6 +650,12 @@ def test_oracle_equals_the_executed_reference_shader_text(oracle):
         key = L.snkor_ptcl_cell_key(int(cell[0]), int(cell[1]), int(cell[2]), C.c_uint32(int(g["cell_count"][i])))
         assert key == int(g["ref_cell_key"][i]), (i, key, g["ref_cell_key"][i])
     assert (g["ref_cell_pos"] < 0).any() and len(set(g["ref_cell_key"].tolist())) > 100
+    # RayGen.rgen:123-137 — CreateCoordinateSystem: bit for bit; UniformSampleHemisphere: sin / cos differ by an ulp between libms
+    for i in range(n_cases):
+        nt, nb, sm = np.zeros(3, np.float32), np.zeros(3, np.float32), np.zeros(3, np.float32)
+        L.snkor_hemisphere_helpers(fp(np.ascontiguousarray(g["n"][i], np.float32)), C.c_float(g["hemi_r"][i, 0]), C.c_float(g["hemi_r"][i, 1]), fp(nt), fp(nb), fp(sm))
+        assert np.array_equal(nt.view(np.uint32), g["ref_nt"][i].view(np.uint32)) and np.array_equal(nb.view(np.uint32), g["ref_nb"][i].view(np.uint32)), i
+        assert np.allclose(sm, g["ref_hemisphere"][i], rtol=0, atol=3e-7), (i, sm, g["ref_hemisphere"][i])
     # GBuffer.frag:41-43 — CalcVelocity: bit for bit
     for i in range(g["clip_cur"].shape[0]):
         o2 = np.zeros(2, np.float32)

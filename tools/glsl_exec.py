@@ -54,8 +54,8 @@ BUILTINS = {
     "sqrt": lambda a: np.sqrt(np.asarray(a, F)).astype(F)[()],
     "abs": lambda a: np.abs(np.asarray(a, F)).astype(F)[()],
 }
-_TYPES = r"(?:float|int|uint|bool|vec[234]|ivec[234]|uvec[234]|mat[34])"
-_SWIZZLE = {"xyz": "[:3]", "rgb": "[:3]", "xy": "[:2]", "x": "[0]", "y": "[1]", "z": "[2]", "w": "[3]", "r": "[0]", "g": "[1]", "b": "[2]"}
+_TYPES = r"(?:void|float|int|uint|bool|vec[234]|ivec[234]|uvec[234]|mat[34])"
+_SWIZZLE = {"xyz": "[:3]", "rgb": "[:3]", "xy": "[:2]", "xz": "[[0, 2]]", "yz": "[1:3]", "x": "[0]", "y": "[1]", "z": "[2]", "w": "[3]", "r": "[0]", "g": "[1]", "b": "[2]"}
 
 
 class U32(int):
@@ -96,6 +96,8 @@ def _ivec(n):
 U32.__mod__ = lambda self, o: U32(int(self) % int(o))
 BUILTINS.update({
     "ivec2": _ivec(2), "ivec3": _ivec(3),
+    "cross": lambda a, b: np.array([F(F(a[1] * b[2]) - F(b[1] * a[2])), F(F(a[2] * b[0]) - F(b[2] * a[0])), F(F(a[0] * b[1]) - F(b[0] * a[1]))], F),
+    "sin": lambda a: np.sin(np.asarray(a, F)).astype(F)[()], "cos": lambda a: np.cos(np.asarray(a, F)).astype(F)[()],
     "floatBitsToUint": lambda f: U32(int(np.asarray(f, F).view(np.uint32))),
     "uintBitsToFloat": lambda u: np.asarray(int(u) & 0xFFFFFFFF, np.uint32).view(F)[()],
     "fract": lambda a: (np.asarray(a, F) - np.floor(np.asarray(a, F))).astype(F)[()],
@@ -107,24 +109,30 @@ def _expr(e):
     e = re.sub(r"\b(0x[0-9A-Fa-f]+|\d+)u\b", r"U32(\1)", e)
     e = re.sub(r"\b(\d+\.\d*|\.\d+)f\b", r"\1", e)  # 0.5f
     # swizzles after an identifier, `)` or `]` (never inside a float literal)
-    return re.sub(r"(?<=[A-Za-z_0-9\)\]])\.(xyz|rgb|xy|x|y|z|w|r|g|b)\b(?!\s*\()", lambda m: _SWIZZLE[m.group(1)], e)
+    return re.sub(r"(?<=[A-Za-z_0-9\)\]])\.(xyz|rgb|xy|xz|yz|x|y|z|w|r|g|b)\b(?!\s*\()", lambda m: _SWIZZLE[m.group(1)], e)
 
 
 def _translate(name, params, body):
-    args = []
+    args, outs = [], []
     for p in params.split(","):
         p = p.strip()
         if p:
-            args.append(p.split()[-1])
+            if p.split()[0] == "out":
+                outs.append(p.split()[-1])  # `out` parameters are returned (as a tuple, in declaration order)
+            else:
+                args.append(p.split()[-1])
     lines = [f"def {name}({', '.join(args)}):"]
     body = re.sub(r"//[^\n]*", "", body)
     for st in body.split(";"):
         st = " ".join(st.split())
         if not st:
             continue
-        assert not re.match(r"(for|while|switch|else)\b", st), f"{name}: control flow is outside the supported subset: {st}"
+        assert not re.match(r"(for|while|switch)\b", st), f"{name}: control flow is outside the supported subset: {st}"
         prefix = ""
-        if st.startswith("if"):  # single-statement form only: if (cond) statement;
+        if st.startswith("else"):  # single-statement else of the single-statement if before it
+            prefix, st = "else: ", st[4:].strip()
+            assert st and not st.startswith(("{", "if")), f"{name}: only single-statement else is supported"
+        elif st.startswith("if"):  # single-statement form only: if (cond) statement;
             i = st.index("(")
             depth, j = 1, i + 1
             while depth:
@@ -134,6 +142,8 @@ def _translate(name, params, body):
             assert st and not st.startswith("{"), f"{name}: only single-statement if is supported"
         st = re.sub(rf"^(?:const\s+)?{_TYPES}\s+(?=\w+\s*=)", "", st)
         lines.append("    " + prefix + _expr(st))
+    if outs:
+        lines.append("    return " + ", ".join(outs))
     return "\n".join(lines)
 
 

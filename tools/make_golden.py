@@ -311,6 +311,12 @@ def reference_shader_vectors():
     old = (cur + rng.normal(scale=0.05, size=(n_cases, 4))).astype(f32)
     out.update(clip_cur=cur, clip_old=old)
     out["ref_velocity"] = np.asarray([gb["CalcVelocity"](cur[i], old[i]) for i in range(n_cases)], f32)
+    # RayGen.rgen:123-137: tangent frame and uniform hemisphere sample of BounceDiffuse (PI comes from LightBuffers.glsl)
+    rg = G.load_functions(os.path.join(REF, "Core/res/shaders/RayGen.rgen"), ["CreateCoordinateSystem", "UniformSampleHemisphere"], defines={"PI": env["PI"]})
+    r12 = rng.uniform(0, 1, (n_cases, 2)).astype(f32)
+    frames = [rg["CreateCoordinateSystem"](n[i]) for i in range(n_cases)]
+    out.update(hemi_r=r12, ref_nt=np.asarray([f[0] for f in frames], f32), ref_nb=np.asarray([f[1] for f in frames], f32))
+    out["ref_hemisphere"] = np.asarray([rg["UniformSampleHemisphere"](r12[i, 0], r12[i, 1]) for i in range(n_cases)], f32)
     np.savez_compressed(os.path.join(GOLD, "reference_shader_vectors.npz"), **out)
 
 
