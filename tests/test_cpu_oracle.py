@@ -632,6 +632,12 @@ def test_oracle_equals_the_executed_reference_shader_text(oracle):
     got = np.array([L.snkor_random(float(x)) for x in g["random_in"]], np.float32)
     assert np.array_equal(got.view(np.uint32), g["ref_random"].view(np.uint32))
     assert g["ref_random"].min() >= 0.0 and g["ref_random"].max() < 1.0 and len(set(g["ref_random"].tolist())) > 200
+    # Util.glsl:77-82 — gold_noise: chaotic (tan of up to ~1000 rad times the pixel x); numpy's and libm's float64 tan may differ
+    # in the last place before rounding, so nearly all, not all, values are bit-identical
+    L.snkor_gold_noise.restype = C.c_float
+    gn = np.array([L.snkor_gold_noise(C.c_float(float(g["gold_xy"][i, 0])), C.c_float(float(g["gold_xy"][i, 1])), C.c_float(float(g["gold_seed"][i])))
+                   for i in range(g["gold_seed"].shape[0])], np.float32)
+    assert (gn.view(np.uint32) == g["ref_gold_noise"].view(np.uint32)).mean() >= 0.98
     # TAA_Resolve.comp:12-35 — clip_aabb: float32 + - * / in the shader's order: bit for bit
     clipped = 0
     for i in range(g["clip_p"].shape[0]):

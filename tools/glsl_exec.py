@@ -97,6 +97,9 @@ U32.__mod__ = lambda self, o: U32(int(self) % int(o))
 BUILTINS.update({
     "ivec2": _ivec(2), "ivec3": _ivec(3),
     "cross": lambda a, b: np.array([F(F(a[1] * b[2]) - F(b[1] * a[2])), F(F(a[2] * b[0]) - F(b[2] * a[0])), F(F(a[0] * b[1]) - F(b[0] * a[1]))], F),
+    "distance": lambda a, b: _length(np.asarray(a, F) - np.asarray(b, F)),
+    # the numerics contract of this repository for transcendental functions: float64 libm, rounded once (oracle/snk_math.h)
+    "tan": lambda a: F(np.tan(np.float64(F(a)))),
     "sin": lambda a: np.sin(np.asarray(a, F)).astype(F)[()], "cos": lambda a: np.cos(np.asarray(a, F)).astype(F)[()],
     "floatBitsToUint": lambda f: U32(int(np.asarray(f, F).view(np.uint32))),
     "uintBitsToFloat": lambda u: np.asarray(int(u) & 0xFFFFFFFF, np.uint32).view(F)[()],
@@ -154,6 +157,8 @@ def load_functions(path, names, defines=None):
     env["U32"] = U32
     for m in re.finditer(r"^#define\s+(\w+)\s+([0-9.]+)f?\s*$", text, re.M):
         env[m.group(1)] = F(float(m.group(2)))
+    for m in re.finditer(r"^\s*const\s+float\s+(\w+)\s*=\s*([0-9.]+)f?\s*;", text, re.M):  # file-scope float constants
+        env.setdefault(m.group(1), F(float(m.group(2))))
     env.update(defines or {})
     for name in names:
         m = re.search(rf"^\s*{_TYPES}\s+{name}\s*\(([^)]*)\)\s*\{{", text, re.M)

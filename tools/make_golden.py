@@ -291,6 +291,12 @@ def reference_shader_vectors():
     rx = np.concatenate([np.array([0.0, -0.0, 1.0, 0.5, 1e-30, 123456.789], f32), rng.normal(scale=100.0, size=250).astype(f32)])
     out["random_in"] = rx
     out["ref_random"] = np.array([util["random"](x) for x in rx], f32)
+    # Util.glsl:77-82: gold_noise (tan in float64 rounded once = the numerics contract; chaotic, so compared statistically)
+    gn = G.load_functions(os.path.join(REF, "Core/res/shaders/Util.glsl"), ["gold_noise"])
+    gxy = np.stack([rng.integers(0, 1920, n_cases), rng.integers(0, 1080, n_cases)], -1).astype(f32)
+    gseed = rng.uniform(0, 1, n_cases).astype(f32)
+    out.update(gold_xy=gxy, gold_seed=gseed)
+    out["ref_gold_noise"] = np.array([gn["gold_noise"](gxy[i], gseed[i]) for i in range(n_cases)], f32)
     # TAA_Resolve.comp:12-35: clip_aabb (history colour clipped towards the neighbourhood box)
     taa = G.load_functions(os.path.join(REF, "Core/res/shaders/TAA_Resolve.comp"), ["clip_aabb"])
     lo = rng.uniform(0, 1, (n_cases, 3)).astype(f32); hi = (lo + rng.uniform(0, 1, (n_cases, 3))).astype(f32)
