@@ -199,6 +199,21 @@ ORACLE_API void snkor_wrs_pointlight_script(void* fp, const uint32_t* idx, const
   for (uint32_t i = 0; i < n; ++i) inv.update_pointlight_reservoir(r, idx[i], weight[i], 0.0f);
   *out = r;
 }
+// the same streaming updates with the shader's OWN random numbers (gold_noise of the pixel, the frame time and the weight):
+// pinned against the reference functions executed from the shader text (tests/golden/reference_shader_vectors.npz)
+ORACLE_API void snkor_wrs_native(void* fp, uint32_t x, uint32_t y, const uint32_t* idx, const uint32_t* tri, const float* bary2,
+                                 const float* weight, const float* seed, uint32_t n, PixelReservoir* out_pl, PixelReservoir* out_em,
+                                 uint8_t* selected_pl, uint8_t* selected_em) {
+  Frame& f = *(Frame*)fp;
+  Invocation inv(f, x, y, nullptr);
+  PixelReservoir a; Invocation::init_pixel_reservoir(a);
+  PixelReservoir b; Invocation::init_pixel_reservoir(b);
+  for (uint32_t i = 0; i < n; ++i) {
+    selected_pl[i] = inv.update_pointlight_reservoir(a, idx[i], weight[i], seed[i]) ? 1 : 0;
+    selected_em[i] = inv.update_emissive_reservoir(b, idx[i], tri[i], bary2[2 * i], bary2[2 * i + 1], weight[i], seed[i]) ? 1 : 0;
+  }
+  *out_pl = a; *out_em = b;
+}
 // run one pixel of one pass with scripted random numbers (KAT for the temporal / spatial state machines)
 ORACLE_API void snkor_pixel_scripted(void* fp, uint32_t x, uint32_t y, uint32_t pass, const float* u, uint32_t n) {
   Frame& f = *(Frame*)fp;

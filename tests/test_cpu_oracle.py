@@ -667,3 +667,37 @@ def test_oracle_equals_the_executed_reference_shader_text(oracle):
         o2 = np.zeros(2, np.float32)
         L.snkor_calc_velocity(fp(np.ascontiguousarray(g["clip_cur"][i], np.float32)), fp(np.ascontiguousarray(g["clip_old"][i], np.float32)), fp(o2))
         assert np.array_equal(o2.view(np.uint32), g["ref_velocity"][i].view(np.uint32)), (i, o2, g["ref_velocity"][i])
+
+
+def test_reservoir_updates_equal_the_executed_reference_shader(snk, oracle):
+    """InitPixelReservoir / UpdatePointlightReservoir / UpdateEmissiveReservoir (RayGen.rgen:215-239, :284-294) executed from the
+    reference's shader text with the shader's own gold_noise random numbers (tools/glsl_exec.py): 48 pixels x 32 candidates,
+    some with zero weight. The oracle's streaming updates must make the same selection at every step and end in the same state."""
+    g = np.load(os.path.join(GOLD, "reference_shader_vectors.npz"))
+    sc = snk.scenes.cornell(32, 32, with_pointlight=True)
+    fr = oracle.OracleFrame(oracle.OracleScene(sc))
+    L = oracle.lib()
+    n_runs, n_cand = g["wrs_idx"].shape
+    same_steps = total_steps = 0
+    for r in range(n_runs):
+        ubo = sc.ubo(0)
+        ubo["time_elapsed"] = g["wrs_time"][r]
+        fr.set(ubo, ubo)
+        a, b = np.zeros((), snk.scenes.RESERVOIR_DTYPE), np.zeros((), snk.scenes.RESERVOIR_DTYPE)
+        sp, se = np.zeros(n_cand, np.uint8), np.zeros(n_cand, np.uint8)
+        arrs = [np.ascontiguousarray(g[k][r]) for k in ("wrs_idx", "wrs_tri", "wrs_bary", "wrs_weight", "wrs_seed")]
+        L.snkor_wrs_native(fr.h, int(g["wrs_px"][r, 0]), int(g["wrs_px"][r, 1]), fp(arrs[0]), fp(arrs[1]), fp(arrs[2]), fp(arrs[3]), fp(arrs[4]),
+                           n_cand, fp(a), fp(b), fp(sp), fp(se))
+        same_steps += int((sp == g["ref_wrs_sel_pl"][r]).sum() + (se == g["ref_wrs_sel_em"][r]).sum())
+        total_steps += 2 * n_cand
+        if np.array_equal(sp, g["ref_wrs_sel_pl"][r]):
+            w_sum, idx, m = g["ref_wrs_pl"][r]
+            assert np.float32(a["w_sum_pl"]) == np.float32(w_sum) and int(a["pl_idx"]) == int(idx) and int(a["pl_m"]) == int(m) == n_cand
+        if np.array_equal(se, g["ref_wrs_sel_em"][r]):
+            w_sum, obj, tri, m, bx, by = g["ref_wrs_em"][r]
+            assert np.float32(b["w_sum_em"]) == np.float32(w_sum) and int(b["m_em"]) == int(m) == n_cand
+            assert (int(b["object_instance_idx"]), int(b["triangle_idx"])) == (int(obj), int(tri))
+            assert np.array_equal(b["bary"], np.float32([bx, by]))
+    # gold_noise is chaotic: a last-place difference of tan() between numpy and libm can flip a single comparison
+    assert same_steps >= 0.995 * total_steps, f"{total_steps - same_steps} of {total_steps} selection decisions differ"
+    assert g["ref_wrs_sel_pl"].sum() > n_runs and (g["wrs_weight"] == 0).any()

@@ -6,8 +6,8 @@ Python function by a mechanical rewrite (declarations lose their type, swizzles 
 numpy helpers with the same operation order) and returns them. Nothing of the shader text is stored in this repository: the
 generator (tools/make_golden.py) commits only the numeric input / output vectors.
 
-Supported subset: functions whose body is a sequence of declarations, assignments, compound assignments, single-statement `if`s and
-one return; scalar / vec3 / vec4 float arithmetic and 32-bit unsigned arithmetic; struct parameters and the `ssbo_light_data` block as attribute access; the built-ins listed in BUILTINS.
+Supported subset: functions whose body consists of declarations, assignments, compound assignments, `++`, `if` / `else` (single
+statements or blocks, nested) and returns — no loops; scalar / vec3 / vec4 float arithmetic and 32-bit unsigned arithmetic; struct parameters and the `ssbo_light_data` block as attribute access; the built-ins listed in BUILTINS.
 """
 import re
 import types
@@ -115,45 +115,96 @@ def _expr(e):
     return re.sub(r"(?<=[A-Za-z_0-9\)\]])\.(xyz|rgb|xy|xz|yz|x|y|z|w|r|g|b)\b(?!\s*\()", lambda m: _SWIZZLE[m.group(1)], e)
 
 
+def _stmt(st):
+    st = re.sub(rf"^(?:const\s+)?{_TYPES}\s+(?=\w+\s*=)", "", st)
+    st = re.sub(r"^([\w\.\[\]]+)\+\+$", r"\1 += 1", st)
+    st = re.sub(r"^([\w\.\[\]]+)--$", r"\1 -= 1", st)
+    return _expr(st)
+
+
+def _cond(c):
+    c = c.replace("&&", " and ").replace("||", " or ")
+    c = re.sub(r"!(?!=)", " not ", c)
+    return _expr(c)
+
+
+def _split_paren(st):
+    """'if (cond) rest' -> (cond, rest)"""
+    i = st.index("(")
+    depth, j = 1, i + 1
+    while depth:
+        depth += {"(": 1, ")": -1}.get(st[j], 0)
+        j += 1
+    return st[i + 1:j - 1], st[j:].strip()
+
+
 def _translate(name, params, body):
     args, outs = [], []
     for p in params.split(","):
         p = p.strip()
         if p:
             if p.split()[0] == "out":
-                outs.append(p.split()[-1])  # `out` parameters are returned (as a tuple, in declaration order)
+                outs.append(p.split()[-1])  # `out` parameters are returned (as a tuple, in declaration order); `inout` structs are mutated
             else:
                 args.append(p.split()[-1])
     lines = [f"def {name}({', '.join(args)}):"]
     body = re.sub(r"//[^\n]*", "", body)
-    for st in body.split(";"):
-        st = " ".join(st.split())
-        if not st:
-            continue
-        assert not re.match(r"(for|while|switch)\b", st), f"{name}: control flow is outside the supported subset: {st}"
-        prefix = ""
-        if st.startswith("else"):  # single-statement else of the single-statement if before it
-            prefix, st = "else: ", st[4:].strip()
-            assert st and not st.startswith(("{", "if")), f"{name}: only single-statement else is supported"
-        elif st.startswith("if"):  # single-statement form only: if (cond) statement;
-            i = st.index("(")
-            depth, j = 1, i + 1
-            while depth:
-                depth += {"(": 1, ")": -1}.get(st[j], 0)
-                j += 1
-            prefix, st = f"if {_expr(st[i + 1:j - 1])}: ", st[j:].strip()
-            assert st and not st.startswith("{"), f"{name}: only single-statement if is supported"
-        st = re.sub(rf"^(?:const\s+)?{_TYPES}\s+(?=\w+\s*=)", "", st)
-        lines.append("    " + prefix + _expr(st))
+    body = re.sub(r"\btrue\b", "True", re.sub(r"\bfalse\b", "False", body))
+    indent, cur, depth, emitted = 1, "", 0, [0]
+
+    def emit(text):
+        lines.append("    " * indent + text)
+        emitted[-1] += 1
+
+    for ch in body:
+        if ch == "(":
+            depth += 1
+        elif ch == ")":
+            depth -= 1
+        if depth == 0 and ch in ";{}":
+            st = " ".join(cur.split())
+            cur = ""
+            if ch == ";":
+                if not st:
+                    continue
+                assert not re.match(r"(for|while|switch|do)\b", st), f"{name}: loops are outside the supported subset: {st}"
+                prefix = ""
+                if re.match(r"else\b", st):
+                    st = st[4:].strip()
+                    prefix = "el" if st.startswith("if") else "else: "
+                if st.startswith("if"):  # single-statement form: if (cond) statement;
+                    cond, st = _split_paren(st)
+                    prefix += f"if {_cond(cond)}: "
+                emit(prefix + _stmt(st))
+            elif ch == "{":
+                assert not re.match(r"(for|while|switch|do)\b", st), f"{name}: loops are outside the supported subset: {st}"
+                if re.match(r"else\s+if\b", st):
+                    emit(f"elif {_cond(_split_paren(st)[0])}:")
+                elif st.startswith("if"):
+                    emit(f"if {_cond(_split_paren(st)[0])}:")
+                elif st == "else":
+                    emit("else:")
+                else:
+                    assert not st, f"{name}: unsupported block header: {st}"
+                    emit("if True:")
+                indent += 1
+                emitted.append(0)
+            else:
+                assert not st, f"{name}: statement without ';' before '}}': {st}"
+                if emitted.pop() == 0:
+                    lines.append("    " * indent + "pass")
+                indent -= 1
+        else:
+            cur += ch
     if outs:
         lines.append("    return " + ", ".join(outs))
     return "\n".join(lines)
 
 
-def load_functions(path, names, defines=None):
+def load_functions(path, names, defines=None, env=None):
     """-> dict name -> python function, plus the `defines` found in the file (object-like macros with a numeric value)"""
     text = open(path, encoding="utf-8", errors="replace").read()
-    env = dict(BUILTINS)
+    env = dict(BUILTINS) if env is None else env
     env["U32"] = U32
     for m in re.finditer(r"^#define\s+(\w+)\s+([0-9.]+)f?\s*$", text, re.M):
         env[m.group(1)] = F(float(m.group(2)))

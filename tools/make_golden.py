@@ -323,6 +323,37 @@ def reference_shader_vectors():
     frames = [rg["CreateCoordinateSystem"](n[i]) for i in range(n_cases)]
     out.update(hemi_r=r12, ref_nt=np.asarray([f[0] for f in frames], f32), ref_nb=np.asarray([f[1] for f in frames], f32))
     out["ref_hemisphere"] = np.asarray([rg["UniformSampleHemisphere"](r12[i, 0], r12[i, 1]) for i in range(n_cases)], f32)
+    # RayGen.rgen:215-239, :284-294: the streaming reservoir updates with the shader's own random numbers
+    wenv = G.load_functions(os.path.join(REF, "Core/res/shaders/Util.glsl"), ["gold_noise"])
+    G.load_functions(os.path.join(REF, "Core/res/shaders/RayGen.rgen"), ["InitPixelReservoir", "UpdatePointlightReservoir", "UpdateEmissiveReservoir"],
+                     defines={"INVALID_RESERVOIR_IDX": G.U32(0xFFFFFFFF)}, env=wenv)
+    n_runs, n_cand = 48, 32
+    w_px = np.stack([rng.integers(1, 1920, n_runs), rng.integers(0, 1080, n_runs)], -1).astype(np.uint32)
+    w_time = rng.uniform(0, 60000, n_runs).astype(f32)
+    w_idx = rng.integers(0, 1024, (n_runs, n_cand)).astype(np.uint32)
+    w_tri = rng.integers(0, 5000, (n_runs, n_cand)).astype(np.uint32)
+    w_bary = rng.uniform(0, 0.5, (n_runs, n_cand, 2)).astype(f32)
+    w_weight = (rng.uniform(0, 4, (n_runs, n_cand)) * (rng.uniform(0, 1, (n_runs, n_cand)) > 0.2)).astype(f32)  # some zero weights
+    w_seed = rng.uniform(0, 1, (n_runs, n_cand)).astype(f32)
+    res_pl, res_em, sel_pl, sel_em = [], [], [], []
+    for r in range(n_runs):
+        wenv["gl_LaunchIDEXT"] = np.array([w_px[r, 0], w_px[r, 1], 0], f32)
+        wenv["common_ubo"] = G.namespace(time_elapsed=w_time[r])
+        a = G.namespace(emissive_triangle=G.namespace()); wenv["InitPixelReservoir"](a)
+        b = G.namespace(emissive_triangle=G.namespace()); wenv["InitPixelReservoir"](b)
+        sp, se = [], []
+        for i in range(n_cand):
+            sp.append(bool(wenv["UpdatePointlightReservoir"](a, G.U32(int(w_idx[r, i])), w_weight[r, i], w_seed[r, i])))
+            t = G.namespace(object_instance_idx=G.U32(int(w_idx[r, i])), triangle_idx=G.U32(int(w_tri[r, i])), bary_coords=w_bary[r, i])
+            se.append(bool(wenv["UpdateEmissiveReservoir"](b, t, w_weight[r, i], w_seed[r, i])))
+        res_pl.append([float(a.w_sum_pl), int(a.pl_idx), int(a.pl_m)])
+        et = b.emissive_triangle
+        res_em.append([float(b.w_sum_em), int(et.object_instance_idx), int(et.triangle_idx), int(b.m_em)] +
+                      (list(map(float, et.bary_coords)) if hasattr(et, "bary_coords") else [0.0, 0.0]))
+        sel_pl.append(sp); sel_em.append(se)
+    out.update(wrs_px=w_px, wrs_time=w_time, wrs_idx=w_idx, wrs_tri=w_tri, wrs_bary=w_bary, wrs_weight=w_weight, wrs_seed=w_seed,
+               ref_wrs_pl=np.array(res_pl, np.float64), ref_wrs_em=np.array(res_em, np.float64),
+               ref_wrs_sel_pl=np.array(sel_pl, np.uint8), ref_wrs_sel_em=np.array(sel_em, np.uint8))
     np.savez_compressed(os.path.join(GOLD, "reference_shader_vectors.npz"), **out)
 
 
