@@ -214,6 +214,17 @@ ORACLE_API void snkor_wrs_native(void* fp, uint32_t x, uint32_t y, const uint32_
   }
   *out_pl = a; *out_em = b;
 }
+// the point-light loop of DoInitialWRS on an explicit surface (not a G-buffer pixel)
+ORACLE_API float snkor_ris_pointlights(void* fp, uint32_t x, uint32_t y, const float* v, const float* f0, const float* world_pos, const float* n,
+                                       float roughness, float metallic, const float* albedo, PixelReservoir* out) {
+  Frame& f = *(Frame*)fp;
+  Invocation inv(f, x, y, nullptr);
+  PixelReservoir r; Invocation::init_pixel_reservoir(r);
+  const float p_hat = inv.ris_pointlights(r, v3(v[0], v[1], v[2]), v3(f0[0], f0[1], f0[2]), v3(world_pos[0], world_pos[1], world_pos[2]),
+                                          v3(n[0], n[1], n[2]), roughness, metallic, v3(albedo[0], albedo[1], albedo[2]));
+  *out = r;
+  return p_hat;
+}
 // run one pixel of one pass with scripted random numbers (KAT for the temporal / spatial state machines)
 ORACLE_API void snkor_pixel_scripted(void* fp, uint32_t x, uint32_t y, uint32_t pass, const float* u, uint32_t n) {
   Frame& f = *(Frame*)fp;

@@ -328,11 +328,11 @@ struct Invocation {
   }
 
   // RayGen.rgen:296-357
-  void do_initial_wrs(PixelReservoir& r, vec3 v, vec3 f0, vec3 world_pos, vec3 n, float roughness, float metallic, vec3 albedo, vec3 biased_pos) {
-    float p_hat_pl = 0.0f, p_hat_em = 0.0f;
+  // RayGen.rgen:300-309: the point-light half of DoInitialWRS; returns p_hat of the selected light
+  float ris_pointlights(PixelReservoir& r, vec3 v, vec3 f0, vec3 world_pos, vec3 n, float roughness, float metallic, vec3 albedo) {
+    float p_hat_pl = 0.0f;
     const uint32_t iters = F.settings.ris_iters;
     const uint32_t n_pl = L.num_pointlights;
-    const uint32_t n_em = (uint32_t)sc.emissive_idx.size();
     for (uint32_t i = 0; i < iters; ++i) {
       if (n_pl == 0) { r.pl_m++; continue; }  // DEVIATION: reference reads light slot 0 of an empty array (weight 0/NaN, never selected)
       const float seed = fract(((time() * 0.001197f + world_pos.x) + world_pos.y) + world_pos.z) + (float)i / (float)iters;
@@ -342,6 +342,13 @@ struct Invocation {
       const float weight = p_hat / (1.0f / (float)n_pl);
       if (update_pointlight_reservoir(r, rnd_idx, weight, sin_c((float)i * 20382997.34741f))) p_hat_pl = p_hat;
     }
+    return p_hat_pl;
+  }
+  void do_initial_wrs(PixelReservoir& r, vec3 v, vec3 f0, vec3 world_pos, vec3 n, float roughness, float metallic, vec3 albedo, vec3 biased_pos) {
+    float p_hat_em = 0.0f;
+    const uint32_t iters = F.settings.ris_iters;
+    const uint32_t n_em = (uint32_t)sc.emissive_idx.size();
+    const float p_hat_pl = ris_pointlights(r, v, f0, world_pos, n, roughness, metallic, albedo);
     for (uint32_t i = 0; i < iters; ++i) {
       if (n_em == 0) { r.m_em++; continue; }  // DEVIATION: reference reads idx[0] of an empty list
       const float wsum = (world_pos.x + world_pos.y) + world_pos.z;

@@ -701,3 +701,32 @@ def test_reservoir_updates_equal_the_executed_reference_shader(snk, oracle):
     # gold_noise is chaotic: a last-place difference of tan() between numpy and libm can flip a single comparison
     assert same_steps >= 0.995 * total_steps, f"{total_steps - same_steps} of {total_steps} selection decisions differ"
     assert g["ref_wrs_sel_pl"].sum() > n_runs and (g["wrs_weight"] == 0).any()
+
+
+def test_pointlight_ris_loop_equals_the_executed_reference_shader(snk, oracle):
+    """The point-light loop of DoInitialWRS (RayGen.rgen:300-309) executed from the reference's shader text — light pick
+    uint(gold_noise * N), p_hat = |CalcPointlight|, weight = p_hat * N, streaming update seeded by sin(i * 20382997.34741) — on 64
+    surfaces with 16 lights. The oracle's loop must arrive at the same reservoir (weight sum, selected light, M) and p_hat."""
+    g = np.load(os.path.join(GOLD, "reference_shader_vectors.npz"))
+    sc = snk.scenes.cornell(32, 32)
+    sc.pointlights = np.ascontiguousarray(g["ris_lights"], np.float32)
+    fr = oracle.OracleFrame(oracle.OracleScene(sc))
+    L = oracle.lib()
+    L.snkor_ris_pointlights.restype = C.c_float
+    n_ris = g["ris_px"].shape[0]
+    same = 0
+    for r in range(n_ris):
+        ubo = sc.ubo(0)
+        ubo["time_elapsed"] = g["ris_time"][r]
+        fr.set(ubo, ubo, oracle.default_settings())
+        a = [np.ascontiguousarray(g[k][r], np.float32) for k in ("v", "f0", "world_pos", "n", "albedo")]
+        res = np.zeros((), snk.scenes.RESERVOIR_DTYPE)
+        p_hat = L.snkor_ris_pointlights(fr.h, int(g["ris_px"][r, 0]), int(g["ris_px"][r, 1]), fp(a[0]), fp(a[1]), fp(a[2]), fp(a[3]),
+                                        C.c_float(g["roughness"][r]), C.c_float(g["metallic"][r]), fp(a[4]), fp(res))
+        w_sum, idx, m, ref_p_hat = g["ref_ris_pl"][r]
+        assert int(res["pl_m"]) == int(m) == 32
+        assert np.isclose(res["w_sum_pl"], w_sum, rtol=2e-5), (r, res["w_sum_pl"], w_sum)  # 32 float32 additions of pow()-dependent terms
+        same += int(int(res["pl_idx"]) == int(idx) and np.isclose(p_hat, ref_p_hat, rtol=2e-5))
+    # the chaotic RNG may turn a last-place difference into another pick now and then
+    assert same >= n_ris - 2, f"selected light / p_hat differ on {n_ris - same} of {n_ris} surfaces"
+    assert len(set(g["ref_ris_pl"][:, 1].tolist())) >= 8 and (g["ref_ris_pl"][:, 3] > 0).mean() > 0.8

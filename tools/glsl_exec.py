@@ -7,7 +7,7 @@ numpy helpers with the same operation order) and returns them. Nothing of the sh
 generator (tools/make_golden.py) commits only the numeric input / output vectors.
 
 Supported subset: functions whose body consists of declarations, assignments, compound assignments, `++`, `if` / `else` (single
-statements or blocks, nested) and returns — no loops; scalar / vec3 / vec4 float arithmetic and 32-bit unsigned arithmetic; struct parameters and the `ssbo_light_data` block as attribute access; the built-ins listed in BUILTINS.
+statements or blocks, nested), counted `for (uint i = a; cond; i++)` loops and returns; scalar / vec3 / vec4 float arithmetic and 32-bit unsigned arithmetic; struct parameters and the `ssbo_light_data` block as attribute access; the built-ins listed in BUILTINS.
 """
 import re
 import types
@@ -100,7 +100,9 @@ BUILTINS.update({
     "distance": lambda a, b: _length(np.asarray(a, F) - np.asarray(b, F)),
     # the numerics contract of this repository for transcendental functions: float64 libm, rounded once (oracle/snk_math.h)
     "tan": lambda a: F(np.tan(np.float64(F(a)))),
-    "sin": lambda a: np.sin(np.asarray(a, F)).astype(F)[()], "cos": lambda a: np.cos(np.asarray(a, F)).astype(F)[()],
+    "sin": lambda a: F(np.sin(np.float64(F(a)))), "cos": lambda a: F(np.cos(np.float64(F(a)))),
+    "uint": lambda a: U32(int(a)) if isinstance(a, int) else U32(int(np.trunc(np.float64(a)))),  # float -> uint truncates
+    "float": lambda a: F(a),
     "floatBitsToUint": lambda f: U32(int(np.asarray(f, F).view(np.uint32))),
     "uintBitsToFloat": lambda u: np.asarray(int(u) & 0xFFFFFFFF, np.uint32).view(F)[()],
     "fract": lambda a: (np.asarray(a, F) - np.floor(np.asarray(a, F))).astype(F)[()],
@@ -111,6 +113,8 @@ def _expr(e):
     # unsigned literals (10u, 0x007FFFFFu) become wrap-around integers
     e = re.sub(r"\b(0x[0-9A-Fa-f]+|\d+)u\b", r"U32(\1)", e)
     e = re.sub(r"\b(\d+\.\d*|\.\d+)f\b", r"\1", e)  # 0.5f
+    # float literals are binary32 in GLSL (matters when the other operand is an integer: i * 20382997.34741)
+    e = re.sub(r"(?<![\w.])(\d+\.\d*(?:[eE][-+]?\d+)?|\.\d+(?:[eE][-+]?\d+)?)(?![\w.])", r"F(\1)", e)
     # swizzles after an identifier, `)` or `]` (never inside a float literal)
     return re.sub(r"(?<=[A-Za-z_0-9\)\]])\.(xyz|rgb|xy|xz|yz|x|y|z|w|r|g|b)\b(?!\s*\()", lambda m: _SWIZZLE[m.group(1)], e)
 
@@ -150,7 +154,8 @@ def _translate(name, params, body):
     lines = [f"def {name}({', '.join(args)}):"]
     body = re.sub(r"//[^\n]*", "", body)
     body = re.sub(r"\btrue\b", "True", re.sub(r"\bfalse\b", "False", body))
-    indent, cur, depth, emitted = 1, "", 0, [0]
+    indent, cur, depth, emitted, epilogue = 1, "", 0, [0], []
+    assert not re.search(r"\bcontinue\b|\bbreak\b", body), f"{name}: continue / break are outside the supported subset"
 
     def emit(text):
         lines.append("    " * indent + text)
@@ -177,7 +182,18 @@ def _translate(name, params, body):
                     prefix += f"if {_cond(cond)}: "
                 emit(prefix + _stmt(st))
             elif ch == "{":
-                assert not re.match(r"(for|while|switch|do)\b", st), f"{name}: loops are outside the supported subset: {st}"
+                assert not re.match(r"(while|switch|do)\b", st), f"{name}: unsupported control flow: {st}"
+                m_for = re.match(r"for\s*\(\s*(?:uint|int)\s+(\w+)\s*=\s*([^;]+);\s*([^;]+);\s*(\w+)\+\+\s*\)$", st)
+                if st.startswith("for"):
+                    assert m_for and m_for.group(1) == m_for.group(4), f"{name}: only `for (uint i = a; cond; i++)` is supported: {st}"
+                    emit(f"{m_for.group(1)} = {_expr(m_for.group(2).strip())}")
+                    emit(f"while {_cond(m_for.group(3).strip())}:")
+                    epilogue.append(f"{m_for.group(1)} += 1")
+                    indent += 1
+                    emitted.append(0)
+                    cur = ""
+                    continue
+                epilogue.append(None)
                 if re.match(r"else\s+if\b", st):
                     emit(f"elif {_cond(_split_paren(st)[0])}:")
                 elif st.startswith("if"):
@@ -191,8 +207,12 @@ def _translate(name, params, body):
                 emitted.append(0)
             else:
                 assert not st, f"{name}: statement without ';' before '}}': {st}"
-                if emitted.pop() == 0:
+                ep = epilogue.pop()
+                if ep:
+                    lines.append("    " * indent + ep)  # loop increment (no `continue` in the supported subset)
+                elif emitted[-1] == 0:
                     lines.append("    " * indent + "pass")
+                emitted.pop()
                 indent -= 1
         else:
             cur += ch
@@ -206,6 +226,7 @@ def load_functions(path, names, defines=None, env=None):
     text = open(path, encoding="utf-8", errors="replace").read()
     env = dict(BUILTINS) if env is None else env
     env["U32"] = U32
+    env["F"] = F
     for m in re.finditer(r"^#define\s+(\w+)\s+([0-9.]+)f?\s*$", text, re.M):
         env[m.group(1)] = F(float(m.group(2)))
     for m in re.finditer(r"^\s*const\s+float\s+(\w+)\s*=\s*([0-9.]+)f?\s*;", text, re.M):  # file-scope float constants
@@ -220,6 +241,26 @@ def load_functions(path, names, defines=None, env=None):
             i += 1
         exec(_translate(name, m.group(1), text[m.end():i - 1]), env)  # noqa: S102 - the input is the reference shader, read-only
     return env
+
+
+def load_block(path, start_regex, name, params, prologue="", result="", env=None, defines=None):
+    """a brace-delimited block INSIDE a function (the text from the match of `start_regex`, which must end at its `{`, to the
+    matching `}`) as a function `name(params)`: `prologue` statements run first, `result` is returned"""
+    text = open(path, encoding="utf-8", errors="replace").read()
+    m = re.search(start_regex, text)
+    assert m and text[m.end() - 1] == "{", f"block not found: {start_regex}"
+    depth, i = 1, m.end()
+    while depth:
+        depth += {"{": 1, "}": -1}.get(text[i], 0)
+        i += 1
+    env = dict(BUILTINS) if env is None else env
+    env["U32"], env["F"] = U32, F
+    env.update(defines or {})
+    src = _translate(name, params, prologue + text[m.start():i])
+    if result:
+        src += f"\n    return {result}"
+    exec(src, env)  # noqa: S102
+    return env, text.count("\n", 0, m.start()) + 1, text.count("\n", 0, i) + 1
 
 
 def namespace(**kw):

@@ -354,6 +354,34 @@ def reference_shader_vectors():
     out.update(wrs_px=w_px, wrs_time=w_time, wrs_idx=w_idx, wrs_tri=w_tri, wrs_bary=w_bary, wrs_weight=w_weight, wrs_seed=w_seed,
                ref_wrs_pl=np.array(res_pl, np.float64), ref_wrs_em=np.array(res_em, np.float64),
                ref_wrs_sel_pl=np.array(sel_pl, np.uint8), ref_wrs_sel_em=np.array(sel_em, np.uint8))
+    # RayGen.rgen:300-309: the point-light loop of DoInitialWRS (32 candidates: light pick, p_hat = |CalcPointlight|,
+    # weight = p_hat * N, streaming update seeded with sin(i * 20382997.34741)) on explicit surfaces and 16 random lights
+    renv = G.load_functions(os.path.join(REF, "Core/res/shaders/Util.glsl"), ["gold_noise"])
+    G.load_functions(os.path.join(REF, "Core/res/shaders/LightBuffers.glsl"), names[:5] + ["CalcPointlight"], env=renv)
+    G.load_functions(os.path.join(REF, "Core/res/shaders/RayGen.rgen"), ["InitPixelReservoir", "UpdatePointlightReservoir"],
+                     defines={"INVALID_RESERVOIR_IDX": G.U32(0xFFFFFFFF)}, env=renv)
+    _, l0, l1 = G.load_block(os.path.join(REF, "Core/res/shaders/RayGen.rgen"), r"for \(uint i = 0u; i < LIGHT_RIS_ITERS; i\+\+\) \{", "RisPointlights",
+                             "reservoir, v, f0, world_pos, n, roughness, metallic, albedo", prologue="float p_hat_pl = 0.0;", result="p_hat_pl",
+                             env=renv, defines={"LIGHT_RIS_ITERS": G.U32(32)})
+    assert (l0, l1) == (300, 309), (l0, l1)
+    n_ris = 64
+    ris_lights = np.zeros((16, 12), f32)
+    ris_lights[:, 0:3] = rng.uniform(0, 30, (16, 3)); ris_lights[:, 3] = 1
+    ris_lights[:, 4:7] = rng.uniform(-6, 6, (16, 3)); ris_lights[:, 7] = 1
+    ris_lights[:, 8:11] = [0.05, 0.25, 0.5]
+    renv["ssbo_light_data"] = G.namespace(num_pointlights=G.U32(16), pointlights=[
+        G.namespace(colour=ris_lights[k, 0:4], pos=ris_lights[k, 4:8], atten_exp=ris_lights[k, 8], atten_linear=ris_lights[k, 9], atten_constant=ris_lights[k, 10])
+        for k in range(16)])
+    ris_px = np.stack([rng.integers(1, 1920, n_ris), rng.integers(0, 1080, n_ris)], -1).astype(np.uint32)
+    ris_time = rng.uniform(0, 60000, n_ris).astype(f32)
+    ris_res = []
+    for r in range(n_ris):
+        renv["gl_LaunchIDEXT"] = np.array([ris_px[r, 0], ris_px[r, 1], 0], f32)
+        renv["common_ubo"] = G.namespace(time_elapsed=ris_time[r])
+        res_ = G.namespace(emissive_triangle=G.namespace()); renv["InitPixelReservoir"](res_)
+        p_hat = renv["RisPointlights"](res_, v[r], f0[r], world_pos[r], n[r], rough[r], metal[r], albedo[r])
+        ris_res.append([float(res_.w_sum_pl), int(res_.pl_idx), int(res_.pl_m), float(p_hat)])
+    out.update(ris_lights=ris_lights, ris_px=ris_px, ris_time=ris_time, ref_ris_pl=np.array(ris_res, np.float64))
     np.savez_compressed(os.path.join(GOLD, "reference_shader_vectors.npz"), **out)
 
 
