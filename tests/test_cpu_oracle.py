@@ -730,3 +730,27 @@ def test_pointlight_ris_loop_equals_the_executed_reference_shader(snk, oracle):
     # the chaotic RNG may turn a last-place difference into another pick now and then
     assert same >= n_ris - 2, f"selected light / p_hat differ on {n_ris - same} of {n_ris} surfaces"
     assert len(set(g["ref_ris_pl"][:, 1].tolist())) >= 8 and (g["ref_ris_pl"][:, 3] > 0).mean() > 0.8
+
+
+def test_triangle_radiance_equals_the_executed_reference_shader(snk, oracle):
+    """ComputeTriangleRadiance (RayGen.rgen:258-282, shadow_test = false) executed from the reference's shader text on the emissive
+    cubes of small_test_scene through the shader's own buffer indexing (instance -> indices -> vertices -> model matrix ->
+    material): emitted albedo * surface albedo * Cook-Torrance / squared distance, bary weights (x, y, 1-x-y) on (ti.x, ti.y, ti.z)."""
+    g = np.load(os.path.join(GOLD, "reference_shader_vectors.npz"))
+    sc = snk.scenes.small_test_scene(64, 48)
+    fr = oracle.OracleFrame(oracle.OracleScene(sc))
+    ubo = sc.ubo(0)
+    fr.set(ubo, ubo, oracle.default_settings())
+    L = oracle.lib()
+    n_tr = g["tri_obj"].shape[0]
+    exact = 0
+    for k in range(n_tr):
+        a = [np.ascontiguousarray(g[key][k], np.float32) for key in ("tri_v", "f0", "tri_surface_pos", "tri_n", "albedo")]
+        out = np.zeros(3, np.float32)
+        L.snkor_compute_triangle_radiance(fr.h, int(g["tri_obj"][k]), int(g["tri_tri"][k]), C.c_float(g["tri_bary"][k, 0]), C.c_float(g["tri_bary"][k, 1]),
+                                          fp(a[0]), fp(a[1]), fp(a[2]), fp(a[3]), C.c_float(g["roughness"][k]), C.c_float(g["metallic"][k]), fp(a[4]), fp(out))
+        want = g["ref_triangle_radiance"][k]
+        assert np.allclose(out, want, rtol=2e-5, atol=1e-12), (k, out, want)
+        exact += int(np.array_equal(out.view(np.uint32), want.view(np.uint32)))
+    assert (g["ref_triangle_radiance"].max(1) > 0).mean() > 0.9
+    assert exact >= n_tr // 2, f"only {exact} of {n_tr} radiances are bit-identical"

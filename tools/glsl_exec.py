@@ -83,19 +83,46 @@ class I32(int):
         return U32((int(self) & 0xFFFFFFFF) % int(o))
 
 
+class IVec(tuple):
+    """ivecN: component-wise addition"""
+    def __add__(self, o): return IVec(I32._w(int(a) + int(b)) for a, b in zip(self, o))
+
+
 def _ivec(n):
     def ctor(*a):
         parts = []
         for x in a:
             parts.extend(np.asarray(x).reshape(-1).tolist())
+        if len(parts) == 1:
+            parts = parts * n
         assert len(parts) == n
-        return tuple(I32._w(int(np.trunc(v))) for v in parts)  # float -> int conversion truncates
+        return IVec(I32._w(int(np.trunc(v))) for v in parts)  # float -> int conversion truncates
     return ctor
+
+
+class Mat:
+    """matN, column-major like GLSL: m[c] is column c. Products accumulate left to right in float32; inverse() goes through
+    float64 and is rounded once (the transposed inverse of the model matrix is a per-instance constant in this repository)"""
+    def __init__(self, cols): self.c = np.asarray(cols, F)  # c[col, row]
+    def __mul__(self, o):
+        if isinstance(o, Mat):
+            return Mat([self * o.c[k] for k in range(o.c.shape[0])])
+        v = np.asarray(o, F)
+        acc = (self.c[0] * v[0]).astype(F)
+        for k in range(1, self.c.shape[0]):
+            acc = (acc + (self.c[k] * v[k]).astype(F)).astype(F)
+        return acc
+
+
+U32.__truediv__ = lambda self, o: U32(int(self) // int(o)) if isinstance(o, int) else F(int(self)) / o  # uint / uint is integral
 
 
 U32.__mod__ = lambda self, o: U32(int(self) % int(o))
 BUILTINS.update({
     "ivec2": _ivec(2), "ivec3": _ivec(3),
+    "mat3": lambda m: Mat(m.c[:3, :3]),
+    "transpose": lambda m: Mat(m.c.T),
+    "inverse": lambda m: Mat(np.linalg.inv(m.c.astype(np.float64).T).T.astype(F)),
     "cross": lambda a, b: np.array([F(F(a[1] * b[2]) - F(b[1] * a[2])), F(F(a[2] * b[0]) - F(b[2] * a[0])), F(F(a[0] * b[1]) - F(b[0] * a[1]))], F),
     "distance": lambda a, b: _length(np.asarray(a, F) - np.asarray(b, F)),
     # the numerics contract of this repository for transcendental functions: float64 libm, rounded once (oracle/snk_math.h)
@@ -121,6 +148,8 @@ def _expr(e):
 
 def _stmt(st):
     st = re.sub(rf"^(?:const\s+)?{_TYPES}\s+(?=\w+\s*=)", "", st)
+    if not re.match(r"(return|else|if)\b", st):  # declaration with a struct type: `InstanceData instance = ...`
+        st = re.sub(r"^(?:const\s+)?[A-Za-z_]\w*\s+(?=[A-Za-z_]\w*\s*=[^=])", "", st)
     st = re.sub(r"^([\w\.\[\]]+)\+\+$", r"\1 += 1", st)
     st = re.sub(r"^([\w\.\[\]]+)--$", r"\1 -= 1", st)
     return _expr(st)

@@ -382,6 +382,38 @@ def reference_shader_vectors():
         p_hat = renv["RisPointlights"](res_, v[r], f0[r], world_pos[r], n[r], rough[r], metal[r], albedo[r])
         ris_res.append([float(res_.w_sum_pl), int(res_.pl_idx), int(res_.pl_m), float(p_hat)])
     out.update(ris_lights=ris_lights, ris_px=ris_px, ris_time=ris_time, ref_ris_pl=np.array(ris_res, np.float64))
+    # RayGen.rgen:258-282: ComputeTriangleRadiance (shadow_test = false) on the emissive cubes of small_test_scene, read through
+    # the shader's own buffer indexing (instances -> indices -> positions / normals -> model matrix -> material)
+    sc = snk_scenes.small_test_scene(64, 48)
+    flat = sc.flatten()
+    tenv = G.load_functions(os.path.join(REF, "Core/res/shaders/LightBuffers.glsl"), names[:5])
+    G.load_functions(os.path.join(REF, "Core/res/shaders/RayGen.rgen"), ["ComputeTriangleRadiance"], env=tenv)
+    u32 = G.U32
+    tenv["rt_instances"] = G.namespace(i=[G.namespace(transform_idx=u32(int(r_[0])), mesh_buffer_index_offset=u32(int(r_[1])), mesh_buffer_vertex_offset=u32(int(r_[2])),
+                                                      material_idx=u32(int(r_[3])), num_mesh_indices=u32(int(r_[4]))) for r_ in flat["instances"]])
+    tri_idx = flat["indices"].reshape(-1, 3)
+    tenv["indices"] = G.namespace(i=[G.IVec(G.I32(int(c)) for c in t) for t in tri_idx])
+    tenv["vert_positions"] = G.namespace(p=[row for row in flat["positions"]])
+    tenv["vert_normals"] = G.namespace(n=[row for row in flat["normals"]])
+    tenv["transforms"] = G.namespace(m=[G.Mat(np.asarray(t, f32).reshape(4, 4)) for t in flat["transforms"]])
+    tenv["material_ubo"] = G.namespace(materials=[G.namespace(albedo=np.asarray(sc.materials["albedo"][k], f32)) for k in range(sc.materials.shape[0])])
+    em = [int(e) for e in flat["emissive_idx"]]
+    assert em, "small_test_scene has emissive instances"
+    n_tr = 128
+    tr_obj = np.array([em[k % len(em)] for k in range(n_tr)], np.uint32)
+    tr_tri = np.array([rng.integers(0, int(flat["instances"][o][4]) // 3) for o in tr_obj], np.uint32)
+    tr_bary = rng.uniform(0, 0.5, (n_tr, 2)).astype(f32)
+    tr_pos = rng.uniform((-6, 0.2, -4), (6, 5, 4), (n_tr, 3)).astype(f32)
+    # surfaces that roughly face their light (centre of the cube = translation of its model matrix), so that most values are lit
+    centres = np.array([np.asarray(flat["transforms"][int(flat["instances"][o][0])], f32).reshape(4, 4)[3, :3] for o in tr_obj], f32)
+    tr_n = unit(centres - tr_pos + 0.6 * rng.normal(size=(n_tr, 3)))
+    tr_v = unit(tr_n + 0.7 * rng.normal(size=(n_tr, 3)))
+    ref_tr = []
+    for k in range(n_tr):
+        tdat = G.namespace(object_instance_idx=u32(int(tr_obj[k])), triangle_idx=u32(int(tr_tri[k])), bary_coords=tr_bary[k])
+        ref_tr.append(tenv["ComputeTriangleRadiance"](tdat, tr_v[k], f0[k], tr_pos[k], tr_n[k], rough[k], metal[k], albedo[k], tr_pos[k], False))
+    out.update(tri_obj=tr_obj, tri_tri=tr_tri, tri_bary=tr_bary, tri_surface_pos=tr_pos, tri_n=tr_n, tri_v=tr_v,
+               ref_triangle_radiance=np.asarray(ref_tr, f32))
     np.savez_compressed(os.path.join(GOLD, "reference_shader_vectors.npz"), **out)
 
 
