@@ -225,6 +225,18 @@ ORACLE_API float snkor_ris_pointlights(void* fp, uint32_t x, uint32_t y, const f
   *out = r;
   return p_hat;
 }
+// the emissive-triangle loop of DoInitialWRS on an explicit surface
+ORACLE_API float snkor_ris_emissives(void* fp, uint32_t x, uint32_t y, const float* v, const float* f0, const float* world_pos, const float* n,
+                                     float roughness, float metallic, const float* albedo, PixelReservoir* out) {
+  Frame& f = *(Frame*)fp;
+  Invocation inv(f, x, y, nullptr);
+  PixelReservoir r; Invocation::init_pixel_reservoir(r);
+  const vec3 wp = v3(world_pos[0], world_pos[1], world_pos[2]);
+  const float p_hat = inv.ris_emissives(r, v3(v[0], v[1], v[2]), v3(f0[0], f0[1], f0[2]), wp, v3(n[0], n[1], n[2]), roughness, metallic,
+                                        v3(albedo[0], albedo[1], albedo[2]), wp);
+  *out = r;
+  return p_hat;
+}
 // ComputeTriangleRadiance(…, shadow_test = false) for a point on an emissive triangle seen from an explicit surface
 ORACLE_API void snkor_compute_triangle_radiance(void* fp, uint32_t obj, uint32_t tri, float bx, float by, const float* v, const float* f0,
                                                 const float* world_pos, const float* n, float roughness, float metallic, const float* albedo,

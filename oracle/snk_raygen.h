@@ -344,11 +344,11 @@ struct Invocation {
     }
     return p_hat_pl;
   }
-  void do_initial_wrs(PixelReservoir& r, vec3 v, vec3 f0, vec3 world_pos, vec3 n, float roughness, float metallic, vec3 albedo, vec3 biased_pos) {
+  // RayGen.rgen:311-342: the emissive-triangle half of DoInitialWRS; returns p_hat of the selected triangle point
+  float ris_emissives(PixelReservoir& r, vec3 v, vec3 f0, vec3 world_pos, vec3 n, float roughness, float metallic, vec3 albedo, vec3 biased_pos) {
     float p_hat_em = 0.0f;
     const uint32_t iters = F.settings.ris_iters;
     const uint32_t n_em = (uint32_t)sc.emissive_idx.size();
-    const float p_hat_pl = ris_pointlights(r, v, f0, world_pos, n, roughness, metallic, albedo);
     for (uint32_t i = 0; i < iters; ++i) {
       if (n_em == 0) { r.m_em++; continue; }  // DEVIATION: reference reads idx[0] of an empty list
       const float wsum = (world_pos.x + world_pos.y) + world_pos.z;
@@ -370,6 +370,11 @@ struct Invocation {
       const float weight = p_hat / pdf;
       if (update_emissive_reservoir(r, obj, tri, bx, by, weight, sin_c((float)i * 38293.28347f))) p_hat_em = p_hat;
     }
+    return p_hat_em;
+  }
+  void do_initial_wrs(PixelReservoir& r, vec3 v, vec3 f0, vec3 world_pos, vec3 n, float roughness, float metallic, vec3 albedo, vec3 biased_pos) {
+    const float p_hat_pl = ris_pointlights(r, v, f0, world_pos, n, roughness, metallic, albedo);
+    const float p_hat_em = ris_emissives(r, v, f0, world_pos, n, roughness, metallic, albedo, biased_pos);
     if (r.pl_idx != INVALID) {
       const Pointlight& pl = L.pointlights[r.pl_idx];
       const vec3 lp = v3(pl.pos[0], pl.pos[1], pl.pos[2]);

@@ -754,3 +754,33 @@ def test_triangle_radiance_equals_the_executed_reference_shader(snk, oracle):
         exact += int(np.array_equal(out.view(np.uint32), want.view(np.uint32)))
     assert (g["ref_triangle_radiance"].max(1) > 0).mean() > 0.9
     assert exact >= n_tr // 2, f"only {exact} of {n_tr} radiances are bit-identical"
+
+
+def test_emissive_ris_loop_equals_the_executed_reference_shader(snk, oracle):
+    """The emissive-triangle loop of DoInitialWRS (RayGen.rgen:311-342) executed from the reference's shader text on
+    small_test_scene: emissive instance and triangle picks, random barycentrics with the flip, area = det(mat3(M)) / 2 * |cross|,
+    pdf = 1 / (N_em * N_tri * area), weight = p_hat / pdf, streaming update seeded by sin(i * 38293.28347). The oracle's loop must
+    end in the same reservoir (weight sum, instance, triangle, barycentrics, M) with the same p_hat."""
+    g = np.load(os.path.join(GOLD, "reference_shader_vectors.npz"))
+    sc = snk.scenes.small_test_scene(64, 48)
+    fr = oracle.OracleFrame(oracle.OracleScene(sc))
+    L = oracle.lib()
+    L.snkor_ris_emissives.restype = C.c_float
+    n_runs = g["em_px"].shape[0]
+    same = 0
+    for r in range(n_runs):
+        ubo = sc.ubo(0)
+        ubo["time_elapsed"] = g["em_time"][r]
+        fr.set(ubo, ubo, oracle.default_settings())
+        a = [np.ascontiguousarray(g[k][r], np.float32) for k in ("tri_v", "f0", "tri_surface_pos", "tri_n", "albedo")]
+        res = np.zeros((), snk.scenes.RESERVOIR_DTYPE)
+        p_hat = L.snkor_ris_emissives(fr.h, int(g["em_px"][r, 0]), int(g["em_px"][r, 1]), fp(a[0]), fp(a[1]), fp(a[2]), fp(a[3]),
+                                      C.c_float(g["roughness"][r]), C.c_float(g["metallic"][r]), fp(a[4]), fp(res))
+        w_sum, obj, tri, m, bx, by, ref_p_hat = g["ref_ris_em"][r]
+        assert int(res["m_em"]) == int(m) == 32
+        ok = (np.isclose(res["w_sum_em"], w_sum, rtol=5e-5) and (int(res["object_instance_idx"]), int(res["triangle_idx"])) == (int(obj), int(tri))
+              and np.allclose(res["bary"], [bx, by], rtol=0, atol=1e-7) and np.isclose(p_hat, ref_p_hat, rtol=5e-5))
+        same += int(ok)
+    # chaotic RNG: a last-place difference can change one pick of the 32 in a run
+    assert same >= n_runs - 3, f"{n_runs - same} of {n_runs} runs end in a different reservoir"
+    assert len(set(map(tuple, g["ref_ris_em"][:, 1:3].tolist()))) >= 10

@@ -70,6 +70,26 @@ class U32(int):
     __iadd__, __ixor__, __iand__, __ior__ = __add__, __xor__, __and__, __or__
 
 
+def _is_float(o):
+    return isinstance(o, (float, np.floating, np.ndarray))
+
+
+def _mixed(cls):
+    """int OP float converts the integer to float32 first (GLSL implicit conversion); numpy would promote an int SUBCLASS to float64"""
+    for op in ("add", "sub", "mul", "truediv"):
+        ident = getattr(cls, f"__{op}__")
+        def fwd(self, o, _op=op, _ident=ident):
+            if _is_float(o):
+                return getattr(F(int(self)), f"__{_op}__")(o if isinstance(o, np.ndarray) else F(o))
+            return _ident(self, o)
+        def rev(self, o, _op=op):
+            return getattr(F(o) if not isinstance(o, np.ndarray) else o, f"__{_op}__")(F(int(self)))
+        setattr(cls, f"__{op}__", fwd)
+        setattr(cls, f"__r{op}__", rev)
+    cls.__array_priority__ = 100  # numpy scalars / arrays defer to these reflected operators
+    return cls
+
+
 class I32(int):
     """GLSL int: 32-bit two's-complement wrap-around; mixed with a uint it converts to uint (GLSL 4.60 section 4.1.10)"""
     @staticmethod
@@ -114,7 +134,13 @@ class Mat:
         return acc
 
 
-U32.__truediv__ = lambda self, o: U32(int(self) // int(o)) if isinstance(o, int) else F(int(self)) / o  # uint / uint is integral
+U32.__truediv__ = lambda self, o: U32(int(self) // int(o))  # uint / uint is integral (floats are handled by _mixed)
+U32.__sub__ = lambda self, o: U32((int(self) - int(o)) & 0xFFFFFFFF)
+I32.__add__ = lambda self, o: I32._w(int(self) + int(o))
+I32.__sub__ = lambda self, o: I32._w(int(self) - int(o))
+I32.__truediv__ = lambda self, o: I32._w(int(int(self) / int(o)))  # truncating division
+_mixed(U32)
+_mixed(I32)
 
 
 U32.__mod__ = lambda self, o: U32(int(self) % int(o))
@@ -122,6 +148,7 @@ BUILTINS.update({
     "ivec2": _ivec(2), "ivec3": _ivec(3),
     "mat3": lambda m: Mat(m.c[:3, :3]),
     "transpose": lambda m: Mat(m.c.T),
+    "determinant": lambda m: F(np.linalg.det(m.c.astype(np.float64))),
     "inverse": lambda m: Mat(np.linalg.inv(m.c.astype(np.float64).T).T.astype(F)),
     "cross": lambda a, b: np.array([F(F(a[1] * b[2]) - F(b[1] * a[2])), F(F(a[2] * b[0]) - F(b[2] * a[0])), F(F(a[0] * b[1]) - F(b[0] * a[1]))], F),
     "distance": lambda a, b: _length(np.asarray(a, F) - np.asarray(b, F)),
@@ -150,6 +177,7 @@ def _stmt(st):
     st = re.sub(rf"^(?:const\s+)?{_TYPES}\s+(?=\w+\s*=)", "", st)
     if not re.match(r"(return|else|if)\b", st):  # declaration with a struct type: `InstanceData instance = ...`
         st = re.sub(r"^(?:const\s+)?[A-Za-z_]\w*\s+(?=[A-Za-z_]\w*\s*=[^=])", "", st)
+    st = re.sub(r"^[A-Z]\w*\s+([A-Za-z_]\w*)$", r"\1 = namespace()", st)  # `TriangleData triangle;`
     st = re.sub(r"^([\w\.\[\]]+)\+\+$", r"\1 += 1", st)
     st = re.sub(r"^([\w\.\[\]]+)--$", r"\1 -= 1", st)
     return _expr(st)
@@ -256,6 +284,7 @@ def load_functions(path, names, defines=None, env=None):
     env = dict(BUILTINS) if env is None else env
     env["U32"] = U32
     env["F"] = F
+    env["namespace"] = namespace
     for m in re.finditer(r"^#define\s+(\w+)\s+([0-9.]+)f?\s*$", text, re.M):
         env[m.group(1)] = F(float(m.group(2)))
     for m in re.finditer(r"^\s*const\s+float\s+(\w+)\s*=\s*([0-9.]+)f?\s*;", text, re.M):  # file-scope float constants
@@ -272,18 +301,19 @@ def load_functions(path, names, defines=None, env=None):
     return env
 
 
-def load_block(path, start_regex, name, params, prologue="", result="", env=None, defines=None):
+def load_block(path, start_regex, name, params, prologue="", result="", env=None, defines=None, occurrence=1):
     """a brace-delimited block INSIDE a function (the text from the match of `start_regex`, which must end at its `{`, to the
     matching `}`) as a function `name(params)`: `prologue` statements run first, `result` is returned"""
     text = open(path, encoding="utf-8", errors="replace").read()
-    m = re.search(start_regex, text)
-    assert m and text[m.end() - 1] == "{", f"block not found: {start_regex}"
+    ms = list(re.finditer(start_regex, text))
+    assert len(ms) >= occurrence and text[ms[occurrence - 1].end() - 1] == "{", f"block not found: {start_regex}"
+    m = ms[occurrence - 1]
     depth, i = 1, m.end()
     while depth:
         depth += {"{": 1, "}": -1}.get(text[i], 0)
         i += 1
     env = dict(BUILTINS) if env is None else env
-    env["U32"], env["F"] = U32, F
+    env["U32"], env["F"], env["namespace"] = U32, F, namespace
     env.update(defines or {})
     src = _translate(name, params, prologue + text[m.start():i])
     if result:

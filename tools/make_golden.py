@@ -414,6 +414,28 @@ def reference_shader_vectors():
         ref_tr.append(tenv["ComputeTriangleRadiance"](tdat, tr_v[k], f0[k], tr_pos[k], tr_n[k], rough[k], metal[k], albedo[k], tr_pos[k], False))
     out.update(tri_obj=tr_obj, tri_tri=tr_tri, tri_bary=tr_bary, tri_surface_pos=tr_pos, tri_n=tr_n, tri_v=tr_v,
                ref_triangle_radiance=np.asarray(ref_tr, f32))
+    # RayGen.rgen:311-342: the emissive-triangle loop of DoInitialWRS on the same scene: instance pick, triangle pick, random
+    # barycentrics with the flip, area = det(mat3(M)) / 2 * |cross|, pdf, weight, streaming update seeded by sin(i * 38293.28347)
+    G.load_functions(os.path.join(REF, "Core/res/shaders/Util.glsl"), ["gold_noise", "hash", "floatConstruct", "random"], env=tenv)
+    G.load_functions(os.path.join(REF, "Core/res/shaders/RayGen.rgen"), ["InitPixelReservoir", "UpdateEmissiveReservoir"],
+                     defines={"INVALID_RESERVOIR_IDX": G.U32(0xFFFFFFFF)}, env=tenv)
+    _, e0, e1 = G.load_block(os.path.join(REF, "Core/res/shaders/RayGen.rgen"), r"for \(uint i = 0u; i < LIGHT_RIS_ITERS; i\+\+\) \{", "RisEmissives",
+                             "reservoir, v, f0, world_pos, n, roughness, metallic, albedo, biased_pos", prologue="float p_hat_em = 0.0;", result="p_hat_em",
+                             env=tenv, defines={"LIGHT_RIS_ITERS": G.U32(32)}, occurrence=2)
+    assert (e0, e1) == (311, 342), (e0, e1)
+    tenv["rt_emissive_instance_indices"] = G.namespace(num_emissive_instances=u32(len(em)), i=[u32(e) for e in em])
+    n_em_runs = 48
+    em_px = np.stack([rng.integers(1, 1920, n_em_runs), rng.integers(0, 1080, n_em_runs)], -1).astype(np.uint32)
+    em_time = rng.uniform(0, 60000, n_em_runs).astype(f32)
+    em_res = []
+    for r in range(n_em_runs):
+        tenv["gl_LaunchIDEXT"] = np.array([em_px[r, 0], em_px[r, 1], 0], f32)
+        tenv["common_ubo"] = G.namespace(time_elapsed=em_time[r])
+        res_ = G.namespace(emissive_triangle=G.namespace(bary_coords=np.zeros(2, f32))); tenv["InitPixelReservoir"](res_)
+        p_hat = tenv["RisEmissives"](res_, tr_v[r], f0[r], tr_pos[r], tr_n[r], rough[r], metal[r], albedo[r], tr_pos[r])
+        et = res_.emissive_triangle
+        em_res.append([float(res_.w_sum_em), int(et.object_instance_idx), int(et.triangle_idx), int(res_.m_em), float(et.bary_coords[0]), float(et.bary_coords[1]), float(p_hat)])
+    out.update(em_px=em_px, em_time=em_time, ref_ris_em=np.array(em_res, np.float64))
     np.savez_compressed(os.path.join(GOLD, "reference_shader_vectors.npz"), **out)
 
 
