@@ -237,6 +237,18 @@ ORACLE_API float snkor_ris_emissives(void* fp, uint32_t x, uint32_t y, const flo
   *out = r;
   return p_hat;
 }
+// CombinePixelReservoir with every shadow ray visible: the merge arithmetic alone
+ORACLE_API void snkor_combine_visible(void* fp, uint32_t x, uint32_t y, PixelReservoir* cur, const PixelReservoir* nb, float* p_hat2, const float* v,
+                                      const float* f0, const float* world_pos, const float* n, float roughness, float metallic, const float* albedo,
+                                      const float* biased_pos, float rnd_seed) {
+  Frame& f = *(Frame*)fp;
+  Invocation inv(f, x, y, nullptr);
+  f.force_visible = true;
+  inv.combine_pixel_reservoir(*cur, *nb, p_hat2[0], p_hat2[1], v3(v[0], v[1], v[2]), v3(f0[0], f0[1], f0[2]), v3(world_pos[0], world_pos[1], world_pos[2]),
+                              v3(n[0], n[1], n[2]), roughness, metallic, v3(albedo[0], albedo[1], albedo[2]),
+                              v3(biased_pos[0], biased_pos[1], biased_pos[2]), rnd_seed);
+  f.force_visible = false;
+}
 // ComputeTriangleRadiance(…, shadow_test = false) for a point on an emissive triangle seen from an explicit surface
 ORACLE_API void snkor_compute_triangle_radiance(void* fp, uint32_t obj, uint32_t tri, float bx, float by, const float* v, const float* f0,
                                                 const float* world_pos, const float* n, float roughness, float metallic, const float* albedo,

@@ -150,6 +150,7 @@ struct Frame {
   std::vector<float> direct_rgba;          // dir light + reservoir radiance (pass-2 `light`)
   std::atomic<uint64_t> rays_closest{0}, rays_any{0};
   mat4 ivp{};
+  bool force_visible = false;  // tests only: every shadow ray reports 'visible' (function-level checks against the executed shader text)
   void resize(uint32_t w, uint32_t h) {
     g.resize(w, h);
     PixelReservoir e{}; e.pl_idx = INVALID; e.object_instance_idx = INVALID; e.triangle_idx = INVALID;
@@ -186,6 +187,7 @@ struct Invocation {
   // RayGen.rgen:101-121 / RayClosestHit.rchit:64-84
   float shadow_test(vec3 ro, vec3 rd, float max_dist) {
     ++n_any;
+    if (F.force_visible) return 1.0f;
     Ray r{{ro.x, ro.y, ro.z}, 0.001f, {rd.x, rd.y, rd.z}, max_dist};
     Hit h = sc.trace(r, true);
     return 1.0f - (h.t >= 0.0f ? 1.0f : 0.0f);

@@ -784,3 +784,44 @@ def test_emissive_ris_loop_equals_the_executed_reference_shader(snk, oracle):
     # chaotic RNG: a last-place difference can change one pick of the 32 in a run
     assert same >= n_runs - 3, f"{n_runs - same} of {n_runs} runs end in a different reservoir"
     assert len(set(map(tuple, g["ref_ris_em"][:, 1:3].tolist()))) >= 10
+
+
+def test_combine_pixel_reservoir_equals_the_executed_reference_shader(snk, oracle):
+    """CombinePixelReservoir (RayGen.rgen:359-386) — the merge step of temporal and spatial reuse — executed from the reference's
+    shader text with ShadowTest stubbed to 'visible' (the oracle runs with Frame::force_visible): p_hat of the neighbour's samples
+    at the receiving surface, weight = p_hat * M * W (point light) / p_hat * W * M (emissive), the update seeds. 96 merges of random
+    current / neighbour reservoirs, 15 % of them with an invalid point-light or emissive sample."""
+    g = np.load(os.path.join(GOLD, "reference_shader_vectors.npz"))
+    sc = snk.scenes.small_test_scene(64, 48)
+    fr = oracle.OracleFrame(oracle.OracleScene(sc))
+    L = oracle.lib()
+    n_cb, n_tr = g["cb_px"].shape[0], g["tri_obj"].shape[0]
+    RD = snk.scenes.RESERVOIR_DTYPE
+
+    def pack(vals):
+        r = np.zeros((), RD)
+        r["w_sum_pl"], r["w_pl"], r["pl_idx"], r["pl_m"] = vals[0], vals[1], int(vals[2]), int(vals[3])
+        r["object_instance_idx"], r["triangle_idx"], r["bary"] = int(vals[4]), int(vals[5]), vals[6:8]
+        r["w_sum_em"], r["w_em"], r["m_em"] = vals[8], vals[9], int(vals[10])
+        return r
+
+    same = exact = 0
+    for k in range(n_cb):
+        ubo = sc.ubo(0)
+        ubo["time_elapsed"] = g["cb_time"][k]
+        fr.set(ubo, ubo, oracle.default_settings())
+        cur, nb = pack(g["cb_in"][k, 0]), pack(g["cb_in"][k, 1])
+        ph = np.ascontiguousarray(g["cb_phat_in"][k], np.float32).copy()
+        j = k % n_tr
+        a = [np.ascontiguousarray(g[key][j], np.float32) for key in ("tri_v", "f0", "tri_surface_pos", "tri_n", "albedo")]
+        L.snkor_combine_visible(fr.h, int(g["cb_px"][k, 0]), int(g["cb_px"][k, 1]), fp(cur), fp(nb), fp(ph), fp(a[0]), fp(a[1]), fp(a[2]), fp(a[3]),
+                                C.c_float(g["roughness"][j]), C.c_float(g["metallic"][j]), fp(a[4]), fp(a[2]), C.c_float(g["cb_seed"][k]))
+        want, want_ph = pack(g["ref_cb_out"][k]), g["ref_cb_phat"][k].astype(np.float32)
+        assert int(cur["pl_m"]) == int(want["pl_m"]) and int(cur["m_em"]) == int(want["m_em"]), k
+        ok = (int(cur["pl_idx"]) == int(want["pl_idx"]) and (int(cur["object_instance_idx"]), int(cur["triangle_idx"])) == (int(want["object_instance_idx"]), int(want["triangle_idx"]))
+              and np.isclose(cur["w_sum_pl"], want["w_sum_pl"], rtol=2e-5) and np.isclose(cur["w_sum_em"], want["w_sum_em"], rtol=2e-5)
+              and np.allclose(ph, want_ph, rtol=2e-5) and np.array_equal(cur["bary"], want["bary"]))
+        same += int(ok)
+        exact += int(ok and cur["w_sum_pl"] == want["w_sum_pl"] and cur["w_sum_em"] == want["w_sum_em"] and np.array_equal(ph, want_ph))
+    assert same >= n_cb - 2, f"{n_cb - same} of {n_cb} merges differ"
+    assert exact >= n_cb // 2, f"only {exact} of {n_cb} merges are bit-identical"

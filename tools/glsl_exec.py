@@ -204,10 +204,13 @@ def _translate(name, params, body):
     for p in params.split(","):
         p = p.strip()
         if p:
-            if p.split()[0] == "out":
-                outs.append(p.split()[-1])  # `out` parameters are returned (as a tuple, in declaration order); `inout` structs are mutated
+            toks = p.split()
+            if toks[0] == "out":
+                outs.append(toks[-1])  # `out` parameters are returned (as a tuple, in declaration order); `inout` structs are mutated
             else:
-                args.append(p.split()[-1])
+                args.append(toks[-1])
+                if toks[0] == "inout" and re.fullmatch(_TYPES, toks[1]):
+                    outs.append(toks[-1])  # scalars / vectors passed `inout` come back in the returned tuple as well
     lines = [f"def {name}({', '.join(args)}):"]
     body = re.sub(r"//[^\n]*", "", body)
     body = re.sub(r"\btrue\b", "True", re.sub(r"\bfalse\b", "False", body))

@@ -436,6 +436,44 @@ def reference_shader_vectors():
         et = res_.emissive_triangle
         em_res.append([float(res_.w_sum_em), int(et.object_instance_idx), int(et.triangle_idx), int(res_.m_em), float(et.bary_coords[0]), float(et.bary_coords[1]), float(p_hat)])
     out.update(em_px=em_px, em_time=em_time, ref_ris_em=np.array(em_res, np.float64))
+    # RayGen.rgen:359-386: CombinePixelReservoir with every shadow ray visible (ShadowTest stubbed to 1): the merge arithmetic of
+    # temporal and spatial reuse — p_hat at the receiving surface, weight = p_hat * M * W (and p_hat * W * M), the seeds
+    G.load_functions(os.path.join(REF, "Core/res/shaders/LightBuffers.glsl"), ["CalcPointlight"], env=tenv)
+    tenv["ShadowTest"] = lambda ro, rd, max_dist: f32(1.0)
+    G.load_functions(os.path.join(REF, "Core/res/shaders/RayGen.rgen"), ["UpdatePointlightReservoir", "CombinePixelReservoir"], env=tenv)
+    spl = np.asarray(sc.pointlights, f32)
+    tenv["ssbo_light_data"] = G.namespace(num_pointlights=u32(spl.shape[0]), pointlights=[
+        G.namespace(colour=spl[k, 0:4], pos=spl[k, 4:8], atten_exp=spl[k, 8], atten_linear=spl[k, 9], atten_constant=spl[k, 10]) for k in range(spl.shape[0])])
+    n_cb = 96
+    INV = 0xFFFFFFFF
+    cb_px = np.stack([rng.integers(1, 1920, n_cb), rng.integers(0, 1080, n_cb)], -1).astype(np.uint32)
+    cb_time = rng.uniform(0, 60000, n_cb).astype(f32)
+    cb_seed = rng.uniform(0, 1, n_cb).astype(f32)
+    cb_in = np.zeros((n_cb, 2, 11), np.float64)  # per reservoir (current, neighbour): w_sum_pl w_pl pl_idx pl_m obj tri bx by w_sum_em w_em m_em
+    cb_phat = rng.uniform(0, 0.5, (n_cb, 2)).astype(f32)
+    cb_out, cb_phat_out = [], []
+    for k in range(n_cb):
+        rs = []
+        for which in range(2):
+            has_pl, has_em = rng.uniform() < 0.85, rng.uniform() < 0.85
+            o = em[int(rng.integers(0, len(em)))]
+            vals = [f32(rng.uniform(0, 3)), f32(rng.uniform(0, 2)), int(rng.integers(0, spl.shape[0])) if has_pl else INV, int(rng.integers(1, 40)),
+                    o if has_em else INV, int(rng.integers(0, int(flat["instances"][o][4]) // 3)) if has_em else INV, f32(rng.uniform(0, 0.5)), f32(rng.uniform(0, 0.5)),
+                    f32(rng.uniform(0, 0.2)), f32(rng.uniform(0, 30)), int(rng.integers(1, 40))]
+            cb_in[k, which] = vals
+            rs.append(G.namespace(w_sum_pl=f32(vals[0]), w_pl=f32(vals[1]), pl_idx=u32(vals[2]), pl_m=u32(vals[3]),
+                                  emissive_triangle=G.namespace(object_instance_idx=u32(vals[4]), triangle_idx=u32(vals[5]), bary_coords=np.array(vals[6:8], f32)),
+                                  w_sum_em=f32(vals[8]), w_em=f32(vals[9]), m_em=u32(vals[10])))
+        tenv["gl_LaunchIDEXT"] = np.array([cb_px[k, 0], cb_px[k, 1], 0], f32)
+        tenv["common_ubo"] = G.namespace(time_elapsed=cb_time[k])
+        j = k % n_tr
+        ph = tenv["CombinePixelReservoir"](rs[0], rs[1], cb_phat[k, 0], cb_phat[k, 1], tr_v[j], f0[j], tr_pos[j], tr_n[j], rough[j], metal[j], albedo[j], tr_pos[j], cb_seed[k])
+        c, et = rs[0], rs[0].emissive_triangle
+        cb_out.append([float(c.w_sum_pl), float(c.w_pl), int(c.pl_idx), int(c.pl_m), int(et.object_instance_idx), int(et.triangle_idx),
+                       float(et.bary_coords[0]), float(et.bary_coords[1]), float(c.w_sum_em), float(c.w_em), int(c.m_em)])
+        cb_phat_out.append([float(ph[0]), float(ph[1])])
+    out.update(cb_px=cb_px, cb_time=cb_time, cb_seed=cb_seed, cb_in=cb_in, cb_phat_in=cb_phat, ref_cb_out=np.array(cb_out, np.float64),
+               ref_cb_phat=np.array(cb_phat_out, np.float64))
     np.savez_compressed(os.path.join(GOLD, "reference_shader_vectors.npz"), **out)
 
 
