@@ -249,6 +249,18 @@ ORACLE_API void snkor_combine_visible(void* fp, uint32_t x, uint32_t y, PixelRes
                               v3(biased_pos[0], biased_pos[1], biased_pos[2]), rnd_seed);
   f.force_visible = false;
 }
+// CalculateRadianceFromReservoirs with every shadow ray visible
+ORACLE_API void snkor_reservoir_radiance_visible(void* fp, const PixelReservoir* r, const float* v, const float* f0, const float* ro, const float* n,
+                                                 const float* rma, const float* albedo, const float* biased_pos, float* out3) {
+  Frame& f = *(Frame*)fp;
+  Invocation inv(f, 0, 0, nullptr);
+  f.force_visible = true;
+  const vec3 c = inv.radiance_from_reservoirs(*r, v3(v[0], v[1], v[2]), v3(f0[0], f0[1], f0[2]), v3(ro[0], ro[1], ro[2]), v3(n[0], n[1], n[2]),
+                                              v3(rma[0], rma[1], rma[2]), v3(albedo[0], albedo[1], albedo[2]),
+                                              v3(biased_pos[0], biased_pos[1], biased_pos[2]));
+  f.force_visible = false;
+  out3[0] = c.x; out3[1] = c.y; out3[2] = c.z;
+}
 // ComputeTriangleRadiance(…, shadow_test = false) for a point on an emissive triangle seen from an explicit surface
 ORACLE_API void snkor_compute_triangle_radiance(void* fp, uint32_t obj, uint32_t tri, float bx, float by, const float* v, const float* f0,
                                                 const float* world_pos, const float* n, float roughness, float metallic, const float* albedo,

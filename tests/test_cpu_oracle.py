@@ -825,3 +825,31 @@ def test_combine_pixel_reservoir_equals_the_executed_reference_shader(snk, oracl
         exact += int(ok and cur["w_sum_pl"] == want["w_sum_pl"] and cur["w_sum_em"] == want["w_sum_em"] and np.array_equal(ph, want_ph))
     assert same >= n_cb - 2, f"{n_cb - same} of {n_cb} merges differ"
     assert exact >= n_cb // 2, f"only {exact} of {n_cb} merges are bit-identical"
+
+
+def test_reservoir_final_shading_equals_the_executed_reference_shader(snk, oracle):
+    """CalculateRadianceFromReservoirs (RayGen.rgen:508-528) executed from the reference's shader text, visibility stubbed on both
+    sides: CalcPointlight * W of the point-light sample + ComputeTriangleRadiance * W of the emissive sample, invalid samples skipped."""
+    g = np.load(os.path.join(GOLD, "reference_shader_vectors.npz"))
+    sc = snk.scenes.small_test_scene(64, 48)
+    fr = oracle.OracleFrame(oracle.OracleScene(sc))
+    ubo = sc.ubo(0)
+    fr.set(ubo, ubo, oracle.default_settings())
+    L = oracle.lib()
+    n_cb, n_tr = g["cb_in"].shape[0], g["tri_obj"].shape[0]
+    exact = 0
+    for k in range(n_cb):
+        vals = g["cb_in"][k, 1]
+        r = np.zeros((), snk.scenes.RESERVOIR_DTYPE)
+        r["w_sum_pl"], r["w_pl"], r["pl_idx"], r["pl_m"] = vals[0], vals[1], int(vals[2]), int(vals[3])
+        r["object_instance_idx"], r["triangle_idx"], r["bary"] = int(vals[4]), int(vals[5]), vals[6:8]
+        r["w_sum_em"], r["w_em"], r["m_em"] = vals[8], vals[9], int(vals[10])
+        j = k % n_tr
+        a = [np.ascontiguousarray(g[key][j], np.float32) for key in ("tri_v", "f0", "tri_surface_pos", "tri_n", "albedo")]
+        rma = np.array([g["roughness"][j], g["metallic"][j], 1.0], np.float32)
+        out = np.zeros(3, np.float32)
+        L.snkor_reservoir_radiance_visible(fr.h, fp(r), fp(a[0]), fp(a[1]), fp(a[2]), fp(a[3]), fp(rma), fp(a[4]), fp(a[2]), fp(out))
+        want = g["ref_reservoir_radiance"][k]
+        assert np.allclose(out, want, rtol=3e-5, atol=1e-10), (k, out, want)
+        exact += int(np.array_equal(out.view(np.uint32), want.view(np.uint32)))
+    assert exact >= n_cb // 2 and (g["ref_reservoir_radiance"].max(1) > 0).mean() > 0.8

@@ -474,6 +474,20 @@ def reference_shader_vectors():
         cb_phat_out.append([float(ph[0]), float(ph[1])])
     out.update(cb_px=cb_px, cb_time=cb_time, cb_seed=cb_seed, cb_in=cb_in, cb_phat_in=cb_phat, ref_cb_out=np.array(cb_out, np.float64),
                ref_cb_phat=np.array(cb_phat_out, np.float64))
+    # RayGen.rgen:508-528: CalculateRadianceFromReservoirs (final shading of the two reservoir samples), visibility stubbed
+    tenv["textureSize"] = lambda sampler, lod: G.IVec((G.I32(64), G.I32(48)))
+    tenv["sampler_pixel_motion"] = None
+    G.load_functions(os.path.join(REF, "Core/res/shaders/RayGen.rgen"), ["CalculateRadianceFromReservoirs"], env=tenv)
+    ref_rad = []
+    for k in range(n_cb):
+        vals = cb_in[k, 1]
+        rsv = G.namespace(w_sum_pl=f32(vals[0]), w_pl=f32(vals[1]), pl_idx=u32(int(vals[2])), pl_m=u32(int(vals[3])),
+                          emissive_triangle=G.namespace(object_instance_idx=u32(int(vals[4])), triangle_idx=u32(int(vals[5])), bary_coords=np.array(vals[6:8], f32)),
+                          w_sum_em=f32(vals[8]), w_em=f32(vals[9]), m_em=u32(int(vals[10])))
+        j = k % n_tr
+        rma = np.array([rough[j], metal[j], 1.0], f32)
+        ref_rad.append(tenv["CalculateRadianceFromReservoirs"](rsv, tr_v[j], f0[j], tr_pos[j], tr_n[j], rma, albedo[j], tr_pos[j]))
+    out["ref_reservoir_radiance"] = np.asarray(ref_rad, f32)
     np.savez_compressed(os.path.join(GOLD, "reference_shader_vectors.npz"), **out)
 
 
