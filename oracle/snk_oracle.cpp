@@ -261,6 +261,11 @@ ORACLE_API void snkor_reservoir_radiance_visible(void* fp, const PixelReservoir*
   f.force_visible = false;
   out3[0] = c.x; out3[1] = c.y; out3[2] = c.z;
 }
+ORACLE_API void snkor_find_neighbour(void* fp, uint32_t x, uint32_t y, float sx, float sy, float radius, float seed_x, float seed_y, float* out2) {
+  Frame& f = *(Frame*)fp;
+  Invocation inv(f, x, y, nullptr);
+  inv.find_neighbour_pixel_coord(sx, sy, radius, seed_x, seed_y, out2[0], out2[1]);
+}
 // ComputeTriangleRadiance(…, shadow_test = false) for a point on an emissive triangle seen from an explicit surface
 ORACLE_API void snkor_compute_triangle_radiance(void* fp, uint32_t obj, uint32_t tri, float bx, float by, const float* v, const float* f0,
                                                 const float* world_pos, const float* n, float roughness, float metallic, const float* albedo,

@@ -853,3 +853,26 @@ def test_reservoir_final_shading_equals_the_executed_reference_shader(snk, oracl
         assert np.allclose(out, want, rtol=3e-5, atol=1e-10), (k, out, want)
         exact += int(np.array_equal(out.view(np.uint32), want.view(np.uint32)))
     assert exact >= n_cb // 2 and (g["ref_reservoir_radiance"].max(1) > 0).mean() > 0.8
+
+
+def test_find_neighbour_equals_the_executed_reference_shader(snk, oracle):
+    """FindNeighbourPixelCoord (RayGen.rgen:390-409) executed from the reference's shader text: a gold_noise offset within the 30-pixel
+    radius, re-drawn (pixel + i, seed + sin(i * 293.28937)) until the coordinate lies on the screen. Chaotic RNG: nearly all of the
+    128 coordinates must be bit-identical, all must lie in [0, 1]."""
+    g = np.load(os.path.join(GOLD, "reference_shader_vectors.npz"))
+    sc = snk.scenes.small_test_scene(64, 48)
+    fr = oracle.OracleFrame(oracle.OracleScene(sc))
+    L = oracle.lib()
+    n_fn = g["fn_px"].shape[0]
+    same = 0
+    for k in range(n_fn):
+        ubo = sc.ubo(0)
+        ubo["time_elapsed"] = g["fn_time"][k]
+        fr.set(ubo, ubo, oracle.default_settings())
+        o2 = np.zeros(2, np.float32)
+        L.snkor_find_neighbour(fr.h, int(g["fn_px"][k, 0]), int(g["fn_px"][k, 1]), C.c_float(g["fn_start"][k, 0]), C.c_float(g["fn_start"][k, 1]), C.c_float(30.0),
+                               C.c_float(g["fn_seed"][k, 0]), C.c_float(g["fn_seed"][k, 1]), fp(o2))
+        assert (o2 >= 0).all() and (o2 <= 1).all()
+        same += int(np.array_equal(o2.view(np.uint32), g["ref_find_neighbour"][k].view(np.uint32)))
+    assert same >= 0.95 * n_fn, f"only {same} of {n_fn} neighbour coordinates are bit-identical"
+    assert (np.abs(g["ref_find_neighbour"] - g["fn_start"]) <= np.array([30.0 / 64, 30.0 / 48]) + 1e-6).all()

@@ -7,7 +7,7 @@ numpy helpers with the same operation order) and returns them. Nothing of the sh
 generator (tools/make_golden.py) commits only the numeric input / output vectors.
 
 Supported subset: functions whose body consists of declarations, assignments, compound assignments, `++`, `if` / `else` (single
-statements or blocks, nested), counted `for (uint i = a; cond; i++)` loops and returns; scalar / vec3 / vec4 float arithmetic and 32-bit unsigned arithmetic; struct parameters and the `ssbo_light_data` block as attribute access; the built-ins listed in BUILTINS.
+statements or blocks, nested), counted `for (uint i = a; cond; i++)` loops, `while` loops and returns; scalar / vec3 / vec4 float arithmetic and 32-bit unsigned arithmetic; struct parameters and the `ssbo_light_data` block as attribute access; the built-ins listed in BUILTINS.
 """
 import re
 import types
@@ -148,6 +148,8 @@ BUILTINS.update({
     "ivec2": _ivec(2), "ivec3": _ivec(3),
     "mat3": lambda m: Mat(m.c[:3, :3]),
     "transpose": lambda m: Mat(m.c.T),
+    "any": lambda b: bool(np.any(b)), "lessThan": lambda a, b: np.asarray(a, F) < np.asarray(b, F),
+    "greaterThan": lambda a, b: np.asarray(a, F) > np.asarray(b, F),
     "determinant": lambda m: F(np.linalg.det(m.c.astype(np.float64))),
     "inverse": lambda m: Mat(np.linalg.inv(m.c.astype(np.float64).T).T.astype(F)),
     "cross": lambda a, b: np.array([F(F(a[1] * b[2]) - F(b[1] * a[2])), F(F(a[2] * b[0]) - F(b[2] * a[0])), F(F(a[0] * b[1]) - F(b[0] * a[1]))], F),
@@ -242,7 +244,14 @@ def _translate(name, params, body):
                     prefix += f"if {_cond(cond)}: "
                 emit(prefix + _stmt(st))
             elif ch == "{":
-                assert not re.match(r"(while|switch|do)\b", st), f"{name}: unsupported control flow: {st}"
+                assert not re.match(r"(switch|do)\b", st), f"{name}: unsupported control flow: {st}"
+                if st.startswith("while"):
+                    emit(f"while {_cond(_split_paren(st)[0])}:")
+                    epilogue.append(None)
+                    indent += 1
+                    emitted.append(0)
+                    cur = ""
+                    continue
                 m_for = re.match(r"for\s*\(\s*(?:uint|int)\s+(\w+)\s*=\s*([^;]+);\s*([^;]+);\s*(\w+)\+\+\s*\)$", st)
                 if st.startswith("for"):
                     assert m_for and m_for.group(1) == m_for.group(4), f"{name}: only `for (uint i = a; cond; i++)` is supported: {st}"

@@ -488,6 +488,19 @@ def reference_shader_vectors():
         rma = np.array([rough[j], metal[j], 1.0], f32)
         ref_rad.append(tenv["CalculateRadianceFromReservoirs"](rsv, tr_v[j], f0[j], tr_pos[j], tr_n[j], rma, albedo[j], tr_pos[j]))
     out["ref_reservoir_radiance"] = np.asarray(ref_rad, f32)
+    # RayGen.rgen:390-409: FindNeighbourPixelCoord (random offset within the radius, re-drawn until it lies on the screen)
+    G.load_functions(os.path.join(REF, "Core/res/shaders/RayGen.rgen"), ["FindNeighbourPixelCoord"], env=tenv)
+    n_fn = 128
+    fn_px = np.stack([rng.integers(1, 64, n_fn), rng.integers(0, 48, n_fn)], -1).astype(np.uint32)
+    fn_time = rng.uniform(0, 60000, n_fn).astype(f32)
+    fn_seed = rng.uniform(-1, 1, (n_fn, 2)).astype(f32)
+    fn_start = ((fn_px.astype(f32) + f32(0.5)) / np.array([64, 48], f32)).astype(f32)
+    ref_fn = []
+    for k in range(n_fn):
+        tenv["gl_LaunchIDEXT"] = np.array([fn_px[k, 0], fn_px[k, 1], 0], f32)
+        tenv["common_ubo"] = G.namespace(time_elapsed=fn_time[k])
+        ref_fn.append(tenv["FindNeighbourPixelCoord"](fn_start[k], f32(30.0), fn_seed[k]))
+    out.update(fn_px=fn_px, fn_time=fn_time, fn_seed=fn_seed, fn_start=fn_start, ref_find_neighbour=np.asarray(ref_fn, f32))
     np.savez_compressed(os.path.join(GOLD, "reference_shader_vectors.npz"), **out)
 
 
