@@ -266,6 +266,16 @@ ORACLE_API void snkor_find_neighbour(void* fp, uint32_t x, uint32_t y, float sx,
   Invocation inv(f, x, y, nullptr);
   inv.find_neighbour_pixel_coord(sx, sy, radius, seed_x, seed_y, out2[0], out2[1]);
 }
+// the tail of DoInitialWRS with visibility forced: W of both samples and the two shadow rays it asks for (rays7: origin, dir, max)
+ORACLE_API uint32_t snkor_finish_initial_wrs(void* fp, PixelReservoir* r, const float* biased_pos, float p_hat_pl, float p_hat_em, float* rays7x2) {
+  Frame& f = *(Frame*)fp;
+  Invocation inv(f, 0, 0, nullptr);
+  f.force_visible = true; f.n_forced = 0;
+  inv.finish_initial_wrs(*r, v3(biased_pos[0], biased_pos[1], biased_pos[2]), p_hat_pl, p_hat_em);
+  f.force_visible = false;
+  memcpy(rays7x2, f.forced_rays, sizeof(float) * 14);
+  return f.n_forced;
+}
 // ComputeTriangleRadiance(…, shadow_test = false) for a point on an emissive triangle seen from an explicit surface
 ORACLE_API void snkor_compute_triangle_radiance(void* fp, uint32_t obj, uint32_t tri, float bx, float by, const float* v, const float* f0,
                                                 const float* world_pos, const float* n, float roughness, float metallic, const float* albedo,

@@ -151,6 +151,8 @@ struct Frame {
   std::atomic<uint64_t> rays_closest{0}, rays_any{0};
   mat4 ivp{};
   bool force_visible = false;  // tests only: every shadow ray reports 'visible' (function-level checks against the executed shader text)
+  float forced_rays[4][7] = {};  // ... and the last shadow rays asked for are kept: origin, direction, max distance
+  uint32_t n_forced = 0;
   void resize(uint32_t w, uint32_t h) {
     g.resize(w, h);
     PixelReservoir e{}; e.pl_idx = INVALID; e.object_instance_idx = INVALID; e.triangle_idx = INVALID;
@@ -187,7 +189,11 @@ struct Invocation {
   // RayGen.rgen:101-121 / RayClosestHit.rchit:64-84
   float shadow_test(vec3 ro, vec3 rd, float max_dist) {
     ++n_any;
-    if (F.force_visible) return 1.0f;
+    if (F.force_visible) {
+      float* q = F.forced_rays[F.n_forced++ & 3u];
+      q[0] = ro.x; q[1] = ro.y; q[2] = ro.z; q[3] = rd.x; q[4] = rd.y; q[5] = rd.z; q[6] = max_dist;
+      return 1.0f;
+    }
     Ray r{{ro.x, ro.y, ro.z}, 0.001f, {rd.x, rd.y, rd.z}, max_dist};
     Hit h = sc.trace(r, true);
     return 1.0f - (h.t >= 0.0f ? 1.0f : 0.0f);
@@ -377,6 +383,10 @@ struct Invocation {
   void do_initial_wrs(PixelReservoir& r, vec3 v, vec3 f0, vec3 world_pos, vec3 n, float roughness, float metallic, vec3 albedo, vec3 biased_pos) {
     const float p_hat_pl = ris_pointlights(r, v, f0, world_pos, n, roughness, metallic, albedo);
     const float p_hat_em = ris_emissives(r, v, f0, world_pos, n, roughness, metallic, albedo, biased_pos);
+    finish_initial_wrs(r, biased_pos, p_hat_pl, p_hat_em);
+  }
+  // RayGen.rgen:344-356: visibility-tested W of the two selected samples
+  void finish_initial_wrs(PixelReservoir& r, vec3 biased_pos, float p_hat_pl, float p_hat_em) {
     if (r.pl_idx != INVALID) {
       const Pointlight& pl = L.pointlights[r.pl_idx];
       const vec3 lp = v3(pl.pos[0], pl.pos[1], pl.pos[2]);

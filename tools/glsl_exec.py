@@ -334,5 +334,19 @@ def load_block(path, start_regex, name, params, prologue="", result="", env=None
     return env, text.count("\n", 0, m.start()) + 1, text.count("\n", 0, i) + 1
 
 
+def load_lines(path, first_line, last_line, must_start_with, name, params, result="", env=None, defines=None):
+    """lines first_line..last_line (1-based, inclusive) of a function body as a function `name(params)`"""
+    lines = open(path, encoding="utf-8", errors="replace").read().split("\n")
+    assert lines[first_line - 1].strip().startswith(must_start_with), lines[first_line - 1]
+    env = dict(BUILTINS) if env is None else env
+    env["U32"], env["F"], env["namespace"] = U32, F, namespace
+    env.update(defines or {})
+    src = _translate(name, params, "\n".join(lines[first_line - 1:last_line]))
+    if result:
+        src += f"\n    return {result}"
+    exec(src, env)  # noqa: S102
+    return env
+
+
 def namespace(**kw):
     return types.SimpleNamespace(**kw)

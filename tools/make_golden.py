@@ -501,6 +501,26 @@ def reference_shader_vectors():
         tenv["common_ubo"] = G.namespace(time_elapsed=fn_time[k])
         ref_fn.append(tenv["FindNeighbourPixelCoord"](fn_start[k], f32(30.0), fn_seed[k]))
     out.update(fn_px=fn_px, fn_time=fn_time, fn_seed=fn_seed, fn_start=fn_start, ref_find_neighbour=np.asarray(ref_fn, f32))
+    # RayGen.rgen:344-356: the tail of DoInitialWRS — W of the two selected samples and the shadow rays it asks for, including the
+    # point-light direction `pos - biased_pos / pl_dist` as written (operator precedence: not a unit vector)
+    G.load_functions(os.path.join(REF, "Core/res/shaders/RayGen.rgen"), ["TriangleShadowTest"], env=tenv)
+    G.load_lines(os.path.join(REF, "Core/res/shaders/RayGen.rgen"), 344, 356, "if (reservoir.pl_idx != INVALID_RESERVOIR_IDX)", "WrsTail",
+                 "reservoir, biased_pos, p_hat_pl, p_hat_em", env=tenv)
+    asked = []
+    tenv["ShadowTest"] = lambda ro, rd, max_dist: (asked.append(np.concatenate([ro, rd, [max_dist]]).astype(f32)), f32(1.0))[1]
+    ref_tail, ref_rays, ref_nrays = [], [], []
+    for k in range(n_cb):
+        vals = cb_in[k, 0]
+        rsv = G.namespace(w_sum_pl=f32(vals[0]), w_pl=f32(vals[1]), pl_idx=u32(int(vals[2])), pl_m=u32(int(vals[3])),
+                          emissive_triangle=G.namespace(object_instance_idx=u32(int(vals[4])), triangle_idx=u32(int(vals[5])), bary_coords=np.array(vals[6:8], f32)),
+                          w_sum_em=f32(vals[8]), w_em=f32(vals[9]), m_em=u32(int(vals[10])))
+        del asked[:]
+        tenv["WrsTail"](rsv, tr_pos[k % n_tr], cb_phat[k, 0] + f32(0.01), cb_phat[k, 1] + f32(0.01))
+        ref_tail.append([float(rsv.w_pl), float(rsv.w_em)])
+        ref_nrays.append(len(asked))
+        ref_rays.append(np.concatenate(asked + [np.zeros(7, f32)] * (2 - len(asked))))
+    tenv["ShadowTest"] = lambda ro, rd, max_dist: f32(1.0)
+    out.update(ref_wrs_tail=np.array(ref_tail, f32), ref_wrs_tail_rays=np.array(ref_rays, f32), ref_wrs_tail_nrays=np.array(ref_nrays, np.uint32))
     np.savez_compressed(os.path.join(GOLD, "reference_shader_vectors.npz"), **out)
 
 
