@@ -276,6 +276,21 @@ ORACLE_API uint32_t snkor_finish_initial_wrs(void* fp, PixelReservoir* r, const 
   memcpy(rays7x2, f.forced_rays, sizeof(float) * 14);
   return f.n_forced;
 }
+// RayClosestHit.rchit main() for a given hit, visibility forced; out9 = colour3 normal3 distance roughness mat_flags, ray7 = the shadow ray
+ORACLE_API uint32_t snkor_shade_hit_visible(void* fp, uint32_t inst, uint32_t prim, float u, float v, float t, const float* rd, float* out9, float* ray7) {
+  Frame& f = *(Frame*)fp;
+  Invocation inv(f, 0, 0, nullptr);
+  Hit h{}; h.t = t; h.u = u; h.v = v; h.prim = prim; h.inst = inst;
+  f.force_visible = true; f.n_forced = 0;
+  inv.payload = Payload{};
+  inv.shade_closest_hit(h, v3(rd[0], rd[1], rd[2]));
+  f.force_visible = false;
+  const Payload& p = inv.payload;
+  out9[0] = p.colour.x; out9[1] = p.colour.y; out9[2] = p.colour.z; out9[3] = p.normal.x; out9[4] = p.normal.y; out9[5] = p.normal.z;
+  out9[6] = p.distance; out9[7] = p.roughness; out9[8] = (float)p.mat_flags;
+  memcpy(ray7, f.forced_rays[0], sizeof(float) * 7);
+  return f.n_forced;
+}
 // ComputeTriangleRadiance(…, shadow_test = false) for a point on an emissive triangle seen from an explicit surface
 ORACLE_API void snkor_compute_triangle_radiance(void* fp, uint32_t obj, uint32_t tri, float bx, float by, const float* v, const float* f0,
                                                 const float* world_pos, const float* n, float roughness, float metallic, const float* albedo,

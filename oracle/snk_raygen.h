@@ -205,6 +205,10 @@ struct Invocation {
     Ray r{{ro.x, ro.y, ro.z}, tmin, {rd.x, rd.y, rd.z}, tmax};
     Hit h = sc.trace(r, false);
     if (h.t < 0.0f) { payload.colour = v3(0.0f); payload.distance = -1.0f; return; }
+    shade_closest_hit(h, rd);
+  }
+  // RayClosestHit.rchit:87-142 for a given hit
+  void shade_closest_hit(const Hit& h, vec3 rd) {
     const float b0 = (1.0f - h.u) - h.v, b1 = h.u, b2 = h.v;                     // rchit:88
     const InstanceData& in = sc.instances[h.inst];                              // rchit:90
     uint32_t ia, ib, ic; sc.tri_indices(in, h.prim, ia, ib, ic);                // rchit:91

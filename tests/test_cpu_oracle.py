@@ -911,3 +911,35 @@ def test_initial_wrs_tail_equals_the_executed_reference_shader(snk, oracle):
             non_unit += int(abs(np.linalg.norm(want_rays[3:6]) - 1.0) > 0.05)
     assert exact >= n_cb // 2
     assert non_unit > 0.8 * (g["cb_in"][:, 0, 2] != 0xFFFFFFFF).sum()  # the precedence quirk is in the golden data, and reproduced
+
+
+def test_closest_hit_shader_equals_the_executed_reference_shader(snk, oracle):
+    """main() of RayClosestHit.rchit (:87-142) executed from the reference's shader text for 160 given hits on every instance of
+    small_test_scene (emissive ones included): barycentrics (1-x-y, x, y), vertex fetch, model and normal matrix, emissive early
+    return, f0 mix, biased_pos = pos + n * 0.01, CalcDirectionalLight * visibility, the payload fields — and the directional-light
+    shadow ray (origin, direction, tmax 10000) as recorded by the ShadowTest stub."""
+    g = np.load(os.path.join(GOLD, "reference_shader_vectors.npz"))
+    sc = snk.scenes.small_test_scene(64, 48)
+    fr = oracle.OracleFrame(oracle.OracleScene(sc))
+    ubo = sc.ubo(0)
+    fr.set(ubo, ubo, oracle.default_settings())
+    L = oracle.lib()
+    L.snkor_shade_hit_visible.restype = C.c_uint32
+    n_hit = g["hit_inst"].shape[0]
+    exact = emissive = 0
+    for k in range(n_hit):
+        out9, ray7 = np.zeros(9, np.float32), np.zeros(7, np.float32)
+        rd = np.ascontiguousarray(g["hit_rd"][k], np.float32)
+        n_rays = L.snkor_shade_hit_visible(fr.h, int(g["hit_inst"][k]), int(g["hit_prim"][k]), C.c_float(g["hit_uv"][k, 0]), C.c_float(g["hit_uv"][k, 1]),
+                                           C.c_float(g["hit_t"][k]), fp(rd), fp(out9), fp(ray7))
+        want = g["ref_hit_payload"][k]
+        assert n_rays == int(g["ref_hit_nray"][k]), k
+        assert int(out9[8]) == int(want[8]) and out9[6] == want[6], (k, out9, want)
+        if int(want[8]) & 1:   # emissive: colour = albedo, normal / roughness untouched (rchit:119-123)
+            emissive += 1
+            assert np.array_equal(out9[:3], want[:3]) and n_rays == 0
+            continue
+        assert np.allclose(out9[:8], want[:8], rtol=3e-5, atol=1e-7), (k, out9, want)
+        assert np.allclose(ray7, g["ref_hit_ray"][k], rtol=3e-6, atol=2e-6) and ray7[6] == 10000.0, (k, ray7, g["ref_hit_ray"][k])
+        exact += int(np.array_equal(out9[:8].view(np.uint32), want[:8].view(np.uint32)))
+    assert emissive > 10 and exact >= (n_hit - emissive) // 2

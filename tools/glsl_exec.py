@@ -148,6 +148,8 @@ BUILTINS.update({
     "ivec2": _ivec(2), "ivec3": _ivec(3),
     "mat3": lambda m: Mat(m.c[:3, :3]),
     "transpose": lambda m: Mat(m.c.T),
+    "reflect": lambda i, n: (np.asarray(i, F) - (F(F(2.0) * _dot(n, i)) * np.asarray(n, F)).astype(F)).astype(F),
+    "bool": lambda a: bool(a), "all": lambda b: bool(np.all(b)),
     "any": lambda b: bool(np.any(b)), "lessThan": lambda a, b: np.asarray(a, F) < np.asarray(b, F),
     "greaterThan": lambda a, b: np.asarray(a, F) > np.asarray(b, F),
     "determinant": lambda m: F(np.linalg.det(m.c.astype(np.float64))),

@@ -521,6 +521,42 @@ def reference_shader_vectors():
         ref_rays.append(np.concatenate(asked + [np.zeros(7, f32)] * (2 - len(asked))))
     tenv["ShadowTest"] = lambda ro, rd, max_dist: f32(1.0)
     out.update(ref_wrs_tail=np.array(ref_tail, f32), ref_wrs_tail_rays=np.array(ref_rays, f32), ref_wrs_tail_nrays=np.array(ref_nrays, np.uint32))
+    # RayClosestHit.rchit:87-142: main() of the closest-hit shader for given hits (every instance of the scene, emissive ones included;
+    # no albedo textures in this scene), the directional-light shadow ray recorded by the ShadowTest stub
+    asked2 = []
+    henv = dict(tenv)
+    henv["ShadowTest"] = lambda ro, rd, max_dist: (asked2.append(np.concatenate([ro, rd, [max_dist]]).astype(f32)), f32(1.0))[1]
+    G.load_functions(os.path.join(REF, "Core/res/shaders/LightBuffers.glsl"), names[:5] + ["CalcDirectionalLight"], env=henv)
+    G.load_functions(os.path.join(REF, "Core/res/shaders/RayClosestHit.rchit"), ["main"], env=henv,
+                     defines={"INVALID_GLOBAL_INDEX": u32(0xFFFFFFFF), "MAT_FLAG_EMISSIVE": u32(1)})
+    henv["vert_tex_coords"] = G.namespace(t=[row for row in flat["uvs"]])
+    henv["material_ubo"] = G.namespace(materials=[G.namespace(albedo=np.asarray(sc.materials["albedo"][k], f32), albedo_tex_idx=u32(int(sc.materials["tex"][k][0])),
+                                                              flags=u32(int(sc.materials["flags"][k])), roughness=f32(sc.materials["roughness"][k]),
+                                                              metallic=f32(sc.materials["metallic"][k])) for k in range(sc.materials.shape[0])])
+    lights_buf = sc.flatten()["lights"]
+    dl_col = np.frombuffer(lights_buf, f32, 4, 0).copy(); dl_dir = np.frombuffer(lights_buf, f32, 4, 16).copy()
+    henv["ssbo_light_data"] = G.namespace(dir_light=G.namespace(colour=dl_col, dir=dl_dir))
+    n_hit = 160
+    n_inst = flat["instances"].shape[0]
+    hit_inst = rng.integers(0, n_inst, n_hit).astype(np.uint32)
+    hit_prim = np.array([rng.integers(0, int(flat["instances"][i][4]) // 3) for i in hit_inst], np.uint32)
+    hit_uv = rng.uniform(0, 0.5, (n_hit, 2)).astype(f32)
+    hit_t = rng.uniform(0.5, 30, n_hit).astype(f32)
+    hit_rd = unit(rng.normal(size=(n_hit, 3)))
+    ref_hit, ref_hit_ray, ref_hit_nray = [], [], []
+    for k in range(n_hit):
+        del asked2[:]
+        henv["payload"] = G.namespace(colour=np.zeros(3, f32), normal=np.zeros(3, f32), distance=f32(-1.0), roughness=f32(0.0), mat_flags=u32(0))
+        henv["attribs"] = hit_uv[k]
+        henv["gl_InstanceCustomIndexEXT"] = u32(int(hit_inst[k])); henv["gl_PrimitiveID"] = u32(int(hit_prim[k]))
+        henv["gl_RayTmaxEXT"] = hit_t[k]; henv["gl_WorldRayDirectionEXT"] = hit_rd[k]
+        henv["main"]()
+        pl_ = henv["payload"]
+        ref_hit.append(np.concatenate([pl_.colour, pl_.normal, [pl_.distance, pl_.roughness, float(int(pl_.mat_flags))]]).astype(f32))
+        ref_hit_nray.append(len(asked2))
+        ref_hit_ray.append(asked2[0] if asked2 else np.zeros(7, f32))
+    out.update(hit_inst=hit_inst, hit_prim=hit_prim, hit_uv=hit_uv, hit_t=hit_t, hit_rd=hit_rd, ref_hit_payload=np.array(ref_hit, f32),
+               ref_hit_ray=np.array(ref_hit_ray, f32), ref_hit_nray=np.array(ref_hit_nray, np.uint32))
     np.savez_compressed(os.path.join(GOLD, "reference_shader_vectors.npz"), **out)
 
 
