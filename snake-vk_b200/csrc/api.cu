@@ -13,6 +13,8 @@
 
 #include "kernels.h"
 
+#include <cstdlib>
+
 using namespace snk;
 
 static thread_local std::string g_create_error;
@@ -118,9 +120,9 @@ int traced_launch(SnkPt* ctx, const char* name, const float4* rays, uint64_t n, 
 
 // ---- compact ray-reference queues of the frame (trace_q.cu) ----
 // dev_counters u32 view [64 + 2k] = entries appended to queue k, [65 + 2k] = ticket of its traversal launch
-RefQueue ref_queue(SnkPt* ctx, int k, uint32_t cap) {
+RefQueue ref_queue(SnkPt* ctx, int k, uint32_t cap, uint32_t first_ref) {
   RefQueue q;
-  q.refs = ctx->wave_refs.as<uint32_t>();
+  q.refs = ctx->wave_refs.as<uint32_t>() + first_ref;
   q.count = ctx->dev_counters.as<uint32_t>() + 64 + 2 * k;
   q.ticket = q.count + 1;
   q.cap = cap;
@@ -134,11 +136,21 @@ int reserve_ref_queues(SnkPt* ctx, uint32_t cap, cudaStream_t st) {
 // 24 queues (u32 [64..112)) and the per-stage path-list counters of northstar.cu (u32 [112..136))
 void reset_ref_queues(SnkPt* ctx, cudaStream_t st) { cudaMemsetAsync(ctx->dev_counters.as<uint32_t>() + 64, 0, 4 * (136 - 64), st); }
 
-int traced_launch_q(SnkPt* ctx, const char* name, const TraceSegs& segs, const RefQueue& q, cudaStream_t st) {
+// north-star frame: the ReSTIR chain may run on the auxiliary stream (off under profiling, whose per-launch timings want one
+// launch at a time, and with SNKPT_NS_OVERLAP=0)
+bool ns_overlap_enabled(const SnkPt* ctx) {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SNKPT_NS_OVERLAP"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1 && ctx->profiling == 0;
+}
+
+int traced_launch_q(SnkPt* ctx, const char* name, const TraceSegs& segs, const RefQueue& q, cudaStream_t st, int spill_region) {
   const bool count = ctx->profiling >= 2 && ctx->prof_n < PROF_MAX;
   float* prof_t = nullptr;
   if (count && ctx->prof_hits.reserve(4ull * q.cap, false, st) == cudaSuccess) prof_t = ctx->prof_hits.as<float>();
-  const TraceScene S = ctx->trace_scene();
+  TraceScene S = ctx->trace_scene();
+  // two traversal launches may be in flight at once (north-star chains): each gets its own stack spill region
+  S.spill += (size_t)spill_region * (trace_spill_bytes() / sizeof(uint2));
   const int rec = prof_begin(ctx, name, q.cap, true, false, st);
   const int launches = launch_trace_q(S, segs, q, prof_t, st);
   prof_end(ctx, rec, st);
@@ -304,7 +316,7 @@ int snkpt_create(const SnkPtConfig* cfg, SnkPt** out) {
     if (e2 == cudaSuccess) e2 = cudaMemsetAsync(ctx->materials.p, 0, sizeof(SnkMaterial) * ctx->max_materials, ctx->stream);
     if (e2 == cudaSuccess) e2 = ctx->dev_counters.reserve(1024, false, ctx->stream);
     if (e2 == cudaSuccess) e2 = cudaMemsetAsync(ctx->dev_counters.p, 0, 1024, ctx->stream);
-    if (e2 == cudaSuccess) e2 = ctx->trav_spill.reserve(trace_spill_bytes(), false, ctx->stream);
+    if (e2 == cudaSuccess) e2 = ctx->trav_spill.reserve(2 * trace_spill_bytes(), false, ctx->stream);
     if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(ctx->stream);
     if (e2 != cudaSuccess) { ctx->err = cudaGetErrorString(e2); rc = SNKPT_E_CUDA; }
   }
@@ -339,6 +351,11 @@ void snkpt_destroy(SnkPt* ctx) {
   for (auto& ev : ctx->ev_read_done) if (ev) cudaEventDestroy(ev);
   if (ctx->ev_frame_done) cudaEventDestroy(ctx->ev_frame_done);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+  if (ctx->hi_stream) { cudaStreamSynchronize(ctx->hi_stream); cudaStreamDestroy(ctx->hi_stream); }
+  if (ctx->ev_join_b) cudaEventDestroy(ctx->ev_join_b);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   for (auto& r : ctx->prof) { if (r.e0) cudaEventDestroy(r.e0); if (r.e1) cudaEventDestroy(r.e1); }
   ctx->prof_work.release(); ctx->prof_hits.release();

@@ -153,6 +153,9 @@ struct SnkPt {
   bool ring_armed[RING_CHUNKS] = {};
   cudaStream_t work_stream = nullptr;  // stream of the last frame call (snkpt_build_tlas / trace_primary / render), default: `stream`
   // asynchronous read-back of the output image (snkpt_read_output_async): own copy stream, two slots
+  // north-star frame: low-priority stream of the ReSTIR chain (northstar.cu), forked from / joined to the frame's stream
+  cudaStream_t aux_stream = nullptr, hi_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join_b = nullptr;
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_frame_done = nullptr, ev_read_done[2] = {};
   bool read_pending[2] = {false, false};

@@ -21,13 +21,18 @@ int launch_count_work_sum(const TraceScene& S, const float4* rays, const float4*
 // trace_q.cu — queue traversal: drains a compact queue of ray references (closest-hit and any-hit rays of several
 // segments mixed); prof_t (optional) receives the reported hit distance per queue position
 int launch_trace_q(const TraceScene& S, const TraceSegs& segs, const RefQueue& q, float* prof_t, cudaStream_t st);
+// trace_mx.cu — the same queue drained with several rays multiplexed per lane (state in shared memory, one voted phase per iteration)
+int launch_trace_mx(const TraceScene& S, const TraceSegs& segs, const RefQueue& q, float* prof_t, int sms, cudaStream_t st);
+size_t trace_mx_spill_bytes(int sms);
+int device_sm_count();
 int launch_count_work_q(const TraceScene& S, const TraceSegs& segs, const RefQueue& q, const float* prof_t, unsigned long long* sums8,
                         cudaStream_t st);
 // launch_trace_q bracketed by a profiling record (+ counted replay at level 2)
-int traced_launch_q(SnkPt* ctx, const char* name, const TraceSegs& segs, const RefQueue& q, cudaStream_t st);
+int traced_launch_q(SnkPt* ctx, const char* name, const TraceSegs& segs, const RefQueue& q, cudaStream_t st, int spill_region = 0);
+bool ns_overlap_enabled(const SnkPt* ctx);
 // queue k (0..23) of the frame: refs in ctx->wave_refs (shared: a queue is drained before the next one is filled), counters in
 // dev_counters; all are reset by reset_ref_queues
-RefQueue ref_queue(SnkPt* ctx, int k, uint32_t cap);
+RefQueue ref_queue(SnkPt* ctx, int k, uint32_t cap, uint32_t first_ref = 0);
 int reserve_ref_queues(SnkPt* ctx, uint32_t cap, cudaStream_t st);
 void reset_ref_queues(SnkPt* ctx, cudaStream_t st);
 

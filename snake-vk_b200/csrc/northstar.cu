@@ -301,45 +301,77 @@ int launch_northstar_frame(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st) 
   const uint32_t g128 = (npix + 127) / 128;
   const bool bounce = !(s.flags & SNKPT_RT_NO_BOUNCE);
   const uint32_t max_bounces = bounce ? s.max_bounces : 0u;
-  // Every traversal launch drains ONE queue that all stages ready at that point have appended to:
-  //   queue 0: ReSTIR initial-candidate shadow rays + the path's first continuation ray (+ its NEE ray without ReSTIR)
-  //   queue 1: ReSTIR final shadow rays + NEE ray of vertex 1 + continuation ray 2
-  //   queue b: NEE ray of vertex b + continuation ray b+1
+  // Two independent chains share the frame after the G-buffer: the ReSTIR DI stages (direct light at x0) and the path
+  // (vertices 1..max_bounces). Each chain appends its rays to its own queues and every traversal launch drains ONE queue:
+  //   chain A (ReSTIR): rs_initial -> [queue A0: initial-candidate shadow rays] -> temporal, spatial, final -> [queue A1: final
+  //                     shadow rays] -> rs_resolve
+  //   chain B (path):   ns_gen -> [queue B0: first continuation ray (+ its NEE ray without ReSTIR)] -> vertex b ->
+  //                     [queue Bb: NEE ray of vertex b + continuation ray b+1] ...
+  // With overlap on (default outside profiling) chain A runs on the context's low-priority auxiliary stream: the late
+  // bounces of chain B are latency-bound tails (0.05-0.65 M live rays, 18-42 % achieved occupancy, profiles/r03h) and the
+  // traversal kernels leave two CTA slots per SM free (launch grid 6 of 8 resident CTAs), so the bulk kernels of chain A
+  // fill the SMs the tails leave idle. Results do not depend on which queue or launch a ray went through.
+  const bool overlap = nee_from && ns_overlap_enabled(ctx);
+  cudaStream_t sa = st;
+  if (overlap) {
+    if (!ctx->aux_stream) {
+      int lo = 0, hi = 0;
+      cudaDeviceGetStreamPriorityRange(&lo, &hi);
+      if (cudaStreamCreateWithPriority(&ctx->aux_stream, cudaStreamNonBlocking, lo) != cudaSuccess) { ctx->err = "north-star frame: cannot create the auxiliary stream"; return SNKPT_E_CUDA; }
+      if (cudaStreamCreateWithPriority(&ctx->hi_stream, cudaStreamNonBlocking, hi) != cudaSuccess) { ctx->err = "north-star frame: cannot create the path stream"; return SNKPT_E_CUDA; }
+      cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+      cudaEventCreateWithFlags(&ctx->ev_join_b, cudaEventDisableTiming);
+    }
+    sa = ctx->aux_stream;
+  }
+  // the path chain is the frame's critical path: with overlap on it runs on a high-priority stream of the context, so its
+  // (small, latency-bound) launches get the CTA slots the bulk kernels of the ReSTIR chain free first
+  cudaStream_t sb = overlap ? ctx->hi_stream : st;
   cudaEventRecord(ctx->ev[2], st);
   launches += build_emissive_table(ctx, st);
-  int q = 0;
-  RefQueue Q = ref_queue(ctx, q, qcap);
-  if (nee_from) launches += restir_ns_initial(ctx, s, Q, st);
-  int rec = prof_begin(ctx, "ns_gen", npix, false, false, st);
-  k_ns_gen<<<(stage_threads(fc.W, fc.row1 - fc.row0) + 127) / 128, 128, 0, st>>>(D, fc, ctx->planes, B, npix, max_bounces, nee_from, counters, Q.refs, Q.count, paths[0], path_count);
-  prof_end(ctx, rec, st);
-  ++launches;
   char name[32];
-  snprintf(name, sizeof(name), "trace.q%d", q);
-  launches += traced_launch_q(ctx, name, segs, Q, st);
-  Q = ref_queue(ctx, ++q, qcap);
-  if (nee_from) launches += restir_ns_reuse(ctx, s, Q, st);
-  else { cudaEventRecord(ctx->ev[3], st); }
+  int rec;
+  // queue capacities: chain A up to 3 rays per pixel (final point / emissive / directional), chain B 2 (NEE + continuation)
+  const uint32_t capA = 3u * npix_frame, capB = 2u * npix_frame;
+  if (nee_from) {
+    if (overlap) { cudaEventRecord(ctx->ev_fork, st); cudaStreamWaitEvent(sa, ctx->ev_fork, 0); cudaStreamWaitEvent(sb, ctx->ev_fork, 0); }
+    RefQueue QA = ref_queue(ctx, 0, capA, 0);
+    launches += restir_ns_initial(ctx, s, QA, sa);
+    launches += traced_launch_q(ctx, "trace.qA0", segs, QA, sa, overlap ? 1 : 0);
+    QA = ref_queue(ctx, 1, capA, 0);
+    launches += restir_ns_reuse(ctx, s, QA, sa);
+    launches += traced_launch_q(ctx, "trace.qA1", segs, QA, sa, overlap ? 1 : 0);
+    launches += restir_ns_resolve(ctx, sa);
+    if (overlap) cudaEventRecord(ctx->ev_join, sa);
+  } else {
+    cudaEventRecord(ctx->ev[3], st);
+    cudaMemsetAsync(ctx->planes.direct + (size_t)fc.row0 * fc.W, 0, 16ull * npix, st);
+  }
+  int q = 2;
+  RefQueue Q = ref_queue(ctx, q, capB, capA);
+  rec = prof_begin(ctx, "ns_gen", npix, false, false, sb);
+  k_ns_gen<<<(stage_threads(fc.W, fc.row1 - fc.row0) + 127) / 128, 128, 0, sb>>>(D, fc, ctx->planes, B, npix, max_bounces, nee_from, counters, Q.refs, Q.count, paths[0], path_count);
+  prof_end(ctx, rec, sb);
+  ++launches;
+  launches += traced_launch_q(ctx, "trace.qB0", segs, Q, sb, 0);
+  const uint32_t sms = (uint32_t)device_sm_count();
   for (uint32_t b = 1; b <= max_bounces; ++b) {
+    Q = ref_queue(ctx, ++q, capB, capA);
     snprintf(name, sizeof(name), "ns_vertex.%u", b);
-    rec = prof_begin(ctx, name, npix, false, false, st);
-    // expected survivors: everything at bounce 1, then a shrinking multiple of the resident grid (148 SMs x 6 CTAs)
-    const uint32_t g_cap = 148u * 6u * (b == 1 ? 32u : b == 2 ? 8u : b == 3 ? 4u : 2u);
-    k_ns_vertex<<<g128 < g_cap ? g128 : g_cap, 128, 0, st>>>(D, fc, B, npix, b, max_bounces, nee_from, counters, Q.refs, Q.count, paths[(b - 1) & 1], path_count + (b - 1),
+    rec = prof_begin(ctx, name, npix, false, false, sb);
+    // expected survivors: everything at bounce 1, then a shrinking multiple of the resident grid (6 CTAs per SM)
+    const uint32_t g_cap = sms * 6u * (b == 1 ? 32u : b == 2 ? 8u : b == 3 ? 4u : 2u);
+    k_ns_vertex<<<g128 < g_cap ? g128 : g_cap, 128, 0, sb>>>(D, fc, B, npix, b, max_bounces, nee_from, counters, Q.refs, Q.count, paths[(b - 1) & 1], path_count + (b - 1),
                                       paths[b & 1], path_count + b);
-    prof_end(ctx, rec, st);
-    snprintf(name, sizeof(name), "trace.q%d", q);
-    launches += 1 + traced_launch_q(ctx, name, segs, Q, st);
-    if (b == 1) cudaEventRecord(ctx->ev[4], st);
-    Q = ref_queue(ctx, ++q, qcap);
+    prof_end(ctx, rec, sb);
+    snprintf(name, sizeof(name), "trace.qB%u", b);
+    launches += 1 + traced_launch_q(ctx, name, segs, Q, sb, 0);
+    if (b == 1) cudaEventRecord(ctx->ev[4], sb);
   }
-  if (max_bounces == 0) {
-    // no path vertices: the ReSTIR final rays still have to be traced
-    if (nee_from) { snprintf(name, sizeof(name), "trace.q%d", q); launches += traced_launch_q(ctx, name, segs, Q, st); }
-    cudaEventRecord(ctx->ev[4], st);
-  }
-  if (nee_from) launches += restir_ns_resolve(ctx, st);
-  else cudaMemsetAsync(ctx->planes.direct + (size_t)fc.row0 * fc.W, 0, 16ull * npix, st);
+  if (max_bounces == 0) cudaEventRecord(ctx->ev[4], sb);
+  if (overlap) { cudaEventRecord(ctx->ev_join_b, sb); cudaStreamWaitEvent(st, ctx->ev_join_b, 0); }
+  if (overlap) cudaStreamWaitEvent(st, ctx->ev_join, 0);
   wait_readback(ctx, st);  // the resolve overwrites the output image
   rec = prof_begin(ctx, "ns_resolve", npix, false, false, st);
   k_ns_resolve<<<(npix + 255) / 256, 256, 0, st>>>(D, fc, ctx->planes, B, npix, max_bounces, nee_from);

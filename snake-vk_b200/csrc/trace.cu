@@ -195,11 +195,16 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_count_work_sum(TraceScene S, 
 
 static int trace_grid(uint64_t n) {
   const uint64_t blocks = (n + TRACE_THREADS - 1) / TRACE_THREADS;
-  const uint64_t persistent = 148ull * PT_CTAS_PER_SM;
+  const uint64_t persistent = (uint64_t)device_sm_count() * PT_CTAS_PER_SM;
   return (int)(blocks < persistent ? (blocks ? blocks : 1) : persistent);
 }
 
-size_t trace_spill_bytes() { return (size_t)148 * 8 * /* the largest persistent grid: 8 CTAs per SM */ (TRACE_THREADS / 32) * SPILL_STACK * 32 * sizeof(uint2); }
+size_t trace_spill_bytes() {
+  const int sms = device_sm_count();
+  const size_t one_ray = (size_t)sms * 8 * /* the largest persistent grid: 8 CTAs per SM */ (TRACE_THREADS / 32) * SPILL_STACK * 32 * sizeof(uint2);
+  const size_t mx = trace_mx_spill_bytes(sms);
+  return one_ray > mx ? one_ray : mx;
+}
 
 int launch_trace(const TraceScene& S, const float4* rays, uint64_t n, bool any, SnkHit* hits_aos, float4* hits_soa,
                  uint32_t* inst_soa, float* vis_out, unsigned long long* ticket, cudaStream_t st) {

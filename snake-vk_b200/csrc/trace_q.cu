@@ -10,6 +10,8 @@
 // Replaces the driver side of vkCmdTraceRaysKHR (Core/src/rendering/Raytracing.cpp:253, :260) like trace.cu.
 #include "kernels.h"
 
+#include <cstdlib>
+
 namespace snk {
 
 namespace {
@@ -17,6 +19,10 @@ namespace {
 constexpr int TQ_THREADS = 128;
 #ifndef SNK_TQ_CTAS
 #define SNK_TQ_CTAS 8
+#endif
+#ifndef SNK_TQ_GRID_CTAS
+#define SNK_TQ_GRID_CTAS 6  // CTAs per SM the persistent grid launches (of the 8 the launch bounds allow): 5-7 run within 1.5 % of 8
+                            // (profiles/r02a_variants_occupancy_stack.txt) and the free slots let the other chain's kernels in
 #endif
 #ifndef SNK_TQ_VOTE
 #define SNK_TQ_VOTE 0  // 0: node + triangle + pop every iteration (trav_step); 1: one voted phase per iteration (trav_vote_step) — measured 20 % slower (r01r)
@@ -178,11 +184,34 @@ __global__ void __launch_bounds__(TQ_THREADS) k_count_work_q(TraceScene S, Trace
 
 }  // namespace
 
+int device_sm_count() {
+  static int sms[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (sms[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    sms[dev] = v;
+  }
+  return sms[dev];
+}
+
+// SNKPT_TRACE_KERNEL=mx selects the multiplexed kernel of trace_mx.cu (A/B measurements: bit-identical results, 21 instead of
+// 15 active threads per warp and 18 % fewer instructions, but 4-35 % slower because its shared-memory state caps the
+// occupancy — profiles/r04a_*, r04b_*); default: the one-ray-per-lane kernel of this file
+static bool use_mx_kernel() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SNKPT_TRACE_KERNEL"); v = (e && e[0] == 'm') ? 1 : 0; }
+  return v == 1;
+}
+
 int launch_trace_q(const TraceScene& S, const TraceSegs& segs, const RefQueue& q, float* prof_t, cudaStream_t st) {
   if (!q.refs || !q.count || !q.ticket || !S.spill || q.cap == 0) return 0;
+  if (use_mx_kernel()) return launch_trace_mx(S, segs, q, prof_t, device_sm_count(), st);
   // persistent grid; a queue that cannot fill it gets one CTA per 128 possible entries
   const uint64_t blocks = ((uint64_t)q.cap + TQ_THREADS - 1) / TQ_THREADS;
-  const uint64_t persistent = 148ull * SNK_TQ_CTAS;
+  const uint64_t persistent = (uint64_t)device_sm_count() * SNK_TQ_GRID_CTAS;
   const int grid = (int)(blocks < persistent ? blocks : persistent);
   k_trace_q<<<grid, TQ_THREADS, 0, st>>>(S, segs, q.refs, q.count, q.ticket, prof_t);
   return 1;
@@ -192,7 +221,7 @@ int launch_count_work_q(const TraceScene& S, const TraceSegs& segs, const RefQue
                         cudaStream_t st) {
   if (!q.refs || !q.count || q.cap == 0 || !prof_t) return 0;
   const uint64_t blocks = ((uint64_t)q.cap + TQ_THREADS - 1) / TQ_THREADS;
-  k_count_work_q<<<(unsigned)(blocks < 148ull * 16 ? blocks : 148ull * 16), TQ_THREADS, 0, st>>>(S, segs, q.refs, q.count, prof_t, sums8);
+  k_count_work_q<<<(unsigned)(blocks < (uint64_t)device_sm_count() * 16 ? blocks : (uint64_t)device_sm_count() * 16), TQ_THREADS, 0, st>>>(S, segs, q.refs, q.count, prof_t, sums8);
   return 1;
 }
 
