@@ -6,9 +6,14 @@ Python function by a mechanical rewrite (declarations lose their type, swizzles 
 numpy helpers with the same operation order) and returns them. Nothing of the shader text is stored in this repository: the
 generator (tools/make_golden.py) commits only the numeric input / output vectors.
 
-Supported subset: functions whose body consists of declarations, assignments, compound assignments, `++`, `if` / `else` (single
-statements or blocks, nested), counted `for (uint i = a; cond; i++)` loops, `while` loops and returns; scalar / vec3 / vec4 float arithmetic and 32-bit unsigned arithmetic; struct parameters and the `ssbo_light_data` block as attribute access; the built-ins listed in BUILTINS.
+Supported subset: functions whose body consists of declarations (with or without initialiser), assignments, compound assignments,
+`++`, `?:`, `if` / `else` (single statements or blocks, nested), counted `for (uint i = a; cond; i++)` loops, `while` loops, `continue`,
+`break` and returns; scalar / vec3 / vec4 float arithmetic and 32-bit unsigned arithmetic; struct parameters and buffer blocks as
+attribute access; calls of functions with `out` / `inout` parameters; the built-ins listed in BUILTINS.
+GLSL value semantics are kept: every assignment and every `in` parameter copies its value (structs deeply), compound assignments
+never update an array in place.
 """
+import copy
 import re
 import types
 
@@ -86,6 +91,13 @@ def _mixed(cls):
             return getattr(F(o) if not isinstance(o, np.ndarray) else o, f"__{_op}__")(F(int(self)))
         setattr(cls, f"__{op}__", fwd)
         setattr(cls, f"__r{op}__", rev)
+    for op in ("lt", "le", "gt", "ge"):
+        ident = getattr(int, f"__{op}__")
+        def cmp(self, o, _op=op, _ident=ident):
+            if _is_float(o):
+                return bool(getattr(F(int(self)), f"__{_op}__")(F(o)))
+            return _ident(self, o)
+        setattr(cls, f"__{op}__", cmp)
     cls.__array_priority__ = 100  # numpy scalars / arrays defer to these reflected operators
     return cls
 
@@ -104,8 +116,12 @@ class I32(int):
 
 
 class IVec(tuple):
-    """ivecN: component-wise addition"""
+    """ivecN: component-wise addition; ivec * vec converts to float32 first (numpy would promote the integers to float64)"""
+    __array_ufunc__ = None  # float-vector OP ivec goes through the reflected operators below
     def __add__(self, o): return IVec(I32._w(int(a) + int(b)) for a, b in zip(self, o))
+    def _f(self): return np.array([F(int(c)) for c in self], F)
+    def __mul__(self, o): return (self._f() * np.asarray(o, F)).astype(F)
+    def __rmul__(self, o): return (np.asarray(o, F) * self._f()).astype(F)
 
 
 def _ivec(n):
@@ -115,6 +131,8 @@ def _ivec(n):
             parts.extend(np.asarray(x).reshape(-1).tolist())
         if len(parts) == 1:
             parts = parts * n
+        if len(a) == 1 and len(parts) > n:
+            parts = parts[:n]  # ivec2(uvec3): the leading components
         assert len(parts) == n
         return IVec(I32._w(int(np.trunc(v))) for v in parts)  # float -> int conversion truncates
     return ctor
@@ -177,13 +195,142 @@ def _expr(e):
     return re.sub(r"(?<=[A-Za-z_0-9\)\]])\.(xyz|rgb|xy|xz|yz|x|y|z|w|r|g|b)\b(?!\s*\()", lambda m: _SWIZZLE[m.group(1)], e)
 
 
+def _val(x):
+    """GLSL assigns by value: structs (namespaces) are copied deeply, vectors / matrices are copied"""
+    if isinstance(x, types.SimpleNamespace):
+        return copy.deepcopy(x)
+    if isinstance(x, np.ndarray):
+        return x.copy()
+    if isinstance(x, Mat):
+        return Mat(x.c.copy())
+    return x
+
+
+# struct definitions seen so far: name -> [(member type, member name)]; `PixelReservoir r;` creates the nested members
+_STRUCTS = {}
+
+
+def new_struct(name):
+    ns = types.SimpleNamespace()
+    for ty, member in _STRUCTS.get(name, []):
+        setattr(ns, member, new_struct(ty) if ty in _STRUCTS else None)
+    return ns
+
+
+# signatures of the functions seen so far: name -> [(qualifier, is_basic_type)] per parameter (call sites with out / inout arguments)
+_SIGS = {}
+
+
+def _top_level(st, tokens):
+    """index and token of the first occurrence of one of `tokens` outside parentheses / brackets, else (-1, None)"""
+    depth = 0
+    i = 0
+    while i < len(st):
+        ch = st[i]
+        if ch in "([":
+            depth += 1
+        elif ch in ")]":
+            depth -= 1
+        elif depth == 0:
+            for t in tokens:
+                if st.startswith(t, i):
+                    return i, t
+        i += 1
+    return -1, None
+
+
+def _split_args(argstr):
+    out, depth, cur = [], 0, ""
+    for ch in argstr:
+        if ch in "([":
+            depth += 1
+        elif ch in ")]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur.strip())
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur.strip())
+    return out
+
+
+def _ternary(e):
+    """c ? a : b (right associative) -> Python conditional expression; the pieces go through _expr / _cond"""
+    i, _ = _top_level(e, ["?"])
+    if i < 0:
+        return _expr(e)
+    cond, rest = e[:i], e[i + 1:]
+    depth, j, nest = 0, 0, 0
+    while j < len(rest):
+        ch = rest[j]
+        if ch in "([":
+            depth += 1
+        elif ch in ")]":
+            depth -= 1
+        elif depth == 0 and ch == "?":
+            nest += 1
+        elif depth == 0 and ch == ":":
+            if nest == 0:
+                break
+            nest -= 1
+        j += 1
+    return f"(({_ternary(rest[:j])}) if ({_cond(cond)}) else ({_ternary(rest[j + 1:])}))"
+
+
+def _assign_index(st):
+    """index of the top-level plain `=` of an assignment (not ==, <=, >=, !=), else -1"""
+    depth = 0
+    for i, ch in enumerate(st):
+        if ch in "([":
+            depth += 1
+        elif ch in ")]":
+            depth -= 1
+        elif ch == "=" and depth == 0:
+            if st[i + 1:i + 2] == "=" or st[i - 1:i] in ("=", "<", ">", "!", "+", "-", "*", "/", "^", "&", "|"):
+                continue
+            return i
+    return -1
+
+
+def _call_with_outs(st):
+    """`f(a, b, c);` where f has out / inout scalar or vector parameters -> `b, c = f(a, c)` (as _translate returns them)"""
+    m = re.match(r"^(\w+)\((.*)\)$", st)
+    if not m or m.group(1) not in _SIGS:
+        return None
+    sig = _SIGS[m.group(1)]
+    args = _split_args(m.group(2))
+    if len(args) != len(sig) or not any(q == "out" or (q == "inout" and basic) for q, basic in sig):
+        return None
+    outs = [a for a, (q, basic) in zip(args, sig) if q == "out" or (q == "inout" and basic)]
+    ins = [a for a, (q, basic) in zip(args, sig) if q != "out"]
+    lhs = ", ".join(_expr(o) for o in outs)
+    return f"{lhs}{',' if len(outs) == 1 else ''} = {m.group(1)}({', '.join(_ternary(a) for a in ins)})"
+
+
 def _stmt(st):
+    if re.match(r"(return|else|if)\b", st):
+        m = re.match(r"return\s+(.*)$", st)
+        return f"return {_ternary(m.group(1))}" if m else _expr(st)
+    if st in ("continue", "break"):
+        return st
+    st = re.sub(rf"^(?:const\s+)?{_TYPES}\s+(\w+)$", r"\1 = None", st)       # `vec3 nt;`
     st = re.sub(rf"^(?:const\s+)?{_TYPES}\s+(?=\w+\s*=)", "", st)
-    if not re.match(r"(return|else|if)\b", st):  # declaration with a struct type: `InstanceData instance = ...`
-        st = re.sub(r"^(?:const\s+)?[A-Za-z_]\w*\s+(?=[A-Za-z_]\w*\s*=[^=])", "", st)
-    st = re.sub(r"^[A-Z]\w*\s+([A-Za-z_]\w*)$", r"\1 = namespace()", st)  # `TriangleData triangle;`
+    st = re.sub(r"^(?:const\s+)?[A-Za-z_]\w*\s+(?=[A-Za-z_]\w*\s*=[^=])", "", st)  # declaration with a struct type: `InstanceData instance = ...`
+    st = re.sub(r"^([A-Z]\w*)\s+([A-Za-z_]\w*)$", r'\2 = new_struct("\1")', st)  # `TriangleData triangle;`
     st = re.sub(r"^([\w\.\[\]]+)\+\+$", r"\1 += 1", st)
     st = re.sub(r"^([\w\.\[\]]+)--$", r"\1 -= 1", st)
+    call = _call_with_outs(st)
+    if call:
+        return call
+    i, op = _top_level(st, ["<<=", ">>=", "+=", "-=", "*=", "/=", "^=", "&=", "|="])
+    if i >= 0 and _assign_index(st) < 0:
+        lhs, rhs = st[:i].strip(), st[i + len(op):].strip()
+        return f"{_expr(lhs)} = {_expr(lhs)} {op[:-1]} ({_ternary(rhs)})"  # never in place: `xy += v` must not write through a swizzle view
+    i = _assign_index(st)
+    if i >= 0:
+        return f"{_expr(st[:i].strip())} = _val({_ternary(st[i + 1:].strip())})"
     return _expr(st)
 
 
@@ -203,8 +350,20 @@ def _split_paren(st):
     return st[i + 1:j - 1], st[j:].strip()
 
 
-def _translate(name, params, body):
-    args, outs = [], []
+def _signature(params):
+    sig = []
+    for p in params.split(","):
+        toks = p.strip().split()
+        if not toks:
+            continue
+        q = toks[0] if toks[0] in ("in", "out", "inout") else "in"
+        ty = toks[1] if toks[0] in ("in", "out", "inout", "const") else toks[0]
+        sig.append((q, bool(re.fullmatch(_TYPES, ty))))
+    return sig
+
+
+def _translate(name, params, body, copy_params=True):
+    args, outs, copies = [], [], []
     for p in params.split(","):
         p = p.strip()
         if p:
@@ -215,11 +374,14 @@ def _translate(name, params, body):
                 args.append(toks[-1])
                 if toks[0] == "inout" and re.fullmatch(_TYPES, toks[1]):
                     outs.append(toks[-1])  # scalars / vectors passed `inout` come back in the returned tuple as well
+                elif toks[0] != "inout":
+                    copies.append(toks[-1])  # `in` parameters are copies of the caller's values
     lines = [f"def {name}({', '.join(args)}):"]
+    for c in copies if copy_params else []:
+        lines.append(f"    {c} = _val({c})")
     body = re.sub(r"//[^\n]*", "", body)
     body = re.sub(r"\btrue\b", "True", re.sub(r"\bfalse\b", "False", body))
     indent, cur, depth, emitted, epilogue = 1, "", 0, [0], []
-    assert not re.search(r"\bcontinue\b|\bbreak\b", body), f"{name}: continue / break are outside the supported subset"
 
     def emit(text):
         lines.append("    " * indent + text)
@@ -259,6 +421,8 @@ def _translate(name, params, body):
                     assert m_for and m_for.group(1) == m_for.group(4), f"{name}: only `for (uint i = a; cond; i++)` is supported: {st}"
                     emit(f"{m_for.group(1)} = {_expr(m_for.group(2).strip())}")
                     emit(f"while {_cond(m_for.group(3).strip())}:")
+                    indent += 1
+                    lines.append("    " * indent + "try:")  # the increment runs on `continue` as well
                     epilogue.append(f"{m_for.group(1)} += 1")
                     indent += 1
                     emitted.append(0)
@@ -279,12 +443,14 @@ def _translate(name, params, body):
             else:
                 assert not st, f"{name}: statement without ';' before '}}': {st}"
                 ep = epilogue.pop()
-                if ep:
-                    lines.append("    " * indent + ep)  # loop increment (no `continue` in the supported subset)
-                elif emitted[-1] == 0:
+                if emitted[-1] == 0:
                     lines.append("    " * indent + "pass")
                 emitted.pop()
                 indent -= 1
+                if ep:  # close the `try:` of a counted loop
+                    lines.append("    " * indent + "finally:")
+                    lines.append("    " * (indent + 1) + ep)
+                    indent -= 1
         else:
             cur += ch
     if outs:
@@ -294,18 +460,25 @@ def _translate(name, params, body):
 
 def load_functions(path, names, defines=None, env=None):
     """-> dict name -> python function, plus the `defines` found in the file (object-like macros with a numeric value)"""
-    text = open(path, encoding="utf-8", errors="replace").read()
+    text = _read_shader(path)
     env = dict(BUILTINS) if env is None else env
     env["U32"] = U32
     env["F"] = F
     env["namespace"] = namespace
+    env["_val"] = _val
+    env["new_struct"] = new_struct
+    for m in re.finditer(r"^\s*struct\s+(\w+)\s*\{([^}]*)\}", text, re.M):
+        body = re.sub(r"//[^\n]*", "", m.group(2))
+        _STRUCTS.setdefault(m.group(1), [tuple(d.split()[-2:]) for d in body.split(";") if len(d.split()) >= 2])
+    for m in re.finditer(rf"^\s*(?:{_TYPES}|[A-Z]\w*)\s+(\w+)\s*\(([^)]*)\)\s*\{{", text, re.M):
+        _SIGS.setdefault(m.group(1), _signature(m.group(2)))
     for m in re.finditer(r"^#define\s+(\w+)\s+([0-9.]+)f?\s*$", text, re.M):
         env[m.group(1)] = F(float(m.group(2)))
     for m in re.finditer(r"^\s*const\s+float\s+(\w+)\s*=\s*([0-9.]+)f?\s*;", text, re.M):  # file-scope float constants
         env.setdefault(m.group(1), F(float(m.group(2))))
     env.update(defines or {})
     for name in names:
-        m = re.search(rf"^\s*{_TYPES}\s+{name}\s*\(([^)]*)\)\s*\{{", text, re.M)
+        m = re.search(rf"^\s*(?:{_TYPES}|[A-Z]\w*)\s+{name}\s*\(([^)]*)\)\s*\{{", text, re.M)
         assert m, f"{name} not found in {path}"
         depth, i = 1, m.end()
         while depth:
@@ -315,10 +488,15 @@ def load_functions(path, names, defines=None, env=None):
     return env
 
 
+def _read_shader(path):
+    text = open(path, encoding="utf-8", errors="replace").read()
+    return re.sub(r"\bas\b", "accel", text)  # the acceleration-structure binding is called `as`, a Python keyword
+
+
 def load_block(path, start_regex, name, params, prologue="", result="", env=None, defines=None, occurrence=1):
     """a brace-delimited block INSIDE a function (the text from the match of `start_regex`, which must end at its `{`, to the
     matching `}`) as a function `name(params)`: `prologue` statements run first, `result` is returned"""
-    text = open(path, encoding="utf-8", errors="replace").read()
+    text = _read_shader(path)
     ms = list(re.finditer(start_regex, text))
     assert len(ms) >= occurrence and text[ms[occurrence - 1].end() - 1] == "{", f"block not found: {start_regex}"
     m = ms[occurrence - 1]
@@ -327,9 +505,9 @@ def load_block(path, start_regex, name, params, prologue="", result="", env=None
         depth += {"{": 1, "}": -1}.get(text[i], 0)
         i += 1
     env = dict(BUILTINS) if env is None else env
-    env["U32"], env["F"], env["namespace"] = U32, F, namespace
+    env["U32"], env["F"], env["namespace"], env["_val"], env["new_struct"] = U32, F, namespace, _val, new_struct
     env.update(defines or {})
-    src = _translate(name, params, prologue + text[m.start():i])
+    src = _translate(name, params, prologue + text[m.start():i], copy_params=False)
     if result:
         src += f"\n    return {result}"
     exec(src, env)  # noqa: S102
@@ -341,9 +519,9 @@ def load_lines(path, first_line, last_line, must_start_with, name, params, resul
     lines = open(path, encoding="utf-8", errors="replace").read().split("\n")
     assert lines[first_line - 1].strip().startswith(must_start_with), lines[first_line - 1]
     env = dict(BUILTINS) if env is None else env
-    env["U32"], env["F"], env["namespace"] = U32, F, namespace
+    env["U32"], env["F"], env["namespace"], env["_val"], env["new_struct"] = U32, F, namespace, _val, new_struct
     env.update(defines or {})
-    src = _translate(name, params, "\n".join(lines[first_line - 1:last_line]))
+    src = _translate(name, params, "\n".join(lines[first_line - 1:last_line]), copy_params=False)
     if result:
         src += f"\n    return {result}"
     exec(src, env)  # noqa: S102

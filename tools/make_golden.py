@@ -9,6 +9,8 @@
   shipped_meshes.json facts parsed from Core/res/meshes/{cube,sphere}.glb (counts, bounds) and, for the
                       sphere, analytic-vs-mesh hit statistics of the brute-force intersector
   trace_cornell.npz   seeded rays + brute-force closest / any hits on C1 (oracle)
+  reference_frame_vectors.npz  main() of RayGen.rgen (+ closest-hit / miss shaders) EXECUTED from the reference's shader text for
+                      40 pixels x 4 frames x both passes (tools/glsl_frame.py): temporal + final reservoirs, colour, ray counts
   frame_small.npz     3 consecutive reference-mode frames of the small test scene (oracle):
                       prim ids, depth, both reservoir halves, direct, radiance, ray counts
 """
@@ -560,16 +562,76 @@ def reference_shader_vectors():
     np.savez_compressed(os.path.join(GOLD, "reference_shader_vectors.npz"), **out)
 
 
+FRAME_SCENE = dict(width=40, height=28)   # small_test_scene: spheres + emissive cubes + point lights + directional light
+FRAME_COUNT, FRAME_PIXELS = 5, 96
+
+
+def frame_sequence(sc, n_frames=FRAME_COUNT):
+    """the UBO sequence of the executed-frame pin (camera dolly; frame 0 has no history)"""
+    prev = None
+    for f in range(n_frames):
+        pos = np.asarray(sc.camera.pos, np.float32) + np.asarray((0.05, 0.0, 0.1), np.float32) * np.float32(f)
+        ubo = sc.ubo(f, cam_pos=pos)
+        yield f, ubo, (ubo if prev is None else prev)
+        prev = ubo
+
+
+def reference_frame_vectors(n_pixels=FRAME_PIXELS, out_path=None):
+    """main() of RayGen.rgen executed from the reference's shader text (tools/glsl_frame.py) for `n_pixels` pixels of each of
+    FRAME_COUNT consecutive frames, both passes: the temporal reservoir WriteInitialReservoirs stores, the final reservoir
+    ComputeAndWriteSpatialReservoirReuse stores and the colour main() stores (directional light + reservoir radiance +
+    BounceDiffuse through the executed closest-hit / miss shaders) -> tests/golden/reference_frame_vectors.npz"""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import glsl_frame as GF
+    sc = snk_scenes.small_test_scene(**FRAME_SCENE)
+    osc = O.OracleScene(sc)
+    fr = O.OracleFrame(osc)
+    ex = GF.FrameExec(sc, osc, shaders=os.path.join(REF, "Core/res/shaders"))
+    st = O.default_settings(mode=0)
+    rng = np.random.default_rng(20261019)
+    px_all, temporal, final, colour, nrays = [], [], [], [], []
+    for f, ubo, prev in frame_sequence(sc):
+        fr.set(ubo, prev, st)
+        fr.gbuffer()
+        ex.set_frame(O, fr, ubo, st)
+        ys, xs = np.nonzero(fr.read("prim") != 0xFFFFFFFF)
+        sel = rng.choice(len(ys), n_pixels, replace=False)
+        px = np.stack([xs[sel], ys[sel]], -1).astype(np.uint32)
+        ex.load_reservoirs()          # history = the oracle's final reservoirs of the previous frame
+        rows1, rays1 = [], []
+        for x, y in px:
+            row, _, rays = ex.run_pixel(int(x), int(y), 1)
+            rows1.append(row if row is not None else [np.nan] * 11)   # emissive pixels return before the pass writes
+            rays1.append([sum(r[0] == "closest" for r in rays), sum(r[0] == "any" for r in rays)])
+        fr.render_pass(1)
+        ex.load_reservoirs()          # spatial reuse reads the oracle's temporal half of THIS frame
+        rows0, cols0, rays0 = [], [], []
+        for x, y in px:
+            row, col, rays = ex.run_pixel(int(x), int(y), 0)
+            rows0.append(row if row is not None else [np.nan] * 11)
+            cols0.append(col)
+            rays0.append([sum(r[0] == "closest" for r in rays), sum(r[0] == "any" for r in rays)])
+        fr.render_pass(0)
+        px_all.append(px); temporal.append(rows1); final.append(rows0); colour.append(cols0); nrays.append(np.concatenate([rays1, rays0], 1))
+    out = dict(px=np.array(px_all, np.uint32), ref_temporal=np.array(temporal, np.float64), ref_final=np.array(final, np.float64),
+               ref_colour=np.array(colour, np.float32), ref_rays=np.array(nrays, np.uint32))
+    if out_path is not False:
+        np.savez_compressed(out_path or os.path.join(GOLD, "reference_frame_vectors.npz"), **out)
+    return out
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "source_facts":
         reference_source_facts()
         reference_layouts()
         reference_shader_vectors()
+        reference_frame_vectors()
         raise SystemExit(0)
     O.build_oracle()
     reference_source_facts()
     reference_layouts()
     reference_shader_vectors()
+    reference_frame_vectors()
     glm_vectors()
     shipped_meshes()
     shipped_scene()
