@@ -281,6 +281,24 @@ SNKPT_API int snkpt_set_rows(SnkPt* ctx, uint32_t row_begin, uint32_t row_end);
  * of rows [band ± (pass1_halo + max motion)] exchanged between band neighbours after every frame, a band
  * renders bit-identically to the same rows of a whole-frame context. Defaults 0, 0 (whole frame). */
 SNKPT_API int snkpt_set_halo(SnkPt* ctx, uint32_t pass1_halo, uint32_t gbuffer_halo);
+/* Row-band GROUPS: the frame strong-scaled over the GPUs of one node (BASELINE config 4; no counterpart in the reference,
+ * whose frame runs on one GPU — SURVEY §8e). Band `rank` of `world` equal bands (snkpt_group_band) is rendered by one
+ * context created with those rows; instead of re-rendering halo rows the library exchanges reservoir rows between band
+ * neighbours inside snkpt_render: the temporal reservoirs of `radius_rows` rows per edge after the temporal stage (spatial
+ * reuse, RayGen.rgen:470-506) and the final reservoirs of `margin_rows` rows per edge after the spatial stage (next
+ * frame's temporal reuse, :424-461). Only the G-buffer keeps a halo of max(radius, margin) + 1 rows. North-star mode.
+ * A band then equals the same rows of a whole-frame context bit for bit while per-frame motion stays below margin_rows.
+ *   snkpt_group_attach_nccl   one process per GPU: ncclSend / ncclRecv on the frame's stream (libnccl.so.2 resolved at run
+ *                             time, SNKPT_NCCL_LIB overrides); rank 0 makes the id (snkpt_group_unique_id), the host
+ *                             broadcasts the 128 bytes with whatever it has (torch.distributed in bench.py)
+ *   snkpt_group_attach_local  the contexts of ONE process (several GPUs, or one GPU in tests), ordered by rank: direct
+ *                             device-to-device copies; each context must then be driven by its own host thread */
+SNKPT_API void snkpt_group_band(uint32_t height, int world, int rank, uint32_t* row_begin, uint32_t* row_end);
+SNKPT_API int snkpt_group_unique_id(void* out128);
+SNKPT_API int snkpt_group_attach_nccl(SnkPt* ctx, int rank, int world, const void* id128, uint32_t radius_rows, uint32_t margin_rows);
+SNKPT_API int snkpt_group_attach_local(SnkPt** ctxs, int n, uint32_t radius_rows, uint32_t margin_rows);
+SNKPT_API int snkpt_group_detach(SnkPt* ctx);
+SNKPT_API int snkpt_group_info(SnkPt* ctx, int* rank, int* world, uint64_t* bytes_sent);
 /* invalidates temporal history (SceneInfoBufferSystem m_prev_frame_invalid) */
 SNKPT_API int snkpt_reset_history(SnkPt* ctx);
 
@@ -381,6 +399,9 @@ SNKPT_API int snkpt_get_stats(SnkPt* ctx, SnkPtStats* out);
 /* level 0: off. 1: bracket every kernel launch with CUDA events (cheap; what
  * bench.py runs with). 2: additionally run the work-counting diagnostic after
  * every traversal launch (timings of those frames are then not representative).
+ * 3: bracket only the traversal launches, on the stream each one runs on, and keep
+ * the north-star frame's two chains overlapped (levels 1 and 2 run one launch at a
+ * time so that every kernel is timed alone) — what bench.py's timed region uses.
  * Records accumulate (up to 2048) until the next snkpt_set_profiling call or
  * snkpt_get_launch_timings, which returns and clears them. */
 SNKPT_API int snkpt_set_profiling(SnkPt* ctx, uint32_t level);

@@ -53,6 +53,8 @@ def load_library() -> C.CDLL:
         "snkpt_get_stats": [vp, vp], "snkpt_synchronize": [vp], "snkpt_trace_rays": [vp, vp, u64, u32, vp, vp],
         "snkpt_count_work": [vp, vp, vp, u64, u32, vp, vp],
         "snkpt_set_profiling": [vp, u32], "snkpt_get_launch_timings": [vp, vp, u32, vp],
+        "snkpt_group_unique_id": [vp], "snkpt_group_attach_nccl": [vp, i32, i32, vp, u32, u32], "snkpt_group_attach_local": [vp, i32, u32, u32],
+        "snkpt_group_detach": [vp], "snkpt_group_info": [vp, vp, vp, vp],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -63,6 +65,8 @@ def load_library() -> C.CDLL:
     L.snkpt_particles_default_params.restype = None
     L.snkpt_frame_jitter.argtypes = [u32, u32, u32, vp, vp]
     L.snkpt_frame_jitter.restype = None
+    L.snkpt_group_band.argtypes = [u32, i32, i32, vp, vp]
+    L.snkpt_group_band.restype = None
     L.snkpt_destroy.argtypes = [vp]
     L.snkpt_destroy.restype = None
     L.snkpt_last_error.argtypes = [vp]
@@ -77,7 +81,8 @@ EXPORTS = ["snkpt_create", "snkpt_destroy", "snkpt_last_error", "snkpt_default_s
            "snkpt_set_frame", "snkpt_trace_primary", "snkpt_render", "snkpt_accumulate", "snkpt_read_output", "snkpt_read_aux",
            "snkpt_aux_size", "snkpt_write_reservoirs", "snkpt_device_ptr", "snkpt_get_stats", "snkpt_synchronize",
            "snkpt_trace_rays", "snkpt_count_work", "snkpt_set_profiling", "snkpt_get_launch_timings", "snkpt_taa_resolve", "snkpt_set_texture", "snkpt_read_output_async", "snkpt_read_output_wait", "snkpt_frame_jitter", "snkpt_particles_default_params",
-           "snkpt_particles_create", "snkpt_particles_write", "snkpt_particles_read", "snkpt_particles_update", "snkpt_particles_rays"]
+           "snkpt_particles_create", "snkpt_particles_write", "snkpt_particles_read", "snkpt_particles_update", "snkpt_particles_rays",
+           "snkpt_group_band", "snkpt_group_unique_id", "snkpt_group_attach_nccl", "snkpt_group_attach_local", "snkpt_group_detach", "snkpt_group_info"]
 
 CONFIG_DTYPE = np.dtype([("width", "<u4"), ("height", "<u4"), ("device", "<i4"), ("max_instances", "<u4"),
                          ("max_transforms", "<u4"), ("max_materials", "<u4"), ("row_begin", "<u4"), ("row_end", "<u4"),
@@ -146,6 +151,30 @@ def default_settings(**kw) -> np.ndarray:
     for k, v in kw.items():
         s[k] = v
     return s
+
+
+def group_band(height: int, world: int, rank: int) -> tuple[int, int]:
+    """rows [b0, b1) of band `rank` of `world` equal bands (snkpt_group_band)"""
+    a, b = C.c_uint32(), C.c_uint32()
+    load_library().snkpt_group_band(height, world, rank, C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def group_unique_id() -> bytes:
+    """NCCL unique id for snkpt_group_attach_nccl (made on rank 0, broadcast by the caller)"""
+    buf = C.create_string_buffer(128)
+    rc = load_library().snkpt_group_unique_id(buf)
+    if rc != 0:
+        raise SnkError(f"snkpt_group_unique_id failed ({rc}): libnccl.so.2 not found (SNKPT_NCCL_LIB)")
+    return buf.raw
+
+
+def group_attach_local(tracers, radius_rows: int = 30, margin_rows: int = 16):
+    """the contexts of ONE process (ordered by rank) become a row-band group; each must then be driven by its own host thread"""
+    arr = (C.c_void_p * len(tracers))(*[t.h for t in tracers])
+    rc = load_library().snkpt_group_attach_local(arr, len(tracers), radius_rows, margin_rows)
+    if rc != 0:
+        raise SnkError(f"snkpt_group_attach_local failed ({rc}): {load_library().snkpt_last_error(tracers[0].h).decode()}")
 
 
 class PathTracer:
@@ -291,6 +320,20 @@ class PathTracer:
 
     def reset_history(self):
         self._ck(self.L.snkpt_reset_history(self.h), "snkpt_reset_history")
+
+    # ---- row-band groups (strong scaling; include/snkpt.h "Row-band GROUPS") -------------------------------------
+    def group_attach_nccl(self, rank: int, world: int, unique_id: bytes, radius_rows: int = 30, margin_rows: int = 16):
+        """one process per GPU: this context renders band `rank` of `world`; reservoir rows travel by ncclSend / ncclRecv"""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._ck(self.L.snkpt_group_attach_nccl(self.h, rank, world, buf, radius_rows, margin_rows), "snkpt_group_attach_nccl")
+
+    def group_detach(self):
+        self._ck(self.L.snkpt_group_detach(self.h), "snkpt_group_detach")
+
+    def group_info(self):
+        r, w, b = C.c_int(), C.c_int(), C.c_uint64()
+        self._ck(self.L.snkpt_group_info(self.h, C.byref(r), C.byref(w), C.byref(b)), "snkpt_group_info")
+        return r.value, w.value, b.value
 
     def resize(self, width: int, height: int):
         """window resize (EditorLayer.cpp:351-366, :415-423): every per-pixel resource is recreated, the history is invalid"""

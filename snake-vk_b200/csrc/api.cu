@@ -84,6 +84,7 @@ namespace snk {
 void prof_reset(SnkPt*) {}  // records accumulate until read (snkpt_get_launch_timings) or re-armed (snkpt_set_profiling)
 int prof_begin(SnkPt* ctx, const char* name, uint64_t units, bool is_trace, bool any, cudaStream_t st) {
   if (!ctx->profiling || ctx->prof_n >= PROF_MAX) return -1;
+  if (ctx->profiling == 3 && !is_trace) return -1;  // level 3: traversal launches only
   ProfRec& r = ctx->prof[ctx->prof_n];
   if (!r.e0 && (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess)) return -1;
   memset(r.name, 0, sizeof(r.name));
@@ -98,7 +99,7 @@ void prof_end(SnkPt* ctx, int rec, cudaStream_t st) {
 int traced_launch(SnkPt* ctx, const char* name, const float4* rays, uint64_t n, bool any, SnkHit* hits_aos, float4* hits_soa,
                   uint32_t* inst_soa, float* vis_out, cudaStream_t st) {
   if (n == 0) return 0;
-  const bool count = ctx->profiling >= 2 && ctx->prof_n < PROF_MAX;
+  const bool count = ctx->profiling == 2 && ctx->prof_n < PROF_MAX;
   if (count && !hits_soa) {
     // the work counter needs the reported hit distance of every ray
     if (ctx->prof_hits.reserve(16 * n, false, st) == cudaSuccess) hits_soa = ctx->prof_hits.as<float4>();
@@ -141,11 +142,11 @@ void reset_ref_queues(SnkPt* ctx, cudaStream_t st) { cudaMemsetAsync(ctx->dev_co
 bool ns_overlap_enabled(const SnkPt* ctx) {
   static int v = -1;
   if (v < 0) { const char* e = getenv("SNKPT_NS_OVERLAP"); v = (e && e[0] == '0') ? 0 : 1; }
-  return v == 1 && ctx->profiling == 0;
+  return v == 1 && (ctx->profiling == 0 || ctx->profiling == 3);
 }
 
 int traced_launch_q(SnkPt* ctx, const char* name, const TraceSegs& segs, const RefQueue& q, cudaStream_t st, int spill_region) {
-  const bool count = ctx->profiling >= 2 && ctx->prof_n < PROF_MAX;
+  const bool count = ctx->profiling == 2 && ctx->prof_n < PROF_MAX;
   float* prof_t = nullptr;
   if (count && ctx->prof_hits.reserve(4ull * q.cap, false, st) == cudaSuccess) prof_t = ctx->prof_hits.as<float>();
   TraceScene S = ctx->trace_scene();
@@ -247,6 +248,15 @@ static void note_stream(SnkPt* ctx, cudaStream_t st) {
     cudaStreamWaitEvent(st, ctx->ev_frame_done, 0);
   }
   ctx->work_stream = st;
+}
+
+// Entry points that rewrite data an in-flight frame may still read (vertex positions, BVH nodes, textures, reservoirs) first wait
+// for the stream the frames run on: the host is allowed to run a frame ahead of the GPU (the internal chain streams of the
+// north-star frame always join that stream before the frame ends).
+static cudaError_t quiesce_frames(SnkPt* ctx) {
+  cudaError_t e = cudaStreamSynchronize(work_stream(ctx));
+  if (e == cudaSuccess && work_stream(ctx) != ctx->stream) e = cudaStreamSynchronize(ctx->stream);
+  return e;
 }
 
 static int upload_async(SnkPt* ctx, void* dst, const void* src, size_t bytes) {
@@ -352,6 +362,7 @@ void snkpt_destroy(SnkPt* ctx) {
   if (ctx->ev_frame_done) cudaEventDestroy(ctx->ev_frame_done);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->aux_stream) { cudaStreamSynchronize(ctx->aux_stream); cudaStreamDestroy(ctx->aux_stream); }
+  group_free(ctx);
   if (ctx->hi_stream) { cudaStreamSynchronize(ctx->hi_stream); cudaStreamDestroy(ctx->hi_stream); }
   if (ctx->ev_join_b) cudaEventDestroy(ctx->ev_join_b);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
@@ -405,6 +416,7 @@ int snkpt_set_rows(SnkPt* ctx, uint32_t row_begin, uint32_t row_end) {
 
 int snkpt_set_halo(SnkPt* ctx, uint32_t pass1_halo, uint32_t gbuffer_halo) {
   if (!ctx) return SNKPT_E_INVALID;
+  REQUIRE(!ctx->group, SNKPT_E_STATE, "snkpt_set_halo: the context belongs to a row-band group, which sets its own halo");
   REQUIRE(gbuffer_halo >= pass1_halo, SNKPT_E_INVALID, "snkpt_set_halo: the G-buffer halo must cover the pass-1 halo");
   ctx->halo_pass1 = pass1_halo; ctx->halo_gbuffer = gbuffer_halo;
   return SNKPT_OK;
@@ -449,8 +461,10 @@ static int build_blas(SnkPt* ctx, uint32_t blas_id, bool fresh, cudaStream_t st)
   BuildOutput out;
   out.nodes = ctx->blas_nodes.as<SnkNode8>(); out.node_offset = info.node_root; out.node_capacity = node_cap;
   out.tris = ctx->blas_tris.as<SnkTri>(); out.leaf_ids = nullptr; out.leaf_remap = nullptr; out.leaf_offset = info.tri_base;
-  ctx->stats.kernel_launches += launch_build(s, n, out, ctx->positions.as<float>(), ctx->indices.as<uint32_t>(), src.index_offset,
+  const int built = launch_build(s, n, out, ctx->positions.as<float>(), ctx->indices.as<uint32_t>(), src.index_offset,
                                              src.vertex_offset, st);
+  REQUIRE(built >= 0, SNKPT_E_CUDA, "BLAS build: the cooperative collapse kernel could not be launched");
+  ctx->stats.kernel_launches += built;
   cudaEventRecord(ctx->ev[7], st);
   uint32_t counters[16];
   CK(cudaMemcpyAsync(counters, s.counters, sizeof(counters), cudaMemcpyDeviceToHost, st));
@@ -496,6 +510,8 @@ int snkpt_upload_mesh(SnkPt* ctx, const float* positions, const float* normals, 
   }
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  CK(quiesce_frames(ctx));  // the pools may be re-allocated (MeshBufferManager::Resize) under frames in flight
+  note_stream(ctx, st);
   // append to the five global SoA buffers (MeshBufferManager.cpp:49-70)
   const size_t v0 = ctx->num_vertices, i0 = ctx->num_indices, nv = num_vertices, ni = num_indices;
   CK(ctx->positions.reserve(12 * (v0 + nv), true, st)); CK(ctx->normals.reserve(12 * (v0 + nv), true, st));
@@ -533,8 +549,10 @@ int snkpt_update_positions(SnkPt* ctx, const SnkMeshEntry* entry, const float* p
   REQUIRE(entry && positions, SNKPT_E_INVALID, "snkpt_update_positions: null argument");
   REQUIRE((uint64_t)entry->data_start_vertex_idx + num_vertices <= ctx->num_vertices, SNKPT_E_INVALID, "snkpt_update_positions: range");
   CK(cudaSetDevice(ctx->device));
-  CK(cudaMemcpyAsync(ctx->positions.as<char>() + 12ull * entry->data_start_vertex_idx, positions, 12ull * num_vertices, cudaMemcpyHostToDevice, ctx->stream));
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(quiesce_frames(ctx));  // the frame's shading and emissive sampling read these positions
+  cudaStream_t st = work_stream(ctx);
+  CK(cudaMemcpyAsync(ctx->positions.as<char>() + 12ull * entry->data_start_vertex_idx, positions, 12ull * num_vertices, cudaMemcpyHostToDevice, st));
+  CK(cudaStreamSynchronize(st));
   return SNKPT_OK;
 }
 
@@ -543,6 +561,8 @@ int snkpt_rebuild_blas(SnkPt* ctx, uint32_t blas_id, void* stream) {
   REQUIRE(blas_id < ctx->blas.size(), SNKPT_E_INVALID, "snkpt_rebuild_blas: bad id");
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  CK(quiesce_frames(ctx));  // frames in flight traverse these nodes
+  note_stream(ctx, st);
   // rebuild in place: the node/triangle regions of this BLAS were sized for its worst case at first build
   // only when it is the last BLAS in the pools; otherwise append a fresh copy
   const SnkBlasInfo old = ctx->blas[blas_id];
@@ -561,6 +581,8 @@ int snkpt_refit_blas(SnkPt* ctx, uint32_t blas_id, void* stream) {
   REQUIRE(blas_id < ctx->blas.size(), SNKPT_E_INVALID, "snkpt_refit_blas: bad id");
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  CK(quiesce_frames(ctx));  // frames in flight traverse these nodes and triangles
+  note_stream(ctx, st);
   SnkBlasInfo& info = ctx->blas[blas_id];
   if (info.tri_count == 0) return SNKPT_OK;
   if (ctx->blas_refit.size() < ctx->blas.size()) ctx->blas_refit.resize(ctx->blas.size());
@@ -598,7 +620,7 @@ int snkpt_set_texture(SnkPt* ctx, uint32_t tex_idx, uint32_t width, uint32_t hei
   REQUIRE(tex_idx < 4096, SNKPT_E_INVALID, "snkpt_set_texture: index (the descriptor array has 4096 slots)");
   REQUIRE((width == 0 && height == 0) || (rgba8 && width <= 16384 && height <= 16384 && width && height), SNKPT_E_INVALID, "snkpt_set_texture: size / null texels");
   CK(cudaSetDevice(ctx->device));
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(quiesce_frames(ctx));  // frames in flight sample the table and the texels
   if (ctx->h_tex.size() <= tex_idx) { ctx->h_tex.resize(tex_idx + 1, TexDev{nullptr, 0, 0, 0, 0}); ctx->tex_data.resize(tex_idx + 1); }
   DevBuf& buf = ctx->tex_data[tex_idx];
   buf.release();
@@ -678,7 +700,22 @@ int snkpt_set_instances(SnkPt* ctx, const SnkInstanceData* instances, const uint
     REQUIRE(instances[i].transform_idx < ctx->max_transforms && instances[i].material_idx < ctx->max_materials, SNKPT_E_INVALID,
             "snkpt_set_instances: transform / material index out of range");
   }
-  for (uint32_t i = 0; i < num_emissive; ++i) REQUIRE(emissive_idx[i] < count, SNKPT_E_INVALID, "snkpt_set_instances: emissive index out of range");
+  for (uint32_t i = 0; i < num_emissive; ++i) {
+    REQUIRE(emissive_idx[i] < count, SNKPT_E_INVALID, "snkpt_set_instances: emissive index out of range");
+    // the light-sampling stages pick a triangle of every listed instance (RayGen.rgen:311-342): it needs geometry
+    const uint32_t e = emissive_idx[i];
+    REQUIRE(blas_of_instance[e] != SNKPT_INVALID_INDEX && instances[e].num_mesh_indices >= 3, SNKPT_E_INVALID,
+            "snkpt_set_instances: an emissive-list entry references an instance without a BLAS / without triangles");
+  }
+  // stored reservoir samples name (instance, triangle) pairs: an emissive instance whose mesh range changed invalidates them
+  if (ctx->history_valid)
+    for (uint32_t i = 0; i < num_emissive && ctx->history_valid; ++i) {
+      const uint32_t e = emissive_idx[i];
+      if (e >= ctx->h_instances.size() || ctx->h_instances[e].num_mesh_indices != instances[e].num_mesh_indices ||
+          ctx->h_instances[e].mesh_buffer_index_offset != instances[e].mesh_buffer_index_offset ||
+          ctx->h_instances[e].mesh_buffer_vertex_offset != instances[e].mesh_buffer_vertex_offset)
+        ctx->history_valid = false;
+    }
   CK(cudaSetDevice(ctx->device));
   ctx->h_instances.assign(instances, instances + count);
   ctx->h_blas_of_instance.assign(blas_of_instance, blas_of_instance + count);
@@ -769,7 +806,9 @@ int snkpt_build_tlas(SnkPt* ctx, void* stream) {
   BuildOutput out;
   out.nodes = ctx->tlas_nodes.as<SnkNode8>(); out.node_offset = 0; out.node_capacity = ctx->max_instances;
   out.tris = nullptr; out.leaf_ids = ctx->tlas_leaf_ids.as<uint32_t>(); out.leaf_remap = ctx->valid_slots.as<uint32_t>(); out.leaf_offset = 0;
-  ctx->stats.kernel_launches += 2 + launch_build(s, n, out, nullptr, nullptr, 0, 0, st);
+  const int built = launch_build(s, n, out, nullptr, nullptr, 0, 0, st);
+  REQUIRE(built >= 0, SNKPT_E_CUDA, "snkpt_build_tlas: the cooperative collapse kernel could not be launched");
+  ctx->stats.kernel_launches += 2 + built;
   cudaEventRecord(ctx->ev[7], st);
   ctx->build_timing_pending = true;  // ms_build_last is read from ev[6..7] by snkpt_get_stats
   CK(cudaGetLastError());
@@ -873,16 +912,27 @@ int snkpt_render(SnkPt* ctx, const SnkRtSettings* settings, void* stream) {
   REQUIRE(settings->mode <= SNKPT_MODE_NORTHSTAR, SNKPT_E_INVALID, "snkpt_render: unknown mode");
   REQUIRE(settings->ris_iters >= 1 && settings->ris_iters <= 1024, SNKPT_E_INVALID, "snkpt_render: ris_iters");
   REQUIRE(settings->num_spatial_resamples >= 0 && settings->num_spatial_resamples <= 64, SNKPT_E_INVALID, "snkpt_render: num_spatial_resamples");
+  REQUIRE(settings->num_temporal_resamples >= 0, SNKPT_E_INVALID, "snkpt_render: num_temporal_resamples");
+  REQUIRE(settings->spp == 1, SNKPT_E_INVALID, "snkpt_render: spp must be 1 (more samples per pixel = more frames + snkpt_accumulate)");
+  REQUIRE(settings->m_cap >= 1 && settings->m_cap <= 65535, SNKPT_E_INVALID, "snkpt_render: m_cap");
+  REQUIRE(settings->neighbour_radius >= 0.0f && settings->neighbour_radius <= 4096.0f, SNKPT_E_INVALID, "snkpt_render: neighbour_radius (NaN / negative / beyond 4096 pixels)");
+  REQUIRE(settings->normal_threshold >= -1.0f && settings->normal_threshold <= 1.0f, SNKPT_E_INVALID, "snkpt_render: normal_threshold is a cosine");
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
   note_stream(ctx, st);
   fill_frame_dims(ctx);
   if (ctx->history_mode != settings->mode) ctx->history_valid = false;
   ctx->history_mode = settings->mode;
+  if (ctx->group) {
+    REQUIRE(settings->mode == SNKPT_MODE_NORTHSTAR, SNKPT_E_STATE, "snkpt_render: a row-band group renders the north-star mode (reference mode: snkpt_set_halo)");
+    REQUIRE(settings->neighbour_radius >= 0.0f && (uint32_t)ceilf(settings->neighbour_radius) + 1u <= group_gbuffer_halo(ctx), SNKPT_E_INVALID,
+            "snkpt_render: neighbour_radius exceeds the rows the group exchanges");
+  }
   int rc = settings->mode == SNKPT_MODE_REFERENCE ? launch_reference_frame(ctx, *settings, st) : launch_northstar_frame(ctx, *settings, st);
   if (rc < 0) return rc;
   CK(cudaGetLastError());
-  ctx->history_valid = true;
+  // a frame without the reservoir stages writes no history: the next ReSTIR frame must not reuse older reservoirs as "previous frame"
+  ctx->history_valid = !(settings->flags & SNKPT_RT_NO_RESTIR);
   return SNKPT_OK;
 }
 
@@ -1007,7 +1057,7 @@ int snkpt_write_reservoirs(SnkPt* ctx, uint32_t half, const SnkPixelReservoir* s
     memcpy(&pl[count + i], &src[i].object_instance_idx, 16);
     memcpy(&pl[2 * (size_t)count + i], &src[i].w_sum_em, 16);
   }
-  CK(cudaStreamSynchronize(ctx->stream));
+  CK(quiesce_frames(ctx));
   for (int k = 0; k < 3; ++k)
     CK(cudaMemcpy(ctx->planes.res[half][k] + first_pixel, pl.data() + (size_t)k * count, 16 * (size_t)count, cudaMemcpyHostToDevice));
   return SNKPT_OK;
@@ -1096,7 +1146,7 @@ int snkpt_get_stats(SnkPt* ctx, SnkPtStats* out) {
 
 int snkpt_set_profiling(SnkPt* ctx, uint32_t level) {
   if (!ctx) return SNKPT_E_INVALID;
-  REQUIRE(level <= 2, SNKPT_E_INVALID, "snkpt_set_profiling: level");
+  REQUIRE(level <= 3, SNKPT_E_INVALID, "snkpt_set_profiling: level");
   ctx->profiling = level;
   ctx->prof_n = 0;
   return SNKPT_OK;
@@ -1231,6 +1281,7 @@ int snkpt_trace_rays(SnkPt* ctx, const SnkRay* rays, uint64_t count, uint32_t fl
   if (count == 0) return SNKPT_OK;
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  note_stream(ctx, st);  // after the TLAS build / uploads enqueued on the previous stream
   const bool any = flags & SNKPT_RAY_ANY;
   const float4* d_rays; SnkHit* d_hits;
   if (flags & SNKPT_RAY_DEVICE_PTRS) { d_rays = (const float4*)rays; d_hits = hits; }
@@ -1259,6 +1310,7 @@ int snkpt_count_work(SnkPt* ctx, const SnkRay* rays, const SnkHit* hits, uint64_
   if (count == 0) return SNKPT_OK;
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  note_stream(ctx, st);
   const float4* d_rays; const SnkHit* d_hits; uint32_t* d_out;
   if (flags & SNKPT_RAY_DEVICE_PTRS) { d_rays = (const float4*)rays; d_hits = hits; d_out = out3; }
   else {

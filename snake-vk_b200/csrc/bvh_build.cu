@@ -6,6 +6,8 @@
 // latency-bound stage: one thread per wide node, fed through a ticket queue).
 #include "bvh_build.cuh"
 
+#include <atomic>
+
 #include <cfloat>
 
 #include <cooperative_groups.h>
@@ -1439,17 +1441,23 @@ int launch_build(BuildScratch& s, uint32_t n, const BuildOutput& out, const floa
   a.positions = positions; a.indices = indices; a.index_offset = index_offset; a.vertex_offset = vertex_offset;
     a.leaf_max = out.tris ? LEAF_MAX_BLAS : LEAF_MAX_TLAS;
   {
-    static int ctas_per_sm = 0, sms = 0;
-    if (!ctas_per_sm) {
-      int dev = 0;
-      cudaGetDevice(&dev);
+    // resident grid of the cooperative launch, per device (a process may drive contexts on several GPUs, from several threads)
+    static std::atomic<int> resident_of_device[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int slot = (dev >= 0 && dev < 64) ? dev : 0;
+    int resident_i = resident_of_device[slot].load(std::memory_order_relaxed);
+    if (resident_i == 0) {
+      int sms = 0, ctas_per_sm = 0;
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_collapse, 128, 0);
       if (ctas_per_sm < 1) ctas_per_sm = 1;
+      resident_i = (sms > 0 ? sms : 1) * ctas_per_sm;
+      resident_of_device[slot].store(resident_i, std::memory_order_relaxed);
     }
-    const uint32_t want = (uint32_t)(((uint64_t)cap * (SNK_COLLAPSE_OCTET ? 8 : 1) + 127) / 128), resident = (uint32_t)(sms * ctas_per_sm);
+    const uint32_t want = (uint32_t)(((uint64_t)cap * (SNK_COLLAPSE_OCTET ? 8 : 1) + 127) / 128), resident = (uint32_t)resident_i;
     void* args[] = {&a};
-    cudaLaunchCooperativeKernel((const void*)k_collapse, dim3(want < resident ? want : resident), dim3(128), args, 0, st);
+    if (cudaLaunchCooperativeKernel((const void*)k_collapse, dim3(want < resident ? want : resident), dim3(128), args, 0, st) != cudaSuccess) return -1;
     ++launches;
   }
   return launches;

@@ -103,6 +103,7 @@ struct SceneDev {
   uint32_t num_textures;
 };
 
+struct GroupState;  // group.cu: row-band group this context belongs to (halo exchange of reservoir rows)
 }  // namespace snk
 
 struct SnkPt {
@@ -111,6 +112,7 @@ struct SnkPt {
   std::string err;
   uint32_t W = 0, H = 0, row0 = 0, row1 = 0;
   uint32_t halo_pass1 = 0, halo_gbuffer = 0;  // extra rows around the band (snkpt_set_halo)
+  snk::GroupState* group = nullptr;           // row-band group (snkpt_group_attach_*): reservoir rows are exchanged, not re-rendered
   uint32_t max_instances = 4096, max_transforms = 4096, max_materials = 4096;
 
   // mesh pools

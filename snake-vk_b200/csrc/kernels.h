@@ -36,6 +36,12 @@ RefQueue ref_queue(SnkPt* ctx, int k, uint32_t cap, uint32_t first_ref = 0);
 int reserve_ref_queues(SnkPt* ctx, uint32_t cap, cudaStream_t st);
 void reset_ref_queues(SnkPt* ctx, cudaStream_t st);
 
+// group.cu — row-band groups: exchange of reservoir rows between band neighbours (kind 0: temporal half after the temporal
+// stage, kind 1: final half after the spatial stage); no-ops without a group
+int group_exchange(SnkPt* ctx, int kind, cudaStream_t st);
+uint32_t group_gbuffer_halo(const SnkPt* ctx);
+void group_free(SnkPt* ctx);
+
 // particles.cu — Particle.comp Init; one sub-step of ParticleSystem::UpdateParticles (keys, sort, start indices, update): P -> out
 int launch_particles_init(SnkParticle* P, uint32_t n, cudaStream_t st);
 int launch_particles_substep(SnkPt* ctx, const SnkParticle* P, SnkParticle* out, uint32_t n, uint32_t* cell_start, const SnkPhysicsParams& prm,

@@ -528,9 +528,13 @@ int restir_ns_reuse(SnkPt* ctx, const SnkRtSettings& s, const RefQueue& q, cudaS
   k_rs_temporal<<<(stage_threads(L.f1.W, L.f1.row1 - L.f1.row0) + 127) / 128, 128, 0, st>>>(D, L.f1, ctx->planes, L.rp, L.B, L.npix1);
   prof_end(ctx, rec, st);
   cudaEventRecord(ctx->ev[3], st);
+  // row-band group: the neighbours' temporal reservoirs of the rows spatial reuse can reach arrive here ...
+  if (ctx->group) { const int xr = group_exchange(ctx, 0, st); if (xr < 0) return xr; }
   rec = prof_begin(ctx, "rs_spatial", L.npix, false, false, st);
   k_rs_spatial<<<(stage_threads(ctx->fc.W, ctx->fc.row1 - ctx->fc.row0) + 127) / 128, 128, 0, st>>>(D, ctx->fc, ctx->planes, L.rp, L.npix);
   prof_end(ctx, rec, st);
+  // ... and the final reservoirs the next frame's temporal reuse may reproject to leave as soon as they exist
+  if (ctx->group) { const int xr = group_exchange(ctx, 1, st); if (xr < 0) return xr; }
   rec = prof_begin(ctx, "rs_final", L.npix, false, false, st);
   k_rs_final<<<(stage_threads(ctx->fc.W, ctx->fc.row1 - ctx->fc.row0) + 127) / 128, 128, 0, st>>>(D, ctx->fc, ctx->planes, L.rp, L.B, L.npix, counters, q.refs, q.count);
   prof_end(ctx, rec, st);
