@@ -593,6 +593,10 @@ def strong_scaling(args, snk, torch, dist, sc, whole, stream, rank, world, local
     for _ in range(args.warmup):
         lb.step()
     ms_b, rays_b, launches_b = timed(torch, lb, steps, barrier)
+    # every rank's own time and ray count (bands differ in content: load balance) beside the max that defines the frame
+    mine = torch.tensor([ms_b / steps, rays_b / steps], device=f"cuda:{local}", dtype=torch.float64)
+    per_rank = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(per_rank, mine)
     ms_b, rays_b, launches_b = reduce_max_sum([ms_b, float(rays_b), float(launches_b)])
     ms_b /= steps
     sent = pb.group_info()[2]
@@ -602,7 +606,8 @@ def strong_scaling(args, snk, torch, dist, sc, whole, stream, rank, world, local
         whole.close()
     return {"n_gpus": world, "resolution": [W, H], "ms_per_frame": ms_b, "ms_per_frame_1gpu": ms_w, "efficiency_vs_n1": ms_w / (world * ms_b),
             "speedup": ms_w / ms_b, "mrays_per_s": rays_b / steps / (ms_b * 1e-3) / 1e6, "gpu_launches_per_frame_all_ranks": launches_b / steps,
-            "verified_bit_exact_vs_whole_frame": bool(verify), "nccl_bytes_sent_rank0_total": int(sent), "steps": steps}
+            "verified_bit_exact_vs_whole_frame": bool(verify), "nccl_bytes_sent_rank0_total": int(sent), "steps": steps,
+            "per_rank_ms": [round(float(t[0]), 4) for t in per_rank], "per_rank_mrays": [round(float(t[1]) / 1e6, 3) for t in per_rank]}
 
 
 def other_configs(args, snk, torch, stream):
