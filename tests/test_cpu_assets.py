@@ -100,3 +100,18 @@ def test_shipped_project_template_scene(snk, assets):
     lights = np.frombuffer(f["lights"], np.float32)
     assert np.allclose(lights[4:7], (0.0, 0.0, 1.0)) and np.allclose(lights[0:3], (1, 1, 1))     # spherical (0, 0) = +z
     fe.close()
+
+
+def test_committed_mesh_arrays_equal_the_shipped_glb_files(snk, assets):
+    """tests/golden/shipped_mesh_arrays.npz (what the GPU tests render: the box has no /root/reference) = load_glb of the .glb files"""
+    d = np.load(os.path.join(GOLD, "shipped_mesh_arrays.npz"))
+    facts = json.load(open(os.path.join(GOLD, "shipped_meshes.json")))
+    for name in ("cube", "sphere"):
+        assert d[f"{name}_positions"].shape[0] == facts[name]["num_vertices"] and d[f"{name}_indices"].size == 3 * facts[name]["num_triangles"]
+        assert np.allclose(d[f"{name}_positions"].min(0), facts[name]["bounds_lo"]) and np.allclose(d[f"{name}_positions"].max(0), facts[name]["bounds_hi"])
+        assert np.allclose(np.linalg.norm(d[f"{name}_normals"], axis=1), 1.0, atol=1e-3)
+        ref = f"/root/reference/Core/res/meshes/{name}.glb"
+        if os.path.exists(ref):
+            m = assets.load_glb(ref)
+            for k in ("positions", "normals", "tangents", "uvs", "indices", "submeshes"):
+                assert np.array_equal(getattr(m, k), d[f"{name}_{k}"]), (name, k)

@@ -115,6 +115,17 @@ def shipped_meshes():
     json.dump(out, open(os.path.join(GOLD, "shipped_meshes.json"), "w"), indent=1)
 
 
+def shipped_mesh_arrays():
+    """vertex / index arrays of Core/res/meshes/{cube,sphere}.glb as snake-vk_b200.assets.load_glb reads them: the GPU box has no
+    /root/reference, and tests/test_gpu_assets.py renders exactly these meshes -> tests/golden/shipped_mesh_arrays.npz"""
+    out = {}
+    for name in ("cube", "sphere"):
+        m = assets.load_glb(os.path.join(REF, "Core", "res", "meshes", f"{name}.glb"))
+        for k in ("positions", "normals", "tangents", "uvs", "indices", "submeshes"):
+            out[f"{name}_{k}"] = np.ascontiguousarray(getattr(m, k))
+    np.savez_compressed(os.path.join(GOLD, "shipped_mesh_arrays.npz"), **out)
+
+
 def trace_cornell():
     sc = snk_scenes.cornell(64, 64)
     rng = np.random.default_rng(11)
@@ -634,6 +645,7 @@ if __name__ == "__main__":
     reference_frame_vectors()
     glm_vectors()
     shipped_meshes()
+    shipped_mesh_arrays()
     shipped_scene()
     trace_cornell()
     frame_small()
