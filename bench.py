@@ -64,6 +64,13 @@ def make_scene(snk, name: str, width: int, height: int):
         return S.c4(v, width=width, height=height), f"C4 {v}: floor + 2343 icospheres = 2,999,042 tris" + (" in one BLAS" if v == "flat" else ", 2344 instances")
     if name == "cornell":
         return S.cornell(width, height, True), "C1 Cornell box, 32 tris"
+    if name == "shipped":
+        # the engine's own meshes (Core/res/meshes/sphere.glb, cube.glb) from the committed arrays (the GPU box has no /root/reference)
+        d = np.load(os.path.join(ROOT, "tests", "golden", "shipped_mesh_arrays.npz"))
+        mesh = lambda n: S.Mesh(*(np.ascontiguousarray(d[f"{n}_{k}"]) for k in ("positions", "normals", "uvs", "tangents", "indices", "submeshes")))
+        sc = S.shipped_field(mesh("sphere"), mesh("cube"), width=width, height=height)
+        tris = sum((sc.meshes[e.mesh].indices.size // 3) for e in sc.entities)
+        return sc, f"shipped meshes: 600 instances of Core/res/meshes/sphere.glb + cube.glb over a cube floor = {tris:,} tris, {len(sc.entities)} instances, 18 emissive cubes, 16 point lights"
     raise SystemExit(f"unknown scene {name}")
 
 
@@ -618,7 +625,7 @@ def other_configs(args, snk, torch, stream):
     def barrier():
         torch.cuda.synchronize()
 
-    for name, (w, h) in (("c2m", (1920, 1080)), ("c3", (1920, 1080)), ("c4", (3840, 2160))):
+    for name, (w, h) in (("c2m", (1920, 1080)), ("c3", (1920, 1080)), ("shipped", (1920, 1080)), ("c4", (3840, 2160))):
         sc, desc = make_scene(snk, name, w, h)
         pt = snk.PathTracer(w, h)
         pt.upload_scene(sc)

@@ -7,6 +7,7 @@
 #include "bvh_build.cuh"
 
 #include <atomic>
+#include <cstdlib>
 
 #include <cfloat>
 
@@ -237,11 +238,12 @@ __device__ __forceinline__ unsigned long long morton_key(const float4* __restric
   const float qz = fminf(fmaxf((0.5f * (a.z + b.z) - lz) * sz, 0.f), 2097151.f);
   return (expand21((unsigned long long)qx) << 2) | (expand21((unsigned long long)qy) << 1) | expand21((unsigned long long)qz);
 }
+// `drop` low key bits are shifted out: the radix sort then needs (63 - drop) / 8 passes instead of 8 (launch_build)
 __global__ void k_morton(const float4* __restrict__ prim_lo, const float4* __restrict__ prim_hi, uint32_t n,
-                         const uint32_t* __restrict__ counters, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+                         const uint32_t* __restrict__ counters, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, int drop) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  keys[i] = morton_key(prim_lo, prim_hi, i, counters);
+  keys[i] = morton_key(prim_lo, prim_hi, i, counters) >> drop;
   vals[i] = i;
 }
 
@@ -1304,6 +1306,84 @@ __global__ void k_refit_nodes(SnkNode8* __restrict__ nodes, uint32_t node_root, 
   }
 }
 
+
+// Refit, 8 lanes per wide node (lane s = child slot s), bottom-up: every lane rebuilds ITS slot — a leaf slot gathers the moved
+// vertices of its (<= 3) triangles, rewrites the 48-byte records and takes their box, an inner slot reads its child's box — then
+// the node box is a shuffle reduction over the 8 lanes, every lane quantises and stores its own 6 bytes and lane 0 the header.
+// Replaces k_refit_tris + one thread per node (local arrays of 8 boxes, 80-byte struct copies): 1.41 -> see profiles/ at 10 M.
+__global__ void __launch_bounds__(256) k_refit_nodes8(SnkNode8* __restrict__ nodes, uint32_t node_root, uint32_t node_count, SnkTri* __restrict__ tris,
+                                                      const float* __restrict__ positions, const uint32_t* __restrict__ indices, uint32_t index_offset,
+                                                      uint32_t vertex_offset, const uint32_t* __restrict__ parent, uint32_t* __restrict__ arrive,
+                                                      float4* __restrict__ node_box) {
+  const uint32_t lane = threadIdx.x & 31u, s = lane & 7u, gshift = lane & 24u, gm = 0xFFu << gshift;
+  uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+  if (w >= node_count) return;
+  {
+    const uint4 h0 = *reinterpret_cast<const uint4*>(nodes + node_root + w);
+    if ((h0.w >> 24) != 0u) return;  // only nodes without inner children start a climb (uniform over the 8 lanes)
+  }
+  while (true) {
+    uint4* np = reinterpret_cast<uint4*>(nodes + node_root + w);
+    const uint4 h0 = __ldcg(np), h1 = __ldcg(np + 1);
+    const uint32_t imask = h0.w >> 24, child_base = h1.x, tri_base = h1.y;
+    const uint32_t meta = ((s < 4 ? h1.z : h1.w) >> (8 * (s & 3))) & 0xFFu;
+    float3 lo = make_float3(FLT_MAX, FLT_MAX, FLT_MAX), hi = make_float3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
+    if (meta != 0u) {
+      if ((meta & 0x18u) == 0x18u) {
+        const uint32_t c = child_base - node_root + __popc(imask & ((1u << s) - 1u));
+        const float4 l = __ldcg(&node_box[2ull * c]), h = __ldcg(&node_box[2ull * c + 1]);
+        lo = make_float3(l.x, l.y, l.z); hi = make_float3(h.x, h.y, h.z);
+      } else {
+        const uint32_t first = tri_base + (meta & 31u), cnt = __popc(meta >> 5);
+        for (uint32_t k = 0; k < cnt; ++k) {
+          float4* t = reinterpret_cast<float4*>(tris + first + k);
+          const uint32_t prim = __float_as_uint(t[0].w);
+          const uint32_t* ip = indices + index_offset + 3ull * prim;
+          const uint32_t iv[3] = {ip[0] + vertex_offset, ip[1] + vertex_offset, ip[2] + vertex_offset};
+#pragma unroll
+          for (int v = 0; v < 3; ++v) {
+            const float x = positions[3ull * iv[v]], y = positions[3ull * iv[v] + 1], z = positions[3ull * iv[v] + 2];
+            t[v] = make_float4(x, y, z, v == 0 ? __uint_as_float(prim) : 0.f);
+            lo = make_float3(fminf(lo.x, x), fminf(lo.y, y), fminf(lo.z, z));
+            hi = make_float3(fmaxf(hi.x, x), fmaxf(hi.y, y), fmaxf(hi.z, z));
+          }
+        }
+        lo = make_float3(pad_dn(lo.x), pad_dn(lo.y), pad_dn(lo.z));
+        hi = make_float3(pad_up(hi.x), pad_up(hi.y), pad_up(hi.z));
+      }
+    }
+    float3 nlo = lo, nhi = hi;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      nlo.x = fminf(nlo.x, __shfl_xor_sync(gm, nlo.x, o)); nlo.y = fminf(nlo.y, __shfl_xor_sync(gm, nlo.y, o)); nlo.z = fminf(nlo.z, __shfl_xor_sync(gm, nlo.z, o));
+      nhi.x = fmaxf(nhi.x, __shfl_xor_sync(gm, nhi.x, o)); nhi.y = fmaxf(nhi.y, __shfl_xor_sync(gm, nhi.y, o)); nhi.z = fmaxf(nhi.z, __shfl_xor_sync(gm, nhi.z, o));
+    }
+    const int be[3] = {quant_exp(nhi.x - nlo.x), quant_exp(nhi.y - nlo.y), quant_exp(nhi.z - nlo.z)};
+    uint8_t* bytes = reinterpret_cast<uint8_t*>(np);
+    if (meta != 0u) {
+      uint8_t ql[3], qh[3];
+      quantise_child(make_float4(nlo.x, nlo.y, nlo.z, 0.f), be, make_float4(lo.x, lo.y, lo.z, 0.f), make_float4(hi.x, hi.y, hi.z, 0.f), ql, qh);
+      bytes[32 + s] = ql[0]; bytes[40 + s] = ql[1]; bytes[48 + s] = ql[2];
+      bytes[56 + s] = qh[0]; bytes[64 + s] = qh[1]; bytes[72 + s] = qh[2];
+    }
+    uint32_t next = EMPTY;
+    if (s == 0) {
+      np[0] = make_uint4(__float_as_uint(nlo.x), __float_as_uint(nlo.y), __float_as_uint(nlo.z),
+                         (uint32_t)be[0] | ((uint32_t)be[1] << 8) | ((uint32_t)be[2] << 16) | (imask << 24));
+      node_box[2ull * w] = make_float4(nlo.x, nlo.y, nlo.z, 0.f); node_box[2ull * w + 1] = make_float4(nhi.x, nhi.y, nhi.z, 0.f);
+      const uint32_t par = parent[w];
+      if (par != EMPTY) {
+        __threadfence();
+        const uint32_t need = __popc((uint32_t)nodes[node_root + par].imask);
+        if (atomicAdd(&arrive[par], 1u) + 1u >= need) { __threadfence(); next = par; }  // the last child continues with the parent
+      }
+    }
+    next = __shfl_sync(gm, next, gshift);
+    if (next == EMPTY) return;
+    w = next;
+  }
+}
+
 template <class T>
 cudaError_t alloc(T*& p, size_t count) {
   return cudaMalloc(reinterpret_cast<void**>(&p), count * sizeof(T));
@@ -1351,8 +1431,13 @@ int launch_refit(RefitState& r, SnkNode8* nodes, uint32_t node_root, uint32_t no
     ++launches;
   }
   cudaMemsetAsync(r.arrive, 0, sizeof(uint32_t) * node_count, st);
+#ifdef SNK_REFIT_ONE_THREAD
   if (tri_count) { k_refit_tris<<<(tri_count + 255) / 256, 256, 0, st>>>(tris, tri_base, tri_count, positions, indices, index_offset, vertex_offset); ++launches; }
   k_refit_nodes<<<(node_count + 127) / 128, 128, 0, st>>>(nodes, node_root, node_count, tris, r.parent, r.arrive, r.node_box);
+#else
+  k_refit_nodes8<<<(unsigned)(((uint64_t)node_count * 8 + 255) / 256), 256, 0, st>>>(nodes, node_root, node_count, tris, positions, indices, index_offset, vertex_offset,
+                                                                                    r.parent, r.arrive, r.node_box);
+#endif
   return launches + 1;
 }
 void refit_free(RefitState& r) { cudaFree(r.parent); cudaFree(r.arrive); cudaFree(r.node_box); r = RefitState(); }
@@ -1414,11 +1499,20 @@ int launch_build(BuildScratch& s, uint32_t n, const BuildOutput& out, const floa
     return 1;
   }
 #endif
-  k_morton<<<g, 256, 0, st>>>(s.prim_lo, s.prim_hi, n, s.counters, s.keys[0], s.vals[0]); ++launches;
+  // Morton resolution: 63 bits (21 per axis) are far more than n primitives can use; the keys keep 3 * b bits with
+  // 2^(3b) >= 4096 n cells (at least 13 bits per axis beyond 4 M primitives, 10 below), i.e. 5 or 4 radix passes instead of 8.
+  // Equal keys are ordered by primitive index (stable sort, Karras's tie-break), so the hierarchy stays well defined.
+  // SNKPT_SORT_PASSES=8 restores the full keys (A/B: profiles/r04m_*).
+  static int forced_passes = -1;
+  if (forced_passes < 0) { const char* e = getenv("SNKPT_SORT_PASSES"); forced_passes = e ? atoi(e) : 0; }
+  int passes = forced_passes >= 1 && forced_passes <= 8 ? forced_passes : (n > (4u << 20) ? 5 : 4);
+  const int axis_bits = passes == 8 ? 21 : (8 * passes) / 3;
+  const int key_bits = 3 * axis_bits;
+  k_morton<<<g, 256, 0, st>>>(s.prim_lo, s.prim_hi, n, s.counters, s.keys[0], s.vals[0], 63 - key_bits); ++launches;
   int cur = 0;
   if (n > 1) {
     const uint32_t nb = (n + SORT_TILE - 1) / SORT_TILE;
-    for (int shift = 0; shift < 64; shift += 8) {
+    for (int shift = 0; shift < key_bits; shift += 8) {
       k_sort_hist<<<nb, SORT_THREADS, 0, st>>>(s.keys[cur], n, shift, s.block_hist, nb);
       k_scan_rows<<<256, 256, 0, st>>>(s.block_hist, nb, s.digit_total);
       k_scan_digits<<<1, 256, 0, st>>>(s.digit_total);

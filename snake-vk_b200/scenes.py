@@ -481,6 +481,30 @@ def sphere_field(n_spheres: int, subdiv: int, box=(60.0, 12.0, 30.0), seed=0x5EE
     return sc
 
 
+def shipped_field(sphere: Mesh, cube: Mesh, n=600, box=(60.0, 12.0, 30.0), seed=0x5EED0006, width=1920, height=1080) -> Scene:
+    """the meshes the engine ships (Core/res/meshes/sphere.glb: 960 triangles, cube.glb: 12) instanced `n` times over a cube floor,
+    one emissive cube lamp per 32 instances, 16 point lights (north_star: throughput on any mesh shipped in Core/res)"""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    bx, by, bz = box
+    specs = [(c, 0.5, 0.0, 0) for c in _PALETTE] + [((20.0, 18.0, 14.0), 0.5, 0.0, MAT_FLAG_EMISSIVE)]
+    mats = make_materials(specs)
+    ents = [Entity(1, trs((0.0, -1.0, 0.0), (0, 0, 0), (bx, 1.0, bz)), [0])]
+    pos = rng.uniform((-bx / 2, 0.5, -bz / 2), (bx / 2, by, bz / 2), (n, 3))
+    scale = rng.uniform(0.5, 2.0, n)
+    euler = rng.uniform(0, 360.0, (n, 3))
+    mat_id = rng.integers(1, len(_PALETTE), n)
+    for i in range(n):
+        if i % 32 == 31:
+            ents.append(Entity(1, trs(pos[i], euler[i], (0.15,) * 3), [len(_PALETTE)]))
+        else:
+            ents.append(Entity(0 if i % 4 else 1, trs(pos[i], euler[i], (scale[i],) * 3 if i % 4 else (0.6 * scale[i],) * 3), [int(mat_id[i])]))
+    sc = Scene("shipped-field", width, height, [sphere, cube], ents, mats, Camera((0.0, by * 0.45, -bz * 0.5 - 8.0), (0.0, -0.05, 1.0)))
+    sc.dir_light_colour = (1.0, 1.0, 1.0)
+    sc.dir_light_spherical = (0.8, 0.9)
+    sc.pointlights = default_pointlights(rng, 16, (-bx / 2, 1.0, -bz / 2), (bx / 2, by, bz / 2))
+    return sc
+
+
 def c2(variant="instanced", subdiv=3, width=1920, height=1080) -> Scene:
     """C2 Sponza-scale: 204 icospheres (1280 tris) + floor = 261,122 tris; subdiv 4 → 1.04 M."""
     return sphere_field(204, subdiv, variant=variant, width=width, height=height, name="C2")
