@@ -173,6 +173,7 @@ TraceScene SnkPt::trace_scene() const {
   S.blas_nodes = blas_nodes.as<uint4>();
   S.tris = blas_tris.as<float4>();
   S.inst = inst_recs.as<SnkInstRec>();
+  S.inst_sphere = inst_sphere.as<float4>();
   S.overflow = dev_counters.as<uint32_t>();
   S.tlas_node_count = (tlas_built && tlas_prims) ? 1u : 0u;
   S.spill = trav_spill.as<uint2>();
@@ -248,6 +249,52 @@ static void note_stream(SnkPt* ctx, cudaStream_t st) {
     cudaStreamWaitEvent(st, ctx->ev_frame_done, 0);
   }
   ctx->work_stream = st;
+}
+
+// object-space bounding sphere of a vertex range: centre of its box, largest distance to it (float64, rounded outwards later)
+static void sphere_of_vertices(const float* pos, uint32_t count, BlasSphere& sp) {
+  sp.r = -1.0;
+  if (!pos || count == 0) return;
+  double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+  for (uint32_t v = 0; v < count; ++v)
+    for (int k = 0; k < 3; ++k) {
+      const double x = pos[3ull * v + k];
+      if (!(x == x) || x > 1e30 || x < -1e30) return;  // NaN / huge coordinates: no sphere, no culling
+      lo[k] = x < lo[k] ? x : lo[k]; hi[k] = x > hi[k] ? x : hi[k];
+    }
+  for (int k = 0; k < 3; ++k) sp.c[k] = 0.5 * (lo[k] + hi[k]);
+  double r2 = 0.0;
+  for (uint32_t v = 0; v < count; ++v) {
+    double d2 = 0.0;
+    for (int k = 0; k < 3; ++k) { const double d = pos[3ull * v + k] - sp.c[k]; d2 += d * d; }
+    r2 = d2 > r2 ? d2 : r2;
+  }
+  sp.r = sqrt(r2);
+}
+
+// world-space bounding sphere of an instance: centre = M c, radius = r * (upper bound of the largest singular value of mat3(M))
+static void world_sphere(const float* M /* column-major 4x4 */, const BlasSphere& sp, float out[4]) {
+  out[0] = out[1] = out[2] = 0.f; out[3] = -1.f;
+  if (sp.r < 0.0) return;
+  double B[3][3];  // B = A^T A, A = upper 3x3 (columns M[0..2], M[4..6], M[8..10])
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) {
+      double s = 0.0;
+      for (int k = 0; k < 3; ++k) s += (double)M[4 * i + k] * (double)M[4 * j + k];
+      B[i][j] = s;
+    }
+  // largest eigenvalue of B <= min(largest Gershgorin disc, trace): exact for a rotation times a uniform scale
+  double g = 0.0, tr = B[0][0] + B[1][1] + B[2][2];
+  for (int i = 0; i < 3; ++i) { const double row = fabs(B[i][0]) + fabs(B[i][1]) + fabs(B[i][2]); g = row > g ? row : g; }
+  const double lam = g < tr ? g : tr;
+  if (!(lam == lam) || lam > 1e30) return;
+  double c[3];
+  for (int k = 0; k < 3; ++k) c[k] = (double)M[k] * sp.c[0] + (double)M[4 + k] * sp.c[1] + (double)M[8 + k] * sp.c[2] + (double)M[12 + k];
+  const double cmax = fmax(fabs(c[0]), fmax(fabs(c[1]), fabs(c[2])));
+  // outward slack: float32 rounding of the centre and of the device arithmetic (relative), vertex transform error (absolute)
+  const double r = sp.r * sqrt(lam) * (1.0 + 2e-4) + 4e-6 * cmax + 1e-30;
+  out[0] = (float)c[0]; out[1] = (float)c[1]; out[2] = (float)c[2];
+  out[3] = (float)(r * r * (1.0 + 1e-6));
 }
 
 // Entry points that rewrite data an in-flight frame may still read (vertex positions, BVH nodes, textures, reservoirs) first wait
@@ -342,7 +389,7 @@ void snkpt_destroy(SnkPt* ctx) {
   DevBuf* bufs[] = {&ctx->positions, &ctx->normals, &ctx->tangents, &ctx->uvs, &ctx->indices, &ctx->blas_nodes, &ctx->blas_tris,
                     &ctx->d_blas, &ctx->materials, &ctx->lights, &ctx->transforms, &ctx->prev_transforms, &ctx->normal_mats,
                     &ctx->det3, &ctx->instances, &ctx->blas_of_instance, &ctx->emissive_idx, &ctx->tlas_nodes, &ctx->tlas_leaf_ids,
-                    &ctx->inst_recs, &ctx->valid_slots, &ctx->q_rays, &ctx->q_hits, &ctx->q_work, &ctx->dev_counters, &ctx->trav_spill,
+                    &ctx->inst_recs, &ctx->inst_sphere, &ctx->valid_slots, &ctx->q_rays, &ctx->q_hits, &ctx->q_work, &ctx->dev_counters, &ctx->trav_spill,
                     &ctx->wave_refs, &ctx->wave_paths, &ctx->prof_work, &ctx->prof_hits, &ctx->em_table, &ctx->em_base_of_obj, &ctx->em_base, &ctx->tex_table, &ctx->srgb_lut};
   for (auto& b : ctx->tex_data) b.release();
   for (DevBuf* b : bufs) b->release();
@@ -535,6 +582,10 @@ int snkpt_upload_mesh(SnkPt* ctx, const float* positions, const float* normals, 
     const uint32_t id = (uint32_t)ctx->blas.size();
     ctx->blas.push_back(SnkBlasInfo{});
     ctx->blas_src.push_back(BlasSrc{(uint32_t)i0 + submeshes[s].base_index, (uint32_t)v0 + submeshes[s].base_vertex, submeshes[s].num_indices / 3});
+    BlasSphere sph;
+    sph.v_begin = (uint32_t)v0 + submeshes[s].base_vertex; sph.v_count = submeshes[s].num_vertices;
+    sphere_of_vertices(positions + 3ull * submeshes[s].base_vertex, submeshes[s].num_vertices, sph);
+    ctx->blas_sphere.push_back(sph);
     out_entry->blas_id[s] = id;
     int rc = build_blas(ctx, id, true, st);
     if (rc) return rc;
@@ -553,6 +604,14 @@ int snkpt_update_positions(SnkPt* ctx, const SnkMeshEntry* entry, const float* p
   cudaStream_t st = work_stream(ctx);
   CK(cudaMemcpyAsync(ctx->positions.as<char>() + 12ull * entry->data_start_vertex_idx, positions, 12ull * num_vertices, cudaMemcpyHostToDevice, st));
   CK(cudaStreamSynchronize(st));
+  // the bounding spheres of the BLASes whose vertices moved (instance culling in the traversal)
+  for (BlasSphere& sph : ctx->blas_sphere) {
+    const uint64_t b0 = entry->data_start_vertex_idx, b1 = b0 + num_vertices;
+    if (sph.v_begin + (uint64_t)sph.v_count <= b0 || sph.v_begin >= b1) continue;
+    if (sph.v_begin >= b0 && sph.v_begin + (uint64_t)sph.v_count <= b1) sphere_of_vertices(positions + 3ull * (sph.v_begin - b0), sph.v_count, sph);
+    else sph.r = -1.0;  // partially updated range: unknown
+  }
+  ctx->tlas_built = false;
   return SNKPT_OK;
 }
 
@@ -762,7 +821,7 @@ int snkpt_build_tlas(SnkPt* ctx, void* stream) {
   // BLAS::GenerateInstance (TLAS.cpp:188-200): one record per instance slot that references a BLAS.
   // The records are staged in pinned host memory owned by the context so that the upload is a true asynchronous copy:
   // no stream synchronisation per frame (the host may run a frame ahead of the GPU). ev_stage guards the reuse.
-  const size_t need = (sizeof(SnkInstRec) + 4) * (size_t)ctx->max_instances;
+  const size_t need = (sizeof(SnkInstRec) + 4 + 16) * (size_t)ctx->max_instances;
   if (ctx->h_stage_bytes < need) {
     if (ctx->h_stage) { CK(cudaStreamSynchronize(st)); cudaFreeHost(ctx->h_stage); ctx->h_stage = nullptr; ctx->h_stage_bytes = 0; }
     CK(cudaMallocHost(&ctx->h_stage, need));
@@ -774,20 +833,25 @@ int snkpt_build_tlas(SnkPt* ctx, void* stream) {
   ctx->stage_in_flight = false;
   SnkInstRec* recs = reinterpret_cast<SnkInstRec*>(ctx->h_stage);
   uint32_t* valid = reinterpret_cast<uint32_t*>(recs + ctx->max_instances);
+  float* spheres = reinterpret_cast<float*>(valid + ctx->max_instances);  // 4 floats per instance slot
+  static const bool cull_instances = !(getenv("SNKPT_NO_INSTANCE_CULL") && getenv("SNKPT_NO_INSTANCE_CULL")[0] == '1');
   uint32_t n = 0;
   float nm[9], det;
   for (uint32_t i = 0; i < ctx->num_instances; ++i) {
     SnkInstRec& r = recs[i];
     memset(&r, 0, sizeof(r));
+    spheres[4 * i] = spheres[4 * i + 1] = spheres[4 * i + 2] = 0.f; spheres[4 * i + 3] = -1.f;
     const uint32_t b = ctx->h_blas_of_instance[i];
     if (b == SNKPT_INVALID_INDEX || ctx->blas[b].tri_count == 0) continue;
     const uint32_t t = ctx->h_instances[i].transform_idx;
     REQUIRE((size_t)t * 16 + 16 <= ctx->h_transforms.size(), SNKPT_E_STATE, "snkpt_build_tlas: instance references a transform that was never set");
     derive_transform(ctx->h_transforms.data() + 16 * (size_t)t, r.w2o, nm, &det);
     r.blas_root = ctx->blas[b].node_root; r.custom_idx = i; r.blas_id = b; r.flags = 0;
+    if (cull_instances && b < ctx->blas_sphere.size()) world_sphere(ctx->h_transforms.data() + 16 * (size_t)t, ctx->blas_sphere[b], spheres + 4 * (size_t)i);
     valid[n++] = i;
   }
   CK(ctx->inst_recs.reserve(sizeof(SnkInstRec) * (size_t)(ctx->max_instances), false, st));
+  CK(ctx->inst_sphere.reserve(16 * (size_t)(ctx->max_instances), false, st));
   CK(ctx->valid_slots.reserve(4 * (size_t)ctx->max_instances, false, st));
   CK(ctx->tlas_nodes.reserve(sizeof(SnkNode8) * (size_t)(ctx->max_instances + 1), false, st));
   CK(ctx->tlas_leaf_ids.reserve(4 * (size_t)(ctx->max_instances + 1), false, st));
@@ -797,6 +861,7 @@ int snkpt_build_tlas(SnkPt* ctx, void* stream) {
   if (n == 0) return SNKPT_OK;
   cudaEventRecord(ctx->ev[6], st);
   CK(cudaMemcpyAsync(ctx->inst_recs.p, recs, sizeof(SnkInstRec) * (size_t)ctx->num_instances, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->inst_sphere.p, spheres, 16 * (size_t)ctx->num_instances, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ctx->valid_slots.p, valid, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(ctx->ev_stage, st));
   ctx->stage_in_flight = true;

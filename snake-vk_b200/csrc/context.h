@@ -40,6 +40,8 @@ struct DevBuf {
 };
 
 struct BlasSrc { uint32_t index_offset, vertex_offset, num_tris; };
+// object-space bounding sphere of a BLAS's vertex range (host side; the TLAS build turns it into a world-space sphere per instance)
+struct BlasSphere { uint32_t v_begin = 0, v_count = 0; double c[3] = {0, 0, 0}; double r = -1.0; };  // r < 0: unknown (no culling)
 
 // one timed kernel launch (snkpt_set_profiling / snkpt_get_launch_timings)
 struct ProfRec {
@@ -122,6 +124,7 @@ struct SnkPt {
   uint32_t n_blas_nodes = 0, n_blas_tris = 0;
   std::vector<SnkBlasInfo> blas;
   std::vector<snk::BlasSrc> blas_src;
+  std::vector<snk::BlasSphere> blas_sphere;   // per BLAS, from the vertices handed to snkpt_upload_mesh / snkpt_update_positions
   std::vector<snk::RefitState> blas_refit;  // side arrays of refitted BLASes (empty until the first refit)
   snk::BuildScratch scratch_blas, scratch_tlas, scratch_ptcl;
   // particle pass (particles.cu): two particle buffers (ping-pong), cell start table, ray counter
@@ -142,6 +145,7 @@ struct SnkPt {
 
   // TLAS
   snk::DevBuf tlas_nodes, tlas_leaf_ids, inst_recs, valid_slots;
+  snk::DevBuf inst_sphere;  // float4 per instance slot: world-space bounding sphere (xyz, r^2), r^2 < 0 = none (traverse.cuh)
   uint32_t tlas_prims = 0;
   bool tlas_built = false;
   // small per-frame uploads (transforms, instances, lights, materials) go through a ring of pinned chunks and are enqueued

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_count_work(TraceScene S, cons
   if (i >= n) return;
   const float4 a = __ldg(rays + 2 * i), b = __ldg(rays + 2 * i + 1);
   const float tend = hits[i].t >= 0.f ? hits[i].t : b.w;
-  uint32_t nodes = 0, recs = 0, insts = 0;
+  uint32_t nodes = 0, recs = 0, insts = 0, entered = 0;
   if (S.tlas_node_count) {
     RaySpace r;
     setup_ray_space(r, a.x, a.y, a.z, b.x, b.y, b.z);
@@ -138,8 +138,11 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_count_work(TraceScene S, cons
     uint32_t dummy = 0;
     count_subtree(r, S.tlas_nodes, 0u, a.w, tend, nodes, dummy, leaf, ln, 64);
     insts = dummy;
+    (void)insts;
     for (int k = 0; k < ln; ++k) {
       const uint32_t slot = S.tlas_leaf_ids[leaf[k]];
+      if (S.inst_sphere && !ray_may_hit_sphere(S.inst_sphere[slot], a.x, a.y, a.z, b.x, b.y, b.z, tend)) continue;  // culled before the entry (traverse.cuh)
+      ++entered;
       const float4* M = reinterpret_cast<const float4*>(S.inst + slot);
       const float4 r0 = M[0], r1 = M[1], r2 = M[2];
       RaySpace o;
@@ -150,7 +153,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_count_work(TraceScene S, cons
       count_subtree(o, S.blas_nodes, S.inst[slot].blas_root, a.w, tend, nodes, recs, nullptr, unused, 0);
     }
   }
-  out3[3 * i] = nodes; out3[3 * i + 1] = recs; out3[3 * i + 2] = insts;
+  out3[3 * i] = nodes; out3[3 * i + 1] = recs; out3[3 * i + 2] = entered;  // instances entered after the bounding-sphere cull
 }
 
 // whole-queue sums of the same quantities (profiling level 2)
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_count_work_sum(TraceScene S, 
     if (b.w >= a.w && S.tlas_node_count) {
       const float ht = hits[i].x;
       const float tend = ht >= 0.f ? ht : b.w;
-      uint32_t nodes = 0, recs = 0, insts = 0;
+      uint32_t nodes = 0, recs = 0, insts = 0, entered = 0;
       RaySpace r;
       setup_ray_space(r, a.x, a.y, a.z, b.x, b.y, b.z);
       uint32_t leaf[64];
@@ -172,6 +175,8 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_count_work_sum(TraceScene S, 
       count_subtree(r, S.tlas_nodes, 0u, a.w, tend, nodes, insts, leaf, ln, 64);
       for (int k = 0; k < ln; ++k) {
         const uint32_t slot = S.tlas_leaf_ids[leaf[k]];
+        if (S.inst_sphere && !ray_may_hit_sphere(S.inst_sphere[slot], a.x, a.y, a.z, b.x, b.y, b.z, tend)) continue;  // culled before the entry (traverse.cuh)
+        ++entered;
         const float4* M = reinterpret_cast<const float4*>(S.inst + slot);
         const float4 r0 = M[0], r1 = M[1], r2 = M[2];
         RaySpace o;
@@ -181,7 +186,7 @@ __global__ void __launch_bounds__(TRACE_THREADS) k_count_work_sum(TraceScene S, 
         int unused = 0;
         count_subtree(o, S.blas_nodes, S.inst[slot].blas_root, a.w, tend, nodes, recs, nullptr, unused, 0);
       }
-      v[0] = 1; v[1] = nodes; v[2] = recs; v[3] = insts;
+      v[0] = 1; v[1] = nodes; v[2] = recs; v[3] = entered;
     }
   }
 #pragma unroll

@@ -230,35 +230,46 @@ k_trace_mx(TraceScene S, TraceSegs segs, const uint32_t* __restrict__ refs, cons
         const float4* rp = sg.rays + 2ull * (D.w & REF_SLOT_MASK);
         const float4 a = __ldcg(rp), b = __ldcg(rp + 1);
         RaySpace r;
+        bool entered = false;
         if (T.y) {
           // enter the next instance of the pending TLAS leaf group; the rest of the group and the pending inner group wait
           const uint32_t bit = __ffs(T.y) - 1;
           T.y &= ~(1u << bit);
           const uint32_t islot = __ldg(S.tlas_leaf_ids + T.x + bit);
-          if (T.y) mx_push(stk, k, sp, T);
-          if (G.y & 0xFF000000u) mx_push(stk, k, sp, G);
-          const float4* M = reinterpret_cast<const float4*>(S.inst + islot);
-          const float4 r0 = __ldg(M), r1 = __ldg(M + 1), r2 = __ldg(M + 2);
-          const uint4 meta = __ldg(reinterpret_cast<const uint4*>(M + 3));
-          // o' = ((m0*x + m1*y) + m2*z) + m3 ; d' = (m0*x + m1*y) + m2*z   (unfused, as the oracle)
-          const float oox = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0.x, a.x), __fmul_rn(r0.y, a.y)), __fmul_rn(r0.z, a.z)), r0.w);
-          const float ooy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r1.x, a.x), __fmul_rn(r1.y, a.y)), __fmul_rn(r1.z, a.z)), r1.w);
-          const float ooz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2.x, a.x), __fmul_rn(r2.y, a.y)), __fmul_rn(r2.z, a.z)), r2.w);
-          const float odx = __fadd_rn(__fadd_rn(__fmul_rn(r0.x, b.x), __fmul_rn(r0.y, b.y)), __fmul_rn(r0.z, b.z));
-          const float ody = __fadd_rn(__fadd_rn(__fmul_rn(r1.x, b.x), __fmul_rn(r1.y, b.y)), __fmul_rn(r1.z, b.z));
-          const float odz = __fadd_rn(__fadd_rn(__fmul_rn(r2.x, b.x), __fmul_rn(r2.y, b.y)), __fmul_rn(r2.z, b.z));
-          setup_box_space(r, oox, ooy, ooz, odx, ody, odz);
-          setup_tri_space(r);
-          packed = (packed & (P_ANY | P_HIT)) | sp | (sp << P_BSP_SH) | ((uint32_t)r.kx << P_K_SH) | ((uint32_t)r.ky << (P_K_SH + 2)) |
-                   ((uint32_t)r.kz << (P_K_SH + 4)) | (r.octinv << P_OCT_SH) | P_INBLAS;
-          MX_AT(CH_S, k) = make_uint4(__float_as_uint(r.Sx), __float_as_uint(r.Sy), __float_as_uint(r.Sz), 0u);
-          reinterpret_cast<uint32_t*>(&MX_AT(CH_B, k))[3] = meta.y;
-          G = make_uint2(meta.x, 0x01000000u);  // one inner bit, empty child mask: the BLAS root
-          T = make_uint2(0u, 0u);
-        } else {
-          // back in world space with a TLAS inner group pending
+          if (!S.inst_sphere || ray_may_hit_sphere(__ldg(S.inst_sphere + islot), a.x, a.y, a.z, b.x, b.y, b.z, __uint_as_float(D.y))) {
+            entered = true;
+            if (T.y) mx_push(stk, k, sp, T);
+            if (G.y & 0xFF000000u) mx_push(stk, k, sp, G);
+            const float4* M = reinterpret_cast<const float4*>(S.inst + islot);
+            const float4 r0 = __ldg(M), r1 = __ldg(M + 1), r2 = __ldg(M + 2);
+            const uint4 meta = __ldg(reinterpret_cast<const uint4*>(M + 3));
+            // o' = ((m0*x + m1*y) + m2*z) + m3 ; d' = (m0*x + m1*y) + m2*z   (unfused, as the oracle)
+            const float oox = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0.x, a.x), __fmul_rn(r0.y, a.y)), __fmul_rn(r0.z, a.z)), r0.w);
+            const float ooy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r1.x, a.x), __fmul_rn(r1.y, a.y)), __fmul_rn(r1.z, a.z)), r1.w);
+            const float ooz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2.x, a.x), __fmul_rn(r2.y, a.y)), __fmul_rn(r2.z, a.z)), r2.w);
+            const float odx = __fadd_rn(__fadd_rn(__fmul_rn(r0.x, b.x), __fmul_rn(r0.y, b.y)), __fmul_rn(r0.z, b.z));
+            const float ody = __fadd_rn(__fadd_rn(__fmul_rn(r1.x, b.x), __fmul_rn(r1.y, b.y)), __fmul_rn(r1.z, b.z));
+            const float odz = __fadd_rn(__fadd_rn(__fmul_rn(r2.x, b.x), __fmul_rn(r2.y, b.y)), __fmul_rn(r2.z, b.z));
+            setup_box_space(r, oox, ooy, ooz, odx, ody, odz);
+            setup_tri_space(r);
+            packed = (packed & (P_ANY | P_HIT)) | sp | (sp << P_BSP_SH) | ((uint32_t)r.kx << P_K_SH) | ((uint32_t)r.ky << (P_K_SH + 2)) |
+                     ((uint32_t)r.kz << (P_K_SH + 4)) | (r.octinv << P_OCT_SH) | P_INBLAS;
+            MX_AT(CH_S, k) = make_uint4(__float_as_uint(r.Sx), __float_as_uint(r.Sy), __float_as_uint(r.Sz), 0u);
+            reinterpret_cast<uint32_t*>(&MX_AT(CH_B, k))[3] = meta.y;
+            G = make_uint2(meta.x, 0x01000000u);  // one inner bit, empty child mask: the BLAS root
+            T = make_uint2(0u, 0u);
+            next = W_NODE;
+          }
+        }
+        if (!entered) {
+          // back in (or still in) world space: the box constants of the world-space ray; an instance whose bounding sphere the
+          // ray misses was skipped above and the rest of its leaf group is tried in the next SPACE phase
           setup_box_space(r, a.x, a.y, a.z, b.x, b.y, b.z);
-          packed = (packed & ~(7u << P_OCT_SH)) | (r.octinv << P_OCT_SH);
+          packed = (packed & ~(7u << P_OCT_SH)) | (r.octinv << P_OCT_SH) | sp;
+          packed = (packed & ~P_SP) | sp;
+          if (T.y) next = W_SPACE;
+          else if (G.y & 0xFF000000u) next = W_NODE;
+          else next = mx_pop(stk, k, packed, G, T);
         }
         uint4* ap = &MX_AT(CH_A, k);
         reinterpret_cast<float*>(ap)[0] = r.ox; reinterpret_cast<float*>(ap)[1] = r.oy; reinterpret_cast<float*>(ap)[2] = r.oz;
@@ -266,7 +277,6 @@ k_trace_mx(TraceScene S, TraceSegs segs, const uint32_t* __restrict__ refs, cons
         reinterpret_cast<float*>(bp)[0] = r.idx; reinterpret_cast<float*>(bp)[1] = r.idy; reinterpret_cast<float*>(bp)[2] = r.idz;
         MX_AT(CH_C, k) = make_uint4(G.x, G.y, T.x, T.y);
         reinterpret_cast<uint32_t*>(&MX_AT(CH_D, k))[2] = packed;
-        next = W_NODE;
       }
     } else {
       // ---- FETCH: retire my finished ray, then take the next queue entry (one atomic per warp)

@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(TQ_THREADS) k_count_work_q(TraceScene S, Trace
     if (!(b.w >= a.w) || !S.tlas_node_count) continue;
     const float ht = prof_t[q];
     const float tend = ht >= 0.f ? ht : b.w;
-    uint32_t nodes = 0, recs = 0, insts = 0;
+    uint32_t nodes = 0, recs = 0, insts = 0, entered = 0;
     RaySpace r;
     setup_ray_space(r, a.x, a.y, a.z, b.x, b.y, b.z);
     uint32_t leaf[64];
@@ -164,6 +164,8 @@ __global__ void __launch_bounds__(TQ_THREADS) k_count_work_q(TraceScene S, Trace
     count_subtree_q(r, S.tlas_nodes, 0u, a.w, tend, nodes, insts, leaf, ln, 64);
     for (int k = 0; k < ln; ++k) {
       const uint32_t slot = S.tlas_leaf_ids[leaf[k]];
+      if (S.inst_sphere && !ray_may_hit_sphere(S.inst_sphere[slot], a.x, a.y, a.z, b.x, b.y, b.z, tend)) continue;  // culled before the entry (traverse.cuh)
+      ++entered;
       const float4* M = reinterpret_cast<const float4*>(S.inst + slot);
       const float4 r0 = M[0], r1 = M[1], r2 = M[2];
       RaySpace o;
@@ -173,6 +175,7 @@ __global__ void __launch_bounds__(TQ_THREADS) k_count_work_q(TraceScene S, Trace
       int unused = 0;
       count_subtree_q(o, S.blas_nodes, S.inst[slot].blas_root, a.w, tend, nodes, recs, nullptr, unused, 0);
     }
+    insts = entered;  // instances actually entered (after the bounding-sphere cull)
     v[0] += 1; v[1] += nodes; v[2] += recs; v[3] += insts; v[4] += sg.any ? 1 : 0;
   }
 #pragma unroll

@@ -25,6 +25,7 @@ struct TraceScene {
   const uint4* blas_nodes;        // node pool of all BLASes
   const float4* tris;             // 3 x float4 per triangle record
   const SnkInstRec* inst;         // indexed by instance slot
+  const float4* inst_sphere;      // world-space bounding sphere per instance slot (centre, r^2; r^2 < 0: none) or nullptr
   uint32_t* overflow;             // device counter: traversal stack overflows (must stay 0)
   uint32_t tlas_node_count;       // 0 = nothing to hit
   uint2* spill;                   // global overflow area of the short stacks (persistent kernels), SPILL_STACK x 32 per warp
@@ -60,6 +61,26 @@ struct HitRec {
 // local-memory array: an earlier version saw lanes that left the divergent loop early clobber the uniform
 // register holding the local-frame base (compute-sanitizer, k_primary on C2).
 constexpr float BOX_PAD = 1.000004f;
+
+// Instance culling: a TLAS leaf only says that the ray crosses the instance's world-space BOX; before paying for the entry
+// (ray transform, box + Woop constants, BLAS root test) the ray is tested against the instance's bounding SPHERE. For compact
+// objects the box is mostly empty (a sphere fills 52 % of its box: half of all entries into the icospheres of C2 were misses).
+// Conservative under float32: the radius is inflated on the host, the squared distances get a relative slack here, and a ray
+// is only rejected when it clearly misses, starts outside and points away, or enters beyond the current closest hit.
+__device__ __forceinline__ bool ray_may_hit_sphere(float4 sph, float ox, float oy, float oz, float dx, float dy, float dz, float tcur) {
+  if (!(sph.w >= 0.0f)) return true;
+  const float cx = sph.x - ox, cy = sph.y - oy, cz = sph.z - oz;
+  const float oc2 = cx * cx + cy * cy + cz * cz, dd = dx * dx + dy * dy + dz * dz, b = cx * dx + cy * dy + cz * dz;
+  const float cc = oc2 * 0.999996f - sph.w;          // > 0: the origin is outside
+  if (!(cc > 0.0f)) return true;
+  const float slack = 2e-6f * dd * oc2;
+  const float disc = b * b - dd * cc + slack;        // upper bound of the discriminant
+  if (disc < 0.0f) return false;                     // the line misses
+  if (b < 0.0f && b * b > slack) return false;       // outside and pointing away
+  const float e = b - tcur * dd;                     // > 0: the closest approach lies beyond tcur
+  if (e > 0.0f && e * e > disc) return false;        // the entry point lies beyond the current closest hit / tmax
+  return true;
+}
 
 struct RaySpace {
   float ox, oy, oz;
@@ -356,6 +377,8 @@ __device__ __forceinline__ bool trav_step_impl(const TraceScene& S, Trav& t, con
       const uint32_t bit = __ffs(t.T.y) - 1;
       t.T.y &= ~(1u << bit);
       const uint32_t slot = __ldg(S.tlas_leaf_ids + t.T.x + bit);
+      // instance culling: a ray that misses the bounding sphere skips the entry (this lane idles for the rest of the iteration)
+      if (!S.inst_sphere || ray_may_hit_sphere(__ldg(S.inst_sphere + slot), t.ox, t.oy, t.oz, t.dx, t.dy, t.dz, t.tcur)) {
       if (t.T.y) stk_push<STRIDE>(stk, t.sp, t.T, S.overflow);
       if (t.G.y & 0xFF000000u) stk_push<STRIDE>(stk, t.sp, t.G, S.overflow);
       t.blas_sp = t.sp;
@@ -374,6 +397,7 @@ __device__ __forceinline__ bool trav_step_impl(const TraceScene& S, Trav& t, con
       t.cur_inst = meta.y;
       node_idx = meta.x;
       open = true;
+      }
     } else if (t.T.y == 0u && (t.G.y & 0xFF000000u) != 0u) {
       const uint32_t hits_imask = t.G.y;
       const uint32_t bit = 31u - __clz(hits_imask);
