@@ -970,7 +970,9 @@ __global__ void __launch_bounds__(128, SNK_COLLAPSE_CTAS) k_collapse(CollapseArg
 // (key, index) pairs in shared memory -> Karras hierarchy -> bottom-up boxes -> level-synchronous collapse, with
 // __syncthreads() where the general path has kernel boundaries or grid syncs.
 #ifndef SNK_SMALL_PLOC
-#define SNK_SMALL_PLOC 0  // measured (profiles/r02p_variants_ploc.txt): nodes per ray 15.0 -> 14.2 but triangles per ray 4.0 -> 4.6; C2 frame 7.29 -> 7.43 ms, C4 40.9 -> 40.1 ms: not adopted
+#define SNK_SMALL_PLOC 3  // r02p: PLOC for every small build: nodes per ray 15.0 -> 14.2 but triangles per ray 4.0 -> 4.6, C2 +2 %. r04p (with instance
+                          // culling the TLAS is most of a ray's nodes): PLOC for the TLAS only: C4 (2344 instances) 32.3 -> 30.7 ms, C2 (205) 5.71 -> 5.67 ms
+                          // with a 0.1 ms slower rebuild: adopted for TLASes of >= 1024 instances (3)
 #endif
 constexpr int SMALL_MAX = 4096, SMALL_THREADS = 1024;
 __global__ void __launch_bounds__(SMALL_THREADS) k_build_small(const float4* __restrict__ prim_lo, const float4* __restrict__ prim_hi, int n,
@@ -1488,14 +1490,16 @@ int launch_build(BuildScratch& s, uint32_t n, const BuildOutput& out, const floa
     a.leaf_max = out.tris ? LEAF_MAX_BLAS : LEAF_MAX_TLAS;
     uint32_t threads = 128;
     while (threads < n && threads < (uint32_t)SMALL_THREADS) threads <<= 1;
-#if SNK_SMALL_PLOC
-    a.sorted_prims = s.vals[1];
-    k_build_small_ploc<<<1, threads, 0, st>>>(s.prim_lo, s.prim_hi, (int)n, s.counters, s.vals[0], s.vals[1], s.left, s.right, s.parent, s.first, s.last,
-                                               s.bb_lo, s.bb_hi, s.flags, a);
-#else
-    k_build_small<<<1, threads, 0, st>>>(s.prim_lo, s.prim_hi, (int)n, s.counters, s.keys[0], s.vals[0], s.left, s.right, s.parent, s.first,
-                                              s.last, s.bb_lo, s.bb_hi, s.flags, a);
-#endif
+    // SNK_SMALL_PLOC: 0 = Karras hierarchy, 1 = locally-ordered clustering for every small build, 2 = for the TLAS only, 3 = for large TLASes
+    const bool ploc = SNK_SMALL_PLOC == 1 || (SNK_SMALL_PLOC == 2 && !out.tris) || (SNK_SMALL_PLOC == 3 && !out.tris && n >= 1024u);
+    if (ploc) {
+      a.sorted_prims = s.vals[1];
+      k_build_small_ploc<<<1, threads, 0, st>>>(s.prim_lo, s.prim_hi, (int)n, s.counters, s.vals[0], s.vals[1], s.left, s.right, s.parent, s.first, s.last,
+                                                 s.bb_lo, s.bb_hi, s.flags, a);
+    } else {
+      k_build_small<<<1, threads, 0, st>>>(s.prim_lo, s.prim_hi, (int)n, s.counters, s.keys[0], s.vals[0], s.left, s.right, s.parent, s.first,
+                                                s.last, s.bb_lo, s.bb_hi, s.flags, a);
+    }
     return 1;
   }
 #endif
