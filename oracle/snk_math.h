@@ -31,6 +31,8 @@ inline vec3 operator/(vec3 a, vec3 b) { return {a.x / b.x, a.y / b.y, a.z / b.z}
 inline vec3 operator*(vec3 a, float s) { return {a.x * s, a.y * s, a.z * s}; }
 inline vec3 operator*(float s, vec3 a) { return {s * a.x, s * a.y, s * a.z}; }
 inline vec3 operator/(vec3 a, float s) { return {a.x / s, a.y / s, a.z / s}; }
+// north-star estimator only (csrc/vecmath.cuh:inv_scale): one reciprocal, three products
+inline vec3 inv_scale(vec3 a, float s) { const float r = 1.0f / s; return {a.x * r, a.y * r, a.z * r}; }
 inline vec3 operator-(vec3 a) { return {-a.x, -a.y, -a.z}; }
 inline vec3& operator+=(vec3& a, vec3 b) { a = a + b; return a; }
 inline vec3& operator*=(vec3& a, vec3 b) { a = a * b; return a; }

@@ -72,11 +72,11 @@ inline vec3 ns_bsdf_cos(vec3 n, vec3 wo, vec3 wi, vec3 albedo, float roughness, 
   const float g = geometry_smith(wo, wi, n, roughness);
   const vec3 num = (ndf * g) * f;
   const float denom = 4.0f * gmax(dot(n, wo), 0.0f) * gmax(dot(n, wi), 0.0f) + 0.0001f;
-  const vec3 specular = num / denom;
+  const vec3 specular = inv_scale(num, denom);
   vec3 kd = v3(1.0f) - f;
   kd *= 1.0f - metallic;
   const float n_dot_l = gmax(dot(n, wi), 0.0f);
-  return (kd * albedo / PI_GLSL + specular) * n_dot_l;
+  return ((kd * albedo) * (1.0f / PI_GLSL) + specular) * n_dot_l;
 }
 inline float ns_spec_prob(float metallic) { return 0.25f + 0.5f * metallic; }
 inline float ns_pdf(vec3 n, vec3 wo, vec3 wi, float roughness, float metallic) {

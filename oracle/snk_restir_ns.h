@@ -72,10 +72,10 @@ inline RsEval rs_eval_pl(const RsSurf& s, const Pointlight& pl) {
   const vec3 d = v3(pl.pos[0], pl.pos[1], pl.pos[2]) - s.o;
   const float dist = length(d);
   if (!(dist > 0.002f)) return e;
-  const vec3 wi = d / dist;
+  const vec3 wi = inv_scale(d, dist);
   if (!(dot(s.n, wi) > 0.0f)) return e;
   const float atten = (pl.atten_constant + pl.atten_linear * dist) + pl.atten_exp * (dist * dist);
-  e.C = (ns_bsdf_cos(s.n, s.wo, wi, s.albedo, s.roughness, s.metallic) * v3(pl.colour[0], pl.colour[1], pl.colour[2])) / atten;
+  e.C = inv_scale(ns_bsdf_cos(s.n, s.wo, wi, s.albedo, s.roughness, s.metallic) * v3(pl.colour[0], pl.colour[1], pl.colour[2]), atten);
   e.wi = wi; e.tmax = dist - 0.001f;
   return e;
 }
@@ -84,10 +84,10 @@ inline RsEval rs_eval_em(const RsSurf& s, const NsSurf& q) {
   const vec3 d = q.p - s.o;
   const float dist = length(d);
   if (!(dist > 0.01f)) return e;
-  const vec3 wi = d / dist;
+  const vec3 wi = inv_scale(d, dist);
   const float cos_l = fabsf(dot(q.n, wi));
   if (!(dot(s.n, wi) > 0.0f) || !(cos_l > 0.000001f)) return e;
-  e.C = ((ns_bsdf_cos(s.n, s.wo, wi, s.albedo, s.roughness, s.metallic) * q.albedo) * cos_l) / (dist * dist);
+  e.C = inv_scale((ns_bsdf_cos(s.n, s.wo, wi, s.albedo, s.roughness, s.metallic) * q.albedo) * cos_l, dist * dist);
   e.wi = wi; e.tmax = dist - 0.005f;
   return e;
 }

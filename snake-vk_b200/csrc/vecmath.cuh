@@ -30,6 +30,9 @@ __device__ __forceinline__ vec3 operator/(vec3 a, vec3 b) { return v3(a.x / b.x,
 __device__ __forceinline__ vec3 operator*(vec3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
 __device__ __forceinline__ vec3 operator*(float s, vec3 a) { return v3(s * a.x, s * a.y, s * a.z); }
 __device__ __forceinline__ vec3 operator/(vec3 a, float s) { return v3(a.x / s, a.y / s, a.z / s); }
+// north-star estimator only (its numerics are this repository's own, oracle/snk_math.h:inv_scale is the same expression): one
+// IEEE reciprocal and three products instead of three IEEE divisions — the light-sampling loops evaluate 4 of these per candidate
+__device__ __forceinline__ vec3 inv_scale(vec3 a, float s) { const float r = 1.0f / s; return v3(a.x * r, a.y * r, a.z * r); }
 __device__ __forceinline__ vec3 operator-(vec3 a) { return v3(-a.x, -a.y, -a.z); }
 __device__ __forceinline__ vec3& operator+=(vec3& a, vec3 b) { a = a + b; return a; }
 __device__ __forceinline__ vec3& operator*=(vec3& a, vec3 b) { a = a * b; return a; }
