@@ -21,8 +21,10 @@ constexpr int TQ_THREADS = 128;
 #define SNK_TQ_CTAS 8
 #endif
 #ifndef SNK_TQ_GRID_CTAS
-#define SNK_TQ_GRID_CTAS 6  // CTAs per SM the persistent grid launches (of the 8 the launch bounds allow): 5-7 run within 1.5 % of 8
-                            // (profiles/r02a_variants_occupancy_stack.txt) and the free slots let the other chain's kernels in
+#define SNK_TQ_GRID_CTAS 8  // CTAs per SM of the persistent grid. r04s (after instance culling): 5 / 6 / 7 / 8 CTAs give a C2 frame of
+                            // 5.68 / 5.56 / 5.56 / 5.53 ms with the two chains overlapped and a kernel sum of 6.28 / 5.98 / 5.80 / 5.66 ms when
+                            // every launch runs alone: a smaller grid leaves slots for the other chain's kernels, but a full grid is
+                            // faster by about as much, so the full grid stays (profiles/r04s_variants_grid.txt)
 #endif
 #ifndef SNK_TQ_VOTE
 #define SNK_TQ_VOTE 0  // 0: node + triangle + pop every iteration (trav_step); 1: one voted phase per iteration (trav_vote_step) — measured 20 % slower (r01r)
