@@ -194,14 +194,20 @@ __global__ void __launch_bounds__(128, 6) k_ns_vertex(SceneDev D, FrameConsts fc
   uint32_t count = __ldcg(paths_in_count);
   if (count > npix) count = npix;
   unsigned long long n_shadow = 0, n_closest = 0;
+  // Two phases per batch of 128 paths. Phase 1, one thread per path: add the previous vertex's resolved next-event term and look
+  // at the hit record; rays that left the scene or were dead end here. Phase 2 runs the surface work (vertex fetch, emission MIS,
+  // next-event sample, BSDF sample) on the paths that DID hit, compacted through shared memory so that whole warps work: in an open
+  // scene 40-50 % of the rays of a bounce miss, and with one thread per listed path the stage ran at 13-17 of 32 lanes (ncu r04r).
+  // Per path the same operations in the same order as before; only the order of the queue entries changes (results do not depend on it).
+  __shared__ uint32_t sm_list[128];
+  __shared__ uint32_t sm_warp_n[4];
+  const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
   for (uint32_t base = blockIdx.x * blockDim.x; base < count; base += gridDim.x * blockDim.x) {  // CTA-uniform trip count
   const uint32_t j = base + threadIdx.x;
-  bool has_shadow = false, has_closest = false;
+  bool hit = false;
   uint32_t i = 0;
   if (j < count) {
     i = paths_in[j];
-    const uint32_t x = i % fc.W, y = fc.row0 + i / fc.W;
-    const uint32_t pixel = y * fc.W + x;
     // the previous vertex's next-event estimate, now that its shadow ray is resolved
     float4 L4 = B.L[i];
     vec3 L = v3(L4.x, L4.y, L4.z);
@@ -209,35 +215,51 @@ __global__ void __launch_bounds__(128, 6) k_ns_vertex(SceneDev D, FrameConsts fc
       const float4 c = B.C[i];
       L += v3(c.x, c.y, c.z) * B.vis[i];
     }
-    const float4 r1 = B.rays[2 * i + 1];
-    bool alive = r1.w >= 0.0f;
-    const float4 h = B.hit[i];
-    if (alive && h.x < 0.0f) alive = false;
-    NsSurf s;
-    const vec3 wi = v3(r1.x, r1.y, r1.z);
-    const float4 T4 = B.T[i];
-    const vec3 T = v3(T4.x, T4.y, T4.z);
-    if (alive) {
-      s = ns_surface(D, B.inst[i], __float_as_uint(h.w), h.y, h.z);
-      if (s.flags & SNKPT_MAT_FLAG_EMISSIVE) {
-        if (b >= 1u + nee_from) {  // the ray left x_{b-1}, a vertex that also did next-event estimation
-          const NsLightCounts lc = ns_light_counts(D);
-          const float pdf_b = T4.w;
-          const float p_nee = ns_nee_pdf_emissive(lc, s.ntri, s.area, h.x, s.n, wi);
-          const float w = (pdf_b * pdf_b) / (pdf_b * pdf_b + p_nee * p_nee);
-          L += (T * s.albedo) * w;
-        }
-        alive = false;
-      }
-    }
+    const float r1w = B.rays[2 * i + 1].w;
+    hit = r1w >= 0.0f && !(B.hit[i].x < 0.0f);
     B.L[i] = make_float4(L.x, L.y, L.z, 0.0f);
-    if (alive) {
-      ns_vertex_work(D, B, i, pixel, fc.frame_idx, b, max_bounces, nee_from, s, -wi, T, has_shadow, has_closest);
-    } else {
-      if (r1.w >= 0.0f) put_dead_dir(B.rays, i);
+    if (!hit) {
+      if (r1w >= 0.0f) put_dead_dir(B.rays, i);
       B.C[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
+  const uint32_t m = __ballot_sync(0xFFFFFFFFu, hit);
+  if (lane == 0) sm_warp_n[wid] = __popc(m);
+  __syncthreads();
+  uint32_t before = 0, n_hit = 0;
+#pragma unroll
+  for (uint32_t k = 0; k < 4; ++k) { const uint32_t c = sm_warp_n[k]; before += k < wid ? c : 0u; n_hit += c; }
+  if (hit) sm_list[before + __popc(m & ((1u << lane) - 1u))] = i;
+  __syncthreads();
+  bool has_shadow = false, has_closest = false;
+  i = 0;
+  if (threadIdx.x < n_hit) {
+    i = sm_list[threadIdx.x];
+    const uint32_t x = i % fc.W, y = fc.row0 + i / fc.W;
+    const uint32_t pixel = y * fc.W + x;
+    const float4 r1 = B.rays[2 * i + 1];
+    const float4 h = B.hit[i];
+    const vec3 wi = v3(r1.x, r1.y, r1.z);
+    const float4 T4 = B.T[i];
+    const vec3 T = v3(T4.x, T4.y, T4.z);
+    const NsSurf s = ns_surface(D, B.inst[i], __float_as_uint(h.w), h.y, h.z);
+    if (s.flags & SNKPT_MAT_FLAG_EMISSIVE) {
+      if (b >= 1u + nee_from) {  // the ray left x_{b-1}, a vertex that also did next-event estimation
+        const NsLightCounts lc = ns_light_counts(D);
+        const float pdf_b = T4.w;
+        const float p_nee = ns_nee_pdf_emissive(lc, s.ntri, s.area, h.x, s.n, wi);
+        const float w = (pdf_b * pdf_b) / (pdf_b * pdf_b + p_nee * p_nee);
+        const float4 L4 = B.L[i];
+        const vec3 L = v3(L4.x, L4.y, L4.z) + (T * s.albedo) * w;
+        B.L[i] = make_float4(L.x, L.y, L.z, 0.0f);
+      }
+      put_dead_dir(B.rays, i);
+      B.C[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      ns_vertex_work(D, B, i, pixel, fc.frame_idx, b, max_bounces, nee_from, s, -wi, T, has_shadow, has_closest);
+    }
+  }
+  __syncthreads();  // sm_list / sm_warp_n are rewritten by the next batch
   q_append3(q_refs, q_count, has_closest, make_ref(SEG_NS_CLOSEST, i), has_shadow, make_ref(SEG_NS_SHADOW, i), false, 0u);
   q_append1(paths_out, paths_out_count, has_closest, i);
   n_shadow += has_shadow ? 1ull : 0ull; n_closest += has_closest ? 1ull : 0ull;

@@ -294,7 +294,7 @@ constexpr int RS_MAXN = 9;  // this pixel + up to 8 neighbours
 #endif
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #ifndef SNK_RS_SPATIAL_CTAS
-#define SNK_RS_SPATIAL_CTAS 5
+#define SNK_RS_SPATIAL_CTAS 6  // 5 / 6 / 8 resident CTAs (96 / 80 / 64 registers): 0.492 / 0.443 / 0.449 ms on C2 (profiles/r04t_variants_occupancy.txt)
 #endif
 __global__ void __launch_bounds__(128, SNK_RS_SPATIAL_CTAS) k_rs_spatial(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, uint32_t npix) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
