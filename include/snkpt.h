@@ -193,7 +193,10 @@ typedef struct SnkRtSettings {
 } SnkRtSettings;
 enum {
   SNKPT_RT_NO_RESTIR = 1u, /* skip both reservoir passes                         */
-  SNKPT_RT_NO_BOUNCE = 2u  /* skip BounceDiffuse / path continuation             */
+  SNKPT_RT_NO_BOUNCE = 2u, /* skip BounceDiffuse / path continuation             */
+  SNKPT_RT_UNBIASED_REUSE = 4u /* north-star mode: the MIS weights of spatial reuse carry the visibility of the selected sample
+                                * from every contributing pixel's surface (<= 2 shadow rays per accepted neighbour): removes the
+                                * darkening bias of reuse across shadow boundaries (Bitterli et al. 2020, Alg. 6)            */
 };
 
 /* what snkpt_read_aux / snkpt_device_ptr can name */

@@ -34,7 +34,7 @@ struct RtSettings {
   uint32_t reserved[6] = {0, 0, 0, 0, 0, 0};
 };
 static_assert(sizeof(RtSettings) == 64, "RtSettings mirrors SnkRtSettings");
-constexpr uint32_t RT_NO_RESTIR = 1u, RT_NO_BOUNCE = 2u;
+constexpr uint32_t RT_NO_RESTIR = 1u, RT_NO_BOUNCE = 2u, RT_UNBIASED_REUSE = 4u;
 
 // optional scripted random numbers for known-answer tests: when set, every
 // gold_noise()/random() call returns the next value of the stream instead

@@ -15,7 +15,9 @@
 //     world position (from prev depth), M clamped to m_cap x M_initial; the initial sample is kept when history fails
 //   * spatial: k neighbours within the radius, accepted on current-frame normal and hit distance; the selected
 //     sample's weight is corrected with the MIS weight m_s(y) = p^_s(y) / sum_j p^_j(y) M_j over the pixels that
-//     contributed (Bitterli et al. 2020, Alg. 6 with MIS weights; the p^_j are unshadowed)
+//     contributed (Bitterli et al. 2020, Alg. 6 with MIS weights). By default the p^_j are unshadowed (biased: darkens where
+//     a neighbour could not have produced the sample); with RT_UNBIASED_REUSE every neighbour term carries the visibility of
+//     the selected sample from THAT neighbour's surface (one shadow ray per neighbour and light type), which removes the bias
 //   * the final contribution is evaluated on the exact primary-hit surface (not the quantised G-buffer), one shadow
 //     ray per reservoir + one for the directional light
 // Stages (each a loop over pixels here, a kernel + a wavefront shadow-ray launch in the CUDA path):
@@ -220,7 +222,18 @@ inline void rs_temporal_pixel(Frame& F, RsScratch& S, const mat4& prev_ivp, bool
 }
 
 // ---- stage 3: spatial reuse with MIS bias correction -> buffer half 0; final contributions + shadow rays -----------
-inline void rs_spatial_pixel(Frame& F, RsScratch& S, uint32_t x, uint32_t y) {
+// visibility of a light sample from a neighbour's G-buffer surface (unbiased reuse): the shadow ray rs_eval_* describes
+inline float rs_mis_visibility(const Frame& F, const RsSurf& sj, const RsEval& e, uint32_t& rays) {
+  Ray r;
+  rs_put_ray(r, sj.o, e.wi, e.tmax);
+  ++rays;
+  return F.sc->trace(r, true).t >= 0.0f ? 0.0f : 1.0f;
+}
+
+// returns the shadow rays it traced itself (unbiased reuse only)
+inline uint32_t rs_spatial_pixel(Frame& F, RsScratch& S, uint32_t x, uint32_t y) {
+  uint32_t mis_rays = 0;
+  const bool unbiased = (F.settings.flags & RT_UNBIASED_REUSE) != 0u;
   const Scene& sc = *F.sc;
   const uint32_t W = F.g.w, H = F.g.h;
   const size_t px = (size_t)y * W + x, n = (size_t)W * H;
@@ -229,7 +242,7 @@ inline void rs_spatial_pixel(Frame& F, RsScratch& S, uint32_t x, uint32_t y) {
   for (int k = 0; k < 9; ++k) S.C[9 * px + k] = 0.0f;
   PixelReservoir out; rs_empty(out);
   RsSurf s; vec3 pos, n_raw;
-  if (!rs_gsurf(F, F.ivp, cam, x, y, false, s, pos, n_raw)) { F.reservoirs[px] = out; return; }
+  if (!rs_gsurf(F, F.ivp, cam, x, y, false, s, pos, n_raw)) { F.reservoirs[px] = out; return 0u; }
   const bool restir = !(F.settings.flags & RT_NO_RESTIR);
   const uint32_t n_pl = sc.lights.num_pointlights;
   if (restir) {
@@ -283,13 +296,17 @@ inline void rs_spatial_pixel(Frame& F, RsScratch& S, uint32_t x, uint32_t y) {
       float num = 0.0f, den = 0.0f;
       for (int j = 0; j < nc; ++j) {
         float ph = p_pl;
+        bool visible = true;
         if (j > 0) {
           RsSurf sj; vec3 pj, nj;
           rs_gsurf(F, F.ivp, cam, cx[j], cy[j], false, sj, pj, nj);
-          ph = rs_phat(rs_eval_pl(sj, sc.lights.pointlights[out.pl_idx]));
+          const RsEval e = rs_eval_pl(sj, sc.lights.pointlights[out.pl_idx]);
+          ph = rs_phat(e);
+          if (unbiased && ph > 0.0f) visible = rs_mis_visibility(F, sj, e, mis_rays) != 0.0f;
         }
-        den += ph * (float)F.reservoirs[n + (size_t)cy[j] * W + cx[j]].pl_m;
-        if (j == src_pl) num = ph;
+        const float term = ph * (float)F.reservoirs[n + (size_t)cy[j] * W + cx[j]].pl_m;
+        den += visible ? term : 0.0f;
+        if (j == src_pl) num = visible ? ph : 0.0f;
       }
       out.w_pl = (den > 0.0f && p_pl > 0.0f) ? (out.w_sum_pl * (num / den)) / p_pl : 0.0f;
     }
@@ -298,13 +315,17 @@ inline void rs_spatial_pixel(Frame& F, RsScratch& S, uint32_t x, uint32_t y) {
       float num = 0.0f, den = 0.0f;
       for (int j = 0; j < nc; ++j) {
         float ph = p_em;
+        bool visible = true;
         if (j > 0) {
           RsSurf sj; vec3 pj, nj;
           rs_gsurf(F, F.ivp, cam, cx[j], cy[j], false, sj, pj, nj);
-          ph = rs_phat(rs_eval_em(sj, q));
+          const RsEval e = rs_eval_em(sj, q);
+          ph = rs_phat(e);
+          if (unbiased && ph > 0.0f) visible = rs_mis_visibility(F, sj, e, mis_rays) != 0.0f;
         }
-        den += ph * (float)F.reservoirs[n + (size_t)cy[j] * W + cx[j]].m_em;
-        if (j == src_em) num = ph;
+        const float term = ph * (float)F.reservoirs[n + (size_t)cy[j] * W + cx[j]].m_em;
+        den += visible ? term : 0.0f;
+        if (j == src_em) num = visible ? ph : 0.0f;
       }
       out.w_em = (den > 0.0f && p_em > 0.0f) ? (out.w_sum_em * (num / den)) / p_em : 0.0f;
     }
@@ -340,6 +361,7 @@ inline void rs_spatial_pixel(Frame& F, RsScratch& S, uint32_t x, uint32_t y) {
       rs_put_ray(S.rays[3 * px + 2], xs.o, wi, 10000.0f);
     }
   }
+  return mis_rays;
 }
 
 inline uint64_t rs_trace(const Frame& F, RsScratch& S, uint32_t nplanes, uint32_t y0, uint32_t y1, int threads) {
@@ -375,7 +397,13 @@ inline void render_restir_ns(Frame& F, RsScratch& S, bool history_ok, uint32_t y
     F.rays_any += rs_trace(F, S, 2, a0, a1, threads);
     parallel_rows(a0, a1, threads, [&](uint32_t y) { for (uint32_t x = 0; x < W; ++x) rs_temporal_pixel(F, S, prev_ivp, history_ok, x, y); });
   }
-  parallel_rows(y0, y1, threads, [&](uint32_t y) { for (uint32_t x = 0; x < W; ++x) rs_spatial_pixel(F, S, x, y); });
+  std::atomic<uint64_t> mis_total{0};
+  parallel_rows(y0, y1, threads, [&](uint32_t y) {
+    uint64_t c = 0;
+    for (uint32_t x = 0; x < W; ++x) c += rs_spatial_pixel(F, S, x, y);
+    mis_total += c;
+  });
+  F.rays_any += mis_total.load();
   F.rays_any += rs_trace(F, S, 3, y0, y1, threads);
   parallel_rows(y0, y1, threads, [&](uint32_t y) {
     for (uint32_t x = 0; x < W; ++x) {

@@ -109,7 +109,7 @@ assert SETTINGS_DTYPE.itemsize == 64 and CONFIG_DTYPE.itemsize == 48 and SUBMESH
 
 MODE_REFERENCE, MODE_NORTHSTAR = 0, 1
 RAY_CLOSEST, RAY_ANY, RAY_DEVICE_PTRS = 0, 1, 2
-RT_NO_RESTIR, RT_NO_BOUNCE = 1, 2
+RT_NO_RESTIR, RT_NO_BOUNCE, RT_UNBIASED_REUSE = 1, 2, 4
 
 AUX = dict(prim=(0, np.uint32, 1), inst=(1, np.uint32, 1), depth=(2, np.float32, 1), normal=(3, np.float16, 4),
            albedo=(4, np.int8, 4), rma=(5, np.float16, 4), motion=(6, np.float16, 2), flags=(7, np.uint16, 1),

@@ -71,7 +71,7 @@ int launch_northstar_frame(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st);
 int restir_ns_prepare(SnkPt* ctx, TraceSegs& segs, cudaStream_t st);
 int build_emissive_table(SnkPt* ctx, cudaStream_t st);
 int restir_ns_initial(SnkPt* ctx, const SnkRtSettings& s, const RefQueue& q, cudaStream_t st);
-int restir_ns_reuse(SnkPt* ctx, const SnkRtSettings& s, const RefQueue& q, cudaStream_t st);
+int restir_ns_reuse(SnkPt* ctx, const SnkRtSettings& s, const RefQueue& q, cudaStream_t st, int spill_region);
 int restir_ns_resolve(SnkPt* ctx, cudaStream_t st);
 int launch_accumulate(const PixelPlanes& P, uint32_t npix, uint32_t count, cudaStream_t st);
 // taa.cu — TAA_Resolve.comp: resolved frame -> out (next history), this frame's velocity -> vel_out

@@ -380,7 +380,7 @@ int launch_northstar_frame(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st) 
     launches += restir_ns_initial(ctx, s, QA, sa);
     launches += traced_launch_q(ctx, "trace.qA0", segs, QA, sa, overlap ? 1 : 0);
     QA = ref_queue(ctx, 1, capA, 0);
-    rc = restir_ns_reuse(ctx, s, QA, sa);
+    rc = restir_ns_reuse(ctx, s, QA, sa, overlap ? 1 : 0);
     if (rc < 0) return rc;
     launches += rc;
     launches += traced_launch_q(ctx, "trace.qA1", segs, QA, sa, overlap ? 1 : 0);

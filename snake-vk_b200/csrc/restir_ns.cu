@@ -296,8 +296,21 @@ __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefe
 #ifndef SNK_RS_SPATIAL_CTAS
 #define SNK_RS_SPATIAL_CTAS 6  // 5 / 6 / 8 resident CTAs (96 / 80 / 64 registers): 0.492 / 0.443 / 0.449 ms on C2 (profiles/r04t_variants_occupancy.txt)
 #endif
-__global__ void __launch_bounds__(128, SNK_RS_SPATIAL_CTAS) k_rs_spatial(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, uint32_t npix) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+// SNKPT_RT_UNBIASED_REUSE: the shadow rays of the MIS weights are the one place where a north-star shading stage traces inline
+// (warp-synchronous tracer of traverse.cuh, as the reference-mode passes do): up to 2 rays per accepted neighbour, each needed
+// by the very next addition of the same thread
+struct RsTracer {
+  const TraceScene* S;
+  uint2 *sm_col, *gl_col;
+  // true when nothing lies between the surface point and the light sample (oracle: rs_mis_visibility)
+  __device__ __forceinline__ bool visible(vec3 o, const RsEval& e) const {
+    return trace_warp_any<128>(S, o.x, o.y, o.z, 0.001f, e.wi.x, e.wi.y, e.wi.z, e.tmax, sm_col, gl_col) == 0.0f;
+  }
+};
+
+template <bool UNBIASED>
+__device__ __forceinline__ void rs_spatial_thread(const SceneDev& D, const FrameConsts& fc, const PixelPlanes& P, const RsParams& rp, uint32_t i,
+                                                  const RsTracer& T, unsigned long long& n_mis) {
   size_t px = 0;
   uint32_t x, y;
   if (pixel_of(fc, i, x, y, px)) {
@@ -370,14 +383,31 @@ __global__ void __launch_bounds__(128, SNK_RS_SPATIAL_CTAS) k_rs_spatial(SceneDe
         const PointLightRec pl = load_pointlight(D.lights, src_pl >= 0 ? out.pl_idx : 0u);
         for (int j = 0; j < nc; ++j) {
           float ph_pl = p_pl, ph_em = p_em;
+          bool vis_pl = true, vis_em = true;
           if (j > 0) {
             RsSurf sj; vec3 pj, nj;
             rs_gsurf(fc, P, cpx[j] & 0xFFFFu, cpx[j] >> 16, sj, pj, nj);
-            if (src_pl >= 0) ph_pl = rs_phat(rs_eval_pl(sj, pl));
-            if (src_em >= 0) ph_em = rs_phat(rs_eval_em(sj, q));
+            if (src_pl >= 0) {
+              const RsEval e = rs_eval_pl(sj, pl);
+              ph_pl = rs_phat(e);
+              if (UNBIASED && ph_pl > 0.0f) { vis_pl = T.visible(sj.o, e); ++n_mis; }
+            }
+            if (src_em >= 0) {
+              const RsEval e = rs_eval_em(sj, q);
+              ph_em = rs_phat(e);
+              if (UNBIASED && ph_em > 0.0f) { vis_em = T.visible(sj.o, e); ++n_mis; }
+            }
           }
-          if (src_pl >= 0) { den_pl += ph_pl * (float)m_pl[j]; if (j == src_pl) num_pl = ph_pl; }
-          if (src_em >= 0) { den_em += ph_em * (float)m_em[j]; if (j == src_em) num_em = ph_em; }
+          if (src_pl >= 0) {
+            const float term = ph_pl * (float)m_pl[j];
+            den_pl += vis_pl ? term : 0.0f;
+            if (j == src_pl) num_pl = vis_pl ? ph_pl : 0.0f;
+          }
+          if (src_em >= 0) {
+            const float term = ph_em * (float)m_em[j];
+            den_em += vis_em ? term : 0.0f;
+            if (j == src_em) num_em = vis_em ? ph_em : 0.0f;
+          }
         }
         if (src_pl >= 0) out.w_pl = (den_pl > 0.0f && p_pl > 0.0f) ? (out.w_sum_pl * (num_pl / den_pl)) / p_pl : 0.0f;
         if (src_em >= 0) out.w_em = (den_em > 0.0f && p_em > 0.0f) ? (out.w_sum_em * (num_em / den_em)) / p_em : 0.0f;
@@ -385,6 +415,24 @@ __global__ void __launch_bounds__(128, SNK_RS_SPATIAL_CTAS) k_rs_spatial(SceneDe
     }
     store_reservoir(half0, px, out);
   }
+}
+
+__global__ void __launch_bounds__(128, SNK_RS_SPATIAL_CTAS) k_rs_spatial(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, uint32_t npix) {
+  unsigned long long n_mis = 0;
+  rs_spatial_thread<false>(D, fc, P, rp, blockIdx.x * blockDim.x + threadIdx.x, RsTracer{nullptr, nullptr, nullptr}, n_mis);
+}
+
+// unbiased reuse: persistent CTAs (the global spill area of the inline tracer is sized for resident grids, trace.cu:trace_spill_bytes)
+__global__ void __launch_bounds__(128, 4) k_rs_spatial_unbiased(TraceScene S, SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, uint32_t nthreads,
+                                                                unsigned long long* counters) {
+  __shared__ uint2 sm_stack[SHORT_STACK * 128];
+  __shared__ TraceScene sS;
+  if (threadIdx.x == 0) sS = S;
+  __syncthreads();
+  const RsTracer T{&sS, sm_stack + threadIdx.x, S.spill + ((size_t)blockIdx.x * 4 + (threadIdx.x >> 5)) * (SPILL_STACK * 32) + (threadIdx.x & 31u)};
+  unsigned long long n_mis = 0;
+  for (uint32_t base = blockIdx.x * 128u; base < nthreads; base += gridDim.x * 128u) rs_spatial_thread<true>(D, fc, P, rp, base + threadIdx.x, T, n_mis);
+  flush_counts(n_mis, 0ull, counters);
 }
 
 #ifndef SNK_RS_FINAL_CTAS
@@ -520,7 +568,7 @@ int restir_ns_initial(SnkPt* ctx, const SnkRtSettings& s, const RefQueue& q, cud
 
 // stages 2-3 (after the initial shadow rays are resolved): temporal reuse, spatial reuse + final evaluation; appends
 // the final shadow rays (point, emissive, directional) to q
-int restir_ns_reuse(SnkPt* ctx, const SnkRtSettings& s, const RefQueue& q, cudaStream_t st) {
+int restir_ns_reuse(SnkPt* ctx, const SnkRtSettings& s, const RefQueue& q, cudaStream_t st, int spill_region) {
   const RsLaunch L = rs_launch(ctx, s);
   unsigned long long* counters = reinterpret_cast<unsigned long long*>(ctx->dev_counters.as<uint32_t>() + 2);
   const SceneDev D = ctx->scene_dev();
@@ -531,7 +579,15 @@ int restir_ns_reuse(SnkPt* ctx, const SnkRtSettings& s, const RefQueue& q, cudaS
   // row-band group: the neighbours' temporal reservoirs of the rows spatial reuse can reach arrive here ...
   if (ctx->group) { const int xr = group_exchange(ctx, 0, st); if (xr < 0) return xr; }
   rec = prof_begin(ctx, "rs_spatial", L.npix, false, false, st);
-  k_rs_spatial<<<(stage_threads(ctx->fc.W, ctx->fc.row1 - ctx->fc.row0) + 127) / 128, 128, 0, st>>>(D, ctx->fc, ctx->planes, L.rp, L.npix);
+  const uint32_t sp_threads = stage_threads(ctx->fc.W, ctx->fc.row1 - ctx->fc.row0);
+  if (s.flags & SNKPT_RT_UNBIASED_REUSE) {
+    TraceScene S = ctx->trace_scene();
+    S.spill += (size_t)spill_region * (trace_spill_bytes() / sizeof(uint2));
+    const uint32_t resident = (uint32_t)device_sm_count() * 4u, want = (sp_threads + 127u) / 128u;
+    k_rs_spatial_unbiased<<<want < resident ? want : resident, 128, 0, st>>>(S, D, ctx->fc, ctx->planes, L.rp, sp_threads, counters);
+  } else {
+    k_rs_spatial<<<(sp_threads + 127) / 128, 128, 0, st>>>(D, ctx->fc, ctx->planes, L.rp, L.npix);
+  }
   prof_end(ctx, rec, st);
   // ... and the final reservoirs the next frame's temporal reuse may reproject to leave as soon as they exist
   if (ctx->group) { const int xr = group_exchange(ctx, 1, st); if (xr < 0) return xr; }

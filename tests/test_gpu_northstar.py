@@ -65,10 +65,12 @@ def test_bounce_count_and_flags(snk, oracle):
 
 
 @pytest.mark.parametrize("kw", [dict(flags=1), dict(num_temporal=0, num_spatial=0), dict(num_temporal=1, num_spatial=0),
-                                dict(num_temporal=0, num_spatial=6), dict(ris_iters=4, m_cap=3, neighbour_radius=8.0)])
+                                dict(num_temporal=0, num_spatial=6), dict(ris_iters=4, m_cap=3, neighbour_radius=8.0),
+                                dict(flags=4), dict(flags=4, num_spatial=6, neighbour_radius=12.0)])
 def test_restir_settings_match_oracle(snk, oracle, kw):
     """north-star ReSTIR DI stages under other settings (flags=1: reservoir passes off = plain path tracer with NEE at x0;
-    ris_iters < number of point lights exercises the random-candidate branch), emissive + point lights (small scene)"""
+    ris_iters < number of point lights exercises the random-candidate branch; flags=4: unbiased reuse, the MIS weights' shadow rays
+    traced inline by the spatial stage and counted), emissive + point lights (small scene)"""
     sc = snk.scenes.small_test_scene(80, 48)
     for f, pt, fr in run(snk, oracle, sc, frames=3, **kw):
         a, b = pt.read_aux("radiance")[..., :3], fr.read("radiance")[..., :3]
