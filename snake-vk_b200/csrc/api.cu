@@ -959,7 +959,7 @@ int snkpt_trace_primary(SnkPt* ctx, const float* jitter_xy, void* stream) {
   FrameConsts fg = ctx->fc;
   widen_rows(ctx, ctx->halo_gbuffer, fg.row0, fg.row1);
   const int rec = prof_begin(ctx, "primary", (uint64_t)ctx->W * (fg.row1 - fg.row0), false, false, st);
-  ctx->stats.kernel_launches += launch_primary(ctx->trace_scene(), ctx->scene_dev(), fg, ctx->planes, st);
+  ctx->stats.kernel_launches += launch_primary(ctx->trace_scene(), ctx->scene_dev(), fg, ctx->planes, ctx->dev_counters.as<uint32_t>() + 200, ctx->primary_parity++, st);
   prof_end(ctx, rec, st);
   cudaEventRecord(ctx->ev[1], st);
   CK(cudaGetLastError());

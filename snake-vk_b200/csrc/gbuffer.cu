@@ -150,16 +150,16 @@ __device__ __forceinline__ void pk_node(const uint4* __restrict__ nodes, uint32_
                                         uint32_t& inner, uint32_t& leaf, uint32_t& rec_base, uint32_t& my_child) {
   uint4 n0, n1, n2, n3, n4;
   load_node(nodes, idx, n0, n1, n2, n3, n4);
-  const uint32_t c = (lane & 7u) ^ s.octinv, sh = (c & 3u) * 8u;
-  const bool hi = c >= 4u;
-  const uint32_t meta = ((hi ? n1.w : n1.z) >> sh) & 0xFFu;
+  const uint32_t c = (lane & 7u) ^ s.octinv;
+  // byte c of an 8-byte row = one PRMT over the word pair (selector nibble 0..7); the & 0xFF folds into the I2F.U8
+  const uint32_t meta = __byte_perm(n1.z, n1.w, c) & 0xFFu;
   const float px = __uint_as_float(n0.x) - s.ox, py = __uint_as_float(n0.y) - s.oy, pz = __uint_as_float(n0.z) - s.oz;
   const float sx = __uint_as_float((n0.w & 0xFFu) << 23), sy = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23),
               sz = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23);
   // child box relative to the origin (layouts.h: w2 = qlo_x | qlo_y, w3 = qlo_z | qhi_x, w4 = qhi_y | qhi_z)
-  const float lox = fmaf((float)(((hi ? n2.y : n2.x) >> sh) & 0xFFu), sx, px), hix = fmaf((float)(((hi ? n3.w : n3.z) >> sh) & 0xFFu), sx, px);
-  const float loy = fmaf((float)(((hi ? n2.w : n2.z) >> sh) & 0xFFu), sy, py), hiy = fmaf((float)(((hi ? n4.y : n4.x) >> sh) & 0xFFu), sy, py);
-  const float loz = fmaf((float)(((hi ? n3.y : n3.x) >> sh) & 0xFFu), sz, pz), hiz = fmaf((float)(((hi ? n4.w : n4.z) >> sh) & 0xFFu), sz, pz);
+  const float lox = fmaf((float)(__byte_perm(n2.x, n2.y, c) & 0xFFu), sx, px), hix = fmaf((float)(__byte_perm(n3.z, n3.w, c) & 0xFFu), sx, px);
+  const float loy = fmaf((float)(__byte_perm(n2.z, n2.w, c) & 0xFFu), sy, py), hiy = fmaf((float)(__byte_perm(n4.x, n4.y, c) & 0xFFu), sy, py);
+  const float loz = fmaf((float)(__byte_perm(n3.x, n3.y, c) & 0xFFu), sz, pz), hiz = fmaf((float)(__byte_perm(n4.z, n4.w, c) & 0xFFu), sz, pz);
   // largest signed distance of the box to this lane's plane; < 0 (beyond the slack): the box is outside the pyramid
   const float m = (fmaxf(s.nx * lox, s.nx * hix) + fmaxf(s.ny * loy, s.ny * hiy)) + fmaxf(s.nz * loz, s.nz * hiz);
   const float ext = ((fabsf(lox) + fabsf(hix)) + (fabsf(loy) + fabsf(hiy))) + (fabsf(loz) + fabsf(hiz));
@@ -279,14 +279,23 @@ __device__ __forceinline__ void pk_trace(const TraceScene& S, float ox, float oy
 #ifndef SNK_PACKET_CTAS
 #define SNK_PACKET_CTAS 8
 #endif
-__global__ void __launch_bounds__(128, SNK_PACKET_CTAS) k_primary_packet(TraceScene S, SceneDev D, FrameConsts fc, PixelPlanes P) {
+__global__ void __launch_bounds__(128, SNK_PACKET_CTAS) k_primary_packet(TraceScene S, SceneDev D, FrameConsts fc, PixelPlanes P, uint32_t* ticket,
+                                                                         uint32_t* next_ticket) {
   __shared__ uint32_t sm_stack[4 * PK_STACK];
-  const uint32_t t = threadIdx.x, w = t >> 5, l = t & 31;
+  const uint32_t w = threadIdx.x >> 5, l = threadIdx.x & 31;
   uint32_t* stk = sm_stack + w * PK_STACK;
-  const uint32_t tiles_x = (fc.W + 15u) / 16u, n_tiles = tiles_x * ((fc.row1 - fc.row0 + 7u) / 8u);
-  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const uint32_t x = (tile % tiles_x) * 16 + (w & 1) * 8 + (l & 7);
-    const uint32_t y = fc.row0 + (tile / tiles_x) * 8 + (w >> 1) * 4 + (l >> 3);
+  // the warps are independent: each draws its 8x4 tiles from a ticket (four consecutive tickets = one 16x8 block, so
+  // neighbouring warps work on neighbouring pixels); tiles of sky and of dense geometry differ 10x in cost
+  const uint32_t tiles_x = (fc.W + 15u) / 16u, n_tiles = 4u * tiles_x * ((fc.row1 - fc.row0 + 7u) / 8u);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *next_ticket = 0u;  // the next launch's ticket (stream order: nobody reads it before)
+  for (;;) {
+    uint32_t tile = 0;
+    if (l == 0) tile = atomicAdd(ticket, 1u);
+    tile = __shfl_sync(PK_FULL, tile, 0);
+    if (tile >= n_tiles) break;
+    const uint32_t q = tile & 3u, blk = tile >> 2;
+    const uint32_t x = (blk % tiles_x) * 16 + (q & 1) * 8 + (l & 7);
+    const uint32_t y = fc.row0 + (blk / tiles_x) * 8 + (q >> 1) * 4 + (l >> 3);
     const bool in_range = x < fc.W && y < fc.row1;
     const size_t px = in_range ? (size_t)y * fc.W + x : 0;
     if (in_range) {
@@ -317,16 +326,19 @@ __global__ void k_accumulate(const float4* __restrict__ radiance, float4* __rest
 
 }  // namespace
 
-int launch_primary(const TraceScene& S, const SceneDev& D, const FrameConsts& fc, const PixelPlanes& P, cudaStream_t st) {
+int launch_primary(const TraceScene& S, const SceneDev& D, const FrameConsts& fc, const PixelPlanes& P, uint32_t* tickets2, uint32_t parity,
+                   cudaStream_t st) {
   if (fc.row1 <= fc.row0) return 0;
   const uint32_t n_tiles = ((fc.W + 15) / 16) * ((fc.row1 - fc.row0 + 7) / 8);
-  const uint32_t grid = n_tiles < 148u * PRIMARY_CTAS_PER_SM ? n_tiles : 148u * PRIMARY_CTAS_PER_SM;
   // SNKPT_PRIMARY=ray selects the one-ray-per-lane kernel (A/B measurements; same bits either way)
   static const bool one_ray = getenv("SNKPT_PRIMARY") && getenv("SNKPT_PRIMARY")[0] == 'r';
-  if (one_ray) k_primary<<<grid, 128, 0, st>>>(S, D, fc, P);
-  else {
+  if (one_ray) {
+    const uint32_t resident = (uint32_t)device_sm_count() * PRIMARY_CTAS_PER_SM;
+    k_primary<<<n_tiles < resident ? n_tiles : resident, 128, 0, st>>>(S, D, fc, P);
+  } else {
+    // two tickets used in turn: a launch draws from one and zeroes the other for its successor (no memset between frames)
     const uint32_t resident = (uint32_t)device_sm_count() * SNK_PACKET_CTAS;
-    k_primary_packet<<<n_tiles < resident ? n_tiles : resident, 128, 0, st>>>(S, D, fc, P);
+    k_primary_packet<<<n_tiles < resident ? n_tiles : resident, 128, 0, st>>>(S, D, fc, P, tickets2 + (parity & 1u), tickets2 + ((parity & 1u) ^ 1u));
   }
   return 1 + (D.num_textures ? launch_gbuffer_normal_map(D, fc, P, st) : 0);
 }

@@ -59,7 +59,8 @@ int traced_launch(SnkPt* ctx, const char* name, const float4* rays, uint64_t n, 
                   uint32_t* inst_soa, float* vis_out, cudaStream_t st);
 
 // gbuffer.cu — primary visibility (replaces GBufferPass::RecordCommandBuffer, GBufferPass.cpp:70-196)
-int launch_primary(const TraceScene& S, const SceneDev& D, const FrameConsts& fc, const PixelPlanes& P, cudaStream_t st);
+// tickets2: two device words used in turn by the packet kernel's tile fetch (dev_counters u32 [200, 201])
+int launch_primary(const TraceScene& S, const SceneDev& D, const FrameConsts& fc, const PixelPlanes& P, uint32_t* tickets2, uint32_t parity, cudaStream_t st);
 // gbuffer_nm.cu — normal maps applied to the G-buffer normal plane (second pass, only when textures are set)
 int launch_gbuffer_normal_map(const SceneDev& D, const FrameConsts& fc, const PixelPlanes& P, cudaStream_t st);
 
