@@ -718,6 +718,7 @@ int snkpt_set_lights(SnkPt* ctx, const void* light_data, size_t bytes) {
   int rc = upload_async(ctx, ctx->lights.p, light_data, bytes);
   if (rc) return rc;
   ctx->num_pointlights = L->num_pointlights;
+  ctx->has_dir_light = L->dir_light.colour[0] > 0.0f || L->dir_light.colour[1] > 0.0f || L->dir_light.colour[2] > 0.0f;  // as ns_light_counts
   return SNKPT_OK;
 }
 

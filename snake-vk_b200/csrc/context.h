@@ -136,6 +136,7 @@ struct SnkPt {
   std::vector<uint32_t> h_blas_of_instance, h_emissive;
   std::vector<float> h_transforms, h_prev_transforms;
   uint32_t num_instances = 0, num_emissive = 0, num_pointlights = 0;
+  bool has_dir_light = false;  // host mirror: the directional light has a colour (snkpt_set_lights)
   snk::DevBuf materials, lights, transforms, prev_transforms, normal_mats, det3, instances, blas_of_instance, emissive_idx;
   snk::DevBuf tex_table, srgb_lut;  // albedo textures
   std::vector<snk::DevBuf> tex_data;
@@ -196,7 +197,7 @@ struct SnkPt {
   snk::DevBuf dev_counters;
   snk::DevBuf trav_spill;    // global overflow of the short traversal stacks (traverse.cuh)
   uint32_t ticket_rr = 0;
-  uint32_t primary_parity = 0;  // which of the two tile tickets the next k_primary_packet launch draws from
+  uint32_t primary_parity = 0, shadow_parity = 0;  // which of the two tile tickets the next k_primary_packet launch draws from
 
   SnkPtStats stats{};
   cudaEvent_t ev[8] = {};

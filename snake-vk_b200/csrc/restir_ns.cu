@@ -15,8 +15,11 @@
 // oracle/snk_restir_ns.h (which lists how it differs from the reference's biased passes); this file must match that
 // statement bit for bit: same expression order, -fmad=false, PCG-hash random numbers, no trigonometry.
 // No shadow ray is traced inside a shading kernel: every ray goes through the wavefront traversal kernel.
+#include <cstdlib>
+
 #include "kernels.h"
 #include "northstar.cuh"
+#include "packet.cuh"
 
 namespace snk {
 
@@ -441,7 +444,7 @@ __global__ void __launch_bounds__(128, 4) k_rs_spatial_unbiased(TraceScene S, Sc
 // final contributions of the reservoir the spatial stage just stored, on the exact primary-hit surface. Its own kernel: together
 // with the reuse loops the stage needed 96 registers AND 190 local-memory spill instructions (cuobjdump, r02z).
 __global__ void __launch_bounds__(128, SNK_RS_FINAL_CTAS) k_rs_final(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, RsBuffers B, uint32_t npix,
-                                                                     unsigned long long* counters, uint32_t* q_refs, uint32_t* q_count) {
+                                                                     unsigned long long* counters, uint32_t* q_refs, uint32_t* q_count, uint32_t dir_packet) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long n_shadow = 0;
   bool ray0 = false, ray1 = false, ray2 = false;
@@ -489,13 +492,47 @@ __global__ void __launch_bounds__(128, SNK_RS_FINAL_CTAS) k_rs_final(SceneDev D,
     }
     if (n_pl > 0 && !ray0) B.vis[px] = 1.0f;
     if (n_em > 0 && !ray1) B.vis[np + px] = 1.0f;
-    if (!ray2) B.vis[2 * np + px] = 1.0f;
+    if (!ray2) {
+      B.vis[2 * np + px] = 1.0f;
+      if (dir_packet) put_dead(B.rays, 2 * np + px);  // k_rs_shadow_dir walks every pixel of the band
+    }
     B.C[px] = make_float4(C0.x, C0.y, C0.z, 0.0f);
     B.C[np + px] = make_float4(C1.x, C1.y, C1.z, 0.0f);
     B.C[2 * np + px] = make_float4(C2.x, C2.y, C2.z, 0.0f);
   }
-  q_append3(q_refs, q_count, ray0, make_ref(SEG_RS_PL, px), ray1, make_ref(SEG_RS_EM, px), ray2, make_ref(SEG_RS_DIR, px));
+  // with dir_packet the directional shadow rays are not queued: k_rs_shadow_dir traces them tile by tile as packets
+  q_append3(q_refs, q_count, ray0, make_ref(SEG_RS_PL, px), ray1, make_ref(SEG_RS_EM, px), ray2 && !dir_packet, make_ref(SEG_RS_DIR, px));
   flush_counts(n_shadow, 0ull, counters);
+}
+
+// shadow rays towards the directional light: the 32 rays of an 8x4 pixel tile are parallel and start from neighbouring surface
+// points — one packet (packet.cuh) instead of 32 entries of the traversal queue. Same visibility bits: the triangle test is the
+// queue kernel's, the any-hit answer does not depend on the order or the number of triangles looked at.
+#ifndef SNK_SHADOW_PACKET_CTAS
+#define SNK_SHADOW_PACKET_CTAS 8
+#endif
+__global__ void __launch_bounds__(128, SNK_SHADOW_PACKET_CTAS) k_rs_shadow_dir(TraceScene S, FrameConsts fc, const float4* __restrict__ rays, float* __restrict__ vis,
+                                                                               uint32_t* ticket, uint32_t* next_ticket) {
+  __shared__ uint32_t sm_stack[4 * PK_STACK];
+  const uint32_t w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  uint32_t* stk = sm_stack + w * PK_STACK;
+  const uint32_t tiles_x = (fc.W + 15u) / 16u, n_tiles = 4u * tiles_x * ((fc.row1 - fc.row0 + 7u) / 8u);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *next_ticket = 0u;
+  for (;;) {
+    uint32_t tile = 0;
+    if (l == 0) tile = atomicAdd(ticket, 1u);
+    tile = __shfl_sync(PK_FULL, tile, 0);
+    if (tile >= n_tiles) break;
+    const uint32_t q = tile & 3u, blk = tile >> 2;
+    const uint32_t x = (blk % tiles_x) * 16 + (q & 1) * 8 + (l & 7);
+    const uint32_t y = fc.row0 + (blk / tiles_x) * 8 + (q >> 1) * 4 + (l >> 3);
+    const bool in_range = x < fc.W && y < fc.row1;
+    const size_t px = in_range ? (size_t)y * fc.W + x : 0;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 1.f, 0.f, -1.0f);
+    if (in_range) { a = rays[2 * px]; b = rays[2 * px + 1]; }
+    const bool hit = pk_trace_parallel_any(S, a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, stk, l);
+    if (in_range && b.w > a.w) vis[px] = hit ? 0.0f : 1.0f;
+  }
 }
 
 __global__ void __launch_bounds__(256) k_rs_resolve(FrameConsts fc, PixelPlanes P, RsBuffers B, uint32_t npix, uint32_t npix_frame, uint32_t has_pl,
@@ -592,8 +629,26 @@ int restir_ns_reuse(SnkPt* ctx, const SnkRtSettings& s, const RefQueue& q, cudaS
   // ... and the final reservoirs the next frame's temporal reuse may reproject to leave as soon as they exist
   if (ctx->group) { const int xr = group_exchange(ctx, 1, st); if (xr < 0) return xr; }
   rec = prof_begin(ctx, "rs_final", L.npix, false, false, st);
-  k_rs_final<<<(stage_threads(ctx->fc.W, ctx->fc.row1 - ctx->fc.row0) + 127) / 128, 128, 0, st>>>(D, ctx->fc, ctx->planes, L.rp, L.B, L.npix, counters, q.refs, q.count);
+  // SNKPT_SHADOW_DIR=packet traces the directional shadow rays as parallel-ray packets (k_rs_shadow_dir) instead of queueing them.
+  // Measured and NOT adopted (profiles/r05g_variants_shadow_packet.txt): C2 0.81 M rays cost 0.39 ms as packets against 0.22 ms
+  // inside trace.qA1 — the rays of a tile leave from surface points that lie metres apart at grazing view angles, the shared
+  // volume is wide, and an any-hit ray is cheap on its own (8 nodes); C4 at 4K: 0.68 vs 0.79 ms, within noise of the frame.
+  static const bool dir_packet_env = getenv("SNKPT_SHADOW_DIR") && getenv("SNKPT_SHADOW_DIR")[0] == 'p';
+  const bool dir_packet = ctx->has_dir_light && dir_packet_env;
+  k_rs_final<<<(stage_threads(ctx->fc.W, ctx->fc.row1 - ctx->fc.row0) + 127) / 128, 128, 0, st>>>(D, ctx->fc, ctx->planes, L.rp, L.B, L.npix, counters, q.refs, q.count,
+                                                                                                   dir_packet ? 1u : 0u);
   prof_end(ctx, rec, st);
+  if (dir_packet) {
+    rec = prof_begin(ctx, "shadow.dir", L.npix, false, false, st);
+    const uint32_t n_tiles = ((ctx->fc.W + 15u) / 16u) * ((ctx->fc.row1 - ctx->fc.row0 + 7u) / 8u);
+    const uint32_t resident = (uint32_t)device_sm_count() * SNK_SHADOW_PACKET_CTAS;
+    uint32_t* tickets2 = ctx->dev_counters.as<uint32_t>() + 202;  // second self-resetting ticket pair (the first: gbuffer.cu)
+    const uint32_t par = ctx->shadow_parity++ & 1u;
+    k_rs_shadow_dir<<<n_tiles < resident ? n_tiles : resident, 128, 0, st>>>(ctx->trace_scene(), ctx->fc, L.B.rays + 4ull * L.npix_frame, L.B.vis + 2ull * L.npix_frame,
+                                                                             tickets2 + par, tickets2 + (par ^ 1u));
+    prof_end(ctx, rec, st);
+    return 4;
+  }
   return 3;
 }
 
