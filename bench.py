@@ -513,7 +513,7 @@ def run_gpu_arm(args, snk):
         sc4, desc4 = make_scene(snk, "c4", 3840, 2160)
         strong["C4_4K"] = strong_scaling(args, snk, torch, dist, sc4, None, stream, rank, world, local, barrier, reduce_max_sum, verify=False)
         strong["C4_4K"]["workload"] = desc4
-        strong["note"] = ("row bands of ONE image (snkpt_group_attach_nccl): each rank renders H/N rows; temporal reservoirs of 30 rows and final reservoirs of 16 rows "
+        strong["note"] = ("row bands of ONE image (snkpt_group_attach_nccl), band heights balanced by the rays each band traced in two probe rounds (snkpt_group_set_bands; --equal-bands keeps H/N rows): temporal reservoirs of 30 rows and final reservoirs of 16 rows "
                           "per band edge travel by ncclSend/ncclRecv on the frame's stream; only the G-buffer keeps a 31-row halo. efficiency = whole-frame ms / (N x band ms)")
 
     # ---- the other BASELINE configs on one GPU
@@ -571,14 +571,48 @@ def strong_scaling(args, snk, torch, dist, sc, whole, stream, rank, world, local
     steps = max(5, min(args.steps, 20))
     ms_w, _, _ = timed(torch, lw, steps, barrier)
     ms_w = reduce_max_sum([ms_w])[0] / steps
-    band = snk.api.group_band(H, world, rank)
-    pb = snk.PathTracer(W, H, device=local, rows=band)
-    pb.upload_scene(sc)
-    # the 128-byte NCCL id travels through torch.distributed (plumbing); the exchange itself lives in the library
-    ids = [snk.api.group_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(ids, src=0)
-    pb.group_attach_nccl(rank, world, ids[0], 30, 16)
-    lb = FrameLoop(snk, sc, pb, stream, settings)
+    def make_group(starts):
+        band = (int(starts[rank]), int(starts[rank + 1]))
+        pb = snk.PathTracer(W, H, device=local, rows=band)
+        pb.upload_scene(sc)
+        pb.group_set_bands(starts)
+        # the 128-byte NCCL id travels through torch.distributed (plumbing); the exchange itself lives in the library
+        ids = [snk.api.group_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        pb.group_attach_nccl(rank, world, ids[0], 30, 16)
+        return pb, band, FrameLoop(snk, sc, pb, stream, settings)
+
+    def gather(x):
+        mine = torch.tensor([float(x)], device=f"cuda:{local}", dtype=torch.float64)
+        allv = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        return [float(t[0]) for t in allv]
+
+    # band heights: equal bands first; the rays each band traced over a few frames give a piecewise-constant cost per row
+    # (plus a fixed share per row for the stages that touch every pixel), and the boundaries are moved to equal cost —
+    # rows of sky cost a fraction of rows full of geometry (snkpt_group_set_bands). Two rounds settle it.
+    starts = [snk.api.group_band(H, world, r)[0] for r in range(world)] + [H]
+    balance_log = []
+    for _ in range(0 if args.equal_bands else 2):
+        pb, band, lb = make_group(starts)
+        for _ in range(3):
+            lb.step()
+        _, rays_probe, _ = timed(torch, lb, 3, barrier)
+        rays = gather(rays_probe / 3)
+        pb.group_detach(); pb.close()
+        rows = np.diff(np.asarray(starts, np.float64))
+        mean_density = sum(rays) / H
+        cost_row = np.concatenate([np.full(int(rows[r]), rays[r] / rows[r] + 0.5 * mean_density) for r in range(world)])  # 0.5: per-pixel stages
+        cum = np.concatenate([[0.0], np.cumsum(cost_row)])
+        new = [0] + [int(np.searchsorted(cum, cum[-1] * r / world)) for r in range(1, world)] + [H]
+        for r in range(1, world + 1):  # at least 8 rows per band
+            new[r] = max(new[r], new[r - 1] + 8)
+        new[world] = H
+        for r in range(world - 1, 0, -1):
+            new[r] = min(new[r], new[r + 1] - 8)
+        balance_log.append({"starts": [int(v) for v in starts], "mrays_per_band": [round(v / 1e6, 3) for v in rays]})
+        starts = new
+    pb, band, lb = make_group(starts)
     ok = 1.0
     if verify:
         # parity of the group path: my band of frames 0-3 equals the same rows of a whole-frame context, bit for bit
@@ -614,7 +648,8 @@ def strong_scaling(args, snk, torch, dist, sc, whole, stream, rank, world, local
     return {"n_gpus": world, "resolution": [W, H], "ms_per_frame": ms_b, "ms_per_frame_1gpu": ms_w, "efficiency_vs_n1": ms_w / (world * ms_b),
             "speedup": ms_w / ms_b, "mrays_per_s": rays_b / steps / (ms_b * 1e-3) / 1e6, "gpu_launches_per_frame_all_ranks": launches_b / steps,
             "verified_bit_exact_vs_whole_frame": bool(verify), "nccl_bytes_sent_rank0_total": int(sent), "steps": steps,
-            "per_rank_ms": [round(float(t[0]), 4) for t in per_rank], "per_rank_mrays": [round(float(t[1]) / 1e6, 3) for t in per_rank]}
+            "per_rank_ms": [round(float(t[0]), 4) for t in per_rank], "per_rank_mrays": [round(float(t[1]) / 1e6, 3) for t in per_rank],
+            "band_starts": [int(v) for v in starts], "band_balancing": balance_log}
 
 
 def other_configs(args, snk, torch, stream):
@@ -717,6 +752,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="N = 1: skip the C2-1M / C3 / C4 / C5 sub-records")
     ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the row-band (strong scaling) sub-record")
+    ap.add_argument("--equal-bands", action="store_true", help="N > 1: keep the row bands equal instead of balancing them by traced rays")
     args = ap.parse_args()
     snk = importlib.import_module("snake-vk_b200")
     if args.impl == "reference":

@@ -295,8 +295,13 @@ SNKPT_API int snkpt_set_halo(SnkPt* ctx, uint32_t pass1_halo, uint32_t gbuffer_h
  *                             time, SNKPT_NCCL_LIB overrides); rank 0 makes the id (snkpt_group_unique_id), the host
  *                             broadcasts the 128 bytes with whatever it has (torch.distributed in bench.py)
  *   snkpt_group_attach_local  the contexts of ONE process (several GPUs, or one GPU in tests), ordered by rank: direct
- *                             device-to-device copies; each context must then be driven by its own host thread */
+ *                             device-to-device copies; each context must then be driven by its own host thread
+ *   snkpt_group_set_bands     optional, before attaching: bands of unequal height (row_starts[0] = 0 < ... < row_starts[world]
+ *                             = height, the same table on every context of the group) — rows cost what they show (sky against
+ *                             geometry), so equal bands leave GPUs idle at the two exchanges; bench.py balances them from the
+ *                             rays each band traced. world = 0 / NULL returns to equal bands. */
 SNKPT_API void snkpt_group_band(uint32_t height, int world, int rank, uint32_t* row_begin, uint32_t* row_end);
+SNKPT_API int snkpt_group_set_bands(SnkPt* ctx, int world, const uint32_t* row_starts);
 SNKPT_API int snkpt_group_unique_id(void* out128);
 SNKPT_API int snkpt_group_attach_nccl(SnkPt* ctx, int rank, int world, const void* id128, uint32_t radius_rows, uint32_t margin_rows);
 SNKPT_API int snkpt_group_attach_local(SnkPt** ctxs, int n, uint32_t radius_rows, uint32_t margin_rows);

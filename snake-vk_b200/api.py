@@ -54,7 +54,7 @@ def load_library() -> C.CDLL:
         "snkpt_count_work": [vp, vp, vp, u64, u32, vp, vp],
         "snkpt_set_profiling": [vp, u32], "snkpt_get_launch_timings": [vp, vp, u32, vp],
         "snkpt_group_unique_id": [vp], "snkpt_group_attach_nccl": [vp, i32, i32, vp, u32, u32], "snkpt_group_attach_local": [vp, i32, u32, u32],
-        "snkpt_group_detach": [vp], "snkpt_group_info": [vp, vp, vp, vp],
+        "snkpt_group_detach": [vp], "snkpt_group_info": [vp, vp, vp, vp], "snkpt_group_set_bands": [vp, i32, vp],
     }
     for name, args in sig.items():
         fn = getattr(L, name)
@@ -82,7 +82,7 @@ EXPORTS = ["snkpt_create", "snkpt_destroy", "snkpt_last_error", "snkpt_default_s
            "snkpt_aux_size", "snkpt_write_reservoirs", "snkpt_device_ptr", "snkpt_get_stats", "snkpt_synchronize",
            "snkpt_trace_rays", "snkpt_count_work", "snkpt_set_profiling", "snkpt_get_launch_timings", "snkpt_taa_resolve", "snkpt_set_texture", "snkpt_read_output_async", "snkpt_read_output_wait", "snkpt_frame_jitter", "snkpt_particles_default_params",
            "snkpt_particles_create", "snkpt_particles_write", "snkpt_particles_read", "snkpt_particles_update", "snkpt_particles_rays",
-           "snkpt_group_band", "snkpt_group_unique_id", "snkpt_group_attach_nccl", "snkpt_group_attach_local", "snkpt_group_detach", "snkpt_group_info"]
+           "snkpt_group_band", "snkpt_group_unique_id", "snkpt_group_attach_nccl", "snkpt_group_attach_local", "snkpt_group_detach", "snkpt_group_info", "snkpt_group_set_bands"]
 
 CONFIG_DTYPE = np.dtype([("width", "<u4"), ("height", "<u4"), ("device", "<i4"), ("max_instances", "<u4"),
                          ("max_transforms", "<u4"), ("max_materials", "<u4"), ("row_begin", "<u4"), ("row_end", "<u4"),
@@ -326,6 +326,14 @@ class PathTracer:
         """one process per GPU: this context renders band `rank` of `world`; reservoir rows travel by ncclSend / ncclRecv"""
         buf = C.create_string_buffer(bytes(unique_id), 128)
         self._ck(self.L.snkpt_group_attach_nccl(self.h, rank, world, buf, radius_rows, margin_rows), "snkpt_group_attach_nccl")
+
+    def group_set_bands(self, row_starts):
+        """bands of unequal height for the next group_attach_* (world + 1 row boundaries); None -> equal bands"""
+        if row_starts is None:
+            self._ck(self.L.snkpt_group_set_bands(self.h, 0, None), "snkpt_group_set_bands")
+        else:
+            a = np.ascontiguousarray(row_starts, np.uint32)
+            self._ck(self.L.snkpt_group_set_bands(self.h, a.size - 1, _p(a)), "snkpt_group_set_bands")
 
     def group_detach(self):
         self._ck(self.L.snkpt_group_detach(self.h), "snkpt_group_detach")

@@ -197,7 +197,8 @@ struct SnkPt {
   snk::DevBuf dev_counters;
   snk::DevBuf trav_spill;    // global overflow of the short traversal stacks (traverse.cuh)
   uint32_t ticket_rr = 0;
-  uint32_t primary_parity = 0, shadow_parity = 0;  // which of the two tile tickets the next k_primary_packet launch draws from
+  uint32_t primary_parity = 0, shadow_parity = 0;
+  std::vector<uint32_t> band_starts;  // snkpt_group_set_bands: row boundaries of the group's bands (empty: equal bands)  // which of the two tile tickets the next k_primary_packet launch draws from
 
   SnkPtStats stats{};
   cudaEvent_t ev[8] = {};

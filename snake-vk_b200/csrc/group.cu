@@ -78,13 +78,15 @@ struct GroupState {
   std::atomic<uint64_t> posted[2];      // records issued per kind
   uint64_t seq[2] = {0, 0};
   uint64_t bytes_sent = 0;
+  std::vector<uint32_t> starts;         // world + 1 row boundaries (equal bands, or the table of snkpt_group_set_bands)
 };
 
-static void band_of(uint32_t H, int world, int r, uint32_t& b0, uint32_t& b1) {
+static void equal_band(uint32_t H, int world, int r, uint32_t& b0, uint32_t& b1) {
   const uint32_t q = H / (uint32_t)world, rem = H % (uint32_t)world;
   b0 = (uint32_t)r * q + ((uint32_t)r < rem ? (uint32_t)r : rem);
   b1 = b0 + q + ((uint32_t)r < rem ? 1u : 0u);
 }
+static void band_of(const GroupState* g, int r, uint32_t& b0, uint32_t& b1) { b0 = g->starts[r]; b1 = g->starts[r + 1]; }
 static void window_of(uint32_t H, uint32_t b0, uint32_t b1, uint32_t n, uint32_t& w0, uint32_t& w1) {
   w0 = b0 > n ? b0 - n : 0u;
   w1 = b1 + n < H ? b1 + n : H;
@@ -103,14 +105,14 @@ int group_exchange(SnkPt* ctx, int kind, cudaStream_t st) {
   const int half = kind == 0 ? 1 : 0;
   const size_t row_bytes = (size_t)W * sizeof(float4);
   uint32_t b0, b1, w0, w1;
-  band_of(H, g->world, g->rank, b0, b1);
+  band_of(g, g->rank, b0, b1);
   window_of(H, b0, b1, n, w0, w1);
   struct Xfer { int peer; uint32_t s0, s1, r0, r1; };
   std::vector<Xfer> plan;
   for (int p = 0; p < g->world; ++p) {
     if (p == g->rank) continue;
     uint32_t p0, p1, pw0, pw1;
-    band_of(H, g->world, p, p0, p1);
+    band_of(g, p, p0, p1);
     window_of(H, p0, p1, n, pw0, pw1);
     Xfer x{p, b0 > pw0 ? b0 : pw0, b1 < pw1 ? b1 : pw1, p0 > w0 ? p0 : w0, p1 < w1 ? p1 : w1};  // my rows the peer needs | its rows I need
     if (x.s0 < x.s1 || x.r0 < x.r1) plan.push_back(x);
@@ -160,10 +162,20 @@ int group_exchange(SnkPt* ctx, int kind, cudaStream_t st) {
 static int attach_common(SnkPt* ctx, int rank, int world, uint32_t radius_rows, uint32_t margin_rows, GroupState** out) {
   if (!ctx || world < 1 || rank < 0 || rank >= world) return SNKPT_E_INVALID;
   if (ctx->group) { ctx->err = "row-band group: the context already belongs to a group"; return SNKPT_E_STATE; }
-  uint32_t b0, b1;
-  band_of(ctx->H, world, rank, b0, b1);
-  if (ctx->row0 != b0 || ctx->row1 != b1) { ctx->err = "row-band group: the context's rows are not band `rank` of `world` equal bands (snkpt_group_band)"; return SNKPT_E_INVALID; }
+  std::vector<uint32_t> starts;
+  if (!ctx->band_starts.empty()) {
+    if ((int)ctx->band_starts.size() != world + 1) { ctx->err = "row-band group: the band table of snkpt_group_set_bands is for another group size"; return SNKPT_E_INVALID; }
+    starts = ctx->band_starts;
+  } else {
+    starts.resize((size_t)world + 1);
+    for (int r = 0; r < world; ++r) { uint32_t a, b; equal_band(ctx->H, world, r, a, b); starts[r] = a; starts[r + 1] = b; }
+  }
+  if (ctx->row0 != starts[rank] || ctx->row1 != starts[rank + 1]) {
+    ctx->err = "row-band group: the context's rows are not band `rank` of the group (snkpt_group_band, or the table of snkpt_group_set_bands)";
+    return SNKPT_E_INVALID;
+  }
   GroupState* g = new GroupState();
+  g->starts = starts;
   g->rank = rank; g->world = world; g->radius = radius_rows; g->margin = margin_rows;
   g->posted[0].store(0); g->posted[1].store(0);
   for (auto& a : g->ev) for (auto& e : a) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
@@ -192,9 +204,21 @@ extern "C" {
 
 SNKPT_API void snkpt_group_band(uint32_t height, int world, int rank, uint32_t* row_begin, uint32_t* row_end) {
   uint32_t b0 = 0, b1 = 0;
-  if (world >= 1 && rank >= 0 && rank < world) band_of(height, world, rank, b0, b1);
+  if (world >= 1 && rank >= 0 && rank < world) equal_band(height, world, rank, b0, b1);
   if (row_begin) *row_begin = b0;
   if (row_end) *row_end = b1;
+}
+
+SNKPT_API int snkpt_group_set_bands(SnkPt* ctx, int world, const uint32_t* row_starts) {
+  if (!ctx) return SNKPT_E_INVALID;
+  if (ctx->group) { ctx->err = "snkpt_group_set_bands: the context already belongs to a group (detach first)"; return SNKPT_E_STATE; }
+  if (world == 0 || !row_starts) { ctx->band_starts.clear(); return SNKPT_OK; }  // back to equal bands
+  if (world < 1) return SNKPT_E_INVALID;
+  if (row_starts[0] != 0u || row_starts[world] != ctx->H) { ctx->err = "snkpt_group_set_bands: the table must start at row 0 and end at the image height"; return SNKPT_E_INVALID; }
+  for (int r = 0; r < world; ++r)
+    if (row_starts[r] >= row_starts[r + 1]) { ctx->err = "snkpt_group_set_bands: every band needs at least one row"; return SNKPT_E_INVALID; }
+  ctx->band_starts.assign(row_starts, row_starts + world + 1);
+  return SNKPT_OK;
 }
 
 SNKPT_API int snkpt_group_unique_id(void* out128) {

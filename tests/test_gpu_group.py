@@ -31,17 +31,22 @@ def render_bands(snk, parts, ubo, prev, settings):
     assert not errs, errs
 
 
-@pytest.mark.parametrize("world,radius,margin", [(2, 6, 4), (3, 6, 4), (4, 30, 16)])
-def test_local_group_equals_whole_frame(snk, world, radius, margin):
+@pytest.mark.parametrize("world,radius,margin,starts", [(2, 6, 4, None), (3, 6, 4, None), (4, 30, 16, None),
+                                                        (3, 6, 4, (0, 10, 40, 64)),            # unequal bands (snkpt_group_set_bands)
+                                                        (4, 30, 16, (0, 100, 104, 200, 256))])  # a band thinner than the reuse radius
+def test_local_group_equals_whole_frame(snk, world, radius, margin, starts):
     sc = snk.scenes.small_test_scene(96, 64) if world < 4 else snk.scenes.small_test_scene(128, 256)
     H, W = sc.height, sc.width
+    band = (lambda r: (starts[r], starts[r + 1])) if starts else (lambda r: snk.api.group_band(H, world, r))
     st = snk.api.default_settings(mode=snk.api.MODE_NORTHSTAR, neighbour_radius=float(radius))
     whole = snk.PathTracer(W, H)
     whole.upload_scene(sc)
     parts = []
     for r in range(world):
-        pt = snk.PathTracer(W, H, rows=snk.api.group_band(H, world, r))
+        pt = snk.PathTracer(W, H, rows=band(r))
         pt.upload_scene(sc)
+        if starts:
+            pt.group_set_bands(starts)
         parts.append(pt)
     snk.api.group_attach_local(parts, radius, margin)
     assert parts[1].group_info()[:2] == (1, world)
@@ -56,7 +61,7 @@ def test_local_group_equals_whole_frame(snk, world, radius, margin):
         whole.render(st)
         render_bands(snk, parts, ubo, p, st)
         for name in ("radiance", "direct", "reservoirs_final", "reservoirs_temporal"):
-            got = np.concatenate([parts[r].read_aux(name)[slice(*snk.api.group_band(H, world, r))] for r in range(world)])
+            got = np.concatenate([parts[r].read_aux(name)[slice(*band(r))] for r in range(world)])
             want = whole.read_aux(name)
             assert got.tobytes() == want.tobytes(), f"world {world} frame {f}: {name} differs on {(got != want).reshape(H, W, -1).any(-1).sum()} pixels"
     out = np.concatenate([parts[r].read_output("f32") for r in range(world)])
@@ -76,6 +81,13 @@ def test_group_rejects_wrong_rows_and_reference_mode(snk):
     b = snk.PathTracer(64, 48, rows=(20, 48))
     with pytest.raises(snk.api.SnkError):
         snk.api.group_attach_local([a, b], 6, 4)   # not the equal bands of snkpt_group_band
+    with pytest.raises(snk.api.SnkError):
+        a.group_set_bands((0, 20, 20, 48))          # an empty band
+    with pytest.raises(snk.api.SnkError):
+        a.group_set_bands((0, 20, 40))              # does not end at the image height
+    a.group_set_bands((0, 20, 48)); b.group_set_bands((0, 20, 48))
+    snk.api.group_attach_local([a, b], 6, 4)       # the same rows are a group once the table says so
+    a.group_detach(); b.group_detach()
     a.close(); b.close()
     parts = [snk.PathTracer(64, 48, rows=snk.api.group_band(48, 2, r)) for r in range(2)]
     for pt in parts:
