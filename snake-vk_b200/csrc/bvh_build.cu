@@ -220,8 +220,11 @@ __device__ __forceinline__ unsigned long long expand21(unsigned long long x) {
   return x;
 }
 
+#ifndef SNK_HOIST_LARGE
+#define SNK_HOIST_LARGE 8  // 0 = off
+#endif
 __device__ __forceinline__ unsigned long long morton_key(const float4* __restrict__ prim_lo, const float4* __restrict__ prim_hi, uint32_t i,
-                                                         const uint32_t* __restrict__ counters) {
+                                                         const uint32_t* __restrict__ counters, const bool hoist_large = false) {
   const float lx = ord2f(counters[C_BOUNDS]), ly = ord2f(counters[C_BOUNDS + 1]), lz = ord2f(counters[C_BOUNDS + 2]);
   const float hx = ord2f(counters[C_BOUNDS + 3]), hy = ord2f(counters[C_BOUNDS + 4]), hz = ord2f(counters[C_BOUNDS + 5]);
   const float4 a = prim_lo[i], b = prim_hi[i];
@@ -236,14 +239,30 @@ __device__ __forceinline__ unsigned long long morton_key(const float4* __restric
   const float qx = fminf(fmaxf((0.5f * (a.x + b.x) - lx) * sx, 0.f), 2097151.f);
   const float qy = fminf(fmaxf((0.5f * (a.y + b.y) - ly) * sy, 0.f), 2097151.f);
   const float qz = fminf(fmaxf((0.5f * (a.z + b.z) - lz) * sz, 0.f), 2097151.f);
-  return (expand21((unsigned long long)qx) << 2) | (expand21((unsigned long long)qy) << 1) | expand21((unsigned long long)qz);
+  unsigned long long key = (expand21((unsigned long long)qx) << 2) | (expand21((unsigned long long)qy) << 1) | expand21((unsigned long long)qz);
+#if SNK_HOIST_LARGE
+  // Large-primitive hoisting (triangle builds of the multi-CTA path): a triangle much larger than its neighbours (a floor under a
+  // field of small objects) inflates the box of every ancestor on its path to the root, and every ray then has to open those
+  // ancestors. Bit 63 (above the 63 Morton bits; k_morton shifts it down with the key) moves such triangles into a subtree of
+  // their own directly under the root: two Morton-ordered hierarchies, one of the few large triangles and one of everything else
+  // with tight boxes. Large = longest box edge above 1/SNK_HOIST_LARGE of the longest edge of the centroid bounds.
+  // Measured (profiles/r05m_variants_hoist_large.txt): 1 M-triangle flat scene 15.4 -> 14.9 nodes per ray, frame 6.87 -> 6.74 ms;
+  // 3 M flat 33.7 -> 33.2 ms; thresholds 1/4, 1/8, 1/32 alike. For the TLAS (the floor INSTANCE) and the small meshes of the
+  // single-CTA builder it costs nodes (C2: 7.8 -> 8.4 per ray, frame 5.10 -> 5.21 ms): not applied there.
+  if (hoist_large) {
+    const float ext = fmaxf(fmaxf(hx - lx, hy - ly), hz - lz), pe = fmaxf(fmaxf(b.x - a.x, b.y - a.y), b.z - a.z);
+    if (pe * (float)SNK_HOIST_LARGE > ext && ext > 0.f) key |= 1ull << 63;
+  }
+#endif
+  return key;
 }
 // `drop` low key bits are shifted out: the radix sort then needs (63 - drop) / 8 passes instead of 8 (launch_build)
 __global__ void k_morton(const float4* __restrict__ prim_lo, const float4* __restrict__ prim_hi, uint32_t n,
-                         const uint32_t* __restrict__ counters, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, int drop) {
+                         const uint32_t* __restrict__ counters, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals, int drop,
+                         bool hoist_large) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  keys[i] = morton_key(prim_lo, prim_hi, i, counters) >> drop;
+  keys[i] = morton_key(prim_lo, prim_hi, i, counters, hoist_large) >> drop;
   vals[i] = i;
 }
 
@@ -1512,11 +1531,11 @@ int launch_build(BuildScratch& s, uint32_t n, const BuildOutput& out, const floa
   int passes = forced_passes >= 1 && forced_passes <= 8 ? forced_passes : (n > (4u << 20) ? 5 : 4);
   const int axis_bits = passes == 8 ? 21 : (8 * passes) / 3;
   const int key_bits = 3 * axis_bits;
-  k_morton<<<g, 256, 0, st>>>(s.prim_lo, s.prim_hi, n, s.counters, s.keys[0], s.vals[0], 63 - key_bits); ++launches;
+  k_morton<<<g, 256, 0, st>>>(s.prim_lo, s.prim_hi, n, s.counters, s.keys[0], s.vals[0], 63 - key_bits, out.tris != nullptr); ++launches;
   int cur = 0;
   if (n > 1) {
     const uint32_t nb = (n + SORT_TILE - 1) / SORT_TILE;
-    for (int shift = 0; shift < key_bits; shift += 8) {
+    for (int shift = 0; shift < key_bits + (SNK_HOIST_LARGE ? 1 : 0); shift += 8) {  // + the large-primitive bit above the Morton bits
       k_sort_hist<<<nb, SORT_THREADS, 0, st>>>(s.keys[cur], n, shift, s.block_hist, nb);
       k_scan_rows<<<256, 256, 0, st>>>(s.block_hist, nb, s.digit_total);
       k_scan_digits<<<1, 256, 0, st>>>(s.digit_total);

@@ -245,7 +245,7 @@ int launch_particles_substep(SnkPt* ctx, const SnkParticle* P, SnkParticle* out,
   cudaMemsetAsync(cell_start, 0xFF, 4ull * n, st);
   k_ptcl_cell_start<<<(n + 255) / 256, 256, 0, st>>>(s.keys[cur], n, cell_start);
   ++launches;
-  const uint32_t blocks = (n + PT_THREADS - 1) / PT_THREADS, persistent = 148u * PT_CTAS_PER_SM;
+  const uint32_t blocks = (n + PT_THREADS - 1) / PT_THREADS, persistent = (uint32_t)device_sm_count() * PT_CTAS_PER_SM;
   const int rec = prof_begin(ctx, "ptcl_update", n, false, false, st);
   k_ptcl_update<<<blocks < persistent ? blocks : persistent, PT_THREADS, 0, st>>>(ctx->trace_scene(), ctx->scene_dev(), P, out, s.keys[cur], s.vals[cur],
                                                                                    cell_start, n, prm, ray_counter);

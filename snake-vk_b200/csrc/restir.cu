@@ -419,13 +419,13 @@ __global__ void __launch_bounds__(RT_THREADS, RT_CTAS_PER_SM) k_restir_pass2(Tra
 int launch_restir_passes(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st) {
   const FrameConsts& fc = ctx->fc;
   const uint32_t n_tiles = ((fc.W + 15) / 16) * ((fc.row1 - fc.row0 + 7) / 8);
-  const uint32_t grid = n_tiles < 148u * RT_CTAS_PER_SM ? n_tiles : 148u * RT_CTAS_PER_SM;
+  const uint32_t grid = n_tiles < (uint32_t)device_sm_count() * RT_CTAS_PER_SM ? n_tiles : (uint32_t)device_sm_count() * RT_CTAS_PER_SM;
   // pass 1 also covers the halo rows whose temporal reservoirs this band's spatial reuse reads (snkpt_set_halo)
   FrameConsts f1 = fc;
   f1.row0 = fc.row0 > ctx->halo_pass1 ? fc.row0 - ctx->halo_pass1 : 0u;
   f1.row1 = fc.row1 + ctx->halo_pass1 < fc.H ? fc.row1 + ctx->halo_pass1 : fc.H;
   const uint32_t n_tiles1 = ((fc.W + 15) / 16) * ((f1.row1 - f1.row0 + 7) / 8);
-  const uint32_t grid1 = n_tiles1 < 148u * RT_CTAS_PER_SM ? n_tiles1 : 148u * RT_CTAS_PER_SM;
+  const uint32_t grid1 = n_tiles1 < (uint32_t)device_sm_count() * RT_CTAS_PER_SM ? n_tiles1 : (uint32_t)device_sm_count() * RT_CTAS_PER_SM;
   RestirParams rp{s.num_temporal_resamples, s.num_spatial_resamples, s.ris_iters, s.m_cap, s.neighbour_radius, s.normal_threshold, s.flags};
   unsigned long long* counter = reinterpret_cast<unsigned long long*>(ctx->dev_counters.as<uint32_t>() + 2);
   FrameConsts f = fc;
