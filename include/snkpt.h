@@ -389,7 +389,7 @@ SNKPT_API int snkpt_taa_resolve(SnkPt* ctx, void* stream);
  * Copies rows [row_begin,row_end) × width into dst (device→host, synchronous). */
 SNKPT_API int snkpt_read_output(SnkPt* ctx, void* dst, uint32_t format);
 /* The same copy without blocking: enqueued behind the frame on the context's copy stream, so it overlaps the next
- * frame (whose kernels wait for it before they overwrite the image). dst should be page-locked. slot = 0 / 1: two reads may
+ * frame (whose kernels wait for it before they overwrite the image). dst should be page-locked. slot = 0..3: up to four reads may
  * be in flight; snkpt_read_output_wait(slot) returns when that read has landed (the engine presents frame N while N+1 renders,
  * as the reference's frames in flight do, EditorLayer.cpp:563-665). */
 SNKPT_API int snkpt_read_output_async(SnkPt* ctx, void* dst, uint32_t format, uint32_t slot);

@@ -335,7 +335,7 @@ static int upload_async(SnkPt* ctx, void* dst, const void* src, size_t bytes) {
 
 namespace snk {
 void wait_readback(SnkPt* ctx, cudaStream_t st) {
-  for (int k = 0; k < 2; ++k)
+  for (int k = 0; k < 4; ++k)
     if (ctx->read_pending[k]) cudaStreamWaitEvent(st, ctx->ev_read_done[k], 0);
 }
 }  // namespace snk
@@ -1143,11 +1143,11 @@ int snkpt_read_output(SnkPt* ctx, void* dst, uint32_t format) {
 
 int snkpt_read_output_async(SnkPt* ctx, void* dst, uint32_t format, uint32_t slot) {
   if (!ctx) return SNKPT_E_INVALID;
-  REQUIRE(dst && format <= SNKPT_FMT_RGBA32F && slot < 2, SNKPT_E_INVALID, "snkpt_read_output_async: arguments");
+  REQUIRE(dst && format <= SNKPT_FMT_RGBA32F && slot < 4, SNKPT_E_INVALID, "snkpt_read_output_async: arguments");
   CK(cudaSetDevice(ctx->device));
   if (!ctx->copy_stream) {
     CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-    for (int k = 0; k < 2; ++k) CK(cudaEventCreateWithFlags(&ctx->ev_read_done[k], cudaEventDisableTiming));
+    for (int k = 0; k < 4; ++k) CK(cudaEventCreateWithFlags(&ctx->ev_read_done[k], cudaEventDisableTiming));
     if (!ctx->ev_frame_done) CK(cudaEventCreateWithFlags(&ctx->ev_frame_done, cudaEventDisableTiming));
   }
   // the copy starts when everything enqueued on the frame's stream so far is done and runs beside the next frame; kernels that
@@ -1155,8 +1155,13 @@ int snkpt_read_output_async(SnkPt* ctx, void* dst, uint32_t format, uint32_t slo
   CK(cudaEventRecord(ctx->ev_frame_done, work_stream(ctx)));
   CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_frame_done, 0));
   const size_t off = (size_t)ctx->row0 * ctx->W, cnt = (size_t)(ctx->row1 - ctx->row0) * ctx->W;
-  if (format == SNKPT_FMT_RGBA16F) CK(cudaMemcpyAsync(dst, ctx->planes.out16 + off, 8 * cnt, cudaMemcpyDeviceToHost, ctx->copy_stream));
-  else CK(cudaMemcpyAsync(dst, ctx->planes.radiance + off, 16 * cnt, cudaMemcpyDeviceToHost, ctx->copy_stream));
+  // in 1 MB pieces: one 16 MB transfer holds its copy engine for 0.3 ms, and the small copies / memsets with which the NEXT frame
+  // starts (TLAS staging, per-frame uploads) queued up behind it — measured +0.07 ms per frame for a single transfer beside the
+  // frame, +0.01 ms in pieces (tools/e2e_bisect.py, profiles/r05s_e2e_bisect.txt)
+  const char* src = format == SNKPT_FMT_RGBA16F ? reinterpret_cast<const char*>(ctx->planes.out16 + off) : reinterpret_cast<const char*>(ctx->planes.radiance + off);
+  const size_t total = (format == SNKPT_FMT_RGBA16F ? 8 : 16) * cnt, piece = 1u << 20;
+  for (size_t o = 0; o < total; o += piece)
+    CK(cudaMemcpyAsync(static_cast<char*>(dst) + o, src + o, total - o < piece ? total - o : piece, cudaMemcpyDeviceToHost, ctx->copy_stream));
   CK(cudaEventRecord(ctx->ev_read_done[slot], ctx->copy_stream));
   ctx->read_pending[slot] = true;
   return SNKPT_OK;
@@ -1164,7 +1169,7 @@ int snkpt_read_output_async(SnkPt* ctx, void* dst, uint32_t format, uint32_t slo
 
 int snkpt_read_output_wait(SnkPt* ctx, uint32_t slot) {
   if (!ctx) return SNKPT_E_INVALID;
-  REQUIRE(slot < 2, SNKPT_E_INVALID, "snkpt_read_output_wait: slot");
+  REQUIRE(slot < 4, SNKPT_E_INVALID, "snkpt_read_output_wait: slot");
   if (!ctx->read_pending[slot]) return SNKPT_OK;
   CK(cudaSetDevice(ctx->device));
   CK(cudaEventSynchronize(ctx->ev_read_done[slot]));

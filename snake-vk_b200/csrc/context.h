@@ -164,8 +164,8 @@ struct SnkPt {
   cudaStream_t aux_stream = nullptr, hi_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join_b = nullptr;
   cudaStream_t copy_stream = nullptr;
-  cudaEvent_t ev_frame_done = nullptr, ev_read_done[2] = {};
-  bool read_pending[2] = {false, false};
+  cudaEvent_t ev_frame_done = nullptr, ev_read_done[4] = {};
+  bool read_pending[4] = {false, false, false, false};
   void* h_stage = nullptr;       // pinned staging of the per-frame instance records (snkpt_build_tlas)
   size_t h_stage_bytes = 0;
   cudaEvent_t ev_stage = nullptr;
