@@ -389,7 +389,7 @@ void snkpt_destroy(SnkPt* ctx) {
   DevBuf* bufs[] = {&ctx->positions, &ctx->normals, &ctx->tangents, &ctx->uvs, &ctx->indices, &ctx->blas_nodes, &ctx->blas_tris,
                     &ctx->d_blas, &ctx->materials, &ctx->lights, &ctx->transforms, &ctx->prev_transforms, &ctx->normal_mats,
                     &ctx->det3, &ctx->instances, &ctx->blas_of_instance, &ctx->emissive_idx, &ctx->tlas_nodes, &ctx->tlas_leaf_ids,
-                    &ctx->inst_recs, &ctx->inst_sphere, &ctx->valid_slots, &ctx->q_rays, &ctx->q_hits, &ctx->q_work, &ctx->dev_counters, &ctx->trav_spill,
+                    &ctx->inst_recs, &ctx->inst_sphere, &ctx->valid_slots, &ctx->tlas_stage, &ctx->q_rays, &ctx->q_hits, &ctx->q_work, &ctx->dev_counters, &ctx->trav_spill,
                     &ctx->wave_refs, &ctx->wave_paths, &ctx->prof_work, &ctx->prof_hits, &ctx->em_table, &ctx->em_base_of_obj, &ctx->em_base, &ctx->tex_table, &ctx->srgb_lut};
   for (auto& b : ctx->tex_data) b.release();
   for (DevBuf* b : bufs) b->release();
@@ -832,9 +832,11 @@ int snkpt_build_tlas(SnkPt* ctx, void* stream) {
     CK(cudaEventSynchronize(ctx->ev_stage));
   }
   ctx->stage_in_flight = false;
+  // compact layout for THIS frame's instance count ni: records (64 B) | spheres (16 B) | valid slots (4 B), one transfer of 84 ni bytes
+  const size_t ni = ((size_t)ctx->num_instances + 3) & ~(size_t)3;
   SnkInstRec* recs = reinterpret_cast<SnkInstRec*>(ctx->h_stage);
-  uint32_t* valid = reinterpret_cast<uint32_t*>(recs + ctx->max_instances);
-  float* spheres = reinterpret_cast<float*>(valid + ctx->max_instances);  // 4 floats per instance slot
+  float* spheres = reinterpret_cast<float*>(recs + ni);  // 4 floats per instance slot
+  uint32_t* valid = reinterpret_cast<uint32_t*>(spheres + 4 * ni);
   static const bool cull_instances = !(getenv("SNKPT_NO_INSTANCE_CULL") && getenv("SNKPT_NO_INSTANCE_CULL")[0] == '1');
   uint32_t n = 0;
   float nm[9], det;
@@ -851,9 +853,14 @@ int snkpt_build_tlas(SnkPt* ctx, void* stream) {
     if (cull_instances && b < ctx->blas_sphere.size()) world_sphere(ctx->h_transforms.data() + 16 * (size_t)t, ctx->blas_sphere[b], spheres + 4 * (size_t)i);
     valid[n++] = i;
   }
-  CK(ctx->inst_recs.reserve(sizeof(SnkInstRec) * (size_t)(ctx->max_instances), false, st));
-  CK(ctx->inst_sphere.reserve(16 * (size_t)(ctx->max_instances), false, st));
-  CK(ctx->valid_slots.reserve(4 * (size_t)ctx->max_instances, false, st));
+  // device copy of the staging block, same layout; inst_recs / inst_sphere / valid_slots are views into it
+  CK(ctx->tlas_stage.reserve(need, false, st));
+  {
+    char* base = static_cast<char*>(ctx->tlas_stage.p);
+    ctx->inst_recs.alias(base, sizeof(SnkInstRec) * ni);
+    ctx->inst_sphere.alias(base + sizeof(SnkInstRec) * ni, 16 * ni);
+    ctx->valid_slots.alias(base + (sizeof(SnkInstRec) + 16) * ni, 4 * ni);
+  }
   CK(ctx->tlas_nodes.reserve(sizeof(SnkNode8) * (size_t)(ctx->max_instances + 1), false, st));
   CK(ctx->tlas_leaf_ids.reserve(4 * (size_t)(ctx->max_instances + 1), false, st));
   CK(scratch_reserve(ctx->scratch_tlas, ctx->max_instances));
@@ -861,9 +868,7 @@ int snkpt_build_tlas(SnkPt* ctx, void* stream) {
   ctx->tlas_built = true;
   if (n == 0) return SNKPT_OK;
   cudaEventRecord(ctx->ev[6], st);
-  CK(cudaMemcpyAsync(ctx->inst_recs.p, recs, sizeof(SnkInstRec) * (size_t)ctx->num_instances, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(ctx->inst_sphere.p, spheres, 16 * (size_t)ctx->num_instances, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(ctx->valid_slots.p, valid, 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(ctx->tlas_stage.p, ctx->h_stage, (sizeof(SnkInstRec) + 16 + 4) * ni, cudaMemcpyHostToDevice, st));
   CK(cudaEventRecord(ctx->ev_stage, st));
   ctx->stage_in_flight = true;
   BuildScratch& s = ctx->scratch_tlas;

@@ -59,8 +59,9 @@ __device__ __forceinline__ float ord2f(uint32_t u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
 }
 
-__global__ void k_init(uint32_t* counters, uint32_t* queue) {
-  const int t = threadIdx.x;
+__device__ __forceinline__ void init_counters(uint32_t* counters, uint32_t* queue, int t);
+__global__ void k_init(uint32_t* counters, uint32_t* queue) { init_counters(counters, queue, threadIdx.x); }
+__device__ __forceinline__ void init_counters(uint32_t* counters, uint32_t* queue, int t) {
   if (t < 16) {
     uint32_t v = 0;
     if (t == C_NODES) v = 1;
@@ -602,6 +603,7 @@ struct CollapseArgs {
   const uint32_t* indices;
   uint32_t index_offset, vertex_offset;
   int leaf_max;
+  int self_reset;  // single-CTA builds: leave counters / queue[0] as k_init would (the TLAS is rebuilt every frame: one launch less)
 };
 
 __device__ __forceinline__ float half_area(float4 lo, float4 hi) {
@@ -1052,6 +1054,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_build_small(const float4* __r
     end = s_end;
     __syncthreads();
   }
+  if (a.self_reset) init_counters(a.counters, a.queue, t);
 }
 
 // ---- the same single-CTA build with a better binary tree: PLOC (parallel locally-ordered clustering, Meister & Bittner 2018)
@@ -1238,6 +1241,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_build_small_ploc(const float4
     end = s_end;
     __syncthreads();
   }
+  if (a.self_reset) init_counters(a.counters, a.queue, t);
 }
 
 // ---- topology-preserving refit of a built BVH8 (animated vertices) -------------------------------------------
@@ -1466,13 +1470,15 @@ void refit_free(RefitState& r) { cudaFree(r.parent); cudaFree(r.arrive); cudaFre
 void launch_triangle_bounds(BuildScratch& s, const float* positions, const uint32_t* indices, uint32_t index_offset,
                             uint32_t vertex_offset, uint32_t n, cudaStream_t st) {
   k_init<<<1, 32, 0, st>>>(s.counters, s.queue);
+  s.clean = false;
   if (n) k_triangle_bounds<<<(n + 255) / 256, 256, 0, st>>>(positions, indices, index_offset, vertex_offset, n, s.prim_lo, s.prim_hi, s.counters);
 }
 
 void launch_instance_bounds(BuildScratch& s, const float* transforms_cm, const SnkInstanceData* inst,
                             const uint32_t* blas_of_instance, const SnkBlasInfo* blas, const SnkNode8* blas_nodes, const uint32_t* valid_slots,
                             uint32_t n, cudaStream_t st) {
-  k_init<<<1, 32, 0, st>>>(s.counters, s.queue);
+  if (!s.clean) k_init<<<1, 32, 0, st>>>(s.counters, s.queue);  // a single-CTA TLAS build leaves its scratch initialised
+  s.clean = false;
   if (n) k_instance_bounds<<<(n + 7) / 8, 256, 0, st>>>(transforms_cm, inst, blas_of_instance, blas, blas_nodes, valid_slots, n, s.prim_lo, s.prim_hi, s.counters);
 }
 
@@ -1507,6 +1513,8 @@ int launch_build(BuildScratch& s, uint32_t n, const BuildOutput& out, const floa
     a.node_capacity = cap; a.tris = out.tris; a.leaf_ids = out.leaf_ids; a.leaf_remap = out.leaf_remap; a.leaf_offset = out.leaf_offset;
     a.positions = positions; a.indices = indices; a.index_offset = index_offset; a.vertex_offset = vertex_offset;
     a.leaf_max = out.tris ? LEAF_MAX_BLAS : LEAF_MAX_TLAS;
+    a.self_reset = out.tris ? 0 : 1;
+    s.clean = a.self_reset != 0;
     uint32_t threads = 128;
     while (threads < n && threads < (uint32_t)SMALL_THREADS) threads <<= 1;
     // SNK_SMALL_PLOC: 0 = Karras hierarchy, 1 = locally-ordered clustering for every small build, 2 = for the TLAS only, 3 = for large TLASes
@@ -1557,6 +1565,7 @@ int launch_build(BuildScratch& s, uint32_t n, const BuildOutput& out, const floa
   a.node_capacity = cap; a.tris = out.tris; a.leaf_ids = out.leaf_ids; a.leaf_remap = out.leaf_remap; a.leaf_offset = out.leaf_offset;
   a.positions = positions; a.indices = indices; a.index_offset = index_offset; a.vertex_offset = vertex_offset;
     a.leaf_max = out.tris ? LEAF_MAX_BLAS : LEAF_MAX_TLAS;
+    a.self_reset = 0;
   {
     // resident grid of the cooperative launch, per device (a process may drive contexts on several GPUs, from several threads)
     static std::atomic<int> resident_of_device[64];

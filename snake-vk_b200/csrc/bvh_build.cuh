@@ -28,6 +28,7 @@ struct BuildScratch {
   uint32_t* counters = nullptr;                          // 16 words, see bvh_build.cu
   uint32_t* digit_total = nullptr;                       // 256 words: per-digit totals / bases of the current sort pass
   uint32_t hist_blocks = 0;
+  bool clean = false;                                    // counters / queue[0] are in their initial state (left so by a single-CTA TLAS build)
 };
 
 cudaError_t scratch_reserve(BuildScratch& s, uint32_t n);

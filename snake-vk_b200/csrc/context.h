@@ -20,8 +20,11 @@ namespace snk {
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
+  bool view = false;  // p points into another DevBuf's allocation (never freed or grown through this object)
+  void alias(void* q, size_t n) { if (!view) release(); p = q; bytes = n; view = true; }
   cudaError_t reserve(size_t need, bool keep, cudaStream_t st) {
     if (need <= bytes) return cudaSuccess;
+    if (view) return cudaErrorInvalidValue;
     size_t nb = bytes ? bytes : 4096;
     while (nb < need) nb += nb / 2 + 4096;
     void* q = nullptr;
@@ -35,7 +38,7 @@ struct DevBuf {
     p = q; bytes = nb;
     return e;
   }
-  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  void release() { if (p && !view) cudaFree(p); p = nullptr; bytes = 0; view = false; }
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
@@ -145,7 +148,8 @@ struct SnkPt {
   uint32_t num_emissive_tris = 0;
 
   // TLAS
-  snk::DevBuf tlas_nodes, tlas_leaf_ids, inst_recs, valid_slots;
+  snk::DevBuf tlas_nodes, tlas_leaf_ids, inst_recs, valid_slots;  // inst_recs, valid_slots, inst_sphere: views into tlas_stage
+  snk::DevBuf tlas_stage;  // instance records | valid slots | spheres, laid out like the pinned staging block: ONE upload per TLAS build
   snk::DevBuf inst_sphere;  // float4 per instance slot: world-space bounding sphere (xyz, r^2), r^2 < 0 = none (traverse.cuh)
   uint32_t tlas_prims = 0;
   bool tlas_built = false;
