@@ -63,6 +63,31 @@ inline NsSurf ns_surface(const Scene& sc, uint32_t inst, uint32_t prim, float u,
   return s;
 }
 
+// A point on an emissive triangle as a LIGHT SAMPLE (next-event estimation, ReSTIR candidates and stored samples): the triangle's
+// vertices and vertex normals are taken to world space first (mul_point / normal matrix per vertex) and interpolated there — what
+// the CUDA path reads from its per-frame emissive-triangle table (northstar.cuh: 96 bytes per triangle instead of the instance ->
+// indices -> vertices -> matrices -> material chain). Differs from ns_surface (interpolate, then transform) by rounding only.
+// Emitted radiance = the material albedo (RayGen.rgen:270); roughness / metallic of an emitter are not used by any caller.
+inline NsSurf ns_light_point(const Scene& sc, uint32_t inst, uint32_t prim, float u, float v) {
+  NsSurf s;
+  const float b0 = (1.0f - u) - v;
+  const InstanceData& in = sc.instances[inst];
+  uint32_t ia, ib, ic; sc.tri_indices(in, prim, ia, ib, ic);
+  const mat4& M = sc.transforms[in.transform_idx];
+  const vec3 wa = mul_point(M, sc.pos(ia)), wb = mul_point(M, sc.pos(ib)), wc = mul_point(M, sc.pos(ic));
+  const vec3 na = mul(sc.normal_matrix[in.transform_idx], sc.nrm(ia)), nb = mul(sc.normal_matrix[in.transform_idx], sc.nrm(ib)),
+             nc = mul(sc.normal_matrix[in.transform_idx], sc.nrm(ic));
+  s.p = (wa * b0 + wb * u) + wc * v;
+  s.n = normalize((na * b0 + nb * u) + nc * v);
+  const Material& m = sc.materials[in.material_idx];
+  s.albedo = v3(m.albedo[0], m.albedo[1], m.albedo[2]);
+  s.roughness = 0.0f; s.metallic = 0.0f;
+  s.flags = m.flags;
+  s.ntri = in.num_mesh_indices / 3u;
+  s.area = 0.5f * length(cross(wb - wa, wc - wa));
+  return s;
+}
+
 // f(wi, wo) * cos(theta_i): the Cook-Torrance terms of LightBuffers.glsl:126-144 without the light colour
 inline vec3 ns_bsdf_cos(vec3 n, vec3 wo, vec3 wi, vec3 albedo, float roughness, float metallic) {
   const vec3 f0 = mix(v3(0.04f), albedo, metallic);
@@ -193,7 +218,7 @@ inline vec3 ns_indirect(Frame& F, Invocation& inv, uint32_t x, uint32_t y) {
         const uint32_t tri = ns_pick(u2, ntri);
         float bu = u3, bv = u4;
         if (bu + bv >= 1.0f) { bu = 1.0f - bu; bv = 1.0f - bv; }
-        const NsSurf q = ns_surface(sc, obj, tri, bu, bv);
+        const NsSurf q = ns_light_point(sc, obj, tri, bu, bv);
         const vec3 d = q.p - o;
         const float dist = length(d);
         wi = d / dist;

@@ -148,7 +148,7 @@ inline void rs_initial_pixel(Frame& F, RsScratch& S, uint32_t x, uint32_t y) {
         const uint32_t tri = ns_pick(rs_rand(h0, d + 1u), ntri);
         float bu = rs_rand(h0, d + 2u), bv = rs_rand(h0, d + 3u);
         if (bu + bv >= 1.0f) { bu = 1.0f - bu; bv = 1.0f - bv; }
-        const NsSurf q = ns_surface(sc, obj, tri, bu, bv);
+        const NsSurf q = ns_light_point(sc, obj, tri, bu, bv);
         const RsEval e = rs_eval_em(s, q);
         const float p_hat = rs_phat(e);
         const float w = (p_hat * ((float)n_em * (float)ntri)) * q.area;
@@ -204,7 +204,7 @@ inline void rs_temporal_pixel(Frame& F, RsScratch& S, const mat4& prev_ivp, bool
         }
         r.pl_m += h.pl_m;
         if (rs_em_valid(sc, h.object_instance_idx, h.triangle_idx)) {
-          const NsSurf q = ns_surface(sc, h.object_instance_idx, h.triangle_idx, h.bary[0], h.bary[1]);
+          const NsSurf q = ns_light_point(sc, h.object_instance_idx, h.triangle_idx, h.bary[0], h.bary[1]);
           const float ph = rs_phat(rs_eval_em(s, q));
           const float w = (ph * h.w_em) * (float)h.m_em;
           r.w_sum_em += w;
@@ -280,7 +280,7 @@ inline uint32_t rs_spatial_pixel(Frame& F, RsScratch& S, uint32_t x, uint32_t y)
       }
       out.pl_m += c.pl_m;
       if (rs_em_valid(sc, c.object_instance_idx, c.triangle_idx)) {
-        const NsSurf q = ns_surface(sc, c.object_instance_idx, c.triangle_idx, c.bary[0], c.bary[1]);
+        const NsSurf q = ns_light_point(sc, c.object_instance_idx, c.triangle_idx, c.bary[0], c.bary[1]);
         const float ph = rs_phat(rs_eval_em(s, q));
         const float w = (ph * c.w_em) * (float)c.m_em;
         out.w_sum_em += w;
@@ -311,7 +311,7 @@ inline uint32_t rs_spatial_pixel(Frame& F, RsScratch& S, uint32_t x, uint32_t y)
       out.w_pl = (den > 0.0f && p_pl > 0.0f) ? (out.w_sum_pl * (num / den)) / p_pl : 0.0f;
     }
     if (src_em >= 0) {
-      const NsSurf q = ns_surface(sc, out.object_instance_idx, out.triangle_idx, out.bary[0], out.bary[1]);
+      const NsSurf q = ns_light_point(sc, out.object_instance_idx, out.triangle_idx, out.bary[0], out.bary[1]);
       float num = 0.0f, den = 0.0f;
       for (int j = 0; j < nc; ++j) {
         float ph = p_em;
@@ -344,7 +344,7 @@ inline uint32_t rs_spatial_pixel(Frame& F, RsScratch& S, uint32_t x, uint32_t y)
     }
   }
   if (restir && out.object_instance_idx != INVALID && out.w_em > 0.0f) {
-    const NsSurf q = ns_surface(sc, out.object_instance_idx, out.triangle_idx, out.bary[0], out.bary[1]);
+    const NsSurf q = ns_light_point(sc, out.object_instance_idx, out.triangle_idx, out.bary[0], out.bary[1]);
     const RsEval e = rs_eval_em(xs, q);
     if (e.tmax > 0.0f) {
       const vec3 c = e.C * out.w_em;

@@ -806,7 +806,7 @@ int snkpt_set_instances(SnkPt* ctx, const SnkInstanceData* instances, const uint
   }
   CK(ctx->em_base_of_obj.reserve(4 * (size_t)ctx->max_instances, false, ctx->stream));
   CK(ctx->em_base.reserve(4 * (size_t)ctx->max_instances, false, ctx->stream));
-  CK(ctx->em_table.reserve(192ull * (total ? total : 1), false, ctx->stream));
+  CK(ctx->em_table.reserve(96ull * (total ? total : 1), false, ctx->stream));  // EM_REC_F4 x 16 B per emissive triangle
   rc = upload_async(ctx, ctx->em_base_of_obj.p, base_of_obj.data(), 4 * (size_t)ctx->max_instances);
   if (!rc && num_emissive) rc = upload_async(ctx, ctx->em_base.p, base.data(), 4 * (size_t)num_emissive);
   if (rc) return rc;

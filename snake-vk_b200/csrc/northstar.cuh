@@ -52,44 +52,29 @@ static __device__ __noinline__ NsSurf ns_surface(const SceneDev& D, uint32_t ins
 }
 
 // ---- emissive-triangle table ------------------------------------------------------------------------------------
-// Light sampling evaluates ns_surface on 32 random emissive triangles per pixel; through the scene buffers that is ~60
+// Light sampling evaluates a point on 32 random emissive triangles per pixel; through the scene buffers that is ~60
 // dependent 4-byte gathers per candidate (instance record, 3 indices, 3 positions, 3 normals, mat4, normal matrix,
 // material) — ncu: 81 % excessive sectors, IPC 1.4 on C3 (profiles/r01t_prof_shade.txt). k_build_em_table (restir_ns.cu)
-// flattens everything ns_surface needs about one emissive triangle into ONE 192-byte record per frame; the lookup
-// below is 12 x 128-bit loads and evaluates the SAME expressions in the same order, so results are bit-identical.
-constexpr int EM_REC_F4 = 12;
-//  r0 pa.xyz area | r1 pb.xyz albedo.r | r2 pc.xyz albedo.g | r3 na.xyz albedo.b | r4 nb.xyz roughness | r5 nc.xyz metallic
-//  r6 M[0..2] flags | r7 M[4..6] ntri | r8 M[8..10] A[8] | r9 M[12..14] - | r10 A[0..2] A[6] | r11 A[3..5] A[7]
+// flattens everything a LIGHT SAMPLE needs about one emissive triangle into ONE record per frame. Round 1 kept the record in
+// object space (192 B: vertices, normals, mat4, normal matrix, material) and the lookup re-did the transforms; at 66 M candidates
+// per frame on C3 that is 12.7 GB of L2 -> L1 traffic, the stage ran at the L2's bandwidth. Now the record is in WORLD space
+// (oracle: ns_light_point — vertices and vertex normals transformed per vertex when the table is built, interpolated at the
+// lookup): 96 B = 6 x 128-bit loads, no matrix work per candidate.
+constexpr int EM_REC_F4 = 6;
+//  r0 wa.xyz area | r1 wb.xyz albedo.r | r2 wc.xyz albedo.g | r3 wna.xyz albedo.b | r4 wnb.xyz ntri | r5 wnc.xyz flags
 static __device__ __noinline__ NsSurf ns_surface_em(const SceneDev& D, uint32_t obj, uint32_t tri, float u, float v) {
   const uint32_t base = __ldg(D.em_base_of_obj + obj);  // callers make sure obj is in the emissive list (rs_em_valid)
   const float4* r = D.em_table + (size_t)EM_REC_F4 * (base + tri);
   NsSurf s;
   const float b0 = (1.0f - u) - v;
-  // position first, then the normal: keeps at most ~7 of the 12 record words live (the register count of every kernel
-  // that calls this function is the maximum over its call graph)
-  float a8;
-  {
-    const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2);
-    const vec3 p = (v3(r0.x, r0.y, r0.z) * b0 + v3(r1.x, r1.y, r1.z) * u) + v3(r2.x, r2.y, r2.z) * v;
-    s.area = r0.w;
-    s.albedo.x = r1.w; s.albedo.y = r2.w;
-    const float4 r6 = __ldg(r + 6), r7 = __ldg(r + 7), r8 = __ldg(r + 8), r9 = __ldg(r + 9);
-    s.p = v3(((r6.x * p.x + r7.x * p.y) + r8.x * p.z) + r9.x, ((r6.y * p.x + r7.y * p.y) + r8.y * p.z) + r9.y,
-             ((r6.z * p.x + r7.z * p.y) + r8.z * p.z) + r9.z);
-    s.flags = __float_as_uint(r6.w);
-    s.ntri = __float_as_uint(r7.w);
-    a8 = r8.w;
-  }
-  {
-    const float4 r3 = __ldg(r + 3), r4 = __ldg(r + 4), r5 = __ldg(r + 5);
-    const vec3 n = (v3(r3.x, r3.y, r3.z) * b0 + v3(r4.x, r4.y, r4.z) * u) + v3(r5.x, r5.y, r5.z) * v;
-    s.albedo.z = r3.w;
-    s.roughness = r4.w;
-    s.metallic = r5.w;
-    const float4 r10 = __ldg(r + 10), r11 = __ldg(r + 11);
-    s.n = normalize(v3((r10.x * n.x + r10.y * n.y) + r10.z * n.z, (r11.x * n.x + r11.y * n.y) + r11.z * n.z,
-                       (r10.w * n.x + r11.w * n.y) + a8 * n.z));
-  }
+  const float4 r0 = __ldg(r), r1 = __ldg(r + 1), r2 = __ldg(r + 2), r3 = __ldg(r + 3), r4 = __ldg(r + 4), r5 = __ldg(r + 5);
+  s.p = (v3(r0.x, r0.y, r0.z) * b0 + v3(r1.x, r1.y, r1.z) * u) + v3(r2.x, r2.y, r2.z) * v;
+  s.n = normalize((v3(r3.x, r3.y, r3.z) * b0 + v3(r4.x, r4.y, r4.z) * u) + v3(r5.x, r5.y, r5.z) * v);
+  s.area = r0.w;
+  s.albedo = v3(r1.w, r2.w, r3.w);
+  s.roughness = 0.0f; s.metallic = 0.0f;
+  s.ntri = __float_as_uint(r4.w);
+  s.flags = __float_as_uint(r5.w);
   return s;
 }
 

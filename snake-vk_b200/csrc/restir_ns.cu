@@ -133,28 +133,21 @@ __global__ void __launch_bounds__(128) k_build_em_table(SceneDev D, float4* __re
   const float* A = D.normal_mats + 9ull * in.transform_idx;
   const SnkMaterial* m = D.materials + in.material_idx;
   const float4 alb = __ldg(reinterpret_cast<const float4*>(m->albedo));
-  const float roughness = gmax(__ldg(&m->roughness), 0.05f), metallic = __ldg(&m->metallic);
   const uint32_t flags = __ldg(&m->flags);
   for (uint32_t tri = threadIdx.x; tri < ntri; tri += blockDim.x) {
     uint32_t ia, ib, ic;
     tri_indices(D, in, tri, ia, ib, ic);
-    const vec3 pa = ld3(D.positions, ia), pb = ld3(D.positions, ib), pc = ld3(D.positions, ic);
-    const vec3 na = ld3(D.normals, ia), nb = ld3(D.normals, ib), nc = ld3(D.normals, ic);
-    const vec3 wa = mul_point(M, pa), wb = mul_point(M, pb), wc = mul_point(M, pc);
-    const float area = 0.5f * length(cross(wb - wa, wc - wa));  // as ns_surface
+    // world-space vertices and vertex normals (oracle: ns_light_point)
+    const vec3 wa = mul_point(M, ld3(D.positions, ia)), wb = mul_point(M, ld3(D.positions, ib)), wc = mul_point(M, ld3(D.positions, ic));
+    const vec3 na = mul_mat3r(A, ld3(D.normals, ia)), nb = mul_mat3r(A, ld3(D.normals, ib)), nc = mul_mat3r(A, ld3(D.normals, ic));
+    const float area = 0.5f * length(cross(wb - wa, wc - wa));
     float4* r = table + (size_t)EM_REC_F4 * (base + tri);
-    r[0] = make_float4(pa.x, pa.y, pa.z, area);
-    r[1] = make_float4(pb.x, pb.y, pb.z, alb.x);
-    r[2] = make_float4(pc.x, pc.y, pc.z, alb.y);
+    r[0] = make_float4(wa.x, wa.y, wa.z, area);
+    r[1] = make_float4(wb.x, wb.y, wb.z, alb.x);
+    r[2] = make_float4(wc.x, wc.y, wc.z, alb.y);
     r[3] = make_float4(na.x, na.y, na.z, alb.z);
-    r[4] = make_float4(nb.x, nb.y, nb.z, roughness);
-    r[5] = make_float4(nc.x, nc.y, nc.z, metallic);
-    r[6] = make_float4(M[0], M[1], M[2], __uint_as_float(flags));
-    r[7] = make_float4(M[4], M[5], M[6], __uint_as_float(ntri));
-    r[8] = make_float4(M[8], M[9], M[10], A[8]);
-    r[9] = make_float4(M[12], M[13], M[14], 0.0f);
-    r[10] = make_float4(A[0], A[1], A[2], A[6]);
-    r[11] = make_float4(A[3], A[4], A[5], A[7]);
+    r[4] = make_float4(nb.x, nb.y, nb.z, __uint_as_float(ntri));
+    r[5] = make_float4(nc.x, nc.y, nc.z, __uint_as_float(flags));
   }
 }
 
