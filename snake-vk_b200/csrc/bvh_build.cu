@@ -10,6 +10,7 @@
 #include <cstdlib>
 
 #include <cfloat>
+#include <cstdio>
 
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
@@ -996,13 +997,42 @@ __global__ void __launch_bounds__(128, SNK_COLLAPSE_CTAS) k_collapse(CollapseArg
                           // with a 0.1 ms slower rebuild: adopted for TLASes of >= 1024 instances (3)
 #endif
 constexpr int SMALL_MAX = 4096, SMALL_THREADS = 1024;
+constexpr int SMALL_TREE_MAX = 1024;  // largest single-CTA build whose binary hierarchy lives in shared memory
+constexpr size_t SMALL_TREE_SMEM = (size_t)SMALL_TREE_MAX * (7 * 4 + 2 * 2 * 16);  // 7 int arrays (parent twice) + 2 x 2n float4 boxes = 92 KB
+#ifdef SNK_SMALL_TIMING  // phase stamps of the single-CTA builder (debug builds only)
+#define SNK_STAMP(k) if (threadIdx.x == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(snk_stamp[k])); }
+#define SNK_STAMP_PRINT() if (threadIdx.x == 0 && n > 100) printf("k_build_small n=%d: keys %llu sort %llu karras %llu boxes %llu collapse %llu ns\n", n, snk_stamp[1]-snk_stamp[0], snk_stamp[2]-snk_stamp[1], snk_stamp[3]-snk_stamp[2], snk_stamp[4]-snk_stamp[3], snk_stamp[5]-snk_stamp[4]);
+#else
+#define SNK_STAMP(k)
+#define SNK_STAMP_PRINT()
+#endif
 __global__ void __launch_bounds__(SMALL_THREADS) k_build_small(const float4* __restrict__ prim_lo, const float4* __restrict__ prim_hi, int n,
                                                                uint32_t* counters, unsigned long long* keys_g, uint32_t* vals_g, int* left,
                                                                int* right, int* parent, int* first, int* last, float4* bb_lo, float4* bb_hi,
-                                                               uint32_t* flags, CollapseArgs a) {
+                                                               uint32_t* flags, CollapseArgs a, int tree_in_smem) {
   __shared__ unsigned long long sk[SMALL_MAX];
   __shared__ uint32_t sv[SMALL_MAX];
+#ifdef SNK_SMALL_TIMING
+  unsigned long long snk_stamp[6];
+#endif
   const int t = threadIdx.x, NT = blockDim.x;  // launched with as many threads as there are elements to sort (128..1024)
+  SNK_STAMP(0);
+  // Builds of <= SMALL_TREE_MAX primitives (the per-frame TLAS of a few hundred instances) keep the whole binary hierarchy — child /
+  // range / parent indices, node boxes, the collapse's work queue — in dynamic shared memory: the collapse opens up to seven
+  // children per wide node one after the other, each step a dependent read of two nodes, and three levels of that through the
+  // L2 were 40 of the kernel's 63 us on C2's 205 instances (phase stamps, SNK_SMALL_TIMING). Generic pointers: the device
+  // functions below do not care which memory they walk.
+  extern __shared__ __align__(16) unsigned char small_dyn[];
+  float4 *const root_lo = bb_lo, *const root_hi = bb_hi;  // the host reads the root box of a BLAS from the global arrays
+  if (tree_in_smem) {
+    int* si = reinterpret_cast<int*>(small_dyn);
+    left = si; right = si + SMALL_TREE_MAX; first = si + 2 * SMALL_TREE_MAX; last = si + 3 * SMALL_TREE_MAX; parent = si + 4 * SMALL_TREE_MAX;  // 2 n entries
+    a.queue = reinterpret_cast<uint32_t*>(si + 6 * SMALL_TREE_MAX);
+    bb_lo = reinterpret_cast<float4*>(si + 7 * SMALL_TREE_MAX);
+    bb_hi = bb_lo + 2 * SMALL_TREE_MAX;
+    a.left = left; a.right = right; a.first = first; a.last = last; a.bb_lo = bb_lo; a.bb_hi = bb_hi;
+    if (t == 0) a.queue[0] = 0u;  // wide node 0 collapses the binary root (k_init does this for the global queue)
+  }
   int np2 = 1;
   while (np2 < n) np2 <<= 1;
   for (int i = t; i < np2; i += NT) {
@@ -1011,6 +1041,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_build_small(const float4* __r
   }
   for (int i = t; i < n; i += NT) flags[i] = 0u;
   __syncthreads();
+  SNK_STAMP(1);
   // bitonic sort by (key, index): the index breaks ties the way the stable radix sort of the general path does
   for (int k = 2; k <= np2; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
@@ -1027,6 +1058,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_build_small(const float4* __r
       __syncthreads();
     }
   }
+  SNK_STAMP(2);
   for (int i = t; i < n; i += NT) { keys_g[i] = sk[i]; vals_g[i] = sv[i]; }
   if (n > 1) {
     for (int i = t; i < n - 1; i += NT) karras_node(sk, n, i, left, right, parent, first, last);
@@ -1035,9 +1067,58 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_build_small(const float4* __r
   }
   __threadfence();
   __syncthreads();
-  for (int k = t; k < n; k += NT) refit_from_leaf(prim_lo, prim_hi, vals_g, n, k, left, right, parent, bb_lo, bb_hi, flags);
+  SNK_STAMP(3);
+  // Boxes of the binary nodes WITHOUT the bottom-up walk: every internal node covers a contiguous range [first, last] of the
+  // sorted leaves, so its box is the union over that range — whole 32-leaf chunks through a chunk box, the ragged ends leaf by
+  // leaf (<= 62 + n / 32 reads, all independent). The bottom-up refit of the multi-CTA path (refit_from_leaf: an L2 atomic, two
+  // fences and three dependent loads per level) was ~35 of this kernel's 63 us on the 205 instances of C2: the depth of the tree
+  // times the L2 latency. min / max are exact, so the boxes are the same bits.
+  float* chunk = reinterpret_cast<float*>(sk);  // the keys are dead: 6 floats per chunk of 32 sorted leaves (<= 128 chunks)
+  {
+    const int lane = t & 31, nchunks = (n + 31) >> 5;
+    for (int c = t >> 5; c < nchunks; c += NT >> 5) {
+      const int k = c * 32 + lane;
+      float4 lo = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, 0.f), hi = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, 0.f);
+      if (k < n) {
+        const uint32_t p = sv[k];
+        lo = prim_lo[p]; hi = prim_hi[p];
+        bb_lo[n - 1 + k] = lo; bb_hi[n - 1 + k] = hi;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        lo.x = fminf(lo.x, __shfl_xor_sync(0xffffffffu, lo.x, o)); lo.y = fminf(lo.y, __shfl_xor_sync(0xffffffffu, lo.y, o));
+        lo.z = fminf(lo.z, __shfl_xor_sync(0xffffffffu, lo.z, o));
+        hi.x = fmaxf(hi.x, __shfl_xor_sync(0xffffffffu, hi.x, o)); hi.y = fmaxf(hi.y, __shfl_xor_sync(0xffffffffu, hi.y, o));
+        hi.z = fmaxf(hi.z, __shfl_xor_sync(0xffffffffu, hi.z, o));
+      }
+      if (lane == 0) { float* cb = chunk + 6 * c; cb[0] = lo.x; cb[1] = lo.y; cb[2] = lo.z; cb[3] = hi.x; cb[4] = hi.y; cb[5] = hi.z; }
+    }
+  }
   __threadfence();
   __syncthreads();
+  for (int i = t; i < n - 1; i += NT) {
+    const int f = first[i], l = last[i];
+    float4 lo = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, 0.f), hi = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, 0.f);
+    int k = f;
+    while (k <= l) {
+      if ((k & 31) == 0 && k + 31 <= l) {
+        const float* cb = chunk + 6 * (k >> 5);
+        lo.x = fminf(lo.x, cb[0]); lo.y = fminf(lo.y, cb[1]); lo.z = fminf(lo.z, cb[2]);
+        hi.x = fmaxf(hi.x, cb[3]); hi.y = fmaxf(hi.y, cb[4]); hi.z = fmaxf(hi.z, cb[5]);
+        k += 32;
+      } else {
+        const float4 a0 = bb_lo[n - 1 + k], a1 = bb_hi[n - 1 + k];  // written by this CTA before the barrier; never cached before that
+        lo.x = fminf(lo.x, a0.x); lo.y = fminf(lo.y, a0.y); lo.z = fminf(lo.z, a0.z);
+        hi.x = fmaxf(hi.x, a1.x); hi.y = fmaxf(hi.y, a1.y); hi.z = fmaxf(hi.z, a1.z);
+        k += 1;
+      }
+    }
+    bb_lo[i] = lo; bb_hi[i] = hi;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tree_in_smem && t == 0) { root_lo[0] = bb_lo[0]; root_hi[0] = bb_hi[0]; }
+  SNK_STAMP(4);
   // collapse, level by level (queue[0] = binary root and counters[C_NODES] = 1 were set by k_init)
   volatile uint32_t& s_end = *reinterpret_cast<volatile uint32_t*>(&sk[0]);  // the keys are dead by now (static smem is at its 48 KB limit)
   uint32_t begin = 0, end = 1;
@@ -1054,7 +1135,9 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_build_small(const float4* __r
     end = s_end;
     __syncthreads();
   }
-  if (a.self_reset) init_counters(a.counters, a.queue, t);
+  SNK_STAMP(5);
+  SNK_STAMP_PRINT();
+  if (a.self_reset) init_counters(a.counters, tree_in_smem ? a.counters + 15 : a.queue, t);  // (queue[0] of the global queue was never touched: a spare counter word takes the store)
 }
 
 // ---- the same single-CTA build with a better binary tree: PLOC (parallel locally-ordered clustering, Meister & Bittner 2018)
@@ -1524,8 +1607,18 @@ int launch_build(BuildScratch& s, uint32_t n, const BuildOutput& out, const floa
       k_build_small_ploc<<<1, threads, 0, st>>>(s.prim_lo, s.prim_hi, (int)n, s.counters, s.vals[0], s.vals[1], s.left, s.right, s.parent, s.first, s.last,
                                                  s.bb_lo, s.bb_hi, s.flags, a);
     } else {
-      k_build_small<<<1, threads, 0, st>>>(s.prim_lo, s.prim_hi, (int)n, s.counters, s.keys[0], s.vals[0], s.left, s.right, s.parent, s.first,
-                                                s.last, s.bb_lo, s.bb_hi, s.flags, a);
+      const bool in_smem = n <= (uint32_t)SMALL_TREE_MAX;
+      if (in_smem) {
+        static bool configured[64] = {};  // the opt-in to > 48 KB of dynamic shared memory is per device
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !configured[dev]) {
+          cudaFuncSetAttribute(k_build_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMALL_TREE_SMEM);
+          if (dev >= 0 && dev < 64) configured[dev] = true;
+        }
+      }
+      k_build_small<<<1, threads, in_smem ? SMALL_TREE_SMEM : 0, st>>>(s.prim_lo, s.prim_hi, (int)n, s.counters, s.keys[0], s.vals[0], s.left, s.right, s.parent, s.first,
+                                                                       s.last, s.bb_lo, s.bb_hi, s.flags, a, in_smem ? 1 : 0);
     }
     return 1;
   }
