@@ -199,7 +199,7 @@ SceneDev SnkPt::scene_dev() const {
 // ---- per-pixel planes ----------------------------------------------------------------------
 static int alloc_pixels(SnkPt* ctx) {
   const size_t n = (size_t)ctx->W * ctx->H;
-  const size_t sizes[] = {4, 8, 4, 8, 4, 2, 8, 4, 4, 4, 4, 8, 16, 16, 16, 16, 16, 16, 16, 16, 16, 8, 8, 8, 4, 4};
+  const size_t sizes[] = {4, 8, 4, 8, 4, 2, 8, 4, 4, 4, 4, 8, 16, 16, 16, 16, 16, 16, 16, 16, 16, 8, 8, 8, 4, 4, 32};
   const int count = (int)(sizeof(sizes) / sizeof(sizes[0]));
   for (int i = 0; i < count; ++i) {
     ctx->px[i].release();
@@ -217,6 +217,7 @@ static int alloc_pixels(SnkPt* ctx) {
   P.out16 = ctx->px[21].as<ushort4>();
   P.taa_hist[0] = ctx->px[22].as<ushort4>(); P.taa_hist[1] = ctx->px[23].as<ushort4>();
   P.taa_prev_vel[0] = ctx->px[24].as<ushort2>(); P.taa_prev_vel[1] = ctx->px[25].as<ushort2>();
+  P.surf = ctx->px[26].as<uint4>();
   // depth planes clear to 1.0 (GBufferPass.cpp:79); prim ids to "sky"; reservoirs to empty
   std::vector<float> ones(n, 1.0f);
   CK(cudaMemcpyAsync(P.depth, ones.data(), 4 * n, cudaMemcpyHostToDevice, ctx->stream));

@@ -1182,7 +1182,12 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_build_small_ploc(const float4
                                                                     CollapseArgs a) {
   __shared__ unsigned long long sk[SMALL_MAX];
   __shared__ uint32_t sv[SMALL_MAX];
+#ifdef SNK_SMALL_TIMING
+  unsigned long long snk_stamp[6];
+  int snk_rounds = 0;
+#endif
   const int t = threadIdx.x, NT = blockDim.x;
+  SNK_STAMP(0);
   int np2 = 1;
   while (np2 < n) np2 <<= 1;
   for (int i = t; i < np2; i += NT) {
@@ -1205,6 +1210,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_build_small_ploc(const float4
       __syncthreads();
     }
   }
+  SNK_STAMP(1);
   // leaves: node n-1+i = sorted primitive i
   for (int i = t; i < n; i += NT) {
     const uint32_t prim = sv[i];
@@ -1226,7 +1232,11 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_build_small_ploc(const float4
     __syncthreads();
     int c = n, next = n - 2;
     auto node_size = [&](int node) { return node >= n - 1 ? 1 : last[node]; };
+    SNK_STAMP(2);
     while (c > 1) {
+#ifdef SNK_SMALL_TIMING
+      ++snk_rounds;
+#endif
       for (int i = t; i < c; i += NT) {
         const float4 lo = bb_lo[cl[i]], hi = bb_hi[cl[i]];
         const int j0 = i - SNK_PLOC_RADIUS < 0 ? 0 : i - SNK_PLOC_RADIUS, j1 = i + SNK_PLOC_RADIUS > c - 1 ? c - 1 : i + SNK_PLOC_RADIUS;
@@ -1275,6 +1285,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_build_small_ploc(const float4
       __threadfence_block();
       __syncthreads();
     }
+    SNK_STAMP(3);
     if (t == 0) parent[0] = -1;
     __syncthreads();
     // position of every leaf in a depth-first order: sum of the sizes of the left siblings on the way to the root
@@ -1309,6 +1320,7 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_build_small_ploc(const float4
   }
   __threadfence();
   __syncthreads();
+  SNK_STAMP(4);
   volatile uint32_t& s_end = *reinterpret_cast<volatile uint32_t*>(&sv[SMALL_MAX - 1]);
   uint32_t begin = 0, end = 1;
   while (begin < end) {
@@ -1324,6 +1336,10 @@ __global__ void __launch_bounds__(SMALL_THREADS) k_build_small_ploc(const float4
     end = s_end;
     __syncthreads();
   }
+  SNK_STAMP(5);
+#ifdef SNK_SMALL_TIMING
+  if (threadIdx.x == 0 && n > 100) printf("k_build_small_ploc n=%d: sort %llu leaves %llu ploc %llu (%d rounds) order %llu collapse %llu ns\n", n, snk_stamp[1]-snk_stamp[0], snk_stamp[2]-snk_stamp[1], snk_stamp[3]-snk_stamp[2], snk_rounds, snk_stamp[4]-snk_stamp[3], snk_stamp[5]-snk_stamp[4]);
+#endif
   if (a.self_reset) init_counters(a.counters, a.queue, t);
 }
 

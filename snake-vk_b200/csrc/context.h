@@ -74,6 +74,9 @@ struct PixelPlanes {
   ushort4* prev_normal; float* prev_depth;
   // aux
   uint32_t *prim, *inst; float* hit_t; float2* bary;
+  // packed surface record, 2 x uint4 per pixel: what a NEIGHBOUR's gather needs of the planes above in one 32-byte sector
+  // (shading.cuh: pack_surf / SurfRec) — written with the G-buffer, read by the spatial-reuse stage of the north-star ReSTIR
+  uint4* surf;
   // reservoirs: 2 halves x 3 planes of 16 B (SoA); half 0 = final, half 1 = temporal
   float4* res[2][3];
   // images

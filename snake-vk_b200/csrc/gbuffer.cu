@@ -37,6 +37,7 @@ __device__ __forceinline__ void write_gbuffer(const SceneDev& D, const FrameCons
     P.depth[px] = 1.0f;
     P.motion[px] = make_ushort2(0, 0);
     P.flags[px] = 0;
+    pack_surf(P.surf, px, make_ushort4(0, 0, 0, 0), 0u, h.t, 1.0f, make_char4(0, 0, 0, 0), make_ushort4(0, 0, 0, 0), false);
     return;
   }
   P.bary[px] = make_float2(h.u, h.v);
@@ -59,15 +60,21 @@ __device__ __forceinline__ void write_gbuffer(const SceneDev& D, const FrameCons
   const float4 clip = mul_vec4(fc.proj_view, world.x, world.y, world.z, 1.0f);
   const vec3 pworld = mul_point(D.prev_transforms + 16ull * in.transform_idx, p);
   const float4 pclip = mul_vec4(fc.prev_proj_view, pworld.x, pworld.y, pworld.z, 1.0f);
-  P.depth[px] = clip.z / clip.w;
+  const float depth = clip.z / clip.w;
+  P.depth[px] = depth;
   const float mx = (pclip.x / pclip.w - clip.x / clip.w) * 0.5f, my = (pclip.y / pclip.w - clip.y / clip.w) * 0.5f;
   P.motion[px] = make_ushort2(f2h(mx), f2h(my));
   const SnkMaterial* m = D.materials + in.material_idx;
   const vec3 alb = albedo_at(D, m, ia, ib, ic, b0, b1, b2);  // GBuffer.frag:56-58
-  P.albedo[px] = make_char4(f2snorm8(alb.x), f2snorm8(alb.y), f2snorm8(alb.z), 127);
-  P.normal[px] = make_ushort4(f2h(n.x), f2h(n.y), f2h(n.z), f2h(1.0f));
-  P.rma[px] = make_ushort4(f2h(m->roughness), f2h(m->metallic), f2h(m->ao), f2h(1.0f));
-  P.flags[px] = (uint16_t)m->flags;
+  const char4 alb8 = make_char4(f2snorm8(alb.x), f2snorm8(alb.y), f2snorm8(alb.z), 127);
+  const ushort4 n16 = make_ushort4(f2h(n.x), f2h(n.y), f2h(n.z), f2h(1.0f));
+  const ushort4 rma16 = make_ushort4(f2h(m->roughness), f2h(m->metallic), f2h(m->ao), f2h(1.0f));
+  const uint16_t mflags = (uint16_t)m->flags;
+  P.albedo[px] = alb8;
+  P.normal[px] = n16;
+  P.rma[px] = rma16;
+  P.flags[px] = mflags;
+  pack_surf(P.surf, px, n16, mflags, h.t, depth, alb8, rma16, true);
 }
 
 __global__ void __launch_bounds__(128, PRIMARY_CTAS_PER_SM) k_primary(TraceScene S, SceneDev D, FrameConsts fc, PixelPlanes P) {

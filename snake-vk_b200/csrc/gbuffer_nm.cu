@@ -24,8 +24,15 @@ __global__ void __launch_bounds__(256) k_gbuffer_normal_map(SceneDev D, FrameCon
   const float2 bc = P.bary[px];
   const float b0 = (1.0f - bc.x) - bc.y;
   vec3 nm;
-  if (mapped_normal(D, m, D.transforms + 16ull * in.transform_idx, ia, ib, ic, b0, bc.x, bc.y, nm))
-    P.normal[px] = make_ushort4(f2h(nm.x), f2h(nm.y), f2h(nm.z), f2h(1.0f));
+  if (mapped_normal(D, m, D.transforms + 16ull * in.transform_idx, ia, ib, ic, b0, bc.x, bc.y, nm)) {
+    const ushort4 n16 = make_ushort4(f2h(nm.x), f2h(nm.y), f2h(nm.z), f2h(1.0f));
+    P.normal[px] = n16;
+    // the packed surface record repeats the normal (shading.cuh: pack_surf)
+    uint4 a = P.surf[2 * px];
+    a.x = (uint32_t)n16.x | ((uint32_t)n16.y << 16);
+    a.y = (a.y & 0xFFFF0000u) | (uint32_t)n16.z;
+    P.surf[2 * px] = a;
+  }
 }
 
 }  // namespace

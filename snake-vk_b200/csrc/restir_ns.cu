@@ -75,6 +75,22 @@ __device__ __forceinline__ void rs_gsurf(const FrameConsts& fc, const PixelPlane
   if (dot(s.n, s.wo) < 0.0f) s.n = -s.n;
   s.o = pos + s.n * 0.01f;
 }
+// the same surface from a packed record (a neighbour's pixel: one sector instead of five planes)
+__device__ __forceinline__ void rs_gsurf_rec(const FrameConsts& fc, const SurfRec& r, uint32_t x, uint32_t y, RsSurf& s, vec3& pos, vec3& n_raw) {
+  n_raw = surf_normal(r);
+  const float u = ((float)x + 0.5f) / (float)fc.W, v = ((float)y + 0.5f) / (float)fc.H;
+  pos = world_pos_from_depth(fc.ivp, __uint_as_float(r.a.w), u, v);
+  char4 a;
+  memcpy(&a, &r.b.x, 4);
+  s.albedo = v3(snorm8_2f(a.x), snorm8_2f(a.y), snorm8_2f(a.z));
+  s.roughness = gmax(h2f((uint16_t)(r.b.y & 0xFFFFu)), 0.05f);
+  s.metallic = h2f((uint16_t)(r.b.y >> 16));
+  const vec3 cam = v3(fc.cam_pos[0], fc.cam_pos[1], fc.cam_pos[2]);
+  s.wo = normalize(cam - pos);
+  s.n = n_raw;
+  if (dot(s.n, s.wo) < 0.0f) s.n = -s.n;
+  s.o = pos + s.n * 0.01f;
+}
 __device__ __forceinline__ RsSurf rs_xsurf(const NsSurf& h, vec3 cam) {
   RsSurf s;
   s.albedo = h.albedo; s.roughness = h.roughness; s.metallic = h.metallic;
@@ -342,9 +358,10 @@ __device__ __forceinline__ void rs_spatial_thread(const SceneDev& D, const Frame
         const int qx = (int)x + ox, qy = (int)y + oy;
         if ((ox == 0 && oy == 0) || qx < 0 || qy < 0 || qx >= (int)fc.W || qy >= (int)fc.H) continue;
         const size_t qp = (size_t)qy * fc.W + qx;
-        if (!px_shaded(P, qp)) continue;
-        if (!(dot(px_normal(P.normal, qp), n_raw) >= rp.normal_threshold)) continue;
-        if (!(fabsf(P.hit_t[qp] - t_q) <= 0.1f * t_q)) continue;
+        const SurfRec q = load_surf(P.surf, qp);  // prim / flags / normal / hit distance of the neighbour in one sector
+        if (!surf_shaded(q)) continue;
+        if (!(dot(surf_normal(q), n_raw) >= rp.normal_threshold)) continue;
+        if (!(fabsf(__uint_as_float(q.a.z) - t_q) <= 0.1f * t_q)) continue;
         cpx[nc++] = (uint32_t)qx | ((uint32_t)qy << 16);
       }
       int src_pl = -1, src_em = -1;
@@ -382,7 +399,8 @@ __device__ __forceinline__ void rs_spatial_thread(const SceneDev& D, const Frame
           bool vis_pl = true, vis_em = true;
           if (j > 0) {
             RsSurf sj; vec3 pj, nj;
-            rs_gsurf(fc, P, cpx[j] & 0xFFFFu, cpx[j] >> 16, sj, pj, nj);
+            const uint32_t jx = cpx[j] & 0xFFFFu, jy = cpx[j] >> 16;
+            rs_gsurf_rec(fc, load_surf(P.surf, (size_t)jy * fc.W + jx), jx, jy, sj, pj, nj);
             if (src_pl >= 0) {
               const RsEval e = rs_eval_pl(sj, pl);
               ph_pl = rs_phat(e);
