@@ -21,6 +21,23 @@
 
 namespace snk {
 
+// SNK_NS_INLINE: the path-vertex stages inline the surface / BSDF / pdf helpers (a handful of call sites per kernel; results are
+// the same bits, -fmad=false). 0 keeps real calls (the round-1 rule against instruction-cache pressure).
+#ifndef SNK_NS_INLINE
+#define SNK_NS_INLINE 1
+#endif
+#if SNK_NS_INLINE
+#define NS_SURFACE ns_surface_inl
+#define NS_SURFACE_EM ns_surface_em_inl
+#define NS_BSDF_COS ns_bsdf_cos_inl
+#define NS_PDF ns_pdf_inl
+#else
+#define NS_SURFACE ns_surface
+#define NS_SURFACE_EM ns_surface_em
+#define NS_BSDF_COS ns_bsdf_cos
+#define NS_PDF ns_pdf
+#endif
+
 namespace {
 
 struct NsBuffers {
@@ -93,7 +110,7 @@ __device__ void ns_vertex_work(const SceneDev& D, const NsBuffers& B, size_t i, 
       const uint32_t tri = ns_pick(u2, ntri);
       float bu = u3, bv = u4;
       if (bu + bv >= 1.0f) { bu = 1.0f - bu; bv = 1.0f - bv; }
-      const NsSurf q = ns_surface_em(D, obj, tri, bu, bv);
+      const NsSurf q = NS_SURFACE_EM(D, obj, tri, bu, bv);
       const vec3 d = q.p - o;
       const float dist = length(d);
       wi = d / dist;
@@ -107,10 +124,10 @@ __device__ void ns_vertex_work(const SceneDev& D, const NsBuffers& B, size_t i, 
     }
     if (valid) {
       if (type == 2) {
-        const float p_bsdf = ns_pdf(n, wo, wi, s.roughness, s.metallic);
+        const float p_bsdf = NS_PDF(n, wo, wi, s.roughness, s.metallic);
         s0 = (s1 * s1) / (s1 * s1 + p_bsdf * p_bsdf);
       }
-      const vec3 tb = (T * ns_bsdf_cos(n, wo, wi, s.albedo, s.roughness, s.metallic)) * emitted;
+      const vec3 tb = (T * NS_BSDF_COS(n, wo, wi, s.albedo, s.roughness, s.metallic)) * emitted;
       if (type == 0) C = tb / p_type;
       else if (type == 1) C = (tb / s0) / s1;
       else C = (tb * s0) / s1;
@@ -136,11 +153,11 @@ __device__ void ns_vertex_work(const SceneDev& D, const NsBuffers& B, size_t i, 
   float pdf_b = 0.0f;
   if (alive) alive = ns_sample(n, wo, s.roughness, s.metallic, ns_rand(pixel, frame, dim), ns_rand(pixel, frame, dim + 1), ns_rand(pixel, frame, dim + 2), wi);
   if (alive) {
-    pdf_b = ns_pdf(n, wo, wi, s.roughness, s.metallic);
+    pdf_b = NS_PDF(n, wo, wi, s.roughness, s.metallic);
     alive = pdf_b > 0.0f;
   }
   if (alive) {
-    T = (T * ns_bsdf_cos(n, wo, wi, s.albedo, s.roughness, s.metallic)) / pdf_b;
+    T = (T * NS_BSDF_COS(n, wo, wi, s.albedo, s.roughness, s.metallic)) / pdf_b;
     alive = gmax(gmax(T.x, T.y), T.z) > 0.0f;
   }
   if (alive) put_ray(B.rays, i, o, 0.001f, wi, 1000.0f);
@@ -164,7 +181,7 @@ __global__ void __launch_bounds__(128, 8) k_ns_gen(SceneDev D, FrameConsts fc, P
     NsSurf s;
     if (alive) {
       const float2 bc = P.bary[px];
-      s = ns_surface(D, P.inst[px], P.prim[px], bc.x, bc.y);
+      s = NS_SURFACE(D, P.inst[px], P.prim[px], bc.x, bc.y);
       alive = !(s.flags & SNKPT_MAT_FLAG_EMISSIVE);
     }
     if (alive) {
@@ -242,7 +259,7 @@ __global__ void __launch_bounds__(128, 6) k_ns_vertex(SceneDev D, FrameConsts fc
     const vec3 wi = v3(r1.x, r1.y, r1.z);
     const float4 T4 = B.T[i];
     const vec3 T = v3(T4.x, T4.y, T4.z);
-    const NsSurf s = ns_surface(D, B.inst[i], __float_as_uint(h.w), h.y, h.z);
+    const NsSurf s = NS_SURFACE(D, B.inst[i], __float_as_uint(h.w), h.y, h.z);
     if (s.flags & SNKPT_MAT_FLAG_EMISSIVE) {
       if (b >= 1u + nee_from) {  // the ray left x_{b-1}, a vertex that also did next-event estimation
         const NsLightCounts lc = ns_light_counts(D);

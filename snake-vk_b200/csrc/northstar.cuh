@@ -22,7 +22,7 @@ struct NsSurf {
   float area;
 };
 
-static __device__ __noinline__ NsSurf ns_surface(const SceneDev& D, uint32_t inst, uint32_t prim, float u, float v) {
+__device__ __forceinline__ NsSurf ns_surface_inl(const SceneDev& D, uint32_t inst, uint32_t prim, float u, float v) {
   NsSurf s;
   const float b0 = (1.0f - u) - v;
   const SnkInstanceData in = load_instance(D, inst);
@@ -50,6 +50,7 @@ static __device__ __noinline__ NsSurf ns_surface(const SceneDev& D, uint32_t ins
   s.area = 0.5f * length(cross(wb - wa, wc - wa));
   return s;
 }
+static __device__ __noinline__ NsSurf ns_surface(const SceneDev& D, uint32_t inst, uint32_t prim, float u, float v) { return ns_surface_inl(D, inst, prim, u, v); }
 
 // ---- emissive-triangle table ------------------------------------------------------------------------------------
 // Light sampling evaluates a point on 32 random emissive triangles per pixel; through the scene buffers that is ~60
@@ -62,7 +63,7 @@ static __device__ __noinline__ NsSurf ns_surface(const SceneDev& D, uint32_t ins
 // lookup): 96 B = 6 x 128-bit loads, no matrix work per candidate.
 constexpr int EM_REC_F4 = 6;
 //  r0 wa.xyz area | r1 wb.xyz albedo.r | r2 wc.xyz albedo.g | r3 wna.xyz albedo.b | r4 wnb.xyz ntri | r5 wnc.xyz flags
-static __device__ __noinline__ NsSurf ns_surface_em(const SceneDev& D, uint32_t obj, uint32_t tri, float u, float v) {
+__device__ __forceinline__ NsSurf ns_surface_em_inl(const SceneDev& D, uint32_t obj, uint32_t tri, float u, float v) {
   const uint32_t base = __ldg(D.em_base_of_obj + obj);  // callers make sure obj is in the emissive list (rs_em_valid)
   const float4* r = D.em_table + (size_t)EM_REC_F4 * (base + tri);
   NsSurf s;
@@ -77,8 +78,10 @@ static __device__ __noinline__ NsSurf ns_surface_em(const SceneDev& D, uint32_t 
   s.flags = __float_as_uint(r5.w);
   return s;
 }
+// a real call for the kernels with many call sites (instruction-cache pressure, profiles/r01c); candidate loops use the _inl form
+static __device__ __noinline__ NsSurf ns_surface_em(const SceneDev& D, uint32_t obj, uint32_t tri, float u, float v) { return ns_surface_em_inl(D, obj, tri, u, v); }
 
-static __device__ __noinline__ vec3 ns_bsdf_cos(vec3 n, vec3 wo, vec3 wi, vec3 albedo, float roughness, float metallic) {
+__device__ __forceinline__ vec3 ns_bsdf_cos_inl(vec3 n, vec3 wo, vec3 wi, vec3 albedo, float roughness, float metallic) {
   const vec3 f0 = mix(v3(0.04f), albedo, metallic);
   const vec3 h = normalize(wo + wi);
   const vec3 f = fresnel_schlick(gmax(dot(h, wo), 0.0f), f0);
@@ -92,8 +95,11 @@ static __device__ __noinline__ vec3 ns_bsdf_cos(vec3 n, vec3 wo, vec3 wi, vec3 a
   const float n_dot_l = gmax(dot(n, wi), 0.0f);
   return ((kd * albedo) * (1.0f / PI_GLSL) + specular) * n_dot_l;
 }
+static __device__ __noinline__ vec3 ns_bsdf_cos(vec3 n, vec3 wo, vec3 wi, vec3 albedo, float roughness, float metallic) {
+  return ns_bsdf_cos_inl(n, wo, wi, albedo, roughness, metallic);
+}
 __device__ __forceinline__ float ns_spec_prob(float metallic) { return 0.25f + 0.5f * metallic; }
-static __device__ __noinline__ float ns_pdf(vec3 n, vec3 wo, vec3 wi, float roughness, float metallic) {
+__device__ __forceinline__ float ns_pdf_inl(vec3 n, vec3 wo, vec3 wi, float roughness, float metallic) {
   const float ps = ns_spec_prob(metallic);
   const float n_dot_l = gmax(dot(n, wi), 0.0f);
   const vec3 h = normalize(wo + wi);
@@ -102,6 +108,7 @@ static __device__ __noinline__ float ns_pdf(vec3 n, vec3 wo, vec3 wi, float roug
   const float d = distribution_ggx(h, n, roughness);
   return (1.0f - ps) * (n_dot_l / PI_GLSL) + ps * ((d * n_dot_h) / (4.0f * v_dot_h));
 }
+static __device__ __noinline__ float ns_pdf(vec3 n, vec3 wo, vec3 wi, float roughness, float metallic) { return ns_pdf_inl(n, wo, wi, roughness, metallic); }
 __device__ __forceinline__ bool ns_sample(vec3 n, vec3 wo, float roughness, float metallic, float u0, float u1, float u2, vec3& wi) {
   vec3 nt, nb;
   create_coordinate_system(n, nt, nb);

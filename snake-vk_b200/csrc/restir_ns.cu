@@ -100,7 +100,10 @@ __device__ __forceinline__ RsSurf rs_xsurf(const NsSurf& h, vec3 cam) {
   s.o = h.p + s.n * 0.01f;
   return s;
 }
-static __device__ __noinline__ RsEval rs_eval_pl(const RsSurf& s, const PointLightRec& pl) {
+// `INL`: the candidate loops of k_rs_initial inline the evaluation (SNK_RS_INLINE_EVAL; 16-32 calls per pixel, arguments and result
+// through local memory otherwise); the reuse stages keep real calls (many call sites: instruction-cache pressure, r01c)
+template <bool INL>
+__device__ __forceinline__ RsEval rs_eval_pl_body(const RsSurf& s, const PointLightRec& pl) {
   RsEval e; e.C = v3(0.0f); e.wi = v3(0.0f, 1.0f, 0.0f); e.tmax = -1.0f;
   const vec3 d = pl.pos - s.o;
   const float dist = length(d);
@@ -108,11 +111,12 @@ static __device__ __noinline__ RsEval rs_eval_pl(const RsSurf& s, const PointLig
   const vec3 wi = inv_scale(d, dist);
   if (!(dot(s.n, wi) > 0.0f)) return e;
   const float atten = (pl.atten_constant + pl.atten_linear * dist) + pl.atten_exp * (dist * dist);
-  e.C = inv_scale(ns_bsdf_cos(s.n, s.wo, wi, s.albedo, s.roughness, s.metallic) * pl.colour, atten);
+  e.C = inv_scale((INL ? ns_bsdf_cos_inl(s.n, s.wo, wi, s.albedo, s.roughness, s.metallic) : ns_bsdf_cos(s.n, s.wo, wi, s.albedo, s.roughness, s.metallic)) * pl.colour, atten);
   e.wi = wi; e.tmax = dist - 0.001f;
   return e;
 }
-static __device__ __noinline__ RsEval rs_eval_em(const RsSurf& s, const NsSurf& q) {
+template <bool INL>
+__device__ __forceinline__ RsEval rs_eval_em_body(const RsSurf& s, const NsSurf& q) {
   RsEval e; e.C = v3(0.0f); e.wi = v3(0.0f, 1.0f, 0.0f); e.tmax = -1.0f;
   const vec3 d = q.p - s.o;
   const float dist = length(d);
@@ -120,9 +124,45 @@ static __device__ __noinline__ RsEval rs_eval_em(const RsSurf& s, const NsSurf& 
   const vec3 wi = inv_scale(d, dist);
   const float cos_l = fabsf(dot(q.n, wi));
   if (!(dot(s.n, wi) > 0.0f) || !(cos_l > 0.000001f)) return e;
-  e.C = inv_scale((ns_bsdf_cos(s.n, s.wo, wi, s.albedo, s.roughness, s.metallic) * q.albedo) * cos_l, dist * dist);
+  e.C = inv_scale(((INL ? ns_bsdf_cos_inl(s.n, s.wo, wi, s.albedo, s.roughness, s.metallic) : ns_bsdf_cos(s.n, s.wo, wi, s.albedo, s.roughness, s.metallic)) * q.albedo) * cos_l, dist * dist);
   e.wi = wi; e.tmax = dist - 0.005f;
   return e;
+}
+static __device__ __noinline__ RsEval rs_eval_pl(const RsSurf& s, const PointLightRec& pl) { return rs_eval_pl_body<false>(s, pl); }
+static __device__ __noinline__ RsEval rs_eval_em(const RsSurf& s, const NsSurf& q) { return rs_eval_em_body<false>(s, q); }
+#ifndef SNK_RS_INLINE_EVAL
+#define SNK_RS_INLINE_EVAL 1
+#endif
+__device__ __forceinline__ RsEval rs_eval_pl_initial(const RsSurf& s, const PointLightRec& pl) {
+#if SNK_RS_INLINE_EVAL
+  return rs_eval_pl_body<true>(s, pl);
+#else
+  return rs_eval_pl(s, pl);
+#endif
+}
+#ifndef SNK_RS_INLINE_REUSE
+#define SNK_RS_INLINE_REUSE 1  // r06k: rs_spatial 0.384 -> 0.306 ms (C2), 0.672 -> 0.515 ms (C3)
+#endif
+__device__ __forceinline__ RsEval rs_eval_pl_reuse(const RsSurf& s, const PointLightRec& pl) {
+#if SNK_RS_INLINE_REUSE
+  return rs_eval_pl_body<true>(s, pl);
+#else
+  return rs_eval_pl(s, pl);
+#endif
+}
+__device__ __forceinline__ RsEval rs_eval_em_reuse(const RsSurf& s, const NsSurf& q) {
+#if SNK_RS_INLINE_REUSE
+  return rs_eval_em_body<true>(s, q);
+#else
+  return rs_eval_em(s, q);
+#endif
+}
+__device__ __forceinline__ RsEval rs_eval_em_initial(const RsSurf& s, const NsSurf& q) {
+#if SNK_RS_INLINE_EVAL
+  return rs_eval_em_body<true>(s, q);
+#else
+  return rs_eval_em(s, q);
+#endif
 }
 // a stored emissive sample is usable when its instance is (still) in the emissive list — snkpt_set_instances drops the
 // reservoir history when that list changes — and the triangle exists
@@ -191,7 +231,7 @@ __global__ void __launch_bounds__(128, 6) k_rs_initial(SceneDev D, FrameConsts f
         RsEval e_sel; e_sel.C = v3(0.0f); e_sel.wi = v3(0.0f, 1.0f, 0.0f); e_sel.tmax = -1.0f;
         for (uint32_t c = 0; c < m; ++c) {
           const uint32_t idx = all ? c : ns_pick(rs_rand(h0, RS_DIM_INITIAL + 2u * c), n_pl);
-          const RsEval e = rs_eval_pl(s, load_pointlight(D.lights, idx));
+          const RsEval e = rs_eval_pl_initial(s, load_pointlight(D.lights, idx));
           const float p_hat = rs_phat(e);
           const float w = p_hat * (float)n_pl;
           r.w_sum_pl += w;
@@ -214,8 +254,8 @@ __global__ void __launch_bounds__(128, 6) k_rs_initial(SceneDev D, FrameConsts f
           const uint32_t tri = ns_pick(rs_rand(h0, d + 1u), ntri);
           float bu = rs_rand(h0, d + 2u), bv = rs_rand(h0, d + 3u);
           if (bu + bv >= 1.0f) { bu = 1.0f - bu; bv = 1.0f - bv; }
-          const NsSurf q = ns_surface_em(D, obj, tri, bu, bv);
-          const RsEval e = rs_eval_em(s, q);
+          const NsSurf q = SNK_RS_INLINE_EVAL ? ns_surface_em_inl(D, obj, tri, bu, bv) : ns_surface_em(D, obj, tri, bu, bv);
+          const RsEval e = rs_eval_em_initial(s, q);
           const float p_hat = rs_phat(e);
           const float w = (p_hat * ((float)n_em * (float)ntri)) * q.area;
           r.w_sum_em += w;
@@ -276,7 +316,7 @@ __global__ void __launch_bounds__(128, 8) k_rs_temporal(SceneDev D, FrameConsts 
         if (h.pl_m > rp.m_cap * r.pl_m) h.pl_m = rp.m_cap * r.pl_m;
         if (h.m_em > rp.m_cap * r.m_em) h.m_em = rp.m_cap * r.m_em;
         if (h.pl_idx < n_pl) {
-          const float ph = rs_phat(rs_eval_pl(s, load_pointlight(D.lights, h.pl_idx)));
+          const float ph = rs_phat(rs_eval_pl_reuse(s, load_pointlight(D.lights, h.pl_idx)));
           const float w = (ph * h.w_pl) * (float)h.pl_m;
           r.w_sum_pl += w;
           if (w > 0.0f && rs_rand(h0, RS_DIM_TEMPORAL) * r.w_sum_pl < w) { r.pl_idx = h.pl_idx; p_pl = ph; }
@@ -284,7 +324,7 @@ __global__ void __launch_bounds__(128, 8) k_rs_temporal(SceneDev D, FrameConsts 
         r.pl_m += h.pl_m;
         if (rs_em_valid(D, h.obj, h.tri)) {
           const NsSurf q = ns_surface_em(D, h.obj, h.tri, h.bx, h.by);
-          const float ph = rs_phat(rs_eval_em(s, q));
+          const float ph = rs_phat(rs_eval_em_reuse(s, q));
           const float w = (ph * h.w_em) * (float)h.m_em;
           r.w_sum_em += w;
           if (w > 0.0f && rs_rand(h0, RS_DIM_TEMPORAL + 1u) * r.w_sum_em < w) { r.obj = h.obj; r.tri = h.tri; r.bx = h.bx; r.by = h.by; p_em = ph; }
@@ -371,7 +411,7 @@ __device__ __forceinline__ void rs_spatial_thread(const SceneDev& D, const Frame
         const Reservoir c = load_reservoir(half1, (size_t)(cpx[j] >> 16) * fc.W + (cpx[j] & 0xFFFFu));
         m_pl[j] = c.pl_m; m_em[j] = c.m_em;
         if (c.pl_idx < n_pl) {
-          const float ph = rs_phat(rs_eval_pl(s, load_pointlight(D.lights, c.pl_idx)));
+          const float ph = rs_phat(rs_eval_pl_reuse(s, load_pointlight(D.lights, c.pl_idx)));
           const float w = (ph * c.w_pl) * (float)c.pl_m;
           out.w_sum_pl += w;
           if (w > 0.0f && rs_rand(h0, RS_DIM_SPATIAL + 0x100u + 2u * (uint32_t)j) * out.w_sum_pl < w) { out.pl_idx = c.pl_idx; p_pl = ph; src_pl = j; }
@@ -379,7 +419,7 @@ __device__ __forceinline__ void rs_spatial_thread(const SceneDev& D, const Frame
         out.pl_m += c.pl_m;
         if (rs_em_valid(D, c.obj, c.tri)) {
           const NsSurf q = ns_surface_em(D, c.obj, c.tri, c.bx, c.by);
-          const float ph = rs_phat(rs_eval_em(s, q));
+          const float ph = rs_phat(rs_eval_em_reuse(s, q));
           const float w = (ph * c.w_em) * (float)c.m_em;
           out.w_sum_em += w;
           if (w > 0.0f && rs_rand(h0, RS_DIM_SPATIAL + 0x100u + 2u * (uint32_t)j + 1u) * out.w_sum_em < w) {
@@ -402,12 +442,12 @@ __device__ __forceinline__ void rs_spatial_thread(const SceneDev& D, const Frame
             const uint32_t jx = cpx[j] & 0xFFFFu, jy = cpx[j] >> 16;
             rs_gsurf_rec(fc, load_surf(P.surf, (size_t)jy * fc.W + jx), jx, jy, sj, pj, nj);
             if (src_pl >= 0) {
-              const RsEval e = rs_eval_pl(sj, pl);
+              const RsEval e = rs_eval_pl_reuse(sj, pl);
               ph_pl = rs_phat(e);
               if (UNBIASED && ph_pl > 0.0f) { vis_pl = T.visible(sj.o, e); ++n_mis; }
             }
             if (src_em >= 0) {
-              const RsEval e = rs_eval_em(sj, q);
+              const RsEval e = rs_eval_em_reuse(sj, q);
               ph_em = rs_phat(e);
               if (UNBIASED && ph_em > 0.0f) { vis_em = T.visible(sj.o, e); ++n_mis; }
             }
@@ -474,7 +514,7 @@ __global__ void __launch_bounds__(128, SNK_RS_FINAL_CTAS) k_rs_final(SceneDev D,
       const vec3 cam = v3(fc.cam_pos[0], fc.cam_pos[1], fc.cam_pos[2]);
       const RsSurf xs = rs_xsurf(hs, cam);
       if (out.pl_idx != INVALID_IDX && out.w_pl > 0.0f) {
-        const RsEval e = rs_eval_pl(xs, load_pointlight(D.lights, out.pl_idx));
+        const RsEval e = rs_eval_pl_reuse(xs, load_pointlight(D.lights, out.pl_idx));
         if (e.tmax > 0.0f) {
           C0 = e.C * out.w_pl;
           put_ray(B.rays, px, xs.o, 0.001f, e.wi, e.tmax);
@@ -483,7 +523,7 @@ __global__ void __launch_bounds__(128, SNK_RS_FINAL_CTAS) k_rs_final(SceneDev D,
       }
       if (out.obj != INVALID_IDX && out.w_em > 0.0f) {
         const NsSurf q = ns_surface_em(D, out.obj, out.tri, out.bx, out.by);
-        const RsEval e = rs_eval_em(xs, q);
+        const RsEval e = rs_eval_em_reuse(xs, q);
         if (e.tmax > 0.0f) {
           C1 = e.C * out.w_em;
           put_ray(B.rays, np + px, xs.o, 0.001f, e.wi, e.tmax);
