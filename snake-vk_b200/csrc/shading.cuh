@@ -63,7 +63,15 @@ __device__ __forceinline__ float geometry_smith(vec3 v, vec3 l, vec3 n, float ro
   const float ggx1 = geometry_schlick_ggx(n_dot_l, roughness);
   return ggx2 * ggx1;
 }
-static __device__ __noinline__ vec3 cook_torrance_brdf(vec3 light_pos, vec3 surface_pos, vec3 v, vec3 f0, vec3 n, float roughness, float metallic) {
+#ifndef SNK_REF_INLINE
+#define SNK_REF_INLINE 0  // 1: the reference-mode shading helpers are inlined (A/B: profiles/r06n)
+#endif
+#if SNK_REF_INLINE
+#define SNK_REF_FN __device__ __forceinline__
+#else
+#define SNK_REF_FN static __device__ __noinline__
+#endif
+SNK_REF_FN vec3 cook_torrance_brdf(vec3 light_pos, vec3 surface_pos, vec3 v, vec3 f0, vec3 n, float roughness, float metallic) {
   const vec3 frag_to_light = light_pos - surface_pos;
   const vec3 l = normalize(frag_to_light);
   const vec3 h = normalize(v + l);
@@ -78,7 +86,7 @@ static __device__ __noinline__ vec3 cook_torrance_brdf(vec3 light_pos, vec3 surf
   kd *= 1.0f - metallic;
   return (kd / PI_GLSL + specular) * n_dot_l;
 }
-static __device__ __noinline__ vec3 calc_directional_light(vec3 ldir, vec3 lcol, vec3 v, vec3 f0, vec3 n, float roughness, float metallic, vec3 albedo) {
+SNK_REF_FN vec3 calc_directional_light(vec3 ldir, vec3 lcol, vec3 v, vec3 f0, vec3 n, float roughness, float metallic, vec3 albedo) {
   const vec3 l = ldir;
   const vec3 h = normalize(v + l);
   const vec3 f = fresnel_schlick(gmax(dot(h, v), 0.0f), f0);
@@ -207,7 +215,7 @@ static __device__ __noinline__ bool mapped_normal(const SceneDev& D, const SnkMa
 // point on an emissive triangle: shared head of RayGen.rgen:241-251 and :258-268.
 // bary = (bx, by, 1-bx-by) weights of (ti.x, ti.y, ti.z) — NOT the hit-attribute convention.
 struct TriPoint { vec3 p, n, emissive; };
-static __device__ __noinline__ TriPoint triangle_point(const SceneDev& D, uint32_t obj, uint32_t tri, float bx, float by) {
+SNK_REF_FN TriPoint triangle_point(const SceneDev& D, uint32_t obj, uint32_t tri, float bx, float by) {
   const SnkInstanceData in = load_instance(D, obj);
   uint32_t ia, ib, ic;
   tri_indices(D, in, tri, ia, ib, ic);
