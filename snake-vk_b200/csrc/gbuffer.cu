@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(128, SNK_PACKET_CTAS) k_primary_packet(TraceSc
                                                                          uint32_t* next_ticket) {
   __shared__ uint32_t sm_stack[4 * PK_STACK];
   const uint32_t w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  uint32_t* stk = sm_stack + w * PK_STACK;
+  const PkStack stk{sm_stack + w * PK_STACK, reinterpret_cast<uint32_t*>(S.spill + ((size_t)blockIdx.x * 4 + w) * (SPILL_STACK * 32))};
   // the warps are independent: each draws its 8x4 tiles from a ticket (four consecutive tickets = one 16x8 block, so
   // neighbouring warps work on neighbouring pixels); tiles of sky and of dense geometry differ 10x in cost
   const uint32_t tiles_x = (fc.W + 15u) / 16u, n_tiles = 4u * tiles_x * ((fc.row1 - fc.row0 + 7u) / 8u);

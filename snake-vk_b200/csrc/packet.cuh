@@ -20,7 +20,14 @@ namespace snk {
 // one-ray traversal (tri_test, the same instance transform), so the hits — closest t, lowest (instance, primitive) at equal t —
 // are the ones the one-ray kernel and the brute-force oracle find: the plane and distance tests only have to be conservative
 // (relative + absolute slack below), the set of triangles a ray sees only grows.
-constexpr int PK_STACK = 128;               // shared stack entries per warp (u32)
+constexpr int PK_STACK = 128;               // shared stack entries per warp (u32); deeper entries go to the warp's global spill area
+constexpr int PK_SPILL = SPILL_STACK * 32 * 2;  // u32 entries of the per-warp spill region of traverse.cuh (TraceScene::spill)
+// the warp's stack: entry i < PK_STACK in shared memory, the rest (degenerate, chain-like hierarchies) in global memory
+struct PkStack {
+  uint32_t* sm;
+  uint32_t* gl;
+  __device__ __forceinline__ uint32_t& at(int i) const { return i < PK_STACK ? sm[i] : gl[i - PK_STACK]; }
+};
 constexpr uint32_t PK_INST = 0x80000000u;   // stack entry = a TLAS leaf record (instance) instead of a node
 
 struct PkSpace {
@@ -107,15 +114,15 @@ __device__ __forceinline__ void pk_node(const uint4* __restrict__ nodes, uint32_
 
 // parallel push of the surviving inner children: position 7 is visited first (trav_step_impl opens the highest bit first), so
 // position p lands at stack offset rank(p) counted from below
-__device__ __forceinline__ void pk_push_inner(uint32_t* stk, int& sp, uint32_t inner, uint32_t my_child, uint32_t lane, uint32_t* overflow) {
+__device__ __forceinline__ void pk_push_inner(const PkStack& stk, int& sp, uint32_t inner, uint32_t my_child, uint32_t lane, uint32_t* overflow) {
   const int n = __popc(inner);
-  if (sp + n > PK_STACK) { if (lane == 0) atomicAdd(overflow, 1u); return; }
-  if (lane < 8u && ((inner >> lane) & 1u)) stk[sp + __popc(inner & ~(0xFFFFFFFFu << lane))] = my_child;
+  if (sp + n > PK_STACK + PK_SPILL) { if (lane == 0) atomicAdd(overflow, 1u); return; }
+  if (lane < 8u && ((inner >> lane) & 1u)) stk.at(sp + __popc(inner & ~(0xFFFFFFFFu << lane))) = my_child;
   sp += n;
 }
 
 __device__ __forceinline__ void pk_trace(const TraceScene& S, float ox, float oy, float oz, float dx, float dy, float dz, float tmin, float tmax,
-                                         uint32_t* stk, uint32_t lane, HitRec& best) {
+                                         const PkStack& stk, uint32_t lane, HitRec& best) {
   best.t = -1.0f; best.u = 0.f; best.v = 0.f; best.prim = 0xFFFFFFFFu; best.inst = 0xFFFFFFFFu;
   float tcur = tmax;
   if (S.tlas_node_count == 0u) return;
@@ -125,10 +132,10 @@ __device__ __forceinline__ void pk_trace(const TraceScene& S, float ox, float oy
   float far2 = pk_warp_max(tcur > tmin ? (tcur * tcur) * ddw : 0.0f);
   if (!(far2 > 0.0f)) return;
   int sp = 0;
-  stk[sp++] = 0u;  // TLAS root (every lane writes the same word)
+  stk.at(sp++) = 0u;  // TLAS root (every lane writes the same word)
   __syncwarp();
   while (sp > 0) {
-    const uint32_t e = stk[--sp];
+    const uint32_t e = stk.at(--sp);
     __syncwarp();  // everybody has read the entry before anybody overwrites the slot
     if (!(e & PK_INST)) {
       uint32_t inner, leaf, rec_base, my_child;
@@ -136,9 +143,9 @@ __device__ __forceinline__ void pk_trace(const TraceScene& S, float ox, float oy
       pk_push_inner(stk, sp, inner, my_child, lane, S.overflow);
       // the instances of this node's leaf slots go on top: they are entered before the inner children are opened
       const int nl = __popc(leaf);
-      if (sp + nl > PK_STACK) { if (lane == 0) atomicAdd(S.overflow, 1u); }
+      if (sp + nl > PK_STACK + PK_SPILL) { if (lane == 0) atomicAdd(S.overflow, 1u); }
       else {
-        if (lane < 24u && ((leaf >> lane) & 1u)) stk[sp + __popc(leaf & ~(0xFFFFFFFFu << lane))] = PK_INST | (rec_base + lane);
+        if (lane < 24u && ((leaf >> lane) & 1u)) stk.at(sp + __popc(leaf & ~(0xFFFFFFFFu << lane))) = PK_INST | (rec_base + lane);
         sp += nl;
       }
       __syncwarp();
@@ -168,10 +175,10 @@ __device__ __forceinline__ void pk_trace(const TraceScene& S, float ox, float oy
     const uint32_t cur_inst = meta.y;
     const int base = sp;
     bool took_any = false;
-    stk[sp++] = meta.x;
+    stk.at(sp++) = meta.x;
     __syncwarp();
     while (sp > base) {
-      const uint32_t node = stk[--sp];
+      const uint32_t node = stk.at(--sp);
       __syncwarp();
       uint32_t inner, leaf, rec_base, my_child;
       pk_node(S.blas_nodes, node, B, far2o, lane, inner, leaf, rec_base, my_child);
@@ -268,26 +275,26 @@ __device__ __forceinline__ void pk_node_ortho(const uint4* __restrict__ nodes, u
 // any-hit for a packet of parallel rays; returns true when this lane's ray (tmin < t < tmax) hits something. Lanes without a
 // ray pass tmax <= tmin. Every lane of the warp must call it.
 __device__ __forceinline__ bool pk_trace_parallel_any(const TraceScene& S, float ox, float oy, float oz, float tmin, float dx, float dy, float dz, float tmax,
-                                                      uint32_t* stk, uint32_t lane) {
+                                                      const PkStack& stk, uint32_t lane) {
   bool want = tmax > tmin && S.tlas_node_count != 0u;  // still looking for a hit
   if (!__any_sync(PK_FULL, want)) return false;
   bool hit = false;
   PkOrtho W;
   pk_setup_ortho(W, want, ox, oy, oz, dx, dy, dz, lane);
   int sp = 0;
-  stk[sp++] = 0u;
+  stk.at(sp++) = 0u;
   __syncwarp();
   while (sp > 0) {
-    const uint32_t e = stk[--sp];
+    const uint32_t e = stk.at(--sp);
     __syncwarp();
     if (!(e & PK_INST)) {
       uint32_t inner, leaf, rec_base, my_child;
       pk_node_ortho(S.tlas_nodes, e, W, lane, inner, leaf, rec_base, my_child);
       pk_push_inner(stk, sp, inner, my_child, lane, S.overflow);
       const int nl = __popc(leaf);
-      if (sp + nl > PK_STACK) { if (lane == 0) atomicAdd(S.overflow, 1u); }
+      if (sp + nl > PK_STACK + PK_SPILL) { if (lane == 0) atomicAdd(S.overflow, 1u); }
       else {
-        if (lane < 24u && ((leaf >> lane) & 1u)) stk[sp + __popc(leaf & ~(0xFFFFFFFFu << lane))] = PK_INST | (rec_base + lane);
+        if (lane < 24u && ((leaf >> lane) & 1u)) stk.at(sp + __popc(leaf & ~(0xFFFFFFFFu << lane))) = PK_INST | (rec_base + lane);
         sp += nl;
       }
       __syncwarp();
@@ -310,11 +317,11 @@ __device__ __forceinline__ bool pk_trace_parallel_any(const TraceScene& S, float
     PkOrtho B;
     pk_setup_ortho(B, may, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, lane);  // only the rays that can reach this instance span the volume
     const int base = sp;
-    stk[sp++] = meta.x;
+    stk.at(sp++) = meta.x;
     __syncwarp();
     bool live = true;  // some lane that may hit this instance is still looking
     while (sp > base) {
-      const uint32_t node = stk[--sp];
+      const uint32_t node = stk.at(--sp);
       __syncwarp();
       if (!live) continue;  // drain the instance's entries
       uint32_t inner, leaf, rec_base, my_child;

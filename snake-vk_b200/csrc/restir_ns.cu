@@ -566,7 +566,7 @@ __global__ void __launch_bounds__(128, SNK_SHADOW_PACKET_CTAS) k_rs_shadow_dir(T
                                                                                uint32_t* ticket, uint32_t* next_ticket) {
   __shared__ uint32_t sm_stack[4 * PK_STACK];
   const uint32_t w = threadIdx.x >> 5, l = threadIdx.x & 31;
-  uint32_t* stk = sm_stack + w * PK_STACK;
+  const PkStack stk{sm_stack + w * PK_STACK, reinterpret_cast<uint32_t*>(S.spill + ((size_t)blockIdx.x * 4 + w) * (SPILL_STACK * 32))};
   const uint32_t tiles_x = (fc.W + 15u) / 16u, n_tiles = 4u * tiles_x * ((fc.row1 - fc.row0 + 7u) / 8u);
   if (blockIdx.x == 0 && threadIdx.x == 0) *next_ticket = 0u;
   for (;;) {
@@ -695,7 +695,9 @@ int restir_ns_reuse(SnkPt* ctx, const SnkRtSettings& s, const RefQueue& q, cudaS
     const uint32_t resident = (uint32_t)device_sm_count() * SNK_SHADOW_PACKET_CTAS;
     uint32_t* tickets2 = ctx->dev_counters.as<uint32_t>() + 202;  // second self-resetting ticket pair (the first: gbuffer.cu)
     const uint32_t par = ctx->shadow_parity++ & 1u;
-    k_rs_shadow_dir<<<n_tiles < resident ? n_tiles : resident, 128, 0, st>>>(ctx->trace_scene(), ctx->fc, L.B.rays + 4ull * L.npix_frame, L.B.vis + 2ull * L.npix_frame,
+    TraceScene Sd = ctx->trace_scene();
+    Sd.spill += (size_t)spill_region * (trace_spill_bytes() / sizeof(uint2));  // the chain's own spill region (packet stacks spill there)
+    k_rs_shadow_dir<<<n_tiles < resident ? n_tiles : resident, 128, 0, st>>>(Sd, ctx->fc, L.B.rays + 4ull * L.npix_frame, L.B.vis + 2ull * L.npix_frame,
                                                                              tickets2 + par, tickets2 + (par ^ 1u));
     prof_end(ctx, rec, st);
     return 4;

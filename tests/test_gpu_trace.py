@@ -182,7 +182,7 @@ def _soup(rng, n, spread, size):
     return p, nrm, np.arange(3 * n, dtype=np.uint32)
 
 
-@pytest.mark.parametrize("case", ["n1", "n2", "n3", "n9", "n17", "n4096", "n4097", "identical", "coplanar_grid", "mixed_scale", "degenerate"])
+@pytest.mark.parametrize("case", ["n1", "n2", "n3", "n9", "n17", "n4096", "n4097", "identical", "identical3000", "coplanar_grid", "mixed_scale", "degenerate"])
 def test_builder_edge_cases_match_bruteforce(snk, oracle, case):
     """BLAS sizes around the branches of the builder (single leaf, fewer primitives than the 8 slots of a wide node, the
     one-CTA path's 4096-primitive limit and the first size of the general path), Morton-code duplicates (identical and
@@ -193,10 +193,10 @@ def test_builder_edge_cases_match_bruteforce(snk, oracle, case):
     rng = np.random.default_rng(zlib.crc32(case.encode()))
     if case.startswith("n"):
         p, nrm, idx = _soup(rng, int(case[1:]), 4.0, 0.6)
-    elif case == "identical":  # 300 copies of the same triangle + a few others: equal Morton keys, equal boxes
-        p1, _, _ = _soup(rng, 1, 1.0, 1.5)
+    elif case in ("identical", "identical3000"):  # 300 / 3000 copies of the same triangle + a few others: equal Morton keys, equal boxes
+        p1, _, _ = _soup(rng, 1, 1.0, 1.5)                # (3000 copies: a hierarchy deeper than the packet traversal's shared stack)
         p2, _, _ = _soup(rng, 20, 4.0, 0.6)
-        p = np.concatenate([np.tile(p1, (300, 1)), p2]).astype(np.float32)
+        p = np.concatenate([np.tile(p1, (3000 if case == "identical3000" else 300, 1)), p2]).astype(np.float32)
         nrm = np.tile(np.float32([[0, 1, 0]]), (p.shape[0], 1)); idx = np.arange(p.shape[0], dtype=np.uint32)
     elif case == "coplanar_grid":  # 32 x 32 quads in the plane y = 0.5: one Morton axis carries no information
         g = np.arange(33, dtype=np.float32) * 0.25 - 4.0
@@ -235,5 +235,16 @@ def test_builder_edge_cases_match_bruteforce(snk, oracle, case):
     assert np.array_equal(got_any["t"] >= 0, ref["t"] >= 0)
     tbl = pt.blas_table()[0]
     assert (tbl["bounds_lo"] <= p.min(0)).all() and (tbl["bounds_hi"] >= p.max(0)).all()
+    assert int(pt.stats()["stack_overflows"]) == 0
+    # the same hierarchies through the PACKET traversal of the camera rays (gbuffer.cu: one stack per 8x4 tile): ids equal the oracle's
+    ubo = sc.ubo(0)
+    pt.set_frame(ubo, ubo)
+    pt.trace_primary()
+    fr = oracle.OracleFrame(osc)
+    fr.set(ubo, ubo, oracle.default_settings())
+    fr.gbuffer()
+    for name in ("prim", "inst"):
+        assert np.array_equal(pt.read_aux(name), fr.read(name)), f"{case}: primary {name} ids differ"
+    assert np.array_equal(pt.read_aux("hit_t").view(np.uint32), fr.read("hit_t").view(np.uint32))
     assert int(pt.stats()["stack_overflows"]) == 0
     pt.close()
