@@ -438,6 +438,11 @@ SNKPT_API int snkpt_particles_read(SnkPt* ctx, SnkParticle* dst, uint32_t first,
  * current / previous transforms; params NULL = defaults. rays_traced (optional) receives the rays of this call after a sync. */
 SNKPT_API int snkpt_particles_update(SnkPt* ctx, const SnkPhysicsParams* params, uint32_t substeps, void* stream);
 SNKPT_API int snkpt_particles_rays(SnkPt* ctx, uint64_t* rays_traced);
+/* SortUintsByKey (declared, never defined: Core/src/scene/ParticleSystem.cpp:14 — `extern "C" void SortUintsByKey(unsigned*
+ * device_keys, unsigned* device_values, unsigned count)`; the engine's own key sort is the bitonic chain of
+ * ParticleSystem::UpdateParticles): stable ascending sort of `count` DEVICE-resident (key, value) pairs in place, on `stream`
+ * (NULL = the context's stream) — the one-sweep radix sort the BVH builder and the particle grid use. count < 2^30. */
+SNKPT_API int snkpt_sort_uints_by_key(SnkPt* ctx, uint32_t* device_keys, uint32_t* device_values, uint32_t count, void* stream);
 
 /* ---- ray queries --------------------------------------------------------------------- */
 /* traceRayEXT semantics (closest hit in (tmin,tmax), watertight, no culling;

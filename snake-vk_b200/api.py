@@ -47,7 +47,7 @@ def load_library() -> C.CDLL:
         "snkpt_build_tlas": [vp, vp], "snkpt_set_frame": [vp, vp, vp], "snkpt_trace_primary": [vp, vp, vp],
         "snkpt_render": [vp, vp, vp], "snkpt_accumulate": [vp, i32, vp], "snkpt_taa_resolve": [vp, vp], "snkpt_read_output": [vp, vp, u32], "snkpt_read_output_async": [vp, vp, u32, u32], "snkpt_read_output_wait": [vp, u32],
         "snkpt_particles_create": [vp, u32, i32], "snkpt_particles_write": [vp, vp, u32, u32], "snkpt_particles_read": [vp, vp, u32, u32],
-        "snkpt_particles_update": [vp, vp, u32, vp], "snkpt_particles_rays": [vp, vp],
+        "snkpt_particles_update": [vp, vp, u32, vp], "snkpt_particles_rays": [vp, vp], "snkpt_sort_uints_by_key": [vp, vp, vp, u32, vp],
         "snkpt_read_aux": [vp, u32, vp, sz], "snkpt_aux_size": [vp, u32, vp],
         "snkpt_write_reservoirs": [vp, u32, vp, u32, u32], "snkpt_device_ptr": [vp, u32, vp, vp],
         "snkpt_get_stats": [vp, vp], "snkpt_synchronize": [vp], "snkpt_trace_rays": [vp, vp, u64, u32, vp, vp],
@@ -81,7 +81,7 @@ EXPORTS = ["snkpt_create", "snkpt_destroy", "snkpt_last_error", "snkpt_default_s
            "snkpt_set_frame", "snkpt_trace_primary", "snkpt_render", "snkpt_accumulate", "snkpt_read_output", "snkpt_read_aux",
            "snkpt_aux_size", "snkpt_write_reservoirs", "snkpt_device_ptr", "snkpt_get_stats", "snkpt_synchronize",
            "snkpt_trace_rays", "snkpt_count_work", "snkpt_set_profiling", "snkpt_get_launch_timings", "snkpt_taa_resolve", "snkpt_set_texture", "snkpt_read_output_async", "snkpt_read_output_wait", "snkpt_frame_jitter", "snkpt_particles_default_params",
-           "snkpt_particles_create", "snkpt_particles_write", "snkpt_particles_read", "snkpt_particles_update", "snkpt_particles_rays",
+           "snkpt_particles_create", "snkpt_particles_write", "snkpt_particles_read", "snkpt_particles_update", "snkpt_particles_rays", "snkpt_sort_uints_by_key",
            "snkpt_group_band", "snkpt_group_unique_id", "snkpt_group_attach_nccl", "snkpt_group_attach_local", "snkpt_group_detach", "snkpt_group_info", "snkpt_group_set_bands"]
 
 CONFIG_DTYPE = np.dtype([("width", "<u4"), ("height", "<u4"), ("device", "<i4"), ("max_instances", "<u4"),
@@ -298,6 +298,10 @@ class PathTracer:
     def particles_update(self, params: np.ndarray | None = None, substeps=3, stream=None):
         p = None if params is None else np.ascontiguousarray(params)
         self._ck(self.L.snkpt_particles_update(self.h, _p(p), substeps, stream), "snkpt_particles_update")
+
+    def sort_uints_by_key(self, device_keys: int, device_values: int, count: int, stream=None):
+        """SortUintsByKey (ParticleSystem.cpp:14): stable in-place sort of DEVICE-resident uint32 (key, value) pairs"""
+        self._ck(self.L.snkpt_sort_uints_by_key(self.h, device_keys, device_values, count, stream), "snkpt_sort_uints_by_key")
 
     def particles_rays(self) -> int:
         v = C.c_uint64(0)

@@ -1350,6 +1350,20 @@ int snkpt_particles_rays(SnkPt* ctx, uint64_t* rays_traced) {
   return SNKPT_OK;
 }
 
+int snkpt_sort_uints_by_key(SnkPt* ctx, uint32_t* device_keys, uint32_t* device_values, uint32_t count, void* stream) {
+  if (!ctx) return SNKPT_E_INVALID;
+  REQUIRE((device_keys && device_values) || count == 0, SNKPT_E_INVALID, "snkpt_sort_uints_by_key: null argument");
+  REQUIRE(count < (1u << 30), SNKPT_E_INVALID, "snkpt_sort_uints_by_key: count must be below 2^30");
+  if (count < 2) return SNKPT_OK;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
+  note_stream(ctx, st);
+  CK(scratch_reserve(ctx->scratch_ptcl, count));
+  ctx->stats.kernel_launches += launch_sort_uints(ctx->scratch_ptcl, device_keys, device_values, count, st);
+  CK(cudaGetLastError());
+  return SNKPT_OK;
+}
+
 // ---- ray queries ---------------------------------------------------------------------------------------------------
 int snkpt_trace_rays(SnkPt* ctx, const SnkRay* rays, uint64_t count, uint32_t flags, SnkHit* hits, void* stream) {
   if (!ctx) return SNKPT_E_INVALID;

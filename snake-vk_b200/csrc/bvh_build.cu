@@ -5,6 +5,7 @@
 // from the primitive count with 256-thread CTAs (the collapse kernel is the one
 // latency-bound stage: one thread per wide node, fed through a ticket queue).
 #include "bvh_build.cuh"
+#include "kernels.h"
 
 #include <atomic>
 #include <cstdlib>
@@ -50,7 +51,7 @@ constexpr int SORT_WARPS = SORT_THREADS / 32;
 // slot: 7.29 ms, 1: 7.27 ms with 30 % more nodes — profiles/r02d_variants_leaf_size.txt).
 constexpr int LEAF_MAX_BLAS = SNK_LEAF_MAX_BLAS, LEAF_MAX_TLAS = SNK_LEAF_MAX_TLAS;
 
-enum { C_NODES = 0, C_LEAVES = 1, C_DONE = 2, C_TICKET = 3, C_OVERFLOW = 4, C_BOUNDS = 8 };
+enum { C_NODES = 0, C_LEAVES = 1, C_DONE = 2, C_TICKET = 3, C_OVERFLOW = 4, C_PENDING = 5, C_BOUNDS = 8 };
 
 __device__ __forceinline__ uint32_t f2ord(float f) {
   uint32_t u = __float_as_uint(f);
@@ -513,6 +514,192 @@ static void launch_sort_scatter(const unsigned long long* keys_in, const uint32_
 #endif
 }
 
+// ---- one-sweep radix sort (round 2) -------------------------------------------------------------------------------------
+// The LSD passes above cost four launches each (tile histograms, two scans, scatter) and read the keys twice. Here a pass is ONE
+// kernel (Adinets & Merrill's "onesweep"): the digit totals of ALL passes come from one histogram kernel up front (they do not
+// depend on the order of the keys), and a tile learns how many keys with its digit lie in the tiles before it by a decoupled
+// look-back over per-tile status words (count | AGGREGATE or INCLUSIVE flag in one 32-bit word, so no fence is needed): tile t
+// publishes its own counts as soon as it has them, then walks back over t-1, t-2, ... adding aggregates until it meets an
+// inclusive prefix. Tiles are handed out by a ticket, so every tile a CTA waits for has already started. The scatter itself is
+// the staged one above with ONE ranking pass instead of two: the first pass over a warp's keys also remembers each key's place
+// among the warp's keys of the same digit. Same permutation as the LSD passes (stable in warp, tile and ticket order).
+#ifndef SNK_SORT_ONESWEEP
+#define SNK_SORT_ONESWEEP 1
+#endif
+constexpr int SWEEP_MAX_PASSES = 8;
+constexpr uint32_t SW_TICKETS = SWEEP_MAX_PASSES * 256;  // word offset of the per-pass tickets
+constexpr uint32_t SW_HEAD = SW_TICKETS + 64;             // [8][256] digit totals | 8 tickets | pad; then nb x 256 status words per pass
+constexpr uint32_t SW_AGG = 1u << 30, SW_INC = 2u << 30, SW_COUNT = (1u << 30) - 1u;
+
+// digit totals of all passes in one read of the keys. Shared-memory atomics cost 2 cycles per lane on this part (64 per warp
+// instruction): with them this kernel took 176 us for 10 M keys x 5 passes. Instead every warp keeps PRIVATE counters and its
+// lanes agree on them with match.any — the leader of each group of equal digits adds the group's size with a plain load / store.
+constexpr int SWH_THREADS = 512, SWH_WARPS = SWH_THREADS / 32;
+__global__ void __launch_bounds__(SWH_THREADS) k_sweep_hist(const unsigned long long* __restrict__ keys, uint32_t n, int passes,
+                                                            uint32_t* __restrict__ head) {
+  extern __shared__ uint32_t swh[];  // [warp][pass][256]
+  const uint32_t lane = threadIdx.x & 31u, wid = threadIdx.x >> 5, lt = (1u << lane) - 1u;
+  uint32_t* mine = swh + (size_t)wid * passes * 256;
+  for (int i = lane; i < passes * 256; i += 32) mine[i] = 0u;
+  __syncwarp();
+  const uint32_t stride = gridDim.x * SWH_THREADS;
+  for (uint32_t base = blockIdx.x * SWH_THREADS + wid * 32u; base < n; base += stride) {  // warp-uniform trip count
+    const uint32_t idx = base + lane;
+    const bool valid = idx < n;
+    const unsigned long long k = valid ? keys[idx] : 0ull;
+    for (int p = 0; p < passes; ++p) {
+      const uint32_t d = valid ? ((uint32_t)(k >> (8 * p)) & 255u) : 256u;
+      const uint32_t peers = __match_any_sync(0xffffffffu, d);
+      if (valid && (peers & lt) == 0u) mine[p * 256 + d] += (uint32_t)__popc(peers);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < passes * 256; i += SWH_THREADS) {
+    uint32_t t = 0;
+    for (int w = 0; w < SWH_WARPS; ++w) t += swh[(size_t)w * passes * 256 + i];
+    if (t) atomicAdd(&head[i], t);
+  }
+}
+
+constexpr size_t SWEEP_SMEM = (size_t)SORT_TILE * 12 + (size_t)SORT_WARPS * 256 * 4 + 256 * 4 * 2 + 64 + 16;
+__global__ void __launch_bounds__(SORT_THREADS, SNK_SORT_MIN_CTAS) k_sweep_pass(const unsigned long long* __restrict__ keys_in,
+                                                                                  const uint32_t* __restrict__ vals_in, uint32_t n, int shift, int pass,
+                                                                                  uint32_t* head, uint32_t* status,
+                                                                                  unsigned long long* __restrict__ keys_out,
+                                                                                  uint32_t* __restrict__ vals_out) {
+  extern __shared__ __align__(16) unsigned char sort_smem[];
+  unsigned long long* skey = reinterpret_cast<unsigned long long*>(sort_smem);
+  uint32_t* sval = reinterpret_cast<uint32_t*>(skey + SORT_TILE);
+  uint32_t (*wh)[256] = reinterpret_cast<uint32_t (*)[256]>(sval + SORT_TILE);
+  uint32_t* goff = reinterpret_cast<uint32_t*>(wh + SORT_WARPS);  // global position of tile-local position j: goff[d] + j
+  uint32_t* warp_sums = goff + 256;                                // 8 tile sums | 8 global sums
+  uint32_t* s_tile = warp_sums + 16;
+  const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) *s_tile = atomicAdd(&head[SW_TICKETS + pass], 1u);
+  for (int d = lane; d < 256; d += 32) wh[wid][d] = 0;
+  __syncthreads();
+  const uint32_t tile = *s_tile;
+  const uint32_t tile_base = tile * SORT_TILE;
+  const uint32_t warp_base = tile_base + wid * (SORT_ITEMS * 32);
+  const uint32_t lt = (1u << lane) - 1u;
+  unsigned long long key[SORT_ITEMS];
+  uint32_t val[SORT_ITEMS];
+  uint32_t off[SORT_ITEMS];  // place of the key among the keys of the same digit of this warp
+#pragma unroll
+  for (int it = 0; it < SORT_ITEMS; ++it) {
+    const uint32_t idx = warp_base + it * 32 + lane;
+    const bool valid = idx < n;
+    key[it] = valid ? keys_in[idx] : ~0ull;
+    val[it] = valid ? vals_in[idx] : 0u;
+  }
+  // phase 1: per-warp digit counts (each warp owns a contiguous run of the tile -> stable) + the key's place in its warp's run
+#pragma unroll
+  for (int it = 0; it < SORT_ITEMS; ++it) {
+    const bool valid = warp_base + it * 32 + lane < n;
+    const uint32_t d = valid ? ((uint32_t)(key[it] >> shift) & 255u) : 256u;
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    const uint32_t rank = __popc(peers & lt);
+    const uint32_t prev = valid ? wh[wid][d] : 0u;
+    __syncwarp();
+    if (valid && rank == 0u) wh[wid][d] = prev + __popc(peers);
+    __syncwarp();
+    off[it] = prev + rank;
+  }
+  __syncthreads();
+  // phase 2: per-warp counts -> exclusive over the warps; tile totals published, scanned over the digits, looked back over the tiles
+  uint32_t total = 0, gcount = 0;
+  const uint32_t d = threadIdx.x;
+  volatile uint32_t* st = status;
+  if (d < 256u) {
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; ++w) {
+      const uint32_t c = wh[w][d];
+      wh[w][d] = total;
+      total += c;
+    }
+    st[(size_t)tile * 256u + d] = (tile == 0u ? SW_INC : SW_AGG) | total;
+    gcount = head[pass * 256 + d];
+  }
+  uint32_t inc = total, ginc = gcount;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o), g = __shfl_up_sync(0xffffffffu, ginc, o);
+    if (lane >= o) { inc += t; ginc += g; }
+  }
+  if (lane == 31 && wid < 8) { warp_sums[wid] = inc; warp_sums[8 + wid] = ginc; }
+  __syncthreads();
+  if (d < 256u) {
+    uint32_t before = 0, gbefore = 0;
+    for (uint32_t w = 0; w < wid; ++w) { before += warp_sums[w]; gbefore += warp_sums[8 + w]; }
+    const uint32_t start = before + inc - total;          // first tile-local position of digit d
+    const uint32_t gbase = gbefore + ginc - gcount;        // keys with a smaller digit in the whole input
+    uint32_t excl = 0;                                     // keys with digit d in earlier tiles
+    if (tile > 0u) {
+      uint32_t t = tile - 1u;
+      for (;;) {
+        const uint32_t v = st[(size_t)t * 256u + d];
+        if ((v >> 30) == 0u) continue;                     // that tile has not published yet (it has started: ticket order)
+        excl += v & SW_COUNT;
+        if (v & SW_INC) break;
+        --t;
+      }
+      st[(size_t)tile * 256u + d] = SW_INC | (excl + total);
+    }
+    goff[d] = gbase + excl - start;
+#pragma unroll
+    for (int w = 0; w < SORT_WARPS; ++w) wh[w][d] += start;
+  }
+  __syncthreads();
+  // phase 3: move to the tile-local sorted position
+#pragma unroll
+  for (int it = 0; it < SORT_ITEMS; ++it) {
+    const bool valid = warp_base + it * 32 + lane < n;
+    if (valid) {
+      const uint32_t pos = wh[wid][(uint32_t)(key[it] >> shift) & 255u] + off[it];
+      skey[pos] = key[it]; sval[pos] = val[it];
+    }
+  }
+  __syncthreads();
+  // phase 4: write the tile out in sorted order
+  const uint32_t tile_n = n - tile_base < (uint32_t)SORT_TILE ? n - tile_base : (uint32_t)SORT_TILE;
+  for (uint32_t j = threadIdx.x; j < tile_n; j += SORT_THREADS) {
+    const unsigned long long k = skey[j];
+    const uint32_t g = goff[(uint32_t)(k >> shift) & 255u] + j;
+    keys_out[g] = k;
+    vals_out[g] = sval[j];
+  }
+}
+
+// SNKPT_SORT=lsd selects the four-launch LSD passes (A/B runs)
+static bool sort_onesweep() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SNKPT_SORT"); v = (SNK_SORT_ONESWEEP && !(e && e[0] == 'l')) ? 1 : 0; }
+  return v == 1;
+}
+// sorts s.keys[cur] / s.vals[cur] by the key bits [shift0, shift0 + 8 * passes); returns the number of stream operations
+static int launch_sort_sweep(BuildScratch& s, uint32_t n, int passes, int& cur, cudaStream_t st) {
+  static bool configured[64] = {};  // the opt-in to > 48 KB of dynamic shared memory is per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    cudaFuncSetAttribute(k_sweep_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SWEEP_SMEM);
+    cudaFuncSetAttribute(k_sweep_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, SWH_WARPS * SWEEP_MAX_PASSES * 256 * (int)sizeof(uint32_t));
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  const uint32_t nb = (n + SORT_TILE - 1) / SORT_TILE;
+  cudaMemsetAsync(s.sweep, 0, sizeof(uint32_t) * ((size_t)SW_HEAD + (size_t)passes * nb * 256u), st);
+  const uint32_t hist_want = (n + 4u * SWH_THREADS - 1u) / (4u * SWH_THREADS), hist_res = (uint32_t)device_sm_count() * 2u;
+  const size_t hist_smem = (size_t)SWH_WARPS * passes * 256 * sizeof(uint32_t);
+  k_sweep_hist<<<hist_want < hist_res ? hist_want : hist_res, SWH_THREADS, hist_smem, st>>>(s.keys[cur], n, passes, s.sweep);
+  for (int p = 0; p < passes; ++p) {
+    k_sweep_pass<<<nb, SORT_THREADS, SWEEP_SMEM, st>>>(s.keys[cur], s.vals[cur], n, 8 * p, p, s.sweep, s.sweep + SW_HEAD + (size_t)p * nb * 256u,
+                                                        s.keys[cur ^ 1], s.vals[cur ^ 1]);
+    cur ^= 1;
+  }
+  return passes + 2;
+}
+
 // ---- Karras 2012 ------------------------------------------------------------------------
 __device__ __forceinline__ int delta(const unsigned long long* __restrict__ keys, int n, int i, int j) {
   if (j < 0 || j >= n) return -1;
@@ -584,6 +771,90 @@ __global__ void k_refit_binary(const float4* __restrict__ prim_lo, const float4*
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   refit_from_leaf(prim_lo, prim_hi, sorted_prims, n, k, left, right, parent, bb_lo, bb_hi, flags);
+}
+
+// The same boxes with the walk kept ON CHIP (round 2). The walk above pays two device-wide fences, one L2 atomic and three dependent
+// L2 reads per level and node: 0.94 of 3.9 ms at 10 M triangles. Every internal node of the Karras hierarchy covers a contiguous
+// range [first, last] of the sorted leaves and its own index lies inside that range, so a CTA that owns the leaves [c0, c1) also
+// owns — exclusively — every internal node whose range lies inside [c0, c1): their arrival words and the boxes the siblings hand
+// over live in shared memory (index - c0), ordered by block-level fences. A walk that reaches a node whose range crosses a chunk
+// border (about 3 % of the nodes) is parked in a list and finished by a second kernel with the global protocol above — both
+// children of such a node agree on that because the choice depends on the parent alone. (Finishing those walks inside the first
+// kernel kept every CTA resident for its slowest 20-level global walk: 0.85 ms instead of 0.94.) min / max are exact: the boxes
+// are the same bits as before.
+#ifndef SNK_REFIT_CHUNKED
+#define SNK_REFIT_CHUNKED 1
+#endif
+constexpr int RB_CHUNK = 512;
+__global__ void __launch_bounds__(RB_CHUNK, 4) k_refit_binary_chunked(const float4* __restrict__ prim_lo, const float4* __restrict__ prim_hi,
+                                                                      const uint32_t* __restrict__ sorted_prims, int n,
+                                                                      const int* __restrict__ parent, const int* __restrict__ first,
+                                                                      const int* __restrict__ last, float4* bb_lo, float4* bb_hi,
+                                                                      uint32_t* __restrict__ pending, uint32_t* pending_count) {
+  // local ids: internal node i -> i - c0, leaf k -> RB_CHUNK + k - c0
+  __shared__ float s_box[6][2 * RB_CHUNK];
+  __shared__ uint32_t s_flag[RB_CHUNK];
+  __shared__ uint32_t s_npend, s_base;
+  const int c0 = blockIdx.x * RB_CHUNK, c1 = min(c0 + RB_CHUNK, n);
+  s_flag[threadIdx.x] = 0u;
+  if (threadIdx.x == 0) s_npend = 0u;
+  __syncthreads();
+  const int k = c0 + (int)threadIdx.x;
+  int node = -1;  // >= 0 afterwards: this thread's walk goes on at parent[node], outside the chunk
+  if (k < n) {
+    const uint32_t p = sorted_prims[k];
+    float4 lo = prim_lo[p], hi = prim_hi[p];
+    int my = RB_CHUNK + (int)threadIdx.x;
+    node = n - 1 + k;
+    bb_lo[node] = lo; bb_hi[node] = hi;
+    int par = parent[node];
+    while (par >= 0) {
+      if (first[par] < c0 || last[par] >= c1) break;
+      const int j = par - c0;
+      s_box[0][my] = lo.x; s_box[1][my] = lo.y; s_box[2][my] = lo.z; s_box[3][my] = hi.x; s_box[4][my] = hi.y; s_box[5][my] = hi.z;
+      __threadfence_block();
+      const uint32_t seen = atomicExch(&s_flag[j], (uint32_t)my + 1u);
+      if (seen == 0u) { par = -1; break; }  // the sibling will find this box
+      __threadfence_block();
+      const int o = (int)seen - 1;
+      lo = make_float4(fminf(lo.x, s_box[0][o]), fminf(lo.y, s_box[1][o]), fminf(lo.z, s_box[2][o]), 0.f);
+      hi = make_float4(fmaxf(hi.x, s_box[3][o]), fmaxf(hi.y, s_box[4][o]), fmaxf(hi.z, s_box[5][o]), 0.f);
+      bb_lo[par] = lo; bb_hi[par] = hi;
+      node = par; my = j;
+      par = parent[node];
+    }
+    if (par < 0) node = -1;  // handed over to the sibling, or the root is done
+  }
+  uint32_t slot = 0;
+  if (node >= 0) slot = atomicAdd(&s_npend, 1u);
+  __syncthreads();
+  if (threadIdx.x == 0 && s_npend) s_base = atomicAdd(pending_count, s_npend);
+  __syncthreads();
+  if (node >= 0) pending[s_base + slot] = (uint32_t)node;
+}
+// the parked walks: node's box is in bb_lo / bb_hi (written by the kernel before), its parent is shared with another chunk
+__global__ void __launch_bounds__(256) k_refit_binary_top(const uint32_t* __restrict__ pending, const uint32_t* __restrict__ pending_count,
+                                                          const int* __restrict__ parent, float4* bb_lo, float4* bb_hi, uint32_t* flags) {
+  const uint32_t count = *pending_count;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    int node = (int)pending[i];
+    float4 lo = bb_lo[node], hi = bb_hi[node];
+    int par = parent[node];
+    while (par >= 0) {
+      // the first child to arrive leaves its index (+1) and stops; the second one finds its sibling there and continues
+      const uint32_t seen = atomicExch(&flags[par], (uint32_t)node + 1u);
+      if (seen == 0u) break;
+      __threadfence();
+      const int other = (int)seen - 1;
+      const float4 olo = __ldcg(&bb_lo[other]), ohi = __ldcg(&bb_hi[other]);
+      lo = make_float4(fminf(lo.x, olo.x), fminf(lo.y, olo.y), fminf(lo.z, olo.z), 0.f);
+      hi = make_float4(fmaxf(hi.x, ohi.x), fmaxf(hi.y, ohi.y), fmaxf(hi.z, ohi.z), 0.f);
+      bb_lo[par] = lo; bb_hi[par] = hi;
+      __threadfence();
+      node = par;
+      par = parent[node];
+    }
+  }
 }
 
 // ---- collapse to 8-wide nodes ---------------------------------------------------------------
@@ -1519,7 +1790,7 @@ void scratch_free(BuildScratch& s) {
   cudaFree(s.prim_lo); cudaFree(s.prim_hi);
   for (int i = 0; i < 2; ++i) { cudaFree(s.keys[i]); cudaFree(s.vals[i]); }
   cudaFree(s.block_hist); cudaFree(s.left); cudaFree(s.right); cudaFree(s.parent); cudaFree(s.first); cudaFree(s.last);
-  cudaFree(s.bb_lo); cudaFree(s.bb_hi); cudaFree(s.flags); cudaFree(s.queue); cudaFree(s.counters); cudaFree(s.digit_total);
+  cudaFree(s.bb_lo); cudaFree(s.bb_hi); cudaFree(s.flags); cudaFree(s.queue); cudaFree(s.counters); cudaFree(s.digit_total); cudaFree(s.sweep);
   s = BuildScratch();
 }
 
@@ -1537,6 +1808,7 @@ cudaError_t scratch_reserve(BuildScratch& s, uint32_t n) {
   SNK_TRY(alloc(s.first, cap)); SNK_TRY(alloc(s.last, cap));
   SNK_TRY(alloc(s.bb_lo, 2 * cap)); SNK_TRY(alloc(s.bb_hi, 2 * cap));
   SNK_TRY(alloc(s.flags, cap)); SNK_TRY(alloc(s.queue, cap + 1)); SNK_TRY(alloc(s.counters, 16)); SNK_TRY(alloc(s.digit_total, 256));
+  SNK_TRY(alloc(s.sweep, (size_t)SW_HEAD + (size_t)SWEEP_MAX_PASSES * 256 * s.hist_blocks));
 #undef SNK_TRY
   s.capacity = (uint32_t)cap;
   return cudaSuccess;
@@ -1586,6 +1858,7 @@ void launch_instance_bounds(BuildScratch& s, const float* transforms_cm, const S
 int launch_sort_pairs(BuildScratch& s, uint32_t n, int bits, int& cur, cudaStream_t st) {
   int launches = 0;
   if (n <= 1) return 0;
+  if (sort_onesweep() && n < (1u << 30)) return launch_sort_sweep(s, n, (bits + 7) / 8, cur, st);
   const uint32_t nb = (n + SORT_TILE - 1) / SORT_TILE;
   for (int shift = 0; shift < bits; shift += 8) {
     k_sort_hist<<<nb, SORT_THREADS, 0, st>>>(s.keys[cur], n, shift, s.block_hist, nb);
@@ -1596,6 +1869,27 @@ int launch_sort_pairs(BuildScratch& s, uint32_t n, int bits, int& cur, cudaStrea
     launches += 4;
   }
   return launches;
+}
+
+namespace {
+__global__ void k_widen_pairs(const uint32_t* __restrict__ k, const uint32_t* __restrict__ v, uint32_t n, unsigned long long* __restrict__ keys,
+                              uint32_t* __restrict__ vals) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { keys[i] = k[i]; vals[i] = v[i]; }
+}
+__global__ void k_narrow_pairs(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t n, uint32_t* __restrict__ k,
+                               uint32_t* __restrict__ v) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { k[i] = (uint32_t)keys[i]; v[i] = vals[i]; }
+}
+}  // namespace
+int launch_sort_uints(BuildScratch& s, uint32_t* keys, uint32_t* vals, uint32_t n, cudaStream_t st) {
+  const uint32_t g = (n + 255) / 256;
+  k_widen_pairs<<<g, 256, 0, st>>>(keys, vals, n, s.keys[0], s.vals[0]);
+  int cur = 0;
+  const int launches = launch_sort_pairs(s, n, 32, cur, st);
+  k_narrow_pairs<<<g, 256, 0, st>>>(s.keys[cur], s.vals[cur], n, keys, vals);
+  return launches + 2;
 }
 
 int launch_build(BuildScratch& s, uint32_t n, const BuildOutput& out, const float* positions, const uint32_t* indices,
@@ -1652,7 +1946,10 @@ int launch_build(BuildScratch& s, uint32_t n, const BuildOutput& out, const floa
   int cur = 0;
   if (n > 1) {
     const uint32_t nb = (n + SORT_TILE - 1) / SORT_TILE;
-    for (int shift = 0; shift < key_bits + (SNK_HOIST_LARGE ? 1 : 0); shift += 8) {  // + the large-primitive bit above the Morton bits
+    const int sort_bits = key_bits + (SNK_HOIST_LARGE ? 1 : 0);  // + the large-primitive bit above the Morton bits
+    if (sort_onesweep() && n < (1u << 30)) launches += launch_sort_sweep(s, n, (sort_bits + 7) / 8, cur, st);
+    else
+    for (int shift = 0; shift < sort_bits; shift += 8) {
       k_sort_hist<<<nb, SORT_THREADS, 0, st>>>(s.keys[cur], n, shift, s.block_hist, nb);
       k_scan_rows<<<256, 256, 0, st>>>(s.block_hist, nb, s.digit_total);
       k_scan_digits<<<1, 256, 0, st>>>(s.digit_total);
@@ -1665,7 +1962,18 @@ int launch_build(BuildScratch& s, uint32_t n, const BuildOutput& out, const floa
   } else {
     cudaMemsetAsync(s.parent, 0xFF, sizeof(int), st);  // parent[0] = -1: the only leaf is the root
   }
+#if SNK_REFIT_CHUNKED
+  {
+    uint32_t* pending = s.vals[cur ^ 1];  // the sort's other buffer is free again
+    k_refit_binary_chunked<<<(n + RB_CHUNK - 1) / RB_CHUNK, RB_CHUNK, 0, st>>>(s.prim_lo, s.prim_hi, s.vals[cur], (int)n, s.parent, s.first, s.last, s.bb_lo,
+                                                                            s.bb_hi, pending, s.counters + C_PENDING);
+    const uint32_t want = (n / 16u + 255u) / 256u, resident = (uint32_t)device_sm_count() * 8u;
+    k_refit_binary_top<<<want < resident ? (want ? want : 1u) : resident, 256, 0, st>>>(pending, s.counters + C_PENDING, s.parent, s.bb_lo, s.bb_hi, s.flags);
+    launches += 2;
+  }
+#else
   k_refit_binary<<<g, 256, 0, st>>>(s.prim_lo, s.prim_hi, s.vals[cur], (int)n, s.left, s.right, s.parent, s.bb_lo, s.bb_hi, s.flags); ++launches;
+#endif
   // queue[0] = root was set by k_init
   const uint32_t cap = out.node_capacity < n ? out.node_capacity : n;
   CollapseArgs a;

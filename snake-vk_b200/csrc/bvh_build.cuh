@@ -27,6 +27,7 @@ struct BuildScratch {
   uint32_t* queue = nullptr;                             // binary node handled by wide node w
   uint32_t* counters = nullptr;                          // 16 words, see bvh_build.cu
   uint32_t* digit_total = nullptr;                       // 256 words: per-digit totals / bases of the current sort pass
+  uint32_t* sweep = nullptr;                             // one-sweep sort: digit totals and tickets of all passes, then the tiles' status words
   uint32_t hist_blocks = 0;
   bool clean = false;                                    // counters / queue[0] are in their initial state (left so by a single-CTA TLAS build)
 };
@@ -66,6 +67,8 @@ void launch_instance_bounds(BuildScratch& s, const float* transforms_cm, const S
                             uint32_t n, cudaStream_t st);
 // stable LSD radix sort of s.keys[cur] / s.vals[cur] over the low `bits` key bits (8 bits per pass); updates `cur`
 int launch_sort_pairs(BuildScratch& s, uint32_t n, int bits, int& cur, cudaStream_t st);
+// snkpt_sort_uints_by_key: 32-bit keys / values of the caller, sorted in place through the scratch's 64-bit key buffers
+int launch_sort_uints(BuildScratch& s, uint32_t* keys, uint32_t* vals, uint32_t n, cudaStream_t st);
 // generic build over s.prim_lo/hi. Returns the number of kernels launched. After completion s.counters[0] holds
 // the number of wide nodes written, s.counters[1] the number of leaf records, s.counters[4] an overflow flag.
 int launch_build(BuildScratch& s, uint32_t n, const BuildOutput& out, const float* positions, const uint32_t* indices,
