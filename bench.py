@@ -14,7 +14,7 @@ not selected is measured too and reported under `other_mode`.
   value       all rays traced by all ranks / max-over-ranks device time (CUDA events on the frame's stream), inputs resident
   e2e         the same through the C ABI with HOST buffers: per-frame transform / instance upload + read-back of the image
   roofline    dominant traversal launch: algorithmic bytes (counted replay) / its event duration in the timed region
-  other_configs (N = 1)  C2 with 1 M triangles, C3 (10,248 emissive triangles), C4 (3 M triangles, 3840x2160), C5 build /
+  other_configs (N = 1)  C2 with 1 M triangles, C3 (10,248 emissive triangles), C4 (3 M triangles, 3840x2160, instanced and flat), C5 build /
               refit / TLAS sweep at 1e6 and 1e7 triangles
   strong (N > 1)  the frame strong-scaled as row bands (snkpt_group_attach_nccl: reservoir rows travel by ncclSend / ncclRecv
               inside snkpt_render): ms per frame and efficiency against one GPU, on C2 1080p and on C4 4K (BASELINE config 4)
@@ -660,14 +660,14 @@ def other_configs(args, snk, torch, stream):
     def barrier():
         torch.cuda.synchronize()
 
-    for name, (w, h) in (("c2m", (1920, 1080)), ("c3", (1920, 1080)), ("shipped", (1920, 1080)), ("c4", (3840, 2160))):
+    for name, (w, h) in (("c2m", (1920, 1080)), ("c3", (1920, 1080)), ("shipped", (1920, 1080)), ("c4", (3840, 2160)), ("c4flat", (3840, 2160))):
         sc, desc = make_scene(snk, name, w, h)
         pt = snk.PathTracer(w, h)
         pt.upload_scene(sc)
         loop = FrameLoop(snk, sc, pt, stream, settings)
         for _ in range(3):
             loop.step()
-        steps = 10 if name != "c4" else 6
+        steps = 10 if not name.startswith("c4") else 6
         ms, rays, _ = timed(torch, loop, steps, barrier)
         solo = serialized_kernels(loop, frames=2)
         counted = counted_work(loop, frames=1)

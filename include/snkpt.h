@@ -410,6 +410,8 @@ SNKPT_API int snkpt_get_stats(SnkPt* ctx, SnkPtStats* out);
  * 3: bracket only the traversal launches, on the stream each one runs on, and keep
  * the north-star frame's two chains overlapped (levels 1 and 2 run one launch at a
  * time so that every kernel is timed alone) — what bench.py's timed region uses.
+ * 4: bracket every launch AND keep the chains overlapped: a timeline — `nodes` of a record then holds the start of the launch
+ * in ns after the start of the first record (durations of overlapped launches include the time they shared the GPU).
  * Records accumulate (up to 2048) until the next snkpt_set_profiling call or
  * snkpt_get_launch_timings, which returns and clears them. */
 SNKPT_API int snkpt_set_profiling(SnkPt* ctx, uint32_t level);

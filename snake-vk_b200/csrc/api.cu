@@ -142,7 +142,7 @@ void reset_ref_queues(SnkPt* ctx, cudaStream_t st) { cudaMemsetAsync(ctx->dev_co
 bool ns_overlap_enabled(const SnkPt* ctx) {
   static int v = -1;
   if (v < 0) { const char* e = getenv("SNKPT_NS_OVERLAP"); v = (e && e[0] == '0') ? 0 : 1; }
-  return v == 1 && (ctx->profiling == 0 || ctx->profiling == 3);
+  return v == 1 && (ctx->profiling == 0 || ctx->profiling >= 3);
 }
 
 int traced_launch_q(SnkPt* ctx, const char* name, const TraceSegs& segs, const RefQueue& q, cudaStream_t st, int spill_region) {
@@ -413,6 +413,7 @@ void snkpt_destroy(SnkPt* ctx) {
   group_free(ctx);
   if (ctx->hi_stream) { cudaStreamSynchronize(ctx->hi_stream); cudaStreamDestroy(ctx->hi_stream); }
   if (ctx->ev_join_b) cudaEventDestroy(ctx->ev_join_b);
+  for (cudaEvent_t& e : ctx->ev_path) if (e) { cudaEventDestroy(e); e = nullptr; }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -1223,7 +1224,7 @@ int snkpt_get_stats(SnkPt* ctx, SnkPtStats* out) {
 
 int snkpt_set_profiling(SnkPt* ctx, uint32_t level) {
   if (!ctx) return SNKPT_E_INVALID;
-  REQUIRE(level <= 3, SNKPT_E_INVALID, "snkpt_set_profiling: level");
+  REQUIRE(level <= 4, SNKPT_E_INVALID, "snkpt_set_profiling: level");
   ctx->profiling = level;
   ctx->prof_n = 0;
   return SNKPT_OK;
@@ -1244,6 +1245,11 @@ int snkpt_get_launch_timings(SnkPt* ctx, SnkLaunchTiming* out, uint32_t cap, uin
     memset(&o, 0, sizeof(o));
     memcpy(o.name, r.name, sizeof(o.name));
     cudaEventElapsedTime(&o.ms, r.e0, r.e1);
+    if (ctx->profiling == 4) {  // timeline: start of the launch after the first record's start, in ns
+      float off = 0.f;
+      cudaEventElapsedTime(&off, ctx->prof[0].e0, r.e0);
+      o.nodes = (uint64_t)((double)(off > 0.f ? off : 0.f) * 1e6);
+    }
     o.is_trace = r.is_trace ? 1u : 0u;
     o.units = r.units;
     if (r.counted) {

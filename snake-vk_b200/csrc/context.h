@@ -170,6 +170,7 @@ struct SnkPt {
   // north-star frame: low-priority stream of the ReSTIR chain (northstar.cu), forked from / joined to the frame's stream
   cudaStream_t aux_stream = nullptr, hi_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join_b = nullptr;
+  cudaEvent_t ev_path[20] = {};  // path chain: after ns_gen, after every traversal launch (staggered start of the ReSTIR chain)
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t ev_frame_done = nullptr, ev_read_done[4] = {};
   bool read_pending[4] = {false, false, false, false};

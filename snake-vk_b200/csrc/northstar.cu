@@ -391,29 +391,54 @@ int launch_northstar_frame(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st) 
   int rec;
   // queue capacities: chain A up to 3 rays per pixel (final point / emissive / directional), chain B 2 (NEE + continuation)
   const uint32_t capA = 3u * npix_frame, capB = 2u * npix_frame;
-  if (nee_from) {
-    if (overlap) { cudaEventRecord(ctx->ev_fork, st); cudaStreamWaitEvent(sa, ctx->ev_fork, 0); cudaStreamWaitEvent(sb, ctx->ev_fork, 0); }
+  // Staggered start (SNKPT_NS_STAGGER = "a,b", path events: 0 = after ns_gen, k = after the traversal launch of bounce k - 1):
+  // the ReSTIR chain's first half (initial candidates + their shadow rays) starts when path event a has passed, its second half
+  // (temporal / spatial / final + shadow rays + resolve) when event b has passed; -1 = at the fork. The path chain is enqueued first then.
+  static int stagger[2] = {-2, -2};
+  if (stagger[0] == -2) {
+    int a0 = -1, a1 = -1;
+    const char* e = getenv("SNKPT_NS_STAGGER");
+    if (e) sscanf(e, "%d,%d", &a0, &a1);
+    stagger[1] = a1 < 18 ? a1 : 18; stagger[0] = a0 < 18 ? a0 : 18;
+  }
+  const bool staggered = overlap && (stagger[0] >= 0 || stagger[1] >= 0);
+  auto stage_event = [&](int k) {
+    if (!staggered || k >= 19) return;
+    if (!ctx->ev_path[k]) cudaEventCreateWithFlags(&ctx->ev_path[k], cudaEventDisableTiming);
+    cudaEventRecord(ctx->ev_path[k], sb);
+  };
+  int rcA = 0;
+  auto chain_a = [&]() {
+    if (!nee_from) {
+      cudaEventRecord(ctx->ev[3], st);
+      cudaMemsetAsync(ctx->planes.direct + (size_t)fc.row0 * fc.W, 0, 16ull * npix, st);
+      return;
+    }
+    const int last = (int)max_bounces;  // events 0 .. max_bounces exist
+    if (staggered && stagger[0] >= 0) cudaStreamWaitEvent(sa, ctx->ev_path[stagger[0] < last ? stagger[0] : last], 0);
     RefQueue QA = ref_queue(ctx, 0, capA, 0);
     launches += restir_ns_initial(ctx, s, QA, sa);
     launches += traced_launch_q(ctx, "trace.qA0", segs, QA, sa, overlap ? 1 : 0);
+    if (staggered && stagger[1] >= 0) cudaStreamWaitEvent(sa, ctx->ev_path[stagger[1] < last ? stagger[1] : last], 0);
     QA = ref_queue(ctx, 1, capA, 0);
-    rc = restir_ns_reuse(ctx, s, QA, sa, overlap ? 1 : 0);
-    if (rc < 0) return rc;
-    launches += rc;
+    const int r = restir_ns_reuse(ctx, s, QA, sa, overlap ? 1 : 0);
+    if (r < 0) { rcA = r; return; }
+    launches += r;
     launches += traced_launch_q(ctx, "trace.qA1", segs, QA, sa, overlap ? 1 : 0);
     launches += restir_ns_resolve(ctx, sa);
     if (overlap) cudaEventRecord(ctx->ev_join, sa);
-  } else {
-    cudaEventRecord(ctx->ev[3], st);
-    cudaMemsetAsync(ctx->planes.direct + (size_t)fc.row0 * fc.W, 0, 16ull * npix, st);
-  }
+  };
+  if (nee_from && overlap) { cudaEventRecord(ctx->ev_fork, st); cudaStreamWaitEvent(sa, ctx->ev_fork, 0); cudaStreamWaitEvent(sb, ctx->ev_fork, 0); }
+  if (!staggered) { chain_a(); if (rcA < 0) return rcA; }
   int q = 2;
   RefQueue Q = ref_queue(ctx, q, capB, capA);
   rec = prof_begin(ctx, "ns_gen", npix, false, false, sb);
   k_ns_gen<<<(stage_threads(fc.W, fc.row1 - fc.row0) + 127) / 128, 128, 0, sb>>>(D, fc, ctx->planes, B, npix, max_bounces, nee_from, counters, Q.refs, Q.count, paths[0], path_count);
   prof_end(ctx, rec, sb);
   ++launches;
+  stage_event(0);
   launches += traced_launch_q(ctx, "trace.qB0", segs, Q, sb, 0);
+  stage_event(1);
   const uint32_t sms = (uint32_t)device_sm_count();
   for (uint32_t b = 1; b <= max_bounces; ++b) {
     Q = ref_queue(ctx, ++q, capB, capA);
@@ -426,8 +451,10 @@ int launch_northstar_frame(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st) 
     prof_end(ctx, rec, sb);
     snprintf(name, sizeof(name), "trace.qB%u", b);
     launches += 1 + traced_launch_q(ctx, name, segs, Q, sb, 0);
+    if (b < max_bounces) stage_event((int)b + 1);
     if (b == 1) cudaEventRecord(ctx->ev[4], sb);
   }
+  if (staggered) { chain_a(); if (rcA < 0) return rcA; }
   if (max_bounces == 0) cudaEventRecord(ctx->ev[4], sb);
   if (overlap) { cudaEventRecord(ctx->ev_join_b, sb); cudaStreamWaitEvent(st, ctx->ev_join_b, 0); }
   if (overlap) cudaStreamWaitEvent(st, ctx->ev_join, 0);
