@@ -42,8 +42,11 @@ k_trace_pt(TraceScene S, const float4* __restrict__ rays, unsigned long long n, 
            SnkHit* __restrict__ hits_aos, float4* __restrict__ hits_soa, uint32_t* __restrict__ inst_soa, float* __restrict__ vis_out) {
   __shared__ uint2 sm_stack[SHORT_STACK * TRACE_THREADS];
   const uint32_t lane = threadIdx.x & 31u;
-  const StackRef stk{sm_stack + threadIdx.x,
-                     S.spill + ((size_t)blockIdx.x * (TRACE_THREADS / 32) + (threadIdx.x >> 5)) * (SPILL_STACK * 32) + lane};
+  // world-space reciprocal direction / origin / direction and the closest hit's u, v, ids: the thread's cold state (traverse.cuh, COLD)
+  __shared__ float4 sm_world[4 * TRACE_THREADS];
+  StackRef stk{sm_stack + threadIdx.x,
+               S.spill + ((size_t)blockIdx.x * (TRACE_THREADS / 32) + (threadIdx.x >> 5)) * (SPILL_STACK * 32) + lane};
+  stk.world = sm_world + threadIdx.x;
   Trav t;
   bool active = false, exhausted = false;
   unsigned long long idx = 0;
@@ -67,7 +70,12 @@ k_trace_pt(TraceScene S, const float4* __restrict__ rays, unsigned long long n, 
         if (i < n) {
           const float4 a = __ldg(rays + 2 * i), b = __ldg(rays + 2 * i + 1);
           trav_begin(t, a, b);
-          if (b.w > a.w && S.tlas_node_count) { active = true; idx = i; }
+          if (b.w > a.w && S.tlas_node_count) {
+            active = true; idx = i;
+            sm_world[threadIdx.x] = make_float4(t.r.idx, t.r.idy, t.r.idz, __uint_as_float(t.r.octinv));
+            sm_world[TRACE_THREADS + threadIdx.x] = make_float4(a.x, a.y, a.z, 0.f);
+            sm_world[2 * TRACE_THREADS + threadIdx.x] = make_float4(b.x, b.y, b.z, 0.f);
+          }
           else write_result(i, t.best);
         }
       }
@@ -80,7 +88,16 @@ k_trace_pt(TraceScene S, const float4* __restrict__ rays, unsigned long long n, 
     // ---- traverse; the three phases are warp-synchronous (the ballots reconverge all 32 lanes per iteration)
     int lost = 0;
     while (true) {
-      if (trav_step<ANY, TRACE_THREADS>(S, t, stk, active, 0xFFFFFFFFu)) { write_result(idx, t.best); active = false; }
+      if (trav_step_impl<TRACE_THREADS, true, true>(S, t, stk, active, 0xFFFFFFFFu, ANY)) {
+        HitRec h;
+        h.t = t.best.t; h.u = 0.f; h.v = 0.f; h.prim = 0xFFFFFFFFu; h.inst = 0xFFFFFFFFu;
+        if (h.t >= 0.0f) {
+          const float4 b = sm_world[3 * TRACE_THREADS + threadIdx.x];
+          h.u = b.x; h.v = b.y; h.prim = __float_as_uint(b.z); h.inst = __float_as_uint(b.w);
+        }
+        write_result(idx, h);
+        active = false;
+      }
       const uint32_t live = __ballot_sync(0xFFFFFFFFu, active);
       if (live == 0u) break;
       if (!exhausted) {

@@ -32,6 +32,9 @@ constexpr int TQ_THREADS = 128;
 #ifndef SNK_TQ_CACHE_WORLD
 #define SNK_TQ_CACHE_WORLD 1  // world-space 1/d and octant kept in shared memory for leaving an instance: +1-2 % (profiles/r02r_variants_tri_reps_world_cache.txt)
 #endif
+#ifndef SNK_TQ_COLD
+#define SNK_TQ_COLD 1  // world-space ray + closest-hit ids in shared memory instead of registers (traverse.cuh, COLD): no spills around the node test
+#endif
 #ifndef SNK_TQ_REFILL_MIN
 #define SNK_TQ_REFILL_MIN 8  // idle lanes that trigger a refill
 #endif
@@ -41,7 +44,7 @@ k_trace_q(TraceScene S, TraceSegs segs, const uint32_t* __restrict__ refs, const
           uint32_t* __restrict__ ticket, float* __restrict__ prof_t) {
   __shared__ uint2 sm_stack[SHORT_STACK * TQ_THREADS];
 #if SNK_TQ_CACHE_WORLD
-  __shared__ float4 sm_world[TQ_THREADS];
+  __shared__ float4 sm_world[(SNK_TQ_COLD ? 4 : 1) * TQ_THREADS];
 #endif
   const uint32_t lane = threadIdx.x & 31u;
   StackRef stk{sm_stack + threadIdx.x,
@@ -84,6 +87,10 @@ k_trace_q(TraceScene S, TraceSegs segs, const uint32_t* __restrict__ refs, const
           trav_begin(t, a, b);
 #if SNK_TQ_CACHE_WORLD
           sm_world[threadIdx.x] = make_float4(t.r.idx, t.r.idy, t.r.idz, __uint_as_float(t.r.octinv));
+#if SNK_TQ_COLD
+          sm_world[TQ_THREADS + threadIdx.x] = make_float4(a.x, a.y, a.z, 0.f);
+          sm_world[2 * TQ_THREADS + threadIdx.x] = make_float4(b.x, b.y, b.z, 0.f);
+#endif
 #endif
           any = sg.any != 0u;
           qpos = q;
@@ -99,7 +106,7 @@ k_trace_q(TraceScene S, TraceSegs segs, const uint32_t* __restrict__ refs, const
 #if SNK_TQ_VOTE
     const bool finished = trav_vote_step<TQ_THREADS>(S, t, stk, active, any);
 #else
-    const bool finished = trav_step_impl<TQ_THREADS, SNK_TQ_CACHE_WORLD != 0>(S, t, stk, active, 0xFFFFFFFFu, any);
+    const bool finished = trav_step_impl<TQ_THREADS, SNK_TQ_CACHE_WORLD != 0, SNK_TQ_CACHE_WORLD != 0 && SNK_TQ_COLD != 0>(S, t, stk, active, 0xFFFFFFFFu, any);
 #endif
     if (finished) {
       const uint32_t ref = __ldg(refs + qpos);
@@ -108,8 +115,20 @@ k_trace_q(TraceScene S, TraceSegs segs, const uint32_t* __restrict__ refs, const
       if (any) {
         sg.vis[slot] = t.best.t >= 0.0f ? 0.0f : 1.0f;  // Shadow.rmiss:12 → 1 - float(hit)
       } else {
+#if SNK_TQ_CACHE_WORLD && SNK_TQ_COLD
+        float4 h = make_float4(-1.0f, 0.f, 0.f, __uint_as_float(0xFFFFFFFFu));
+        uint32_t hi = 0xFFFFFFFFu;
+        if (t.best.t >= 0.0f) {
+          const float4 b = sm_world[3 * TQ_THREADS + threadIdx.x];
+          h = make_float4(t.best.t, b.x, b.y, b.z);
+          hi = __float_as_uint(b.w);
+        }
+        sg.hit[slot] = h;
+        sg.inst[slot] = hi;
+#else
         sg.hit[slot] = make_float4(t.best.t, t.best.u, t.best.v, __uint_as_float(t.best.prim));
         sg.inst[slot] = t.best.inst;
+#endif
       }
       if (prof_t) prof_t[qpos] = t.best.t;
       active = false;

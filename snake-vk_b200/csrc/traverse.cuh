@@ -117,7 +117,17 @@ __device__ __forceinline__ void setup_ray_space(RaySpace& r, float ox, float oy,
 }
 
 // returns true when the line hits the triangle; (t,u,v) valid then. No range test.
-__device__ __forceinline__ bool tri_test(const RaySpace& r, float4 p0, float4 p1, float4 p2, float& t, float& u, float& v) {
+// DERIVE_K: kx / ky are recomputed from kz and the sign of the dominant direction component (the rule of setup_tri_space) instead
+// of being read from r — two registers less across the traversal loop for ~6 instructions per test; the same values.
+template <bool DERIVE_K = false>
+__device__ __forceinline__ bool tri_test(const RaySpace& r0, float4 p0, float4 p1, float4 p2, float& t, float& u, float& v) {
+  struct { float ox, oy, oz, Sx, Sy, Sz; int kx, ky, kz; } r = {r0.ox, r0.oy, r0.oz, r0.Sx, r0.Sy, r0.Sz, r0.kx, r0.ky, r0.kz};
+  if (DERIVE_K) {
+    int kx = r.kz + 1; if (kx == 3) kx = 0;
+    int ky = kx + 1; if (ky == 3) ky = 0;
+    if (sel3(r0.dx, r0.dy, r0.dz, r.kz) < 0.0f) { const int k = kx; kx = ky; ky = k; }
+    r.kx = kx; r.ky = ky;
+  }
   const float Ax0 = __fsub_rn(p0.x, r.ox), Ay0 = __fsub_rn(p0.y, r.oy), Az0 = __fsub_rn(p0.z, r.oz);
   const float Bx0 = __fsub_rn(p1.x, r.ox), By0 = __fsub_rn(p1.y, r.oy), Bz0 = __fsub_rn(p1.z, r.oz);
   const float Cx0 = __fsub_rn(p2.x, r.ox), Cy0 = __fsub_rn(p2.y, r.oy), Cz0 = __fsub_rn(p2.z, r.oz);
@@ -366,7 +376,11 @@ __device__ __forceinline__ void trav_begin(Trav& t, float4 a, float4 b) {
 //   4. pop phase: lanes with nothing pending pop the stack; popping below the instance-entry height returns
 //      to world space; an empty stack finishes the ray
 // Returns true when this lane's ray is finished (stack empty, or first hit for ANY).
-template <int STRIDE, bool CACHED_WORLD = false>
+// COLD (with CACHED_WORLD): the state a ray touches a few times in its life — the world-space origin and direction (needed again only
+// when it leaves an instance) and u, v, primitive, instance of its closest hit (written when a hit is accepted, read at the end and on
+// an exact distance tie) — lives in the thread's shared-memory column stk.world[1 .. 3] instead of ten registers: at 64 registers the
+// compiler otherwise spills nine values around the node test of EVERY iteration (9 STL + 9 LDL per node, profiles/r04r_k_trace_q.sass).
+template <int STRIDE, bool CACHED_WORLD = false, bool COLD = false>
 __device__ __forceinline__ bool trav_step_impl(const TraceScene& S, Trav& t, const StackRef& stk, bool active, uint32_t warp, const bool ANY) {
   // ---- 1
   uint32_t node_idx = 0;
@@ -378,20 +392,21 @@ __device__ __forceinline__ bool trav_step_impl(const TraceScene& S, Trav& t, con
       t.T.y &= ~(1u << bit);
       const uint32_t slot = __ldg(S.tlas_leaf_ids + t.T.x + bit);
       // instance culling: a ray that misses the bounding sphere skips the entry (this lane idles for the rest of the iteration)
-      if (!S.inst_sphere || ray_may_hit_sphere(__ldg(S.inst_sphere + slot), t.ox, t.oy, t.oz, t.dx, t.dy, t.dz, t.tcur)) {
+      if (!S.inst_sphere || ray_may_hit_sphere(__ldg(S.inst_sphere + slot), t.r.ox, t.r.oy, t.r.oz, t.r.dx, t.r.dy, t.r.dz, t.tcur)) {
       if (t.T.y) stk_push<STRIDE>(stk, t.sp, t.T, S.overflow);
       if (t.G.y & 0xFF000000u) stk_push<STRIDE>(stk, t.sp, t.G, S.overflow);
       t.blas_sp = t.sp;
       const float4* M = reinterpret_cast<const float4*>(S.inst + slot);
       const float4 r0 = __ldg(M), r1 = __ldg(M + 1), r2 = __ldg(M + 2);
       const uint4 meta = __ldg(reinterpret_cast<const uint4*>(M + 3));
-      // o' = ((m0*x + m1*y) + m2*z) + m3 ; d' = (m0*x + m1*y) + m2*z   (unfused, as the oracle)
-      const float oox = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0.x, t.ox), __fmul_rn(r0.y, t.oy)), __fmul_rn(r0.z, t.oz)), r0.w);
-      const float ooy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r1.x, t.ox), __fmul_rn(r1.y, t.oy)), __fmul_rn(r1.z, t.oz)), r1.w);
-      const float ooz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2.x, t.ox), __fmul_rn(r2.y, t.oy)), __fmul_rn(r2.z, t.oz)), r2.w);
-      const float odx = __fadd_rn(__fadd_rn(__fmul_rn(r0.x, t.dx), __fmul_rn(r0.y, t.dy)), __fmul_rn(r0.z, t.dz));
-      const float ody = __fadd_rn(__fadd_rn(__fmul_rn(r1.x, t.dx), __fmul_rn(r1.y, t.dy)), __fmul_rn(r1.z, t.dz));
-      const float odz = __fadd_rn(__fadd_rn(__fmul_rn(r2.x, t.dx), __fmul_rn(r2.y, t.dy)), __fmul_rn(r2.z, t.dz));
+      // o' = ((m0*x + m1*y) + m2*z) + m3 ; d' = (m0*x + m1*y) + m2*z   (unfused, as the oracle); in the TLAS t.r IS the world-space ray
+      const float wox = t.r.ox, woy = t.r.oy, woz = t.r.oz, wdx = t.r.dx, wdy = t.r.dy, wdz = t.r.dz;
+      const float oox = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0.x, wox), __fmul_rn(r0.y, woy)), __fmul_rn(r0.z, woz)), r0.w);
+      const float ooy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r1.x, wox), __fmul_rn(r1.y, woy)), __fmul_rn(r1.z, woz)), r1.w);
+      const float ooz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r2.x, wox), __fmul_rn(r2.y, woy)), __fmul_rn(r2.z, woz)), r2.w);
+      const float odx = __fadd_rn(__fadd_rn(__fmul_rn(r0.x, wdx), __fmul_rn(r0.y, wdy)), __fmul_rn(r0.z, wdz));
+      const float ody = __fadd_rn(__fadd_rn(__fmul_rn(r1.x, wdx), __fmul_rn(r1.y, wdy)), __fmul_rn(r1.z, wdz));
+      const float odz = __fadd_rn(__fadd_rn(__fmul_rn(r2.x, wdx), __fmul_rn(r2.y, wdy)), __fmul_rn(r2.z, wdz));
       setup_box_space(t.r, oox, ooy, ooz, odx, ody, odz);
       t.in_blas = true; t.tri_ready = false;
       t.cur_inst = meta.y;
@@ -440,16 +455,24 @@ __device__ __forceinline__ bool trav_step_impl(const TraceScene& S, Trav& t, con
       const float4* tp = S.tris + 3ull * (t.T.x + bit);
       const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
       float th, u, v;
-      if (tri_test(t.r, p0, p1, p2, th, u, v) && th > t.tmin) {
+      if (tri_test<COLD>(t.r, p0, p1, p2, th, u, v) && th > t.tmin) {
         // tcur == tmax until the first hit, afterwards the closest distance so far: a hit must be strictly inside
         // (tmin, tmax); at the current closest distance the lower (instance, primitive) wins
         const uint32_t prim = __float_as_uint(p0.w);
         bool take;
         if (ANY) take = th < t.tcur;
-        else take = th < t.tcur || (th == t.tcur && t.best.t >= 0.0f &&
-                                    (t.cur_inst < t.best.inst || (t.cur_inst == t.best.inst && prim < t.best.prim)));
+        else if (COLD) {
+          take = th < t.tcur;
+          if (th == t.tcur && t.best.t >= 0.0f) {  // exact tie with the closest hit so far (rare): its ids are in shared memory
+            const float4 b = stk.world[3 * STRIDE];
+            const uint32_t bprim = __float_as_uint(b.z), binst = __float_as_uint(b.w);
+            take = t.cur_inst < binst || (t.cur_inst == binst && prim < bprim);
+          }
+        } else take = th < t.tcur || (th == t.tcur && t.best.t >= 0.0f &&
+                                      (t.cur_inst < t.best.inst || (t.cur_inst == t.best.inst && prim < t.best.prim)));
         if (take) {
-          t.best.t = th; t.best.u = u; t.best.v = v; t.best.prim = prim; t.best.inst = t.cur_inst;
+          if (COLD) { t.best.t = th; stk.world[3 * STRIDE] = make_float4(u, v, __uint_as_float(prim), __uint_as_float(t.cur_inst)); }
+          else { t.best.t = th; t.best.u = u; t.best.v = v; t.best.prim = prim; t.best.inst = t.cur_inst; }
           t.tcur = th;
           done = ANY;
         }
@@ -464,7 +487,12 @@ __device__ __forceinline__ bool trav_step_impl(const TraceScene& S, Trav& t, con
       // cache the world-space constants in shared memory reload them instead of recomputing three reciprocals
       if (CACHED_WORLD) {
         const float4 w = *stk.world;
-        t.r.ox = t.ox; t.r.oy = t.oy; t.r.oz = t.oz; t.r.dx = t.dx; t.r.dy = t.dy; t.r.dz = t.dz;
+        if (COLD) {
+          const float4 wo = stk.world[STRIDE], wd = stk.world[2 * STRIDE];
+          t.r.ox = wo.x; t.r.oy = wo.y; t.r.oz = wo.z; t.r.dx = wd.x; t.r.dy = wd.y; t.r.dz = wd.z;
+        } else {
+          t.r.ox = t.ox; t.r.oy = t.oy; t.r.oz = t.oz; t.r.dx = t.dx; t.r.dy = t.dy; t.r.dz = t.dz;
+        }
         t.r.idx = w.x; t.r.idy = w.y; t.r.idz = w.z; t.r.octinv = __float_as_uint(w.w);
       } else {
         setup_box_space(t.r, t.ox, t.oy, t.oz, t.dx, t.dy, t.dz);
