@@ -18,10 +18,11 @@ namespace {
 
 constexpr int TQ_THREADS = 128;
 #ifndef SNK_TQ_CTAS
-#define SNK_TQ_CTAS 8
+#define SNK_TQ_CTAS 7  // 7 resident CTAs = 72 registers (8 B of spills left) instead of 8 = 64 registers: C2 frame 4.63 -> 4.58 ms, 1 M flat 6.23 -> 6.13 ms;
+                       // 6 CTAs (80 registers): 4.78 / 6.49 ms; 5 or 6 short-stack entries at 8 CTAs: 4.57 / 6.17 ms (profiles/r07h_variants_tq_occupancy.txt)
 #endif
 #ifndef SNK_TQ_GRID_CTAS
-#define SNK_TQ_GRID_CTAS 8  // CTAs per SM of the persistent grid. r04s (after instance culling): 5 / 6 / 7 / 8 CTAs give a C2 frame of
+#define SNK_TQ_GRID_CTAS SNK_TQ_CTAS  // (r04s, when 8 were resident:) CTAs per SM of the persistent grid. r04s (after instance culling): 5 / 6 / 7 / 8 CTAs give a C2 frame of
                             // 5.68 / 5.56 / 5.56 / 5.53 ms with the two chains overlapped and a kernel sum of 6.28 / 5.98 / 5.80 / 5.66 ms when
                             // every launch runs alone: a smaller grid leaves slots for the other chain's kernels, but a full grid is
                             // faster by about as much, so the full grid stays (profiles/r04s_variants_grid.txt)
