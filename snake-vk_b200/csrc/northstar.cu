@@ -202,7 +202,11 @@ __global__ void __launch_bounds__(128, 8) k_ns_gen(SceneDev D, FrameConsts fc, P
 // the hit of the ray that left vertex x_{b-1} becomes vertex x_b. One thread per path that is still alive (compact list
 // written by the previous stage): a path that ended keeps its last pending next-event term in C / vis, which k_ns_resolve
 // adds — the same sum, in the same order, as visiting the dead pixel here would give
-__global__ void __launch_bounds__(128, 6) k_ns_vertex(SceneDev D, FrameConsts fc, NsBuffers B, uint32_t npix, uint32_t b, uint32_t max_bounces,
+#ifndef SNK_NS_VERTEX_CTAS
+#define SNK_NS_VERTEX_CTAS 8  // 5 / 6 / 8 resident CTAs (96 / 80 / 64 registers, 52 B of spills at 64): vertex 1 0.215 / 0.189 / 0.170 ms on C2, 0.259 / 0.231 / 0.204 ms on C3
+                              // (profiles/r07l_variants_shading_occupancy.txt): the stage waits on dependent gathers (issue slots 38 % busy), more warps hide more
+#endif
+__global__ void __launch_bounds__(128, SNK_NS_VERTEX_CTAS) k_ns_vertex(SceneDev D, FrameConsts fc, NsBuffers B, uint32_t npix, uint32_t b, uint32_t max_bounces,
                                                    uint32_t nee_from, unsigned long long* counters, uint32_t* q_refs, uint32_t* q_count,
                                                    const uint32_t* paths_in, const uint32_t* paths_in_count, uint32_t* paths_out,
                                                    uint32_t* paths_out_count) {

@@ -208,7 +208,10 @@ __global__ void __launch_bounds__(128) k_build_em_table(SceneDev D, float4* __re
 }
 
 // ---- stage 1 ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 6) k_rs_initial(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, RsBuffers B, uint32_t npix,
+#ifndef SNK_RS_INITIAL_CTAS
+#define SNK_RS_INITIAL_CTAS 6  // 5 / 6 / 8: 0.279 / 0.254 / 0.236 ms on C2 but 1.335 / 1.272 / 1.410 ms on C3 (10 k emissive triangles; r07l): 6 stays
+#endif
+__global__ void __launch_bounds__(128, SNK_RS_INITIAL_CTAS) k_rs_initial(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, RsBuffers B, uint32_t npix,
                                                     unsigned long long* counters, uint32_t* q_refs, uint32_t* q_count) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long n_shadow = 0;
@@ -282,7 +285,10 @@ __global__ void __launch_bounds__(128, 6) k_rs_initial(SceneDev D, FrameConsts f
 }
 
 // ---- stage 2 ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 8) k_rs_temporal(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, RsBuffers B, uint32_t npix) {
+#ifndef SNK_RS_TEMPORAL_CTAS
+#define SNK_RS_TEMPORAL_CTAS 12  // 8 / 10 / 12 resident CTAs (64 / 48 / 40 registers): 0.108 / 0.097 / 0.095 ms on C2, 0.136 / 0.128 / 0.125 ms on C3 (r07m): DRAM-latency bound
+#endif
+__global__ void __launch_bounds__(128, SNK_RS_TEMPORAL_CTAS) k_rs_temporal(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, RsBuffers B, uint32_t npix) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t x, y; size_t px;
   if (!pixel_of(fc, i, x, y, px)) return;
@@ -346,7 +352,8 @@ constexpr int RS_MAXN = 9;  // this pixel + up to 8 neighbours
 #endif
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 #ifndef SNK_RS_SPATIAL_CTAS
-#define SNK_RS_SPATIAL_CTAS 6  // 5 / 6 / 8 resident CTAs (96 / 80 / 64 registers): 0.492 / 0.443 / 0.449 ms on C2 (profiles/r04t_variants_occupancy.txt)
+#define SNK_RS_SPATIAL_CTAS 8  // 5 / 6 / 8 resident CTAs (96 / 80 / 64 registers): 0.492 / 0.443 / 0.449 ms on C2 (profiles/r04t_variants_occupancy.txt);
+                               // after the helpers were inlined (r07l): 5 / 6 / 8 = 0.339 / 0.309 / 0.291 ms on C2, 0.524 / 0.517 / 0.507 ms on C3
 #endif
 // SNKPT_RT_UNBIASED_REUSE: the shadow rays of the MIS weights are the one place where a north-star shading stage traces inline
 // (warp-synchronous tracer of traverse.cuh, as the reference-mode passes do): up to 2 rays per accepted neighbour, each needed
@@ -490,7 +497,7 @@ __global__ void __launch_bounds__(128, 4) k_rs_spatial_unbiased(TraceScene S, Sc
 }
 
 #ifndef SNK_RS_FINAL_CTAS
-#define SNK_RS_FINAL_CTAS 6
+#define SNK_RS_FINAL_CTAS 8  // 6 / 8: 0.112 / 0.105 ms on C2, 0.145 / 0.137 ms on C3 (r07l)
 #endif
 // final contributions of the reservoir the spatial stage just stored, on the exact primary-hit surface. Its own kernel: together
 // with the reuse loops the stage needed 96 registers AND 190 local-memory spill instructions (cuobjdump, r02z).
