@@ -380,9 +380,14 @@ __device__ __forceinline__ void trav_begin(Trav& t, float4 a, float4 b) {
 // when it leaves an instance) and u, v, primitive, instance of its closest hit (written when a hit is accepted, read at the end and on
 // an exact distance tie) — lives in the thread's shared-memory column stk.world[1 .. 3] instead of ten registers: at 64 registers the
 // compiler otherwise spills nine values around the node test of EVERY iteration (9 STL + 9 LDL per node, profiles/r04r_k_trace_q.sass).
+#ifndef SNK_EARLY_NODE_LOAD
+#define SNK_EARLY_NODE_LOAD 0  // 1: the node is requested inside the pick branch, before the rest of the group is pushed — 20 more live registers there bring
+                                // the spills back: C2 4.41 -> 4.50 ms, reference mode 33.2 -> 35.8 ms (profiles/r07n_variants_load_order.txt)
+#endif
 template <int STRIDE, bool CACHED_WORLD = false, bool COLD = false>
 __device__ __forceinline__ bool trav_step_impl(const TraceScene& S, Trav& t, const StackRef& stk, bool active, uint32_t warp, const bool ANY) {
   // ---- 1
+  uint4 n0, n1, n2, n3, n4;
   uint32_t node_idx = 0;
   const uint4* nodes = S.blas_nodes;
   bool open = false;
@@ -393,12 +398,13 @@ __device__ __forceinline__ bool trav_step_impl(const TraceScene& S, Trav& t, con
       const uint32_t slot = __ldg(S.tlas_leaf_ids + t.T.x + bit);
       // instance culling: a ray that misses the bounding sphere skips the entry (this lane idles for the rest of the iteration)
       if (!S.inst_sphere || ray_may_hit_sphere(__ldg(S.inst_sphere + slot), t.r.ox, t.r.oy, t.r.oz, t.r.dx, t.r.dy, t.r.dz, t.tcur)) {
-      if (t.T.y) stk_push<STRIDE>(stk, t.sp, t.T, S.overflow);
-      if (t.G.y & 0xFF000000u) stk_push<STRIDE>(stk, t.sp, t.G, S.overflow);
-      t.blas_sp = t.sp;
+      // the instance record is requested before the (branchy) stack pushes so that its latency passes under them
       const float4* M = reinterpret_cast<const float4*>(S.inst + slot);
       const float4 r0 = __ldg(M), r1 = __ldg(M + 1), r2 = __ldg(M + 2);
       const uint4 meta = __ldg(reinterpret_cast<const uint4*>(M + 3));
+      if (t.T.y) stk_push<STRIDE>(stk, t.sp, t.T, S.overflow);
+      if (t.G.y & 0xFF000000u) stk_push<STRIDE>(stk, t.sp, t.G, S.overflow);
+      t.blas_sp = t.sp;
       // o' = ((m0*x + m1*y) + m2*z) + m3 ; d' = (m0*x + m1*y) + m2*z   (unfused, as the oracle); in the TLAS t.r IS the world-space ray
       const float wox = t.r.ox, woy = t.r.oy, woz = t.r.oz, wdx = t.r.dx, wdy = t.r.dy, wdz = t.r.dz;
       const float oox = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(r0.x, wox), __fmul_rn(r0.y, woy)), __fmul_rn(r0.z, woz)), r0.w);
@@ -410,25 +416,26 @@ __device__ __forceinline__ bool trav_step_impl(const TraceScene& S, Trav& t, con
       setup_box_space(t.r, oox, ooy, ooz, odx, ody, odz);
       t.in_blas = true; t.tri_ready = false;
       t.cur_inst = meta.y;
+      if (SNK_EARLY_NODE_LOAD) load_node(S.blas_nodes, meta.x, n0, n1, n2, n3, n4);
       node_idx = meta.x;
       open = true;
       }
     } else if (t.T.y == 0u && (t.G.y & 0xFF000000u) != 0u) {
       const uint32_t hits_imask = t.G.y;
       const uint32_t bit = 31u - __clz(hits_imask);
-      t.G.y &= ~(1u << bit);
-      if (t.G.y & 0xFF000000u) stk_push<STRIDE>(stk, t.sp, t.G, S.overflow);
       const uint32_t slot = (bit - 24u) ^ t.r.octinv;
       node_idx = t.G.x + __popc(hits_imask & ~(0xFFFFFFFFu << slot) & 0xFFu);
       nodes = t.in_blas ? S.blas_nodes : S.tlas_nodes;
+      if (SNK_EARLY_NODE_LOAD) load_node(nodes, node_idx, n0, n1, n2, n3, n4);
+      t.G.y &= ~(1u << bit);
+      if (t.G.y & 0xFF000000u) stk_push<STRIDE>(stk, t.sp, t.G, S.overflow);
       open = true;
     }
   }
   __syncwarp(warp);
   // ---- 2
   if (open) {
-    uint4 n0, n1, n2, n3, n4;
-    load_node(nodes, node_idx, n0, n1, n2, n3, n4);
+    if (!SNK_EARLY_NODE_LOAD) load_node(nodes, node_idx, n0, n1, n2, n3, n4);
     const uint32_t hm = intersect_node(t.r, n0, n1, n2, n3, n4, t.tmin, t.tcur);
     t.G = make_uint2(n1.x, (hm & 0xFF000000u) | (n0.w >> 24));
     t.T = make_uint2(n1.y, hm & 0x00FFFFFFu);
@@ -451,9 +458,11 @@ __device__ __forceinline__ bool trav_step_impl(const TraceScene& S, Trav& t, con
     if (go) {
       const uint32_t bit = __ffs(t.T.y) - 1;
       t.T.y &= ~(1u << bit);
-      if (!t.tri_ready) { setup_tri_space(t.r); t.tri_ready = true; }
+      // the record is requested before the (divergent, three-division) Woop setup of the lanes that test their first triangle in this
+      // instance, so that its latency passes under the setup instead of after it
       const float4* tp = S.tris + 3ull * (t.T.x + bit);
       const float4 p0 = __ldg(tp), p1 = __ldg(tp + 1), p2 = __ldg(tp + 2);
+      if (!t.tri_ready) { setup_tri_space(t.r); t.tri_ready = true; }
       float th, u, v;
       if (tri_test<COLD>(t.r, p0, p1, p2, th, u, v) && th > t.tmin) {
         // tcur == tmax until the first hit, afterwards the closest distance so far: a hit must be strictly inside
