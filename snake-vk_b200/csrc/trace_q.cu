@@ -36,6 +36,10 @@ constexpr int TQ_THREADS = 128;
 #ifndef SNK_TQ_COLD
 #define SNK_TQ_COLD 1  // world-space ray + closest-hit ids in shared memory instead of registers (traverse.cuh, COLD): no spills around the node test
 #endif
+#ifndef SNK_TQ_BATCH
+#define SNK_TQ_BATCH 0  // 1: queue entries reserved 32 at a time, their references prefetched into registers (one memory round trip per refill instead
+                        // of three) — measured slower: C2 4.41 -> 4.53 ms, 1 M flat 5.92 -> 6.15 ms (three more live registers, 12 B of spills; profiles/r07o_variants_refill_batch.txt)
+#endif
 #ifndef SNK_TQ_REFILL_MIN
 #define SNK_TQ_REFILL_MIN 8  // idle lanes that trigger a refill
 #endif
@@ -70,10 +74,52 @@ k_trace_q(TraceScene S, TraceSegs segs, const uint32_t* __restrict__ refs, const
   Trav t;
   bool active = false, exhausted = false, any = false;
   uint32_t qpos = 0;
+#if SNK_TQ_BATCH
+  uint32_t res_next = 0, res_end = 0, ref_cache = 0;
+#endif
   while (true) {
     // ---- refill: lanes without a ray take the next queue entries (one atomic per warp)
     const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);
     if (!exhausted && __popc(idle) >= SNK_TQ_REFILL_MIN) {
+#if SNK_TQ_BATCH
+      // the warp reserves 32 queue entries at a time and keeps their references in registers (lane i: entry res_end - 32 + i): a refill
+      // then waits for ONE memory round trip (the ray) instead of three in a row (ticket atomic, reference, ray)
+      uint32_t need = idle;
+#pragma unroll 1
+      for (int round = 0; round < 2 && need != 0u; ++round) {
+        if (res_next == res_end) {
+          uint32_t base = 0;
+          if (lane == 0) base = atomicAdd(ticket, 32u);
+          base = __shfl_sync(0xFFFFFFFFu, base, 0);
+          if (base >= n) { exhausted = true; break; }
+          res_next = base; res_end = base + 32u;
+          ref_cache = base + lane < n ? __ldg(refs + base + lane) : 0u;
+        }
+        const uint32_t avail = res_end - res_next, rank = __popc(need & ((1u << lane) - 1u));
+        const bool take = ((need >> lane) & 1u) != 0u && rank < avail;
+        const uint32_t q = res_next + rank;
+        const uint32_t ref = __shfl_sync(0xFFFFFFFFu, ref_cache, (q - res_end) & 31u);  // entry q sits in lane q - (res_end - 32)
+        if (take && q < n) {
+          const TraceSeg& sg = segs.s[ref >> REF_SLOT_BITS];
+          const float4* rp = sg.rays + 2ull * (ref & REF_SLOT_MASK);
+          const float4 a = __ldcg(rp), b = __ldcg(rp + 1);
+          trav_begin(t, a, b);
+#if SNK_TQ_CACHE_WORLD
+          sm_world[threadIdx.x] = make_float4(t.r.idx, t.r.idy, t.r.idz, __uint_as_float(t.r.octinv));
+#if SNK_TQ_COLD
+          sm_world[TQ_THREADS + threadIdx.x] = make_float4(a.x, a.y, a.z, 0.f);
+          sm_world[2 * TQ_THREADS + threadIdx.x] = make_float4(b.x, b.y, b.z, 0.f);
+#endif
+#endif
+          any = sg.any != 0u;
+          qpos = q;
+          active = true;  // the producers only queue live rays (tmax > tmin)
+        }
+        const uint32_t taken = __ballot_sync(0xFFFFFFFFu, take);
+        res_next += __popc(taken);
+        need &= ~taken;
+      }
+#else
       const uint32_t cnt = __popc(idle);
       uint32_t base = 0;
       if (lane == 0) base = atomicAdd(ticket, cnt);
@@ -99,6 +145,7 @@ k_trace_q(TraceScene S, TraceSegs segs, const uint32_t* __restrict__ refs, const
         }
       }
       if (base + cnt >= n) exhausted = true;
+#endif
     }
     if (__ballot_sync(0xFFFFFFFFu, active) == 0u) {
       if (exhausted) break;
