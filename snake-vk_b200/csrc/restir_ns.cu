@@ -211,7 +211,13 @@ __global__ void __launch_bounds__(128) k_build_em_table(SceneDev D, float4* __re
 #ifndef SNK_RS_INITIAL_CTAS
 #define SNK_RS_INITIAL_CTAS 6  // 5 / 6 / 8: 0.279 / 0.254 / 0.236 ms on C2 but 1.335 / 1.272 / 1.410 ms on C3 (10 k emissive triangles; r07l): 6 stays
 #endif
-__global__ void __launch_bounds__(128, SNK_RS_INITIAL_CTAS) k_rs_initial(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, RsBuffers B, uint32_t npix,
+// HAS_EM = false: the build for scenes without emissive triangles — the emissive candidate loop is compiled out and the kernel runs at
+// SNK_RS_INITIAL_CTAS_PL resident CTAs (the point-light loop alone gains from more warps, the emissive loop loses: r07l)
+#ifndef SNK_RS_INITIAL_CTAS_PL
+#define SNK_RS_INITIAL_CTAS_PL 8
+#endif
+template <bool HAS_EM>
+__global__ void __launch_bounds__(128, HAS_EM ? SNK_RS_INITIAL_CTAS : SNK_RS_INITIAL_CTAS_PL) k_rs_initial(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, RsBuffers B, uint32_t npix,
                                                     unsigned long long* counters, uint32_t* q_refs, uint32_t* q_count) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   unsigned long long n_shadow = 0;
@@ -222,7 +228,7 @@ __global__ void __launch_bounds__(128, SNK_RS_INITIAL_CTAS) k_rs_initial(SceneDe
     const size_t np = rp.npix_frame;
     Reservoir r; rs_empty(r);
     float p_sel_pl = 0.0f, p_sel_em = 0.0f;
-    const uint32_t n_pl = D.lights->num_pointlights, n_em = D.num_emissive;
+    const uint32_t n_pl = D.lights->num_pointlights, n_em = HAS_EM ? D.num_emissive : 0u;
     if (px_shaded(P, px)) {
       RsSurf s; vec3 pos, n_raw;
       rs_gsurf(fc, P, x, y, s, pos, n_raw);
@@ -288,6 +294,9 @@ __global__ void __launch_bounds__(128, SNK_RS_INITIAL_CTAS) k_rs_initial(SceneDe
 #ifndef SNK_RS_TEMPORAL_CTAS
 #define SNK_RS_TEMPORAL_CTAS 12  // 8 / 10 / 12 resident CTAs (64 / 48 / 40 registers): 0.108 / 0.097 / 0.095 ms on C2, 0.136 / 0.128 / 0.125 ms on C3 (r07m): DRAM-latency bound
 #endif
+// HAS_EM = false (here and in the spatial / final stages): build for scenes without emissive triangles — the emissive-reservoir work is
+// compiled out (the M bookkeeping stays: the reservoirs are bit-identical), which frees registers in stages that wait on gathers
+template <bool HAS_EM>
 __global__ void __launch_bounds__(128, SNK_RS_TEMPORAL_CTAS) k_rs_temporal(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, RsBuffers B, uint32_t npix) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t x, y; size_t px;
@@ -302,7 +311,7 @@ __global__ void __launch_bounds__(128, SNK_RS_TEMPORAL_CTAS) k_rs_temporal(Scene
   float p_pl = ph0.x, p_em = ph0.y;
   const uint32_t n_pl = D.lights->num_pointlights;
   if (n_pl > 0 && B.vis[px] == 0.0f) { r.w_sum_pl = 0.0f; r.w_pl = 0.0f; }
-  if (D.num_emissive > 0 && B.vis[np + px] == 0.0f) { r.w_sum_em = 0.0f; r.w_em = 0.0f; }
+  if (HAS_EM && D.num_emissive > 0 && B.vis[np + px] == 0.0f) { r.w_sum_em = 0.0f; r.w_em = 0.0f; }
   if (rp.history_ok && rp.num_temporal != 0) {
     const ushort2 mv = P.motion[px];
     const float hx = ((float)x + 0.5f) / (float)fc.W + h2f(mv.x), hy = ((float)y + 0.5f) / (float)fc.H + h2f(mv.y);
@@ -328,7 +337,7 @@ __global__ void __launch_bounds__(128, SNK_RS_TEMPORAL_CTAS) k_rs_temporal(Scene
           if (w > 0.0f && rs_rand(h0, RS_DIM_TEMPORAL) * r.w_sum_pl < w) { r.pl_idx = h.pl_idx; p_pl = ph; }
         }
         r.pl_m += h.pl_m;
-        if (rs_em_valid(D, h.obj, h.tri)) {
+        if (HAS_EM && rs_em_valid(D, h.obj, h.tri)) {
           const NsSurf q = ns_surface_em(D, h.obj, h.tri, h.bx, h.by);
           const float ph = rs_phat(rs_eval_em_reuse(s, q));
           const float w = (ph * h.w_em) * (float)h.m_em;
@@ -367,7 +376,7 @@ struct RsTracer {
   }
 };
 
-template <bool UNBIASED>
+template <bool UNBIASED, bool HAS_EM>
 __device__ __forceinline__ void rs_spatial_thread(const SceneDev& D, const FrameConsts& fc, const PixelPlanes& P, const RsParams& rp, uint32_t i,
                                                   const RsTracer& T, unsigned long long& n_mis) {
   size_t px = 0;
@@ -424,7 +433,7 @@ __device__ __forceinline__ void rs_spatial_thread(const SceneDev& D, const Frame
           if (w > 0.0f && rs_rand(h0, RS_DIM_SPATIAL + 0x100u + 2u * (uint32_t)j) * out.w_sum_pl < w) { out.pl_idx = c.pl_idx; p_pl = ph; src_pl = j; }
         }
         out.pl_m += c.pl_m;
-        if (rs_em_valid(D, c.obj, c.tri)) {
+        if (HAS_EM && rs_em_valid(D, c.obj, c.tri)) {
           const NsSurf q = ns_surface_em(D, c.obj, c.tri, c.bx, c.by);
           const float ph = rs_phat(rs_eval_em_reuse(s, q));
           const float w = (ph * c.w_em) * (float)c.m_em;
@@ -478,9 +487,10 @@ __device__ __forceinline__ void rs_spatial_thread(const SceneDev& D, const Frame
   }
 }
 
+template <bool HAS_EM>
 __global__ void __launch_bounds__(128, SNK_RS_SPATIAL_CTAS) k_rs_spatial(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, uint32_t npix) {
   unsigned long long n_mis = 0;
-  rs_spatial_thread<false>(D, fc, P, rp, blockIdx.x * blockDim.x + threadIdx.x, RsTracer{nullptr, nullptr, nullptr}, n_mis);
+  rs_spatial_thread<false, HAS_EM>(D, fc, P, rp, blockIdx.x * blockDim.x + threadIdx.x, RsTracer{nullptr, nullptr, nullptr}, n_mis);
 }
 
 // unbiased reuse: persistent CTAs (the global spill area of the inline tracer is sized for resident grids, trace.cu:trace_spill_bytes)
@@ -492,7 +502,7 @@ __global__ void __launch_bounds__(128, 4) k_rs_spatial_unbiased(TraceScene S, Sc
   __syncthreads();
   const RsTracer T{&sS, sm_stack + threadIdx.x, S.spill + ((size_t)blockIdx.x * 4 + (threadIdx.x >> 5)) * (SPILL_STACK * 32) + (threadIdx.x & 31u)};
   unsigned long long n_mis = 0;
-  for (uint32_t base = blockIdx.x * 128u; base < nthreads; base += gridDim.x * 128u) rs_spatial_thread<true>(D, fc, P, rp, base + threadIdx.x, T, n_mis);
+  for (uint32_t base = blockIdx.x * 128u; base < nthreads; base += gridDim.x * 128u) rs_spatial_thread<true, true>(D, fc, P, rp, base + threadIdx.x, T, n_mis);
   flush_counts(n_mis, 0ull, counters);
 }
 
@@ -501,6 +511,7 @@ __global__ void __launch_bounds__(128, 4) k_rs_spatial_unbiased(TraceScene S, Sc
 #endif
 // final contributions of the reservoir the spatial stage just stored, on the exact primary-hit surface. Its own kernel: together
 // with the reuse loops the stage needed 96 registers AND 190 local-memory spill instructions (cuobjdump, r02z).
+template <bool HAS_EM>
 __global__ void __launch_bounds__(128, SNK_RS_FINAL_CTAS) k_rs_final(SceneDev D, FrameConsts fc, PixelPlanes P, RsParams rp, RsBuffers B, uint32_t npix,
                                                                      unsigned long long* counters, uint32_t* q_refs, uint32_t* q_count, uint32_t dir_packet) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -528,7 +539,7 @@ __global__ void __launch_bounds__(128, SNK_RS_FINAL_CTAS) k_rs_final(SceneDev D,
           ray0 = true; ++n_shadow;
         }
       }
-      if (out.obj != INVALID_IDX && out.w_em > 0.0f) {
+      if (HAS_EM && out.obj != INVALID_IDX && out.w_em > 0.0f) {
         const NsSurf q = ns_surface_em(D, out.obj, out.tri, out.bx, out.by);
         const RsEval e = rs_eval_em_reuse(xs, q);
         if (e.tmax > 0.0f) {
@@ -656,7 +667,10 @@ int restir_ns_initial(SnkPt* ctx, const SnkRtSettings& s, const RefQueue& q, cud
   const RsLaunch L = rs_launch(ctx, s);
   unsigned long long* counters = reinterpret_cast<unsigned long long*>(ctx->dev_counters.as<uint32_t>() + 2);
   const int rec = prof_begin(ctx, "rs_initial", L.npix1, false, false, st);
-  k_rs_initial<<<(stage_threads(L.f1.W, L.f1.row1 - L.f1.row0) + 127) / 128, 128, 0, st>>>(ctx->scene_dev(), L.f1, ctx->planes, L.rp, L.B, L.npix1, counters, q.refs, q.count);
+  const SceneDev D = ctx->scene_dev();
+  const uint32_t grid = (stage_threads(L.f1.W, L.f1.row1 - L.f1.row0) + 127) / 128;
+  if (D.num_emissive) k_rs_initial<true><<<grid, 128, 0, st>>>(D, L.f1, ctx->planes, L.rp, L.B, L.npix1, counters, q.refs, q.count);
+  else k_rs_initial<false><<<grid, 128, 0, st>>>(D, L.f1, ctx->planes, L.rp, L.B, L.npix1, counters, q.refs, q.count);
   prof_end(ctx, rec, st);
   return 1;
 }
@@ -668,7 +682,8 @@ int restir_ns_reuse(SnkPt* ctx, const SnkRtSettings& s, const RefQueue& q, cudaS
   unsigned long long* counters = reinterpret_cast<unsigned long long*>(ctx->dev_counters.as<uint32_t>() + 2);
   const SceneDev D = ctx->scene_dev();
   int rec = prof_begin(ctx, "rs_temporal", L.npix1, false, false, st);
-  k_rs_temporal<<<(stage_threads(L.f1.W, L.f1.row1 - L.f1.row0) + 127) / 128, 128, 0, st>>>(D, L.f1, ctx->planes, L.rp, L.B, L.npix1);
+  if (D.num_emissive) k_rs_temporal<true><<<(stage_threads(L.f1.W, L.f1.row1 - L.f1.row0) + 127) / 128, 128, 0, st>>>(D, L.f1, ctx->planes, L.rp, L.B, L.npix1);
+  else k_rs_temporal<false><<<(stage_threads(L.f1.W, L.f1.row1 - L.f1.row0) + 127) / 128, 128, 0, st>>>(D, L.f1, ctx->planes, L.rp, L.B, L.npix1);
   prof_end(ctx, rec, st);
   cudaEventRecord(ctx->ev[3], st);
   // row-band group: the neighbours' temporal reservoirs of the rows spatial reuse can reach arrive here ...
@@ -681,7 +696,8 @@ int restir_ns_reuse(SnkPt* ctx, const SnkRtSettings& s, const RefQueue& q, cudaS
     const uint32_t resident = (uint32_t)device_sm_count() * 4u, want = (sp_threads + 127u) / 128u;
     k_rs_spatial_unbiased<<<want < resident ? want : resident, 128, 0, st>>>(S, D, ctx->fc, ctx->planes, L.rp, sp_threads, counters);
   } else {
-    k_rs_spatial<<<(sp_threads + 127) / 128, 128, 0, st>>>(D, ctx->fc, ctx->planes, L.rp, L.npix);
+    if (D.num_emissive) k_rs_spatial<true><<<(sp_threads + 127) / 128, 128, 0, st>>>(D, ctx->fc, ctx->planes, L.rp, L.npix);
+    else k_rs_spatial<false><<<(sp_threads + 127) / 128, 128, 0, st>>>(D, ctx->fc, ctx->planes, L.rp, L.npix);
   }
   prof_end(ctx, rec, st);
   // ... and the final reservoirs the next frame's temporal reuse may reproject to leave as soon as they exist
@@ -693,8 +709,9 @@ int restir_ns_reuse(SnkPt* ctx, const SnkRtSettings& s, const RefQueue& q, cudaS
   // volume is wide, and an any-hit ray is cheap on its own (8 nodes); C4 at 4K: 0.68 vs 0.79 ms, within noise of the frame.
   static const bool dir_packet_env = getenv("SNKPT_SHADOW_DIR") && getenv("SNKPT_SHADOW_DIR")[0] == 'p';
   const bool dir_packet = ctx->has_dir_light && dir_packet_env;
-  k_rs_final<<<(stage_threads(ctx->fc.W, ctx->fc.row1 - ctx->fc.row0) + 127) / 128, 128, 0, st>>>(D, ctx->fc, ctx->planes, L.rp, L.B, L.npix, counters, q.refs, q.count,
-                                                                                                   dir_packet ? 1u : 0u);
+  const uint32_t fin_grid = (stage_threads(ctx->fc.W, ctx->fc.row1 - ctx->fc.row0) + 127) / 128;
+  if (D.num_emissive) k_rs_final<true><<<fin_grid, 128, 0, st>>>(D, ctx->fc, ctx->planes, L.rp, L.B, L.npix, counters, q.refs, q.count, dir_packet ? 1u : 0u);
+  else k_rs_final<false><<<fin_grid, 128, 0, st>>>(D, ctx->fc, ctx->planes, L.rp, L.B, L.npix, counters, q.refs, q.count, dir_packet ? 1u : 0u);
   prof_end(ctx, rec, st);
   if (dir_packet) {
     rec = prof_begin(ctx, "shadow.dir", L.npix, false, false, st);
