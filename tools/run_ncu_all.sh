@@ -11,7 +11,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_c
   -s 13 -c 16 -f -o /tmp/ncu/prof_build env ONLY=1e7 python tools/build_sweep.py 10000000 > $OUT/ncu_build.log 2>&1; echo "ncu build rc=$?"
 python tools/ncu_digest.py /tmp/ncu/prof_build.ncu-rep $OUT/prof_build.txt 20
 for k in k_trace_q k_primary_packet k_rs_initial k_rs_spatial k_rs_final k_ns_vertex k_build_small k_collapse k_sweep_pass k_refit_binary_chunked k_refit_nodes8; do
-  cuobjdump -sass -fun $(cuobjdump -elf snake-vk_b200/libsnkpt.so 2>/dev/null | grep -o "_ZN3snk[A-Za-z0-9_]*${k}E[A-Za-z0-9_]*" | sort -u | head -1) snake-vk_b200/libsnkpt.so 2>/dev/null | grep -E "^\s+/\*[0-9a-f]{4}\*/" | sed 's#/\* 0x[0-9a-f]* \*/##' > $OUT/$k.sass
+  cuobjdump -sass -fun $(cuobjdump -elf snake-vk_b200/libsnkpt.so 2>/dev/null | grep -o "_ZN3snk[A-Za-z0-9_]*${k}[EI][A-Za-z0-9_]*" | sort -u | head -1) snake-vk_b200/libsnkpt.so 2>/dev/null | grep -E "^\s+/\*[0-9a-f]{4}\*/" | sed 's#/\* 0x[0-9a-f]* \*/##' > $OUT/$k.sass
   echo "$k: $(wc -l < $OUT/$k.sass) SASS lines"
 done
 ls -la $OUT; du -sh $OUT
