@@ -387,10 +387,12 @@ void snkpt_destroy(SnkPt* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->tlas_stream) { cudaStreamSynchronize(ctx->tlas_stream); cudaStreamDestroy(ctx->tlas_stream); ctx->tlas_stream = nullptr; }
+  for (cudaEvent_t* e : {&ctx->ev_tlas_prev[0], &ctx->ev_tlas_prev[1], &ctx->ev_tlas_built, &ctx->ev_tlas_sync}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
   DevBuf* bufs[] = {&ctx->positions, &ctx->normals, &ctx->tangents, &ctx->uvs, &ctx->indices, &ctx->blas_nodes, &ctx->blas_tris,
                     &ctx->d_blas, &ctx->materials, &ctx->lights, &ctx->transforms, &ctx->prev_transforms, &ctx->normal_mats,
                     &ctx->det3, &ctx->instances, &ctx->blas_of_instance, &ctx->emissive_idx, &ctx->tlas_nodes, &ctx->tlas_leaf_ids,
-                    &ctx->inst_recs, &ctx->inst_sphere, &ctx->valid_slots, &ctx->tlas_stage, &ctx->q_rays, &ctx->q_hits, &ctx->q_work, &ctx->dev_counters, &ctx->trav_spill,
+                    &ctx->inst_recs, &ctx->inst_sphere, &ctx->valid_slots, &ctx->tlas_stage, &ctx->tlas_nodes_alt, &ctx->tlas_leaf_ids_alt, &ctx->tlas_stage_alt, &ctx->q_rays, &ctx->q_hits, &ctx->q_work, &ctx->dev_counters, &ctx->trav_spill,
                     &ctx->wave_refs, &ctx->wave_paths, &ctx->prof_work, &ctx->prof_hits, &ctx->em_table, &ctx->em_base_of_obj, &ctx->em_base, &ctx->tex_table, &ctx->srgb_lut};
   for (auto& b : ctx->tex_data) b.release();
   for (DevBuf* b : bufs) b->release();
@@ -546,6 +548,7 @@ int snkpt_upload_mesh(SnkPt* ctx, const float* positions, const float* normals, 
                       uint32_t num_vertices, const uint32_t* indices, uint32_t num_indices, const SnkSubmesh* submeshes,
                       uint32_t num_submeshes, SnkMeshEntry* out_entry, void* stream) {
   if (!ctx) return SNKPT_E_INVALID;
+  ++ctx->scene_epoch;  // the next TLAS rebuild must be ordered after this call's device work (snkpt_build_tlas)
   REQUIRE(positions && indices && submeshes && out_entry, SNKPT_E_INVALID, "snkpt_upload_mesh: null argument");
   REQUIRE(num_submeshes >= 1 && num_submeshes <= SNKPT_MAX_SUBMESHES, SNKPT_E_INVALID, "snkpt_upload_mesh: submesh count");
   REQUIRE(num_indices % 3 == 0, SNKPT_E_INVALID, "snkpt_upload_mesh: indices not a multiple of 3");
@@ -599,6 +602,7 @@ int snkpt_upload_mesh(SnkPt* ctx, const float* positions, const float* normals, 
 
 int snkpt_update_positions(SnkPt* ctx, const SnkMeshEntry* entry, const float* positions, uint32_t num_vertices) {
   if (!ctx) return SNKPT_E_INVALID;
+  ++ctx->scene_epoch;  // the next TLAS rebuild must be ordered after this call's device work (snkpt_build_tlas)
   REQUIRE(entry && positions, SNKPT_E_INVALID, "snkpt_update_positions: null argument");
   REQUIRE((uint64_t)entry->data_start_vertex_idx + num_vertices <= ctx->num_vertices, SNKPT_E_INVALID, "snkpt_update_positions: range");
   CK(cudaSetDevice(ctx->device));
@@ -619,6 +623,7 @@ int snkpt_update_positions(SnkPt* ctx, const SnkMeshEntry* entry, const float* p
 
 int snkpt_rebuild_blas(SnkPt* ctx, uint32_t blas_id, void* stream) {
   if (!ctx) return SNKPT_E_INVALID;
+  ++ctx->scene_epoch;  // the next TLAS rebuild must be ordered after this call's device work (snkpt_build_tlas)
   REQUIRE(blas_id < ctx->blas.size(), SNKPT_E_INVALID, "snkpt_rebuild_blas: bad id");
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
@@ -639,6 +644,7 @@ int snkpt_rebuild_blas(SnkPt* ctx, uint32_t blas_id, void* stream) {
 
 int snkpt_refit_blas(SnkPt* ctx, uint32_t blas_id, void* stream) {
   if (!ctx) return SNKPT_E_INVALID;
+  ++ctx->scene_epoch;  // the next TLAS rebuild must be ordered after this call's device work (snkpt_build_tlas)
   REQUIRE(blas_id < ctx->blas.size(), SNKPT_E_INVALID, "snkpt_refit_blas: bad id");
   CK(cudaSetDevice(ctx->device));
   cudaStream_t st = stream ? (cudaStream_t)stream : ctx->stream;
@@ -726,6 +732,7 @@ int snkpt_set_lights(SnkPt* ctx, const void* light_data, size_t bytes) {
 
 int snkpt_set_transforms(SnkPt* ctx, const float* cur, const float* prev, uint32_t first, uint32_t count) {
   if (!ctx) return SNKPT_E_INVALID;
+  ++ctx->scene_epoch;  // the next TLAS rebuild must be ordered after this call's device work (snkpt_build_tlas)
   REQUIRE(cur && (uint64_t)first + count <= ctx->max_transforms, SNKPT_E_INVALID, "snkpt_set_transforms: range");
   CK(cudaSetDevice(ctx->device));
   const size_t need = (size_t)first + count;
@@ -750,6 +757,7 @@ int snkpt_set_transforms(SnkPt* ctx, const float* cur, const float* prev, uint32
 int snkpt_set_instances(SnkPt* ctx, const SnkInstanceData* instances, const uint32_t* blas_of_instance, uint32_t count,
                         const uint32_t* emissive_idx, uint32_t num_emissive) {
   if (!ctx) return SNKPT_E_INVALID;
+  ++ctx->scene_epoch;  // the next TLAS rebuild must be ordered after this call's device work (snkpt_build_tlas)
   REQUIRE(count <= ctx->max_instances && num_emissive <= ctx->max_instances, SNKPT_E_INVALID, "snkpt_set_instances: capacity (4096 by default)");
   REQUIRE((instances && blas_of_instance) || count == 0, SNKPT_E_INVALID, "snkpt_set_instances: null argument");
   for (uint32_t i = 0; i < count; ++i) {
@@ -855,35 +863,62 @@ int snkpt_build_tlas(SnkPt* ctx, void* stream) {
     if (cull_instances && b < ctx->blas_sphere.size()) world_sphere(ctx->h_transforms.data() + 16 * (size_t)t, ctx->blas_sphere[b], spheres + 4 * (size_t)i);
     valid[n++] = i;
   }
+  // The rebuild writes the copy of the TLAS storage that the frame BEFORE the one in flight read, on its own stream: it waits for
+  // everything enqueued before the previous rebuild call (the last readers of that copy) and — when the scene was changed since —
+  // for the caller's stream as it stands, but not for the frame in flight; the caller's stream then waits for the rebuild.
+  // A 40-us single-CTA kernel (+ its upload) no longer sits between two frames. SNKPT_TLAS_EARLY=0 restores the in-order rebuild.
+  static const bool early_env = !(getenv("SNKPT_TLAS_EARLY") && getenv("SNKPT_TLAS_EARLY")[0] == '0');
+  if (!ctx->tlas_stream) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    CK(cudaStreamCreateWithPriority(&ctx->tlas_stream, cudaStreamNonBlocking, hi));
+    for (cudaEvent_t* e : {&ctx->ev_tlas_prev[0], &ctx->ev_tlas_prev[1], &ctx->ev_tlas_built, &ctx->ev_tlas_sync}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  }
+  std::swap(ctx->tlas_nodes, ctx->tlas_nodes_alt);
+  std::swap(ctx->tlas_leaf_ids, ctx->tlas_leaf_ids_alt);
+  std::swap(ctx->tlas_stage, ctx->tlas_stage_alt);
+  cudaStream_t bs = ctx->tlas_stream;
+  const uint32_t k = ctx->tlas_builds++;
+  const bool early = early_env && k >= 2 && ctx->tlas_epoch == ctx->scene_epoch && !ctx->profiling;
+  if (early) {
+    CK(cudaStreamWaitEvent(bs, ctx->ev_tlas_prev[(k + 1) & 1], 0));  // recorded at the previous rebuild call: frames <= f-1 are behind it
+  } else {
+    CK(cudaEventRecord(ctx->ev_tlas_sync, st));                      // in order with everything the caller enqueued so far
+    CK(cudaStreamWaitEvent(bs, ctx->ev_tlas_sync, 0));
+  }
+  ctx->tlas_epoch = ctx->scene_epoch;
+  CK(cudaEventRecord(ctx->ev_tlas_prev[k & 1], st));  // before this frame's consumers are enqueued
   // device copy of the staging block, same layout; inst_recs / inst_sphere / valid_slots are views into it
-  CK(ctx->tlas_stage.reserve(need, false, st));
+  CK(ctx->tlas_stage.reserve(need, false, bs));
   {
     char* base = static_cast<char*>(ctx->tlas_stage.p);
     ctx->inst_recs.alias(base, sizeof(SnkInstRec) * ni);
     ctx->inst_sphere.alias(base + sizeof(SnkInstRec) * ni, 16 * ni);
     ctx->valid_slots.alias(base + (sizeof(SnkInstRec) + 16) * ni, 4 * ni);
   }
-  CK(ctx->tlas_nodes.reserve(sizeof(SnkNode8) * (size_t)(ctx->max_instances + 1), false, st));
-  CK(ctx->tlas_leaf_ids.reserve(4 * (size_t)(ctx->max_instances + 1), false, st));
+  CK(ctx->tlas_nodes.reserve(sizeof(SnkNode8) * (size_t)(ctx->max_instances + 1), false, bs));
+  CK(ctx->tlas_leaf_ids.reserve(4 * (size_t)(ctx->max_instances + 1), false, bs));
   CK(scratch_reserve(ctx->scratch_tlas, ctx->max_instances));
   ctx->tlas_prims = n;
   ctx->tlas_built = true;
   if (n == 0) return SNKPT_OK;
-  cudaEventRecord(ctx->ev[6], st);
-  CK(cudaMemcpyAsync(ctx->tlas_stage.p, ctx->h_stage, (sizeof(SnkInstRec) + 16 + 4) * ni, cudaMemcpyHostToDevice, st));
-  CK(cudaEventRecord(ctx->ev_stage, st));
+  cudaEventRecord(ctx->ev[6], bs);
+  CK(cudaMemcpyAsync(ctx->tlas_stage.p, ctx->h_stage, (sizeof(SnkInstRec) + 16 + 4) * ni, cudaMemcpyHostToDevice, bs));
+  CK(cudaEventRecord(ctx->ev_stage, bs));
   ctx->stage_in_flight = true;
   BuildScratch& s = ctx->scratch_tlas;
   launch_instance_bounds(s, ctx->transforms.as<float>(), ctx->instances.as<SnkInstanceData>(), ctx->blas_of_instance.as<uint32_t>(),
-                         ctx->d_blas.as<SnkBlasInfo>(), ctx->blas_nodes.as<SnkNode8>(), ctx->valid_slots.as<uint32_t>(), n, st);
+                         ctx->d_blas.as<SnkBlasInfo>(), ctx->blas_nodes.as<SnkNode8>(), ctx->valid_slots.as<uint32_t>(), n, bs);
   BuildOutput out;
   out.nodes = ctx->tlas_nodes.as<SnkNode8>(); out.node_offset = 0; out.node_capacity = ctx->max_instances;
   out.tris = nullptr; out.leaf_ids = ctx->tlas_leaf_ids.as<uint32_t>(); out.leaf_remap = ctx->valid_slots.as<uint32_t>(); out.leaf_offset = 0;
-  const int built = launch_build(s, n, out, nullptr, nullptr, 0, 0, st);
+  const int built = launch_build(s, n, out, nullptr, nullptr, 0, 0, bs);
   REQUIRE(built >= 0, SNKPT_E_CUDA, "snkpt_build_tlas: the cooperative collapse kernel could not be launched");
   ctx->stats.kernel_launches += 2 + built;
-  cudaEventRecord(ctx->ev[7], st);
+  cudaEventRecord(ctx->ev[7], bs);
   ctx->build_timing_pending = true;  // ms_build_last is read from ev[6..7] by snkpt_get_stats
+  CK(cudaEventRecord(ctx->ev_tlas_built, bs));
+  CK(cudaStreamWaitEvent(st, ctx->ev_tlas_built, 0));  // the frame's primary rays, traversal launches and queries come after the rebuild
   CK(cudaGetLastError());
   return SNKPT_OK;
 }

@@ -153,6 +153,15 @@ struct SnkPt {
   // TLAS
   snk::DevBuf tlas_nodes, tlas_leaf_ids, inst_recs, valid_slots;  // inst_recs, valid_slots, inst_sphere: views into tlas_stage
   snk::DevBuf tlas_stage;  // instance records | valid slots | spheres, laid out like the pinned staging block: ONE upload per TLAS build
+  // The per-frame TLAS rebuild runs AHEAD of the frame before it (api.cu:snkpt_build_tlas): it writes the other of two copies of the
+  // TLAS storage on its own stream and only waits for the frames that read that copy (everything enqueued before the PREVIOUS
+  // rebuild) and for scene mutations, not for the frame in flight. *_alt hold the copy the in-flight frame reads.
+  snk::DevBuf tlas_nodes_alt, tlas_leaf_ids_alt, tlas_stage_alt;
+  cudaStream_t tlas_stream = nullptr;
+  cudaEvent_t ev_tlas_prev[2] = {nullptr, nullptr};  // recorded on the frame's stream at each rebuild call (alternating)
+  cudaEvent_t ev_tlas_built = nullptr, ev_tlas_sync = nullptr;
+  uint32_t tlas_builds = 0;
+  uint64_t scene_epoch = 1, tlas_epoch = 0;  // scene_epoch: bumped by every call that changes what the rebuild reads
   snk::DevBuf inst_sphere;  // float4 per instance slot: world-space bounding sphere (xyz, r^2), r^2 < 0 = none (traverse.cuh)
   uint32_t tlas_prims = 0;
   bool tlas_built = false;
