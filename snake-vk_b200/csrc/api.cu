@@ -197,33 +197,53 @@ SceneDev SnkPt::scene_dev() const {
 }
 
 // ---- per-pixel planes ----------------------------------------------------------------------
+// the G-buffer planes exist twice (context.h): index into px[] of the planes of copy 0; copy 1 lives in px_alt[] in the same order
+static const int GB_PLANES = 11;
+static const int GB_PLANE_IDX[GB_PLANES] = {0, 1, 2, 3, 4, 5, 8, 9, 10, 11, 26};
+static void set_gbuffer_planes(SnkPt* ctx) {
+  PixelPlanes& P = ctx->planes;
+  void* cur[GB_PLANES]; void* oth[GB_PLANES];
+  for (int g = 0; g < GB_PLANES; ++g) {
+    void* a = ctx->px[GB_PLANE_IDX[g]].p; void* b = ctx->px_alt[g].p;
+    cur[g] = ctx->gb_cur ? b : a; oth[g] = ctx->gb_cur ? a : b;
+  }
+  P.albedo = (char4*)cur[0]; P.normal = (ushort4*)cur[1]; P.depth = (float*)cur[2]; P.rma = (ushort4*)cur[3]; P.motion = (ushort2*)cur[4];
+  P.flags = (uint16_t*)cur[5]; P.prim = (uint32_t*)cur[6]; P.inst = (uint32_t*)cur[7]; P.hit_t = (float*)cur[8]; P.bary = (float2*)cur[9];
+  P.surf = (uint4*)cur[10];
+  P.prev_normal = (ushort4*)oth[1]; P.prev_depth = (float*)oth[2];  // what the previous snkpt_trace_primary wrote (GBufferPass.cpp:73-77)
+}
 static int alloc_pixels(SnkPt* ctx) {
   const size_t n = (size_t)ctx->W * ctx->H;
-  const size_t sizes[] = {4, 8, 4, 8, 4, 2, 8, 4, 4, 4, 4, 8, 16, 16, 16, 16, 16, 16, 16, 16, 16, 8, 8, 8, 4, 4, 32};
+  // planes 6, 7 were the previous frame's normals / depths: they are the OTHER copy of the G-buffer planes now (px_alt)
+  const size_t sizes[] = {4, 8, 4, 8, 4, 2, 0, 0, 4, 4, 4, 8, 16, 16, 16, 16, 16, 16, 16, 16, 16, 8, 8, 8, 4, 4, 32};
   const int count = (int)(sizeof(sizes) / sizeof(sizes[0]));
   for (int i = 0; i < count; ++i) {
     ctx->px[i].release();
+    if (!sizes[i]) continue;
     CK(ctx->px[i].reserve(sizes[i] * n, false, ctx->stream));
     CK(cudaMemsetAsync(ctx->px[i].p, 0, sizes[i] * n, ctx->stream));
   }
+  for (int g = 0; g < GB_PLANES; ++g) {
+    ctx->px_alt[g].release();
+    CK(ctx->px_alt[g].reserve(sizes[GB_PLANE_IDX[g]] * n, false, ctx->stream));
+    CK(cudaMemsetAsync(ctx->px_alt[g].p, 0, sizes[GB_PLANE_IDX[g]] * n, ctx->stream));
+  }
+  ctx->gb_cur = 0; ctx->gb_calls = 0;
+  set_gbuffer_planes(ctx);
   PixelPlanes& P = ctx->planes;
-  P.albedo = ctx->px[0].as<char4>(); P.normal = ctx->px[1].as<ushort4>(); P.depth = ctx->px[2].as<float>();
-  P.rma = ctx->px[3].as<ushort4>(); P.motion = ctx->px[4].as<ushort2>(); P.flags = ctx->px[5].as<uint16_t>();
-  P.prev_normal = ctx->px[6].as<ushort4>(); P.prev_depth = ctx->px[7].as<float>();
-  P.prim = ctx->px[8].as<uint32_t>(); P.inst = ctx->px[9].as<uint32_t>(); P.hit_t = ctx->px[10].as<float>();
-  P.bary = ctx->px[11].as<float2>();
   for (int h = 0; h < 2; ++h) for (int k = 0; k < 3; ++k) P.res[h][k] = ctx->px[12 + h * 3 + k].as<float4>();
   P.radiance = ctx->px[18].as<float4>(); P.direct = ctx->px[19].as<float4>(); P.accum = ctx->px[20].as<float4>();
   P.out16 = ctx->px[21].as<ushort4>();
   P.taa_hist[0] = ctx->px[22].as<ushort4>(); P.taa_hist[1] = ctx->px[23].as<ushort4>();
   P.taa_prev_vel[0] = ctx->px[24].as<ushort2>(); P.taa_prev_vel[1] = ctx->px[25].as<ushort2>();
-  P.surf = ctx->px[26].as<uint4>();
   // depth planes clear to 1.0 (GBufferPass.cpp:79); prim ids to "sky"; reservoirs to empty
   std::vector<float> ones(n, 1.0f);
   CK(cudaMemcpyAsync(P.depth, ones.data(), 4 * n, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemcpyAsync(P.prev_depth, ones.data(), 4 * n, cudaMemcpyHostToDevice, ctx->stream));
   CK(cudaMemsetAsync(P.prim, 0xFF, 4 * n, ctx->stream));
   CK(cudaMemsetAsync(P.inst, 0xFF, 4 * n, ctx->stream));
+  CK(cudaMemsetAsync(ctx->px_alt[6].p, 0xFF, 4 * n, ctx->stream));  // prim / inst of the other copy
+  CK(cudaMemsetAsync(ctx->px_alt[7].p, 0xFF, 4 * n, ctx->stream));
   std::vector<SnkPixelReservoir> empty(n);
   memset(empty.data(), 0, sizeof(SnkPixelReservoir) * n);
   for (auto& r : empty) { r.pl_idx = r.object_instance_idx = r.triangle_idx = SNKPT_INVALID_INDEX; }
@@ -374,7 +394,7 @@ int snkpt_create(const SnkPtConfig* cfg, SnkPt** out) {
     if (e2 == cudaSuccess) e2 = cudaMemsetAsync(ctx->materials.p, 0, sizeof(SnkMaterial) * ctx->max_materials, ctx->stream);
     if (e2 == cudaSuccess) e2 = ctx->dev_counters.reserve(1024, false, ctx->stream);
     if (e2 == cudaSuccess) e2 = cudaMemsetAsync(ctx->dev_counters.p, 0, 1024, ctx->stream);
-    if (e2 == cudaSuccess) e2 = ctx->trav_spill.reserve(2 * trace_spill_bytes(), false, ctx->stream);
+    if (e2 == cudaSuccess) e2 = ctx->trav_spill.reserve(3 * trace_spill_bytes(), false, ctx->stream);  // regions: path chain | ReSTIR chain | camera rays running ahead
     if (e2 == cudaSuccess) e2 = cudaStreamSynchronize(ctx->stream);
     if (e2 != cudaSuccess) { ctx->err = cudaGetErrorString(e2); rc = SNKPT_E_CUDA; }
   }
@@ -388,7 +408,8 @@ void snkpt_destroy(SnkPt* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->tlas_stream) { cudaStreamSynchronize(ctx->tlas_stream); cudaStreamDestroy(ctx->tlas_stream); ctx->tlas_stream = nullptr; }
-  for (cudaEvent_t* e : {&ctx->ev_tlas_prev[0], &ctx->ev_tlas_prev[1], &ctx->ev_tlas_built, &ctx->ev_tlas_sync}) if (*e) { cudaEventDestroy(*e); *e = nullptr; }
+  for (cudaEvent_t* e : {&ctx->ev_tlas_prev[0], &ctx->ev_tlas_prev[1], &ctx->ev_tlas_built, &ctx->ev_tlas_sync, &ctx->ev_gb_prev[0], &ctx->ev_gb_prev[1], &ctx->ev_gb_done, &ctx->ev_gb_sync, &ctx->ev_prev_free})
+    if (*e) { cudaEventDestroy(*e); *e = nullptr; }
   DevBuf* bufs[] = {&ctx->positions, &ctx->normals, &ctx->tangents, &ctx->uvs, &ctx->indices, &ctx->blas_nodes, &ctx->blas_tris,
                     &ctx->d_blas, &ctx->materials, &ctx->lights, &ctx->transforms, &ctx->prev_transforms, &ctx->normal_mats,
                     &ctx->det3, &ctx->instances, &ctx->blas_of_instance, &ctx->emissive_idx, &ctx->tlas_nodes, &ctx->tlas_leaf_ids,
@@ -398,6 +419,7 @@ void snkpt_destroy(SnkPt* ctx) {
   for (DevBuf* b : bufs) b->release();
   for (auto& b : ctx->wave) b.release();
   for (auto& b : ctx->px) b.release();
+  for (auto& b : ctx->px_alt) b.release();
   for (auto& r : ctx->blas_refit) refit_free(r);
   scratch_free(ctx->scratch_blas);
   scratch_free(ctx->scratch_tlas);
@@ -675,6 +697,7 @@ int snkpt_refit_blas(SnkPt* ctx, uint32_t blas_id, void* stream) {
 // ---- scene buffers -----------------------------------------------------------------------------------
 int snkpt_set_materials(SnkPt* ctx, const SnkMaterial* materials, uint32_t first, uint32_t count) {
   if (!ctx) return SNKPT_E_INVALID;
+  ++ctx->scene_epoch;
   REQUIRE(materials && (uint64_t)first + count <= ctx->max_materials, SNKPT_E_INVALID, "snkpt_set_materials: range");
   CK(cudaSetDevice(ctx->device));
   int rc = upload_async(ctx, ctx->materials.as<SnkMaterial>() + first, materials, sizeof(SnkMaterial) * count);
@@ -684,6 +707,7 @@ int snkpt_set_materials(SnkPt* ctx, const SnkMaterial* materials, uint32_t first
 
 int snkpt_set_texture(SnkPt* ctx, uint32_t tex_idx, uint32_t width, uint32_t height, const void* rgba8, uint32_t srgb) {
   if (!ctx) return SNKPT_E_INVALID;
+  ++ctx->scene_epoch;
   REQUIRE(tex_idx < 4096, SNKPT_E_INVALID, "snkpt_set_texture: index (the descriptor array has 4096 slots)");
   REQUIRE((width == 0 && height == 0) || (rgba8 && width <= 16384 && height <= 16384 && width && height), SNKPT_E_INVALID, "snkpt_set_texture: size / null texels");
   CK(cudaSetDevice(ctx->device));
@@ -718,6 +742,7 @@ int snkpt_set_texture(SnkPt* ctx, uint32_t tex_idx, uint32_t width, uint32_t hei
 
 int snkpt_set_lights(SnkPt* ctx, const void* light_data, size_t bytes) {
   if (!ctx) return SNKPT_E_INVALID;
+  ++ctx->scene_epoch;
   REQUIRE(light_data && bytes >= 112 && bytes <= sizeof(SnkLightData), SNKPT_E_INVALID, "snkpt_set_lights: size");
   const SnkLightData* L = (const SnkLightData*)light_data;
   REQUIRE(L->num_pointlights <= SNKPT_MAX_POINTLIGHTS && 112 + (size_t)L->num_pointlights * 48 <= bytes, SNKPT_E_INVALID,
@@ -824,6 +849,17 @@ int snkpt_set_instances(SnkPt* ctx, const SnkInstanceData* instances, const uint
   return SNKPT_OK;
 }
 
+// the stream (and its events) on which the per-frame TLAS rebuild and the camera rays run ahead of the frame in flight
+static int ensure_early_stream(SnkPt* ctx) {
+  if (ctx->tlas_stream) return SNKPT_OK;
+  int lo = 0, hi = 0;
+  cudaDeviceGetStreamPriorityRange(&lo, &hi);
+  CK(cudaStreamCreateWithPriority(&ctx->tlas_stream, cudaStreamNonBlocking, hi));
+  for (cudaEvent_t* e : {&ctx->ev_tlas_prev[0], &ctx->ev_tlas_prev[1], &ctx->ev_tlas_built, &ctx->ev_tlas_sync, &ctx->ev_gb_prev[0], &ctx->ev_gb_prev[1], &ctx->ev_gb_done, &ctx->ev_gb_sync, &ctx->ev_prev_free})
+    CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+  return SNKPT_OK;
+}
+
 int snkpt_build_tlas(SnkPt* ctx, void* stream) {
   if (!ctx) return SNKPT_E_INVALID;
   CK(cudaSetDevice(ctx->device));
@@ -868,12 +904,7 @@ int snkpt_build_tlas(SnkPt* ctx, void* stream) {
   // for the caller's stream as it stands, but not for the frame in flight; the caller's stream then waits for the rebuild.
   // A 40-us single-CTA kernel (+ its upload) no longer sits between two frames. SNKPT_TLAS_EARLY=0 restores the in-order rebuild.
   static const bool early_env = !(getenv("SNKPT_TLAS_EARLY") && getenv("SNKPT_TLAS_EARLY")[0] == '0');
-  if (!ctx->tlas_stream) {
-    int lo = 0, hi = 0;
-    cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    CK(cudaStreamCreateWithPriority(&ctx->tlas_stream, cudaStreamNonBlocking, hi));
-    for (cudaEvent_t* e : {&ctx->ev_tlas_prev[0], &ctx->ev_tlas_prev[1], &ctx->ev_tlas_built, &ctx->ev_tlas_sync}) CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-  }
+  { const int rc = ensure_early_stream(ctx); if (rc) return rc; }
   std::swap(ctx->tlas_nodes, ctx->tlas_nodes_alt);
   std::swap(ctx->tlas_leaf_ids, ctx->tlas_leaf_ids_alt);
   std::swap(ctx->tlas_stage, ctx->tlas_stage_alt);
@@ -998,13 +1029,37 @@ int snkpt_trace_primary(SnkPt* ctx, const float* jitter_xy, void* stream) {
   fill_frame_dims(ctx);
   ctx->fc.jx = jitter_xy ? jitter_xy[0] : 0.f; ctx->fc.jy = jitter_xy ? jitter_xy[1] : 0.f;
   prof_reset(ctx);
-  cudaEventRecord(ctx->ev[0], st);
+  // The camera rays write the copy of the G-buffer planes that the frame BEFORE the one in flight read, on the stream the TLAS rebuild
+  // runs on (after it): like the rebuild they wait for everything enqueued before the previous snkpt_trace_primary call — the last
+  // readers of that copy — and for scene changes, not for the frame in flight, whose last launches are latency-bound tails; the caller's
+  // stream then waits for them. SNKPT_PRIMARY_EARLY=0 keeps them in order with the caller's stream.
+  { const int rc = ensure_early_stream(ctx); if (rc) return rc; }
+  static const bool early_env = !(getenv("SNKPT_PRIMARY_EARLY") && getenv("SNKPT_PRIMARY_EARLY")[0] == '0');
+  ctx->gb_cur ^= 1u;
+  set_gbuffer_planes(ctx);
+  cudaStream_t es = ctx->tlas_stream;
+  const uint32_t k = ctx->gb_calls++;
+  const bool early = early_env && k >= 2 && ctx->gb_epoch == ctx->scene_epoch && !ctx->profiling && !ctx->group && ctx->prev_free == 1;
+  if (early) {
+    CK(cudaStreamWaitEvent(es, ctx->ev_gb_prev[(k + 1) & 1], 0));
+    if (ctx->prev_free_event) CK(cudaStreamWaitEvent(es, ctx->ev_prev_free, 0));  // the frame in flight is done with the copy written here
+  } else {
+    CK(cudaEventRecord(ctx->ev_gb_sync, st));
+    CK(cudaStreamWaitEvent(es, ctx->ev_gb_sync, 0));
+  }
+  ctx->gb_epoch = ctx->scene_epoch;
+  CK(cudaEventRecord(ctx->ev_gb_prev[k & 1], st));
+  cudaEventRecord(ctx->ev[0], es);
   FrameConsts fg = ctx->fc;
   widen_rows(ctx, ctx->halo_gbuffer, fg.row0, fg.row1);
-  const int rec = prof_begin(ctx, "primary", (uint64_t)ctx->W * (fg.row1 - fg.row0), false, false, st);
-  ctx->stats.kernel_launches += launch_primary(ctx->trace_scene(), ctx->scene_dev(), fg, ctx->planes, ctx->dev_counters.as<uint32_t>() + 200, ctx->primary_parity++, st);
-  prof_end(ctx, rec, st);
-  cudaEventRecord(ctx->ev[1], st);
+  const int rec = prof_begin(ctx, "primary", (uint64_t)ctx->W * (fg.row1 - fg.row0), false, false, es);
+  TraceScene S = ctx->trace_scene();
+  S.spill += 2 * (trace_spill_bytes() / sizeof(uint2));  // a spill region of their own: traversal launches of the frame in flight use the other two
+  ctx->stats.kernel_launches += launch_primary(S, ctx->scene_dev(), fg, ctx->planes, ctx->dev_counters.as<uint32_t>() + 200, ctx->primary_parity++, es);
+  prof_end(ctx, rec, es);
+  cudaEventRecord(ctx->ev[1], es);
+  CK(cudaEventRecord(ctx->ev_gb_done, es));
+  CK(cudaStreamWaitEvent(st, ctx->ev_gb_done, 0));
   CK(cudaGetLastError());
   ctx->stats.rays_primary = (uint64_t)ctx->W * (fg.row1 - fg.row0);
   ctx->stats.total_rays_primary += ctx->stats.rays_primary;
@@ -1036,6 +1091,8 @@ int snkpt_render(SnkPt* ctx, const SnkRtSettings* settings, void* stream) {
     REQUIRE(settings->neighbour_radius >= 0.0f && (uint32_t)ceilf(settings->neighbour_radius) + 1u <= group_gbuffer_halo(ctx), SNKPT_E_INVALID,
             "snkpt_render: neighbour_radius exceeds the rows the group exchanges");
   }
+  { const int erc = ensure_early_stream(ctx); if (erc) return erc; }
+  ctx->prev_free = 0; ctx->prev_free_event = false;  // launch_northstar_frame says when the previous-frame normals / depths are no longer read
   int rc = settings->mode == SNKPT_MODE_REFERENCE ? launch_reference_frame(ctx, *settings, st) : launch_northstar_frame(ctx, *settings, st);
   if (rc < 0) return rc;
   CK(cudaGetLastError());

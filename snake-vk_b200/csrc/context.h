@@ -190,6 +190,19 @@ struct SnkPt {
 
   // per pixel
   snk::DevBuf px[32];
+  // second copy of the G-buffer planes (albedo, normal, depth, rma, motion, flags, prim, inst, hit_t, bary, surf): snkpt_trace_primary
+  // alternates between the two, so the previous frame's normals / depths are simply the other copy (no blit), and the camera rays of
+  // frame f+1 may run under the tail of frame f (api.cu). gb_cur = the copy the last snkpt_trace_primary wrote.
+  snk::DevBuf px_alt[11];
+  uint32_t gb_cur = 0, gb_calls = 0;
+  uint64_t gb_epoch = 0;
+  cudaEvent_t ev_gb_prev[2] = {nullptr, nullptr}, ev_gb_done = nullptr, ev_gb_sync = nullptr;
+  // the frame in flight reads the OTHER copy's normals / depths (its "previous frame") in its temporal-reuse stage: camera rays that run
+  // ahead overwrite that copy, so they also wait for ev_prev_free (recorded after that stage); prev_free = 0: no such event for the last
+  // render (reference mode reads the previous normals until its last pass) -> the camera rays stay in order
+  cudaEvent_t ev_prev_free = nullptr;
+  int prev_free = 1;  // 1 before any render: nobody is reading
+  bool prev_free_event = false;
   snk::PixelPlanes planes{};
   bool history_valid = false;
   uint32_t history_mode = 0;    // estimator that wrote the reservoir history (the two modes' reservoirs are not interchangeable)

@@ -88,10 +88,7 @@ __global__ void __launch_bounds__(128, PRIMARY_CTAS_PER_SM) k_primary(TraceScene
   const uint32_t y = fc.row0 + (tile / tiles_x) * 8 + (w >> 1) * 4 + (l >> 3);
   const bool in_range = x < fc.W && y < fc.row1;
   const size_t px = in_range ? (size_t)y * fc.W + x : 0;
-  if (in_range) {
-  P.prev_normal[px] = P.normal[px];
-  P.prev_depth[px] = P.depth[px];
-  }
+  // (the previous frame's normals / depths are the other copy of the G-buffer planes: P.prev_normal / P.prev_depth point there)
 
   const float u = (((float)x + 0.5f) + fc.jx) / (float)fc.W, v = (((float)y + 0.5f) + fc.jy) / (float)fc.H;
   const vec3 cam = v3(fc.cam_pos[0], fc.cam_pos[1], fc.cam_pos[2]);
@@ -127,10 +124,6 @@ __global__ void __launch_bounds__(128, SNK_PACKET_CTAS) k_primary_packet(TraceSc
     const uint32_t y = fc.row0 + (blk / tiles_x) * 8 + (q >> 1) * 4 + (l >> 3);
     const bool in_range = x < fc.W && y < fc.row1;
     const size_t px = in_range ? (size_t)y * fc.W + x : 0;
-    if (in_range) {
-      P.prev_normal[px] = P.normal[px];
-      P.prev_depth[px] = P.depth[px];
-    }
     const float u = (((float)x + 0.5f) + fc.jx) / (float)fc.W, v = (((float)y + 0.5f) + fc.jy) / (float)fc.H;
     const vec3 cam = v3(fc.cam_pos[0], fc.cam_pos[1], fc.cam_pos[2]);
     const vec3 far = world_pos_from_depth(fc.ivp, 1.0f, u, v);

@@ -432,6 +432,7 @@ int launch_northstar_frame(SnkPt* ctx, const SnkRtSettings& s, cudaStream_t st) 
     launches += restir_ns_resolve(ctx, sa);
     if (overlap) cudaEventRecord(ctx->ev_join, sa);
   };
+  if (!nee_from) ctx->prev_free = 1;  // without the ReSTIR stages nothing of this frame reads the previous normals / depths
   if (nee_from && overlap) { cudaEventRecord(ctx->ev_fork, st); cudaStreamWaitEvent(sa, ctx->ev_fork, 0); cudaStreamWaitEvent(sb, ctx->ev_fork, 0); }
   if (!staggered) { chain_a(); if (rcA < 0) return rcA; }
   int q = 2;

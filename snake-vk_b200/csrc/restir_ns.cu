@@ -684,6 +684,8 @@ int restir_ns_reuse(SnkPt* ctx, const SnkRtSettings& s, const RefQueue& q, cudaS
   int rec = prof_begin(ctx, "rs_temporal", L.npix1, false, false, st);
   if (D.num_emissive) k_rs_temporal<true><<<(stage_threads(L.f1.W, L.f1.row1 - L.f1.row0) + 127) / 128, 128, 0, st>>>(D, L.f1, ctx->planes, L.rp, L.B, L.npix1);
   else k_rs_temporal<false><<<(stage_threads(L.f1.W, L.f1.row1 - L.f1.row0) + 127) / 128, 128, 0, st>>>(D, L.f1, ctx->planes, L.rp, L.B, L.npix1);
+  // the last reader of the previous frame's normals / depths (the other copy of the G-buffer planes): the next frame's camera rays may overwrite them
+  if (ctx->ev_prev_free) { cudaEventRecord(ctx->ev_prev_free, st); ctx->prev_free = 1; ctx->prev_free_event = true; }
   prof_end(ctx, rec, st);
   cudaEventRecord(ctx->ev[3], st);
   // row-band group: the neighbours' temporal reservoirs of the rows spatial reuse can reach arrive here ...
