@@ -910,7 +910,7 @@ int snkpt_build_tlas(SnkPt* ctx, void* stream) {
   std::swap(ctx->tlas_stage, ctx->tlas_stage_alt);
   cudaStream_t bs = ctx->tlas_stream;
   const uint32_t k = ctx->tlas_builds++;
-  const bool early = early_env && k >= 2 && ctx->tlas_epoch == ctx->scene_epoch && !ctx->profiling;
+  const bool early = early_env && k >= 2 && ctx->tlas_epoch == ctx->scene_epoch && (ctx->profiling == 0 || ctx->profiling == 3);
   if (early) {
     CK(cudaStreamWaitEvent(bs, ctx->ev_tlas_prev[(k + 1) & 1], 0));  // recorded at the previous rebuild call: frames <= f-1 are behind it
   } else {
@@ -1039,7 +1039,7 @@ int snkpt_trace_primary(SnkPt* ctx, const float* jitter_xy, void* stream) {
   set_gbuffer_planes(ctx);
   cudaStream_t es = ctx->tlas_stream;
   const uint32_t k = ctx->gb_calls++;
-  const bool early = early_env && k >= 2 && ctx->gb_epoch == ctx->scene_epoch && !ctx->profiling && !ctx->group && ctx->prev_free == 1;
+  const bool early = early_env && k >= 2 && ctx->gb_epoch == ctx->scene_epoch && (ctx->profiling == 0 || ctx->profiling == 3) && !ctx->group && ctx->prev_free == 1;
   if (early) {
     CK(cudaStreamWaitEvent(es, ctx->ev_gb_prev[(k + 1) & 1], 0));
     if (ctx->prev_free_event) CK(cudaStreamWaitEvent(es, ctx->ev_prev_free, 0));  // the frame in flight is done with the copy written here
