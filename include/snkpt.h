@@ -352,7 +352,12 @@ SNKPT_API int snkpt_set_instances(SnkPt* ctx, const SnkInstanceData* instances,
                                   const uint32_t* blas_of_instance, uint32_t count,
                                   const uint32_t* emissive_idx, uint32_t num_emissive);
 /* TlasSystem::BuildTlas (TlasSystem.cpp:27-49) → TLAS::BuildFromInstances
- * (TLAS.cpp:10-87): full rebuild from the current instances + transforms */
+ * (TLAS.cpp:10-87): full rebuild from the current instances + transforms.
+ * Stream semantics (also snkpt_trace_primary): work enqueued on `stream` AFTER this call sees the rebuilt TLAS, as with any
+ * stream-ordered call. The rebuild itself may start EARLIER than the work enqueued before it: when nothing it reads was changed
+ * since the previous rebuild, it runs on an internal stream, into a second copy of the TLAS storage, under the tail of the frame in
+ * flight (the camera rays likewise, into a second copy of the G-buffer planes). Results do not depend on it; SNKPT_TLAS_EARLY=0 /
+ * SNKPT_PRIMARY_EARLY=0 in the environment keep both strictly in order. */
 SNKPT_API int snkpt_build_tlas(SnkPt* ctx, void* stream);
 
 /* ---- per frame ------------------------------------------------------------------ */
