@@ -76,3 +76,47 @@ def test_mutations_between_frames_without_host_sync(snk, mode):
     assert a_res.tobytes() == b_res.tobytes()
     for f, (x, y) in enumerate(zip(a_hits, b_hits)):
         assert x.tobytes() == y.tobytes(), f"query after frame {f}: {(x != y).sum()} hits differ"
+
+
+@pytest.mark.parametrize("mode", ["reference", "northstar"])
+def test_frames_running_ahead_match_synchronised_run(snk, mode):
+    """The TLAS rebuild and the camera rays of frame f+1 run ahead of frame f on an internal stream (second copies of the TLAS storage
+    and of the G-buffer planes) when nothing they read changed since the previous frame; a scene change puts them back in order for
+    one frame. Nine frames enqueued without any host synchronisation — unchanged scene, a moved instance before frames 4 and 5,
+    unchanged again — must leave the same accumulated image, radiance, reservoirs and previous-frame planes as a run that
+    synchronises after every call (where running ahead cannot overlap anything)."""
+    torch = pytest.importorskip("torch")
+    sc = snk.scenes.small_test_scene(640, 360)  # large enough for the GPU to fall behind the host: frames really are in flight
+    s_frame = torch.cuda.Stream()
+    gpu_mode = snk.api.MODE_NORTHSTAR if mode == "northstar" else snk.api.MODE_REFERENCE
+    st = snk.api.default_settings(mode=gpu_mode)
+
+    def run(sync_everything):
+        pt = snk.PathTracer(sc.width, sc.height)
+        flat = pt.upload_scene(sc)
+        tr = flat["transforms"].copy()
+        prev = None
+        for f in range(9):
+            if f in (4, 5):  # move the last instance: the rebuild and the camera rays of this frame must see the new transform
+                old = tr.copy()
+                tr[-1, 13] += np.float32(0.15)
+                pt.set_transforms(tr, old)
+            ubo = sc.ubo(f, cam_pos=np.asarray(sc.camera.pos, np.float32) + np.float32(0.04 * f))
+            p = ubo if prev is None else prev
+            prev = ubo
+            pt.build_tlas(s_frame.cuda_stream)
+            pt.set_frame(ubo, p)
+            pt.trace_primary(stream=s_frame.cuda_stream)
+            pt.render(st, s_frame.cuda_stream)
+            pt.accumulate(reset=(f == 0), stream=s_frame.cuda_stream)
+            if sync_everything:
+                pt.synchronize(); torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        out = [pt.read_aux(k).copy() for k in ("accum", "radiance", "reservoirs_final", "reservoirs_temporal", "prev_normal", "prev_depth", "normal", "prim")]
+        assert int(pt.stats()["stack_overflows"]) == 0
+        pt.close()
+        return out
+
+    a, b = run(False), run(True)
+    for name, x, y in zip(("accum", "radiance", "reservoirs_final", "reservoirs_temporal", "prev_normal", "prev_depth", "normal", "prim"), a, b):
+        assert x.tobytes() == y.tobytes(), f"{mode}: plane '{name}' differs between the run-ahead and the synchronised run"
